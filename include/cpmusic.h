@@ -1,0 +1,249 @@
+/* cpmusic.h — C-ABI of libcpmusic.so: sm_100a kernels for the compound-word (CP)
+ * causal-linear-attention agent (the hot path of
+ * daniel05155/Reinforcement-Learning-in-Music-Generation).
+ *
+ * This is the drop-in boundary.  The reference reaches this
+ * arithmetic through pytorch-fast-transformers 0.4.0's pybind11 extension
+ * (`causal_dot_product(Q,K,V,product)` / `causal_dot_product_backward(...)`, fp32
+ * (N,H,L,E) contiguous, outputs pre-allocated by Python) and through ATen ops
+ * issued from the model files cited next to each entry point.
+ *
+ * Conventions (all entry points):
+ *   - plain pointers and sizes only; every pointer is a DEVICE pointer unless the
+ *     parameter name ends in `_host`;
+ *   - the callee never allocates, never synchronises, never throws; the caller
+ *     owns every buffer including workspaces;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream);
+ *   - returns 0 on success or a negative CPM_ERR_* code; `cpm_last_error_string()`
+ *     gives a thread-local human-readable message for the last failure;
+ *   - `dtype` selects the storage type of activations (CPM_F32 | CPM_BF16);
+ *     accumulation, normalisers, statistics and recurrent state are always fp32;
+ *   - token indices are int64 (the reference passes `.long()` tensors).
+ */
+#ifndef CPMUSIC_H_
+#define CPMUSIC_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define CPM_VERSION 100 /* 0.1.0 */
+
+#define CPM_F32 0
+#define CPM_BF16 1
+
+#define CPM_OK 0
+#define CPM_ERR_BAD_SHAPE (-1)    /* unsupported / inconsistent dimension */
+#define CPM_ERR_BAD_ALIGN (-2)    /* pointer or stride not 16-byte aligned */
+#define CPM_ERR_BAD_DTYPE (-3)
+#define CPM_ERR_NULL (-4)         /* required pointer is NULL */
+#define CPM_ERR_WORKSPACE (-5)    /* workspace too small */
+#define CPM_ERR_CUDA (-6)         /* launch failed; see cpm_last_error_string() */
+#define CPM_ERR_UNSUPPORTED (-7)  /* e.g. tcgen05 path requested for fp32 */
+
+#define CPM_MAX_ATTR 8 /* CP attributes per compound word (reference: 6; upstream CP: 7) */
+
+int cpm_version(void);
+const char *cpm_last_error_string(void);
+const char *cpm_error_name(int code);
+/* Name of the kernel implementation the last cpm_linattn_fwd/bwd call dispatched to
+ * ("tcgen05" | "simt"); lets tests assert which path ran. */
+const char *cpm_linattn_last_impl(void);
+
+/* ------------------------------------------------------------------------------------------
+ * A1/A2 — causal linear attention, parallel (teacher-forced) form.
+ * Replaces ft `CausalLinearAttention.forward` + `causal_product_cuda` fwd/bwd, i.e. the
+ * encoder built at dqn_policy/model.py:128-137, agent_pretrain.py:244-253,
+ * ppo_policy/model.py:129-138,313-321:
+ *     Qf = elu(q)+1, Kf = elu(k)+1
+ *     den[n,l,h] = Qf[n,l,h,:] . sum_{j<=l} Kf[n,j,h,:] + eps
+ *     out[n,l,h,:] = ( sum_{j<=l} (Qf[n,l,h,:].Kf[n,j,h,:]) v[n,j,h,:] ) / den[n,l,h]
+ * Layout: q,k,v are (N,L,H,E) with E contiguous, head h at element offset h*E and token
+ * stride `ld_qkv` elements (so the three can be column slices of one fused QKV GEMM output);
+ * out / gout are (N,L,H,M) with token stride `ld_o`; gq,gk,gv have token stride `ld_g`.
+ * den is (N,L,H) fp32, written by fwd and read by bwd.  E = M = 64 (the reference) only.
+ * impl: 0 = auto (tcgen05 when dtype==BF16 and L%128==0, else simt), 1 = simt, 2 = tcgen05.
+ * Workspace: cpm_linattn_workspace_bytes(N,L,H) bytes (segment states).
+ * ------------------------------------------------------------------------------------------ */
+int64_t cpm_linattn_workspace_bytes(int N, int L, int H);
+int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, float *den,
+                    int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
+                    int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes,
+                    void *stream);
+int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out, const float *den,
+                    const void *gout, void *gq, void *gk, void *gv,
+                    int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o, int64_t ld_g,
+                    int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes,
+                    void *stream);
+
+/* B1 — recurrent one-token step.  Replaces ft `RecurrentLinearAttention.forward`
+ * (builder at dqn_policy/model.py:141-150; call at dqn_policy/model.py:237,
+ * testing-no-type-cp.py:154,167):
+ *     Z += Kf ; S += Kf (x) v ; out = Qf^T S / (Qf.Z + eps)
+ * q,k,v: (N,H,E) rows with row stride ld_qkv; out (N,H,M) row stride ld_o;
+ * S (N,H,E,M) fp32 and Z (N,H,E) fp32 are updated IN PLACE (as ft does under no_grad). */
+int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, float *Z, void *out,
+                     int N, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
+                     int dtype, float eps, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * C1 — CP embedding gather + sqrt(emb) scale + concat.  Replaces `Embeddings.forward` x6 and
+ * `torch.cat` (agent_pretrain.py:185-192,320-335; dqn_policy/model.py:206-221).
+ *   idx (T,n_attr) int64; tables_host[a] -> fp32 table (n_tokens_host[a], emb_sizes_host[a]);
+ *   out (T, sum(emb)) dtype.  Out-of-range indices write zeros and set *err_flag (if non-NULL).
+ * bwd accumulates (+=) into fp32 gtables_host[a] (caller zeroes). emb sizes must be /8.
+ * ------------------------------------------------------------------------------------------ */
+int cpm_embed_fwd(const int64_t *idx, const float *const *tables_host, const int *n_tokens_host,
+                  const int *emb_sizes_host, int n_attr, int64_t T, void *out, int dtype,
+                  int *err_flag, void *stream);
+int cpm_embed_bwd(const int64_t *idx, const void *gout, float *const *gtables_host,
+                  const int *n_tokens_host, const int *emb_sizes_host, int n_attr, int64_t T,
+                  int dtype, void *stream);
+
+/* Positional encoding add + dropout: y[r,:] = drop(x[r,:] + pe[pos(r),:]).
+ * Replaces `PositionalEncoding.forward` (agent_pretrain.py:208-210).  pe fp32 (max_len,d).
+ * pos(r) = pos_offset + (r % L) when pos_dev==NULL, else pos_dev[0] + (r % L) (device-side
+ * step counter for graph-captured rollouts; the reference's recurrent mode always adds
+ * position 0 — SURVEY D8 — which is pos_offset=0, L=1). */
+int cpm_add_pe(const void *x, const float *pe, void *y, int64_t rows, int L, int d,
+               int pos_offset, const int32_t *pos_dev, int max_len, float p_drop, uint64_t seed,
+               uint64_t rng_offset, int dtype, void *stream);
+
+/* Inverted dropout with a counter-based (Philox4x32-10) mask: y = x*mask/(1-p); the mask
+ * depends only on (seed, rng_offset, element index), so applying it to a gradient
+ * reproduces the forward mask without storing it. */
+int cpm_dropout(const void *x, void *y, int64_t n, float p_drop, uint64_t seed,
+                uint64_t rng_offset, int dtype, void *stream);
+
+/* C2 — fused residual + dropout + LayerNorm (affine, eps 1e-5 in the reference).  Replaces
+ * `x = norm(x + dropout(y))` of ft's post-norm TransformerEncoderLayer and the final norm
+ * (K6):
+ *     s = x + drop(res)   (res may be NULL: plain LayerNorm)
+ *     y = (s-mean)*rstd*gamma + beta
+ * Saves s (dtype, may be NULL for inference), mean, rstd (fp32, may be NULL).  d % 8 == 0,
+ * d <= 8192.  bwd: given gy, s, mean, rstd -> gs (grad wrt x), gres (grad wrt res through the
+ * dropout mask; may alias NULL when p_drop==0: then gres==gs), and fp32 partial sums for
+ * dgamma/dbeta in `partials` (cpm_ln_partials_rows() x 2 x d), reduced into dgamma/dbeta (+=).
+ */
+int cpm_ln_residual_fwd(const void *x, const void *res, const float *gamma, const float *beta,
+                        void *y, void *s_out, float *mean, float *rstd, int64_t rows, int d,
+                        float eps, float p_drop, uint64_t seed, uint64_t rng_offset, int dtype,
+                        void *stream);
+int cpm_ln_partials_rows(void);
+int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const float *rstd,
+                        const float *gamma, void *gs, void *gres, float *dgamma, float *dbeta,
+                        float *partials, int64_t rows, int d, float p_drop, uint64_t seed,
+                        uint64_t rng_offset, int dtype, void *stream);
+
+/* bias + exact-erf GELU + dropout (ft activation='gelu' => F.gelu; K6):
+ *     y = drop(gelu(x + bias))   (bias fp32 (d) or NULL)
+ * bwd: gx = gy * mask/(1-p) * gelu'(x + bias). */
+int cpm_gelu_fwd(const void *x, const float *bias, void *y, int64_t rows, int d, float p_drop,
+                 uint64_t seed, uint64_t rng_offset, int dtype, void *stream);
+int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, int64_t rows, int d,
+                 float p_drop, uint64_t seed, uint64_t rng_offset, int dtype, void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * C3 — per-attribute decode over concatenated head logits.  Replaces
+ * `forward_output_sampling` + host numpy `sampling/softmax_with_temperature/nucleus/
+ * weighted_sampling` (dqn_policy/model.py:19-55,259-298) and the softmax/argmax/log read-out of
+ * `choose_action` (ppo_train.py:259-267; IRL_dqn_train.py:244-250).
+ *   logits (rows, ld_logits) ; attribute a occupies columns [seg_host[a], seg_host[a+1]).
+ *   mode 0: greedy argmax (first maximal index).  mode 1: temperature softmax, optional nucleus
+ *   (top_p_host[a] in (0,1); <=0 or >=1 disables), inverse-CDF draw with the Philox uniform of
+ *   (seed, seq_id = seq_base + row, step = *step_dev or step, attribute a).
+ *   tokens (rows,n_attr) int64; logp (rows,n_attr) fp32 = log softmax_{T=1}(logits)[token]
+ *   (may be NULL); entropy (rows,n_attr) fp32 of the T=1 softmax (may be NULL).
+ * Segment width <= 1024.
+ * ------------------------------------------------------------------------------------------ */
+int cpm_heads_sample(const void *logits, int64_t rows, int64_t ld_logits, const int *seg_host,
+                     int n_attr, const float *temperature_host, const float *top_p_host, int mode,
+                     uint64_t seed, int64_t seq_base, int step, const int32_t *step_dev,
+                     int64_t *tokens, float *logp, float *entropy, int dtype, void *stream);
+
+/* log-prob / entropy of GIVEN tokens under the T=1 softmax of each segment (PPO update).
+ * Also the backward: dlogits += glogp*(onehot - p) + gent*(-p*(log p + H)) when dlogits!=NULL is
+ * done by cpm_heads_logp_bwd. */
+int cpm_heads_logp(const void *logits, int64_t rows, int64_t ld_logits, const int *seg_host,
+                   int n_attr, const int64_t *tokens, float *logp, float *entropy, int dtype,
+                   void *stream);
+int cpm_heads_logp_bwd(const void *logits, int64_t rows, int64_t ld_logits, const int *seg_host,
+                       int n_attr, const int64_t *tokens, const float *glogp, const float *gentropy,
+                       void *dlogits, int dtype, void *stream);
+
+/* C4 — masked mean cross-entropy per attribute.  Replaces `compute_loss` x6 inside
+ * `train_step` (agent_pretrain.py:279-311): loss_a = sum_t mask_t*CE(logits_t[seg a], tgt_ta)
+ * / sum_t mask_t.
+ *   fwd: loss_num[a] += numerator (fp32, caller zeroes), mask_sum[0] += sum(mask), lse (T,n_attr).
+ *   bwd: dlogits[t,seg a] = gscale[a] * mask_t / denom[0] * (softmax - onehot)   (device scalars
+ *   gscale (n_attr) and denom (1): the caller may all-reduce denom across ranks first). */
+int cpm_masked_ce_fwd(const void *logits, int64_t T, int64_t ld_logits, const int *seg_host,
+                      int n_attr, const int64_t *targets, const float *mask, float *loss_num,
+                      float *mask_sum, float *lse, int dtype, void *stream);
+int cpm_masked_ce_bwd(const void *logits, int64_t T, int64_t ld_logits, const int *seg_host,
+                      int n_attr, const int64_t *targets, const float *mask, const float *lse,
+                      const float *gscale, const float *denom, void *dlogits, int dtype,
+                      void *stream);
+
+/* ------------------------------------------------------------------------------------------
+ * D1 — returns / advantage scans (fp32, (B,T) row-major; one warp per trajectory).
+ *   mode CPM_RET_COMPAT : reference `calculate_returns` (ppo_train.py:348-353):
+ *        R_i = r_i + gamma*R_{i-1} accumulated forward, stored reversed: ret[t] = R_{T-1-t}.
+ *   mode CPM_RET_TOGO   : ret[t] = r_t + gamma*(1-done_t)*ret[t+1].
+ *   mode CPM_RET_GAE    : GAE(lambda): adv[t] = delta_t + gamma*lam*(1-done_t)*adv[t+1],
+ *        delta_t = r_t + gamma*(1-done_t)*V_{t+1} - V_t (V_T = last_value); ret = adv + V.
+ * values/dones/last_value/adv may be NULL where the mode does not use them.
+ * ------------------------------------------------------------------------------------------ */
+#define CPM_RET_COMPAT 0
+#define CPM_RET_TOGO 1
+#define CPM_RET_GAE 2
+int cpm_returns_scan(const float *rewards, const float *values, const float *dones,
+                     const float *last_value, float *ret, float *adv, int B, int T, float gamma,
+                     float lam, int mode, void *stream);
+/* moments of (x - sub) (sub may be NULL): out3 += {count, sum, sum of squares} in fp64. */
+int cpm_moments(const float *x, const float *sub, int64_t n, double *out3, void *stream);
+/* out = ((x - sub) - mean)/std with mean/std from moments3 (device; may have been all-reduced);
+ * unbiased!=0 uses the n-1 denominator like torch.std (ppo_train.py:356,362). */
+int cpm_zscore(const float *x, const float *sub, float *out, int64_t n, const double *moments3,
+               int unbiased, float eps, void *stream);
+
+/* D2 — PPO losses, forward + backward in one launch (grad of the scalar loss w.r.t. inputs,
+ * scaled by grad_scale).
+ *   mode CPM_PPO_COMPAT (ppo_train.py:388-396): new_logp (C) broadcast over T rows,
+ *        old_logp (T,C), adv (T):  loss = -mean_{t,c} min(0.2*adv_t, clamp(exp(new_c-old_tc),
+ *        1-clip,1+clip)*adv_t);  out[0]=loss;  dnew (C).
+ *   mode CPM_PPO_STANDARD: elementwise n = T*C, new/old/adv/entropy (n), value/ret (nv):
+ *        loss = -mean(min(r*A, clamp(r)*A)) + vf_coef*mse(value,ret) - ent_coef*mean(entropy);
+ *        out[0..3] = {loss, policy, value, entropy}; dnew (n), dvalue (nv), dentropy (n).
+ * `out` must be zeroed by the caller. */
+#define CPM_PPO_COMPAT 0
+#define CPM_PPO_STANDARD 1
+int cpm_ppo_loss_fwd_bwd(const float *new_logp, const float *old_logp, const float *adv,
+                         const float *entropy, const float *value, const float *ret,
+                         float *out, float *dnew, float *dentropy, float *dvalue,
+                         int64_t T, int64_t C, int64_t nv, float clip, float vf_coef,
+                         float ent_coef, float grad_scale, int mode, void *stream);
+
+/* D3 — DQN TD target + MSE, forward + backward (IRL_dqn_train.py:285-330).
+ *   q_logits, next_logits: (B,L,ld) with attribute segments seg_host; action (B,A,n_attr) int64;
+ *   reward, done (B) fp32.  target[b,k,a] = r_b + gamma*(1-done_b)*top_k-th( max_vocab
+ *   next[b,:,seg a] ) (descending over the L positions, A largest).
+ *   mode CPM_TD_COMPAT: Q(s,a)[b,k] = q_logits[0, b, seg a + action[b,k,a]] (the reference's
+ *        gather quirk; requires B <= L).  mode CPM_TD_STANDARD: Q[b,k] = q_logits[b, L-1-k, ...]
+ *        and the target is max_vocab next[b, L-1-k, seg a] (no top-k).
+ *   out[0] += mean over attributes of MSE; dq (B,L,ld) is zero-filled then receives
+ *   grad_scale * dloss/dq_logits (same dtype as logits).  targets_out (B,A,n_attr) fp32 optional. */
+#define CPM_TD_COMPAT 0
+#define CPM_TD_STANDARD 1
+int cpm_dqn_td_fwd_bwd(const void *q_logits, const void *next_logits, const int64_t *action,
+                       const float *reward, const float *done, float *out, void *dq,
+                       float *targets_out, int B, int L, int64_t ld, const int *seg_host,
+                       int n_attr, int A, float gamma, float grad_scale, int mode, int dtype,
+                       void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CPMUSIC_H_ */

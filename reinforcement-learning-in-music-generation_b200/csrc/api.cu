@@ -1,0 +1,182 @@
+// C-ABI entry points: version / errors / linear-attention dispatch / recurrent step.
+#include "cpm_common.cuh"
+#include "linattn_plan.h"
+
+namespace cpm {
+thread_local char g_err[512] = "";
+thread_local const char *g_linattn_impl = "none";
+
+int fail(int code, const char *fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+namespace {
+// ------------------------------------------------------------------------------------------
+// B1: recurrent step. One CTA per (sequence, head); 256 threads; thread t owns row e = t/4 and
+// the 16 columns m = 16*(t%4)..+16 of the 64x64 fp32 state (4 x 128-bit loads in flight, fully
+// coalesced: a warp covers 8 consecutive rows = 2 KB).  out_m = sum_e Qf_e S_em / (Qf.Z + eps)
+// is reduced with warp shuffles (over the 8 rows of a warp) and one shared-memory pass.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__ q, const T *__restrict__ k,
+                                                           const T *__restrict__ v, float *__restrict__ S,
+                                                           float *__restrict__ Z, T *__restrict__ out, int H,
+                                                           int64_t ld_qkv, int64_t ld_o, float eps) {
+    __shared__ float sq[64], sk[64], sv[64];
+    __shared__ float part[8][64];
+    __shared__ float sden;
+    const int nh = blockIdx.x, n = nh / H, h = nh % H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t qoff = (int64_t)n * ld_qkv + h * 64;
+    if (tid < 64) sq[tid] = phi(to_f(q[qoff + tid]));
+    else if (tid < 128) sk[tid - 64] = phi(to_f(k[qoff + tid - 64]));
+    else if (tid < 192) sv[tid - 128] = to_f(v[qoff + tid - 128]);
+    __syncthreads();
+    if (warp == 7) {   // normaliser: Z += Kf ; den = Qf.Z + eps   (2 elements per lane)
+        float *z = Z + (int64_t)nh * 64;
+        float z0 = z[lane] + sk[lane], z1 = z[lane + 32] + sk[lane + 32];
+        z[lane] = z0; z[lane + 32] = z1;
+        float d = warp_sum(sq[lane] * z0 + sq[lane + 32] * z1);
+        if (lane == 0) sden = d + eps;
+    }
+    const int e = tid >> 2, m0 = (tid & 3) * 16;
+    float4 *srow = reinterpret_cast<float4 *>(S + (int64_t)nh * 4096 + e * 64 + m0);
+    float4 s[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) s[i] = srow[i];
+    const float ke = sk[e], qe = sq[e];
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s[i].x = fmaf(ke, sv[m0 + 4 * i + 0], s[i].x); s[i].y = fmaf(ke, sv[m0 + 4 * i + 1], s[i].y);
+        s[i].z = fmaf(ke, sv[m0 + 4 * i + 2], s[i].z); s[i].w = fmaf(ke, sv[m0 + 4 * i + 3], s[i].w);
+        srow[i] = s[i];
+        acc[4 * i + 0] = qe * s[i].x; acc[4 * i + 1] = qe * s[i].y;
+        acc[4 * i + 2] = qe * s[i].z; acc[4 * i + 3] = qe * s[i].w;
+    }
+    // reduce over the 8 rows held by this warp (lanes with equal lane%4)
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part[warp][lane * 16 + i] = acc[i];
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float o = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) o += part[w][tid];
+        out[(int64_t)n * ld_o + h * 64 + tid] = from_f<T>(o / sden);
+    }
+}
+}  // namespace
+}  // namespace cpm
+
+using namespace cpm;
+
+extern "C" {
+
+int cpm_version(void) { return CPM_VERSION; }
+const char *cpm_last_error_string(void) { return g_err; }
+const char *cpm_linattn_last_impl(void) { return g_linattn_impl; }
+const char *cpm_error_name(int code) {
+    switch (code) {
+        case CPM_OK: return "CPM_OK";
+        case CPM_ERR_BAD_SHAPE: return "CPM_ERR_BAD_SHAPE";
+        case CPM_ERR_BAD_ALIGN: return "CPM_ERR_BAD_ALIGN";
+        case CPM_ERR_BAD_DTYPE: return "CPM_ERR_BAD_DTYPE";
+        case CPM_ERR_NULL: return "CPM_ERR_NULL";
+        case CPM_ERR_WORKSPACE: return "CPM_ERR_WORKSPACE";
+        case CPM_ERR_CUDA: return "CPM_ERR_CUDA";
+        case CPM_ERR_UNSUPPORTED: return "CPM_ERR_UNSUPPORTED";
+        default: return "CPM_ERR_UNKNOWN";
+    }
+}
+
+int64_t cpm_linattn_workspace_bytes(int N, int L, int H) {
+    if (N <= 0 || L <= 0 || H <= 0) return 0;
+    int nseg, seg_len;
+    plan_segments(N, H, L, &nseg, &seg_len);
+    return 2ll * N * H * nseg * STATE_FLOATS * (int64_t)sizeof(float);
+}
+
+static int linattn_check(const void *a, const void *b, const void *c, const void *d, int N, int L, int H, int E, int M,
+                         int64_t ld_qkv, int64_t ld_o, int dtype, void *ws, int64_t ws_bytes) {
+    CPM_REQUIRE(a && b && c && d, CPM_ERR_NULL, "linattn: q/k/v/out must be non-NULL");
+    CPM_REQUIRE(N > 0 && L > 0 && H > 0, CPM_ERR_BAD_SHAPE, "linattn: N=%d L=%d H=%d must be positive", N, L, H);
+    CPM_REQUIRE(E == 64 && M == 64, CPM_ERR_BAD_SHAPE, "linattn: only E=M=64 is supported (got E=%d M=%d)", E, M);
+    CPM_REQUIRE(dtype == CPM_F32 || dtype == CPM_BF16, CPM_ERR_BAD_DTYPE, "linattn: dtype %d", dtype);
+    CPM_REQUIRE(ld_qkv >= (int64_t)H * E && ld_o >= (int64_t)H * M && ld_qkv % 8 == 0 && ld_o % 8 == 0, CPM_ERR_BAD_SHAPE,
+                "linattn: token strides (%lld,%lld) must be >= H*64 and multiples of 8", (long long)ld_qkv, (long long)ld_o);
+    CPM_REQUIRE(aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d), CPM_ERR_BAD_ALIGN,
+                "linattn: q/k/v/out must be 16-byte aligned");
+    CPM_REQUIRE(ws_bytes >= cpm_linattn_workspace_bytes(N, L, H) && (ws || ws_bytes == 0), CPM_ERR_WORKSPACE,
+                "linattn: workspace %lld < required %lld", (long long)ws_bytes, (long long)cpm_linattn_workspace_bytes(N, L, H));
+    return CPM_OK;
+}
+
+int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int E, int M,
+                    int64_t ld_qkv, int64_t ld_o, int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes,
+                    void *stream) {
+    int rc = linattn_check(q, k, v, out, N, L, H, E, M, ld_qkv, ld_o, dtype, workspace, workspace_bytes);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tc_ok = dtype == CPM_BF16 && L % 128 == 0;
+    CPM_REQUIRE(impl != 2 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_fwd: tcgen05 path needs bf16 and L%%128==0");
+    if (impl == 2 || (impl == 0 && tc_ok)) {
+        rc = linattn_fwd_tc_launch(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, workspace, st);
+        if (rc != CPM_ERR_UNSUPPORTED || impl == 2) { g_linattn_impl = "tcgen05"; return rc; }
+    }
+    g_linattn_impl = "simt";
+    return linattn_fwd_simt_launch(q, k, v, out, den, N, L, H, ld_qkv, ld_o, dtype, eps, workspace, st);
+}
+
+int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout,
+                    void *gq, void *gk, void *gv, int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
+                    int64_t ld_g, int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes, void *stream) {
+    int rc = linattn_check(q, k, v, out, N, L, H, E, M, ld_qkv, ld_o, dtype, workspace, workspace_bytes);
+    if (rc) return rc;
+    CPM_REQUIRE(den && gout && gq && gk && gv, CPM_ERR_NULL, "linattn_bwd: den/gout/gq/gk/gv must be non-NULL");
+    CPM_REQUIRE(ld_g >= (int64_t)H * 64 && ld_g % 8 == 0, CPM_ERR_BAD_SHAPE, "linattn_bwd: ld_g=%lld", (long long)ld_g);
+    CPM_REQUIRE(aligned16(gout) && aligned16(gq) && aligned16(gk) && aligned16(gv), CPM_ERR_BAD_ALIGN,
+                "linattn_bwd: gradient buffers must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    bool tc_ok = dtype == CPM_BF16 && L % 128 == 0;
+    CPM_REQUIRE(impl != 2 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_bwd: tcgen05 path needs bf16 and L%%128==0");
+    if (impl == 2 || (impl == 0 && tc_ok)) {
+        rc = linattn_bwd_tc_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, eps, workspace, st);
+        if (rc != CPM_ERR_UNSUPPORTED || impl == 2) { g_linattn_impl = "tcgen05"; return rc; }
+    }
+    g_linattn_impl = "simt";
+    return linattn_bwd_simt_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, dtype, eps, workspace, st);
+}
+
+int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, float *Z, void *out, int N, int H, int E, int M,
+                     int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream) {
+    CPM_REQUIRE(q && k && v && S && Z && out, CPM_ERR_NULL, "linattn_step: NULL pointer");
+    CPM_REQUIRE(N > 0 && H > 0, CPM_ERR_BAD_SHAPE, "linattn_step: N=%d H=%d", N, H);
+    CPM_REQUIRE(E == 64 && M == 64, CPM_ERR_BAD_SHAPE, "linattn_step: only E=M=64 (got %d,%d)", E, M);
+    CPM_REQUIRE(ld_qkv >= (int64_t)H * 64 && ld_o >= (int64_t)H * 64, CPM_ERR_BAD_SHAPE, "linattn_step: strides");
+    CPM_REQUIRE(aligned16(S), CPM_ERR_BAD_ALIGN, "linattn_step: S must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CPM_F32)
+        linattn_step_kernel<float><<<N * H, 256, 0, st>>>((const float *)q, (const float *)k, (const float *)v, S, Z,
+                                                          (float *)out, H, ld_qkv, ld_o, eps);
+    else if (dtype == CPM_BF16)
+        linattn_step_kernel<__nv_bfloat16><<<N * H, 256, 0, st>>>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k,
+                                                                  (const __nv_bfloat16 *)v, S, Z, (__nv_bfloat16 *)out, H,
+                                                                  ld_qkv, ld_o, eps);
+    else
+        return fail(CPM_ERR_BAD_DTYPE, "linattn_step: dtype %d", dtype);
+    return check_launch("linattn_step");
+}
+
+}  // extern "C"

@@ -1,0 +1,116 @@
+// Shared device/host helpers for libcpmusic (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string.h>
+#include <stdarg.h>
+#include "../../include/cpmusic.h"
+
+namespace cpm {
+
+// ---------------------------------------------------------------- host error plumbing
+extern thread_local char g_err[512];
+int fail(int code, const char *fmt, ...);
+inline int check_launch(const char *what) {
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "%s: %s", what, cudaGetErrorString(e));
+    return CPM_OK;
+}
+inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+#define CPM_REQUIRE(cond, code, ...) do { if (!(cond)) return ::cpm::fail(code, __VA_ARGS__); } while (0)
+
+// ---------------------------------------------------------------- dtype helpers
+template <typename T> struct Vec8;           // 8 activations = one 16-byte (bf16) or 32-byte (f32) access
+template <> struct Vec8<float> {
+    float v[8];
+    __device__ __forceinline__ void load(const float *p) {
+        float4 a = *reinterpret_cast<const float4 *>(p), b = *reinterpret_cast<const float4 *>(p + 4);
+        v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w;
+    }
+    __device__ __forceinline__ void store(float *p) const {
+        *reinterpret_cast<float4 *>(p) = make_float4(v[0], v[1], v[2], v[3]);
+        *reinterpret_cast<float4 *>(p + 4) = make_float4(v[4], v[5], v[6], v[7]);
+    }
+};
+template <> struct Vec8<__nv_bfloat16> {
+    float v[8];
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) {
+        uint4 raw = *reinterpret_cast<const uint4 *>(p);
+        const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { float2 f = __bfloat1622float2(h[i]); v[2 * i] = f.x; v[2 * i + 1] = f.y; }
+    }
+    __device__ __forceinline__ void store(__nv_bfloat16 *p) const {
+        uint4 raw;
+        __nv_bfloat162 *h = reinterpret_cast<__nv_bfloat162 *>(&raw);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) h[i] = __floats2bfloat162_rn(v[2 * i], v[2 * i + 1]);
+        *reinterpret_cast<uint4 *>(p) = raw;
+    }
+};
+__device__ __forceinline__ float to_f(float x) { return x; }
+__device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
+template <typename T> __device__ __forceinline__ T from_f(float x);
+template <> __device__ __forceinline__ float from_f<float>(float x) { return x; }
+template <> __device__ __forceinline__ __nv_bfloat16 from_f<__nv_bfloat16>(float x) { return __float2bfloat16_rn(x); }
+
+// elu(x)+1 feature map and its derivative (ft default feature map)
+__device__ __forceinline__ float phi(float x) { return x > 0.f ? x + 1.f : __expf(x); }
+__device__ __forceinline__ float dphi(float x) { return x > 0.f ? 1.f : __expf(x); }
+
+// ---------------------------------------------------------------- warp / block reductions
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// ---------------------------------------------------------------- Philox4x32-10 (Salmon et al. 2011)
+struct Philox {
+    __device__ __forceinline__ static uint4 block(uint4 c, uint2 k) {
+#pragma unroll
+        for (int r = 0; r < 10; ++r) {
+            uint32_t hi0 = __umulhi(0xD2511F53u, c.x), lo0 = 0xD2511F53u * c.x;
+            uint32_t hi1 = __umulhi(0xCD9E8D57u, c.z), lo1 = 0xCD9E8D57u * c.z;
+            c = make_uint4(hi1 ^ c.y ^ k.x, lo1, hi0 ^ c.w ^ k.y, lo0);
+            k.x += 0x9E3779B9u; k.y += 0xBB67AE85u;
+        }
+        return c;
+    }
+};
+// Dropout keep-mask for the 8 elements [8*g, 8*g+8): 16 random bits each, keep iff bits >= thr.
+__device__ __forceinline__ void dropout_mask8(uint64_t seed, uint64_t offset, uint64_t g, uint32_t thr, bool keep[8]) {
+    uint64_t ctr = offset + g;
+    uint4 r = Philox::block(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x44524F50u /*"DROP"*/, 0u),
+                            make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    keep[0] = (r.x & 0xFFFFu) >= thr; keep[1] = (r.x >> 16) >= thr;
+    keep[2] = (r.y & 0xFFFFu) >= thr; keep[3] = (r.y >> 16) >= thr;
+    keep[4] = (r.z & 0xFFFFu) >= thr; keep[5] = (r.z >> 16) >= thr;
+    keep[6] = (r.w & 0xFFFFu) >= thr; keep[7] = (r.w >> 16) >= thr;
+}
+inline uint32_t dropout_threshold(float p) {           // host: P(drop) = thr / 65536
+    if (p <= 0.f) return 0u;
+    double t = (double)p * 65536.0 + 0.5;
+    return t >= 65535.0 ? 65535u : (uint32_t)t;
+}
+inline float dropout_scale(float p) { uint32_t t = dropout_threshold(p); return t ? 65536.0f / (65536.0f - (float)t) : 1.0f; }
+
+inline int num_sms() {
+    static int n = 0;
+    if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }
+    return n;
+}
+
+}  // namespace cpm

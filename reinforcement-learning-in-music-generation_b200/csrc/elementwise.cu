@@ -1,0 +1,478 @@
+// Memory-bound fused kernels around the encoder GEMMs: CP embedding gather/scatter,
+// positional-encoding add, dropout, residual+dropout+LayerNorm (fwd/bwd), bias+GELU+dropout.
+// All use 128-bit accesses (8 bf16 / 2x4 fp32 per thread access) and grid-stride loops.
+#include "cpm_common.cuh"
+
+namespace cpm {
+namespace {
+
+struct EmbedParams {
+    const float *tables[CPM_MAX_ATTR];
+    float *gtables[CPM_MAX_ATTR];
+    int n_tokens[CPM_MAX_ATTR];
+    int emb[CPM_MAX_ATTR];
+    int off[CPM_MAX_ATTR + 1];
+    float scale[CPM_MAX_ATTR];
+    int n_attr;
+};
+
+// ---------------------------------------------------------------- C1 embedding forward
+template <typename T>
+__global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t *__restrict__ idx, EmbedParams p, int64_t T_, T *__restrict__ out,
+                                                        int *err_flag) {
+    const int width = p.off[p.n_attr], G = width >> 3;
+    const int64_t total = T_ * G;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t t = i / G;
+        const int col = (int)(i % G) * 8;
+        int a = 0;
+        while (col >= p.off[a + 1]) ++a;
+        const int64_t id = idx[t * p.n_attr + a];
+        Vec8<T> o;
+        if (id < 0 || id >= p.n_tokens[a]) {
+            if (err_flag) atomicExch(err_flag, 1);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) o.v[j] = 0.f;
+        } else {
+            const float *src = p.tables[a] + id * p.emb[a] + (col - p.off[a]);
+            float4 x = *reinterpret_cast<const float4 *>(src), y = *reinterpret_cast<const float4 *>(src + 4);
+            const float s = p.scale[a];
+            o.v[0] = x.x * s; o.v[1] = x.y * s; o.v[2] = x.z * s; o.v[3] = x.w * s;
+            o.v[4] = y.x * s; o.v[5] = y.y * s; o.v[6] = y.z * s; o.v[7] = y.w * s;
+        }
+        o.store(out + t * width + col);
+    }
+}
+
+// ---------------------------------------------------------------- C1 embedding backward
+// grid.x = column tiles of 32 over the concatenated width, grid.y = token chunks.  Each block keeps
+// a [n_tokens_a x 32] fp32 accumulator in shared memory (shared atomics), then flushes the non-zero
+// rows with one global atomic per element.
+template <typename T>
+__global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t *__restrict__ idx, const T *__restrict__ gout, EmbedParams p,
+                                                        int64_t T_, int64_t tokens_per_block) {
+    extern __shared__ float acc[];
+    const int width = p.off[p.n_attr];
+    const int col0 = blockIdx.x * 32;
+    int a = 0;
+    while (col0 >= p.off[a + 1]) ++a;
+    const int nrow = p.n_tokens[a];
+    for (int i = threadIdx.x; i < nrow * 32; i += blockDim.x) acc[i] = 0.f;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nwarp = blockDim.x >> 5;
+    const int64_t t_begin = (int64_t)blockIdx.y * tokens_per_block;
+    const int64_t t_end = min(T_, t_begin + tokens_per_block);
+    for (int64_t t = t_begin + warp; t < t_end; t += nwarp) {
+        const int64_t id = idx[t * p.n_attr + a];
+        if (id < 0 || id >= nrow) continue;
+        atomicAdd(&acc[id * 32 + lane], to_f(gout[t * width + col0 + lane]));
+    }
+    __syncthreads();
+    float *dst = p.gtables[a] + (col0 - p.off[a]);
+    const float s = p.scale[a];
+    for (int i = threadIdx.x; i < nrow * 32; i += blockDim.x) {
+        float g = acc[i];
+        if (g != 0.f) atomicAdd(dst + (int64_t)(i >> 5) * p.emb[a] + (i & 31), g * s);
+    }
+}
+
+// ---------------------------------------------------------------- PE add (+dropout)
+template <typename T>
+__global__ void __launch_bounds__(256) add_pe_kernel(const T *__restrict__ x, const float *__restrict__ pe, T *__restrict__ y, int64_t rows,
+                                                     int L, int d, int pos_offset, const int32_t *__restrict__ pos_dev, int max_len,
+                                                     uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset) {
+    const int G = d >> 3;
+    const int64_t total = rows * G;
+    const int base = pos_dev ? pos_dev[0] : pos_offset;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t r = i / G;
+        const int c = (int)(i % G) * 8;
+        int pos = base + (int)(r % L);
+        pos = pos < max_len ? pos : max_len - 1;
+        Vec8<T> v;
+        v.load(x + r * d + c);
+        const float *ps = pe + (int64_t)pos * d + c;
+        float4 p0 = *reinterpret_cast<const float4 *>(ps), p1 = *reinterpret_cast<const float4 *>(ps + 4);
+        v.v[0] += p0.x; v.v[1] += p0.y; v.v[2] += p0.z; v.v[3] += p0.w;
+        v.v[4] += p1.x; v.v[5] += p1.y; v.v[6] += p1.z; v.v[7] += p1.w;
+        if (thr) {
+            bool keep[8];
+            dropout_mask8(seed, rng_offset, (uint64_t)i, thr, keep);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v.v[j] = keep[j] ? v.v[j] * scale : 0.f;
+        }
+        v.store(y + r * d + c);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) dropout_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t n8, uint32_t thr, float scale,
+                                                      uint64_t seed, uint64_t rng_offset) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
+        Vec8<T> v;
+        v.load(x + i * 8);
+        if (thr) {
+            bool keep[8];
+            dropout_mask8(seed, rng_offset, (uint64_t)i, thr, keep);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) v.v[j] = keep[j] ? v.v[j] * scale : 0.f;
+        }
+        v.store(y + i * 8);
+    }
+}
+
+// ---------------------------------------------------------------- C2 residual + dropout + LayerNorm
+// One warp per row; the row lives in registers (MAXV vectors of 8 per lane).
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(128) ln_residual_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, const float *__restrict__ gamma,
+                                                              const float *__restrict__ beta, T *__restrict__ y, T *__restrict__ s_out,
+                                                              float *__restrict__ mean_out, float *__restrict__ rstd_out, int64_t rows, int d,
+                                                              float eps, uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset) {
+    const int lane = threadIdx.x & 31;
+    const int G = d >> 3;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp_global; r < rows; r += nwarps) {
+        Vec8<T> v[MAXV];
+        float sum = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int g = lane + 32 * i;
+            if (g < G) {
+                v[i].load(x + r * d + g * 8);
+                if (res) {
+                    Vec8<T> rr;
+                    rr.load(res + r * d + g * 8);
+                    if (thr) {
+                        bool keep[8];
+                        dropout_mask8(seed, rng_offset, (uint64_t)(r * G + g), thr, keep);
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rr.v[j] = keep[j] ? rr.v[j] * scale : 0.f;
+                    }
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) v[i].v[j] += rr.v[j];
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) sum += v[i].v[j];
+            }
+        }
+        const float mean = warp_sum(sum) / (float)d;
+        float sq = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i)
+            if (lane + 32 * i < G) {
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { float c = v[i].v[j] - mean; sq += c * c; }
+            }
+        const float rstd = rsqrtf(warp_sum(sq) / (float)d + eps);
+        if (lane == 0) {
+            if (mean_out) mean_out[r] = mean;
+            if (rstd_out) rstd_out[r] = rstd;
+        }
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int g = lane + 32 * i;
+            if (g < G) {
+                if (s_out) v[i].store(s_out + r * d + g * 8);
+                float4 g0 = *reinterpret_cast<const float4 *>(gamma + g * 8), g1 = *reinterpret_cast<const float4 *>(gamma + g * 8 + 4);
+                float4 b0 = *reinterpret_cast<const float4 *>(beta + g * 8), b1 = *reinterpret_cast<const float4 *>(beta + g * 8 + 4);
+                const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w};
+                const float bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                Vec8<T> o;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] = (v[i].v[j] - mean) * rstd * gm[j] + bt[j];
+                o.store(y + r * d + g * 8);
+            }
+        }
+    }
+}
+
+constexpr int LN_BWD_BLOCKS = 296;   // 2 CTAs per SM on 148 SMs
+constexpr int LN_BWD_THREADS = 256;
+
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(LN_BWD_THREADS) ln_residual_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ s, const float *__restrict__ mean,
+                                                                         const float *__restrict__ rstd, const float *__restrict__ gamma, T *__restrict__ gs,
+                                                                         T *__restrict__ gres, float *__restrict__ partials, int64_t rows, int d, uint32_t thr,
+                                                                         float scale, uint64_t seed, uint64_t rng_offset) {
+    extern __shared__ float red[];   // [2][d] block partial sums
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int G = d >> 3;
+    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
+    __syncthreads();
+    float dg[MAXV][8], db[MAXV][8], gm[MAXV][8];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int g = lane + 32 * i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gm[i][j] = (g < G) ? gamma[g * 8 + j] : 0.f; }
+    }
+    const int64_t warp_global = (int64_t)blockIdx.x * (LN_BWD_THREADS / 32) + warp;
+    const int64_t nwarps = (int64_t)gridDim.x * (LN_BWD_THREADS / 32);
+    for (int64_t r = warp_global; r < rows; r += nwarps) {
+        const float mu = mean[r], rs = rstd[r];
+        Vec8<T> g_[MAXV], x_[MAXV];
+        float c1 = 0.f, c2 = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int g = lane + 32 * i;
+            if (g < G) {
+                g_[i].load(gy + r * d + g * 8);
+                x_[i].load(s + r * d + g * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    const float xh = (x_[i].v[j] - mu) * rs;
+                    const float gg = g_[i].v[j];
+                    dg[i][j] += gg * xh;
+                    db[i][j] += gg;
+                    const float w = gg * gm[i][j];
+                    c1 += w * xh;
+                    c2 += w;
+                    x_[i].v[j] = xh;
+                    g_[i].v[j] = w;
+                }
+            }
+        }
+        c1 = warp_sum(c1) / (float)d;
+        c2 = warp_sum(c2) / (float)d;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int g = lane + 32 * i;
+            if (g < G) {
+                Vec8<T> o;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) o.v[j] = rs * (g_[i].v[j] - c2 - x_[i].v[j] * c1);
+                o.store(gs + r * d + g * 8);
+                if (gres && thr) {
+                    bool keep[8];
+                    dropout_mask8(seed, rng_offset, (uint64_t)(r * G + g), thr, keep);
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) o.v[j] = keep[j] ? o.v[j] * scale : 0.f;
+                    o.store(gres + r * d + g * 8);
+                }
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int g = lane + 32 * i;
+        if (g < G) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                atomicAdd(&red[g * 8 + j], dg[i][j]);
+                atomicAdd(&red[d + g * 8 + j], db[i][j]);
+            }
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) partials[(int64_t)blockIdx.x * 2 * d + i] = red[i];
+}
+
+__global__ void ln_reduce_partials_kernel(const float *__restrict__ partials, int nblocks, int d, float *__restrict__ dgamma,
+                                          float *__restrict__ dbeta) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= 2 * d) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * 2 * d + c];
+    if (c < d) dgamma[c] += s; else dbeta[c - d] += s;
+}
+
+// ---------------------------------------------------------------- bias + exact GELU + dropout
+__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
+__device__ __forceinline__ float dgelu_f(float x) {
+    return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+}
+
+template <typename T, bool BWD>
+__global__ void __launch_bounds__(256) gelu_kernel(const T *__restrict__ x, const float *__restrict__ bias, const T *__restrict__ gy, T *__restrict__ out,
+                                                   int64_t rows, int d, uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset) {
+    const int G = d >> 3;
+    const int64_t total = rows * G;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int c = (int)(i % G) * 8;
+        Vec8<T> v, g;
+        v.load(x + i * 8);
+        if (bias) {
+            float4 b0 = *reinterpret_cast<const float4 *>(bias + c), b1 = *reinterpret_cast<const float4 *>(bias + c + 4);
+            v.v[0] += b0.x; v.v[1] += b0.y; v.v[2] += b0.z; v.v[3] += b0.w;
+            v.v[4] += b1.x; v.v[5] += b1.y; v.v[6] += b1.z; v.v[7] += b1.w;
+        }
+        if (BWD) g.load(gy + i * 8);
+        bool keep[8];
+        if (thr) dropout_mask8(seed, rng_offset, (uint64_t)i, thr, keep);
+        Vec8<T> o;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float r = BWD ? g.v[j] * dgelu_f(v.v[j]) : gelu_f(v.v[j]);
+            if (thr) r = keep[j] ? r * scale : 0.f;
+            o.v[j] = r;
+        }
+        o.store(out + i * 8);
+    }
+}
+
+inline int grid_for(int64_t work_items, int threads) {
+    int64_t b = (work_items + threads - 1) / threads;
+    int64_t cap = (int64_t)num_sms() * 16;
+    if (b > cap) b = cap;
+    if (b < 1) b = 1;
+    return (int)b;
+}
+
+int fill_embed_params(EmbedParams &p, const float *const *tables, float *const *gtables, const int *n_tokens, const int *emb,
+                      int n_attr, int mult) {
+    CPM_REQUIRE(n_attr >= 1 && n_attr <= CPM_MAX_ATTR, CPM_ERR_BAD_SHAPE, "embed: n_attr=%d out of [1,%d]", n_attr, CPM_MAX_ATTR);
+    p.n_attr = n_attr;
+    p.off[0] = 0;
+    for (int a = 0; a < n_attr; ++a) {
+        CPM_REQUIRE(emb[a] > 0 && emb[a] % mult == 0, CPM_ERR_BAD_SHAPE, "embed: emb_sizes[%d]=%d must be a multiple of %d", a, emb[a], mult);
+        CPM_REQUIRE(n_tokens[a] > 0, CPM_ERR_BAD_SHAPE, "embed: n_tokens[%d]=%d", a, n_tokens[a]);
+        p.tables[a] = tables ? tables[a] : nullptr;
+        p.gtables[a] = gtables ? gtables[a] : nullptr;
+        CPM_REQUIRE(p.tables[a] || p.gtables[a], CPM_ERR_NULL, "embed: table %d is NULL", a);
+        p.n_tokens[a] = n_tokens[a];
+        p.emb[a] = emb[a];
+        p.off[a + 1] = p.off[a] + emb[a];
+        p.scale[a] = sqrtf((float)emb[a]);
+    }
+    return CPM_OK;
+}
+
+}  // namespace
+}  // namespace cpm
+
+using namespace cpm;
+
+#define DISPATCH_DTYPE(dtype, ...)                                              \
+    if ((dtype) == CPM_F32) { using T = float; __VA_ARGS__; }                   \
+    else if ((dtype) == CPM_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }     \
+    else return fail(CPM_ERR_BAD_DTYPE, "unsupported dtype %d", (int)(dtype));
+
+#define DISPATCH_MAXV(d, ...)                                                   \
+    if ((d) <= 256) { constexpr int MAXV = 1; __VA_ARGS__; }                    \
+    else if ((d) <= 512) { constexpr int MAXV = 2; __VA_ARGS__; }               \
+    else if ((d) <= 1024) { constexpr int MAXV = 4; __VA_ARGS__; }              \
+    else { constexpr int MAXV = 8; __VA_ARGS__; }
+
+extern "C" {
+
+int cpm_embed_fwd(const int64_t *idx, const float *const *tables_host, const int *n_tokens_host, const int *emb_sizes_host,
+                  int n_attr, int64_t T_, void *out, int dtype, int *err_flag, void *stream) {
+    CPM_REQUIRE(idx && tables_host && n_tokens_host && emb_sizes_host && out, CPM_ERR_NULL, "embed_fwd: NULL pointer");
+    CPM_REQUIRE(T_ >= 0, CPM_ERR_BAD_SHAPE, "embed_fwd: T=%lld", (long long)T_);
+    if (T_ == 0) return CPM_OK;
+    EmbedParams p{};
+    int rc = fill_embed_params(p, tables_host, nullptr, n_tokens_host, emb_sizes_host, n_attr, 8);
+    if (rc) return rc;
+    CPM_REQUIRE(aligned16(out), CPM_ERR_BAD_ALIGN, "embed_fwd: out not 16-byte aligned");
+    const int64_t items = T_ * (p.off[n_attr] / 8);
+    DISPATCH_DTYPE(dtype, embed_fwd_kernel<T><<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(idx, p, T_, (T *)out, err_flag));
+    return check_launch("embed_fwd");
+}
+
+int cpm_embed_bwd(const int64_t *idx, const void *gout, float *const *gtables_host, const int *n_tokens_host,
+                  const int *emb_sizes_host, int n_attr, int64_t T_, int dtype, void *stream) {
+    CPM_REQUIRE(idx && gout && gtables_host && n_tokens_host && emb_sizes_host, CPM_ERR_NULL, "embed_bwd: NULL pointer");
+    if (T_ == 0) return CPM_OK;
+    EmbedParams p{};
+    int rc = fill_embed_params(p, nullptr, gtables_host, n_tokens_host, emb_sizes_host, n_attr, 32);
+    if (rc) return rc;
+    int max_rows = 0;
+    for (int a = 0; a < n_attr; ++a) max_rows = n_tokens_host[a] > max_rows ? n_tokens_host[a] : max_rows;
+    const size_t smem = (size_t)max_rows * 32 * sizeof(float);
+    CPM_REQUIRE(smem <= 160 * 1024, CPM_ERR_UNSUPPORTED, "embed_bwd: vocabulary of %d rows exceeds the shared-memory accumulator", max_rows);
+    int ychunks = (int)((T_ + 1023) / 1024);
+    if (ychunks > 64) ychunks = 64;
+    const int64_t tpb = (T_ + ychunks - 1) / ychunks;
+    dim3 grid(p.off[n_attr] / 32, ychunks);
+    DISPATCH_DTYPE(dtype, {
+        if (smem > 48 * 1024) {
+            cudaError_t e = cudaFuncSetAttribute(embed_bwd_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+            if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "embed_bwd smem: %s", cudaGetErrorString(e));
+        }
+        embed_bwd_kernel<T><<<grid, 256, smem, (cudaStream_t)stream>>>(idx, (const T *)gout, p, T_, tpb);
+    });
+    return check_launch("embed_bwd");
+}
+
+int cpm_add_pe(const void *x, const float *pe, void *y, int64_t rows, int L, int d, int pos_offset, const int32_t *pos_dev,
+               int max_len, float p_drop, uint64_t seed, uint64_t rng_offset, int dtype, void *stream) {
+    CPM_REQUIRE(x && pe && y, CPM_ERR_NULL, "add_pe: NULL pointer");
+    CPM_REQUIRE(rows >= 0 && L > 0 && d > 0 && d % 8 == 0 && max_len > 0, CPM_ERR_BAD_SHAPE, "add_pe: rows=%lld L=%d d=%d", (long long)rows, L, d);
+    CPM_REQUIRE(pos_dev || pos_offset + L <= max_len, CPM_ERR_BAD_SHAPE, "add_pe: positions %d..%d exceed max_len %d", pos_offset, pos_offset + L, max_len);
+    CPM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(pe), CPM_ERR_BAD_ALIGN, "add_pe: alignment");
+    if (rows == 0) return CPM_OK;
+    const uint32_t thr = dropout_threshold(p_drop);
+    DISPATCH_DTYPE(dtype, add_pe_kernel<T><<<grid_for(rows * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const T *)x, pe, (T *)y, rows, L, d, pos_offset, pos_dev, max_len, thr, dropout_scale(p_drop), seed, rng_offset));
+    return check_launch("add_pe");
+}
+
+int cpm_dropout(const void *x, void *y, int64_t n, float p_drop, uint64_t seed, uint64_t rng_offset, int dtype, void *stream) {
+    CPM_REQUIRE(x && y, CPM_ERR_NULL, "dropout: NULL pointer");
+    CPM_REQUIRE(n >= 0 && n % 8 == 0, CPM_ERR_BAD_SHAPE, "dropout: n=%lld must be a multiple of 8", (long long)n);
+    CPM_REQUIRE(aligned16(x) && aligned16(y), CPM_ERR_BAD_ALIGN, "dropout: alignment");
+    if (n == 0) return CPM_OK;
+    DISPATCH_DTYPE(dtype, dropout_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const T *)x, (T *)y, n / 8, dropout_threshold(p_drop), dropout_scale(p_drop), seed, rng_offset));
+    return check_launch("dropout");
+}
+
+int cpm_ln_residual_fwd(const void *x, const void *res, const float *gamma, const float *beta, void *y, void *s_out, float *mean,
+                        float *rstd, int64_t rows, int d, float eps, float p_drop, uint64_t seed, uint64_t rng_offset, int dtype,
+                        void *stream) {
+    CPM_REQUIRE(x && gamma && beta && y, CPM_ERR_NULL, "ln_residual_fwd: NULL pointer");
+    CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0 && d <= 2048, CPM_ERR_BAD_SHAPE, "ln_residual_fwd: d=%d must be a multiple of 8 and <= 2048", d);
+    CPM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(gamma) && aligned16(beta) && (!res || aligned16(res)) && (!s_out || aligned16(s_out)),
+                CPM_ERR_BAD_ALIGN, "ln_residual_fwd: alignment");
+    if (rows == 0) return CPM_OK;
+    const uint32_t thr = res ? dropout_threshold(p_drop) : 0u;
+    const int grid = grid_for(rows * 32, 128);
+    DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_fwd_kernel<T, MAXV><<<grid, 128, 0, (cudaStream_t)stream>>>(
+                                               (const T *)x, (const T *)res, gamma, beta, (T *)y, (T *)s_out, mean, rstd, rows, d, eps, thr,
+                                               dropout_scale(p_drop), seed, rng_offset)));
+    return check_launch("ln_residual_fwd");
+}
+
+int cpm_ln_partials_rows(void) { return LN_BWD_BLOCKS; }
+
+int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const float *rstd, const float *gamma, void *gs, void *gres,
+                        float *dgamma, float *dbeta, float *partials, int64_t rows, int d, float p_drop, uint64_t seed,
+                        uint64_t rng_offset, int dtype, void *stream) {
+    CPM_REQUIRE(gy && s && mean && rstd && gamma && gs && dgamma && dbeta && partials, CPM_ERR_NULL, "ln_residual_bwd: NULL pointer");
+    CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0 && d <= 2048, CPM_ERR_BAD_SHAPE, "ln_residual_bwd: d=%d", d);
+    CPM_REQUIRE(aligned16(gy) && aligned16(s) && aligned16(gs) && (!gres || aligned16(gres)), CPM_ERR_BAD_ALIGN, "ln_residual_bwd: alignment");
+    const uint32_t thr = dropout_threshold(p_drop);
+    CPM_REQUIRE(!thr || gres, CPM_ERR_NULL, "ln_residual_bwd: gres required when p_drop > 0");
+    if (rows == 0) return CPM_OK;
+    const size_t smem = 2 * (size_t)d * sizeof(float);
+    DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV><<<LN_BWD_BLOCKS, LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
+                                               (const T *)gy, (const T *)s, mean, rstd, gamma, (T *)gs, (T *)gres, partials, rows, d, thr,
+                                               dropout_scale(p_drop), seed, rng_offset)));
+    ln_reduce_partials_kernel<<<(2 * d + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partials, LN_BWD_BLOCKS, d, dgamma, dbeta);
+    return check_launch("ln_residual_bwd");
+}
+
+int cpm_gelu_fwd(const void *x, const float *bias, void *y, int64_t rows, int d, float p_drop, uint64_t seed, uint64_t rng_offset,
+                 int dtype, void *stream) {
+    CPM_REQUIRE(x && y, CPM_ERR_NULL, "gelu_fwd: NULL pointer");
+    CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0, CPM_ERR_BAD_SHAPE, "gelu_fwd: d=%d", d);
+    CPM_REQUIRE(aligned16(x) && aligned16(y) && (!bias || aligned16(bias)), CPM_ERR_BAD_ALIGN, "gelu_fwd: alignment");
+    if (rows == 0) return CPM_OK;
+    DISPATCH_DTYPE(dtype, gelu_kernel<T, false><<<grid_for(rows * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const T *)x, bias, nullptr, (T *)y, rows, d, dropout_threshold(p_drop), dropout_scale(p_drop), seed, rng_offset));
+    return check_launch("gelu_fwd");
+}
+
+int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, int64_t rows, int d, float p_drop, uint64_t seed,
+                 uint64_t rng_offset, int dtype, void *stream) {
+    CPM_REQUIRE(x && gy && gx, CPM_ERR_NULL, "gelu_bwd: NULL pointer");
+    CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0, CPM_ERR_BAD_SHAPE, "gelu_bwd: d=%d", d);
+    CPM_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(gx) && (!bias || aligned16(bias)), CPM_ERR_BAD_ALIGN, "gelu_bwd: alignment");
+    if (rows == 0) return CPM_OK;
+    DISPATCH_DTYPE(dtype, gelu_kernel<T, true><<<grid_for(rows * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const T *)x, bias, (const T *)gy, (T *)gx, rows, d, dropout_threshold(p_drop), dropout_scale(p_drop), seed, rng_offset));
+    return check_launch("gelu_bwd");
+}
+
+}  // extern "C"

@@ -1,0 +1,351 @@
+// Per-attribute head kernels over the concatenated CP logits: decode (greedy / temperature /
+// nucleus with Philox inverse-CDF draws), log-prob + entropy (fwd/bwd) and masked cross-entropy
+// (fwd/bwd).  One warp owns one (row, attribute) segment; segments are <= 1024 wide.
+#include "cpm_common.cuh"
+
+namespace cpm {
+namespace {
+
+constexpr int MAX_SEG = 1024;
+constexpr int WARPS = 4;
+
+struct SegParams {
+    int seg[CPM_MAX_ATTR + 1];
+    float temperature[CPM_MAX_ATTR];
+    float top_p[CPM_MAX_ATTR];
+    int n_attr;
+};
+
+struct ArgMax { float v; int i; };
+__device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, a.v, o);
+        int oi = __shfl_xor_sync(0xffffffffu, a.i, o);
+        if (ov > a.v || (ov == a.v && oi < a.i)) { a.v = ov; a.i = oi; }
+    }
+    return a;
+}
+
+// loads the segment into buf (fp32), returns first-index argmax and logsumexp (T=1)
+template <typename T>
+__device__ __forceinline__ void load_segment(const T *__restrict__ row, int w, float *buf, int lane, ArgMax &am, float &lse) {
+    ArgMax a{-INFINITY, 0x7fffffff};
+    for (int i = lane; i < w; i += 32) {
+        float x = to_f(row[i]);
+        buf[i] = x;
+        if (x > a.v) { a.v = x; a.i = i; }
+    }
+    am = warp_argmax(a);
+    float s = 0.f;
+    for (int i = lane; i < w; i += 32) s += __expf(buf[i] - am.v);
+    lse = am.v + __logf(warp_sum(s));
+}
+
+// ---------------------------------------------------------------- C3 decode
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) heads_sample_kernel(const T *__restrict__ logits, int64_t rows, int64_t ld, SegParams sp, int mode,
+                                                                  uint64_t seed, int64_t seq_base, int step, const int32_t *__restrict__ step_dev,
+                                                                  int64_t *__restrict__ tokens, float *__restrict__ logp, float *__restrict__ entropy) {
+    __shared__ float sbuf[WARPS][MAX_SEG];
+    __shared__ float sprob[WARPS][MAX_SEG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *buf = sbuf[warp], *pr = sprob[warp];
+    const int64_t items = rows * sp.n_attr;
+    const int cur_step = step_dev ? step_dev[0] : step;
+    for (int64_t it = (int64_t)blockIdx.x * WARPS + warp; it < items; it += (int64_t)gridDim.x * WARPS) {
+        const int64_t r = it / sp.n_attr;
+        const int a = (int)(it % sp.n_attr);
+        const int w = sp.seg[a + 1] - sp.seg[a];
+        ArgMax am;
+        float lse;
+        __syncwarp();
+        load_segment(logits + r * ld + sp.seg[a], w, buf, lane, am, lse);
+        __syncwarp();
+        int tok = am.i;
+        if (mode == 1) {
+            const float invt = 1.f / sp.temperature[a];
+            float s = 0.f;
+            for (int i = lane; i < w; i += 32) { float e = __expf((buf[i] - am.v) * invt); pr[i] = e; s += e; }
+            s = warp_sum(s);
+            const float top_p = sp.top_p[a];
+            const bool use_nucleus = top_p > 0.f && top_p < 1.f;
+            // reference: softmax, then nucleus divides by (sum + 1e-5); weighted_sampling by sum.
+            const float norm = use_nucleus ? 1.f / (s * (1.f + 1e-5f)) : 1.f / s;
+            __syncwarp();
+            for (int i = lane; i < w; i += 32) pr[i] *= norm;
+            __syncwarp();
+            // exclusive mass of everything ranked before element i in descending order
+            float zkeep = 0.f;
+            float ex[MAX_SEG / 32];
+#pragma unroll 1
+            for (int c = 0; c * 32 + lane < w; ++c) {
+                const int i = c * 32 + lane;
+                const float pi = pr[i];
+                float e = 0.f;
+                for (int j = 0; j < w; ++j) {
+                    const float pj = pr[j];
+                    e += (pj > pi || (pj == pi && j < i)) ? pj : 0.f;
+                }
+                const bool keep = !(use_nucleus && e > top_p);
+                ex[c] = keep ? e : -1.f;
+                zkeep += keep ? pi : 0.f;
+            }
+            zkeep = warp_sum(zkeep);
+            // Philox uniform for (sequence, step, attribute)
+            const uint64_t sid = (uint64_t)(seq_base + r);
+            uint4 rnd = Philox::block(make_uint4((uint32_t)sid, (uint32_t)cur_step, (uint32_t)a, (uint32_t)(sid >> 32)),
+                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+            const float u = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
+            const float target = u * zkeep;
+            ArgMax best{-1.f, 0x7fffffff};     // largest exclusive mass <= target among kept
+#pragma unroll 1
+            for (int c = 0; c * 32 + lane < w; ++c) {
+                const float e = ex[c];
+                if (e >= 0.f && e <= target && e > best.v) { best.v = e; best.i = c * 32 + lane; }
+            }
+            best = warp_argmax(best);
+            tok = best.i == 0x7fffffff ? am.i : best.i;
+        }
+        if (lane == 0) {
+            tokens[it] = tok;
+            if (logp) logp[it] = buf[tok] - lse;
+        }
+        if (entropy) {
+            float hx = 0.f;
+            for (int i = lane; i < w; i += 32) { float lp = buf[i] - lse; hx -= __expf(lp) * lp; }
+            hx = warp_sum(hx);
+            if (lane == 0) entropy[it] = hx;
+        }
+    }
+}
+
+// ---------------------------------------------------------------- log-prob / entropy of given tokens
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) heads_logp_kernel(const T *__restrict__ logits, int64_t rows, int64_t ld, SegParams sp,
+                                                                const int64_t *__restrict__ tokens, float *__restrict__ logp,
+                                                                float *__restrict__ entropy) {
+    __shared__ float sbuf[WARPS][MAX_SEG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *buf = sbuf[warp];
+    const int64_t items = rows * sp.n_attr;
+    for (int64_t it = (int64_t)blockIdx.x * WARPS + warp; it < items; it += (int64_t)gridDim.x * WARPS) {
+        const int64_t r = it / sp.n_attr;
+        const int a = (int)(it % sp.n_attr);
+        const int w = sp.seg[a + 1] - sp.seg[a];
+        ArgMax am;
+        float lse;
+        __syncwarp();
+        load_segment(logits + r * ld + sp.seg[a], w, buf, lane, am, lse);
+        __syncwarp();
+        int64_t tok = tokens[it];
+        tok = tok < 0 ? 0 : (tok >= w ? w - 1 : tok);
+        if (lane == 0 && logp) logp[it] = buf[tok] - lse;
+        if (entropy) {
+            float hx = 0.f;
+            for (int i = lane; i < w; i += 32) { float lp = buf[i] - lse; hx -= __expf(lp) * lp; }
+            hx = warp_sum(hx);
+            if (lane == 0) entropy[it] = hx;
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) heads_logp_bwd_kernel(const T *__restrict__ logits, int64_t rows, int64_t ld, SegParams sp,
+                                                                    const int64_t *__restrict__ tokens, const float *__restrict__ glogp,
+                                                                    const float *__restrict__ gent, T *__restrict__ dlogits) {
+    __shared__ float sbuf[WARPS][MAX_SEG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    float *buf = sbuf[warp];
+    const int64_t items = rows * sp.n_attr;
+    for (int64_t it = (int64_t)blockIdx.x * WARPS + warp; it < items; it += (int64_t)gridDim.x * WARPS) {
+        const int64_t r = it / sp.n_attr;
+        const int a = (int)(it % sp.n_attr);
+        const int w = sp.seg[a + 1] - sp.seg[a];
+        ArgMax am;
+        float lse;
+        __syncwarp();
+        load_segment(logits + r * ld + sp.seg[a], w, buf, lane, am, lse);
+        __syncwarp();
+        int64_t tok = tokens[it];
+        tok = tok < 0 ? 0 : (tok >= w ? w - 1 : tok);
+        const float gl = glogp ? glogp[it] : 0.f;
+        const float ge = gent ? gent[it] : 0.f;
+        float hx = 0.f;
+        if (gent) {
+            for (int i = lane; i < w; i += 32) { float lp = buf[i] - lse; hx -= __expf(lp) * lp; }
+            hx = warp_sum(hx);
+        }
+        T *dst = dlogits + r * ld + sp.seg[a];
+        for (int i = lane; i < w; i += 32) {
+            const float lp = buf[i] - lse, p = __expf(lp);
+            float g = gl * ((i == tok ? 1.f : 0.f) - p) - ge * p * (lp + hx);
+            dst[i] = from_f<T>(g);
+        }
+        if (a == sp.n_attr - 1)
+            for (int64_t i = sp.seg[sp.n_attr] + lane; i < ld; i += 32) dlogits[r * ld + i] = from_f<T>(0.f);
+    }
+}
+
+// ---------------------------------------------------------------- C4 masked cross-entropy
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) masked_ce_fwd_kernel(const T *__restrict__ logits, int64_t T_, int64_t ld, SegParams sp,
+                                                                   const int64_t *__restrict__ targets, const float *__restrict__ mask,
+                                                                   float *__restrict__ loss_num, float *__restrict__ mask_sum,
+                                                                   float *__restrict__ lse_out) {
+    __shared__ float sbuf[WARPS][MAX_SEG];
+    __shared__ float sacc[CPM_MAX_ATTR + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    if (threadIdx.x <= CPM_MAX_ATTR) sacc[threadIdx.x] = 0.f;
+    __syncthreads();
+    float *buf = sbuf[warp];
+    const int64_t items = T_ * sp.n_attr;
+    for (int64_t it = (int64_t)blockIdx.x * WARPS + warp; it < items; it += (int64_t)gridDim.x * WARPS) {
+        const int64_t t = it / sp.n_attr;
+        const int a = (int)(it % sp.n_attr);
+        const int w = sp.seg[a + 1] - sp.seg[a];
+        ArgMax am;
+        float lse;
+        __syncwarp();
+        load_segment(logits + t * ld + sp.seg[a], w, buf, lane, am, lse);
+        __syncwarp();
+        if (lane == 0) {
+            int64_t tg = targets[it];
+            tg = tg < 0 ? 0 : (tg >= w ? w - 1 : tg);
+            const float m = mask[t];
+            if (lse_out) lse_out[it] = lse;
+            atomicAdd(&sacc[a], m * (lse - buf[tg]));
+            if (a == 0) atomicAdd(&sacc[CPM_MAX_ATTR], m);
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < sp.n_attr) atomicAdd(&loss_num[threadIdx.x], sacc[threadIdx.x]);
+    if (threadIdx.x == CPM_MAX_ATTR && mask_sum) atomicAdd(mask_sum, sacc[CPM_MAX_ATTR]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) masked_ce_bwd_kernel(const T *__restrict__ logits, int64_t T_, int64_t ld, SegParams sp,
+                                                                   const int64_t *__restrict__ targets, const float *__restrict__ mask,
+                                                                   const float *__restrict__ lse_in, const float *__restrict__ gscale,
+                                                                   const float *__restrict__ denom, T *__restrict__ dlogits) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const int64_t items = T_ * sp.n_attr;
+    const float inv_denom = 1.f / denom[0];
+    for (int64_t it = (int64_t)blockIdx.x * WARPS + warp; it < items; it += (int64_t)gridDim.x * WARPS) {
+        const int64_t t = it / sp.n_attr;
+        const int a = (int)(it % sp.n_attr);
+        const int w = sp.seg[a + 1] - sp.seg[a];
+        int64_t tg = targets[it];
+        tg = tg < 0 ? 0 : (tg >= w ? w - 1 : tg);
+        const float coef = gscale[a] * mask[t] * inv_denom;
+        const float lse = lse_in[it];
+        const T *src = logits + t * ld + sp.seg[a];
+        T *dst = dlogits + t * ld + sp.seg[a];
+        for (int i = lane; i < w; i += 32) {
+            float g = coef == 0.f ? 0.f : coef * (__expf(to_f(src[i]) - lse) - (i == tg ? 1.f : 0.f));
+            dst[i] = from_f<T>(g);
+        }
+        if (a == sp.n_attr - 1)
+            for (int64_t i = sp.seg[sp.n_attr] + lane; i < ld; i += 32) dlogits[t * ld + i] = from_f<T>(0.f);
+    }
+}
+
+int fill_seg(SegParams &sp, const int *seg, int n_attr, int64_t ld, const float *temperature, const float *top_p) {
+    CPM_REQUIRE(seg, CPM_ERR_NULL, "heads: seg_host is NULL");
+    CPM_REQUIRE(n_attr >= 1 && n_attr <= CPM_MAX_ATTR, CPM_ERR_BAD_SHAPE, "heads: n_attr=%d out of [1,%d]", n_attr, CPM_MAX_ATTR);
+    sp.n_attr = n_attr;
+    for (int a = 0; a <= n_attr; ++a) sp.seg[a] = seg[a];
+    for (int a = 0; a < n_attr; ++a) {
+        const int w = seg[a + 1] - seg[a];
+        CPM_REQUIRE(w >= 1 && w <= MAX_SEG, CPM_ERR_BAD_SHAPE, "heads: segment %d width %d out of [1,%d]", a, w, MAX_SEG);
+        sp.temperature[a] = temperature ? temperature[a] : 1.f;
+        sp.top_p[a] = top_p ? top_p[a] : 0.f;
+        CPM_REQUIRE(sp.temperature[a] > 0.f, CPM_ERR_BAD_SHAPE, "heads: temperature[%d]=%f must be > 0", a, sp.temperature[a]);
+    }
+    CPM_REQUIRE(seg[0] >= 0 && (int64_t)seg[n_attr] <= ld, CPM_ERR_BAD_SHAPE, "heads: segments [%d,%d) exceed row stride %lld", seg[0], seg[n_attr], (long long)ld);
+    return CPM_OK;
+}
+
+inline int warp_grid(int64_t items) {
+    int64_t b = (items + WARPS - 1) / WARPS;
+    int64_t cap = (int64_t)num_sms() * 16;
+    if (b > cap) b = cap;
+    return (int)(b < 1 ? 1 : b);
+}
+
+}  // namespace
+}  // namespace cpm
+
+using namespace cpm;
+
+#define DISPATCH_DTYPE(dtype, ...)                                              \
+    if ((dtype) == CPM_F32) { using T = float; __VA_ARGS__; }                   \
+    else if ((dtype) == CPM_BF16) { using T = __nv_bfloat16; __VA_ARGS__; }     \
+    else return fail(CPM_ERR_BAD_DTYPE, "unsupported dtype %d", (int)(dtype));
+
+extern "C" {
+
+int cpm_heads_sample(const void *logits, int64_t rows, int64_t ld_logits, const int *seg_host, int n_attr,
+                     const float *temperature_host, const float *top_p_host, int mode, uint64_t seed, int64_t seq_base, int step,
+                     const int32_t *step_dev, int64_t *tokens, float *logp, float *entropy, int dtype, void *stream) {
+    CPM_REQUIRE(logits && tokens, CPM_ERR_NULL, "heads_sample: NULL pointer");
+    CPM_REQUIRE(mode == 0 || mode == 1, CPM_ERR_BAD_SHAPE, "heads_sample: mode %d", mode);
+    SegParams sp{};
+    int rc = fill_seg(sp, seg_host, n_attr, ld_logits, temperature_host, top_p_host);
+    if (rc) return rc;
+    if (rows <= 0) return rows == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "heads_sample: rows=%lld", (long long)rows);
+    DISPATCH_DTYPE(dtype, heads_sample_kernel<T><<<warp_grid(rows * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                              (const T *)logits, rows, ld_logits, sp, mode, seed, seq_base, step, step_dev, tokens, logp, entropy));
+    return check_launch("heads_sample");
+}
+
+int cpm_heads_logp(const void *logits, int64_t rows, int64_t ld_logits, const int *seg_host, int n_attr, const int64_t *tokens,
+                   float *logp, float *entropy, int dtype, void *stream) {
+    CPM_REQUIRE(logits && tokens && (logp || entropy), CPM_ERR_NULL, "heads_logp: NULL pointer");
+    SegParams sp{};
+    int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
+    if (rc) return rc;
+    if (rows <= 0) return rows == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "heads_logp: rows=%lld", (long long)rows);
+    DISPATCH_DTYPE(dtype, heads_logp_kernel<T><<<warp_grid(rows * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                              (const T *)logits, rows, ld_logits, sp, tokens, logp, entropy));
+    return check_launch("heads_logp");
+}
+
+int cpm_heads_logp_bwd(const void *logits, int64_t rows, int64_t ld_logits, const int *seg_host, int n_attr, const int64_t *tokens,
+                       const float *glogp, const float *gentropy, void *dlogits, int dtype, void *stream) {
+    CPM_REQUIRE(logits && tokens && dlogits, CPM_ERR_NULL, "heads_logp_bwd: NULL pointer");
+    SegParams sp{};
+    int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
+    if (rc) return rc;
+    if (rows <= 0) return rows == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "heads_logp_bwd: rows=%lld", (long long)rows);
+    DISPATCH_DTYPE(dtype, heads_logp_bwd_kernel<T><<<warp_grid(rows * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                              (const T *)logits, rows, ld_logits, sp, tokens, glogp, gentropy, (T *)dlogits));
+    return check_launch("heads_logp_bwd");
+}
+
+int cpm_masked_ce_fwd(const void *logits, int64_t T_, int64_t ld_logits, const int *seg_host, int n_attr, const int64_t *targets,
+                      const float *mask, float *loss_num, float *mask_sum, float *lse, int dtype, void *stream) {
+    CPM_REQUIRE(logits && targets && mask && loss_num, CPM_ERR_NULL, "masked_ce_fwd: NULL pointer");
+    SegParams sp{};
+    int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
+    if (rc) return rc;
+    if (T_ <= 0) return T_ == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "masked_ce_fwd: T=%lld", (long long)T_);
+    DISPATCH_DTYPE(dtype, masked_ce_fwd_kernel<T><<<warp_grid(T_ * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                              (const T *)logits, T_, ld_logits, sp, targets, mask, loss_num, mask_sum, lse));
+    return check_launch("masked_ce_fwd");
+}
+
+int cpm_masked_ce_bwd(const void *logits, int64_t T_, int64_t ld_logits, const int *seg_host, int n_attr, const int64_t *targets,
+                      const float *mask, const float *lse, const float *gscale, const float *denom, void *dlogits, int dtype,
+                      void *stream) {
+    CPM_REQUIRE(logits && targets && mask && lse && gscale && denom && dlogits, CPM_ERR_NULL, "masked_ce_bwd: NULL pointer");
+    SegParams sp{};
+    int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
+    if (rc) return rc;
+    if (T_ <= 0) return T_ == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "masked_ce_bwd: T=%lld", (long long)T_);
+    DISPATCH_DTYPE(dtype, masked_ce_bwd_kernel<T><<<warp_grid(T_ * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                              (const T *)logits, T_, ld_logits, sp, targets, mask, lse, gscale, denom, (T *)dlogits));
+    return check_launch("masked_ce_bwd");
+}
+
+}  // extern "C"
