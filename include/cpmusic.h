@@ -243,6 +243,13 @@ int cpm_dqn_td_fwd_bwd(const void *q_logits, const void *next_logits, const int6
                        int n_attr, int A, float gamma, float grad_scale, int mode, int dtype,
                        void *stream);
 
+/* Rollout bookkeeping for graph-captured generation (device-side step counter):
+ *   history_tok[step*n_tok + i] = tokens[i] ; history_f[step*n_f + i] = vals[i] (optional pair);
+ *   then *step_dev += 1.  Nothing is written once *step_dev >= max_steps.  Single CTA. */
+int cpm_rollout_advance(const int64_t *tokens, int64_t *history_tok, int64_t n_tok, const float *vals,
+                        float *history_f, int64_t n_f, int32_t *step_dev, int32_t max_steps,
+                        void *stream);
+
 #ifdef __cplusplus
 }
 #endif

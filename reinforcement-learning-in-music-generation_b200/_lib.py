@@ -1,0 +1,119 @@
+"""ctypes binding of libcpmusic.so (the C-ABI declared in include/cpmusic.h).
+
+There is NO CPU fallback: if the library is missing or cannot be loaded every
+compute entry point raises.  ``load()`` is lazy so that importing the package on
+a CPU-only box (module definitions, state_dict handling, tests that only check
+exported symbols) works.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libcpmusic.so")
+
+F32, BF16 = 0, 1
+RET_COMPAT, RET_TOGO, RET_GAE = 0, 1, 2
+PPO_COMPAT, PPO_STANDARD = 0, 1
+TD_COMPAT, TD_STANDARD = 0, 1
+MAX_ATTR = 8
+
+ERR_NAMES = {0: "CPM_OK", -1: "CPM_ERR_BAD_SHAPE", -2: "CPM_ERR_BAD_ALIGN", -3: "CPM_ERR_BAD_DTYPE",
+             -4: "CPM_ERR_NULL", -5: "CPM_ERR_WORKSPACE", -6: "CPM_ERR_CUDA", -7: "CPM_ERR_UNSUPPORTED"}
+
+_P = c_void_p
+_FPP = POINTER(c_void_p)
+_IP = POINTER(c_int)
+_FP = POINTER(c_float)
+
+# name -> (restype, argtypes); mirrors include/cpmusic.h one to one
+SIGNATURES = {
+    "cpm_version": (c_int, []),
+    "cpm_last_error_string": (c_char_p, []),
+    "cpm_error_name": (c_char_p, [c_int]),
+    "cpm_linattn_last_impl": (c_char_p, []),
+    "cpm_linattn_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
+    "cpm_linattn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
+                                c_int, c_float, c_int, _P, c_int64, _P]),
+    "cpm_linattn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
+                                c_int64, c_int64, c_int64, c_int, c_float, c_int, _P, c_int64, _P]),
+    "cpm_linattn_step": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
+                                 c_int, c_float, _P]),
+    "cpm_embed_fwd": (c_int, [_P, _FPP, _IP, _IP, c_int, c_int64, _P, c_int, _P, _P]),
+    "cpm_embed_bwd": (c_int, [_P, _P, _FPP, _IP, _IP, c_int, c_int64, c_int, _P]),
+    "cpm_add_pe": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P]),
+    "cpm_dropout": (c_int, [_P, _P, c_int64, c_float, c_uint64, c_uint64, c_int, _P]),
+    "cpm_ln_residual_fwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float, c_float,
+                                    c_uint64, c_uint64, c_int, _P]),
+    "cpm_ln_partials_rows": (c_int, []),
+    "cpm_ln_residual_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int, c_float,
+                                    c_uint64, c_uint64, c_int, _P]),
+    "cpm_gelu_fwd": (c_int, [_P, _P, _P, c_int64, c_int, c_float, c_uint64, c_uint64, c_int, _P]),
+    "cpm_gelu_bwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_float, c_uint64, c_uint64, c_int, _P]),
+    "cpm_heads_sample": (c_int, [_P, c_int64, c_int64, _IP, c_int, _FP, _FP, c_int, c_uint64, c_int64, c_int,
+                                 _P, _P, _P, _P, c_int, _P]),
+    "cpm_heads_logp": (c_int, [_P, c_int64, c_int64, _IP, c_int, _P, _P, _P, c_int, _P]),
+    "cpm_heads_logp_bwd": (c_int, [_P, c_int64, c_int64, _IP, c_int, _P, _P, _P, _P, c_int, _P]),
+    "cpm_masked_ce_fwd": (c_int, [_P, c_int64, c_int64, _IP, c_int, _P, _P, _P, _P, _P, c_int, _P]),
+    "cpm_masked_ce_bwd": (c_int, [_P, c_int64, c_int64, _IP, c_int, _P, _P, _P, _P, _P, _P, c_int, _P]),
+    "cpm_returns_scan": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_float, c_float, c_int, _P]),
+    "cpm_moments": (c_int, [_P, _P, c_int64, _P, _P]),
+    "cpm_zscore": (c_int, [_P, _P, _P, c_int64, _P, c_int, c_float, _P]),
+    "cpm_ppo_loss_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int64, c_int64, c_int64,
+                                     c_float, c_float, c_float, c_float, c_int, _P]),
+    "cpm_dqn_td_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, _IP, c_int, c_int,
+                                   c_float, c_float, c_int, c_int, _P]),
+    "cpm_rollout_advance": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int32, _P]),
+}
+
+_lib = None
+
+
+class CpmError(RuntimeError):
+    """A libcpmusic entry point returned a negative code."""
+
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"{ERR_NAMES.get(code, code)}: {msg}")
+        self.code = code
+
+
+def load() -> ctypes.CDLL:
+    """Load libcpmusic.so or raise — never falls back to a CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise RuntimeError(
+                f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (or "
+                f"`python {os.path.join(_HERE, 'build.py')}`); this package has no CPU fallback.")
+        lib = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(lib, name)      # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+        _lib = lib
+    return _lib
+
+
+def check(rc: int) -> None:
+    """Map an error code to the exception type the reference stack would raise
+    (SURVEY §8b): shape/dtype problems -> ValueError, the rest -> RuntimeError."""
+    if rc == 0:
+        return
+    msg = load().cpm_last_error_string().decode()
+    if rc in (-1, -3):
+        raise ValueError(f"{ERR_NAMES.get(rc, rc)}: {msg}")
+    raise CpmError(rc, msg)
+
+
+def int_array(vals):
+    return (c_int * len(vals))(*[int(v) for v in vals])
+
+
+def float_array(vals):
+    return (c_float * len(vals))(*[float(v) for v in vals])
+
+
+def ptr_array(ptrs):
+    return (c_void_p * len(ptrs))(*[int(p) for p in ptrs])

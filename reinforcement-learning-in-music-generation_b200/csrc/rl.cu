@@ -231,6 +231,18 @@ __global__ void __launch_bounds__(256) dqn_td_kernel(const T *__restrict__ q_log
     if (threadIdx.x == 0) atomicAdd(&out[0], tot * inv);
 }
 
+__global__ void __launch_bounds__(256) rollout_advance_kernel(const int64_t *__restrict__ tokens, int64_t *__restrict__ htok, int64_t n_tok,
+                                                              const float *__restrict__ vals, float *__restrict__ hf, int64_t n_f,
+                                                              int32_t *step_dev, int32_t max_steps) {
+    const int32_t step = *step_dev;
+    if (step < max_steps) {
+        if (htok) for (int64_t i = threadIdx.x; i < n_tok; i += blockDim.x) htok[(int64_t)step * n_tok + i] = tokens[i];
+        if (hf) for (int64_t i = threadIdx.x; i < n_f; i += blockDim.x) hf[(int64_t)step * n_f + i] = vals[i];
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) *step_dev = step + 1;
+}
+
 inline int blocks_for(int64_t n, int threads) {
     int64_t b = (n + threads - 1) / threads;
     int64_t cap = (int64_t)num_sms() * 8;
@@ -320,6 +332,15 @@ int cpm_dqn_td_fwd_bwd(const void *q_logits, const void *next_logits, const int6
         dqn_td_kernel<__nv_bfloat16><<<B, 256, smem, st>>>((const __nv_bfloat16 *)q_logits, (const __nv_bfloat16 *)next_logits, action, reward,
                                                            done, out, (__nv_bfloat16 *)dq, targets_out, B, L, ld, tp, A, gamma, grad_scale, mode);
     return check_launch("dqn_td");
+}
+
+int cpm_rollout_advance(const int64_t *tokens, int64_t *history_tok, int64_t n_tok, const float *vals, float *history_f, int64_t n_f,
+                        int32_t *step_dev, int32_t max_steps, void *stream) {
+    CPM_REQUIRE(step_dev, CPM_ERR_NULL, "rollout_advance: step_dev is NULL");
+    CPM_REQUIRE(!history_tok || tokens, CPM_ERR_NULL, "rollout_advance: tokens is NULL");
+    CPM_REQUIRE(!history_f || vals, CPM_ERR_NULL, "rollout_advance: vals is NULL");
+    rollout_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(tokens, history_tok, n_tok, vals, history_f, n_f, step_dev, max_steps);
+    return check_launch("rollout_advance");
 }
 
 }  // extern "C"

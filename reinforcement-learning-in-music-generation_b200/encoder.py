@@ -1,0 +1,259 @@
+"""fast_transformers-shaped causal-linear encoder running on the cpmusic kernels.
+
+Mirrors the plugin interface the reference builds through
+``TransformerEncoderBuilder.from_kwargs(...).get()`` / ``RecurrentEncoderBuilder``
+(reference dqn_policy/model.py:128-150, agent_pretrain.py:244-266,
+ppo_policy/model.py:129-151,313-321): same constructor kwargs, same submodule and
+parameter names (``layers.{i}.attention.{query,key,value,out}_projection``, ``linear1``,
+``linear2``, ``norm1``, ``norm2``, final ``norm`` — SURVEY App. A.3), same call signatures
+(``forward(x, attn_mask, length_mask)`` and ``forward(x, state=None, memory=None) -> (y, state)``)
+and the same error behaviour (RuntimeError for a non-causal mask, ValueError when the batch size
+changes between recurrent steps).
+
+Per layer (post-norm, exact-erf GELU):  fused QKV GEMM → chunked causal linear attention kernel
+→ out-proj GEMM → fused residual+dropout+LayerNorm → FFN1 GEMM → fused GELU+dropout → FFN2 GEMM →
+fused residual+dropout+LayerNorm.  fp32 master parameters, bf16 (or fp32) compute copies cached
+and re-packed when a parameter changes.
+"""
+from __future__ import annotations
+
+from typing import List, Optional
+
+import torch
+import torch.nn as nn
+
+from . import ops
+
+
+class TriangularCausalMask:
+    """``fast_transformers.masking.TriangularCausalMask(N, device=)``: only the
+    ``lower_triangular`` flag is consulted by causal-linear attention."""
+
+    def __init__(self, N, device="cpu"):
+        self.N = N
+        self.device = device
+        self.lower_triangular = True
+
+
+class FullMask:
+    def __init__(self, N=None, M=None, device="cpu"):
+        self.N = N
+        self.device = device
+        self.lower_triangular = False
+
+
+class LengthMask:
+    def __init__(self, lengths, max_len=None, device=None):
+        self.lengths = lengths
+        self.max_len = max_len
+
+
+class PackCache:
+    """Compute-dtype packings of fp32 master parameters, rebuilt when a master changes."""
+
+    def __init__(self):
+        self._store = {}
+
+    def get(self, key, linears, dtype, pad_rows_to: int = 1):
+        ws = [l.weight for l in linears]
+        bs = [l.bias for l in linears]
+        stamp = tuple((p.data_ptr(), p._version) for p in ws + bs) + (dtype,)
+        hit = self._store.get(key)
+        if hit is not None and hit[0] == stamp:
+            return hit[1]
+        with torch.no_grad():
+            rows = [int(w.shape[0]) for w in ws]
+            total = sum(rows)
+            padded = -(-total // pad_rows_to) * pad_rows_to
+            if len(ws) == 1 and padded == total:
+                wc = ws[0].detach().to(dtype).contiguous()
+                bc = bs[0].detach().to(dtype).contiguous()
+            else:
+                wc = torch.zeros(padded, ws[0].shape[1], dtype=dtype, device=ws[0].device)
+                bc = torch.zeros(padded, dtype=dtype, device=ws[0].device)
+                r0 = 0
+                for w, b in zip(ws, bs):
+                    wc[r0:r0 + w.shape[0]] = w
+                    bc[r0:r0 + w.shape[0]] = b
+                    r0 += w.shape[0]
+        packed = (wc, bc, tuple(rows), tuple(ws + bs))
+        self._store[key] = (stamp, packed)
+        return packed
+
+    def clear(self):
+        self._store.clear()
+
+
+def cached_linear(cache: PackCache, key, linears, x, dtype, pad_rows_to=1):
+    wc, bc, rows, masters = cache.get(key, linears, dtype, pad_rows_to)
+    return ops.packed_linear(x, wc, bc, rows, masters)
+
+
+class AttentionLayer(nn.Module):
+    def __init__(self, d_model, n_heads, d_keys=None, d_values=None):
+        super().__init__()
+        d_keys = d_keys or d_model // n_heads
+        d_values = d_values or d_model // n_heads
+        if d_keys != 64 or d_values != 64:
+            raise ValueError("cpmusic kernels implement query_dimensions = value_dimensions = 64 (the reference's)")
+        self.n_heads = n_heads
+        self.query_projection = nn.Linear(d_model, d_keys * n_heads)
+        self.key_projection = nn.Linear(d_model, d_keys * n_heads)
+        self.value_projection = nn.Linear(d_model, d_values * n_heads)
+        self.out_projection = nn.Linear(d_values * n_heads, d_model)
+
+
+class TransformerEncoderLayer(nn.Module):
+    def __init__(self, d_model, n_heads, d_ff, dropout=0.1):
+        super().__init__()
+        self.attention = AttentionLayer(d_model, n_heads)
+        self.linear1 = nn.Linear(d_model, d_ff)
+        self.linear2 = nn.Linear(d_ff, d_model)
+        self.norm1 = nn.LayerNorm(d_model)
+        self.norm2 = nn.LayerNorm(d_model)
+        self.dropout = nn.Dropout(dropout)
+
+
+class TransformerEncoder(nn.Module):
+    """Parallel (teacher-forced) causal-linear encoder."""
+
+    def __init__(self, n_layers=12, n_heads=8, query_dimensions=64, value_dimensions=64,
+                 feed_forward_dimensions=2048, dropout=0.1, compute_dtype=torch.bfloat16):
+        super().__init__()
+        if query_dimensions != 64 or value_dimensions != 64:
+            raise ValueError("cpmusic kernels implement query_dimensions = value_dimensions = 64")
+        d_model = value_dimensions * n_heads
+        self.d_model, self.n_heads = d_model, n_heads
+        self.layers = nn.ModuleList([
+            TransformerEncoderLayer(d_model, n_heads, feed_forward_dimensions, dropout) for _ in range(n_layers)])
+        self.norm = nn.LayerNorm(d_model)
+        self.compute_dtype = compute_dtype
+        self.attn_impl = 0            # 0 auto | 1 simt | 2 tcgen05  (cpm_linattn_fwd `impl`)
+        self._cache = PackCache()
+
+    # ---- fused path used by the CP model (stays in compute dtype) -------------------------
+    def _layer(self, i, layer, x):
+        p = layer.dropout.p if self.training else 0.0
+        dt, c, at = self.compute_dtype, self._cache, layer.attention
+        qkv = cached_linear(c, ("qkv", i), [at.query_projection, at.key_projection, at.value_projection], x, dt)
+        a = ops.causal_linear_attention_fused(qkv, self.n_heads, ops.EPS_ATTN, self.attn_impl)
+        o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
+        x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
+        h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)
+        g = ops.gelu_dropout(h, p)
+        f = cached_linear(c, ("ff2", i), [layer.linear2], g, dt)
+        return ops.ln_residual(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p)
+
+    def forward_fused(self, x):
+        """x (N,L,d) in compute dtype -> (N,L,d) in compute dtype."""
+        for i, layer in enumerate(self.layers):
+            x = self._layer(i, layer, x)
+        return ops.ln_residual(x, None, self.norm.weight, self.norm.bias, self.norm.eps, 0.0)
+
+    # ---- ft signature ------------------------------------------------------------------------
+    def forward(self, x, attn_mask=None, length_mask=None):
+        if attn_mask is None or not getattr(attn_mask, "lower_triangular", False):
+            raise RuntimeError("CausalLinearAttention only supports full lower triangular masks")
+        if length_mask is not None:
+            raise NotImplementedError("length_mask is never passed by the reference (SURVEY App. A.1); not implemented")
+        return self.forward_fused(x.to(self.compute_dtype)).to(x.dtype)
+
+    def _apply(self, fn, *a, **k):
+        self._cache.clear()
+        return super()._apply(fn, *a, **k)
+
+
+class RecurrentTransformerEncoder(TransformerEncoder):
+    """One-token-per-call encoder.  ``state`` is a list (one entry per layer) of
+    ``[Si (N,H,64,64) fp32, Zi (N,H,64) fp32]`` updated in place; ``memory`` is ft's deprecated
+    alias and the keyword the reference uses (dqn_policy/model.py:237)."""
+
+    def new_state(self, N, device):
+        H = self.n_heads
+        return [[torch.zeros(N, H, 64, 64, dtype=torch.float32, device=device),
+                 torch.zeros(N, H, 64, dtype=torch.float32, device=device)] for _ in self.layers]
+
+    def _step_layer(self, i, layer, x, st):
+        p = layer.dropout.p if self.training else 0.0
+        dt, c, at, H = self.compute_dtype, self._cache, layer.attention, self.n_heads
+        qkv = cached_linear(c, ("qkv", i), [at.query_projection, at.key_projection, at.value_projection], x, dt)
+        N = qkv.shape[0]
+        q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
+        a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * 64)
+        o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
+        x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
+        h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)
+        g = ops.gelu_dropout(h, p)
+        f = cached_linear(c, ("ff2", i), [layer.linear2], g, dt)
+        return ops.ln_residual(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p)
+
+    def step_fused(self, x, state):
+        """x (N,d) compute dtype; state as above (allocated when None)."""
+        if state is None:
+            state = self.new_state(x.shape[0], x.device)
+        for i, layer in enumerate(self.layers):
+            if state[i] is None:
+                state[i] = self.new_state(x.shape[0], x.device)[0]
+            x = self._step_layer(i, layer, x, state[i])
+        return ops.ln_residual(x, None, self.norm.weight, self.norm.bias, self.norm.eps, 0.0), state
+
+    def forward(self, x, state=None, memory=None):
+        state = state if state is not None else memory
+        with torch.no_grad():       # the recurrent kernels update state in place (ft does so under no_grad)
+            y, state = self.step_fused(x.to(self.compute_dtype), state)
+        return y.to(x.dtype), state
+
+
+class _Builder:
+    _cls = TransformerEncoder
+    _known = ("n_layers", "n_heads", "query_dimensions", "value_dimensions", "feed_forward_dimensions", "dropout")
+
+    def __init__(self, **kw):
+        self.kw = kw
+
+    @classmethod
+    def from_kwargs(cls, **kw):
+        return cls(**kw)
+
+    def get(self):
+        kw = dict(self.kw)
+        attention_type = kw.pop("attention_type", "full")
+        if attention_type != "causal-linear":
+            raise ValueError(f"cpmusic implements attention_type='causal-linear' only (got {attention_type!r})")
+        activation = kw.pop("activation", "relu")
+        if activation != "gelu":
+            raise ValueError(f"cpmusic implements activation='gelu' only (got {activation!r})")
+        unknown = set(kw) - set(self._known) - {"compute_dtype"}
+        if unknown:
+            raise ValueError(f"unsupported builder arguments: {sorted(unknown)}")
+        return self._cls(**kw)
+
+
+class TransformerEncoderBuilder(_Builder):
+    _cls = TransformerEncoder
+
+
+class RecurrentEncoderBuilder(_Builder):
+    _cls = RecurrentTransformerEncoder
+
+
+def install_fast_transformers_shim():
+    """Register ``fast_transformers.builders`` / ``fast_transformers.masking`` in sys.modules so the
+    unmodified reference model files import this encoder (``from fast_transformers.builders import
+    TransformerEncoderBuilder`` — dqn_policy/model.py:9-11)."""
+    import sys
+    import types
+    pkg = types.ModuleType("fast_transformers")
+    builders = types.ModuleType("fast_transformers.builders")
+    masking = types.ModuleType("fast_transformers.masking")
+    builders.TransformerEncoderBuilder = TransformerEncoderBuilder
+    builders.RecurrentEncoderBuilder = RecurrentEncoderBuilder
+    masking.TriangularCausalMask = TriangularCausalMask
+    masking.FullMask = FullMask
+    masking.LengthMask = LengthMask
+    pkg.builders, pkg.masking = builders, masking
+    pkg.__path__ = []
+    sys.modules["fast_transformers"] = pkg
+    sys.modules["fast_transformers.builders"] = builders
+    sys.modules["fast_transformers.masking"] = masking
+    return pkg

@@ -1,0 +1,617 @@
+"""torch-facing wrappers of the libcpmusic C-ABI (include/cpmusic.h).
+
+Every function here launches hand-written sm_100a kernels through ctypes on the
+current torch CUDA stream; torch only owns memory and streams.  Plain dense
+GEMMs (the Linear layers) are the one thing delegated to the vendor library
+(cuBLASLt through ``torch.addmm``/``torch.mm``).  Nothing falls back to the CPU:
+tensors must be CUDA tensors and the library must be loadable.
+"""
+from __future__ import annotations
+
+import math
+from typing import List, Optional, Sequence, Tuple
+
+import torch
+
+from . import _lib
+from ._lib import check
+
+EPS_ATTN = 1e-6     # ft CausalLinearAttention eps
+EPS_LN = 1e-5       # torch.nn.LayerNorm default used by ft
+
+
+# --------------------------------------------------------------------------- helpers
+def _dt(t: torch.Tensor) -> int:
+    if t.dtype == torch.float32:
+        return _lib.F32
+    if t.dtype == torch.bfloat16:
+        return _lib.BF16
+    raise ValueError(f"cpmusic kernels take float32 or bfloat16 activations, got {t.dtype}")
+
+
+def _cuda(*ts):
+    for t in ts:
+        if t is not None and not t.is_cuda:
+            raise RuntimeError("cpmusic ops need CUDA tensors: there is no CPU fallback "
+                               "(the CPU restatement lives in oracle/ and is test-only)")
+
+
+def _st() -> int:
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _p(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class _Rng:
+    """Counter-based dropout RNG state: (seed, running offset in units of 8 elements)."""
+    seed = 0x5EED
+    offset = 0
+
+    @classmethod
+    def take(cls, n_elems: int) -> Tuple[int, int]:
+        off = cls.offset
+        cls.offset += (n_elems + 7) // 8
+        return cls.seed, off
+
+
+def manual_seed(seed: int) -> None:
+    _Rng.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
+    _Rng.offset = 0
+
+
+# --------------------------------------------------------------------------- linear attention
+def linattn_workspace(N: int, L: int, H: int, device) -> torch.Tensor:
+    nbytes = _lib.load().cpm_linattn_workspace_bytes(N, L, H)
+    return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+
+
+def _check_qkv_layout(q, k, v):
+    N, L, H, E = q.shape
+    for t in (q, k, v):
+        if t.shape != q.shape or t.stride(3) != 1 or t.stride(2) != E or t.stride(0) != L * t.stride(1):
+            raise ValueError("q,k,v must be (N,L,H,E) with E contiguous, heads packed and a common token stride")
+    if not (q.stride(1) == k.stride(1) == v.stride(1)):
+        raise ValueError("q,k,v must share one token stride")
+    return N, L, H, E, q.stride(1)
+
+
+def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True):
+    """q,k,v: (N,L,H,64) views (may be column slices of one fused QKV buffer)."""
+    _cuda(q, k, v)
+    N, L, H, E, ld = _check_qkv_layout(q, k, v)
+    out = torch.empty(N, L, H, E, dtype=q.dtype, device=q.device)
+    den = torch.empty(N, L, H, dtype=torch.float32, device=q.device) if need_den else None
+    ws = linattn_workspace(N, L, H, q.device)
+    check(_lib.load().cpm_linattn_fwd(_p(q), _p(k), _p(v), _p(out), _p(den), N, L, H, E, E, ld, H * E,
+                                      _dt(q), eps, impl, _p(ws), ws.numel(), _st()))
+    return out, den
+
+
+def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0):
+    N, L, H, E, ld = _check_qkv_layout(q, k, v)
+    _, _, _, _, ldg = _check_qkv_layout(gq, gk, gv)
+    gout = gout.contiguous()
+    ws = linattn_workspace(N, L, H, q.device)
+    check(_lib.load().cpm_linattn_bwd(_p(q), _p(k), _p(v), _p(out), _p(den), _p(gout), _p(gq), _p(gk), _p(gv),
+                                      N, L, H, E, E, ld, H * E, ldg, _dt(q), eps, impl, _p(ws), ws.numel(), _st()))
+
+
+class _LinAttnFused(torch.autograd.Function):
+    """qkv (N,L,3*H*64) fused projection output -> (N,L,H*64)."""
+
+    @staticmethod
+    def forward(ctx, qkv, H, eps, impl):
+        N, L, W = qkv.shape
+        E = W // (3 * H)
+        qkv = qkv.contiguous()
+        q, k, v = (qkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
+        out, den = linattn_fwd_raw(q, k, v, eps, impl)
+        ctx.save_for_backward(qkv, out, den)
+        ctx.cfg = (H, E, eps, impl)
+        return out.view(N, L, H * E)
+
+    @staticmethod
+    def backward(ctx, gout):
+        qkv, out, den = ctx.saved_tensors
+        H, E, eps, impl = ctx.cfg
+        N, L, W = qkv.shape
+        q, k, v = (qkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
+        gqkv = torch.empty_like(qkv)
+        gq, gk, gv = (gqkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
+        linattn_bwd_raw(q, k, v, out, den, gout.reshape(N, L, H, E), gq, gk, gv, eps, impl)
+        return gqkv, None, None, None
+
+
+class _LinAttn(torch.autograd.Function):
+    """Separate q,k,v (N,L,H,64) -> (N,L,H,64) (the ft CausalLinearAttention signature)."""
+
+    @staticmethod
+    def forward(ctx, q, k, v, eps, impl):
+        q, k, v = q.contiguous(), k.contiguous(), v.contiguous()
+        out, den = linattn_fwd_raw(q, k, v, eps, impl)
+        ctx.save_for_backward(q, k, v, out, den)
+        ctx.cfg = (eps, impl)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        q, k, v, out, den = ctx.saved_tensors
+        eps, impl = ctx.cfg
+        gq, gk, gv = torch.empty_like(q), torch.empty_like(k), torch.empty_like(v)
+        linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps, impl)
+        return gq, gk, gv, None, None
+
+
+def causal_linear_attention(q, k, v, eps=EPS_ATTN, impl=0):
+    return _LinAttn.apply(q, k, v, eps, impl)
+
+
+def causal_linear_attention_fused(qkv, n_heads, eps=EPS_ATTN, impl=0):
+    return _LinAttnFused.apply(qkv, n_heads, eps, impl)
+
+
+def linattn_last_impl() -> str:
+    return _lib.load().cpm_linattn_last_impl().decode()
+
+
+def linattn_step(q, k, v, S, Z, eps=EPS_ATTN):
+    """Recurrent step. q,k,v: (N,H,64) views sharing a row stride; S (N,H,64,64), Z (N,H,64) fp32
+    are updated in place; returns (N,H,64)."""
+    _cuda(q, k, v, S, Z)
+    N, H, E = q.shape
+    ld = q.stride(0)
+    if not (k.stride(0) == ld and v.stride(0) == ld and q.stride(2) == 1 and q.stride(1) == E):
+        raise ValueError("q,k,v must be (N,H,E) with a common row stride and packed heads")
+    if S.shape[0] != N:
+        raise ValueError("The batch size changed during iteration")     # ft's message
+    if S.dtype != torch.float32 or Z.dtype != torch.float32 or not S.is_contiguous() or not Z.is_contiguous():
+        raise ValueError("recurrent state must be contiguous float32")
+    out = torch.empty(N, H, E, dtype=q.dtype, device=q.device)
+    check(_lib.load().cpm_linattn_step(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), N, H, E, E, ld, H * E,
+                                       _dt(q), eps, _st()))
+    return out
+
+
+# --------------------------------------------------------------------------- dense linear (vendor GEMM)
+def _mm_f32_out(a, b):
+    """a @ b with fp32 output (bf16 inputs accumulate in fp32 inside cuBLAS either way)."""
+    if a.dtype == torch.float32:
+        return a @ b
+    try:
+        return torch.mm(a, b, out_dtype=torch.float32)
+    except (TypeError, RuntimeError):
+        return (a @ b).float()
+
+
+class _PackedLinear(torch.autograd.Function):
+    """y = x @ Wc^T + bc where (Wc, bc) is a cached compute-dtype packing (row-concatenation,
+    optionally zero-padded) of several fp32 master weights/biases.  Gradients are routed back to
+    the masters as row slices."""
+
+    @staticmethod
+    def forward(ctx, x, wc, bc, rows, *masters):
+        x2 = x.reshape(-1, x.shape[-1])
+        y = torch.addmm(bc, x2, wc.t()) if bc is not None else x2 @ wc.t()
+        ctx.save_for_backward(x2, wc)
+        ctx.rows = rows
+        ctx.n_w = len(rows)
+        ctx.has_bias = bc is not None
+        ctx.xshape = x.shape
+        ctx.master_dtype = masters[0].dtype
+        return y.view(*x.shape[:-1], wc.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        x2, wc = ctx.saved_tensors
+        gy2 = gy.reshape(-1, gy.shape[-1])
+        gx = (gy2 @ wc).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        gw = _mm_f32_out(gy2.t(), x2)
+        gb = gy2.sum(0, dtype=torch.float32) if ctx.has_bias else None
+        grads, r0 = [], 0
+        for r in ctx.rows:
+            grads.append(gw[r0:r0 + r])
+            r0 += r
+        if ctx.has_bias:
+            r0 = 0
+            for r in ctx.rows:
+                grads.append(gb[r0:r0 + r])
+                r0 += r
+        return (gx, None, None, None, *grads)
+
+
+def packed_linear(x, wc, bc, rows, masters):
+    return _PackedLinear.apply(x, wc, bc, tuple(rows), *masters)
+
+
+# --------------------------------------------------------------------------- embedding
+def _embed_meta(tables):
+    n_tok = [int(t.shape[0]) for t in tables]
+    emb = [int(t.shape[1]) for t in tables]
+    return n_tok, emb
+
+
+def embed_fwd_raw(idx, tables, dtype):
+    _cuda(idx, *tables)
+    idx = idx.contiguous()
+    if idx.dtype != torch.int64:
+        raise ValueError("token indices must be int64 (.long()), like the reference")
+    n_attr = idx.shape[-1]
+    if n_attr != len(tables):
+        raise ValueError(f"idx has {n_attr} attributes but {len(tables)} tables were given")
+    for t in tables:
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise ValueError("embedding tables must be contiguous float32")
+    n_tok, emb = _embed_meta(tables)
+    T = idx.numel() // n_attr
+    out = torch.empty(*idx.shape[:-1], sum(emb), dtype=dtype, device=idx.device)
+    err = torch.zeros(1, dtype=torch.int32, device=idx.device)
+    check(_lib.load().cpm_embed_fwd(_p(idx), _lib.ptr_array([t.data_ptr() for t in tables]), _lib.int_array(n_tok),
+                                    _lib.int_array(emb), n_attr, T, _p(out), _dt(out), _p(err), _st()))
+    return out, err
+
+
+class _Embed(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, idx, dtype, *tables):
+        out, err = embed_fwd_raw(idx, tables, dtype)
+        ctx.save_for_backward(idx)
+        ctx.meta = [(t.shape, t.device) for t in tables]
+        ctx.err = err
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        (idx,) = ctx.saved_tensors
+        gout = gout.contiguous()
+        grads = [torch.zeros(s, dtype=torch.float32, device=d) for s, d in ctx.meta]
+        n_tok = [int(s[0]) for s, _ in ctx.meta]
+        emb = [int(s[1]) for s, _ in ctx.meta]
+        T = idx.numel() // len(grads)
+        check(_lib.load().cpm_embed_bwd(_p(idx.contiguous()), _p(gout), _lib.ptr_array([g.data_ptr() for g in grads]),
+                                        _lib.int_array(n_tok), _lib.int_array(emb), len(grads), T, _dt(gout), _st()))
+        return (None, None, *grads)
+
+
+def cp_embed(idx, tables, dtype=torch.bfloat16):
+    """CP gather: idx (...,A) int64, tables[a] (n_a, e_a) fp32 -> (..., sum e_a) * sqrt(e_a)."""
+    return _Embed.apply(idx, dtype, *tables)
+
+
+# --------------------------------------------------------------------------- PE / dropout
+class _AddPE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, pe, L, pos_offset, pos_dev, p_drop):
+        _cuda(x, pe)
+        x = x.contiguous()
+        d = x.shape[-1]
+        rows = x.numel() // d
+        pe2 = pe.reshape(-1, d)
+        seed, off = _Rng.take(x.numel()) if p_drop > 0 else (0, 0)
+        y = torch.empty_like(x)
+        check(_lib.load().cpm_add_pe(_p(x), _p(pe2), _p(y), rows, L, d, pos_offset, _p(pos_dev), pe2.shape[0],
+                                     p_drop, seed, off, _dt(x), _st()))
+        ctx.rng = (p_drop, seed, off)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        p_drop, seed, off = ctx.rng
+        if p_drop <= 0:
+            return gy, None, None, None, None, None
+        gy = gy.contiguous()
+        gx = torch.empty_like(gy)
+        check(_lib.load().cpm_dropout(_p(gy), _p(gx), gy.numel(), p_drop, seed, off, _dt(gy), _st()))
+        return gx, None, None, None, None, None
+
+
+def add_pe(x, pe, L, pos_offset=0, pos_dev=None, p_drop=0.0):
+    return _AddPE.apply(x, pe, L, pos_offset, pos_dev, p_drop)
+
+
+# --------------------------------------------------------------------------- residual + LayerNorm
+class _LNResidual(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, res, gamma, beta, eps, p_drop):
+        _cuda(x, gamma, beta)
+        x = x.contiguous()
+        res = res.contiguous() if res is not None else None
+        d = x.shape[-1]
+        rows = x.numel() // d
+        need = any(ctx.needs_input_grad[:4])
+        y = torch.empty_like(x)
+        s = torch.empty_like(x) if need else None
+        mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
+        rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
+        use_drop = p_drop > 0 and res is not None
+        seed, off = _Rng.take(x.numel()) if use_drop else (0, 0)
+        check(_lib.load().cpm_ln_residual_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(s), _p(mean), _p(rstd), rows, d,
+                                              eps, p_drop if use_drop else 0.0, seed, off, _dt(x), _st()))
+        if need:
+            ctx.save_for_backward(s, mean, rstd, gamma)
+        ctx.cfg = (p_drop if use_drop else 0.0, seed, off, res is not None)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        s, mean, rstd, gamma = ctx.saved_tensors
+        p_drop, seed, off, has_res = ctx.cfg
+        gy = gy.contiguous()
+        d = s.shape[-1]
+        rows = s.numel() // d
+        lib = _lib.load()
+        gs = torch.empty_like(s)
+        gres = torch.empty_like(s) if (has_res and p_drop > 0) else None
+        dgamma = torch.zeros(d, dtype=torch.float32, device=s.device)
+        dbeta = torch.zeros(d, dtype=torch.float32, device=s.device)
+        partials = torch.empty(lib.cpm_ln_partials_rows() * 2 * d, dtype=torch.float32, device=s.device)
+        check(lib.cpm_ln_residual_bwd(_p(gy), _p(s), _p(mean), _p(rstd), _p(gamma), _p(gs), _p(gres), _p(dgamma), _p(dbeta),
+                                      _p(partials), rows, d, p_drop, seed, off, _dt(s), _st()))
+        g_res = (gres if gres is not None else gs) if has_res else None
+        return gs, g_res, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None
+
+
+def ln_residual(x, res, gamma, beta, eps=EPS_LN, p_drop=0.0):
+    """LayerNorm(x + dropout(res)) with fp32 affine parameters."""
+    return _LNResidual.apply(x, res, gamma, beta, eps, p_drop)
+
+
+# --------------------------------------------------------------------------- GELU
+class _Gelu(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, p_drop):
+        _cuda(x)
+        x = x.contiguous()
+        d = x.shape[-1]
+        rows = x.numel() // d
+        seed, off = _Rng.take(x.numel()) if p_drop > 0 else (0, 0)
+        y = torch.empty_like(x)
+        check(_lib.load().cpm_gelu_fwd(_p(x), None, _p(y), rows, d, p_drop, seed, off, _dt(x), _st()))
+        ctx.save_for_backward(x)
+        ctx.rng = (p_drop, seed, off)
+        return y
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x,) = ctx.saved_tensors
+        p_drop, seed, off = ctx.rng
+        gy = gy.contiguous()
+        d = x.shape[-1]
+        gx = torch.empty_like(x)
+        check(_lib.load().cpm_gelu_bwd(_p(x), None, _p(gy), _p(gx), x.numel() // d, d, p_drop, seed, off, _dt(x), _st()))
+        return gx, None
+
+
+def gelu_dropout(x, p_drop=0.0):
+    """dropout(gelu(x)) with the exact-erf GELU ft uses (activation='gelu')."""
+    return _Gelu.apply(x, p_drop)
+
+
+# --------------------------------------------------------------------------- heads: decode / logp / CE
+def seg_offsets(n_token: Sequence[int]) -> List[int]:
+    seg = [0]
+    for n in n_token:
+        seg.append(seg[-1] + int(n))
+    return seg
+
+
+def heads_sample(logits, seg, temperature=None, top_p=None, greedy=True, seed=0, seq_base=0, step=0, step_dev=None,
+                 want_logp=False, want_entropy=False, tokens_out=None, logp_out=None):
+    """Decode every row of the concatenated logits (rows, ld). Returns (tokens int64 (rows,A), logp, entropy)."""
+    _cuda(logits)
+    ld = logits.shape[-1]
+    logits2 = logits.reshape(-1, ld)
+    if logits2.stride(-1) != 1:
+        logits2 = logits2.contiguous()
+    rows, A = logits2.shape[0], len(seg) - 1
+    tokens = tokens_out if tokens_out is not None else torch.empty(rows, A, dtype=torch.int64, device=logits.device)
+    logp = logp_out if logp_out is not None else (torch.empty(rows, A, dtype=torch.float32, device=logits.device) if want_logp else None)
+    ent = torch.empty(rows, A, dtype=torch.float32, device=logits.device) if want_entropy else None
+    t_arr = _lib.float_array(temperature if temperature is not None else [1.0] * A)
+    p_arr = _lib.float_array([0.0 if p is None else p for p in (top_p if top_p is not None else [None] * A)])
+    check(_lib.load().cpm_heads_sample(_p(logits2), rows, logits2.stride(0), _lib.int_array(seg), A, t_arr, p_arr,
+                                       0 if greedy else 1, seed, seq_base, step, _p(step_dev), _p(tokens), _p(logp), _p(ent),
+                                       _dt(logits2), _st()))
+    return tokens, logp, ent
+
+
+class _HeadsLogp(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, tokens, seg, want_entropy):
+        _cuda(logits, tokens)
+        ld = logits.shape[-1]
+        l2 = logits.reshape(-1, ld).contiguous()
+        tok = tokens.reshape(-1, len(seg) - 1).contiguous()
+        rows, A = tok.shape
+        logp = torch.empty(rows, A, dtype=torch.float32, device=logits.device)
+        ent = torch.empty(rows, A, dtype=torch.float32, device=logits.device) if want_entropy else None
+        check(_lib.load().cpm_heads_logp(_p(l2), rows, ld, _lib.int_array(seg), A, _p(tok), _p(logp), _p(ent), _dt(l2), _st()))
+        ctx.save_for_backward(l2, tok)
+        ctx.cfg = (seg, logits.shape, want_entropy)
+        out_shape = tokens.shape
+        if want_entropy:
+            return logp.view(out_shape), ent.view(out_shape)
+        return logp.view(out_shape), None
+
+    @staticmethod
+    def backward(ctx, glogp, gent):
+        l2, tok = ctx.saved_tensors
+        seg, shape, want_entropy = ctx.cfg
+        rows, A = tok.shape
+        glogp = glogp.reshape(rows, A).float().contiguous() if glogp is not None else None
+        gent = gent.reshape(rows, A).float().contiguous() if (gent is not None and want_entropy) else None
+        dl = torch.empty_like(l2)
+        check(_lib.load().cpm_heads_logp_bwd(_p(l2), rows, l2.shape[-1], _lib.int_array(seg), A, _p(tok), _p(glogp), _p(gent),
+                                             _p(dl), _dt(l2), _st()))
+        return dl.view(shape), None, None, None
+
+
+def heads_logp(logits, tokens, seg, want_entropy=False):
+    """log softmax(logits[seg a])[token] (+ entropy) per attribute, differentiable w.r.t. logits."""
+    return _HeadsLogp.apply(logits, tokens, tuple(seg), want_entropy)
+
+
+class _MaskedCE(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, logits, targets, mask, seg, group):
+        _cuda(logits, targets, mask)
+        ld = logits.shape[-1]
+        l2 = logits.reshape(-1, ld).contiguous()
+        A = len(seg) - 1
+        tg = targets.reshape(-1, A).contiguous()
+        m = mask.reshape(-1).to(torch.float32).contiguous()
+        T = tg.shape[0]
+        num = torch.zeros(A, dtype=torch.float32, device=logits.device)
+        msum = torch.zeros(1, dtype=torch.float32, device=logits.device)
+        lse = torch.empty(T, A, dtype=torch.float32, device=logits.device)
+        check(_lib.load().cpm_masked_ce_fwd(_p(l2), T, ld, _lib.int_array(seg), A, _p(tg), _p(m), _p(num), _p(msum), _p(lse),
+                                            _dt(l2), _st()))
+        if group is not None:               # data parallel: the denominator is the GLOBAL mask sum
+            import torch.distributed as dist
+            packed = torch.cat([num, msum])
+            dist.all_reduce(packed, group=group)
+            num, msum = packed[:A].clone(), packed[A:].clone()
+        # The returned loss is the GLOBAL loss; each rank back-propagates its own tokens' share, so
+        # the data-parallel gradient all-reduce must SUM (see dist.py), not average.
+        ctx.save_for_backward(l2, tg, m, lse, msum)
+        ctx.cfg = (seg, logits.shape)
+        return num / msum
+
+    @staticmethod
+    def backward(ctx, gloss):
+        l2, tg, m, lse, msum = ctx.saved_tensors
+        seg, shape = ctx.cfg
+        A = len(seg) - 1
+        gscale = gloss.float().contiguous()
+        dl = torch.empty_like(l2)
+        check(_lib.load().cpm_masked_ce_bwd(_p(l2), tg.shape[0], l2.shape[-1], _lib.int_array(seg), A, _p(tg), _p(m), _p(lse),
+                                            _p(gscale), _p(msum), _p(dl), _dt(l2), _st()))
+        return dl.view(shape), None, None, None, None
+
+
+def masked_ce(logits, targets, mask, seg, group=None):
+    """Per-attribute masked-mean cross-entropy (A,) fp32: sum_t m_t CE_ta / sum_t m_t
+    (reference compute_loss, agent_pretrain.py:279-283)."""
+    return _MaskedCE.apply(logits, targets, mask, tuple(seg), group)
+
+
+# --------------------------------------------------------------------------- RL maths
+def returns_scan(rewards, gamma, mode="compat", values=None, dones=None, last_value=None, lam=0.95):
+    """rewards (B,T) fp32.  mode: 'compat' | 'togo' | 'gae'.  Returns ret (and adv for gae)."""
+    _cuda(rewards)
+    r = rewards.to(torch.float32).contiguous()
+    B, T = r.shape
+    code = {"compat": _lib.RET_COMPAT, "togo": _lib.RET_TOGO, "gae": _lib.RET_GAE}[mode]
+    f = lambda t: None if t is None else t.to(torch.float32).contiguous()
+    values, dones, last_value = f(values), f(dones), f(last_value)
+    ret = torch.empty_like(r)
+    adv = torch.empty_like(r) if code == _lib.RET_GAE else None
+    check(_lib.load().cpm_returns_scan(_p(r), _p(values), _p(dones), _p(last_value), _p(ret), _p(adv), B, T, gamma, lam, code, _st()))
+    return (adv, ret) if code == _lib.RET_GAE else ret
+
+
+def zscore(x, sub=None, unbiased=True, eps=0.0, group=None):
+    """((x - sub) - mean)/std over all elements; moments are all-reduced over `group` if given."""
+    _cuda(x)
+    x = x.to(torch.float32).contiguous()
+    sub = None if sub is None else sub.to(torch.float32).contiguous().expand_as(x).contiguous()
+    m3 = torch.zeros(3, dtype=torch.float64, device=x.device)
+    lib = _lib.load()
+    check(lib.cpm_moments(_p(x), _p(sub), x.numel(), _p(m3), _st()))
+    if group is not None:
+        import torch.distributed as dist
+        dist.all_reduce(m3, group=group)
+    out = torch.empty_like(x)
+    check(lib.cpm_zscore(_p(x), _p(sub), _p(out), x.numel(), _p(m3), 1 if unbiased else 0, eps, _st()))
+    return out
+
+
+class _PPOLoss(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, new_logp, old_logp, adv, entropy, value, ret, clip, vf_coef, ent_coef, mode):
+        _cuda(new_logp, old_logp, adv)
+        f = lambda t: None if t is None else t.detach().to(torch.float32).contiguous()
+        nl, ol, ad, en, va, re = f(new_logp), f(old_logp), f(adv), f(entropy), f(value), f(ret)
+        dev = nl.device
+        out = torch.zeros(4, dtype=torch.float32, device=dev)
+        dnew = torch.empty_like(nl)
+        dent = torch.empty_like(en) if en is not None else None
+        dval = torch.empty_like(va) if va is not None else None
+        if mode == _lib.PPO_COMPAT:
+            T = ol.shape[0]
+            C = ol.numel() // T
+            if nl.numel() != C or ad.numel() != T:
+                raise ValueError("compat PPO loss: new_logp (C), old_logp (T,C), adv (T)")
+            nv = 0
+        else:
+            T, C = nl.numel(), 1
+            if ol.numel() != T or ad.numel() != T:
+                raise ValueError("standard PPO loss: new_logp, old_logp, adv must have equal numel")
+            nv = 0 if va is None else va.numel()
+        check(_lib.load().cpm_ppo_loss_fwd_bwd(_p(nl), _p(ol), _p(ad), _p(en), _p(va), _p(re), _p(out), _p(dnew), _p(dent), _p(dval),
+                                               T, C, nv, clip, vf_coef, ent_coef, 1.0, mode, _st()))
+        ctx.save_for_backward(dnew, dent, dval)
+        ctx.shapes = (new_logp.shape, None if entropy is None else entropy.shape, None if value is None else value.shape)
+        return out
+
+    @staticmethod
+    def backward(ctx, gout):
+        dnew, dent, dval = ctx.saved_tensors
+        s_new, s_ent, s_val = ctx.shapes
+        g = gout[0]
+        return (dnew.view(s_new) * g, None, None, None if dent is None else dent.view(s_ent) * g,
+                None if dval is None else dval.view(s_val) * g, None, None, None, None, None)
+
+
+def ppo_loss_compat(new_logp, old_logp, adv, clip=0.2):
+    """Reference surrogate (ppo_train.py:388-396). Returns the scalar loss (differentiable in new_logp)."""
+    return _PPOLoss.apply(new_logp, old_logp, adv, None, None, None, clip, 0.0, 0.0, _lib.PPO_COMPAT)[0]
+
+
+def ppo_loss_standard(new_logp, old_logp, adv, value=None, ret=None, entropy=None, clip=0.2, vf_coef=0.5, ent_coef=0.01):
+    """Clipped surrogate + vf_coef*MSE - ent_coef*entropy. Returns tensor [loss, policy, value, entropy];
+    only element 0 carries gradient."""
+    return _PPOLoss.apply(new_logp, old_logp, adv, entropy, value, ret, clip, vf_coef, ent_coef, _lib.PPO_STANDARD)
+
+
+class _DQNTD(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, q_logits, next_logits, action, reward, done, seg, A, gamma, mode):
+        _cuda(q_logits, next_logits, action)
+        B, L, ld = q_logits.shape
+        ql, nl = q_logits.contiguous(), next_logits.detach().contiguous()
+        if nl.dtype != ql.dtype:
+            nl = nl.to(ql.dtype)
+        act = action.to(torch.int64).contiguous()
+        rw = reward.reshape(-1).to(torch.float32).contiguous()
+        dn = done.reshape(-1).to(torch.float32).contiguous()
+        out = torch.zeros(1, dtype=torch.float32, device=ql.device)
+        dq = torch.empty_like(ql)
+        n_attr = len(seg) - 1
+        tg = torch.empty(B, A, n_attr, dtype=torch.float32, device=ql.device)
+        check(_lib.load().cpm_dqn_td_fwd_bwd(_p(ql), _p(nl), _p(act), _p(rw), _p(dn), _p(out), _p(dq), _p(tg), B, L, ld,
+                                             _lib.int_array(seg), n_attr, A, gamma, 1.0, mode, _dt(ql), _st()))
+        ctx.save_for_backward(dq)
+        ctx.mark_non_differentiable(tg)
+        return out[0], tg
+
+    @staticmethod
+    def backward(ctx, gloss, _gtg):
+        (dq,) = ctx.saved_tensors
+        return dq * gloss.to(dq.dtype), None, None, None, None, None, None, None, None
+
+
+def dqn_td_loss(q_logits, next_logits, action, reward, done, seg, n_actions=25, gamma=0.95, compat=True):
+    """Mean over attributes of MSE(Q(s,a), r + gamma(1-done) target) over concatenated logits (B,L,ld).
+    Returns (loss, targets (B,A,n_attr)).  The target net's logits are treated as constants (the
+    reference never steps the target net's parameters)."""
+    return _DQNTD.apply(q_logits, next_logits, action, reward, done, tuple(seg), n_actions, gamma,
+                        _lib.TD_COMPAT if compat else _lib.TD_STANDARD)
+
+
+def rollout_advance(tokens, history_tok, vals, history_f, step_dev, max_steps):
+    n_tok = tokens.numel() if tokens is not None else 0
+    n_f = vals.numel() if vals is not None else 0
+    check(_lib.load().cpm_rollout_advance(_p(tokens), _p(history_tok), n_tok, _p(vals), _p(history_f), n_f, _p(step_dev),
+                                          max_steps, _st()))
