@@ -1,0 +1,407 @@
+#!/usr/bin/env python
+"""bench.py — CP tokens/s of one PPO iteration (recurrent rollout + update) on N B200s.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl cpmusic|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
+        --master-port P bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], weak scaling — per GPU): autoregressive RECURRENT rollout of
+32 songs x 1024 compound-word tokens with the reference's per-attribute temperature / nucleus
+sampling, critic values, GAE(lambda) with globally normalised advantages, then one clipped-PPO
+update of the 12-layer / d512 / 8-head actor and critic over those 32x1024 tokens (2 minibatches of
+16x1024, dropout 0.1, Adam, bucketed NCCL gradient all-reduce).  Synthetic data: random-init
+weights, random initial tokens, and a synthetic reward (the reference's Longformer reward model is
+out of scope).  One "step" = one such iteration; value = tokens generated and trained
+on per second over all GPUs.
+
+Prints ONE JSON line (rank 0).  `--impl reference` times the oracle port of the reference's CPU
+path (oracle/, all host threads) on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+VOCAB = [56, 135, 18, 87, 18, 25]            # AIlabs-Pop1K7 dictionary without 'type' (IRL_dqn_train.py:403)
+SONGS_PER_GPU, ROLLOUT_LEN, MINIBATCH = 32, 1024, 16
+METRIC = "CP tokens/s, PPO rollout+update"
+UNIT = "tokens/s"
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+# --------------------------------------------------------------------------------------------
+# clocks sampling during the timed region
+# --------------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
+                                          "-i", str(self.index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._pump, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.25)
+        self.proc.terminate()
+        try:
+            self.proc.wait(2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            f = [x.strip() for x in ln.split(",")]
+            if len(f) < 6:
+                continue
+            try:
+                sm.append(float(f[0]))
+                mx.append(float(f[1]))
+            except ValueError:
+                continue
+            for n, v in zip(names, f[2:6]):
+                if v.lower().startswith("active"):
+                    reasons.add(n)
+        sm.sort()
+        return {"sm_mhz": sm[len(sm) // 2] if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------------
+# CPU arm: the oracle port of the reference path, bounded sample
+# --------------------------------------------------------------------------------------------
+def cpu_reference_sample(roll_steps=6, upd_seqs=2, upd_len=256, seed=0):
+    """Times, on the host cores, (a) batch-32 recurrent rollout steps with host numpy sampling as
+    the reference does (testing-no-type-cp.py:157-167) and (b) a teacher-forced fwd+bwd+Adam update
+    (actor with the C causal-product clone + critic) on upd_seqs x upd_len tokens; returns the
+    tokens/s of one PPO iteration extrapolated from the per-token costs."""
+    import numpy as np
+    import torch
+    from oracle import model_oracle as mo, sampling_oracle as so
+    from oracle.causal_product_c import causal_dot_product_c, num_threads
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    torch.manual_seed(seed)
+    actor_r = mo.OracleCPModel(VOCAB, is_training=False).eval()
+    actor = mo.OracleCPModel(VOCAB, is_training=True).train()
+    critic = mo.OracleCritic(VOCAB).train()
+    actor.transformer_encoder.product = causal_dot_product_c
+    critic.transformer_encoder.product = causal_dot_product_c
+    rng = np.random.RandomState(seed)
+    B = SONGS_PER_GPU
+    cur = torch.stack([torch.randint(0, n, (B,)) for n in VOCAB], -1)
+    # (a) rollout
+    mem = None
+    with torch.no_grad():
+        t0 = None
+        for s in range(roll_steps + 1):
+            if s == 1:
+                t0 = time.perf_counter()          # first step is warm-up
+            z = actor_r.pos_emb(actor_r.embed(cur[:, None, :]), 0).squeeze(1)
+            h, mem = actor_r.transformer_encoder(z, memory=mem)
+            logits = actor_r.forward_output(h)
+            nxt = np.zeros((B, 6), np.int64)
+            for b in range(B):
+                nxt[b] = so.forward_output_sampling({a: logits[i][b].numpy() for i, a in enumerate(so.ATTRS)}, rng)
+            cur = torch.from_numpy(nxt)
+        t_roll = (time.perf_counter() - t0) / (roll_steps * B)                   # s per generated token
+    # (b) update
+    x = torch.stack([torch.randint(0, n, (upd_seqs, upd_len)) for n in VOCAB], -1)
+    opt_a = torch.optim.Adam(actor.parameters(), lr=1e-5)
+    opt_c = torch.optim.Adam(critic.parameters(), lr=1e-5)
+    t0 = time.perf_counter()
+    with torch.no_grad():
+        critic.value_produce(x)                                                   # rollout-time critic values
+    logits = actor.forward_output(actor.forward_hidden(x))
+    lp = sum(torch.log_softmax(l, -1).gather(-1, x[..., i:i + 1]).mean() for i, l in enumerate(logits))
+    opt_a.zero_grad()
+    (-lp).backward()
+    opt_a.step()
+    v = critic.value_produce(x)
+    opt_c.zero_grad()
+    (v ** 2).mean().backward()
+    opt_c.step()
+    t_upd = (time.perf_counter() - t0) / (upd_seqs * upd_len)
+    tokens_per_s = 1.0 / (t_roll + t_upd)
+    return {"value": tokens_per_s, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": f"{roll_steps} batch-{B} recurrent steps + numpy sampling ({t_roll * 1e3:.2f} ms/token) and one actor+critic "
+                      f"fwd+bwd+Adam on {upd_seqs}x{upd_len} tokens ({t_upd * 1e3:.2f} ms/token), oracle port with C/OpenMP "
+                      f"causal_product ({num_threads()} OMP threads), fp32"}
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    t0 = time.perf_counter()
+    vals = []
+    for _ in range(max(1, min(args.warmup, 1))):
+        cpu_reference_sample(roll_steps=2, upd_seqs=1, upd_len=128)
+    for _ in range(max(1, min(args.steps, 3))):
+        r = cpu_reference_sample()
+        vals.append(r["value"])
+    v = sum(vals) / len(vals)
+    r["value"] = v
+    tokens = SONGS_PER_GPU * ROLLOUT_LEN
+    line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": tokens / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic", "impl": "reference",
+            "config": {"workload": "cfg3: PPO rollout (32 songs x 1024 CP tokens, recurrent, nucleus) + GAE + clipped update; "
+                                   "CPU arm extrapolated from a bounded sample", "model": "CP linear transformer 12L d512 h8"},
+            "cpu_baseline": r, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------------
+# GPU arm
+# --------------------------------------------------------------------------------------------
+class PPOIteration:
+    def __init__(self, rank, world, dev, dropout=0.1, lr=1e-5, seed=0):
+        import torch
+        import cpmusic
+        self.torch, self.cpm = torch, cpmusic
+        self.rank, self.world, self.dev = rank, world, dev
+        torch.manual_seed(seed)                       # identical initial weights on every rank
+        self.actor = cpmusic.LinearTransformer(VOCAB, dropout=dropout).to(dev)
+        self.critic = cpmusic.Critic_Transformer(VOCAB, dropout=dropout).to(dev)
+        self.opt_a = torch.optim.Adam(self.actor.parameters(), lr=lr, fused=True)
+        self.opt_c = torch.optim.Adam(self.critic.parameters(), lr=lr, fused=True)
+        self.red_a = cpmusic.dist.BucketedGradAllReduce(self.actor.parameters(), 25.0)
+        self.red_c = cpmusic.dist.BucketedGradAllReduce(self.critic.parameters(), 25.0)
+        self.engine = cpmusic.RolloutEngine(self.actor, SONGS_PER_GPU, ROLLOUT_LEN, greedy=False, true_positions=True,
+                                            seed=1234, seq_base=rank * SONGS_PER_GPU)
+        self.group = None
+        if world > 1:
+            import torch.distributed as dist
+            self.group = dist.group.WORLD
+        g = torch.Generator().manual_seed(1234 + rank)
+        self.init_host = torch.stack([torch.randint(0, n, (SONGS_PER_GPU,), generator=g) for n in VOCAB], -1).pin_memory()
+        self.init_dev = self.init_host.to(dev)
+        self.phase_ms = {"rollout": 0.0, "update": 0.0}
+
+    def step(self, init_tokens, time_phases=False):
+        torch, cpm = self.torch, self.cpm
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if time_phases else None
+        if ev:
+            ev[0].record()
+        roll = self.engine.generate(init_tokens)                       # tokens (B,T+1,A), logp (B,T,A)
+        if ev:
+            ev[1].record()
+        tokens, old_logp = roll["tokens"], roll["logp"]
+        x, act = tokens[:, :-1].contiguous(), tokens[:, 1:].contiguous()
+        B, T, A = act.shape
+        reward = ((act.sum(-1) % 7).float() / 7.0)                     # synthetic per-token reward
+        dones = torch.zeros(B, T, device=self.dev)
+        dones[:, -1] = 1.0
+        self.critic.eval()
+        with torch.no_grad():
+            values = torch.cat([self.critic.value_per_position(x[i:i + MINIBATCH]) for i in range(0, B, MINIBATCH)], 0)
+        adv, ret = cpm.rl.gae(reward, values, dones, torch.zeros(B, device=self.dev), 0.99, 0.95, True, self.group)
+        self.actor.train()
+        self.critic.train()
+        self.red_a.zero_grad()
+        self.red_c.zero_grad()
+        n_mb = B // MINIBATCH
+        scale = 1.0 / (n_mb * self.world)                               # mean over the GLOBAL batch; grads are SUM-reduced
+        stats = torch.zeros(4, device=self.dev)
+        for i in range(0, B, MINIBATCH):
+            sl = slice(i, i + MINIBATCH)
+            lc = self.actor.logits_concat(self.actor.hidden(x[sl]))
+            new_logp, ent = cpm.ops.heads_logp(lc, act[sl], self.actor.seg, True)
+            out = cpm.ops.ppo_loss_standard(new_logp, old_logp[sl], adv[sl, :, None].expand(-1, -1, A), None, None, ent,
+                                            clip=0.2, vf_coef=0.0, ent_coef=0.01)
+            (out[0] * scale).backward()
+            v = self.critic.value_per_position(x[sl])
+            vloss = torch.nn.functional.mse_loss(v, ret[sl])
+            (vloss * scale).backward()
+            stats += torch.stack([out[0].detach(), out[1].detach(), vloss.detach(), out[3].detach()]) * (1.0 / n_mb)
+        self.red_a.finish()
+        self.red_c.finish()
+        torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 3.0, foreach=True)      # reference: clip 3 (agent_pretrain.py:563)
+        self.opt_a.step()
+        self.opt_c.step()
+        if ev:
+            ev[2].record()
+            torch.cuda.synchronize()
+            self.phase_ms["rollout"] += ev[0].elapsed_time(ev[1])
+            self.phase_ms["update"] += ev[1].elapsed_time(ev[2])
+        return tokens, stats
+
+
+def time_recurrent_step_kernel(dev, peak):
+    """Standalone HBM roofline of the recurrent attention step kernel at the rollout shape
+    (32 sequences x 8 heads x 12 layers' states = 50 MB touched per pass, L2 flushed between)."""
+    import torch
+    import cpmusic
+    N, H, layers = SONGS_PER_GPU, 8, 12
+    S = torch.zeros(layers, N, H, 64, 64, device=dev)
+    Z = torch.zeros(layers, N, H, 64, device=dev)
+    qkv = torch.randn(N, 3 * H * 64, device=dev).bfloat16()
+    q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    tot = 0.0
+    reps = 5
+    for r in range(reps + 2):
+        flush.zero_()
+        a.record()
+        for l in range(layers):
+            cpmusic.ops.linattn_step(q, k, v, S[l], Z[l])
+        b.record()
+        torch.cuda.synchronize()
+        if r >= 2:
+            tot += a.elapsed_time(b)
+    ms = tot / reps / layers
+    bytes_alg = N * 270336                     # per (sequence, layer)
+    return {"kernel": "linattn_step_kernel", "bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": peak,
+            "unit": "GB/s", "frac": bytes_alg / (ms * 1e-3) / 1e9 / peak, "us_per_launch": ms * 1e3,
+            "note": "standalone, cold L2, 12 back-to-back launches (one per layer state)"}
+
+
+def run_gpu(args, rank, world):
+    import torch
+    import cpmusic
+    local = int(os.environ.get("LOCAL_RANK", 0))
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    cpmusic._lib.load()
+    peak, peak_src = load_peaks()
+    it = PPOIteration(rank, world, dev)
+
+    def barrier():
+        if world > 1:
+            import torch.distributed as dist
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(max(args.warmup, 3)):
+        it.step(it.init_dev)
+    barrier()
+    # ---- device-resident timed region ------------------------------------------------------
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    cpmusic._lib.reset_counts()
+    cpmusic.ops.KernelTimer.start()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        it.step(it.init_dev)
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1)
+    ktimes = cpmusic.ops.KernelTimer.stop()
+    launches = cpmusic._lib.kernel_launches()
+    barrier()
+    clocks = sampler.stop() if rank == 0 else None
+    # ---- end-to-end region: pinned-host inputs in, tokens + losses out, every step ----------
+    barrier()
+    f0, f1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    f0.record()
+    host_tok = torch.empty(SONGS_PER_GPU, ROLLOUT_LEN + 1, 6, dtype=torch.int64).pin_memory()
+    host_stats = torch.empty(4).pin_memory()
+    for _ in range(args.steps):
+        init = it.init_host.to(dev, non_blocking=True)
+        tokens, stats = it.step(init)
+        host_tok.copy_(tokens, non_blocking=True)
+        host_stats.copy_(stats, non_blocking=True)
+        torch.cuda.synchronize()                    # the caller reads the result every step
+    f1.record()
+    torch.cuda.synchronize()
+    ms_e2e = f0.elapsed_time(f1)
+    # phase split (extra untimed step)
+    it.phase_ms = {"rollout": 0.0, "update": 0.0}
+    it.step(it.init_dev, time_phases=True)
+    if world > 1:
+        import torch.distributed as dist
+        t = torch.tensor([ms, ms_e2e], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, ms_e2e = float(t[0]), float(t[1])
+    if rank != 0:
+        return
+    tokens_step = SONGS_PER_GPU * ROLLOUT_LEN * world
+    value = tokens_step * args.steps / (ms * 1e-3)
+    e2e = tokens_step * args.steps / (ms_e2e * 1e-3)
+    # ---- roofline of the kernel the metric names: chunked linear attention fwd+bwd ----------
+    nf, tf = ktimes.get("linattn_fwd", (0, 0.0))
+    nb, tb = ktimes.get("linattn_bwd", (0, 0.0))
+    tok_call = MINIBATCH * ROLLOUT_LEN
+    bytes_fwd, bytes_bwd = tok_call * 8 * 512, tok_call * 8 * 896            # SURVEY §8d per (token, head): 512 B fwd, 896 B bwd
+    n_pairs = max(min(nf, nb), 1)
+    ms_pair = (tf / max(nf, 1)) + (tb / max(nb, 1))
+    achieved = (bytes_fwd + bytes_bwd) / (ms_pair * 1e-3) / 1e9 if ms_pair > 0 else 0.0
+    roofline = {"kernel": f"linattn fwd+bwd ({cpmusic.ops.linattn_last_impl()})", "bound": "hbm", "achieved": achieved, "peak": peak,
+                "unit": "GB/s", "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_launch_pair": bytes_fwd + bytes_bwd, "ms_fwd": tf / max(nf, 1), "ms_bwd": tb / max(nb, 1),
+                "launch_pairs_timed": n_pairs, "share_of_step": (tf + tb) / ms,
+                "tensor_frac_of_measured_bf16": (tok_call * 8 * 49152) / (ms_pair * 1e-3) / 1e12 / 1651.8 if ms_pair > 0 else 0.0}
+    roofline_step = time_recurrent_step_kernel(dev, peak)
+    cpu = cpu_reference_sample() if world >= 1 and not args.no_cpu_baseline else None
+    line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
+            "data": "synthetic",
+            "config": {"workload": "cfg3: PPO rollout (32 songs x 1024 CP tokens per GPU, recurrent, per-attribute temperature/nucleus "
+                                   "sampling) + critic values + GAE + one clipped-PPO update (actor+critic, 2 minibatches of 16x1024, "
+                                   "dropout 0.1, Adam)", "model": "CP linear transformer 12L d512 h8 ff2048 (38.98M params) x2 (actor, critic)",
+                       "tokens_per_step": tokens_step, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (working set > 1 GB/step)",
+                       "reward": "synthetic (Longformer reward model out of scope)"},
+            "roofline": roofline, "roofline_recurrent_step": roofline_step, "cpu_baseline": cpu,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(it.init_host.numel() * 8),
+                    "d2h_bytes_per_step": int(host_tok.numel() * 8 + 16), "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches, "clocks": clocks,
+            "phase_ms": {k: round(v, 3) for k, v in it.phase_ms.items()},
+            "rollout_kernels_per_token_step": it.engine.launches_per_step}
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="cpmusic", choices=["cpmusic", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world > 1:
+        import cpmusic
+        cpmusic.dist.init_from_env("nccl")
+    run_gpu(args, rank, world)
+    if world > 1:
+        import torch.distributed as dist
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -70,6 +70,45 @@ SIGNATURES = {
 
 _lib = None
 
+# ---- launch accounting (bench.py's `gpu_launches`): C-ABI calls made, and kernels per call -------
+import collections
+COUNTS = collections.Counter()
+KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
+    "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
+    "cpm_linattn_workspace_bytes": 0, "cpm_ln_partials_rows": 0,
+    "cpm_linattn_bwd": 2, "cpm_ln_residual_bwd": 2,
+})
+EXTRA_LAUNCHES = [0]          # segment-total / scan kernels of segmented linear attention, graph replays
+
+
+def kernel_launches() -> int:
+    return sum(n * KERNELS_PER_CALL[name] for name, n in COUNTS.items()) + EXTRA_LAUNCHES[0]
+
+
+def reset_counts() -> None:
+    COUNTS.clear()
+    EXTRA_LAUNCHES[0] = 0
+
+
+class _Counted:
+    """The loaded library with a per-entry-point call counter in front of every function."""
+
+    def __init__(self, cdll):
+        self._cdll = cdll
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(cdll, name)      # AttributeError if the .so is stale
+            fn.restype = res
+            fn.argtypes = args
+            setattr(self, name, self._wrap(name, fn))
+
+    @staticmethod
+    def _wrap(name, fn):
+        def call(*a):
+            COUNTS[name] += 1
+            return fn(*a)
+        call.__name__ = name
+        return call
+
 
 class CpmError(RuntimeError):
     """A libcpmusic entry point returned a negative code."""
@@ -87,12 +126,7 @@ def load() -> ctypes.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (or "
                 f"`python {os.path.join(_HERE, 'build.py')}`); this package has no CPU fallback.")
-        lib = ctypes.CDLL(LIB_PATH)
-        for name, (res, args) in SIGNATURES.items():
-            fn = getattr(lib, name)      # AttributeError if the .so is stale
-            fn.restype = res
-            fn.argtypes = args
-        _lib = lib
+        _lib = _Counted(ctypes.CDLL(LIB_PATH))
     return _lib
 
 

@@ -358,9 +358,9 @@ extern "C" {
 
 int cpm_embed_fwd(const int64_t *idx, const float *const *tables_host, const int *n_tokens_host, const int *emb_sizes_host,
                   int n_attr, int64_t T_, void *out, int dtype, int *err_flag, void *stream) {
-    CPM_REQUIRE(idx && tables_host && n_tokens_host && emb_sizes_host && out, CPM_ERR_NULL, "embed_fwd: NULL pointer");
     CPM_REQUIRE(T_ >= 0, CPM_ERR_BAD_SHAPE, "embed_fwd: T=%lld", (long long)T_);
-    if (T_ == 0) return CPM_OK;
+    if (T_ == 0) return CPM_OK;                 // empty batch: nothing to read or write
+    CPM_REQUIRE(idx && tables_host && n_tokens_host && emb_sizes_host && out, CPM_ERR_NULL, "embed_fwd: NULL pointer");
     EmbedParams p{};
     int rc = fill_embed_params(p, tables_host, nullptr, n_tokens_host, emb_sizes_host, n_attr, 8);
     if (rc) return rc;
@@ -372,8 +372,8 @@ int cpm_embed_fwd(const int64_t *idx, const float *const *tables_host, const int
 
 int cpm_embed_bwd(const int64_t *idx, const void *gout, float *const *gtables_host, const int *n_tokens_host,
                   const int *emb_sizes_host, int n_attr, int64_t T_, int dtype, void *stream) {
-    CPM_REQUIRE(idx && gout && gtables_host && n_tokens_host && emb_sizes_host, CPM_ERR_NULL, "embed_bwd: NULL pointer");
     if (T_ == 0) return CPM_OK;
+    CPM_REQUIRE(idx && gout && gtables_host && n_tokens_host && emb_sizes_host, CPM_ERR_NULL, "embed_bwd: NULL pointer");
     EmbedParams p{};
     int rc = fill_embed_params(p, nullptr, gtables_host, n_tokens_host, emb_sizes_host, n_attr, 32);
     if (rc) return rc;

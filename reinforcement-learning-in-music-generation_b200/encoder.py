@@ -49,36 +49,58 @@ class LengthMask:
 
 
 class PackCache:
-    """Compute-dtype packings of fp32 master parameters, rebuilt when a master changes."""
+    """Compute-dtype packings of fp32 master parameters (row-concatenated, optionally zero-padded).
+    A packing is refreshed IN PLACE when a master changes, so its device address is stable — CUDA
+    graphs captured over these buffers (the rollout step) stay valid across optimizer steps; call
+    ``refresh_all()`` before replaying such a graph."""
 
     def __init__(self):
         self._store = {}
 
+    @staticmethod
+    def _stamp(params, dtype):
+        return tuple((p.data_ptr(), p._version) for p in params) + (dtype,)
+
+    @staticmethod
+    def _fill(wc, bc, ws, bs):
+        r0 = 0
+        for w, b in zip(ws, bs):
+            wc[r0:r0 + w.shape[0]].copy_(w)
+            bc[r0:r0 + w.shape[0]].copy_(b)
+            r0 += w.shape[0]
+
     def get(self, key, linears, dtype, pad_rows_to: int = 1):
         ws = [l.weight for l in linears]
         bs = [l.bias for l in linears]
-        stamp = tuple((p.data_ptr(), p._version) for p in ws + bs) + (dtype,)
+        stamp = self._stamp(ws + bs, dtype)
         hit = self._store.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]
         with torch.no_grad():
             rows = [int(w.shape[0]) for w in ws]
-            total = sum(rows)
-            padded = -(-total // pad_rows_to) * pad_rows_to
-            if len(ws) == 1 and padded == total:
-                wc = ws[0].detach().to(dtype).contiguous()
-                bc = bs[0].detach().to(dtype).contiguous()
+            padded = -(-sum(rows) // pad_rows_to) * pad_rows_to
+            if (hit is not None and hit[1][0].dtype == dtype and hit[1][0].device == ws[0].device
+                    and hit[1][0].shape == (padded, ws[0].shape[1])):
+                wc, bc = hit[1][0], hit[1][1]                       # same buffers, new values
             else:
                 wc = torch.zeros(padded, ws[0].shape[1], dtype=dtype, device=ws[0].device)
                 bc = torch.zeros(padded, dtype=dtype, device=ws[0].device)
-                r0 = 0
-                for w, b in zip(ws, bs):
-                    wc[r0:r0 + w.shape[0]] = w
-                    bc[r0:r0 + w.shape[0]] = b
-                    r0 += w.shape[0]
+            self._fill(wc, bc, ws, bs)
         packed = (wc, bc, tuple(rows), tuple(ws + bs))
         self._store[key] = (stamp, packed)
         return packed
+
+    def refresh_all(self):
+        """Re-sync every existing packing with its masters (in place)."""
+        with torch.no_grad():
+            for key, (stamp, packed) in list(self._store.items()):
+                wc, bc, rows, masters = packed
+                dtype = stamp[-1]
+                now = self._stamp(masters, dtype)
+                if now != stamp:
+                    n = len(rows)
+                    self._fill(wc, bc, masters[:n], masters[n:])
+                    self._store[key] = (now, packed)
 
     def clear(self):
         self._store.clear()
@@ -150,24 +172,7 @@ class TransformerEncoder(nn.Module):
             x = self._layer(i, layer, x)
         return ops.ln_residual(x, None, self.norm.weight, self.norm.bias, self.norm.eps, 0.0)
 
-    # ---- ft signature ------------------------------------------------------------------------
-    def forward(self, x, attn_mask=None, length_mask=None):
-        if attn_mask is None or not getattr(attn_mask, "lower_triangular", False):
-            raise RuntimeError("CausalLinearAttention only supports full lower triangular masks")
-        if length_mask is not None:
-            raise NotImplementedError("length_mask is never passed by the reference (SURVEY App. A.1); not implemented")
-        return self.forward_fused(x.to(self.compute_dtype)).to(x.dtype)
-
-    def _apply(self, fn, *a, **k):
-        self._cache.clear()
-        return super()._apply(fn, *a, **k)
-
-
-class RecurrentTransformerEncoder(TransformerEncoder):
-    """One-token-per-call encoder.  ``state`` is a list (one entry per layer) of
-    ``[Si (N,H,64,64) fp32, Zi (N,H,64) fp32]`` updated in place; ``memory`` is ft's deprecated
-    alias and the keyword the reference uses (dqn_policy/model.py:237)."""
-
+    # ---- recurrent (one token per call) path; shares every parameter with the parallel path ------
     def new_state(self, N, device):
         H = self.n_heads
         return [[torch.zeros(N, H, 64, 64, dtype=torch.float32, device=device),
@@ -197,6 +202,23 @@ class RecurrentTransformerEncoder(TransformerEncoder):
             x = self._step_layer(i, layer, x, state[i])
         return ops.ln_residual(x, None, self.norm.weight, self.norm.bias, self.norm.eps, 0.0), state
 
+    # ---- ft signature ------------------------------------------------------------------------
+    def forward(self, x, attn_mask=None, length_mask=None):
+        if attn_mask is None or not getattr(attn_mask, "lower_triangular", False):
+            raise RuntimeError("CausalLinearAttention only supports full lower triangular masks")
+        if length_mask is not None:
+            raise NotImplementedError("length_mask is never passed by the reference (SURVEY App. A.1); not implemented")
+        return self.forward_fused(x.to(self.compute_dtype)).to(x.dtype)
+
+    def _apply(self, fn, *a, **k):
+        self._cache.clear()
+        return super()._apply(fn, *a, **k)
+
+
+class RecurrentTransformerEncoder(TransformerEncoder):
+    """One-token-per-call encoder.  ``state`` is a list (one entry per layer) of
+    ``[Si (N,H,64,64) fp32, Zi (N,H,64) fp32]`` updated in place; ``memory`` is ft's deprecated
+    alias and the keyword the reference uses (dqn_policy/model.py:237)."""
     def forward(self, x, state=None, memory=None):
         state = state if state is not None else memory
         with torch.no_grad():       # the recurrent kernels update state in place (ft does so under no_grad)

@@ -128,6 +128,12 @@ class CPLinearTransformer(nn.Module):
         self._cache.clear()
         return super()._apply(fn, *a, **k)
 
+    def refresh_packs(self):
+        """Bring every cached bf16 weight packing up to date in place (needed before replaying a CUDA
+        graph captured over them, e.g. the rollout step after an optimizer step)."""
+        self._cache.refresh_all()
+        self.transformer_encoder._cache.refresh_all()
+
     def _tables(self):
         return [getattr(self, f"word_emb_{a}").lut.weight for a in self.attrs]
 

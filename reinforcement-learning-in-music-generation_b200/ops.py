@@ -61,10 +61,64 @@ def manual_seed(seed: int) -> None:
     _Rng.offset = 0
 
 
+# --------------------------------------------------------------------------- in-situ kernel timing
+class KernelTimer:
+    """CUDA-event timing of selected kernels on the launching stream while a real step runs
+    (bench.py's live roofline measurement).  Disabled by default; zero cost when off."""
+    enabled = False
+    events = {}
+
+    @classmethod
+    def start(cls):
+        cls.enabled, cls.events = True, {}
+
+    @classmethod
+    def stop(cls):
+        """-> {name: (calls, total_ms)}; synchronises."""
+        cls.enabled = False
+        torch.cuda.synchronize()
+        out = {k: (len(v), sum(a.elapsed_time(b) for a, b in v)) for k, v in cls.events.items()}
+        cls.events = {}
+        return out
+
+    @classmethod
+    def span(cls, name):
+        return _Span(name) if cls.enabled else _NULL
+
+
+class _Span:
+    def __init__(self, name):
+        self.name = name
+
+    def __enter__(self):
+        self.a = torch.cuda.Event(enable_timing=True)
+        self.b = torch.cuda.Event(enable_timing=True)
+        self.a.record()
+
+    def __exit__(self, *exc):
+        self.b.record()
+        KernelTimer.events.setdefault(self.name, []).append((self.a, self.b))
+
+
+class _Null:
+    def __enter__(self):
+        return None
+
+    def __exit__(self, *exc):
+        return False
+
+
+_NULL = _Null()
+
+
 # --------------------------------------------------------------------------- linear attention
 def linattn_workspace(N: int, L: int, H: int, device) -> torch.Tensor:
     nbytes = _lib.load().cpm_linattn_workspace_bytes(N, L, H)
     return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
+
+
+def linattn_nseg(N: int, L: int, H: int) -> int:
+    return int(_lib.load().cpm_linattn_workspace_bytes(N, L, H) // (2 * N * H * (64 * 64 + 64) * 4))
 
 
 def _check_qkv_layout(q, k, v):
@@ -84,8 +138,11 @@ def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True):
     out = torch.empty(N, L, H, E, dtype=q.dtype, device=q.device)
     den = torch.empty(N, L, H, dtype=torch.float32, device=q.device) if need_den else None
     ws = linattn_workspace(N, L, H, q.device)
-    check(_lib.load().cpm_linattn_fwd(_p(q), _p(k), _p(v), _p(out), _p(den), N, L, H, E, E, ld, H * E,
-                                      _dt(q), eps, impl, _p(ws), ws.numel(), _st()))
+    if linattn_nseg(N, L, H) > 1:
+        _lib.EXTRA_LAUNCHES[0] += 2
+    with KernelTimer.span("linattn_fwd"):
+        check(_lib.load().cpm_linattn_fwd(_p(q), _p(k), _p(v), _p(out), _p(den), N, L, H, E, E, ld, H * E,
+                                          _dt(q), eps, impl, _p(ws), ws.numel(), _st()))
     return out, den
 
 
@@ -94,8 +151,11 @@ def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0):
     _, _, _, _, ldg = _check_qkv_layout(gq, gk, gv)
     gout = gout.contiguous()
     ws = linattn_workspace(N, L, H, q.device)
-    check(_lib.load().cpm_linattn_bwd(_p(q), _p(k), _p(v), _p(out), _p(den), _p(gout), _p(gq), _p(gk), _p(gv),
-                                      N, L, H, E, E, ld, H * E, ldg, _dt(q), eps, impl, _p(ws), ws.numel(), _st()))
+    if linattn_nseg(N, L, H) > 1:
+        _lib.EXTRA_LAUNCHES[0] += 4
+    with KernelTimer.span("linattn_bwd"):
+        check(_lib.load().cpm_linattn_bwd(_p(q), _p(k), _p(v), _p(out), _p(den), _p(gout), _p(gq), _p(gk), _p(gv),
+                                          N, L, H, E, E, ld, H * E, ldg, _dt(q), eps, impl, _p(ws), ws.numel(), _st()))
 
 
 class _LinAttnFused(torch.autograd.Function):

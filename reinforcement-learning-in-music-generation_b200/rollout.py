@@ -13,14 +13,12 @@ from typing import Optional
 
 import torch
 
-from . import ops
+from . import _lib, ops
 
 
 class RolloutEngine:
     def __init__(self, model, batch: int, max_steps: int, greedy: bool = False, true_positions: bool = True,
                  temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True):
-        if not model.recurrent:
-            raise RuntimeError("RolloutEngine needs a model built with is_training=False (recurrent encoder)")
         self.model, self.N, self.max_steps = model, batch, max_steps
         self.greedy, self.true_positions = greedy, true_positions
         self.temperature, self.top_p = model.sampling_config(temperature, top_p)
@@ -65,8 +63,10 @@ class RolloutEngine:
                 self._step()
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
+        before = _lib.kernel_launches()
         with torch.no_grad(), torch.cuda.graph(g):
             self._step()
+        self.launches_per_step = _lib.kernel_launches() - before      # cpmusic kernels captured per token step
         self.graph = g
         self.model.train(was_training)
 
@@ -84,9 +84,11 @@ class RolloutEngine:
         if self.use_graph and self.graph is None:
             self._capture()
         self.reset(init_tokens)
+        self.model.refresh_packs()          # the graph reads the packed weights by address
         if self.use_graph:
             for _ in range(n_steps):
                 self.graph.replay()
+            _lib.EXTRA_LAUNCHES[0] += n_steps * self.launches_per_step
         else:
             for _ in range(n_steps):
                 self._step()

@@ -240,3 +240,24 @@ def test_full_size_model_bf16_smoke_properties(cuda, cpm):
     assert torch.equal(h_a[:, :300], h_b[:, :300])                        # causal: bit-identical prefix
     for a, n in enumerate(VOCAB):
         assert abs(l32[a].item() - np.log(n)) < 0.6
+
+
+def test_rollout_graph_sees_optimizer_updates(cuda, cpm, golden):
+    """The captured rollout graph reads packed bf16 weights by address: after an optimizer step the
+    packs are refreshed in place, so graph replay must equal eager stepping on the NEW weights."""
+    g = golden("model_small")
+    m = _load_small(cpm, g, cuda, dtype=torch.bfloat16)
+    N, T = 3, 16
+    init = torch.stack([torch.randint(0, n, (N,), generator=torch.Generator().manual_seed(15)) for n in VOCAB], -1).to(cuda)
+    eng = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=True)
+    before = eng.generate(init)["tokens"].clone()
+    opt = torch.optim.SGD(m.parameters(), lr=0.5)
+    x = torch.from_numpy(g["x"]).to(cuda)
+    m.train()
+    loss = sum(m.train_step(x, x.roll(-1, 1), torch.ones(2, 70, device=cuda)))
+    loss.backward()
+    opt.step()
+    after_graph = eng.generate(init)["tokens"].clone()
+    after_eager = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False).generate(init)["tokens"]
+    assert torch.equal(after_graph, after_eager)
+    assert not torch.equal(before, after_graph)          # lr 0.5 really changed the policy
