@@ -211,9 +211,12 @@ class PPOIteration:
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if time_phases else None
         if ev:
             ev[0].record()
+        torch.cuda.nvtx.range_push("rollout")
         roll = self.engine.generate(init_tokens)                       # tokens (B,T+1,A), logp (B,T,A)
+        torch.cuda.nvtx.range_pop()
         if ev:
             ev[1].record()
+        torch.cuda.nvtx.range_push("update")
         tokens, old_logp = roll["tokens"], roll["logp"]
         x, act = tokens[:, :-1].contiguous(), tokens[:, 1:].contiguous()
         B, T, A = act.shape
@@ -247,6 +250,7 @@ class PPOIteration:
         torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 3.0, foreach=True)      # reference: clip 3 (agent_pretrain.py:563)
         self.opt_a.step()
         self.opt_c.step()
+        torch.cuda.nvtx.range_pop()
         if ev:
             ev[2].record()
             torch.cuda.synchronize()
@@ -267,13 +271,19 @@ def time_recurrent_step_kernel(dev, peak):
     q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    for l in range(layers):
+        cpmusic.ops.linattn_step(q, k, v, S[l], Z[l])
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()                       # 12 launches captured: GPU time, not Python launch time
+    with torch.cuda.graph(graph):
+        for l in range(layers):
+            cpmusic.ops.linattn_step(q, k, v, S[l], Z[l])
     tot = 0.0
     reps = 5
     for r in range(reps + 2):
         flush.zero_()
         a.record()
-        for l in range(layers):
-            cpmusic.ops.linattn_step(q, k, v, S[l], Z[l])
+        graph.replay()
         b.record()
         torch.cuda.synchronize()
         if r >= 2:
@@ -282,7 +292,7 @@ def time_recurrent_step_kernel(dev, peak):
     bytes_alg = N * 270336                     # per (sequence, layer)
     return {"kernel": "linattn_step_kernel", "bound": "hbm", "achieved": bytes_alg / (ms * 1e-3) / 1e9, "peak": peak,
             "unit": "GB/s", "frac": bytes_alg / (ms * 1e-3) / 1e9 / peak, "us_per_launch": ms * 1e3,
-            "note": "standalone, cold L2, 12 back-to-back launches (one per layer state)"}
+            "note": "standalone CUDA graph of 12 launches (one per layer state), L2 flushed before each replay"}
 
 
 def run_gpu(args, rank, world):
