@@ -518,4 +518,34 @@ int linattn_bwd_simt_launch(const void *q, const void *k, const void *v, const v
     return dtype == CPM_F32 ? bwd_impl<float>(p, st) : bwd_impl<__nv_bfloat16>(p, st);
 }
 
+// Segment prefix (and optionally suffix) states for callers that run their own main kernels (the
+// tcgen05 path): fills ws_fwd with exclusive forward prefixes of [S|z] and, when `reverse_too`,
+// ws_rev with exclusive suffixes of [R|rz].
+int linattn_segment_states_launch(const void *q, const void *k, const void *v, const void *out, const float *den,
+                                  const void *gout, int N, int L, int H, int64_t ld_qkv, int64_t ld_o, int dtype, void *ws,
+                                  bool reverse_too, cudaStream_t st) {
+    Params p{};
+    p.q = q; p.k = k; p.v = v; p.o = out; p.go = gout; p.den = const_cast<float *>(den); p.N = N; p.L = L; p.H = H;
+    p.ld_qkv = ld_qkv; p.ld_o = ld_o;
+    plan_segments(N, H, L, &p.nseg, &p.seg_len);
+    p.ws_fwd = (float *)ws;
+    p.ws_rev = p.ws_fwd + (int64_t)N * H * p.nseg * STATE_FLOATS;
+    if (p.nseg <= 1) return CPM_OK;
+    const int NH = N * H;
+    const size_t smem_tot = (2 * TILE + 64) * sizeof(float);
+    int rc;
+    if (dtype == CPM_F32) {
+        if ((rc = set_smem(linattn_seg_total_simt<float>, smem_tot))) return rc;
+        linattn_seg_total_simt<float><<<NH * p.nseg, NT, smem_tot, st>>>(p, 0);
+        if (reverse_too) linattn_seg_total_simt<float><<<NH * p.nseg, NT, smem_tot, st>>>(p, 1);
+    } else {
+        if ((rc = set_smem(linattn_seg_total_simt<__nv_bfloat16>, smem_tot))) return rc;
+        linattn_seg_total_simt<__nv_bfloat16><<<NH * p.nseg, NT, smem_tot, st>>>(p, 0);
+        if (reverse_too) linattn_seg_total_simt<__nv_bfloat16><<<NH * p.nseg, NT, smem_tot, st>>>(p, 1);
+    }
+    linattn_seg_scan<<<NH, 256, 0, st>>>(p.ws_fwd, p.nseg, 0);
+    if (reverse_too) linattn_seg_scan<<<NH, 256, 0, st>>>(p.ws_rev, p.nseg, 1);
+    return check_launch("linattn_segment_states");
+}
+
 }  // namespace cpm

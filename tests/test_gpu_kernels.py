@@ -436,3 +436,38 @@ def test_dqn_td_replay_batch_1024(cuda, cpm):
     split = lambda t: [t[..., seg[i]:seg[i + 1]].double().cpu() for i in range(6)]
     ref = rl.dqn_td_loss_standard(split(ql[:32]), split(nq[:32]), act[:32].cpu(), rw[:32, None].double().cpu(), dn[:32, None].double().cpu())
     _cmp(cpm.ops.dqn_td_loss(ql[:32], nq[:32], act[:32], rw[:32], dn[:32], seg, 25, 0.95, False)[0], ref, 1e-4, 1e-4, "vs oracle")
+
+
+# ------------------------------------------------------------------ tcgen05 / TMA path
+@pytest.mark.parametrize("shape", [(1, 128, 1), (2, 256, 4), (3, 384, 2), (1, 2048, 2), (32, 512, 8)])
+def test_linattn_tc_fwd(cuda, cpm, shape):
+    """tcgen05 forward (impl=2, bf16) vs the fp64 oracle on the same bf16-rounded inputs and vs the
+    SIMT kernel.  The tensor-core path rounds P (intra-chunk scores) and the carried state to bf16
+    before the second MMA, so its tolerance is a little wider than the fp32-math SIMT path:
+    3e-2 absolute on O(1) outputs; the normaliser `den` within 1e-2 relative."""
+    N, L, H = shape
+    gen = torch.Generator().manual_seed(L + H)
+    q, k, v = (torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16() for _ in range(3))
+    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=2)
+    assert cpm.ops.linattn_last_impl() == "tcgen05"
+    torch.cuda.synchronize()
+    ref_simt, den_simt = cpm.ops.linattn_fwd_raw(q, k, v, impl=1)
+    _cmp(out, ref_simt.float(), 3e-2, 2e-2, "tc vs simt")
+    _cmp(den, den_simt, 1e-3, 1e-2, "den tc vs simt")
+    if N * L * H <= 8192:
+        _cmp(out, _oracle_attn(q.float(), k.float(), v.float()), 3e-2, 2e-2, "tc vs oracle")
+
+
+def test_linattn_tc_fwd_fused_layout_and_autograd(cuda, cpm):
+    """Default dispatch (impl=0) takes the tensor-core forward for bf16, L%128==0, on the fused QKV
+    layout (token stride 3*H*64), and the backward (SIMT) consumes its saved out/den."""
+    N, L, H = 2, 256, 8
+    gen = torch.Generator().manual_seed(77)
+    qkv = torch.randn(N, L, 3 * H * 64, generator=gen).to(cuda).bfloat16().requires_grad_()
+    go = torch.randn(N, L, H * 64, generator=gen).to(cuda).bfloat16()
+    out = cpm.ops.causal_linear_attention_fused(qkv, H)
+    out.backward(go)
+    q, k, v = (qkv.detach()[..., i * H * 64:(i + 1) * H * 64].reshape(N, L, H, 64).float() for i in range(3))
+    ro, rq, rk, rv = _oracle_attn(q, k, v, go.view(N, L, H, 64).float())
+    _cmp(out.view(N, L, H, 64), ro, 3e-2, 2e-2, "out")
+    _cmp(qkv.grad, torch.cat([t.reshape(N, L, H * 64) for t in (rq, rk, rv)], -1), 5e-2, 3e-2, "gqkv")
