@@ -47,6 +47,13 @@ int make_tmap_bf16_2d(CUtensorMap *out, const void *base, uint64_t inner_elems, 
                       uint32_t box_rows) {
     EncodeTiledFn fn = encode_tiled();
     if (!fn) return fail(CPM_ERR_CUDA, "cuTensorMapEncodeTiled is not available from the driver");
+    // The encode call is a driver-API entry point and needs a current context on THIS thread; autograd
+    // worker threads may not have touched the runtime yet, so bind the primary context once per thread.
+    static thread_local bool ctx_bound = false;
+    if (!ctx_bound) {
+        cudaFree(nullptr);
+        ctx_bound = true;
+    }
     cuuint64_t dims[2] = {inner_elems, rows};
     cuuint64_t strides[1] = {row_stride_elems * 2};
     cuuint32_t box[2] = {64, box_rows};
@@ -314,6 +321,474 @@ linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (warp == 0) tmem_dealloc<256>(tmem);
 }
 
+
+// =============================================================================================
+// Backward.  Two kernels with the forward's structure (one CTA per (n, h, segment), 128 threads,
+// 128-token chunks, 2 CTAs/SM, 256 TMEM columns):
+//   dq pass  (chunks in forward order, carries S, z):
+//     X[i][j]  = G'[i].v[j] (+ gd_i) masked j<=i           G' = go/den, gd_i = -(go_i.out_i)/den_i
+//     dQf[i][e] = sum_j X[i][j] Kf[j][e] + sum_m G'[i][m] S[e][m] + gd_i z[e];  dq = dQf * phi'(q)
+//   dk/dv pass (chunks in reverse order, carries R[e][m] = sum_{later i} Qf[i][e] G'[i][m], rz):
+//     PT[j][i] = Kf[j].Qf[i] masked i>=j ;  dv[j][m] = sum_i PT[j][i] G'[i][m] + sum_e Kf[j][e] R[e][m]
+//     WT[j][i] = v[j].G'[i] + gd_i masked ;  dKf[j][e] = sum_i WT[j][i] Qf[i][e] + sum_m v[j][m] R[e][m] + rz[e]
+// The carried state tile (rows e, 64 m contiguous) is read MN-major where the contraction runs over
+// e and K-major where it runs over m, so no transposed copy is ever built.
+// =============================================================================================
+constexpr uint32_t B_OFF_Q = 0, B_OFF_K = 16384, B_OFF_V = 32768, B_OFF_G = 49152, B_OFF_X = 65536, B_OFF_S = 98304;
+constexpr uint32_t B_OFF_Z = 106496;                 // 2 x 64 floats (double-buffered z / rz)
+constexpr uint32_t B_OFF_DZ = B_OFF_Z + 512;         // 2 x 64 floats partial column sums
+constexpr uint32_t B_OFF_GD = B_OFF_DZ + 512;        // 128 floats gd_i (dk/dv pass)
+constexpr uint32_t B_OFF_BAR = B_OFF_GD + 512, B_OFF_TMEM = B_OFF_BAR + 32, BWD_SMEM_USED = B_OFF_TMEM + 16;
+constexpr uint32_t BWD_SMEM_BYTES = BWD_SMEM_USED + 1024;
+constexpr uint32_t TB_X = 0, TB_ACC = 128, TB_ST = 192;
+constexpr uint32_t IDESC_KK128 = idesc_bf16(128, 128, false, false);   // A K-major, B K-major, N=128
+constexpr uint32_t IDESC_KM64 = idesc_bf16(128, 64, false, true);      // A K-major, B MN-major, N=64
+constexpr uint32_t IDESC_KK64 = idesc_bf16(128, 64, false, false);     // A K-major, B K-major,  N=64
+constexpr uint32_t IDESC_MM64 = idesc_bf16(64, 64, true, true);        // A MN-major, B MN-major (state update)
+
+__device__ __forceinline__ void unpack8(uint4 raw, float (&f)[8]) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 x = __bfloat1622float2(h[i]); f[2 * i] = x.x; f[2 * i + 1] = x.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+
+// G' = go/den in place (sG), returns gd_r; o tile is read from sOt.
+__device__ __forceinline__ float prep_grad_row(uint8_t *sG, const uint8_t *sOt, int r, float inv) {
+    float dot = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t off = sw128_off(r, ch);
+        float g[8], o[8];
+        unpack8(*reinterpret_cast<const uint4 *>(sG + off), g);
+        unpack8(*reinterpret_cast<const uint4 *>(sOt + off), o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dot = fmaf(g[i], o[i], dot); g[i] *= inv; }
+        *reinterpret_cast<uint4 *>(sG + off) = pack8(g);
+    }
+    return -dot * inv;
+}
+
+// partial column sums over 64 rows of a swizzled [128 x 64] bf16 tile, optionally weighted per row
+__device__ __forceinline__ float colsum_half(const uint8_t *tile, int e, int half, const float *w) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int j = 64 * half; j < 64 * half + 64; ++j) {
+        const __nv_bfloat16 x = *reinterpret_cast<const __nv_bfloat16 *>(tile + sw128_off(j, e >> 3) + (e & 7) * 2);
+        s = fmaf(__bfloat162float(x), w ? w[j] : 1.f, s);
+    }
+    return s;
+}
+
+// TMEM [rows of this warp] x 128 columns -> (+ optional per-row / per-column add) -> triangular mask -> bf16 -> sX
+// LOWER: keep j <= r (dq pass).  else keep i >= r (dk/dv pass).
+template <bool LOWER>
+__device__ __forceinline__ void convert_x(uint32_t t_lane, uint8_t *sX, int tid, int warp, float row_add, const float *col_add) {
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+        uint32_t r[32];
+        const bool live = LOWER ? (p <= warp) : (p >= warp);
+        const bool diag = p == warp;
+        if (live) {
+            tmem_ld32(t_lane + TB_X + 32 * p, r);
+            tmem_ld_wait();
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c0 = 32 * p + 8 * cc + 2 * i;
+                float a = 0.f, b = 0.f;
+                if (live) {
+                    a = __uint_as_float(r[8 * cc + 2 * i]) + row_add + (col_add ? col_add[c0] : 0.f);
+                    b = __uint_as_float(r[8 * cc + 2 * i + 1]) + row_add + (col_add ? col_add[c0 + 1] : 0.f);
+                    if (diag) {
+                        if (LOWER) { a = c0 <= tid ? a : 0.f; b = c0 + 1 <= tid ? b : 0.f; }
+                        else { a = c0 >= tid ? a : 0.f; b = c0 + 1 >= tid ? b : 0.f; }
+                    }
+                }
+                w[i] = pack_bf16(a, b);
+            }
+            *reinterpret_cast<uint4 *>(sX + (p >> 1) * TILE_BYTES + sw128_off(tid, (p & 1) * 4 + cc)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+}
+
+// carried 64x64 state: TMEM (M=64 layout: lanes 0..15 of each warp) -> bf16 tile rows e
+__device__ __forceinline__ void state_to_smem(uint32_t t_lane, uint8_t *sS, int lane, int erow) {
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + TB_ST + 32 * half, r);
+        tmem_ld_wait();
+        if (lane < 16) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                uint4 pk;
+                pk.x = pack_bf16(__uint_as_float(r[8 * cc + 0]), __uint_as_float(r[8 * cc + 1]));
+                pk.y = pack_bf16(__uint_as_float(r[8 * cc + 2]), __uint_as_float(r[8 * cc + 3]));
+                pk.z = pack_bf16(__uint_as_float(r[8 * cc + 4]), __uint_as_float(r[8 * cc + 5]));
+                pk.w = pack_bf16(__uint_as_float(r[8 * cc + 6]), __uint_as_float(r[8 * cc + 7]));
+                *reinterpret_cast<uint4 *>(sS + sw128_off(erow, half * 4 + cc)) = pk;
+            }
+        }
+    }
+}
+
+__device__ __forceinline__ void seed_state(const float *init, uint32_t t_lane, uint8_t *sS, int lane, int erow) {
+    uint32_t r[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(init[erow * 64 + half * 32 + i]);
+        tmem_st32(t_lane + TB_ST + half * 32, r);
+        if (lane < 16) {
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                uint4 pk;
+                pk.x = pack_bf16(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
+                pk.y = pack_bf16(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
+                pk.z = pack_bf16(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
+                pk.w = pack_bf16(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
+                *reinterpret_cast<uint4 *>(sS + sw128_off(erow, half * 4 + c)) = pk;
+            }
+        }
+    }
+    tmem_st_wait();
+}
+
+struct BwdArgs {
+    const float *den;
+    const float *ws_fwd, *ws_rev;
+    int L, H, nseg, seg_len;
+};
+
+// ---------------------------------------------------------------------------------------------
+// dq pass
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 2)
+linattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                         const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmGo,
+                         const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmGq, BwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = sm + B_OFF_Q, *sK = sm + B_OFF_K, *sV = sm + B_OFF_V, *sG = sm + B_OFF_G, *sX = sm + B_OFF_X, *sS = sm + B_OFF_S;
+    float *sz = reinterpret_cast<float *>(sm + B_OFF_Z), *sdz = reinterpret_cast<float *>(sm + B_OFF_DZ);
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + B_OFF_BAR), *bar_mma = bar_load + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + B_OFF_TMEM);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int seg = blockIdx.x % a.nseg, nh = blockIdx.x / a.nseg, n = nh / a.H, h = nh % a.H;
+    const int col0 = h * 64;
+    const int t_begin = seg * a.seg_len, t_end = min(a.L, t_begin + a.seg_len);
+    const int nchunks = (t_end - t_begin) / CHUNK;
+    const int row_base = n * a.L + t_begin;
+    if (tid == 0) {
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    const float *init = (a.nseg > 1 && seg > 0) ? a.ws_fwd + (int64_t)blockIdx.x * STATE_FLOATS : nullptr;
+    if (tid < 64) sz[tid] = init ? init[4096 + tid] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int erow = 16 * warp + (lane & 15);
+    bool have_state = init != nullptr;
+    if (have_state) {
+        seed_state(init, t_lane, sS, lane, erow);
+        fence_proxy_async();
+    }
+    const uint64_t dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV)), dG = smem_desc_sw128(smem_u32(sG));
+    const uint64_t dX = smem_desc_sw128(smem_u32(sX)), dS = smem_desc_sw128(smem_u32(sS));
+    auto issue_loads = [&](int grow) {
+        mbar_expect_tx(bar_load, 5 * TILE_BYTES);
+        tma_load_2d(sQ, &tmQ, bar_load, col0, grow);
+        tma_load_2d(sK, &tmK, bar_load, col0, grow);
+        tma_load_2d(sV, &tmV, bar_load, col0, grow);
+        tma_load_2d(sG, &tmGo, bar_load, col0, grow);
+        tma_load_2d(sX, &tmO, bar_load, col0, grow);          // out tile parks in sX block 0 until X is written
+    };
+    if (tid == 0 && nchunks > 0) issue_loads(row_base);
+    tc_fence_before();
+    __syncthreads();
+    uint32_t ph_load = 0, ph_mma = 0;
+    for (int c = 0; c < nchunks; ++c) {
+        const int grow = row_base + c * CHUNK;
+        const float *zc = sz + 64 * (c & 1);
+        float *zn = sz + 64 * ((c + 1) & 1);
+        mbar_wait(bar_load, ph_load);
+        ph_load ^= 1;
+        const float inv = 1.f / a.den[(int64_t)(grow + tid) * a.H + h];
+        const float gd = prep_grad_row(sG, sX, tid, inv);
+        uint32_t qraw[32];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t off = sw128_off(tid, ch);
+            float f[8];
+            *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+            const uint4 qv = *reinterpret_cast<const uint4 *>(sQ + off);
+            qraw[4 * ch + 0] = qv.x; qraw[4 * ch + 1] = qv.y; qraw[4 * ch + 2] = qv.z; qraw[4 * ch + 3] = qv.w;
+        }
+        if (tid == 0) tma_store_wait_read0();      // previous chunk's dq store has finished reading sX block 1
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {                      // X = G' V^T
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dG + 2 * k, dV + 2 * k, IDESC_KK128, k > 0);
+            mma_commit(bar_mma);
+        }
+        sdz[64 * (tid >> 6) + (tid & 63)] = colsum_half(sK, tid & 63, tid >> 6, nullptr);     // overlaps the MMA
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        convert_x<true>(t_lane, sX, tid, warp, gd, nullptr);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // dQf = X Kf
+                mma_ss(tmem + TB_ACC, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dK + 128 * k, IDESC_KM64, k > 0);
+            if (have_state) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_ACC, dG + 2 * k, dS + 2 * k, IDESC_KK64, 1);     // + G' S^T
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem + TB_ST, dK + 128 * k, dV + 128 * k, IDESC_MM64, (have_state || k > 0) ? 1u : 0u);
+            mma_commit(bar_mma);
+        }
+        have_state = true;
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        if (tid == 0 && c + 1 < nchunks) issue_loads(grow + CHUNK);
+        // dq rows -> staging (sX block 1)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld32(t_lane + TB_ACC + 32 * half, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                float f[8], qf[8];
+                const int ch = half * 4 + cc;
+                unpack8(make_uint4(qraw[4 * ch], qraw[4 * ch + 1], qraw[4 * ch + 2], qraw[4 * ch + 3]), qf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) f[i] = (__uint_as_float(r[8 * cc + i]) + gd * zc[8 * ch + i]) * dphi(qf[i]);
+                *reinterpret_cast<uint4 *>(sX + TILE_BYTES + sw128_off(tid, ch)) = pack8(f);
+            }
+        }
+        if (c + 1 < nchunks) {
+            state_to_smem(t_lane, sS, lane, erow);
+            if (tid < 64) zn[tid] = zc[tid] + sdz[tid] + sdz[64 + tid];
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_2d(&tmGq, sX + TILE_BYTES, col0, grow);
+            tma_store_commit();
+        }
+    }
+    if (tid == 0) tma_store_wait_all0();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
+// ---------------------------------------------------------------------------------------------
+// dk / dv pass
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 2)
+linattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmGo,
+                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmGk,
+                          const __grid_constant__ CUtensorMap tmGv, BwdArgs a) {
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t *sQ = sm + B_OFF_Q, *sK = sm + B_OFF_K, *sV = sm + B_OFF_V, *sG = sm + B_OFF_G, *sX = sm + B_OFF_X, *sR = sm + B_OFF_S;
+    float *srz = reinterpret_cast<float *>(sm + B_OFF_Z), *sdr = reinterpret_cast<float *>(sm + B_OFF_DZ);
+    float *sgd = reinterpret_cast<float *>(sm + B_OFF_GD);
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + B_OFF_BAR), *bar_mma = bar_load + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + B_OFF_TMEM);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int seg = blockIdx.x % a.nseg, nh = blockIdx.x / a.nseg, n = nh / a.H, h = nh % a.H;
+    const int col0 = h * 64;
+    const int t_begin = seg * a.seg_len, t_end = min(a.L, t_begin + a.seg_len);
+    const int nchunks = (t_end - t_begin) / CHUNK;
+    const int row_base = n * a.L + t_begin;
+    if (tid == 0) {
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+    }
+    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    const float *init = (a.nseg > 1 && seg < a.nseg - 1) ? a.ws_rev + (int64_t)blockIdx.x * STATE_FLOATS : nullptr;
+    if (tid < 64) srz[tid] = init ? init[4096 + tid] : 0.f;
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int erow = 16 * warp + (lane & 15);
+    bool have_state = init != nullptr;
+    if (have_state) {
+        seed_state(init, t_lane, sR, lane, erow);
+        fence_proxy_async();
+    }
+    const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
+    const uint64_t dG = smem_desc_sw128(smem_u32(sG)), dX = smem_desc_sw128(smem_u32(sX)), dR = smem_desc_sw128(smem_u32(sR));
+    auto issue_loads = [&](int grow) {
+        mbar_expect_tx(bar_load, 5 * TILE_BYTES);
+        tma_load_2d(sQ, &tmQ, bar_load, col0, grow);
+        tma_load_2d(sK, &tmK, bar_load, col0, grow);
+        tma_load_2d(sV, &tmV, bar_load, col0, grow);
+        tma_load_2d(sG, &tmGo, bar_load, col0, grow);
+        tma_load_2d(sX, &tmO, bar_load, col0, grow);
+    };
+    if (tid == 0 && nchunks > 0) issue_loads(row_base + (nchunks - 1) * CHUNK);
+    tc_fence_before();
+    __syncthreads();
+    uint32_t ph_load = 0, ph_mma = 0;
+    for (int it = 0; it < nchunks; ++it) {
+        const int c = nchunks - 1 - it;
+        const int grow = row_base + c * CHUNK;
+        const float *rzc = srz + 64 * (it & 1);
+        float *rzn = srz + 64 * ((it + 1) & 1);
+        mbar_wait(bar_load, ph_load);
+        ph_load ^= 1;
+        const float inv = 1.f / a.den[(int64_t)(grow + tid) * a.H + h];
+        sgd[tid] = prep_grad_row(sG, sX, tid, inv);
+        uint32_t kfr[32];
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t off = sw128_off(tid, ch);
+            float f[8];
+            *reinterpret_cast<uint4 *>(sQ + off) = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
+            const uint4 kv = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+            *reinterpret_cast<uint4 *>(sK + off) = kv;
+            kfr[4 * ch + 0] = kv.x; kfr[4 * ch + 1] = kv.y; kfr[4 * ch + 2] = kv.z; kfr[4 * ch + 3] = kv.w;
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {                      // X = PT = Kf Qf^T
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dQ + 2 * k, IDESC_KK128, k > 0);
+            mma_commit(bar_mma);
+        }
+        sdr[64 * (tid >> 6) + (tid & 63)] = colsum_half(sQ, tid & 63, tid >> 6, sgd);          // sum_i Qf[i][e] gd_i
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        convert_x<false>(t_lane, sX, tid, warp, 0.f, nullptr);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // dv = PT G'
+                mma_ss(tmem + TB_ACC, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
+            if (have_state) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_ACC, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);   // + Kf R
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dV + 2 * k, dG + 2 * k, IDESC_KK128, k > 0);      // X = WT = v G'^T
+            mma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        // dv rows -> staging in sK (Kf no longer needed as an operand; this thread keeps its row in kfr)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld32(t_lane + TB_ACC + 32 * half, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                uint4 pk;
+                pk.x = pack_bf16(__uint_as_float(r[8 * cc + 0]), __uint_as_float(r[8 * cc + 1]));
+                pk.y = pack_bf16(__uint_as_float(r[8 * cc + 2]), __uint_as_float(r[8 * cc + 3]));
+                pk.z = pack_bf16(__uint_as_float(r[8 * cc + 4]), __uint_as_float(r[8 * cc + 5]));
+                pk.w = pack_bf16(__uint_as_float(r[8 * cc + 6]), __uint_as_float(r[8 * cc + 7]));
+                *reinterpret_cast<uint4 *>(sK + sw128_off(tid, half * 4 + cc)) = pk;
+            }
+        }
+        convert_x<false>(t_lane, sX, tid, warp, 0.f, sgd);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_2d(&tmGv, sK, col0, grow);
+            tma_store_commit();
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)      // dKf = WT Qf
+                mma_ss(tmem + TB_ACC, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dQ + 128 * k, IDESC_KM64, k > 0);
+            if (have_state) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_ACC, dV + 2 * k, dR + 2 * k, IDESC_KK64, 1);      // + v R^T
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem + TB_ST, dQ + 128 * k, dG + 128 * k, IDESC_MM64, (have_state || k > 0) ? 1u : 0u);
+            mma_commit(bar_mma);
+        }
+        have_state = true;
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        // dk rows -> staging (sX block 1)
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t r[32];
+            tmem_ld32(t_lane + TB_ACC + 32 * half, r);
+            tmem_ld_wait();
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                float f[8], kf[8];
+                const int ch = half * 4 + cc;
+                unpack8(make_uint4(kfr[4 * ch], kfr[4 * ch + 1], kfr[4 * ch + 2], kfr[4 * ch + 3]), kf);
+#pragma unroll
+                for (int i = 0; i < 8; ++i)         // phi'(k) = phi(k) when phi(k) <= 1 (k <= 0), else 1
+                    f[i] = (__uint_as_float(r[8 * cc + i]) + rzc[8 * ch + i]) * (kf[i] <= 1.f ? kf[i] : 1.f);
+                *reinterpret_cast<uint4 *>(sX + TILE_BYTES + sw128_off(tid, ch)) = pack8(f);
+            }
+        }
+        if (it + 1 < nchunks) {
+            state_to_smem(t_lane, sR, lane, erow);
+            if (tid < 64) rzn[tid] = rzc[tid] + sdr[tid] + sdr[64 + tid];
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tma_store_2d(&tmGk, sX + TILE_BYTES, col0, grow);
+            tma_store_commit();
+            if (it + 1 < nchunks) {
+                tma_store_wait_read0();             // both staging tiles (sK, sX block 1) have been read out
+                issue_loads(grow - CHUNK);
+            }
+        }
+    }
+    if (tid == 0) tma_store_wait_all0();
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<256>(tmem);
+}
+
 }  // namespace
 
 int linattn_fwd_tc_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int64_t ld_qkv,
@@ -343,9 +818,45 @@ int linattn_fwd_tc_launch(const void *q, const void *k, const void *v, void *out
     return check_launch("linattn_fwd_tc");
 }
 
-int linattn_bwd_tc_launch(const void *, const void *, const void *, const void *, const float *, const void *, void *, void *, void *,
-                          int, int, int, int64_t, int64_t, int64_t, float, void *, cudaStream_t) {
-    return CPM_ERR_UNSUPPORTED;      // backward runs on the SIMT kernels until the tcgen05 version lands
+int linattn_bwd_tc_launch(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout,
+                          void *gq, void *gk, void *gv, int N, int L, int H, int64_t ld_qkv, int64_t ld_o, int64_t ld_g, float eps,
+                          void *ws, cudaStream_t st) {
+    (void)eps;
+    if (L % CHUNK != 0) return CPM_ERR_UNSUPPORTED;
+    int nseg, seg_len;
+    plan_segments(N, H, L, &nseg, &seg_len);
+    if (seg_len % CHUNK != 0) return CPM_ERR_UNSUPPORTED;
+    CUtensorMap tq, tk, tv, tgo, to, tgq, tgk, tgv;
+    int rc;
+    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
+    if ((rc = make_tmap_bf16_2d(&tq, q, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tgo, gout, inner, rows, ld_o, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&to, out, inner, rows, ld_o, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tgq, gq, inner, rows, ld_g, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tgk, gk, inner, rows, ld_g, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tgv, gv, inner, rows, ld_g, CHUNK))) return rc;
+    if (nseg > 1) {
+        rc = linattn_segment_states_launch(q, k, v, out, den, gout, N, L, H, ld_qkv, ld_o, CPM_BF16, ws, true, st);
+        if (rc) return rc;
+    }
+    static bool attr_set = false;
+    if (!attr_set) {
+        cudaError_t e = cudaFuncSetAttribute(linattn_bwd_dq_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+        if (e == cudaSuccess)
+            e = cudaFuncSetAttribute(linattn_bwd_dkv_tc_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)BWD_SMEM_BYTES);
+        if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "linattn_bwd_tc smem attribute: %s", cudaGetErrorString(e));
+        attr_set = true;
+    }
+    BwdArgs a;
+    a.den = den;
+    a.ws_fwd = (const float *)ws;
+    a.ws_rev = a.ws_fwd + (int64_t)N * H * nseg * STATE_FLOATS;
+    a.L = L; a.H = H; a.nseg = nseg; a.seg_len = seg_len;
+    linattn_bwd_dq_tc_kernel<<<N * H * nseg, 128, BWD_SMEM_BYTES, st>>>(tq, tk, tv, tgo, to, tgq, a);
+    linattn_bwd_dkv_tc_kernel<<<N * H * nseg, 128, BWD_SMEM_BYTES, st>>>(tq, tk, tv, tgo, to, tgk, tgv, a);
+    return check_launch("linattn_bwd_tc");
 }
 
 }  // namespace cpm

@@ -471,3 +471,26 @@ def test_linattn_tc_fwd_fused_layout_and_autograd(cuda, cpm):
     ro, rq, rk, rv = _oracle_attn(q, k, v, go.view(N, L, H, 64).float())
     _cmp(out.view(N, L, H, 64), ro, 3e-2, 2e-2, "out")
     _cmp(qkv.grad, torch.cat([t.reshape(N, L, H * 64) for t in (rq, rk, rv)], -1), 5e-2, 3e-2, "gqkv")
+
+
+@pytest.mark.parametrize("shape", [(1, 128, 1), (2, 256, 4), (3, 384, 2), (1, 2048, 2), (32, 512, 8)])
+def test_linattn_tc_bwd(cuda, cpm, shape):
+    """tcgen05 backward (impl=2) vs the fp64 oracle (small shapes) and vs the SIMT backward fed the
+    same saved out/den.  Tolerance: gradients are O(0.1-1); 4e-2 absolute + 3e-2 relative (bf16
+    rounding of G', of the masked score tiles and of the carried state)."""
+    N, L, H = shape
+    gen = torch.Generator().manual_seed(L * 3 + H)
+    q, k, v, go = (torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16() for _ in range(4))
+    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=2)
+    gq, gk, gv = (torch.empty_like(q) for _ in range(3))
+    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=2)
+    assert cpm.ops.linattn_last_impl() == "tcgen05"
+    torch.cuda.synchronize()
+    sq, sk, sv = (torch.empty_like(q) for _ in range(3))
+    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, sq, sk, sv, impl=1)
+    for name, a, b in (("gq", gq, sq), ("gk", gk, sk), ("gv", gv, sv)):
+        _cmp(a, b.float(), 4e-2, 3e-2, f"tc vs simt {name}")
+    if N * L * H <= 8192:
+        _, rq, rk, rv = _oracle_attn(q.float(), k.float(), v.float(), go.float())
+        for name, a, b in (("gq", gq, rq), ("gk", gk, rk), ("gv", gv, rv)):
+            _cmp(a, b, 4e-2, 3e-2, f"tc vs oracle {name}")
