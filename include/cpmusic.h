@@ -250,6 +250,21 @@ int cpm_rollout_advance(const int64_t *tokens, int64_t *history_tok, int64_t n_t
                         float *history_f, int64_t n_f, int32_t *step_dev, int32_t max_steps,
                         void *stream);
 
+/* Fused skinny linear layer for the recurrent rollout step (M = sequences <= 64, bf16):
+ *     Y[M,N] = epi( pro(A)[M,K] . W[N,K]^T + bias )
+ *   prologue 0: A as is;  1: LayerNorm(A) with fp32 gamma/beta (the post-norm of the previous
+ *               sub-layer folded into its consumer); xout (optional) receives the normalised A.
+ *   epilogue 0: +bias;  1: +bias, exact-erf GELU;  2: +bias + residual[M,N];
+ *            3: +bias + pe[pos,:] with pos = pos_dev ? *pos_dev : pos_offset (PositionalEncoding).
+ * Replaces, per token step, the Linear / LayerNorm / GELU / residual launches of ft's
+ * RecurrentTransformerEncoderLayer with one launch per Linear.
+ * W is the packed bf16 weight (rows = output features, K contiguous), bias bf16 (may be NULL).
+ * K % 64 == 0, K <= 2048, and 16*ceil(M/16)*(K+8)*2 bytes of shared memory must fit (<= 200 KB). */
+int cpm_skinny_linear(const void *A, int64_t lda, const void *W, const void *bias, void *Y, int64_t ldy,
+                      int M, int N, int K, int prologue, const float *gamma, const float *beta, float eps,
+                      void *xout, int epilogue, const void *residual, int64_t ldr, const float *pe,
+                      int pe_max_len, int pos_offset, const int32_t *pos_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

@@ -66,6 +66,8 @@ SIGNATURES = {
     "cpm_dqn_td_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, _IP, c_int, c_int,
                                    c_float, c_float, c_int, c_int, _P]),
     "cpm_rollout_advance": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int32, _P]),
+    "cpm_skinny_linear": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, c_int,
+                                  _P, c_int64, _P, c_int, c_int, _P, _P]),
 }
 
 _lib = None

@@ -675,3 +675,27 @@ def rollout_advance(tokens, history_tok, vals, history_f, step_dev, max_steps):
     n_f = vals.numel() if vals is not None else 0
     check(_lib.load().cpm_rollout_advance(_p(tokens), _p(history_tok), n_tok, _p(vals), _p(history_f), n_f, _p(step_dev),
                                           max_steps, _st()))
+
+
+# --------------------------------------------------------------------------- fused skinny linear (rollout step)
+EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_PE = 0, 1, 2, 3
+
+
+def skinny_linear(a, wc, bc, n_out=None, ln=None, xout=None, epilogue=EPI_BIAS, residual=None, pe=None, pos_offset=0,
+                  pos_dev=None, out=None):
+    """Y = epi(pro(a) @ wc^T + bc) in ONE launch (no autograd; inference / rollout only).
+    a (M,K) bf16, wc (N_pad,K) bf16 packed weight, bc (N_pad) bf16.  ln = (gamma, beta, eps) applies
+    LayerNorm to `a` first (and writes it to `xout` if given)."""
+    _cuda(a, wc)
+    if a.dtype != torch.bfloat16 or wc.dtype != torch.bfloat16:
+        raise ValueError("skinny_linear is bf16 only")
+    M, K = a.shape
+    N = wc.shape[0] if n_out is None else n_out
+    y = out if out is not None else torch.empty(M, wc.shape[0], dtype=torch.bfloat16, device=a.device)
+    gamma, beta, eps = (ln if ln is not None else (None, None, 0.0))
+    pe2 = None if pe is None else pe.reshape(-1, pe.shape[-1])
+    check(_lib.load().cpm_skinny_linear(_p(a), a.stride(0), _p(wc), _p(bc), _p(y), y.stride(0), M, N, K,
+                                        0 if ln is None else 1, _p(gamma), _p(beta), eps, _p(xout), epilogue,
+                                        _p(residual), 0 if residual is None else residual.stride(0), _p(pe2),
+                                        0 if pe2 is None else pe2.shape[0], pos_offset, _p(pos_dev), _st()))
+    return y

@@ -18,7 +18,8 @@ from . import _lib, ops
 
 class RolloutEngine:
     def __init__(self, model, batch: int, max_steps: int, greedy: bool = False, true_positions: bool = True,
-                 temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True):
+                 temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True,
+                 fused: Optional[bool] = None):
         self.model, self.N, self.max_steps = model, batch, max_steps
         self.greedy, self.true_positions = greedy, true_positions
         self.temperature, self.top_p = model.sampling_config(temperature, top_p)
@@ -36,13 +37,62 @@ class RolloutEngine:
         self.hist_logp = torch.zeros(max_steps, batch, A, dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = None
+        self.fused = self.fused_supported() if fused is None else bool(fused)
+        if self.fused and not self.fused_supported():
+            raise ValueError("fused rollout step needs bf16 compute, <= 32 sequences and 64-aligned widths <= 2048")
+
+    # ---- logits of the next token for every sequence, given self.cur and the recurrent state -------
+    def fused_supported(self) -> bool:
+        """The fused skinny-GEMM step needs bf16, <= 32 sequences (activation tile in shared memory
+        up to K = d_inner = 2048) and 64-aligned widths."""
+        m = self.model
+        widths = (m.d_model, m.d_inner, int(sum(m.emb_sizes)))
+        return (m.compute_dtype == torch.bfloat16 and self.N <= 32 and all(w % 64 == 0 and w <= 2048 for w in widths))
+
+    def _logits_unfused(self):
+        m = self.model
+        z = m._embed(self.cur[:, None, :], 0, self.step_dev if self.true_positions else None)
+        h, _ = m.transformer_encoder.step_fused(z.view(self.N, m.d_model), self.state)
+        return m.logits_concat(h)
+
+    def _logits_fused(self):
+        """Same arithmetic with one launch per Linear layer: LayerNorms are folded into the consumer
+        GEMM's prologue, bias / GELU / residual / positional encoding into its epilogue
+        (5 launches per layer instead of 8-9)."""
+        m, enc, N = self.model, self.model.transformer_encoder, self.N
+        dt, H = torch.bfloat16, enc.n_heads
+        emb = ops.cp_embed(self.cur[:, None, :], m._tables(), dt).view(N, -1)
+        w, b, _, _ = m._cache.get("in", [m.in_linear], dt)
+        x = ops.skinny_linear(emb, w, b, epilogue=ops.EPI_PE, pe=m.pos_emb.pe,
+                              pos_dev=self.step_dev if self.true_positions else None)
+        s_prev, prev = None, None
+        for i, layer in enumerate(enc.layers):
+            at = layer.attention
+            wq, bq, _, _ = enc._cache.get(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], dt)
+            if i == 0:
+                xin, qkv = x, ops.skinny_linear(x, wq, bq)
+            else:
+                xin = torch.empty(N, m.d_model, dtype=dt, device=x.device)
+                qkv = ops.skinny_linear(s_prev, wq, bq, ln=(prev.norm2.weight, prev.norm2.bias, prev.norm2.eps), xout=xin)
+            q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
+            a = ops.linattn_step(q, k, v, self.state[i][0], self.state[i][1]).view(N, H * 64)
+            wo, bo, _, _ = enc._cache.get(("out", i), [at.out_projection], dt)
+            s1 = ops.skinny_linear(a, wo, bo, epilogue=ops.EPI_RESIDUAL, residual=xin)
+            w1, b1, _, _ = enc._cache.get(("ff1", i), [layer.linear1], dt)
+            x1 = torch.empty(N, m.d_model, dtype=dt, device=x.device)
+            hmid = ops.skinny_linear(s1, w1, b1, ln=(layer.norm1.weight, layer.norm1.bias, layer.norm1.eps), xout=x1,
+                                     epilogue=ops.EPI_GELU)
+            w2, b2, _, _ = enc._cache.get(("ff2", i), [layer.linear2], dt)
+            s_prev = ops.skinny_linear(hmid, w2, b2, epilogue=ops.EPI_RESIDUAL, residual=x1)
+            prev = layer
+        xl = ops.ln_residual(s_prev, None, prev.norm2.weight, prev.norm2.bias, prev.norm2.eps, 0.0)
+        wh, bh, _, _ = m._cache.get("heads", m._heads(), dt, 8)
+        return ops.skinny_linear(xl, wh, bh, ln=(enc.norm.weight, enc.norm.bias, enc.norm.eps))
 
     # one token for every sequence: reads self.cur, overwrites self.cur with the sampled token
     def _step(self):
         m = self.model
-        z = m._embed(self.cur[:, None, :], 0, self.step_dev if self.true_positions else None)
-        h, _ = m.transformer_encoder.step_fused(z.view(self.N, m.d_model), self.state)
-        lc = m.logits_concat(h)
+        lc = self._logits_fused() if self.fused else self._logits_unfused()
         ops.heads_sample(lc, m.seg, self.temperature, self.top_p, greedy=self.greedy, seed=self.seed,
                          seq_base=self.seq_base, step_dev=self.step_dev, tokens_out=self.cur, logp_out=self.logp)
         ops.rollout_advance(self.cur, self.hist_tok, self.logp, self.hist_logp, self.step_dev, self.max_steps)

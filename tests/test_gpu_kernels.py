@@ -494,3 +494,37 @@ def test_linattn_tc_bwd(cuda, cpm, shape):
         _, rq, rk, rv = _oracle_attn(q.float(), k.float(), v.float(), go.float())
         for name, a, b in (("gq", gq, rq), ("gk", gk, rk), ("gv", gv, rv)):
             _cmp(a, b, 4e-2, 3e-2, f"tc vs oracle {name}")
+
+
+# ------------------------------------------------------------------ fused skinny linear (rollout step)
+@pytest.mark.parametrize("M,N,K", [(32, 1536, 512), (32, 512, 2048), (32, 2048, 512), (32, 512, 1216), (32, 344, 512),
+                                   (5, 384, 128), (1, 512, 512), (16, 256, 256), (17, 344, 192)])
+def test_skinny_linear_variants(cuda, cpm, M, N, K):
+    """One-launch Linear with LayerNorm prologue and bias/GELU/residual/PE epilogues vs the PyTorch
+    composition in fp64 on the same bf16 inputs; tolerance 2e-2 abs + 2e-2 rel (bf16 output rounding
+    of O(1-10) values, bf16 normalised activations)."""
+    gen = torch.Generator().manual_seed(M * 7 + N + K)
+    a = torch.randn(M, K, generator=gen).to(cuda).bfloat16()
+    w = (torch.randn(N, K, generator=gen) / K ** 0.5).to(cuda).bfloat16()
+    b = torch.randn(N, generator=gen).to(cuda).bfloat16()
+    res = torch.randn(M, N, generator=gen).to(cuda).bfloat16()
+    gamma = (1 + 0.1 * torch.randn(K, generator=gen)).to(cuda)
+    beta = (0.1 * torch.randn(K, generator=gen)).to(cuda)
+    pe = torch.randn(50, N, generator=gen).to(cuda)
+    ad, wd, bd = a.double(), w.double(), b.double()
+    lin = lambda x: x @ wd.t() + bd
+    ops = cpm.ops
+    _cmp(ops.skinny_linear(a, w, b), lin(ad), 2e-2, 2e-2, "bias")
+    _cmp(ops.skinny_linear(a, w, None), ad @ wd.t(), 2e-2, 2e-2, "no bias")
+    _cmp(ops.skinny_linear(a, w, b, epilogue=ops.EPI_GELU), torch.nn.functional.gelu(lin(ad)), 2e-2, 2e-2, "gelu")
+    _cmp(ops.skinny_linear(a, w, b, epilogue=ops.EPI_RESIDUAL, residual=res), lin(ad) + res.double(), 3e-2, 2e-2, "residual")
+    _cmp(ops.skinny_linear(a, w, b, epilogue=ops.EPI_PE, pe=pe, pos_offset=7), lin(ad) + pe[7].double(), 3e-2, 2e-2, "pe")
+    pos = torch.tensor([11], dtype=torch.int32, device=cuda)
+    _cmp(ops.skinny_linear(a, w, b, epilogue=ops.EPI_PE, pe=pe, pos_dev=pos), lin(ad) + pe[11].double(), 3e-2, 2e-2, "pe dev")
+    xn = torch.nn.functional.layer_norm(ad, (K,), gamma.double(), beta.double(), 1e-5)
+    xout = torch.zeros(M, K, device=cuda, dtype=torch.bfloat16)
+    y = ops.skinny_linear(a, w, b, ln=(gamma, beta, 1e-5), xout=xout, epilogue=ops.EPI_GELU)
+    _cmp(xout, xn, 2e-2, 1e-2, "xout = LayerNorm(a)")
+    _cmp(y, torch.nn.functional.gelu(lin(xout.double())), 2e-2, 2e-2, "LN prologue + gelu")
+    with pytest.raises(ValueError):
+        ops.skinny_linear(torch.zeros(65, K, device=cuda, dtype=torch.bfloat16), w, b)
