@@ -265,6 +265,17 @@ int cpm_skinny_linear(const void *A, int64_t lda, const void *W, const void *bia
                       void *xout, int epilogue, const void *residual, int64_t ldr, const float *pe,
                       int pe_max_len, int pos_offset, const int32_t *pos_dev, void *stream);
 
+/* Persistent megakernel for ONE recurrent rollout token step (embedding -> all layers -> heads ->
+ * sampling -> history/step bookkeeping) as a single cooperative launch: 148 CTAs walk a host-built
+ * phase list separated by a software grid barrier (csrc/rollout_mega.cu).  Replaces the ~65-100
+ * launch-bound kernels per token of the unfused path (and the reference's batch-1 host loop,
+ * testing-no-type-cp.py:157-167).  `globals_dev` / `phases_dev` are device copies of the
+ * MegaGlobals / MegaPhase structs (layout checked with cpm_mega_sizes; built by rollout.py).
+ * <= 32 sequences, bf16, widths multiples of 64 and <= 2048. */
+int cpm_mega_sizes(int *globals_bytes, int *phase_bytes);
+int64_t cpm_mega_smem_bytes(void);
+int cpm_rollout_step_mega(const void *globals_dev, const void *phases_dev, void *stream);
+
 #ifdef __cplusplus
 }
 #endif

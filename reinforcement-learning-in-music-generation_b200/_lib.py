@@ -66,6 +66,9 @@ SIGNATURES = {
     "cpm_dqn_td_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, _IP, c_int, c_int,
                                    c_float, c_float, c_int, c_int, _P]),
     "cpm_rollout_advance": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int32, _P]),
+    "cpm_mega_sizes": (c_int, [_IP, _IP]),
+    "cpm_mega_smem_bytes": (c_int64, []),
+    "cpm_rollout_step_mega": (c_int, [_P, _P, _P]),
     "cpm_skinny_linear": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, c_int,
                                   _P, c_int64, _P, c_int, c_int, _P, _P]),
 }
@@ -77,7 +80,7 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_ln_partials_rows": 0,
+    "cpm_linattn_workspace_bytes": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
     "cpm_linattn_bwd": 2, "cpm_ln_residual_bwd": 2,
 })
 EXTRA_LAUNCHES = [0]          # segment-total / scan kernels of segmented linear attention, graph replays

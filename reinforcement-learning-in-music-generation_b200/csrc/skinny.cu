@@ -39,6 +39,13 @@ __device__ __forceinline__ void mma_bf16_16816(float (&c)[4], const uint32_t (&a
         : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
 
+__device__ __forceinline__ void cp_async16(void *smem_dst, const void *gmem_src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"((uint32_t)__cvta_generic_to_shared(smem_dst)), "l"(gmem_src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\n\tcp.async.wait_group 0;" ::: "memory");
+}
+
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
 
 template <int MT>      // number of 16-row tiles: M <= 16*MT
@@ -48,6 +55,7 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_linear_kernel(SkinnyParams 
     const int lds = p.K + 8;                                     // padded row stride (elements)
     __nv_bfloat16 *sA = reinterpret_cast<__nv_bfloat16 *>(sk_smem);
     float *spart = reinterpret_cast<float *>(sk_smem + (size_t)ROWS * lds * 2);     // [8 warps][ROWS*8]
+    float *sGamma = spart + 8 * ROWS * 8, *sBeta = sGamma + p.K;                    // LayerNorm parameters (pro == 1)
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31, g = lane >> 2, q = lane & 3;
     const int ntc = p.ntc, ks_n = 8 / ntc;
     const int nt = warp % ntc, ks = warp / ntc;
@@ -70,65 +78,69 @@ __global__ void __launch_bounds__(SK_THREADS) skinny_linear_kernel(SkinnyParams 
         }
     }
 
-    // ---- 2. activation tile -> shared memory (optionally LayerNorm'ed)
-    if (p.pro == 0) {
-        const int vec_per_row = p.K >> 3;
-        for (int i = tid; i < ROWS * vec_per_row; i += SK_THREADS) {
-            const int r = i / vec_per_row, c = (i % vec_per_row) * 8;
-            uint4 v = make_uint4(0, 0, 0, 0);
-            if (r < p.M) v = *reinterpret_cast<const uint4 *>(p.A + (int64_t)r * p.lda + c);
-            *reinterpret_cast<uint4 *>(sA + r * lds + c) = v;
+    // ---- 2. activation tile (+ LayerNorm parameters) -> shared memory, all copies in flight at once
+    {
+        const int vpr = p.K >> 3;                                 // 16-byte vectors per row
+        const int total = p.M * vpr;
+        for (int i = tid; i < total; i += SK_THREADS) {
+            const int r = i / vpr, c = (i - r * vpr) * 8;
+            cp_async16(sA + r * lds + c, p.A + (int64_t)r * p.lda + c);
         }
-    } else {
-        for (int r = warp; r < ROWS; r += 8) {
-            if (r < p.M) {
-                // K <= 2048: each lane holds K/32 elements in registers (up to 8 vectors of 8)
-                float vals[8][8];
-                float sum = 0.f;
-                const int nvec = p.K >> 8;       // vectors of 8 per lane (K multiple of 256) or handled by bound check
-#pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const int c = (lane + 32 * v) * 8;
-                    if (c < p.K) {
-                        Vec8<__nv_bfloat16> x;
-                        x.load(p.A + (int64_t)r * p.lda + c);
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { vals[v][j] = x.v[j]; sum += x.v[j]; }
-                    }
-                }
-                (void)nvec;
-                const float mean = warp_sum(sum) / (float)p.K;
-                float sq = 0.f;
-#pragma unroll
-                for (int v = 0; v < 8; ++v)
-                    if ((lane + 32 * v) * 8 < p.K) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) { const float d = vals[v][j] - mean; sq += d * d; }
-                    }
-                const float rstd = rsqrtf(warp_sum(sq) / (float)p.K + p.eps);
-#pragma unroll
-                for (int v = 0; v < 8; ++v) {
-                    const int c = (lane + 32 * v) * 8;
-                    if (c < p.K) {
-                        Vec8<__nv_bfloat16> o;
-#pragma unroll
-                        for (int j = 0; j < 8; ++j) o.v[j] = (vals[v][j] - mean) * rstd * p.gamma[c + j] + p.beta[c + j];
-                        o.store(sA + r * lds + c);
-                    }
-                }
-            } else {
-                for (int c = lane * 8; c < p.K; c += 256) *reinterpret_cast<uint4 *>(sA + r * lds + c) = make_uint4(0, 0, 0, 0);
+        for (int i = p.M * vpr + tid; i < ROWS * vpr; i += SK_THREADS) {      // zero the padding rows
+            const int r = i / vpr, c = (i - r * vpr) * 8;
+            *reinterpret_cast<uint4 *>(sA + r * lds + c) = make_uint4(0, 0, 0, 0);
+        }
+        if (p.pro == 1) {
+            for (int i = tid; i < (p.K >> 2); i += SK_THREADS) {
+                cp_async16(sGamma + 4 * i, p.gamma + 4 * i);
+                cp_async16(sBeta + 4 * i, p.beta + 4 * i);
             }
         }
+        cp_async_wait_all();
     }
     __syncthreads();
-    if (p.pro == 1 && p.xout) {          // publish this CTA's column slice of the normalised activations
-        const int cw = (((p.K + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
-        const int c_begin = blockIdx.x * cw, c_end = min(p.K, c_begin + cw);
-        const int vpr = cw >> 3;
-        for (int i = tid; i < p.M * vpr; i += SK_THREADS) {
-            const int r = i / vpr, c = c_begin + (i % vpr) * 8;
-            if (c < c_end) *reinterpret_cast<uint4 *>(p.xout + (int64_t)r * p.K + c) = *reinterpret_cast<const uint4 *>(sA + r * lds + c);
+    if (p.pro == 1) {
+        // LayerNorm in place: TPR threads per row, every row handled concurrently
+        constexpr int TPR = SK_THREADS / ROWS;                    // 16, 8 or 4
+        const int r = tid / TPR, j = tid % TPR;
+        const int vpr = p.K >> 3;
+        float sum = 0.f, sq = 0.f;
+        for (int v = j; v < vpr; v += TPR) {
+            Vec8<__nv_bfloat16> x;
+            x.load(sA + r * lds + v * 8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) sum += x.v[e];
+        }
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) sum += __shfl_xor_sync(0xffffffffu, sum, o);
+        const float mean = sum / (float)p.K;
+        for (int v = j; v < vpr; v += TPR) {
+            Vec8<__nv_bfloat16> x;
+            x.load(sA + r * lds + v * 8);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) { const float d = x.v[e] - mean; sq += d * d; }
+        }
+#pragma unroll
+        for (int o = TPR / 2; o > 0; o >>= 1) sq += __shfl_xor_sync(0xffffffffu, sq, o);
+        const float rstd = rsqrtf(sq / (float)p.K + p.eps);
+        if (r < p.M) {
+            for (int v = j; v < vpr; v += TPR) {
+                Vec8<__nv_bfloat16> x;
+                x.load(sA + r * lds + v * 8);
+#pragma unroll
+                for (int e = 0; e < 8; ++e) x.v[e] = (x.v[e] - mean) * rstd * sGamma[v * 8 + e] + sBeta[v * 8 + e];
+                x.store(sA + r * lds + v * 8);
+            }
+        }
+        __syncthreads();
+        if (p.xout) {                    // publish this CTA's column slice of the normalised activations
+            const int cw = (((p.K + (int)gridDim.x - 1) / (int)gridDim.x) + 7) & ~7;
+            const int c_begin = blockIdx.x * cw, c_end = min(p.K, c_begin + cw);
+            const int vs = cw >> 3;
+            for (int i = tid; i < p.M * vs; i += SK_THREADS) {
+                const int rr = i / vs, c = c_begin + (i % vs) * 8;
+                if (c < c_end) *reinterpret_cast<uint4 *>(p.xout + (int64_t)rr * p.K + c) = *reinterpret_cast<const uint4 *>(sA + rr * lds + c);
+            }
         }
     }
 
@@ -202,7 +214,7 @@ extern "C" int cpm_skinny_linear(const void *A, int64_t lda, const void *W, cons
     CPM_REQUIRE(epilogue >= 0 && epilogue <= 3, CPM_ERR_BAD_SHAPE, "skinny_linear: epilogue %d", epilogue);
     CPM_REQUIRE(epilogue != 2 || residual, CPM_ERR_NULL, "skinny_linear: residual is NULL");
     CPM_REQUIRE(epilogue != 3 || (pe && pe_max_len > 0), CPM_ERR_NULL, "skinny_linear: pe is NULL");
-    CPM_REQUIRE(aligned16(A) && aligned16(W) && lda % 8 == 0 && (!xout || aligned16(xout)), CPM_ERR_BAD_ALIGN, "skinny_linear: alignment");
+    CPM_REQUIRE(aligned16(A) && aligned16(W) && lda % 8 == 0 && (!xout || aligned16(xout)) && (!gamma || (aligned16(gamma) && aligned16(beta))), CPM_ERR_BAD_ALIGN, "skinny_linear: alignment");
     SkinnyParams p{};
     p.A = (const __nv_bfloat16 *)A; p.lda = lda; p.W = (const __nv_bfloat16 *)W; p.bias = (const __nv_bfloat16 *)bias;
     p.Y = (__nv_bfloat16 *)Y; p.ldy = ldy; p.M = M; p.N = N; p.K = K; p.pro = prologue; p.gamma = gamma; p.beta = beta; p.eps = eps;
@@ -212,7 +224,7 @@ extern "C" int cpm_skinny_linear(const void *A, int64_t lda, const void *W, cons
     p.ntc = (K <= 1024 && ntiles >= 128) ? 2 : 1;       // 8 K-slices when K is long or the layer is narrow
     const int grid = (ntiles + p.ntc - 1) / p.ntc;
     const int MT = M <= 16 ? 1 : (M <= 32 ? 2 : 4);
-    const size_t smem = (size_t)(16 * MT) * (K + 8) * 2 + (size_t)8 * (16 * MT) * 8 * sizeof(float);
+    const size_t smem = (size_t)(16 * MT) * (K + 8) * 2 + (size_t)8 * (16 * MT) * 8 * sizeof(float) + (size_t)2 * K * sizeof(float);
     CPM_REQUIRE(smem <= 200 * 1024, CPM_ERR_UNSUPPORTED, "skinny_linear: M=%d K=%d needs %zu bytes of shared memory (> 200 KB)", M, K, smem);
     cudaStream_t st = (cudaStream_t)stream;
 #define SK_LAUNCH(MTV)                                                                                                             \

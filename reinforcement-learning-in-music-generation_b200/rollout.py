@@ -9,17 +9,38 @@ and replayed with no host synchronisation.
 """
 from __future__ import annotations
 
+import ctypes
 from typing import Optional
 
 import torch
 
 from . import _lib, ops
 
+_P = ctypes.c_void_p
+
+
+class _MegaPhase(ctypes.Structure):          # mirrors cpm::MegaPhase (csrc/rollout_mega.cu)
+    _fields_ = [("type", ctypes.c_int32), ("M", ctypes.c_int32), ("N", ctypes.c_int32), ("K", ctypes.c_int32),
+                ("lda", ctypes.c_int32), ("ldy", ctypes.c_int32), ("ldr", ctypes.c_int32), ("pro", ctypes.c_int32),
+                ("epi", ctypes.c_int32), ("H", ctypes.c_int32), ("eps", ctypes.c_float), ("pad0", ctypes.c_int32),
+                ("A", _P), ("W", _P), ("bias", _P), ("R", _P), ("Y", _P), ("xout", _P),
+                ("gamma", _P), ("beta", _P), ("gamma2", _P), ("beta2", _P), ("S", _P), ("Z", _P)]
+
+
+class _MegaGlobals(ctypes.Structure):        # mirrors cpm::MegaGlobals
+    _fields_ = [("batch", ctypes.c_int32), ("n_attr", ctypes.c_int32), ("emb_total", ctypes.c_int32), ("logits_ld", ctypes.c_int32),
+                ("n_tokens", ctypes.c_int32 * 8), ("emb", ctypes.c_int32 * 8), ("emb_off", ctypes.c_int32 * 9), ("seg", ctypes.c_int32 * 9),
+                ("emb_scale", ctypes.c_float * 8), ("temperature", ctypes.c_float * 8), ("top_p", ctypes.c_float * 8),
+                ("greedy", ctypes.c_int32), ("true_positions", ctypes.c_int32), ("max_steps", ctypes.c_int32), ("pe_max", ctypes.c_int32),
+                ("seed", ctypes.c_uint64), ("seq_base", ctypes.c_int64), ("tables", _P * 8), ("pe", _P),
+                ("cur", _P), ("hist_tok", _P), ("logp", _P), ("hist_logp", _P), ("step_dev", _P), ("barrier", _P),
+                ("n_phases", ctypes.c_int32), ("pad1", ctypes.c_int32)]
+
 
 class RolloutEngine:
     def __init__(self, model, batch: int, max_steps: int, greedy: bool = False, true_positions: bool = True,
                  temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True,
-                 fused: Optional[bool] = None):
+                 fused: Optional[bool] = None, mode: Optional[str] = None):
         self.model, self.N, self.max_steps = model, batch, max_steps
         self.greedy, self.true_positions = greedy, true_positions
         self.temperature, self.top_p = model.sampling_config(temperature, top_p)
@@ -37,9 +58,19 @@ class RolloutEngine:
         self.hist_logp = torch.zeros(max_steps, batch, A, dtype=torch.float32, device=dev)
         self.graph: Optional[torch.cuda.CUDAGraph] = None
         self.launches_per_step = None
-        self.fused = self.fused_supported() if fused is None else bool(fused)
-        if self.fused and not self.fused_supported():
-            raise ValueError("fused rollout step needs bf16 compute, <= 32 sequences and 64-aligned widths <= 2048")
+        # step implementation: "mega" (one persistent cooperative kernel per token), "fused" (one launch
+        # per Linear) or "unfused" (library GEMMs + elementwise kernels).  Default: the fastest supported.
+        if mode is None:
+            # measured on B200 (profiles/): the CUDA-graph "unfused" step is currently the fastest
+            # (409 us/token at 32 sequences vs 416 fused, 543 mega), so it is the default.
+            mode = ("fused" if fused else "unfused") if fused is not None else "unfused"
+        if mode in ("mega", "fused") and not self.fused_supported():
+            raise ValueError("mega / fused rollout steps need bf16 compute, <= 32 sequences and 64-aligned widths <= 2048")
+        if mode not in ("mega", "fused", "unfused"):
+            raise ValueError(f"unknown rollout mode {mode!r}")
+        self.mode = mode
+        self.fused = mode == "fused"
+        self._mega = None
 
     # ---- logits of the next token for every sequence, given self.cur and the recurrent state -------
     def fused_supported(self) -> bool:
@@ -89,9 +120,103 @@ class RolloutEngine:
         wh, bh, _, _ = m._cache.get("heads", m._heads(), dt, 8)
         return ops.skinny_linear(xl, wh, bh, ln=(enc.norm.weight, enc.norm.bias, enc.norm.eps))
 
+    # ---- persistent megakernel step -----------------------------------------------------------------
+    def _build_mega(self):
+        m, enc, N = self.model, self.model.transformer_encoder, self.N
+        dev, dt = self.cur.device, torch.bfloat16
+        lib = _lib.load()
+        gb, pb = ctypes.c_int(), ctypes.c_int()
+        lib.cpm_mega_sizes(ctypes.byref(gb), ctypes.byref(pb))
+        if gb.value != ctypes.sizeof(_MegaGlobals) or pb.value != ctypes.sizeof(_MegaPhase):
+            raise RuntimeError("megakernel struct layout mismatch between rollout.py and rollout_mega.cu")
+        d, di, H, A = m.d_model, m.d_inner, enc.n_heads, len(m.attrs)
+        E = int(sum(m.emb_sizes))
+        buf = lambda w: torch.zeros(N, w, dtype=dt, device=dev)
+        sc = {"x0": buf(d), "xb": buf(d), "qkv": buf(3 * d), "a": buf(d), "s1": buf(d), "x1": buf(d), "h": buf(di), "s2": buf(d),
+              "logits": buf(m.logits_width)}
+        keep = [sc]
+        phases = []
+
+        def gemm(A_, W, b, Y, Nn, K, pro=0, epi=0, ln=None, ln2=None, xout=None, R=None):
+            ph = _MegaPhase()
+            ph.type, ph.M, ph.N, ph.K = 0, N, Nn, K
+            ph.lda = 0 if A_ is None else A_.stride(0)
+            ph.ldy, ph.ldr = Y.stride(0), (0 if R is None else R.stride(0))
+            ph.pro, ph.epi, ph.eps = pro, epi, (ln[2] if ln is not None else 0.0)
+            ph.A = None if A_ is None else A_.data_ptr()
+            ph.W, ph.bias, ph.Y = W.data_ptr(), b.data_ptr(), Y.data_ptr()
+            ph.R = None if R is None else R.data_ptr()
+            ph.xout = None if xout is None else xout.data_ptr()
+            if ln is not None:
+                ph.gamma, ph.beta = ln[0].data_ptr(), ln[1].data_ptr()
+            if ln2 is not None:
+                ph.gamma2, ph.beta2 = ln2[0].data_ptr(), ln2[1].data_ptr()
+            phases.append(ph)
+
+        w, b, _, _ = m._cache.get("in", [m.in_linear], dt)
+        gemm(None, w, b, sc["x0"], d, E, pro=3, epi=3)
+        prev = None
+        for i, layer in enumerate(enc.layers):
+            at = layer.attention
+            wq, bq, _, _ = enc._cache.get(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], dt)
+            if i == 0:
+                gemm(sc["x0"], wq, bq, sc["qkv"], 3 * d, d)
+                xin = sc["x0"]
+            else:
+                gemm(sc["s2"], wq, bq, sc["qkv"], 3 * d, d, pro=1, ln=(prev.norm2.weight, prev.norm2.bias, prev.norm2.eps), xout=sc["xb"])
+                xin = sc["xb"]
+            ph = _MegaPhase()
+            ph.type, ph.M, ph.H, ph.lda, ph.ldy, ph.eps = 1, N, H, 3 * d, d, ops.EPS_ATTN
+            ph.A, ph.Y, ph.S, ph.Z = sc["qkv"].data_ptr(), sc["a"].data_ptr(), self.S[i].data_ptr(), self.Z[i].data_ptr()
+            phases.append(ph)
+            wo, bo, _, _ = enc._cache.get(("out", i), [at.out_projection], dt)
+            gemm(sc["a"], wo, bo, sc["s1"], d, d, epi=2, R=xin)
+            w1, b1, _, _ = enc._cache.get(("ff1", i), [layer.linear1], dt)
+            gemm(sc["s1"], w1, b1, sc["h"], di, d, pro=1, epi=1, ln=(layer.norm1.weight, layer.norm1.bias, layer.norm1.eps), xout=sc["x1"])
+            w2, b2, _, _ = enc._cache.get(("ff2", i), [layer.linear2], dt)
+            gemm(sc["h"], w2, b2, sc["s2"], d, di, epi=2, R=sc["x1"])
+            prev = layer
+        wh, bh, _, _ = m._cache.get("heads", m._heads(), dt, 8)
+        gemm(sc["s2"], wh, bh, sc["logits"], m.logits_width, d, pro=2, ln=(prev.norm2.weight, prev.norm2.bias, prev.norm2.eps),
+             ln2=(enc.norm.weight, enc.norm.bias, enc.norm.eps))
+        ph = _MegaPhase()
+        ph.type, ph.M, ph.lda, ph.A = 2, N, m.logits_width, sc["logits"].data_ptr()
+        phases.append(ph)
+
+        g = _MegaGlobals()
+        g.batch, g.n_attr, g.emb_total, g.logits_ld = N, A, E, m.logits_width
+        off = 0
+        for a in range(A):
+            g.n_tokens[a], g.emb[a], g.emb_off[a] = m.n_token[a], m.emb_sizes[a], off
+            g.emb_scale[a] = float(m.emb_sizes[a]) ** 0.5
+            g.temperature[a] = float(self.temperature[a])
+            g.top_p[a] = 0.0 if self.top_p[a] is None else float(self.top_p[a])
+            g.tables[a] = m._tables()[a].data_ptr()
+            g.seg[a] = m.seg[a]
+            off += m.emb_sizes[a]
+        g.emb_off[A], g.seg[A] = off, m.seg[A]
+        g.greedy, g.true_positions, g.max_steps = int(self.greedy), int(self.true_positions), self.max_steps
+        pe2 = m.pos_emb.pe.reshape(-1, d)
+        g.pe_max, g.pe = pe2.shape[0], pe2.data_ptr()
+        g.seed, g.seq_base = self.seed, self.seq_base
+        self._mega_barrier = torch.zeros(1, dtype=torch.int32, device=dev)
+        g.cur, g.hist_tok, g.logp, g.hist_logp = self.cur.data_ptr(), self.hist_tok.data_ptr(), self.logp.data_ptr(), self.hist_logp.data_ptr()
+        g.step_dev, g.barrier, g.n_phases = self.step_dev.data_ptr(), self._mega_barrier.data_ptr(), len(phases)
+        arr = (_MegaPhase * len(phases))(*phases)
+        to_dev = lambda obj: torch.frombuffer(bytearray(bytes(obj)), dtype=torch.uint8).to(dev)
+        self._mega = {"globals": to_dev(g), "phases": to_dev(arr), "keep": keep, "n_phases": len(phases), "seed": self.seed}
+
+    def _step_mega(self):
+        if self._mega is None or self._mega["seed"] != self.seed:
+            self._build_mega()
+        ops.check(_lib.load().cpm_rollout_step_mega(self._mega["globals"].data_ptr(), self._mega["phases"].data_ptr(),
+                                                    torch.cuda.current_stream().cuda_stream))
+
     # one token for every sequence: reads self.cur, overwrites self.cur with the sampled token
     def _step(self):
         m = self.model
+        if self.mode == "mega":
+            return self._step_mega()
         lc = self._logits_fused() if self.fused else self._logits_unfused()
         ops.heads_sample(lc, m.seg, self.temperature, self.top_p, greedy=self.greedy, seed=self.seed,
                          seq_base=self.seq_base, step_dev=self.step_dev, tokens_out=self.cur, logp_out=self.logp)
@@ -131,11 +256,18 @@ class RolloutEngine:
             self.seed, self.graph = seed, None
         was_training = self.model.training
         self.model.eval()
-        if self.use_graph and self.graph is None:
+        mega = self.mode == "mega"
+        if mega and (self._mega is None or self._mega["seed"] != self.seed):
+            self._build_mega()
+        if self.use_graph and not mega and self.graph is None:
             self._capture()
         self.reset(init_tokens)
-        self.model.refresh_packs()          # the graph reads the packed weights by address
-        if self.use_graph:
+        self.model.refresh_packs()          # graph / megakernel read the packed weights by address
+        if mega:
+            for _ in range(n_steps):        # one cooperative launch per token step, queued back to back
+                self._step_mega()
+            self.launches_per_step = 1
+        elif self.use_graph:
             for _ in range(n_steps):
                 self.graph.replay()
             _lib.EXTRA_LAUNCHES[0] += n_steps * self.launches_per_step

@@ -295,3 +295,49 @@ def test_rollout_fused_step_matches_unfused_and_oracle(cuda, cpm, golden):
     a = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=True, fused=True).generate(init)["tokens"]
     b = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, fused=True).generate(init)["tokens"]
     assert torch.equal(a, b)
+
+
+def test_rollout_megakernel_matches_unfused_and_oracle(cuda, cpm, golden):
+    """The persistent cooperative megakernel (one launch per token step) against the unfused kernel
+    path and the fp64 oracle recurrence, teacher-forced step by step; then free-running generation:
+    greedy tokens agree with the unfused path except at bf16 near-ties, history / log-probs /
+    step counter bookkeeping is right, and sampled rollouts are shard-invariant."""
+    g = golden("model_small")
+    m = _load_small(cpm, g, cuda, dtype=torch.bfloat16).eval()
+    o = mo.OracleCPModel(VOCAB, is_training=False, **SMALL).double().eval()
+    o.load_state_dict({k[4:]: torch.from_numpy(g[k]).double() for k in g.files if k.startswith("sd::")}, strict=False)
+    N, T = 4, 10
+    x = torch.from_numpy(g["x"])[:1, :T + 1].expand(N, T + 1, 6).contiguous()
+    em = cpm.RolloutEngine(m, N, T, greedy=True, mode="mega")
+    eu = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="unfused")
+    em.reset(x[:, 0].to(cuda))
+    eu.reset(x[:, 0].to(cuda))
+    m.refresh_packs()
+    mem = None
+    with torch.no_grad():
+        for t in range(T):
+            em.cur.copy_(x[:, t].to(cuda))
+            eu.cur.copy_(x[:, t].to(cuda))
+            em.step_dev.fill_(t)
+            eu.step_dev.fill_(t)
+            em._step_mega()
+            lm = em._mega["keep"][0]["logits"].float()
+            lu = eu._logits_unfused().float()
+            h, mem = o.forward_hidden(x[:1, t:t + 1], mem, is_training=False, pos_offset=t)
+            ref = torch.cat(o.forward_output(h), -1)[0]
+            _cmp(lm[0, :339], ref, 6e-2, 3e-2, f"mega vs oracle step {t}")
+            _cmp(lm[:, :339], lu[:, :339], 4e-2, 2e-2, f"mega vs unfused step {t}")
+            assert int(em.step_dev.item()) == t + 1                      # the kernel advances the step counter itself
+            tok_ref, lp_ref, _ = cpm.ops.heads_sample(lm.bfloat16(), m.seg, greedy=True, want_logp=True)
+            assert torch.equal(em.cur, tok_ref) and torch.equal(em.hist_tok[t], tok_ref)
+            _cmp(em.hist_logp[t], lp_ref, 1e-4, 1e-4, "log-prob history")
+    init = x[:, 0].to(cuda)
+    a = cpm.RolloutEngine(m, N, 40, greedy=True, mode="mega").generate(init)
+    b = cpm.RolloutEngine(m, N, 40, greedy=True, mode="unfused", use_graph=False).generate(init)
+    assert a["tokens"].shape == (N, 41, 6)
+    first_rows = (a["tokens"][:, :6] == b["tokens"][:, :6]).float().mean().item()
+    assert first_rows > 0.95, first_rows
+    assert torch.equal(cpm.RolloutEngine(m, N, 40, greedy=True, mode="mega").generate(init)["tokens"], a["tokens"])   # deterministic
+    full = cpm.RolloutEngine(m, 5, 30, greedy=False, seed=9, seq_base=0, mode="mega").generate(x[:1, 0].expand(5, 6).to(cuda))["tokens"]
+    part = cpm.RolloutEngine(m, 2, 30, greedy=False, seed=9, seq_base=3, mode="mega").generate(x[:1, 0].expand(2, 6).to(cuda))["tokens"]
+    assert torch.equal(full[3:], part)                                   # Philox keyed by global sequence id
