@@ -69,18 +69,8 @@ namespace {
 using namespace tc;
 
 constexpr int CHUNK = 128;
+constexpr int NTH = 256;                          // 8 warps: two threads per token row (column halves)
 constexpr uint32_t TILE_BYTES = 128 * 128;       // [128 rows x 128 B] bf16 tile
-// shared-memory carve-up (byte offsets from a 1024-aligned base)
-constexpr uint32_t OFF_Q = 0, OFF_K = 16384, OFF_V = 32768, OFF_P = 49152, OFF_O = 81920, OFF_S = 98304, OFF_ONES = 106496;
-constexpr uint32_t OFF_Z = 108544, OFF_BAR = OFF_Z + 256, OFF_TMEM = OFF_BAR + 32, FWD_SMEM_USED = OFF_TMEM + 16;
-constexpr uint32_t FWD_SMEM_BYTES = FWD_SMEM_USED + 1024;     // + alignment slack
-// TMEM columns (256 allocated): P / O at 0 (128 wide), S at 128 (64), Z at 192 (8)
-constexpr uint32_t TM_P = 0, TM_S = 128, TM_Z = 192;
-constexpr uint32_t IDESC_P = idesc_bf16(128, 128, false, false);
-constexpr uint32_t IDESC_QS = idesc_bf16(128, 64, false, true);
-constexpr uint32_t IDESC_PV = idesc_bf16(128, 64, false, true);
-constexpr uint32_t IDESC_KV = idesc_bf16(64, 64, true, true);
-constexpr uint32_t IDESC_Z = idesc_bf16(64, 8, true, true);
 
 // elu(x)+1 on 8 packed bf16, rounded back to bf16; returns the packed result and the fp32 values
 __device__ __forceinline__ uint4 phi8(uint4 raw, float (&f)[8]) {
@@ -98,20 +88,137 @@ __device__ __forceinline__ uint4 phi8(uint4 raw, float (&f)[8]) {
     }
     return o;
 }
+__device__ __forceinline__ void unpack8(uint4 raw, float (&f)[8]) {
+    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { float2 x = __bfloat1622float2(h[i]); f[2 * i] = x.x; f[2 * i + 1] = x.y; }
+}
+__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
+    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
+}
+__device__ __forceinline__ uint4 pack8u(const uint32_t *r, float scale) {
+    return make_uint4(pack_bf16(__uint_as_float(r[0]) * scale, __uint_as_float(r[1]) * scale),
+                      pack_bf16(__uint_as_float(r[2]) * scale, __uint_as_float(r[3]) * scale),
+                      pack_bf16(__uint_as_float(r[4]) * scale, __uint_as_float(r[5]) * scale),
+                      pack_bf16(__uint_as_float(r[6]) * scale, __uint_as_float(r[7]) * scale));
+}
 
-__global__ void __launch_bounds__(128, 2)
+// Per-thread geometry: 8 warps; warp w reads TMEM lanes 32*(w&3).., i.e. token rows 32*(w&3)+lane, and
+// owns column half (w>>2) of every 64-wide row (16-byte chunks 4*half .. 4*half+3).
+struct Geo {
+    int tid, warp, lane, row, half, erow;
+    uint32_t t_lane;
+    __device__ __forceinline__ Geo(uint32_t tmem) {
+        tid = threadIdx.x; warp = tid >> 5; lane = tid & 31;
+        row = ((warp & 3) << 5) + lane; half = warp >> 2;
+        erow = 16 * (warp & 3) + (lane & 15);                 // row of a 64x64 state tile (M=64 TMEM layout)
+        t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    }
+};
+
+// 64x64 fp32 state in TMEM (M=64 layout) -> bf16 smem tile rows e, this thread's 32 columns
+__device__ __forceinline__ void state_half_to_smem(const Geo &g, uint32_t tm_col, uint8_t *sS) {
+    uint32_t r[32];
+    tmem_ld32(g.t_lane + tm_col + 32 * g.half, r);
+    tmem_ld_wait();
+    if (g.lane < 16) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sS + sw128_off(g.erow, g.half * 4 + cc)) = pack8u(r + 8 * cc, 1.f);
+    }
+}
+// initial state (fp32, row-major [e][m]) -> TMEM + bf16 smem tile
+__device__ __forceinline__ void seed_state_half(const Geo &g, const float *init, uint32_t tm_col, uint8_t *sS) {
+    uint32_t r[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(init[g.erow * 64 + g.half * 32 + i]);
+    tmem_st32(g.t_lane + tm_col + 32 * g.half, r);
+    if (g.lane < 16) {
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sS + sw128_off(g.erow, g.half * 4 + cc)) = pack8u(r + 8 * cc, 1.f);
+    }
+    tmem_st_wait();
+}
+
+// TMEM [128 x 128] score tile -> (+row_add, +col_add[c]) -> triangular mask -> bf16 -> sX block `half`.
+// LOWER keeps column c <= row (forward / dq);  otherwise keeps c >= row (dk/dv).  Returns the row sum of
+// the bf16-rounded kept entries over this thread's 64 columns.
+template <bool LOWER>
+__device__ __forceinline__ float convert_scores(const Geo &g, uint32_t tm_col, uint8_t *sX, float row_add, const float *col_add) {
+    float rowsum = 0.f;
+    const int wq = g.warp & 3;
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+        const int p = 2 * g.half + pp;                      // 32-column piece
+        uint32_t r[32];
+        const bool live = LOWER ? (p <= wq) : (p >= wq);
+        const bool diag = p == wq;
+        if (live) {
+            tmem_ld32(g.t_lane + tm_col + 32 * p, r);
+            tmem_ld_wait();
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            uint32_t w[4];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int c0 = 32 * p + 8 * cc + 2 * i;
+                float a = 0.f, b = 0.f;
+                if (live) {
+                    a = __uint_as_float(r[8 * cc + 2 * i]) + row_add + (col_add ? col_add[c0] : 0.f);
+                    b = __uint_as_float(r[8 * cc + 2 * i + 1]) + row_add + (col_add ? col_add[c0 + 1] : 0.f);
+                    if (diag) {
+                        if (LOWER) { a = c0 <= g.row ? a : 0.f; b = c0 + 1 <= g.row ? b : 0.f; }
+                        else { a = c0 >= g.row ? a : 0.f; b = c0 + 1 >= g.row ? b : 0.f; }
+                    }
+                }
+                const __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
+                const float2 fb = __bfloat1622float2(hb);
+                rowsum += fb.x + fb.y;
+                w[i] = *reinterpret_cast<const uint32_t *>(&hb);
+            }
+            *reinterpret_cast<uint4 *>(sX + g.half * TILE_BYTES + sw128_off(g.row, pp * 4 + cc)) = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+    }
+    return rowsum;
+}
+
+// partial column sums over 32 rows (quarter) of a swizzled [128 x 64] bf16 tile, optionally row-weighted
+__device__ __forceinline__ float colsum_quarter(const uint8_t *tile, int e, int quarter, const float *w) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int j = 32 * quarter; j < 32 * quarter + 32; ++j) {
+        const __nv_bfloat16 x = *reinterpret_cast<const __nv_bfloat16 *>(tile + sw128_off(j, e >> 3) + (e & 7) * 2);
+        s = fmaf(__bfloat162float(x), w ? w[j] : 1.f, s);
+    }
+    return s;
+}
+
+// =============================================================================================
+// forward
+// =============================================================================================
+constexpr uint32_t OFF_Q = 0, OFF_K = 16384, OFF_V = 32768, OFF_P = 49152, OFF_O = 81920, OFF_S = 98304, OFF_ONES = 106496;
+constexpr uint32_t OFF_Z = 108544, OFF_DP = OFF_Z + 256 /* den partials [2][2][128] */, OFF_BAR = OFF_DP + 2048, OFF_TMEM = OFF_BAR + 32;
+constexpr uint32_t FWD_SMEM_BYTES = OFF_TMEM + 16;
+constexpr uint32_t TM_P = 0, TM_S = 128, TM_Z = 192;
+constexpr uint32_t IDESC_P = idesc_bf16(128, 128, false, false);
+constexpr uint32_t IDESC_QS = idesc_bf16(128, 64, false, true);
+constexpr uint32_t IDESC_PV = idesc_bf16(128, 64, false, true);
+constexpr uint32_t IDESC_KV = idesc_bf16(64, 64, true, true);
+constexpr uint32_t IDESC_Z = idesc_bf16(64, 8, true, true);
+
+__global__ void __launch_bounds__(NTH, 2)
 linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                       const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmO, float *__restrict__ den,
                       int L, int H, int nseg, int seg_len, const float *__restrict__ ws_fwd, float eps) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sQ = sm + OFF_Q, *sK = sm + OFF_K, *sV = sm + OFF_V, *sP = sm + OFF_P, *sO = sm + OFF_O, *sS = sm + OFF_S;
     uint32_t *sOnes = reinterpret_cast<uint32_t *>(sm + OFF_ONES);
     float *sz = reinterpret_cast<float *>(sm + OFF_Z);
+    float *sdp = reinterpret_cast<float *>(sm + OFF_DP);          // [0..255]: inter partials [half][row]; [256..511]: intra partials
     uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + OFF_BAR), *bar_mma = bar_load + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + OFF_TMEM);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int seg = blockIdx.x % nseg, nh = blockIdx.x / nseg, n = nh / H, h = nh % H;
     const int col0 = h * 64;
     const int t_begin = seg * seg_len, t_end = min(L, t_begin + seg_len);
@@ -119,6 +226,7 @@ linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     const int row_base = n * L + t_begin;
 
     if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
         fence_barrier_init();
@@ -127,45 +235,28 @@ linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         tma_prefetch_desc(&tmV);
         tma_prefetch_desc(&tmO);
     }
-    if (warp == 0) tmem_alloc<256>(tmem_slot);
-    for (int i = tid; i < 512; i += 128) sOnes[i] = 0x3F803F80u;            // bf16 1.0 everywhere (layout-agnostic)
+    if ((tid >> 5) == 0) tmem_alloc<256>(tmem_slot);
+    for (int i = tid; i < 512; i += NTH) sOnes[i] = 0x3F803F80u;             // bf16 1.0 everywhere (layout-agnostic)
     const float *init = (nseg > 1 && seg > 0) ? ws_fwd + (int64_t)blockIdx.x * STATE_FLOATS : nullptr;
     if (tid < 64) sz[tid] = init ? init[4096 + tid] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    const int erow = 16 * warp + (lane & 15);          // state row owned by this lane (lanes 0..15 of each warp)
+    const Geo g(tmem);
 
     bool have_state = init != nullptr;
-    if (have_state) {      // seed TMEM (fp32) and sS (bf16) with the segment's initial state
-        uint32_t r[32];
+    if (have_state) {
+        seed_state_half(g, init, TM_S, sS);
+        if (g.half == 0) {
+            uint32_t z8[8];
 #pragma unroll
-        for (int half = 0; half < 2; ++half) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(init[erow * 64 + half * 32 + i]);
-            tmem_st32(t_lane + TM_S + half * 32, r);
-            if (lane < 16) {
-#pragma unroll
-                for (int c = 0; c < 4; ++c) {
-                    uint4 pk;
-                    pk.x = pack_bf16(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
-                    pk.y = pack_bf16(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
-                    pk.z = pack_bf16(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
-                    pk.w = pack_bf16(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
-                    *reinterpret_cast<uint4 *>(sS + sw128_off(erow, half * 4 + c)) = pk;
-                }
-            }
+            for (int i = 0; i < 8; ++i) z8[i] = __float_as_uint(init[4096 + g.erow]);
+            tmem_st8(g.t_lane + TM_Z, z8);
+            tmem_st_wait();
         }
-        uint32_t z8[8];
-#pragma unroll
-        for (int i = 0; i < 8; ++i) z8[i] = __float_as_uint(init[4096 + erow]);
-        tmem_st8(t_lane + TM_Z, z8);
-        tmem_st_wait();
         fence_proxy_async();
     }
-
     const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
     const uint64_t dP = smem_desc_sw128(smem_u32(sP)), dS = smem_desc_sw128(smem_u32(sS)), dOnes = smem_desc_sw128(smem_u32(sOnes));
 
@@ -183,19 +274,19 @@ linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         const int grow = row_base + c * CHUNK;
         mbar_wait(bar_load, ph_load);
         ph_load ^= 1;
-        // ---- feature map in place (thread = token row), inter-chunk normaliser
+        // ---- feature map in place (this thread: 4 chunks of its row), inter-chunk normaliser partial
         float den_inter = 0.f;
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-            const uint32_t off = sw128_off(tid, ch);
+        for (int cc = 0; cc < 4; ++cc) {
+            const int ch = 4 * g.half + cc;
+            const uint32_t off = sw128_off(g.row, ch);
             float f[8];
-            uint4 qv = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
-            *reinterpret_cast<uint4 *>(sQ + off) = qv;
+            *reinterpret_cast<uint4 *>(sQ + off) = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
 #pragma unroll
             for (int i = 0; i < 8; ++i) den_inter = fmaf(f[i], sz[ch * 8 + i], den_inter);
-            uint4 kv = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
-            *reinterpret_cast<uint4 *>(sK + off) = kv;
+            *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
         }
+        sdp[g.half * 128 + g.row] = den_inter;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -209,31 +300,9 @@ linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        // ---- P -> mask -> bf16 -> sP ; intra-chunk normaliser
-        float den_intra = 0.f;
-#pragma unroll
-        for (int p = 0; p < 4; ++p) {
-            uint32_t r[32];
-            const bool live = (32 * p) <= (32 * warp + 31);        // warp-uniform: some j <= r in this block of columns
-            if (live) {
-                tmem_ld32(t_lane + TM_P + 32 * p, r);
-                tmem_ld_wait();
-            }
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                uint32_t w[4];
-#pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    const int j0 = 32 * p + 8 * cc + 2 * i;
-                    float a = (live && j0 <= tid) ? bf16_round(__uint_as_float(r[8 * cc + 2 * i])) : 0.f;
-                    float b = (live && j0 + 1 <= tid) ? bf16_round(__uint_as_float(r[8 * cc + 2 * i + 1])) : 0.f;
-                    den_intra += a + b;
-                    w[i] = pack_bf16(a, b);
-                }
-                *reinterpret_cast<uint4 *>(sP + (p >> 1) * TILE_BYTES + sw128_off(tid, (p & 1) * 4 + cc)) = make_uint4(w[0], w[1], w[2], w[3]);
-            }
-        }
-        if (tid == 0) tma_store_wait_read0();            // the previous chunk's TMA store no longer reads sO
+        // ---- P -> mask -> bf16 -> sP ; intra-chunk normaliser partial
+        sdp[256 + g.half * 128 + g.row] = convert_scores<true>(g, TM_P, sP, 0.f, nullptr);
+        if (tid == 0) tma_store_wait_read0();             // the previous chunk's TMA store no longer reads sO
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -257,55 +326,31 @@ linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        // ---- all MMAs of this chunk are complete: refill the operand tiles for the next chunk
-        if (tid == 0 && c + 1 < nchunks) {
+        if (tid == 0 && c + 1 < nchunks) {               // operand tiles are free: prefetch the next chunk
             mbar_expect_tx(bar_load, 3 * TILE_BYTES);
             tma_load_2d(sQ, &tmQ, bar_load, col0, grow + CHUNK);
             tma_load_2d(sK, &tmK, bar_load, col0, grow + CHUNK);
             tma_load_2d(sV, &tmV, bar_load, col0, grow + CHUNK);
         }
-        // ---- output rows
-        const float dn = den_intra + den_inter + eps;
+        // ---- output rows (this thread: 32 columns)
+        const float dn = sdp[g.row] + sdp[128 + g.row] + sdp[256 + g.row] + sdp[384 + g.row] + eps;
         const float inv = 1.f / dn;
-        if (den) den[(int64_t)(grow + tid) * H + h] = dn;
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        if (den && g.half == 0) den[(int64_t)(grow + g.row) * H + h] = dn;
+        {
             uint32_t r[32];
-            tmem_ld32(t_lane + TM_P + 32 * half, r);
+            tmem_ld32(g.t_lane + TM_P + 32 * g.half, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                uint4 pk;
-                pk.x = pack_bf16(__uint_as_float(r[8 * cc + 0]) * inv, __uint_as_float(r[8 * cc + 1]) * inv);
-                pk.y = pack_bf16(__uint_as_float(r[8 * cc + 2]) * inv, __uint_as_float(r[8 * cc + 3]) * inv);
-                pk.z = pack_bf16(__uint_as_float(r[8 * cc + 4]) * inv, __uint_as_float(r[8 * cc + 5]) * inv);
-                pk.w = pack_bf16(__uint_as_float(r[8 * cc + 6]) * inv, __uint_as_float(r[8 * cc + 7]) * inv);
-                *reinterpret_cast<uint4 *>(sO + sw128_off(tid, half * 4 + cc)) = pk;
-            }
+            for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sO + sw128_off(g.row, g.half * 4 + cc)) = pack8u(r + 8 * cc, inv);
         }
-        // ---- state for the next chunk: S -> bf16 sS, Z -> fp32 sz
-        if (c + 1 < nchunks) {
-#pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                uint32_t r[32];
-                tmem_ld32(t_lane + TM_S + 32 * half, r);
+        if (c + 1 < nchunks) {                            // state for the next chunk
+            state_half_to_smem(g, TM_S, sS);
+            if (g.half == 0) {
+                uint32_t z8[8];
+                tmem_ld8(g.t_lane + TM_Z, z8);
                 tmem_ld_wait();
-                if (lane < 16) {
-#pragma unroll
-                    for (int cc = 0; cc < 4; ++cc) {
-                        uint4 pk;
-                        pk.x = pack_bf16(__uint_as_float(r[8 * cc + 0]), __uint_as_float(r[8 * cc + 1]));
-                        pk.y = pack_bf16(__uint_as_float(r[8 * cc + 2]), __uint_as_float(r[8 * cc + 3]));
-                        pk.z = pack_bf16(__uint_as_float(r[8 * cc + 4]), __uint_as_float(r[8 * cc + 5]));
-                        pk.w = pack_bf16(__uint_as_float(r[8 * cc + 6]), __uint_as_float(r[8 * cc + 7]));
-                        *reinterpret_cast<uint4 *>(sS + sw128_off(erow, half * 4 + cc)) = pk;
-                    }
-                }
+                if (g.lane < 16) sz[g.erow] = __uint_as_float(z8[0]);
             }
-            uint32_t z8[8];
-            tmem_ld8(t_lane + TM_Z, z8);
-            tmem_ld_wait();
-            if (lane < 16) sz[erow] = __uint_as_float(z8[0]);
         }
         fence_proxy_async();
         tc_fence_before();
@@ -318,12 +363,11 @@ linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
     if (tid == 0) tma_store_wait_all0();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem);
+    if ((tid >> 5) == 0) tmem_dealloc<256>(tmem);
 }
 
-
 // =============================================================================================
-// Backward.  Two kernels with the forward's structure (one CTA per (n, h, segment), 128 threads,
+// Backward.  Two kernels with the forward's structure (one CTA per (n, h, segment), 256 threads,
 // 128-token chunks, 2 CTAs/SM, 256 TMEM columns):
 //   dq pass  (chunks in forward order, carries S, z):
 //     X[i][j]  = G'[i].v[j] (+ gd_i) masked j<=i           G' = go/den, gd_i = -(go_i.out_i)/den_i
@@ -336,128 +380,31 @@ linattn_fwd_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_cons
 // =============================================================================================
 constexpr uint32_t B_OFF_Q = 0, B_OFF_K = 16384, B_OFF_V = 32768, B_OFF_G = 49152, B_OFF_X = 65536, B_OFF_S = 98304;
 constexpr uint32_t B_OFF_Z = 106496;                 // 2 x 64 floats (double-buffered z / rz)
-constexpr uint32_t B_OFF_DZ = B_OFF_Z + 512;         // 2 x 64 floats partial column sums
-constexpr uint32_t B_OFF_GD = B_OFF_DZ + 512;        // 128 floats gd_i (dk/dv pass)
-constexpr uint32_t B_OFF_BAR = B_OFF_GD + 512, B_OFF_TMEM = B_OFF_BAR + 32, BWD_SMEM_USED = B_OFF_TMEM + 16;
-constexpr uint32_t BWD_SMEM_BYTES = BWD_SMEM_USED + 1024;
+constexpr uint32_t B_OFF_DZ = B_OFF_Z + 512;         // 4 x 64 floats partial column sums
+constexpr uint32_t B_OFF_GD = B_OFF_DZ + 1024;       // 128 floats gd_i
+constexpr uint32_t B_OFF_GP = B_OFF_GD + 512;        // 2 x 128 floats partial go.out dots
+constexpr uint32_t B_OFF_BAR = B_OFF_GP + 1024, B_OFF_TMEM = B_OFF_BAR + 32;
+constexpr uint32_t BWD_SMEM_BYTES = B_OFF_TMEM + 16;
 constexpr uint32_t TB_X = 0, TB_ACC = 128, TB_ST = 192;
 constexpr uint32_t IDESC_KK128 = idesc_bf16(128, 128, false, false);   // A K-major, B K-major, N=128
 constexpr uint32_t IDESC_KM64 = idesc_bf16(128, 64, false, true);      // A K-major, B MN-major, N=64
 constexpr uint32_t IDESC_KK64 = idesc_bf16(128, 64, false, false);     // A K-major, B K-major,  N=64
 constexpr uint32_t IDESC_MM64 = idesc_bf16(64, 64, true, true);        // A MN-major, B MN-major (state update)
 
-__device__ __forceinline__ void unpack8(uint4 raw, float (&f)[8]) {
-    const __nv_bfloat162 *h = reinterpret_cast<const __nv_bfloat162 *>(&raw);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) { float2 x = __bfloat1622float2(h[i]); f[2 * i] = x.x; f[2 * i + 1] = x.y; }
-}
-__device__ __forceinline__ uint4 pack8(const float (&f)[8]) {
-    return make_uint4(pack_bf16(f[0], f[1]), pack_bf16(f[2], f[3]), pack_bf16(f[4], f[5]), pack_bf16(f[6], f[7]));
-}
-
-// G' = go/den in place (sG), returns gd_r; o tile is read from sOt.
-__device__ __forceinline__ float prep_grad_row(uint8_t *sG, const uint8_t *sOt, int r, float inv) {
+// G' = go/den in place over this thread's 4 chunks; returns the partial dot go.out
+__device__ __forceinline__ float prep_grad_half(const Geo &g, uint8_t *sG, const uint8_t *sOt, float inv) {
     float dot = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        const uint32_t off = sw128_off(r, ch);
-        float g[8], o[8];
-        unpack8(*reinterpret_cast<const uint4 *>(sG + off), g);
+    for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
+        float gg[8], o[8];
+        unpack8(*reinterpret_cast<const uint4 *>(sG + off), gg);
         unpack8(*reinterpret_cast<const uint4 *>(sOt + off), o);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dot = fmaf(g[i], o[i], dot); g[i] *= inv; }
-        *reinterpret_cast<uint4 *>(sG + off) = pack8(g);
+        for (int i = 0; i < 8; ++i) { dot = fmaf(gg[i], o[i], dot); gg[i] *= inv; }
+        *reinterpret_cast<uint4 *>(sG + off) = pack8(gg);
     }
-    return -dot * inv;
-}
-
-// partial column sums over 64 rows of a swizzled [128 x 64] bf16 tile, optionally weighted per row
-__device__ __forceinline__ float colsum_half(const uint8_t *tile, int e, int half, const float *w) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int j = 64 * half; j < 64 * half + 64; ++j) {
-        const __nv_bfloat16 x = *reinterpret_cast<const __nv_bfloat16 *>(tile + sw128_off(j, e >> 3) + (e & 7) * 2);
-        s = fmaf(__bfloat162float(x), w ? w[j] : 1.f, s);
-    }
-    return s;
-}
-
-// TMEM [rows of this warp] x 128 columns -> (+ optional per-row / per-column add) -> triangular mask -> bf16 -> sX
-// LOWER: keep j <= r (dq pass).  else keep i >= r (dk/dv pass).
-template <bool LOWER>
-__device__ __forceinline__ void convert_x(uint32_t t_lane, uint8_t *sX, int tid, int warp, float row_add, const float *col_add) {
-#pragma unroll
-    for (int p = 0; p < 4; ++p) {
-        uint32_t r[32];
-        const bool live = LOWER ? (p <= warp) : (p >= warp);
-        const bool diag = p == warp;
-        if (live) {
-            tmem_ld32(t_lane + TB_X + 32 * p, r);
-            tmem_ld_wait();
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            uint32_t w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c0 = 32 * p + 8 * cc + 2 * i;
-                float a = 0.f, b = 0.f;
-                if (live) {
-                    a = __uint_as_float(r[8 * cc + 2 * i]) + row_add + (col_add ? col_add[c0] : 0.f);
-                    b = __uint_as_float(r[8 * cc + 2 * i + 1]) + row_add + (col_add ? col_add[c0 + 1] : 0.f);
-                    if (diag) {
-                        if (LOWER) { a = c0 <= tid ? a : 0.f; b = c0 + 1 <= tid ? b : 0.f; }
-                        else { a = c0 >= tid ? a : 0.f; b = c0 + 1 >= tid ? b : 0.f; }
-                    }
-                }
-                w[i] = pack_bf16(a, b);
-            }
-            *reinterpret_cast<uint4 *>(sX + (p >> 1) * TILE_BYTES + sw128_off(tid, (p & 1) * 4 + cc)) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    }
-}
-
-// carried 64x64 state: TMEM (M=64 layout: lanes 0..15 of each warp) -> bf16 tile rows e
-__device__ __forceinline__ void state_to_smem(uint32_t t_lane, uint8_t *sS, int lane, int erow) {
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-        uint32_t r[32];
-        tmem_ld32(t_lane + TB_ST + 32 * half, r);
-        tmem_ld_wait();
-        if (lane < 16) {
-#pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                uint4 pk;
-                pk.x = pack_bf16(__uint_as_float(r[8 * cc + 0]), __uint_as_float(r[8 * cc + 1]));
-                pk.y = pack_bf16(__uint_as_float(r[8 * cc + 2]), __uint_as_float(r[8 * cc + 3]));
-                pk.z = pack_bf16(__uint_as_float(r[8 * cc + 4]), __uint_as_float(r[8 * cc + 5]));
-                pk.w = pack_bf16(__uint_as_float(r[8 * cc + 6]), __uint_as_float(r[8 * cc + 7]));
-                *reinterpret_cast<uint4 *>(sS + sw128_off(erow, half * 4 + cc)) = pk;
-            }
-        }
-    }
-}
-
-__device__ __forceinline__ void seed_state(const float *init, uint32_t t_lane, uint8_t *sS, int lane, int erow) {
-    uint32_t r[32];
-#pragma unroll
-    for (int half = 0; half < 2; ++half) {
-#pragma unroll
-        for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(init[erow * 64 + half * 32 + i]);
-        tmem_st32(t_lane + TB_ST + half * 32, r);
-        if (lane < 16) {
-#pragma unroll
-            for (int c = 0; c < 4; ++c) {
-                uint4 pk;
-                pk.x = pack_bf16(__uint_as_float(r[8 * c + 0]), __uint_as_float(r[8 * c + 1]));
-                pk.y = pack_bf16(__uint_as_float(r[8 * c + 2]), __uint_as_float(r[8 * c + 3]));
-                pk.z = pack_bf16(__uint_as_float(r[8 * c + 4]), __uint_as_float(r[8 * c + 5]));
-                pk.w = pack_bf16(__uint_as_float(r[8 * c + 6]), __uint_as_float(r[8 * c + 7]));
-                *reinterpret_cast<uint4 *>(sS + sw128_off(erow, half * 4 + c)) = pk;
-            }
-        }
-    }
-    tmem_st_wait();
+    return dot;
 }
 
 struct BwdArgs {
@@ -466,42 +413,39 @@ struct BwdArgs {
     int L, H, nseg, seg_len;
 };
 
-// ---------------------------------------------------------------------------------------------
-// dq pass
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(NTH, 2)
 linattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                          const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmGo,
                          const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmGq, BwdArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sQ = sm + B_OFF_Q, *sK = sm + B_OFF_K, *sV = sm + B_OFF_V, *sG = sm + B_OFF_G, *sX = sm + B_OFF_X, *sS = sm + B_OFF_S;
     float *sz = reinterpret_cast<float *>(sm + B_OFF_Z), *sdz = reinterpret_cast<float *>(sm + B_OFF_DZ);
+    float *sgp = reinterpret_cast<float *>(sm + B_OFF_GP);
     uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + B_OFF_BAR), *bar_mma = bar_load + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + B_OFF_TMEM);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int seg = blockIdx.x % a.nseg, nh = blockIdx.x / a.nseg, n = nh / a.H, h = nh % a.H;
     const int col0 = h * 64;
     const int t_begin = seg * a.seg_len, t_end = min(a.L, t_begin + a.seg_len);
     const int nchunks = (t_end - t_begin) / CHUNK;
     const int row_base = n * a.L + t_begin;
     if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    if ((tid >> 5) == 0) tmem_alloc<256>(tmem_slot);
     const float *init = (a.nseg > 1 && seg > 0) ? a.ws_fwd + (int64_t)blockIdx.x * STATE_FLOATS : nullptr;
     if (tid < 64) sz[tid] = init ? init[4096 + tid] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    const int erow = 16 * warp + (lane & 15);
+    const Geo g(tmem);
     bool have_state = init != nullptr;
     if (have_state) {
-        seed_state(init, t_lane, sS, lane, erow);
+        seed_state_half(g, init, TB_ST, sS);
         fence_proxy_async();
     }
     const uint64_t dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV)), dG = smem_desc_sw128(smem_u32(sG));
@@ -524,16 +468,16 @@ linattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         float *zn = sz + 64 * ((c + 1) & 1);
         mbar_wait(bar_load, ph_load);
         ph_load ^= 1;
-        const float inv = 1.f / a.den[(int64_t)(grow + tid) * a.H + h];
-        const float gd = prep_grad_row(sG, sX, tid, inv);
-        uint32_t qraw[32];
+        const float inv = 1.f / a.den[(int64_t)(grow + g.row) * a.H + h];
+        sgp[g.half * 128 + g.row] = prep_grad_half(g, sG, sX, inv);
+        uint32_t qraw[16];
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-            const uint32_t off = sw128_off(tid, ch);
+        for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
             float f[8];
             *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
             const uint4 qv = *reinterpret_cast<const uint4 *>(sQ + off);
-            qraw[4 * ch + 0] = qv.x; qraw[4 * ch + 1] = qv.y; qraw[4 * ch + 2] = qv.z; qraw[4 * ch + 3] = qv.w;
+            qraw[4 * cc + 0] = qv.x; qraw[4 * cc + 1] = qv.y; qraw[4 * cc + 2] = qv.z; qraw[4 * cc + 3] = qv.w;
         }
         if (tid == 0) tma_store_wait_read0();      // previous chunk's dq store has finished reading sX block 1
         fence_proxy_async();
@@ -545,11 +489,12 @@ linattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
             for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dG + 2 * k, dV + 2 * k, IDESC_KK128, k > 0);
             mma_commit(bar_mma);
         }
-        sdz[64 * (tid >> 6) + (tid & 63)] = colsum_half(sK, tid & 63, tid >> 6, nullptr);     // overlaps the MMA
+        const float gd = -inv * (sgp[g.row] + sgp[128 + g.row]);
+        sdz[64 * (tid >> 6) + (tid & 63)] = colsum_quarter(sK, tid & 63, tid >> 6, nullptr);     // overlaps the MMA
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        convert_x<true>(t_lane, sX, tid, warp, gd, nullptr);
+        convert_scores<true>(g, TB_X, sX, gd, nullptr);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -571,25 +516,23 @@ linattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
         ph_mma ^= 1;
         tc_fence_after();
         if (tid == 0 && c + 1 < nchunks) issue_loads(grow + CHUNK);
-        // dq rows -> staging (sX block 1)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {   // dq rows -> staging (sX block 1), this thread's 32 columns
             uint32_t r[32];
-            tmem_ld32(t_lane + TB_ACC + 32 * half, r);
+            tmem_ld32(g.t_lane + TB_ACC + 32 * g.half, r);
             tmem_ld_wait();
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 float f[8], qf[8];
-                const int ch = half * 4 + cc;
-                unpack8(make_uint4(qraw[4 * ch], qraw[4 * ch + 1], qraw[4 * ch + 2], qraw[4 * ch + 3]), qf);
+                const int ch = g.half * 4 + cc;
+                unpack8(make_uint4(qraw[4 * cc], qraw[4 * cc + 1], qraw[4 * cc + 2], qraw[4 * cc + 3]), qf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) f[i] = (__uint_as_float(r[8 * cc + i]) + gd * zc[8 * ch + i]) * dphi(qf[i]);
-                *reinterpret_cast<uint4 *>(sX + TILE_BYTES + sw128_off(tid, ch)) = pack8(f);
+                *reinterpret_cast<uint4 *>(sX + TILE_BYTES + sw128_off(g.row, ch)) = pack8(f);
             }
         }
         if (c + 1 < nchunks) {
-            state_to_smem(t_lane, sS, lane, erow);
-            if (tid < 64) zn[tid] = zc[tid] + sdz[tid] + sdz[64 + tid];
+            state_half_to_smem(g, TB_ST, sS);
+            if (tid < 64) zn[tid] = zc[tid] + sdz[tid] + sdz[64 + tid] + sdz[128 + tid] + sdz[192 + tid];
         }
         fence_proxy_async();
         tc_fence_before();
@@ -602,47 +545,43 @@ linattn_bwd_dq_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_c
     if (tid == 0) tma_store_wait_all0();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem);
+    if ((tid >> 5) == 0) tmem_dealloc<256>(tmem);
 }
 
-// ---------------------------------------------------------------------------------------------
-// dk / dv pass
-// ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(128, 2)
+__global__ void __launch_bounds__(NTH, 2)
 linattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                           const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmGo,
                           const __grid_constant__ CUtensorMap tmO, const __grid_constant__ CUtensorMap tmGk,
                           const __grid_constant__ CUtensorMap tmGv, BwdArgs a) {
-    extern __shared__ uint8_t smem_raw[];
-    uint8_t *sm = reinterpret_cast<uint8_t *>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sQ = sm + B_OFF_Q, *sK = sm + B_OFF_K, *sV = sm + B_OFF_V, *sG = sm + B_OFF_G, *sX = sm + B_OFF_X, *sR = sm + B_OFF_S;
     float *srz = reinterpret_cast<float *>(sm + B_OFF_Z), *sdr = reinterpret_cast<float *>(sm + B_OFF_DZ);
-    float *sgd = reinterpret_cast<float *>(sm + B_OFF_GD);
+    float *sgd = reinterpret_cast<float *>(sm + B_OFF_GD), *sgp = reinterpret_cast<float *>(sm + B_OFF_GP);
     uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + B_OFF_BAR), *bar_mma = bar_load + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(sm + B_OFF_TMEM);
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x;
     const int seg = blockIdx.x % a.nseg, nh = blockIdx.x / a.nseg, n = nh / a.H, h = nh % a.H;
     const int col0 = h * 64;
     const int t_begin = seg * a.seg_len, t_end = min(a.L, t_begin + a.seg_len);
     const int nchunks = (t_end - t_begin) / CHUNK;
     const int row_base = n * a.L + t_begin;
     if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
         fence_barrier_init();
     }
-    if (warp == 0) tmem_alloc<256>(tmem_slot);
+    if ((tid >> 5) == 0) tmem_alloc<256>(tmem_slot);
     const float *init = (a.nseg > 1 && seg < a.nseg - 1) ? a.ws_rev + (int64_t)blockIdx.x * STATE_FLOATS : nullptr;
     if (tid < 64) srz[tid] = init ? init[4096 + tid] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    const int erow = 16 * warp + (lane & 15);
+    const Geo g(tmem);
     bool have_state = init != nullptr;
     if (have_state) {
-        seed_state(init, t_lane, sR, lane, erow);
+        seed_state_half(g, init, TB_ST, sR);
         fence_proxy_async();
     }
     const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
@@ -666,18 +605,20 @@ linattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         float *rzn = srz + 64 * ((it + 1) & 1);
         mbar_wait(bar_load, ph_load);
         ph_load ^= 1;
-        const float inv = 1.f / a.den[(int64_t)(grow + tid) * a.H + h];
-        sgd[tid] = prep_grad_row(sG, sX, tid, inv);
-        uint32_t kfr[32];
+        const float inv = 1.f / a.den[(int64_t)(grow + g.row) * a.H + h];
+        sgp[g.half * 128 + g.row] = prep_grad_half(g, sG, sX, inv);
+        uint32_t kfr[16];
 #pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-            const uint32_t off = sw128_off(tid, ch);
+        for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
             float f[8];
             *reinterpret_cast<uint4 *>(sQ + off) = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
             const uint4 kv = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
             *reinterpret_cast<uint4 *>(sK + off) = kv;
-            kfr[4 * ch + 0] = kv.x; kfr[4 * ch + 1] = kv.y; kfr[4 * ch + 2] = kv.z; kfr[4 * ch + 3] = kv.w;
+            kfr[4 * cc + 0] = kv.x; kfr[4 * cc + 1] = kv.y; kfr[4 * cc + 2] = kv.z; kfr[4 * cc + 3] = kv.w;
         }
+        __syncthreads();                     // both halves of every go.out dot are in sgp
+        if (g.half == 0) sgd[g.row] = -inv * (sgp[g.row] + sgp[128 + g.row]);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -687,11 +628,11 @@ linattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
             for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dQ + 2 * k, IDESC_KK128, k > 0);
             mma_commit(bar_mma);
         }
-        sdr[64 * (tid >> 6) + (tid & 63)] = colsum_half(sQ, tid & 63, tid >> 6, sgd);          // sum_i Qf[i][e] gd_i
+        sdr[64 * (tid >> 6) + (tid & 63)] = colsum_quarter(sQ, tid & 63, tid >> 6, sgd);          // sum_i Qf[i][e] gd_i
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        convert_x<false>(t_lane, sX, tid, warp, 0.f, nullptr);
+        convert_scores<false>(g, TB_X, sX, 0.f, nullptr);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -711,23 +652,14 @@ linattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        // dv rows -> staging in sK (Kf no longer needed as an operand; this thread keeps its row in kfr)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {   // dv rows -> staging in sK (Kf is no longer an operand; this thread keeps its part of the row in kfr)
             uint32_t r[32];
-            tmem_ld32(t_lane + TB_ACC + 32 * half, r);
+            tmem_ld32(g.t_lane + TB_ACC + 32 * g.half, r);
             tmem_ld_wait();
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) {
-                uint4 pk;
-                pk.x = pack_bf16(__uint_as_float(r[8 * cc + 0]), __uint_as_float(r[8 * cc + 1]));
-                pk.y = pack_bf16(__uint_as_float(r[8 * cc + 2]), __uint_as_float(r[8 * cc + 3]));
-                pk.z = pack_bf16(__uint_as_float(r[8 * cc + 4]), __uint_as_float(r[8 * cc + 5]));
-                pk.w = pack_bf16(__uint_as_float(r[8 * cc + 6]), __uint_as_float(r[8 * cc + 7]));
-                *reinterpret_cast<uint4 *>(sK + sw128_off(tid, half * 4 + cc)) = pk;
-            }
+            for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sK + sw128_off(g.row, g.half * 4 + cc)) = pack8u(r + 8 * cc, 1.f);
         }
-        convert_x<false>(t_lane, sX, tid, warp, 0.f, sgd);
+        convert_scores<false>(g, TB_X, sX, 0.f, sgd);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -750,26 +682,24 @@ linattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        // dk rows -> staging (sX block 1)
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
+        {   // dk rows -> staging (sX block 1)
             uint32_t r[32];
-            tmem_ld32(t_lane + TB_ACC + 32 * half, r);
+            tmem_ld32(g.t_lane + TB_ACC + 32 * g.half, r);
             tmem_ld_wait();
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 float f[8], kf[8];
-                const int ch = half * 4 + cc;
-                unpack8(make_uint4(kfr[4 * ch], kfr[4 * ch + 1], kfr[4 * ch + 2], kfr[4 * ch + 3]), kf);
+                const int ch = g.half * 4 + cc;
+                unpack8(make_uint4(kfr[4 * cc], kfr[4 * cc + 1], kfr[4 * cc + 2], kfr[4 * cc + 3]), kf);
 #pragma unroll
                 for (int i = 0; i < 8; ++i)         // phi'(k) = phi(k) when phi(k) <= 1 (k <= 0), else 1
                     f[i] = (__uint_as_float(r[8 * cc + i]) + rzc[8 * ch + i]) * (kf[i] <= 1.f ? kf[i] : 1.f);
-                *reinterpret_cast<uint4 *>(sX + TILE_BYTES + sw128_off(tid, ch)) = pack8(f);
+                *reinterpret_cast<uint4 *>(sX + TILE_BYTES + sw128_off(g.row, ch)) = pack8(f);
             }
         }
         if (it + 1 < nchunks) {
-            state_to_smem(t_lane, sR, lane, erow);
-            if (tid < 64) rzn[tid] = rzc[tid] + sdr[tid] + sdr[64 + tid];
+            state_half_to_smem(g, TB_ST, sR);
+            if (tid < 64) rzn[tid] = rzc[tid] + sdr[tid] + sdr[64 + tid] + sdr[128 + tid] + sdr[192 + tid];
         }
         fence_proxy_async();
         tc_fence_before();
@@ -786,7 +716,7 @@ linattn_bwd_dkv_tc_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_
     if (tid == 0) tma_store_wait_all0();
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<256>(tmem);
+    if ((tid >> 5) == 0) tmem_dealloc<256>(tmem);
 }
 
 }  // namespace
@@ -814,7 +744,7 @@ int linattn_fwd_tc_launch(const void *q, const void *k, const void *v, void *out
         if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "linattn_fwd_tc smem attribute: %s", cudaGetErrorString(e));
         attr_set = true;
     }
-    linattn_fwd_tc_kernel<<<N * H * nseg, 128, FWD_SMEM_BYTES, st>>>(tq, tk, tv, to, den, L, H, nseg, seg_len, (const float *)ws, eps);
+    linattn_fwd_tc_kernel<<<N * H * nseg, NTH, FWD_SMEM_BYTES, st>>>(tq, tk, tv, to, den, L, H, nseg, seg_len, (const float *)ws, eps);
     return check_launch("linattn_fwd_tc");
 }
 
@@ -854,8 +784,8 @@ int linattn_bwd_tc_launch(const void *q, const void *k, const void *v, const voi
     a.ws_fwd = (const float *)ws;
     a.ws_rev = a.ws_fwd + (int64_t)N * H * nseg * STATE_FLOATS;
     a.L = L; a.H = H; a.nseg = nseg; a.seg_len = seg_len;
-    linattn_bwd_dq_tc_kernel<<<N * H * nseg, 128, BWD_SMEM_BYTES, st>>>(tq, tk, tv, tgo, to, tgq, a);
-    linattn_bwd_dkv_tc_kernel<<<N * H * nseg, 128, BWD_SMEM_BYTES, st>>>(tq, tk, tv, tgo, to, tgk, tgv, a);
+    linattn_bwd_dq_tc_kernel<<<N * H * nseg, NTH, BWD_SMEM_BYTES, st>>>(tq, tk, tv, tgo, to, tgq, a);
+    linattn_bwd_dkv_tc_kernel<<<N * H * nseg, NTH, BWD_SMEM_BYTES, st>>>(tq, tk, tv, tgo, to, tgk, tgv, a);
     return check_launch("linattn_bwd_tc");
 }
 

@@ -15,11 +15,15 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--impl", type=int, nargs="+", default=[1, 2])
     ap.add_argument("--iters", type=int, default=20)
+    ap.add_argument("--shape", default=None, help="substring filter on the shape name")
+    ap.add_argument("--dirs", nargs="+", default=["fwd", "bwd"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
     for name, (N, L, H) in SHAPES.items():
+        if args.shape and args.shape not in name:
+            continue
         g = torch.Generator().manual_seed(0)
         qkv = torch.randn(N, L, 3 * H * 64, generator=g).to(dev).bfloat16()
         q, k, v = (qkv[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
@@ -27,7 +31,7 @@ def main():
         gqkv = torch.empty_like(qkv)
         gq, gk, gv = (gqkv[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
         for impl in args.impl:
-            for direction in ("fwd", "bwd"):
+            for direction in args.dirs:
                 out, den = cpmusic.ops.linattn_fwd_raw(q, k, v, impl=impl)
                 def run():
                     if direction == "fwd":
