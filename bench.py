@@ -5,11 +5,13 @@
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 \
         --master-port P bench.py --gpus N --steps K --warmup W
 
-Workload (BASELINE.json configs[2], weak scaling — per GPU): autoregressive RECURRENT rollout of
-32 songs x 1024 compound-word tokens with the reference's per-attribute temperature / nucleus
-sampling, critic values, GAE(lambda) with globally normalised advantages, then one clipped-PPO
-update of the 12-layer / d512 / 8-head actor and critic over those 32x1024 tokens (2 minibatches of
-16x1024, dropout 0.1, Adam, bucketed NCCL gradient all-reduce).  Synthetic data: random-init
+Workload (BASELINE.json configs[2]: "rollout of 256 songs x 1024 CP tokens with nucleus sampling,
+followed by a GAE plus clipped-loss update"; it fits one GPU, so it is the per-GPU workload and N GPUs
+run N such shards — weak scaling): autoregressive RECURRENT rollout of 256 songs x 1024 compound-word
+tokens with the reference's per-attribute temperature / nucleus sampling, critic values, GAE(lambda)
+with globally normalised advantages, then one clipped-PPO update of the 12-layer / d512 / 8-head actor
+and critic over those 256x1024 tokens (16 minibatches of 16x1024 with gradient accumulation, dropout
+0.1, grad-clip 3, Adam, bucketed NCCL gradient all-reduce).  Synthetic data: random-init
 weights, random initial tokens, and a synthetic reward (the reference's Longformer reward model is
 out of scope).  One "step" = one such iteration; value = tokens generated and trained
 on per second over all GPUs.
@@ -30,7 +32,7 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VOCAB = [56, 135, 18, 87, 18, 25]            # AIlabs-Pop1K7 dictionary without 'type' (IRL_dqn_train.py:403)
-SONGS_PER_GPU, ROLLOUT_LEN, MINIBATCH = 32, 1024, 16
+SONGS_PER_GPU, ROLLOUT_LEN, MINIBATCH = 256, 1024, 16
 METRIC = "CP tokens/s, PPO rollout+update"
 UNIT = "tokens/s"
 
@@ -172,8 +174,8 @@ def run_reference(args, rank):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tokens / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": "cfg3: PPO rollout (32 songs x 1024 CP tokens, recurrent, nucleus) + GAE + clipped update; "
-                                   "CPU arm extrapolated from a bounded sample", "model": "CP linear transformer 12L d512 h8"},
+            "config": {"workload": f"cfg3: PPO rollout ({SONGS_PER_GPU} songs x {ROLLOUT_LEN} CP tokens, recurrent, nucleus) + GAE + clipped "
+                                   "update; CPU arm extrapolated from a bounded sample", "model": "CP linear transformer 12L d512 h8"},
             "cpu_baseline": r, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
@@ -378,9 +380,9 @@ def run_gpu(args, rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": "cfg3: PPO rollout (32 songs x 1024 CP tokens per GPU, recurrent, per-attribute temperature/nucleus "
-                                   "sampling) + critic values + GAE + one clipped-PPO update (actor+critic, 2 minibatches of 16x1024, "
-                                   "dropout 0.1, Adam)", "model": "CP linear transformer 12L d512 h8 ff2048 (38.98M params) x2 (actor, critic)",
+            "config": {"workload": f"cfg3: PPO rollout ({SONGS_PER_GPU} songs x {ROLLOUT_LEN} CP tokens per GPU, recurrent, per-attribute "
+                                   f"temperature/nucleus sampling) + critic values + GAE + one clipped-PPO update (actor+critic, "
+                                   f"{SONGS_PER_GPU // MINIBATCH} minibatches of {MINIBATCH}x{ROLLOUT_LEN}, dropout 0.1, grad-clip 3, Adam)", "model": "CP linear transformer 12L d512 h8 ff2048 (38.98M params) x2 (actor, critic)",
                        "tokens_per_step": tokens_step, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (working set > 1 GB/step)",
                        "reward": "synthetic (Longformer reward model out of scope)"},
             "roofline": roofline, "roofline_recurrent_step": roofline_step, "cpu_baseline": cpu,

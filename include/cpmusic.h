@@ -49,7 +49,7 @@ int cpm_version(void);
 const char *cpm_last_error_string(void);
 const char *cpm_error_name(int code);
 /* Name of the kernel implementation the last cpm_linattn_fwd/bwd call dispatched to
- * ("tcgen05" | "simt"); lets tests assert which path ran. */
+ * ("tcgen05-cp" | "tcgen05" | "simt"); lets tests assert which path ran. */
 const char *cpm_linattn_last_impl(void);
 
 /* ------------------------------------------------------------------------------------------
@@ -64,19 +64,25 @@ const char *cpm_linattn_last_impl(void);
  * stride `ld_qkv` elements (so the three can be column slices of one fused QKV GEMM output);
  * out / gout are (N,L,H,M) with token stride `ld_o`; gq,gk,gv have token stride `ld_g`.
  * den is (N,L,H) fp32, written by fwd and read by bwd.  E = M = 64 (the reference) only.
- * impl: 0 = auto (tcgen05 when dtype==BF16 and L%128==0, else simt), 1 = simt, 2 = tcgen05.
- * Workspace: cpm_linattn_workspace_bytes(N,L,H) bytes (segment states).
+ * impl: 0 = auto (chunk-parallel tcgen05 when dtype==BF16 and L%128==0, else simt), 1 = simt,
+ *       2 = tcgen05, one CTA per (batch, head[, segment]) walking its chunks in order,
+ *       3 = tcgen05, chunk-parallel (one CTA per 128-token chunk; state pre-pass + prefix scan).
+ * Workspace: cpm_linattn_workspace_bytes(N,L,H) bytes (segment / chunk states), scratch only.
+ * saved (optional, impl 3): cpm_linattn_saved_bytes(N,L,H) bytes that fwd fills with the per-chunk
+ * prefix states (bf16 tiles + fp32 key sums) and bwd reads back instead of rebuilding them — the
+ * one tensor besides `den` the caller keeps for backward.  NULL = not kept (bwd recomputes).
  * ------------------------------------------------------------------------------------------ */
 int64_t cpm_linattn_workspace_bytes(int N, int L, int H);
+int64_t cpm_linattn_saved_bytes(int N, int L, int H);
 int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, float *den,
                     int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
                     int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes,
-                    void *stream);
+                    void *saved, int64_t saved_bytes, void *stream);
 int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out, const float *den,
                     const void *gout, void *gq, void *gk, void *gv,
                     int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o, int64_t ld_g,
                     int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes,
-                    void *stream);
+                    const void *saved, int64_t saved_bytes, void *stream);
 
 /* B1 — recurrent one-token step.  Replaces ft `RecurrentLinearAttention.forward`
  * (builder at dqn_policy/model.py:141-150; call at dqn_policy/model.py:237,

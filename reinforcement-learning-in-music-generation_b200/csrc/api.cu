@@ -105,7 +105,12 @@ int64_t cpm_linattn_workspace_bytes(int N, int L, int H) {
     if (N <= 0 || L <= 0 || H <= 0) return 0;
     int nseg, seg_len;
     plan_segments(N, H, L, &nseg, &seg_len);
-    return 2ll * N * H * nseg * STATE_FLOATS * (int64_t)sizeof(float);
+    const int64_t seg = 2ll * N * H * nseg * STATE_FLOATS * (int64_t)sizeof(float), cp = linattn_cp_workspace_bytes(N, L, H);
+    return seg > cp ? seg : cp;
+}
+int64_t cpm_linattn_saved_bytes(int N, int L, int H) {
+    if (N <= 0 || L <= 0 || H <= 0) return 0;
+    return linattn_cp_saved_bytes(N, L, H);
 }
 
 static int linattn_check(const void *a, const void *b, const void *c, const void *d, int N, int L, int H, int E, int M,
@@ -125,12 +130,18 @@ static int linattn_check(const void *a, const void *b, const void *c, const void
 
 int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int E, int M,
                     int64_t ld_qkv, int64_t ld_o, int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes,
-                    void *stream) {
+                    void *saved, int64_t saved_bytes, void *stream) {
     int rc = linattn_check(q, k, v, out, N, L, H, E, M, ld_qkv, ld_o, dtype, workspace, workspace_bytes);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     bool tc_ok = dtype == CPM_BF16 && L % 128 == 0;
-    CPM_REQUIRE(impl != 2 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_fwd: tcgen05 path needs bf16 and L%%128==0");
+    CPM_REQUIRE((impl != 2 && impl != 3) || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_fwd: tcgen05 path needs bf16 and L%%128==0");
+    CPM_REQUIRE(!saved || saved_bytes >= cpm_linattn_saved_bytes(N, L, H), CPM_ERR_WORKSPACE, "linattn_fwd: saved-state buffer %lld < %lld",
+                (long long)saved_bytes, (long long)cpm_linattn_saved_bytes(N, L, H));
+    if (impl == 3 || (impl == 0 && tc_ok)) {
+        rc = linattn_fwd_cp_launch(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, workspace, saved, st);
+        if (rc != CPM_ERR_UNSUPPORTED || impl == 3) { g_linattn_impl = "tcgen05-cp"; return rc; }
+    }
     if (impl == 2 || (impl == 0 && tc_ok)) {
         rc = linattn_fwd_tc_launch(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, workspace, st);
         if (rc != CPM_ERR_UNSUPPORTED || impl == 2) { g_linattn_impl = "tcgen05"; return rc; }
@@ -141,7 +152,8 @@ int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, floa
 
 int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout,
                     void *gq, void *gk, void *gv, int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
-                    int64_t ld_g, int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes, void *stream) {
+                    int64_t ld_g, int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes, const void *saved,
+                    int64_t saved_bytes, void *stream) {
     int rc = linattn_check(q, k, v, out, N, L, H, E, M, ld_qkv, ld_o, dtype, workspace, workspace_bytes);
     if (rc) return rc;
     CPM_REQUIRE(den && gout && gq && gk && gv, CPM_ERR_NULL, "linattn_bwd: den/gout/gq/gk/gv must be non-NULL");
@@ -150,7 +162,13 @@ int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out
                 "linattn_bwd: gradient buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     bool tc_ok = dtype == CPM_BF16 && L % 128 == 0;
-    CPM_REQUIRE(impl != 2 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_bwd: tcgen05 path needs bf16 and L%%128==0");
+    CPM_REQUIRE((impl != 2 && impl != 3) || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_bwd: tcgen05 path needs bf16 and L%%128==0");
+    CPM_REQUIRE(!saved || saved_bytes >= cpm_linattn_saved_bytes(N, L, H), CPM_ERR_WORKSPACE, "linattn_bwd: saved-state buffer %lld < %lld",
+                (long long)saved_bytes, (long long)cpm_linattn_saved_bytes(N, L, H));
+    if (impl == 3 || (impl == 0 && tc_ok)) {
+        rc = linattn_bwd_cp_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, workspace, saved, st);
+        if (rc != CPM_ERR_UNSUPPORTED || impl == 3) { g_linattn_impl = "tcgen05-cp"; return rc; }
+    }
     if (impl == 2 || (impl == 0 && tc_ok)) {
         rc = linattn_bwd_tc_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, eps, workspace, st);
         if (rc != CPM_ERR_UNSUPPORTED || impl == 2) { g_linattn_impl = "tcgen05"; return rc; }

@@ -1,0 +1,770 @@
+// Chunk-parallel causal linear attention on tcgen05 / TMA (sm_100a), bf16 I/O, fp32 accumulation.
+//
+// The sequential-chunk kernels (linattn_tc.cu) give one CTA a whole (batch, head) row of chunks, so a
+// 16 x 1024 x 8 call exposes only 128 independent chains to 148 SMs.  Here every 128-token chunk of
+// every (batch, head) is its own CTA; the inter-chunk dependency (the KV state) is broken out into a
+// tensor-core pre-pass plus a prefix scan:
+//
+//   forward   F1  cp_state_fwd    per chunk c < C-1 : dS_c = Kf_c^T V_c (M64 N64 K128 UMMA), dz_c = colsum Kf_c   -> fp32 partials
+//             F2  cp_scan         per (n,h)         : exclusive prefix over c  -> Sp_c (bf16 tile), zp_c (fp32)   [saved for backward]
+//             F3  cp_out_fwd      per chunk         : P = Qf Kf^T (masked), O = Qf Sp_c + P V, den = rowsum P + Qf.zp_c
+//   backward  B1  cp_state_bwd    per chunk         : G' = go/den, gd = -(go.out)/den, dR_c = Qf_c^T G'_c, drz_c = Qf_c^T gd
+//             B2  cp_scan (reverse)                 : exclusive suffix over c  -> Rs_c (bf16 tile), rzs_c (fp32)
+//             B3  cp_bwd_main     per chunk         : dq, dk, dv of the chunk from (q,k,v,go) + Sp_c + Rs_c, all within the CTA
+//
+// HBM traffic per (chunk, head): forward reads q,k,v (48 KB) and writes out (16 KB) + den; k,v are read a
+// second time by F1 (L2 hits when the call fits the 126 MB L2) and the state costs 16.6 KB fp32 + 8.4 KB bf16
+// through L2.  Shared-memory tiles are SWIZZLE_128B as TMA writes them; the intra-chunk score tile goes
+// TMEM -> registers (mask, bf16) -> shared memory -> second UMMA, exactly as in linattn_tc.cu.
+#include "cpm_common.cuh"
+#include "linattn_plan.h"
+#include "tc_common.cuh"
+#include "linattn_tc_dev.cuh"
+
+namespace cpm {
+namespace {
+using namespace tc;
+using namespace tcdev;
+
+constexpr uint32_t S_TILE_BYTES = 64 * 128;                           // [64 e rows x 64 m] bf16 state tile
+constexpr uint32_t IDESC_KK128 = idesc_bf16(128, 128, false, false);   // A K-major, B K-major, N=128
+constexpr uint32_t IDESC_KM64 = idesc_bf16(128, 64, false, true);      // A K-major, B MN-major, N=64
+constexpr uint32_t IDESC_KK64 = idesc_bf16(128, 64, false, false);     // A K-major, B K-major,  N=64
+constexpr uint32_t IDESC_MM64 = idesc_bf16(64, 64, true, true);        // A MN-major, B MN-major (M=64 state tile)
+
+// byte offsets inside the `saved` / workspace state regions: NHC tiles of 8 KB, then NHC x 64 floats
+__host__ __device__ inline int64_t state_tiles_bytes(int64_t nhc) { return nhc * (int64_t)S_TILE_BYTES; }
+__host__ __device__ inline int64_t state_region_bytes(int64_t nhc) { return nhc * (int64_t)(S_TILE_BYTES + 256); }
+
+// M=64 accumulator in TMEM columns [col, col+64) -> fp32 rows dst[e*64 + m] (128-thread kernels, warps 0..3:
+// warp w holds rows 16w..16w+15 in lanes 0..15 of its TMEM quarter).
+__device__ __forceinline__ void state64_to_global(uint32_t tmem, uint32_t col, float *dst) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int erow = 16 * warp + (lane & 15);
+#pragma unroll
+    for (int p = 0; p < 2; ++p) {
+        uint32_t r[32];
+        tmem_ld32(t_lane + col + 32 * p, r);
+        tmem_ld_wait();
+        if (lane < 16) {
+            float4 *d = reinterpret_cast<float4 *>(dst + erow * 64 + 32 * p);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                d[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]), __uint_as_float(r[4 * i + 2]),
+                                   __uint_as_float(r[4 * i + 3]));
+        }
+    }
+}
+
+// column sums over 64 rows (half) of a swizzled [128 x 64] bf16 tile, optionally row-weighted
+__device__ __forceinline__ float colsum_half(const uint8_t *tile, int e, int half, const float *w) {
+    float s = 0.f;
+#pragma unroll 8
+    for (int j = 64 * half; j < 64 * half + 64; ++j) {
+        const __nv_bfloat16 x = *reinterpret_cast<const __nv_bfloat16 *>(tile + sw128_off(j, e >> 3) + (e & 7) * 2);
+        s = fmaf(__bfloat162float(x), w ? w[j] : 1.f, s);
+    }
+    return s;
+}
+
+// =============================================================================================
+// F1: per-chunk state increments  dS = Kf^T V, dz = colsum Kf        (128 threads, 64 TMEM columns)
+// =============================================================================================
+constexpr uint32_t P_OFF_A = 0, P_OFF_B = 16384, P_OFF_C = 32768;      // up to three input tiles
+constexpr uint32_t PF_OFF_MISC = 32768, PB_OFF_MISC = 49152;
+constexpr uint32_t PF_SMEM = PF_OFF_MISC + 512 + 64, PB_SMEM = PB_OFF_MISC + 512 + 512 + 64;
+
+__global__ void __launch_bounds__(128)
+cp_state_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, float *__restrict__ part,
+                    int L, int H, int nchunks) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sK = sm + P_OFF_A, *sV = sm + P_OFF_B;
+    float *sdz = reinterpret_cast<float *>(sm + PF_OFF_MISC);                  // [2][64]
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + PF_OFF_MISC + 512), *bar_mma = bar_load + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
+    const int tid = threadIdx.x;
+    const int per = nchunks - 1;
+    const int nh = blockIdx.x / per, c = blockIdx.x % per, n = nh / H, h = nh % H;
+    const int grow = n * L + c * CHUNK, col0 = h * 64;
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar_load, 2 * TILE_BYTES);
+        tma_load_2d(sK, &tmK, bar_load, col0, grow);
+        tma_load_2d(sV, &tmV, bar_load, col0, grow);
+    }
+    if ((tid >> 5) == 0) tmem_alloc<64>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    mbar_wait(bar_load, 0);
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t off = sw128_off(tid, ch);
+        float f[8];
+        *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    if (tid == 0) {
+        tc_fence_after();
+        const uint64_t dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
+#pragma unroll
+        for (int k = 0; k < 8; ++k) mma_ss(tmem, dK + 128 * k, dV + 128 * k, IDESC_MM64, k > 0);
+        mma_commit(bar_mma);
+    }
+    sdz[tid] = colsum_half(sK, tid & 63, tid >> 6, nullptr);                   // overlaps the MMA
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    float *dst = part + ((int64_t)nh * nchunks + c) * STATE_FLOATS;
+    state64_to_global(tmem, 0, dst);
+    tc_fence_before();
+    __syncthreads();
+    if (tid < 64) dst[4096 + tid] = sdz[tid] + sdz[64 + tid];
+    if ((tid >> 5) == 0) tmem_dealloc<64>(tmem);
+}
+
+// =============================================================================================
+// B1: G' = go/den, gd = -(go.out)/den (stored per token), dR = Qf^T G', drz = Qf^T gd
+// =============================================================================================
+__global__ void __launch_bounds__(128)
+cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmGo,
+                    const __grid_constant__ CUtensorMap tmO, const float *__restrict__ den, float *__restrict__ gd_out,
+                    float *__restrict__ part, int L, int H, int nchunks) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sQ = sm + P_OFF_A, *sG = sm + P_OFF_B, *sO = sm + P_OFF_C;
+    float *sdr = reinterpret_cast<float *>(sm + PB_OFF_MISC);                  // [2][64]
+    float *sgd = sdr + 128;                                                    // [128]
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + PB_OFF_MISC + 1024), *bar_mma = bar_load + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
+    const int tid = threadIdx.x;
+    const int nh = blockIdx.x / nchunks, c = blockIdx.x % nchunks, n = nh / H, h = nh % H;
+    const int grow = n * L + c * CHUNK, col0 = h * 64;
+    const bool need_state = c > 0;                     // chunk 0's increment is never consumed (suffix scan)
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar_load, (need_state ? 3 : 2) * TILE_BYTES);
+        tma_load_2d(sG, &tmGo, bar_load, col0, grow);
+        tma_load_2d(sO, &tmO, bar_load, col0, grow);
+        if (need_state) tma_load_2d(sQ, &tmQ, bar_load, col0, grow);
+    }
+    if ((tid >> 5) == 0) tmem_alloc<64>(tmem_slot);
+    const float inv = 1.f / den[(int64_t)(grow + tid) * H + h];
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    mbar_wait(bar_load, 0);
+    float dot = 0.f;
+#pragma unroll
+    for (int ch = 0; ch < 8; ++ch) {
+        const uint32_t off = sw128_off(tid, ch);
+        float gg[8], o[8];
+        unpack8(*reinterpret_cast<const uint4 *>(sG + off), gg);
+        unpack8(*reinterpret_cast<const uint4 *>(sO + off), o);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { dot = fmaf(gg[i], o[i], dot); gg[i] *= inv; }
+        if (need_state) {
+            *reinterpret_cast<uint4 *>(sG + off) = pack8(gg);
+            float f[8];
+            *reinterpret_cast<uint4 *>(sQ + off) = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
+        }
+    }
+    const float gd = -inv * dot;
+    gd_out[(int64_t)(grow + tid) * H + h] = gd;
+    if (need_state) {                                   // uniform over the CTA
+        sgd[tid] = gd;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dG = smem_desc_sw128(smem_u32(sG));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem, dQ + 128 * k, dG + 128 * k, IDESC_MM64, k > 0);
+            mma_commit(bar_mma);
+        }
+        sdr[tid] = colsum_half(sQ, tid & 63, tid >> 6, sgd);
+        mbar_wait(bar_mma, 0);
+        tc_fence_after();
+        float *dst = part + ((int64_t)nh * nchunks + c) * STATE_FLOATS;
+        state64_to_global(tmem, 0, dst);
+        tc_fence_before();
+        __syncthreads();
+        if (tid < 64) dst[4096 + tid] = sdr[tid] + sdr[64 + tid];
+    } else {
+        tc_fence_before();
+        __syncthreads();
+    }
+    if ((tid >> 5) == 0) tmem_dealloc<64>(tmem);
+}
+
+// =============================================================================================
+// F1s: streaming prefix states.  One CTA per (batch, head) walks its chunks in order; the KV state
+// accumulates in TMEM across chunks (UMMA accumulate flag) and is snapshotted after every chunk straight
+// into the bf16 prefix tile of the NEXT chunk - no fp32 increments, no scan launch.  The loop carries no
+// dependency through memory, so K/V tiles are prefetched ST_STAGES chunks ahead by TMA.
+// Used when there are enough (batch, head) pairs to fill the GPU; otherwise F1 + F2.
+// =============================================================================================
+constexpr int ST_STAGES = 3;
+constexpr uint32_t ST_STAGE_BYTES = 2 * TILE_BYTES;
+constexpr uint32_t ST_OFF_MISC = ST_STAGES * ST_STAGE_BYTES, ST_SMEM = ST_OFF_MISC + 512 + 64;
+
+__global__ void __launch_bounds__(128)
+cp_prefix_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
+                            uint8_t *__restrict__ tiles, float *__restrict__ zs, int L, int H, int nchunks) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    float *sdz = reinterpret_cast<float *>(sm + ST_OFF_MISC);                  // [2][64]
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + ST_OFF_MISC + 512);  // [ST_STAGES]
+    uint64_t *bar_mma = bar_full + ST_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nh = blockIdx.x, n = nh / H, h = nh % H;
+    const int row0 = n * L, col0 = h * 64;
+    const int nwork = nchunks - 1;                       // chunks 0 .. C-2 feed the prefixes of chunks 1 .. C-1
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        for (int s = 0; s < ST_STAGES; ++s) mbar_init(bar_full + s, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+        for (int s = 0; s < ST_STAGES && s < nwork; ++s) {
+            mbar_expect_tx(bar_full + s, ST_STAGE_BYTES);
+            tma_load_2d(sm + s * ST_STAGE_BYTES, &tmK, bar_full + s, col0, row0 + s * CHUNK);
+            tma_load_2d(sm + s * ST_STAGE_BYTES + TILE_BYTES, &tmV, bar_full + s, col0, row0 + s * CHUNK);
+        }
+    }
+    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
+    const int erow = 16 * warp + (lane & 15);
+    float zacc = 0.f;
+    for (int c = 0; c < nwork; ++c) {
+        const int s = c % ST_STAGES;
+        uint8_t *sK = sm + s * ST_STAGE_BYTES, *sV = sK + TILE_BYTES;
+        mbar_wait(bar_full + s, (c / ST_STAGES) & 1);
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t off = sw128_off(tid, ch);
+            float f[8];
+            *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem, dK + 128 * k, dV + 128 * k, IDESC_MM64, (c > 0 || k > 0) ? 1u : 0u);
+            mma_commit(bar_mma);
+        }
+        sdz[tid] = colsum_half(sK, tid & 63, tid >> 6, nullptr);               // overlaps the MMA
+        mbar_wait(bar_mma, c & 1);
+        tc_fence_after();
+        const int64_t slot = (int64_t)nh * nchunks + c + 1;
+        uint8_t *dst = tiles + slot * S_TILE_BYTES + erow * 128;
+#pragma unroll
+        for (int p = 0; p < 2; ++p) {
+            uint32_t r[32];
+            tmem_ld32(t_lane + 32 * p, r);
+            tmem_ld_wait();
+            if (lane < 16) {
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(dst + 64 * p + 16 * cc) = pack8u(r + 8 * cc, 1.f);
+            }
+        }
+        tc_fence_before();
+        __syncthreads();                                  // sdz complete; every warp has read its TMEM rows and this stage's tiles
+        if (tid == 0 && c + ST_STAGES < nwork) {          // refill the stage
+            mbar_expect_tx(bar_full + s, ST_STAGE_BYTES);
+            tma_load_2d(sK, &tmK, bar_full + s, col0, row0 + (c + ST_STAGES) * CHUNK);
+            tma_load_2d(sV, &tmV, bar_full + s, col0, row0 + (c + ST_STAGES) * CHUNK);
+        }
+        if (tid < 64) {
+            zacc += sdz[tid] + sdz[64 + tid];
+            zs[slot * 64 + tid] = zacc;
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<64>(tmem);
+}
+
+// =============================================================================================
+// F2 / B2: exclusive prefix (reverse = 0) or exclusive suffix (reverse = 1) of the per-chunk increments over
+// the chunk axis; fp32 accumulation, bf16 state tile + fp32 z out.  One thread = 4 consecutive state floats.
+// =============================================================================================
+__global__ void __launch_bounds__(256)
+cp_scan_kernel(const float *__restrict__ part, uint8_t *__restrict__ tiles, float *__restrict__ zs, int nchunks, int reverse) {
+    const int nh = blockIdx.x, i4 = blockIdx.y * 256 + threadIdx.x;
+    if (i4 >= STATE_FLOATS / 4) return;
+    const float4 *src = reinterpret_cast<const float4 *>(part + (int64_t)nh * nchunks * STATE_FLOATS) + i4;
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+    for (int s = 0; s + 1 < nchunks; ++s) {
+        const int c = reverse ? nchunks - 1 - s : s;        // increment consumed
+        const int d = reverse ? c - 1 : c + 1;              // chunk that receives the running sum
+        const float4 p = src[(int64_t)c * (STATE_FLOATS / 4)];
+        acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
+        const int64_t slot = (int64_t)nh * nchunks + d;
+        if (i4 < 1024) {
+            uint2 o = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
+            *reinterpret_cast<uint2 *>(tiles + slot * S_TILE_BYTES + (int64_t)i4 * 8) = o;
+        } else {
+            *reinterpret_cast<float4 *>(zs + slot * 64 + (i4 - 1024) * 4) = acc;
+        }
+    }
+}
+
+// =============================================================================================
+// F3: per-chunk outputs.  256 threads (two per token row), 128 TMEM columns, 3 CTAs / SM.
+//   shared memory: sQ | sV | sS | sK..sP  (the 32 KB bf16 score tile starts on the dead K tile)
+// =============================================================================================
+constexpr uint32_t F_OFF_Q = 0, F_OFF_V = 16384, F_OFF_S = 32768, F_OFF_K = 40960, F_OFF_P = 40960;
+constexpr uint32_t F_OFF_Z = 73728, F_OFF_DP = F_OFF_Z + 256, F_OFF_BAR = F_OFF_DP + 2048, F_SMEM = F_OFF_BAR + 32;
+
+__device__ __forceinline__ void store_row32(void *base, int64_t ld_elems, int64_t row, int col, const uint4 (&v)[4]) {
+    uint4 *d = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(base) + row * ld_elems + col);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) d[i] = v[i];
+}
+
+__global__ void __launch_bounds__(NTH, 3)
+cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmS, const float *__restrict__ zp,
+                  void *__restrict__ out, float *__restrict__ den, int L, int H, int nchunks, int NH, int64_t ld_o, float eps) {
+    // Persistent: CTA b handles tiles b, b + gridDim.x, ... in chunk-major order (tile t = chunk t / NH of pair t % NH),
+    // so barrier / TMEM set-up is paid once and the next tile's TMA loads fly while this tile's epilogue runs.
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sQ = sm + F_OFF_Q, *sK = sm + F_OFF_K, *sV = sm + F_OFF_V, *sS = sm + F_OFF_S, *sP = sm + F_OFF_P;
+    float *sz = reinterpret_cast<float *>(sm + F_OFF_Z), *sdp = reinterpret_cast<float *>(sm + F_OFF_DP);
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + F_OFF_BAR), *bar_mma = bar_load + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
+    const int tid = threadIdx.x;
+    const int ntiles = NH * nchunks;
+    auto issue_loads = [&](int t) {                   // tid 0 only
+        const int c = t / NH, nh = t % NH, n = nh / H, h = nh % H;
+        const int grow = n * L + c * CHUNK, col0 = h * 64;
+        mbar_expect_tx(bar_load, 3 * TILE_BYTES + (c > 0 ? S_TILE_BYTES : 0));
+        tma_load_2d(sQ, &tmQ, bar_load, col0, grow);
+        tma_load_2d(sK, &tmK, bar_load, col0, grow);
+        tma_load_2d(sV, &tmV, bar_load, col0, grow);
+        if (c > 0) tma_load_2d(sS, &tmS, bar_load, 0, (int)(((int64_t)nh * nchunks + c) * 64));
+    };
+    auto load_z = [&](int t) {                        // tid < 64
+        const int c = t / NH, nh = t % NH;
+        sz[tid] = c > 0 ? zp[((int64_t)nh * nchunks + c) * 64 + tid] : 0.f;
+    };
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+        if ((int)blockIdx.x < ntiles) issue_loads(blockIdx.x);
+    }
+    if ((tid >> 5) == 0) tmem_alloc<128>(tmem_slot);
+    if (tid < 64 && (int)blockIdx.x < ntiles) load_z(blockIdx.x);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const Geo g(tmem);
+    const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
+    const uint64_t dP = smem_desc_sw128(smem_u32(sP)), dS = smem_desc_sw128(smem_u32(sS));
+    uint32_t ph_load = 0, ph_mma = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        const int c = t / NH, nh = t % NH, n = nh / H, h = nh % H;
+        const int grow = n * L + c * CHUNK, col0 = h * 64;
+        const bool have_state = c > 0;
+        mbar_wait(bar_load, ph_load);
+        ph_load ^= 1;
+        float den_inter = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const int ch = 4 * g.half + cc;
+            const uint32_t off = sw128_off(g.row, ch);
+            float f[8];
+            *reinterpret_cast<uint4 *>(sQ + off) = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) den_inter = fmaf(f[i], sz[ch * 8 + i], den_inter);
+            *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+        }
+        sdp[g.half * 128 + g.row] = den_inter;
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {                                   // P = Qf Kf^T
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem, dQ + 2 * k, dK + 2 * k, IDESC_KK128, k > 0);
+            mma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        sdp[256 + g.half * 128 + g.row] = convert_scores<true>(g, 0, sP, 0.f, nullptr);     // overwrites the dead K tile
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        if (tid == 0) {                                   // O = Qf Sp + P V   (into the score tile's first 64 columns)
+            tc_fence_after();
+            uint32_t acc = 0;
+            if (have_state) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) { mma_ss(tmem, dQ + 2 * k, dS + 128 * k, IDESC_KM64, acc); acc = 1; }
+            }
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { mma_ss(tmem, dP + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dV + 128 * k, IDESC_KM64, acc); acc = 1; }
+            mma_commit(bar_mma);
+        }
+        const float dn = sdp[g.row] + sdp[128 + g.row] + sdp[256 + g.row] + sdp[384 + g.row] + eps;
+        const float inv = 1.f / dn;
+        if (den && g.half == 0) den[(int64_t)(grow + g.row) * H + h] = dn;
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        const int tn = t + gridDim.x;
+        if (tn < ntiles) {                                // every operand tile is dead: fetch the next tile under the epilogue
+            if (tid == 0) issue_loads(tn);
+            if (tid < 64) load_z(tn);
+        }
+        {
+            uint32_t r[32];
+            tmem_ld32(g.t_lane + 32 * g.half, r);
+            tmem_ld_wait();
+            uint4 o[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, inv);
+            store_row32(out, ld_o, grow + g.row, col0 + 32 * g.half, o);
+        }
+        tc_fence_before();
+        __syncthreads();                                  // TMEM columns and sz / sdp are reused by the next tile
+        tc_fence_after();
+    }
+    if ((tid >> 5) == 0) tmem_dealloc<128>(tmem);
+}
+
+// =============================================================================================
+// B3: dq, dk, dv of one chunk.  256 threads, 256 TMEM columns, 2 CTAs / SM.
+//   X[i][j]  = G'[i].v[j] + gd_i   (j <= i)        dQf = X Kf + G' Sp^T + gd z         dq = dQf * phi'(q)
+//   PT[j][i] = Kf[j].Qf[i]         (i >= j)        dv  = PT G' + Kf Rs
+//   WT[j][i] = v[j].G'[i] + gd_i   (i >= j)        dKf = WT Qf + v Rs^T + rz           dk = dKf * phi'(k)
+// =============================================================================================
+constexpr uint32_t B_OFF_Q = 0, B_OFF_K = 16384, B_OFF_V = 32768, B_OFF_G = 49152, B_OFF_S = 65536, B_OFF_R = 73728, B_OFF_X = 81920;
+constexpr uint32_t B_OFF_GD = 114688, B_OFF_BAR = B_OFF_GD + 512, B_SMEM = B_OFF_BAR + 32;
+constexpr uint32_t TB_X = 0, TB_A1 = 128, TB_A2 = 192;
+
+struct BwdMainArgs {
+    const float *den, *gd, *zp, *rzs;
+    void *gq, *gk, *gv;
+    int64_t ld_g;
+    int L, H, nchunks;
+};
+
+__global__ void __launch_bounds__(NTH, 2)
+cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
+                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmGo,
+                   const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmR, BwdMainArgs a) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sQ = sm + B_OFF_Q, *sK = sm + B_OFF_K, *sV = sm + B_OFF_V, *sG = sm + B_OFF_G, *sS = sm + B_OFF_S, *sR = sm + B_OFF_R;
+    uint8_t *sX = sm + B_OFF_X;
+    float *sgd = reinterpret_cast<float *>(sm + B_OFF_GD);
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + B_OFF_BAR), *bar_mma = bar_load + 1;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
+    const int tid = threadIdx.x;
+    const int nh = blockIdx.x / a.nchunks, c = blockIdx.x % a.nchunks, n = nh / a.H, h = nh % a.H;
+    const int grow = n * a.L + c * CHUNK, col0 = h * 64;
+    const bool have_s = c > 0, have_r = c + 1 < a.nchunks;
+    const int64_t slot = (int64_t)nh * a.nchunks + c;
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        mbar_init(bar_load, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+        mbar_expect_tx(bar_load, 4 * TILE_BYTES + (have_s ? S_TILE_BYTES : 0) + (have_r ? S_TILE_BYTES : 0));
+        tma_load_2d(sQ, &tmQ, bar_load, col0, grow);
+        tma_load_2d(sK, &tmK, bar_load, col0, grow);
+        tma_load_2d(sV, &tmV, bar_load, col0, grow);
+        tma_load_2d(sG, &tmGo, bar_load, col0, grow);
+        if (have_s) tma_load_2d(sS, &tmS, bar_load, 0, (int)(slot * 64));
+        if (have_r) tma_load_2d(sR, &tmR, bar_load, 0, (int)(slot * 64));
+    }
+    if ((tid >> 5) == 0) tmem_alloc<256>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const Geo g(tmem);
+    const float inv = 1.f / a.den[(int64_t)(grow + g.row) * a.H + h];
+    const float gd = a.gd[(int64_t)(grow + g.row) * a.H + h];
+    if (g.half == 0) sgd[g.row] = gd;
+    const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
+    const uint64_t dG = smem_desc_sw128(smem_u32(sG)), dS = smem_desc_sw128(smem_u32(sS)), dR = smem_desc_sw128(smem_u32(sR));
+    const uint64_t dX = smem_desc_sw128(smem_u32(sX));
+    mbar_wait(bar_load, 0);
+    uint32_t qfr[16], kfr[16];                         // this thread's Qf / Kf values (packed bf16) for phi'
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
+        float f[8];
+        unpack8(*reinterpret_cast<const uint4 *>(sG + off), f);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) f[i] *= inv;
+        *reinterpret_cast<uint4 *>(sG + off) = pack8(f);
+        const uint4 qv = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
+        *reinterpret_cast<uint4 *>(sQ + off) = qv;
+        qfr[4 * cc + 0] = qv.x; qfr[4 * cc + 1] = qv.y; qfr[4 * cc + 2] = qv.z; qfr[4 * cc + 3] = qv.w;
+        const uint4 kv = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+        *reinterpret_cast<uint4 *>(sK + off) = kv;
+        kfr[4 * cc + 0] = kv.x; kfr[4 * cc + 1] = kv.y; kfr[4 * cc + 2] = kv.z; kfr[4 * cc + 3] = kv.w;
+    }
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- round 1: X = G' V^T
+    if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dG + 2 * k, dV + 2 * k, IDESC_KK128, k > 0);
+        mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    convert_scores<true>(g, TB_X, sX, gd, nullptr);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- round 2: dQf = X Kf (+ G' Sp^T) ; PT = Kf Qf^T
+    if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dK + 128 * k, IDESC_KM64, k > 0);
+        if (have_s) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dG + 2 * k, dS + 2 * k, IDESC_KK64, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dQ + 2 * k, IDESC_KK128, k > 0);
+        mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 1);
+    tc_fence_after();
+    {   // dq rows
+        uint32_t r[32];
+        tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
+        tmem_ld_wait();
+        const float *z = a.zp + slot * 64 + 32 * g.half;
+        uint4 o[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            float f[8], qf[8];
+            unpack8(make_uint4(qfr[4 * cc], qfr[4 * cc + 1], qfr[4 * cc + 2], qfr[4 * cc + 3]), qf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float zz = have_s ? __ldg(z + 8 * cc + i) : 0.f;
+                f[i] = (__uint_as_float(r[8 * cc + i]) + gd * zz) * (qf[i] <= 1.f ? qf[i] : 1.f);
+            }
+            o[cc] = pack8(f);
+        }
+        store_row32(a.gq, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+    }
+    convert_scores<false>(g, TB_X, sX, 0.f, nullptr);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- round 3: dv = PT G' (+ Kf Rs) ; WT = V G'^T
+    if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            mma_ss(tmem + TB_A2, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
+        if (have_r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A2, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);
+        }
+#pragma unroll
+        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dV + 2 * k, dG + 2 * k, IDESC_KK128, k > 0);
+        mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 0);
+    tc_fence_after();
+    {   // dv rows
+        uint32_t r[32];
+        tmem_ld32(g.t_lane + TB_A2 + 32 * g.half, r);
+        tmem_ld_wait();
+        uint4 o[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, 1.f);
+        store_row32(a.gv, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+    }
+    convert_scores<false>(g, TB_X, sX, 0.f, sgd);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    // ---- round 4: dKf = WT Qf (+ v Rs^T)
+    if (tid == 0) {
+        tc_fence_after();
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dQ + 128 * k, IDESC_KM64, k > 0);
+        if (have_r) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dV + 2 * k, dR + 2 * k, IDESC_KK64, 1);
+        }
+        mma_commit(bar_mma);
+    }
+    mbar_wait(bar_mma, 1);
+    tc_fence_after();
+    {   // dk rows
+        uint32_t r[32];
+        tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
+        tmem_ld_wait();
+        const float *rz = a.rzs + slot * 64 + 32 * g.half;
+        uint4 o[4];
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            float f[8], kf[8];
+            unpack8(make_uint4(kfr[4 * cc], kfr[4 * cc + 1], kfr[4 * cc + 2], kfr[4 * cc + 3]), kf);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const float rr = have_r ? __ldg(rz + 8 * cc + i) : 0.f;
+                f[i] = (__uint_as_float(r[8 * cc + i]) + rr) * (kf[i] <= 1.f ? kf[i] : 1.f);
+            }
+            o[cc] = pack8(f);
+        }
+        store_row32(a.gk, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if ((tid >> 5) == 0) tmem_dealloc<256>(tmem);
+}
+
+int set_smem_once(const void *fn, uint32_t bytes, bool *done, const char *what) {
+    if (*done) return CPM_OK;
+    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "%s smem attribute: %s", what, cudaGetErrorString(e));
+    *done = true;
+    return CPM_OK;
+}
+
+}  // namespace
+
+// ---------------------------------------------------------------- host side
+// workspace: [increments fp32 NHC x 4160][Sp region][Rs region][gd fp32 N*L*H]
+int64_t linattn_cp_workspace_bytes(int N, int L, int H) {
+    if (L % CHUNK != 0) return 0;
+    const int64_t nhc = (int64_t)N * H * (L / CHUNK);
+    return nhc * STATE_FLOATS * 4 + 2 * state_region_bytes(nhc) + (int64_t)N * L * H * 4;
+}
+int64_t linattn_cp_saved_bytes(int N, int L, int H) {
+    if (L % CHUNK != 0) return 0;
+    return state_region_bytes((int64_t)N * H * (L / CHUNK));
+}
+
+namespace {
+// F1 + F2 into a state region (tiles | z)
+int prefix_states(const void *k, const void *v, int N, int L, int H, int64_t ld_qkv, float *part, uint8_t *region, cudaStream_t st) {
+    const int nchunks = L / CHUNK;
+    if (nchunks <= 1) return CPM_OK;
+    const int64_t nhc = (int64_t)N * H * nchunks;
+    CUtensorMap tk, tv;
+    int rc;
+    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
+    if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
+    float *zs = reinterpret_cast<float *>(region + state_tiles_bytes(nhc));
+    if (N * H >= 96) {                                  // enough independent (batch, head) chains: stream, no scan
+        static bool as = false;
+        if ((rc = set_smem_once((const void *)cp_prefix_stream_fwd_kernel, ST_SMEM, &as, "cp_prefix_stream_fwd"))) return rc;
+        cp_prefix_stream_fwd_kernel<<<N * H, 128, ST_SMEM, st>>>(tk, tv, region, zs, L, H, nchunks);
+        return check_launch("linattn_cp prefix stream");
+    }
+    static bool a1 = false;
+    if ((rc = set_smem_once((const void *)cp_state_fwd_kernel, PF_SMEM, &a1, "cp_state_fwd"))) return rc;
+    cp_state_fwd_kernel<<<N * H * (nchunks - 1), 128, PF_SMEM, st>>>(tk, tv, part, L, H, nchunks);
+    cp_scan_kernel<<<dim3(N * H, (STATE_FLOATS / 4 + 255) / 256), 256, 0, st>>>(part, region, reinterpret_cast<float *>(region + state_tiles_bytes(nhc)),
+                                                                                nchunks, 0);
+    return check_launch("linattn_cp prefix states");
+}
+}  // namespace
+
+int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int64_t ld_qkv,
+                          int64_t ld_o, float eps, void *ws, void *saved, cudaStream_t st) {
+    if (L % CHUNK != 0) return CPM_ERR_UNSUPPORTED;
+    const int nchunks = L / CHUNK;
+    const int64_t nhc = (int64_t)N * H * nchunks;
+    if (nhc * 64 > 0x7fffffffLL) return CPM_ERR_UNSUPPORTED;
+    float *part = reinterpret_cast<float *>(ws);
+    uint8_t *region = saved ? reinterpret_cast<uint8_t *>(saved) : reinterpret_cast<uint8_t *>(ws) + nhc * STATE_FLOATS * 4;
+    int rc;
+    if ((rc = prefix_states(k, v, N, L, H, ld_qkv, part, region, st))) return rc;
+    CUtensorMap tq, tk, tv, ts;
+    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
+    if ((rc = make_tmap_bf16_2d(&tq, q, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&ts, region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
+    static bool a3 = false;
+    if ((rc = set_smem_once((const void *)cp_out_fwd_kernel, F_SMEM, &a3, "cp_out_fwd"))) return rc;
+    const int64_t slots = 3ll * num_sms();
+    cp_out_fwd_kernel<<<(unsigned)(nhc < slots ? nhc : slots), NTH, F_SMEM, st>>>(
+        tq, tk, tv, ts, reinterpret_cast<const float *>(region + state_tiles_bytes(nhc)), out, den, L, H, nchunks, N * H, ld_o, eps);
+    return check_launch("linattn_fwd_cp");
+}
+
+int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout,
+                          void *gq, void *gk, void *gv, int N, int L, int H, int64_t ld_qkv, int64_t ld_o, int64_t ld_g,
+                          void *ws, const void *saved, cudaStream_t st) {
+    if (L % CHUNK != 0) return CPM_ERR_UNSUPPORTED;
+    const int nchunks = L / CHUNK;
+    const int64_t nhc = (int64_t)N * H * nchunks;
+    if (nhc * 64 > 0x7fffffffLL) return CPM_ERR_UNSUPPORTED;
+    uint8_t *w8 = reinterpret_cast<uint8_t *>(ws);
+    float *part = reinterpret_cast<float *>(w8);
+    uint8_t *sp_region = w8 + nhc * STATE_FLOATS * 4;
+    uint8_t *rs_region = sp_region + state_region_bytes(nhc);
+    float *gd = reinterpret_cast<float *>(rs_region + state_region_bytes(nhc));
+    int rc;
+    if (!saved) {                                       // forward did not keep its prefix states: rebuild them
+        if ((rc = prefix_states(k, v, N, L, H, ld_qkv, part, sp_region, st))) return rc;
+    } else {
+        sp_region = const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(saved));
+    }
+    CUtensorMap tq, tk, tv, tgo, to, ts, tr;
+    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
+    if ((rc = make_tmap_bf16_2d(&tq, q, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tgo, gout, inner, rows, ld_o, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&to, out, inner, rows, ld_o, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&ts, sp_region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tr, rs_region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
+    static bool a1 = false, a3 = false;
+    if ((rc = set_smem_once((const void *)cp_state_bwd_kernel, PB_SMEM, &a1, "cp_state_bwd"))) return rc;
+    if ((rc = set_smem_once((const void *)cp_bwd_main_kernel, B_SMEM, &a3, "cp_bwd_main"))) return rc;
+    cp_state_bwd_kernel<<<(unsigned)nhc, 128, PB_SMEM, st>>>(tq, tgo, to, den, gd, part, L, H, nchunks);
+    if (nchunks > 1)
+        cp_scan_kernel<<<dim3(N * H, (STATE_FLOATS / 4 + 255) / 256), 256, 0, st>>>(part, rs_region,
+                                                                                    reinterpret_cast<float *>(rs_region + state_tiles_bytes(nhc)), nchunks, 1);
+    BwdMainArgs a;
+    a.den = den; a.gd = gd;
+    a.zp = reinterpret_cast<const float *>(sp_region + state_tiles_bytes(nhc));
+    a.rzs = reinterpret_cast<const float *>(rs_region + state_tiles_bytes(nhc));
+    a.gq = gq; a.gk = gk; a.gv = gv; a.ld_g = ld_g; a.L = L; a.H = H; a.nchunks = nchunks;
+    cp_bwd_main_kernel<<<(unsigned)nhc, NTH, B_SMEM, st>>>(tq, tk, tv, tgo, ts, tr, a);
+    return check_launch("linattn_bwd_cp");
+}
+
+}  // namespace cpm

@@ -117,10 +117,6 @@ def linattn_workspace(N: int, L: int, H: int, device) -> torch.Tensor:
     return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
 
 
-def linattn_nseg(N: int, L: int, H: int) -> int:
-    return int(_lib.load().cpm_linattn_workspace_bytes(N, L, H) // (2 * N * H * (64 * 64 + 64) * 4))
-
-
 def _check_qkv_layout(q, k, v):
     N, L, H, E = q.shape
     for t in (q, k, v):
@@ -131,31 +127,36 @@ def _check_qkv_layout(q, k, v):
     return N, L, H, E, q.stride(1)
 
 
-def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True):
-    """q,k,v: (N,L,H,64) views (may be column slices of one fused QKV buffer)."""
+def linattn_saved(N: int, L: int, H: int, device) -> Optional[torch.Tensor]:
+    """Buffer for the chunk-parallel kernels' per-chunk prefix states (kept from fwd to bwd)."""
+    nbytes = _lib.load().cpm_linattn_saved_bytes(N, L, H)
+    return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
+
+
+def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True, saved=None):
+    """q,k,v: (N,L,H,64) views (may be column slices of one fused QKV buffer).  `saved`: optional
+    buffer from linattn_saved() that receives the prefix states for linattn_bwd_raw."""
     _cuda(q, k, v)
     N, L, H, E, ld = _check_qkv_layout(q, k, v)
     out = torch.empty(N, L, H, E, dtype=q.dtype, device=q.device)
     den = torch.empty(N, L, H, dtype=torch.float32, device=q.device) if need_den else None
     ws = linattn_workspace(N, L, H, q.device)
-    if linattn_nseg(N, L, H) > 1:
-        _lib.EXTRA_LAUNCHES[0] += 2
     with KernelTimer.span("linattn_fwd"):
         check(_lib.load().cpm_linattn_fwd(_p(q), _p(k), _p(v), _p(out), _p(den), N, L, H, E, E, ld, H * E,
-                                          _dt(q), eps, impl, _p(ws), ws.numel(), _st()))
+                                          _dt(q), eps, impl, _p(ws), ws.numel(), _p(saved),
+                                          0 if saved is None else saved.numel(), _st()))
     return out, den
 
 
-def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0):
+def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0, saved=None):
     N, L, H, E, ld = _check_qkv_layout(q, k, v)
     _, _, _, _, ldg = _check_qkv_layout(gq, gk, gv)
     gout = gout.contiguous()
     ws = linattn_workspace(N, L, H, q.device)
-    if linattn_nseg(N, L, H) > 1:
-        _lib.EXTRA_LAUNCHES[0] += 4
     with KernelTimer.span("linattn_bwd"):
         check(_lib.load().cpm_linattn_bwd(_p(q), _p(k), _p(v), _p(out), _p(den), _p(gout), _p(gq), _p(gk), _p(gv),
-                                          N, L, H, E, E, ld, H * E, ldg, _dt(q), eps, impl, _p(ws), ws.numel(), _st()))
+                                          N, L, H, E, E, ld, H * E, ldg, _dt(q), eps, impl, _p(ws), ws.numel(),
+                                          _p(saved), 0 if saved is None else saved.numel(), _st()))
 
 
 class _LinAttnFused(torch.autograd.Function):
@@ -167,20 +168,22 @@ class _LinAttnFused(torch.autograd.Function):
         E = W // (3 * H)
         qkv = qkv.contiguous()
         q, k, v = (qkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
-        out, den = linattn_fwd_raw(q, k, v, eps, impl)
-        ctx.save_for_backward(qkv, out, den)
+        need = ctx.needs_input_grad[0]
+        saved = linattn_saved(N, L, H, qkv.device) if (need and impl in (0, 3) and qkv.dtype == torch.bfloat16) else None
+        out, den = linattn_fwd_raw(q, k, v, eps, impl, saved=saved)
+        ctx.save_for_backward(qkv, out, den, saved)
         ctx.cfg = (H, E, eps, impl)
         return out.view(N, L, H * E)
 
     @staticmethod
     def backward(ctx, gout):
-        qkv, out, den = ctx.saved_tensors
+        qkv, out, den, saved = ctx.saved_tensors
         H, E, eps, impl = ctx.cfg
         N, L, W = qkv.shape
         q, k, v = (qkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
         gqkv = torch.empty_like(qkv)
         gq, gk, gv = (gqkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
-        linattn_bwd_raw(q, k, v, out, den, gout.reshape(N, L, H, E), gq, gk, gv, eps, impl)
+        linattn_bwd_raw(q, k, v, out, den, gout.reshape(N, L, H, E), gq, gk, gv, eps, impl, saved=saved)
         return gqkv, None, None, None
 
 

@@ -439,17 +439,18 @@ def test_dqn_td_replay_batch_1024(cuda, cpm):
 
 
 # ------------------------------------------------------------------ tcgen05 / TMA path
+@pytest.mark.parametrize("impl", [2, 3])
 @pytest.mark.parametrize("shape", [(1, 128, 1), (2, 256, 4), (3, 384, 2), (1, 2048, 2), (32, 512, 8)])
-def test_linattn_tc_fwd(cuda, cpm, shape):
-    """tcgen05 forward (impl=2, bf16) vs the fp64 oracle on the same bf16-rounded inputs and vs the
+def test_linattn_tc_fwd(cuda, cpm, shape, impl):
+    """tcgen05 forward (impl=2 sequential chunks, impl=3 chunk-parallel; bf16) vs the fp64 oracle on the same bf16-rounded inputs and vs the
     SIMT kernel.  The tensor-core path rounds P (intra-chunk scores) and the carried state to bf16
     before the second MMA, so its tolerance is a little wider than the fp32-math SIMT path:
     3e-2 absolute on O(1) outputs; the normaliser `den` within 1e-2 relative."""
     N, L, H = shape
     gen = torch.Generator().manual_seed(L + H)
     q, k, v = (torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16() for _ in range(3))
-    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=2)
-    assert cpm.ops.linattn_last_impl() == "tcgen05"
+    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=impl)
+    assert cpm.ops.linattn_last_impl() == ("tcgen05" if impl == 2 else "tcgen05-cp")
     torch.cuda.synchronize()
     ref_simt, den_simt = cpm.ops.linattn_fwd_raw(q, k, v, impl=1)
     _cmp(out, ref_simt.float(), 3e-2, 2e-2, "tc vs simt")
@@ -473,19 +474,27 @@ def test_linattn_tc_fwd_fused_layout_and_autograd(cuda, cpm):
     _cmp(qkv.grad, torch.cat([t.reshape(N, L, H * 64) for t in (rq, rk, rv)], -1), 5e-2, 3e-2, "gqkv")
 
 
+@pytest.mark.parametrize("impl", [2, 3])
 @pytest.mark.parametrize("shape", [(1, 128, 1), (2, 256, 4), (3, 384, 2), (1, 2048, 2), (32, 512, 8)])
-def test_linattn_tc_bwd(cuda, cpm, shape):
-    """tcgen05 backward (impl=2) vs the fp64 oracle (small shapes) and vs the SIMT backward fed the
+def test_linattn_tc_bwd(cuda, cpm, shape, impl):
+    """tcgen05 backward (impl=2 sequential chunks; impl=3 chunk-parallel, once rebuilding the prefix
+    states and once reading the ones the forward saved) vs the fp64 oracle (small shapes) and vs the SIMT backward fed the
     same saved out/den.  Tolerance: gradients are O(0.1-1); 4e-2 absolute + 3e-2 relative (bf16
     rounding of G', of the masked score tiles and of the carried state)."""
     N, L, H = shape
     gen = torch.Generator().manual_seed(L * 3 + H)
     q, k, v, go = (torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16() for _ in range(4))
-    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=2)
+    saved = cpm.ops.linattn_saved(N, L, H, cuda) if impl == 3 else None
+    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=impl, saved=saved)
     gq, gk, gv = (torch.empty_like(q) for _ in range(3))
-    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=2)
-    assert cpm.ops.linattn_last_impl() == "tcgen05"
+    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=impl)
+    assert cpm.ops.linattn_last_impl() == ("tcgen05" if impl == 2 else "tcgen05-cp")
     torch.cuda.synchronize()
+    if impl == 3:          # same result when backward reads the forward's saved prefix states
+        tq, tk, tv = (torch.empty_like(q) for _ in range(3))
+        cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, tq, tk, tv, impl=3, saved=saved)
+        for a, b in ((gq, tq), (gk, tk), (gv, tv)):
+            assert torch.equal(a, b)
     sq, sk, sv = (torch.empty_like(q) for _ in range(3))
     cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, sq, sk, sv, impl=1)
     for name, a, b in (("gq", gq, sq), ("gk", gk, sk), ("gv", gv, sv)):

@@ -29,24 +29,27 @@ def test_library_exports_every_declared_symbol(cpm):
         assert name in cpm._lib.SIGNATURES, f"{name} has no ctypes signature"
     assert lib.cpm_version() == 100
     assert lib.cpm_error_name(-1) == b"CPM_ERR_BAD_SHAPE"
-    assert lib.cpm_linattn_workspace_bytes(32, 512, 8) == 2 * 32 * 8 * 1 * (64 * 64 + 64) * 4
-    assert lib.cpm_linattn_workspace_bytes(1, 8192, 16) == 2 * 16 * 16 * (64 * 64 + 64) * 4      # 16 segments of 512
+    nhc = 32 * 8 * 4                                    # chunk-parallel path: increments + 2 state regions + gd
+    assert lib.cpm_linattn_workspace_bytes(32, 512, 8) == nhc * 4160 * 4 + 2 * nhc * (8192 + 256) + 32 * 512 * 8 * 4
+    assert lib.cpm_linattn_saved_bytes(32, 512, 8) == nhc * (8192 + 256)
+    assert lib.cpm_linattn_workspace_bytes(4, 100, 8) == 2 * 4 * 8 * 1 * (64 * 64 + 64) * 4   # L%128 != 0: segment states only
+    assert lib.cpm_linattn_workspace_bytes(1, 8192 + 64, 16) == 2 * 16 * 17 * (64 * 64 + 64) * 4   # SIMT path: 17 segments of 512
     assert lib.cpm_ln_partials_rows() == 296
 
 
 def test_argument_validation_without_gpu(cpm):
     """Validation happens before any CUDA call, so error codes are testable on CPU."""
     lib = cpm._lib.load()
-    rc = lib.cpm_linattn_fwd(None, None, None, None, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 0, None, 0, None)
+    rc = lib.cpm_linattn_fwd(None, None, None, None, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 0, None, 0, None, 0, None)
     assert rc == -4 and b"non-NULL" in lib.cpm_last_error_string()
     buf = ctypes.create_string_buffer(1 << 16)
     p = ctypes.addressof(buf)
     p += (-p) % 16
-    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 64, 1, 32, 32, 64, 64, 0, 1e-6, 0, None, 0, None)
+    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 64, 1, 32, 32, 64, 64, 0, 1e-6, 0, None, 0, None, 0, None)
     assert rc == -1 and b"E=M=64" in lib.cpm_last_error_string()
-    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 2, p, 1 << 20, None)
+    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 2, p, 1 << 20, None, 0, None)
     assert rc == -7                                                   # tcgen05 path refuses fp32
-    rc = lib.cpm_linattn_fwd(p + 2, p, p, p, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 0, p, 1 << 20, None)
+    rc = lib.cpm_linattn_fwd(p + 2, p, p, p, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 0, p, 1 << 20, None, 0, None)
     assert rc == -2
     with pytest.raises(ValueError):
         cpm._lib.check(-1)
@@ -129,7 +132,13 @@ def test_segment_plan_matches_header_contract(cpm):
     per = (64 * 64 + 64) * 4 * 2
     for N, L, H in ((4, 512, 8), (32, 512, 8), (1, 8192, 16), (1, 8192, 8), (2, 100, 1), (1, 50, 8)):
         b = lib.cpm_linattn_workspace_bytes(N, L, H)
-        assert b % (per * N * H) == 0 and b >= per * N * H
+        assert b >= per * N * H
+        if L % 128:                              # SIMT-only shapes: whole segments
+            assert b % (per * N * H) == 0
+        else:                                    # chunk-parallel tcgen05 path: increments + 2 state regions + gd
+            nhc = N * H * (L // 128)
+            assert b >= nhc * 4160 * 4 + 2 * nhc * 8448 + N * L * H * 4
+            assert lib.cpm_linattn_saved_bytes(N, L, H) == nhc * 8448
 
 
 def test_shard_range(cpm):

@@ -32,20 +32,25 @@ def main():
         gq, gk, gv = (gqkv[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
         for impl in args.impl:
             for direction in args.dirs:
-                out, den = cpmusic.ops.linattn_fwd_raw(q, k, v, impl=impl)
-                def run():
+                saved = cpmusic.ops.linattn_saved(N, L, H, dev) if impl in (0, 3) else None
+                out, den = cpmusic.ops.linattn_fwd_raw(q, k, v, impl=impl, saved=saved)
+                def run_eager():
                     if direction == "fwd":
-                        cpmusic.ops.linattn_fwd_raw(q, k, v, impl=impl)
+                        cpmusic.ops.linattn_fwd_raw(q, k, v, impl=impl, saved=saved)
                     else:
-                        cpmusic.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=impl)
+                        cpmusic.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=impl, saved=saved)
                 try:
                     for _ in range(3):
-                        run()
+                        run_eager()
                 except Exception as e:
                     print(json.dumps({"shape": name, "impl": impl, "dir": direction, "error": str(e)[:100]}))
                     continue
                 used = cpmusic.ops.linattn_last_impl()
                 torch.cuda.synchronize()
+                graph = torch.cuda.CUDAGraph()          # GPU time only: no Python / tensor-map-encode gaps between launches
+                with torch.cuda.graph(graph):
+                    run_eager()
+                run = graph.replay
                 tot = 0.0
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 for _ in range(args.iters):
