@@ -21,43 +21,63 @@ namespace {
 // coalesced: a warp covers 8 consecutive rows = 2 KB).  out_m = sum_e Qf_e S_em / (Qf.Z + eps)
 // is reduced with warp shuffles (over the 8 rows of a warp) and one shared-memory pass.
 // ------------------------------------------------------------------------------------------
+// streaming access to the recurrent state: it is touched exactly once per token step and is far larger than
+// L2 at rollout batch sizes (256 sequences x 12 layers x 128 KB), so keep it from evicting the weights.
+struct F8 { float4 a, b; };
+__device__ __forceinline__ F8 ld_stream(const float *p) {          // 256-bit load, 32-byte aligned
+    F8 v;
+    asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                 : "=f"(v.a.x), "=f"(v.a.y), "=f"(v.a.z), "=f"(v.a.w), "=f"(v.b.x), "=f"(v.b.y), "=f"(v.b.z), "=f"(v.b.w) : "l"(p));
+    return v;
+}
+__device__ __forceinline__ void st_stream(float *p, const F8 &v) {
+    asm volatile("st.global.L1::no_allocate.L2::evict_first.v8.f32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(p), "f"(v.a.x), "f"(v.a.y),
+                 "f"(v.a.z), "f"(v.a.w), "f"(v.b.x), "f"(v.b.y), "f"(v.b.z), "f"(v.b.w)
+                 : "memory");
+}
+
 template <typename T>
 __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__ q, const T *__restrict__ k,
                                                            const T *__restrict__ v, float *__restrict__ S,
                                                            float *__restrict__ Z, T *__restrict__ out, int H,
                                                            int64_t ld_qkv, int64_t ld_o, float eps) {
-    __shared__ float sq[64], sk[64], sv[64];
-    __shared__ float part[8][64];
-    __shared__ float sden;
+    __shared__ float part[8][68];                      // per warp: 64 output partials + the normaliser partial
     const int nh = blockIdx.x, n = nh / H, h = nh % H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int64_t qoff = (int64_t)n * ld_qkv + h * 64;
-    if (tid < 64) sq[tid] = phi(to_f(q[qoff + tid]));
-    else if (tid < 128) sk[tid - 64] = phi(to_f(k[qoff + tid - 64]));
-    else if (tid < 192) sv[tid - 128] = to_f(v[qoff + tid - 128]);
-    __syncthreads();
-    if (warp == 7) {   // normaliser: Z += Kf ; den = Qf.Z + eps   (2 elements per lane)
-        float *z = Z + (int64_t)nh * 64;
-        float z0 = z[lane] + sk[lane], z1 = z[lane + 32] + sk[lane + 32];
-        z[lane] = z0; z[lane + 32] = z1;
-        float d = warp_sum(sq[lane] * z0 + sq[lane + 32] * z1);
-        if (lane == 0) sden = d + eps;
-    }
     const int e = tid >> 2, m0 = (tid & 3) * 16;
-    float4 *srow = reinterpret_cast<float4 *>(S + (int64_t)nh * 4096 + e * 64 + m0);
+    // the 16 KB state tile first: its latency overlaps the q/k/v loads below (nothing here depends on them)
+    float *srow = S + (int64_t)nh * 4096 + e * 64 + m0;
     float4 s[4];
+    {
+        const F8 lo = ld_stream(srow), hi = ld_stream(srow + 8);
+        s[0] = lo.a; s[1] = lo.b; s[2] = hi.a; s[3] = hi.b;
+    }
+    const int64_t qoff = (int64_t)n * ld_qkv + h * 64;
+    const float ke = phi(to_f(k[qoff + e])), qe = phi(to_f(q[qoff + e]));
+    float vv[16];
+    {
+        Vec8<T> v0, v1;
+        v0.load(v + qoff + m0);
+        v1.load(v + qoff + m0 + 8);
 #pragma unroll
-    for (int i = 0; i < 4; ++i) s[i] = srow[i];
-    const float ke = sk[e], qe = sq[e];
+        for (int i = 0; i < 8; ++i) { vv[i] = v0.v[i]; vv[8 + i] = v1.v[i]; }
+    }
+    float dpart = 0.f;
+    if ((tid & 3) == 0) {                              // normaliser: Z += Kf ; den = Qf.Z + eps
+        float *z = Z + (int64_t)nh * 64 + e;
+        const float zn = *z + ke;
+        *z = zn;
+        dpart = qe * zn;
+    }
     float acc[16];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
-        s[i].x = fmaf(ke, sv[m0 + 4 * i + 0], s[i].x); s[i].y = fmaf(ke, sv[m0 + 4 * i + 1], s[i].y);
-        s[i].z = fmaf(ke, sv[m0 + 4 * i + 2], s[i].z); s[i].w = fmaf(ke, sv[m0 + 4 * i + 3], s[i].w);
-        srow[i] = s[i];
+        s[i].x = fmaf(ke, vv[4 * i + 0], s[i].x); s[i].y = fmaf(ke, vv[4 * i + 1], s[i].y);
+        s[i].z = fmaf(ke, vv[4 * i + 2], s[i].z); s[i].w = fmaf(ke, vv[4 * i + 3], s[i].w);
         acc[4 * i + 0] = qe * s[i].x; acc[4 * i + 1] = qe * s[i].y;
         acc[4 * i + 2] = qe * s[i].z; acc[4 * i + 3] = qe * s[i].w;
     }
+    { F8 lo, hi; lo.a = s[0]; lo.b = s[1]; hi.a = s[2]; hi.b = s[3]; st_stream(srow, lo); st_stream(srow + 8, hi); }
     // reduce over the 8 rows held by this warp (lanes with equal lane%4)
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -65,16 +85,20 @@ __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__
         acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
         acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
     }
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 4);
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 8);
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 16);
     if (lane < 4) {
 #pragma unroll
         for (int i = 0; i < 16; ++i) part[warp][lane * 16 + i] = acc[i];
+        if (lane == 0) part[warp][64] = dpart;
     }
     __syncthreads();
     if (tid < 64) {
-        float o = 0.f;
+        float o = 0.f, d = eps;
 #pragma unroll
-        for (int w = 0; w < 8; ++w) o += part[w][tid];
-        out[(int64_t)n * ld_o + h * 64 + tid] = from_f<T>(o / sden);
+        for (int w = 0; w < 8; ++w) { o += part[w][tid]; d += part[w][64]; }
+        out[(int64_t)n * ld_o + h * 64 + tid] = from_f<T>(o / d);
     }
 }
 }  // namespace

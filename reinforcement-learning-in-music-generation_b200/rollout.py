@@ -277,3 +277,75 @@ class RolloutEngine:
         self.model.train(was_training)
         toks = torch.cat([init_tokens.to(self.cur.device, torch.int64)[None], self.hist_tok[:n_steps]], 0)
         return {"tokens": toks.permute(1, 0, 2).contiguous(), "logp": self.hist_logp[:n_steps].permute(1, 0, 2).contiguous()}
+
+
+class GroupedRolloutEngine:
+    """The same rollout with the batch cut into ``groups`` independent sub-batches whose token steps are
+    captured as parallel branches of ONE CUDA graph (fork / join over side streams).  A token step is a
+    chain of ~100 small dependent kernels, so a single chain is launch-latency bound; with several chains
+    in flight the latency-bound kernels of one group overlap the bandwidth-bound state updates of the
+    others.  Sampling streams are keyed by the global sequence id, so the generated tokens are identical
+    to the ungrouped engine's for any ``groups`` (tests/test_gpu_model.py pins this)."""
+
+    def __init__(self, model, batch: int, max_steps: int, groups: int = 4, steps_per_graph: int = 1, seq_base: int = 0, **kw):
+        if batch % groups != 0:
+            raise ValueError(f"batch {batch} is not divisible into {groups} groups")
+        self.model, self.N, self.max_steps, self.groups = model, batch, max_steps, groups
+        self.per = batch // groups
+        self.steps_per_graph = max(1, int(steps_per_graph))
+        self.engines = [RolloutEngine(model, self.per, max_steps, seq_base=seq_base + g * self.per, use_graph=False, **kw)
+                        for g in range(groups)]
+        self.streams = None
+        self.graph: Optional[torch.cuda.CUDAGraph] = None
+        self.launches_per_step = None
+
+    def _fork_join_steps(self, n):
+        main = torch.cuda.current_stream()
+        for eng, st in zip(self.engines, self.streams):
+            st.wait_stream(main)
+            with torch.cuda.stream(st):
+                for _ in range(n):
+                    eng._step()
+        for st in self.streams:
+            main.wait_stream(st)
+
+    def _capture(self):
+        was_training = self.model.training
+        self.model.eval()
+        self.streams = [torch.cuda.Stream() for _ in self.engines]
+        with torch.no_grad():
+            for _ in range(2):                      # warm-up: cuBLAS handles / workspaces per stream, weight packs
+                self._fork_join_steps(1)
+        torch.cuda.synchronize()
+        g = torch.cuda.CUDAGraph()
+        before = _lib.kernel_launches()
+        with torch.no_grad(), torch.cuda.graph(g):
+            self._fork_join_steps(self.steps_per_graph)
+        self.launches_per_step = (_lib.kernel_launches() - before) // self.steps_per_graph
+        self.graph = g
+        self.model.train(was_training)
+
+    @torch.no_grad()
+    def generate(self, init_tokens, n_steps: Optional[int] = None):
+        n_steps = self.max_steps if n_steps is None else n_steps
+        if n_steps > self.max_steps:
+            raise ValueError(f"n_steps {n_steps} > max_steps {self.max_steps}")
+        was_training = self.model.training
+        self.model.eval()
+        if self.graph is None:
+            self._capture()
+        init_tokens = init_tokens.to(self.engines[0].cur.device, torch.int64)
+        for g, eng in enumerate(self.engines):
+            eng.reset(init_tokens[g * self.per:(g + 1) * self.per])
+        self.model.refresh_packs()
+        full, rest = divmod(n_steps, self.steps_per_graph)
+        for _ in range(full):
+            self.graph.replay()
+        if rest:                                    # tail shorter than one captured block: eager fork / join
+            self._fork_join_steps(rest)
+        _lib.EXTRA_LAUNCHES[0] += full * self.steps_per_graph * self.launches_per_step
+        self.model.train(was_training)
+        hist_tok = torch.cat([e.hist_tok[:n_steps] for e in self.engines], 1)
+        hist_logp = torch.cat([e.hist_logp[:n_steps] for e in self.engines], 1)
+        toks = torch.cat([init_tokens[None], hist_tok], 0)
+        return {"tokens": toks.permute(1, 0, 2).contiguous(), "logp": hist_logp.permute(1, 0, 2).contiguous()}
