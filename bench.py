@@ -10,7 +10,7 @@ followed by a GAE plus clipped-loss update"; it fits one GPU, so it is the per-G
 run N such shards — weak scaling): autoregressive RECURRENT rollout of 256 songs x 1024 compound-word
 tokens with the reference's per-attribute temperature / nucleus sampling, critic values, GAE(lambda)
 with globally normalised advantages, then one clipped-PPO update of the 12-layer / d512 / 8-head actor
-and critic over those 256x1024 tokens (16 minibatches of 16x1024 with gradient accumulation, dropout
+and critic over those 256x1024 tokens (4 minibatches of 64x1024 with gradient accumulation, dropout
 0.1, grad-clip 3, Adam, bucketed NCCL gradient all-reduce).  Synthetic data: random-init
 weights, random initial tokens, and a synthetic reward (the reference's Longformer reward model is
 out of scope).  One "step" = one such iteration; value = tokens generated and trained
@@ -32,7 +32,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 VOCAB = [56, 135, 18, 87, 18, 25]            # AIlabs-Pop1K7 dictionary without 'type' (IRL_dqn_train.py:403)
-SONGS_PER_GPU, ROLLOUT_LEN, MINIBATCH = 256, 1024, 16
+SONGS_PER_GPU, ROLLOUT_LEN = 256, 1024
+MINIBATCH = int(os.environ.get("CPM_MINIBATCH", "64"))          # sequences per update minibatch (gradient accumulation over 256/MINIBATCH)
 METRIC = "CP tokens/s, PPO rollout+update"
 UNIT = "tokens/s"
 
@@ -197,7 +198,7 @@ class PPOIteration:
         self.opt_c = torch.optim.Adam(self.critic.parameters(), lr=lr, fused=True)
         self.red_a = cpmusic.dist.BucketedGradAllReduce(self.actor.parameters(), 25.0)
         self.red_c = cpmusic.dist.BucketedGradAllReduce(self.critic.parameters(), 25.0)
-        groups = int(os.environ.get("CPM_ROLLOUT_GROUPS", "4"))
+        groups = int(os.environ.get("CPM_ROLLOUT_GROUPS", "1"))
         if groups > 1:      # parallel graph branches: latency-bound kernels of one group overlap the others' state updates
             self.engine = cpmusic.GroupedRolloutEngine(self.actor, SONGS_PER_GPU, ROLLOUT_LEN, groups=groups,
                                                        steps_per_graph=int(os.environ.get("CPM_ROLLOUT_SPG", "4")), greedy=False,
