@@ -36,6 +36,7 @@ SIGNATURES = {
     "cpm_linattn_last_impl": (c_char_p, []),
     "cpm_linattn_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "cpm_linattn_saved_bytes": (c_int64, [c_int, c_int, c_int]),
+    "cpm_debug_linattn_timing": (c_int, [_P]),
     "cpm_linattn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
                                 c_int, c_float, c_int, _P, c_int64, _P, c_int64, _P]),
     "cpm_linattn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
@@ -81,7 +82,7 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
+    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_debug_linattn_timing": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
     "cpm_linattn_fwd": 3, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2,      # chunk-parallel path: pre-pass, scan, main
 })
 EXTRA_LAUNCHES = [0]          # segment-total / scan kernels of segmented linear attention, graph replays

@@ -132,6 +132,10 @@ int64_t cpm_linattn_workspace_bytes(int N, int L, int H) {
     const int64_t seg = 2ll * N * H * nseg * STATE_FLOATS * (int64_t)sizeof(float), cp = linattn_cp_workspace_bytes(N, L, H);
     return seg > cp ? seg : cp;
 }
+int cpm_debug_linattn_timing(void *buf) {
+    linattn_cp_set_timing_buffer(reinterpret_cast<long long *>(buf));
+    return CPM_OK;
+}
 int64_t cpm_linattn_saved_bytes(int N, int L, int H) {
     if (N <= 0 || L <= 0 || H <= 0) return 0;
     return linattn_cp_saved_bytes(N, L, H);

@@ -68,6 +68,90 @@ __device__ __forceinline__ float colsum_half(const uint8_t *tile, int e, int hal
     return s;
 }
 
+// ---------------------------------------------------------------- lean elementwise helpers
+// These kernels are instruction-issue bound, not tensor- or HBM-bound (ncu: ~15 k warp instructions per
+// 128-token tile before this diet), so the per-element code is kept to the minimum: bit-twiddled bf16
+// unpack, branch-free feature map, row sums and normalisers pushed onto the tensor core (ones-column UMMA).
+__device__ __forceinline__ float ex2_approx(float x) {
+    float y;
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+// elu(x)+1 = max(x,0) + exp(min(x,0)) on two packed bf16, rounded back to bf16
+__device__ __forceinline__ uint32_t phi2(uint32_t u) {
+    const float a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xffff0000u);
+    const float ya = fmaxf(a, 0.f) + ex2_approx(fminf(a * 1.4426950408889634f, 0.f));
+    const float yb = fmaxf(b, 0.f) + ex2_approx(fminf(b * 1.4426950408889634f, 0.f));
+    return pack_bf16(ya, yb);
+}
+__device__ __forceinline__ uint4 phi8_lean(uint4 r) { return make_uint4(phi2(r.x), phi2(r.y), phi2(r.z), phi2(r.w)); }
+// same, also accumulating dot += phi(x) . z over the 8 elements (fp32 feature values, before rounding)
+__device__ __forceinline__ uint32_t phi2_dot(uint32_t u, float z0, float z1, float &dot) {
+    const float a = __uint_as_float(u << 16), b = __uint_as_float(u & 0xffff0000u);
+    const float ya = fmaxf(a, 0.f) + ex2_approx(fminf(a * 1.4426950408889634f, 0.f));
+    const float yb = fmaxf(b, 0.f) + ex2_approx(fminf(b * 1.4426950408889634f, 0.f));
+    dot = fmaf(ya, z0, fmaf(yb, z1, dot));
+    return pack_bf16(ya, yb);
+}
+__device__ __forceinline__ uint4 phi8_dot(uint4 r, const float *z, float &dot) {
+    const float4 z0 = *reinterpret_cast<const float4 *>(z), z1 = *reinterpret_cast<const float4 *>(z + 4);
+    return make_uint4(phi2_dot(r.x, z0.x, z0.y, dot), phi2_dot(r.y, z0.z, z0.w, dot), phi2_dot(r.z, z1.x, z1.y, dot),
+                      phi2_dot(r.w, z1.z, z1.w, dot));
+}
+__device__ __forceinline__ uint32_t scale2(uint32_t u, float s) {
+    return pack_bf16(__uint_as_float(u << 16) * s, __uint_as_float(u & 0xffff0000u) * s);
+}
+// phi'(x) from the bf16 feature value f = phi(x): f <= 1  <=>  x <= 0, where phi' = exp(x) = f; else 1
+__device__ __forceinline__ float dphi_from_f(float f) { return fminf(f, 1.f); }
+
+// TMEM [128 x 128] score tile -> (+row_add) (+col_add[c]) -> triangular mask -> bf16 -> sX block `half`.
+// LOWER keeps column c <= row, otherwise c >= row.  No row sums here (they come from a ones-column UMMA).
+template <bool LOWER, bool HAS_ROW, bool HAS_COL, bool ROWSUM = false>
+__device__ __forceinline__ float convert_lean(const Geo &g, uint32_t tm_col, uint8_t *sX, float row_add, const float *col_add) {
+    float rowsum = 0.f;                                      // fp32 sum of the kept entries (this thread's 64 columns)
+    const int wq = g.warp & 3;
+    const uint32_t keep = LOWER ? ((2u << g.lane) - 1u) : ~((1u << g.lane) - 1u);    // diagonal piece: bit i <=> column 32p+i kept
+#pragma unroll
+    for (int pp = 0; pp < 2; ++pp) {
+        const int p = 2 * g.half + pp;                      // 32-column piece (warp-uniform)
+        const bool live = LOWER ? (p <= wq) : (p >= wq);
+        uint8_t *dst = sX + g.half * TILE_BYTES;
+        if (!live) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(dst + sw128_off(g.row, pp * 4 + cc)) = make_uint4(0u, 0u, 0u, 0u);
+            continue;
+        }
+        uint32_t r[32];
+        tmem_ld32(g.t_lane + tm_col + 32 * p, r);
+        tmem_ld_wait();
+        if (HAS_ROW || HAS_COL) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float x = __uint_as_float(r[i]);
+                if (HAS_ROW) x += row_add;
+                if (HAS_COL) x += col_add[32 * p + i];
+                r[i] = __float_as_uint(x);
+            }
+        }
+        if (p == wq) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = (keep >> i) & 1u ? r[i] : 0u;
+        }
+        if (ROWSUM) {
+            float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) {
+                s0 += __uint_as_float(r[i]); s1 += __uint_as_float(r[i + 1]); s2 += __uint_as_float(r[i + 2]); s3 += __uint_as_float(r[i + 3]);
+            }
+            rowsum += (s0 + s1) + (s2 + s3);
+        }
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc)
+            *reinterpret_cast<uint4 *>(dst + sw128_off(g.row, pp * 4 + cc)) = pack8u(r + 8 * cc, 1.f);
+    }
+    return rowsum;
+}
+
 // =============================================================================================
 // F1: per-chunk state increments  dS = Kf^T V, dz = colsum Kf        (128 threads, 64 TMEM columns)
 // =============================================================================================
@@ -216,14 +300,17 @@ cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // =============================================================================================
 constexpr int ST_STAGES = 3;
 constexpr uint32_t ST_STAGE_BYTES = 2 * TILE_BYTES;
-constexpr uint32_t ST_OFF_MISC = ST_STAGES * ST_STAGE_BYTES, ST_SMEM = ST_OFF_MISC + 512 + 64;
+constexpr uint32_t ST_OFF_ONES = ST_STAGES * ST_STAGE_BYTES;                    // 2 KB of bf16 ones (layout-agnostic B operand)
+constexpr uint32_t ST_OFF_BAR = ST_OFF_ONES + 2048, ST_SMEM = ST_OFF_BAR + 64;
+constexpr uint32_t IDESC_Z8 = idesc_bf16(64, 8, true, true);                    // z[e] += sum_j Kf[j][e] * 1
+constexpr uint32_t TS_S = 0, TS_Z = 64;
 
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(NTH)
 cp_prefix_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                             uint8_t *__restrict__ tiles, float *__restrict__ zs, int L, int H, int nchunks) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    float *sdz = reinterpret_cast<float *>(sm + ST_OFF_MISC);                  // [2][64]
-    uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + ST_OFF_MISC + 512);  // [ST_STAGES]
+    uint32_t *sOnes = reinterpret_cast<uint32_t *>(sm + ST_OFF_ONES);
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + ST_OFF_BAR);        // [ST_STAGES]
     uint64_t *bar_mma = bar_full + ST_STAGES;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -241,64 +328,70 @@ cp_prefix_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
             tma_load_2d(sm + s * ST_STAGE_BYTES + TILE_BYTES, &tmV, bar_full + s, col0, row0 + s * CHUNK);
         }
     }
-    if (warp == 0) tmem_alloc<64>(tmem_slot);
+    if (warp == 0) tmem_alloc<128>(tmem_slot);
+    for (int i = tid; i < 512; i += NTH) sOnes[i] = 0x3F803F80u;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
-    const uint32_t t_lane = tmem + ((uint32_t)(warp * 32) << 16);
-    const int erow = 16 * warp + (lane & 15);
-    float zacc = 0.f;
+    const int row = ((warp & 3) << 5) + lane, half = warp >> 2;                 // phi: two threads per token row
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int erow = 16 * (warp & 3) + (lane & 15);                             // snapshot: M=64 accumulator rows
+    const uint64_t dOnes = smem_desc_sw128(smem_u32(sOnes));
+    auto phi_stage = [&](int c) {
+        uint8_t *sK = sm + (c % ST_STAGES) * ST_STAGE_BYTES;
+        mbar_wait(bar_full + (c % ST_STAGES), (c / ST_STAGES) & 1);
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t off = sw128_off(row, 4 * half + cc);
+            *reinterpret_cast<uint4 *>(sK + off) = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
+        }
+    };
+    if (nwork > 0) phi_stage(0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
     for (int c = 0; c < nwork; ++c) {
         const int s = c % ST_STAGES;
-        uint8_t *sK = sm + s * ST_STAGE_BYTES, *sV = sK + TILE_BYTES;
-        mbar_wait(bar_full + s, (c / ST_STAGES) & 1);
-#pragma unroll
-        for (int ch = 0; ch < 8; ++ch) {
-            const uint32_t off = sw128_off(tid, ch);
-            float f[8];
-            *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
-        }
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        if (tid == 0) {
+        if (tid == 0) {                                   // S += Kf^T V ; z += Kf^T 1   (accumulated in TMEM across chunks)
             tc_fence_after();
-            const uint64_t dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
+            const uint64_t dK = smem_desc_sw128(smem_u32(sm + s * ST_STAGE_BYTES)), dV = smem_desc_sw128(smem_u32(sm + s * ST_STAGE_BYTES + TILE_BYTES));
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mma_ss(tmem, dK + 128 * k, dV + 128 * k, IDESC_MM64, (c > 0 || k > 0) ? 1u : 0u);
+            for (int k = 0; k < 8; ++k) mma_ss(tmem + TS_S, dK + 128 * k, dV + 128 * k, IDESC_MM64, (c > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem + TS_Z, dK + 128 * k, dOnes, IDESC_Z8, (c > 0 || k > 0) ? 1u : 0u);
             mma_commit(bar_mma);
         }
-        sdz[tid] = colsum_half(sK, tid & 63, tid >> 6, nullptr);               // overlaps the MMA
+        if (c + 1 < nwork) phi_stage(c + 1);              // overlaps the MMA of chunk c
         mbar_wait(bar_mma, c & 1);
         tc_fence_after();
         const int64_t slot = (int64_t)nh * nchunks + c + 1;
-        uint8_t *dst = tiles + slot * S_TILE_BYTES + erow * 128;
-#pragma unroll
-        for (int p = 0; p < 2; ++p) {
+        {   // snapshot: warp w reads rows 16*(w&3).. (lanes 0..15), columns 32*(w>>2)..+31
             uint32_t r[32];
-            tmem_ld32(t_lane + 32 * p, r);
+            tmem_ld32(t_lane + TS_S + 32 * half, r);
+            uint32_t z8[8];
+            if (half == 0) tmem_ld8(t_lane + TS_Z, z8);
             tmem_ld_wait();
             if (lane < 16) {
+                uint8_t *dst = tiles + slot * S_TILE_BYTES + erow * 128 + 64 * half;
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(dst + 64 * p + 16 * cc) = pack8u(r + 8 * cc, 1.f);
+                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(dst + 16 * cc) = pack8u(r + 8 * cc, 1.f);
+                if (half == 0) zs[slot * 64 + erow] = __uint_as_float(z8[0]);
             }
         }
+        fence_proxy_async();                              // phi(c+1) writes -> visible to the next UMMA
         tc_fence_before();
-        __syncthreads();                                  // sdz complete; every warp has read its TMEM rows and this stage's tiles
+        __syncthreads();                                  // TMEM rows read; stage s consumed
         if (tid == 0 && c + ST_STAGES < nwork) {          // refill the stage
+            uint8_t *sK = sm + s * ST_STAGE_BYTES;
             mbar_expect_tx(bar_full + s, ST_STAGE_BYTES);
             tma_load_2d(sK, &tmK, bar_full + s, col0, row0 + (c + ST_STAGES) * CHUNK);
-            tma_load_2d(sV, &tmV, bar_full + s, col0, row0 + (c + ST_STAGES) * CHUNK);
-        }
-        if (tid < 64) {
-            zacc += sdz[tid] + sdz[64 + tid];
-            zs[slot * 64 + tid] = zacc;
+            tma_load_2d(sK + TILE_BYTES, &tmV, bar_full + s, col0, row0 + (c + ST_STAGES) * CHUNK);
         }
     }
     tc_fence_before();
     __syncthreads();
-    if (warp == 0) tmem_dealloc<64>(tmem);
+    if (warp == 0) tmem_dealloc<128>(tmem);
 }
 
 // =============================================================================================
@@ -332,7 +425,8 @@ cp_scan_kernel(const float *__restrict__ part, uint8_t *__restrict__ tiles, floa
 //   shared memory: sQ | sV | sS | sK..sP  (the 32 KB bf16 score tile starts on the dead K tile)
 // =============================================================================================
 constexpr uint32_t F_OFF_Q = 0, F_OFF_V = 16384, F_OFF_S = 32768, F_OFF_K = 40960, F_OFF_P = 40960;
-constexpr uint32_t F_OFF_Z = 73728, F_OFF_DP = F_OFF_Z + 256, F_OFF_BAR = F_OFF_DP + 2048, F_SMEM = F_OFF_BAR + 32;
+constexpr uint32_t F_OFF_Z = 73728 /* 64 floats */, F_OFF_DP = F_OFF_Z + 256 /* 2 x 128 floats */, F_OFF_BAR = F_OFF_DP + 1024,
+                   F_SMEM = F_OFF_BAR + 32;
 
 __device__ __forceinline__ void store_row32(void *base, int64_t ld_elems, int64_t row, int col, const uint4 (&v)[4]) {
     uint4 *d = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(base) + row * ld_elems + col);
@@ -343,7 +437,8 @@ __device__ __forceinline__ void store_row32(void *base, int64_t ld_elems, int64_
 __global__ void __launch_bounds__(NTH, 3)
 cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmS, const float *__restrict__ zp,
-                  void *__restrict__ out, float *__restrict__ den, int L, int H, int nchunks, int NH, int64_t ld_o, float eps) {
+                  void *__restrict__ out, float *__restrict__ den, int L, int H, int nchunks, int NH, int64_t ld_o, float eps,
+                  long long *__restrict__ dbg) {
     // Persistent: CTA b handles tiles b, b + gridDim.x, ... in chunk-major order (tile t = chunk t / NH of pair t % NH),
     // so barrier / TMEM set-up is paid once and the next tile's TMA loads fly while this tile's epilogue runs.
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -362,9 +457,9 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         tma_load_2d(sV, &tmV, bar_load, col0, grow);
         if (c > 0) tma_load_2d(sS, &tmS, bar_load, 0, (int)(((int64_t)nh * nchunks + c) * 64));
     };
-    auto load_z = [&](int t) {                        // tid < 64
+    auto fetch_z = [&](int t) -> float {              // tid < 64: the key-sum prefix of tile t (0 for a sequence's first chunk)
         const int c = t / NH, nh = t % NH;
-        sz[tid] = c > 0 ? zp[((int64_t)nh * nchunks + c) * 64 + tid] : 0.f;
+        return c > 0 ? zp[((int64_t)nh * nchunks + c) * 64 + tid] : 0.f;
     };
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
@@ -374,7 +469,7 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if ((int)blockIdx.x < ntiles) issue_loads(blockIdx.x);
     }
     if ((tid >> 5) == 0) tmem_alloc<128>(tmem_slot);
-    if (tid < 64 && (int)blockIdx.x < ntiles) load_z(blockIdx.x);
+    if (tid < 64 && (int)blockIdx.x < ntiles) sz[tid] = fetch_z(blockIdx.x);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -383,27 +478,31 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
     const uint64_t dP = smem_desc_sw128(smem_u32(sP)), dS = smem_desc_sw128(smem_u32(sS));
     uint32_t ph_load = 0, ph_mma = 0;
+    int dbg_i = 0;
+#define CPM_STAMP() do { if (dbg && tid == 0 && dbg_i < 64) dbg[(int64_t)blockIdx.x * 64 + dbg_i++] = clock64(); } while (0)
+    CPM_STAMP();
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int c = t / NH, nh = t % NH, n = nh / H, h = nh % H;
         const int grow = n * L + c * CHUNK, col0 = h * 64;
         const bool have_state = c > 0;
+        const int tn = t + gridDim.x;
+        float z_next = 0.f;                               // prefetched now, parked in a register until the epilogue
+        if (tid < 64 && tn < ntiles) z_next = fetch_z(tn);
         mbar_wait(bar_load, ph_load);
         ph_load ^= 1;
-        float den_inter = 0.f;
+        CPM_STAMP();
+        float den_part = 0.f;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
             const int ch = 4 * g.half + cc;
             const uint32_t off = sw128_off(g.row, ch);
-            float f[8];
-            *reinterpret_cast<uint4 *>(sQ + off) = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) den_inter = fmaf(f[i], sz[ch * 8 + i], den_inter);
-            *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+            *reinterpret_cast<uint4 *>(sQ + off) = phi8_dot(*reinterpret_cast<const uint4 *>(sQ + off), sz + 8 * ch, den_part);
+            *reinterpret_cast<uint4 *>(sK + off) = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
         }
-        sdp[g.half * 128 + g.row] = den_inter;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        CPM_STAMP();
         if (tid == 0) {                                   // P = Qf Kf^T
             tc_fence_after();
 #pragma unroll
@@ -413,10 +512,13 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        sdp[256 + g.half * 128 + g.row] = convert_scores<true>(g, 0, sP, 0.f, nullptr);     // overwrites the dead K tile
+        CPM_STAMP();
+        den_part += convert_lean<true, false, false, true>(g, 0, sP, 0.f, nullptr);           // overwrites the dead K tile
+        sdp[g.half * 128 + g.row] = den_part;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        CPM_STAMP();
         if (tid == 0) {                                   // O = Qf Sp + P V   (into the score tile's first 64 columns)
             tc_fence_after();
             uint32_t acc = 0;
@@ -428,16 +530,16 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             for (int k = 0; k < 8; ++k) { mma_ss(tmem, dP + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dV + 128 * k, IDESC_KM64, acc); acc = 1; }
             mma_commit(bar_mma);
         }
-        const float dn = sdp[g.row] + sdp[128 + g.row] + sdp[256 + g.row] + sdp[384 + g.row] + eps;
+        const float dn = sdp[g.row] + sdp[128 + g.row] + eps;
         const float inv = 1.f / dn;
         if (den && g.half == 0) den[(int64_t)(grow + g.row) * H + h] = dn;
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        const int tn = t + gridDim.x;
+        CPM_STAMP();
         if (tn < ntiles) {                                // every operand tile is dead: fetch the next tile under the epilogue
             if (tid == 0) issue_loads(tn);
-            if (tid < 64) load_z(tn);
+            if (tid < 64) sz[tid] = z_next;
         }
         {
             uint32_t r[32];
@@ -449,9 +551,11 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             store_row32(out, ld_o, grow + g.row, col0 + 32 * g.half, o);
         }
         tc_fence_before();
-        __syncthreads();                                  // TMEM columns and sz / sdp are reused by the next tile
+        __syncthreads();                                  // TMEM columns, sz and sdp are reused by the next tile
         tc_fence_after();
+        CPM_STAMP();
     }
+#undef CPM_STAMP
     if ((tid >> 5) == 0) tmem_dealloc<128>(tmem);
 }
 
@@ -662,6 +766,10 @@ int set_smem_once(const void *fn, uint32_t bytes, bool *done, const char *what) 
 }  // namespace
 
 // ---------------------------------------------------------------- host side
+// Optional per-CTA phase timestamps (clock64) of cp_out_fwd_kernel for tools/; 64 slots per CTA.  NULL = off.
+static long long *g_cp_timing = nullptr;
+void linattn_cp_set_timing_buffer(long long *p) { g_cp_timing = p; }
+
 // workspace: [increments fp32 NHC x 4160][Sp region][Rs region][gd fp32 N*L*H]
 int64_t linattn_cp_workspace_bytes(int N, int L, int H) {
     if (L % CHUNK != 0) return 0;
@@ -688,7 +796,7 @@ int prefix_states(const void *k, const void *v, int N, int L, int H, int64_t ld_
     if (N * H >= 96) {                                  // enough independent (batch, head) chains: stream, no scan
         static bool as = false;
         if ((rc = set_smem_once((const void *)cp_prefix_stream_fwd_kernel, ST_SMEM, &as, "cp_prefix_stream_fwd"))) return rc;
-        cp_prefix_stream_fwd_kernel<<<N * H, 128, ST_SMEM, st>>>(tk, tv, region, zs, L, H, nchunks);
+        cp_prefix_stream_fwd_kernel<<<N * H, NTH, ST_SMEM, st>>>(tk, tv, region, zs, L, H, nchunks);
         return check_launch("linattn_cp prefix stream");
     }
     static bool a1 = false;
@@ -720,7 +828,8 @@ int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out
     if ((rc = set_smem_once((const void *)cp_out_fwd_kernel, F_SMEM, &a3, "cp_out_fwd"))) return rc;
     const int64_t slots = 3ll * num_sms();
     cp_out_fwd_kernel<<<(unsigned)(nhc < slots ? nhc : slots), NTH, F_SMEM, st>>>(
-        tq, tk, tv, ts, reinterpret_cast<const float *>(region + state_tiles_bytes(nhc)), out, den, L, H, nchunks, N * H, ld_o, eps);
+        tq, tk, tv, ts, reinterpret_cast<const float *>(region + state_tiles_bytes(nhc)), out, den, L, H, nchunks, N * H, ld_o, eps,
+        g_cp_timing);
     return check_launch("linattn_fwd_cp");
 }
 

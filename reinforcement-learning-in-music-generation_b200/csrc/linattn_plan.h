@@ -45,6 +45,7 @@ int linattn_bwd_tc_launch(const void *q, const void *k, const void *v, const voi
 // chunk-parallel tcgen05 path (linattn_cp.cu)
 int64_t linattn_cp_workspace_bytes(int N, int L, int H);
 int64_t linattn_cp_saved_bytes(int N, int L, int H);
+void linattn_cp_set_timing_buffer(long long *p);
 int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H,
                           int64_t ld_qkv, int64_t ld_o, float eps, void *ws, void *saved, cudaStream_t st);
 int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const void *out, const float *den,
