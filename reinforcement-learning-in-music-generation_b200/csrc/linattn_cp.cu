@@ -560,21 +560,43 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 }
 
 // =============================================================================================
-// B3: dq, dk, dv of one chunk.  256 threads, 256 TMEM columns, 2 CTAs / SM.
+// B3: dq, dk, dv of one chunk.  256 threads, 256 TMEM columns, 2 CTAs / SM, persistent over tiles.
 //   X[i][j]  = G'[i].v[j] + gd_i   (j <= i)        dQf = X Kf + G' Sp^T + gd z         dq = dQf * phi'(q)
 //   PT[j][i] = Kf[j].Qf[i]         (i >= j)        dv  = PT G' + Kf Rs
 //   WT[j][i] = v[j].G'[i] + gd_i   (i >= j)        dKf = WT Qf + v Rs^T + rz           dk = dKf * phi'(k)
+// Loads are split over two barriers so the tiles that die first (K, G' after round 3) are refilled for the next
+// tile a whole round before the rest (Q, V, Sp, Rs after round 4).
 // =============================================================================================
 constexpr uint32_t B_OFF_Q = 0, B_OFF_K = 16384, B_OFF_V = 32768, B_OFF_G = 49152, B_OFF_S = 65536, B_OFF_R = 73728, B_OFF_X = 81920;
-constexpr uint32_t B_OFF_GD = 114688, B_OFF_BAR = B_OFF_GD + 512, B_SMEM = B_OFF_BAR + 32;
+constexpr uint32_t B_OFF_GD = 114688 /* 128 floats: gd, later rz */, B_OFF_Z = B_OFF_GD + 512 /* 64 floats */, B_OFF_BAR = B_OFF_Z + 256,
+                   B_SMEM = B_OFF_BAR + 32;
 constexpr uint32_t TB_X = 0, TB_A1 = 128, TB_A2 = 192;
 
 struct BwdMainArgs {
     const float *den, *gd, *zp, *rzs;
     void *gq, *gk, *gv;
     int64_t ld_g;
-    int L, H, nchunks;
+    int L, H, nchunks, NH;
 };
+
+// acc (32 fp32 TMEM values) + add[c] (+ rowscale * vec[c]) then * phi'(f) -> 32 bf16
+template <bool HAS_VEC>
+__device__ __forceinline__ void grad_row_epilogue(const uint32_t (&r)[32], const uint32_t (&fr)[16], const float *vec, float rowscale,
+                                                  uint4 (&o)[4]) {
+#pragma unroll
+    for (int cc = 0; cc < 4; ++cc) {
+        uint32_t w[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const uint32_t u = fr[4 * cc + i];
+            const float f0 = __uint_as_float(u << 16), f1 = __uint_as_float(u & 0xffff0000u);
+            float a0 = __uint_as_float(r[8 * cc + 2 * i]), a1 = __uint_as_float(r[8 * cc + 2 * i + 1]);
+            if (HAS_VEC) { a0 = fmaf(rowscale, vec[8 * cc + 2 * i], a0); a1 = fmaf(rowscale, vec[8 * cc + 2 * i + 1], a1); }
+            w[i] = pack_bf16(a0 * fminf(f0, 1.f), a1 * fminf(f1, 1.f));
+        }
+        o[cc] = make_uint4(w[0], w[1], w[2], w[3]);
+    }
+}
 
 __global__ void __launch_bounds__(NTH, 2)
 cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
@@ -583,26 +605,41 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sQ = sm + B_OFF_Q, *sK = sm + B_OFF_K, *sV = sm + B_OFF_V, *sG = sm + B_OFF_G, *sS = sm + B_OFF_S, *sR = sm + B_OFF_R;
     uint8_t *sX = sm + B_OFF_X;
-    float *sgd = reinterpret_cast<float *>(sm + B_OFF_GD);
-    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + B_OFF_BAR), *bar_mma = bar_load + 1;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
+    float *sgd = reinterpret_cast<float *>(sm + B_OFF_GD), *sz = reinterpret_cast<float *>(sm + B_OFF_Z);
+    uint64_t *bar_a = reinterpret_cast<uint64_t *>(sm + B_OFF_BAR), *bar_b = bar_a + 1, *bar_mma = bar_a + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 3);
     const int tid = threadIdx.x;
-    const int nh = blockIdx.x / a.nchunks, c = blockIdx.x % a.nchunks, n = nh / a.H, h = nh % a.H;
-    const int grow = n * a.L + c * CHUNK, col0 = h * 64;
-    const bool have_s = c > 0, have_r = c + 1 < a.nchunks;
-    const int64_t slot = (int64_t)nh * a.nchunks + c;
+    const int ntiles = a.NH * a.nchunks;
+    auto tile_coords = [&](int t, int &c, int &nh, int &grow, int &col0) {
+        c = t / a.NH; nh = t % a.NH;
+        const int n = nh / a.H, h = nh % a.H;
+        grow = n * a.L + c * CHUNK; col0 = h * 64;
+    };
+    auto issue_a = [&](int t) {                       // tid 0: K and go tiles
+        int c, nh, grow, col0;
+        tile_coords(t, c, nh, grow, col0);
+        mbar_expect_tx(bar_a, 2 * TILE_BYTES);
+        tma_load_2d(sK, &tmK, bar_a, col0, grow);
+        tma_load_2d(sG, &tmGo, bar_a, col0, grow);
+    };
+    auto issue_b = [&](int t) {                       // tid 0: Q, V and the two carried-state tiles
+        int c, nh, grow, col0;
+        tile_coords(t, c, nh, grow, col0);
+        const bool hs = c > 0, hr = c + 1 < a.nchunks;
+        const int srow = (int)(((int64_t)nh * a.nchunks + c) * 64);
+        mbar_expect_tx(bar_b, 2 * TILE_BYTES + (hs ? S_TILE_BYTES : 0) + (hr ? S_TILE_BYTES : 0));
+        tma_load_2d(sQ, &tmQ, bar_b, col0, grow);
+        tma_load_2d(sV, &tmV, bar_b, col0, grow);
+        if (hs) tma_load_2d(sS, &tmS, bar_b, 0, srow);
+        if (hr) tma_load_2d(sR, &tmR, bar_b, 0, srow);
+    };
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-        mbar_init(bar_load, 1);
+        mbar_init(bar_a, 1);
+        mbar_init(bar_b, 1);
         mbar_init(bar_mma, 1);
         fence_barrier_init();
-        mbar_expect_tx(bar_load, 4 * TILE_BYTES + (have_s ? S_TILE_BYTES : 0) + (have_r ? S_TILE_BYTES : 0));
-        tma_load_2d(sQ, &tmQ, bar_load, col0, grow);
-        tma_load_2d(sK, &tmK, bar_load, col0, grow);
-        tma_load_2d(sV, &tmV, bar_load, col0, grow);
-        tma_load_2d(sG, &tmGo, bar_load, col0, grow);
-        if (have_s) tma_load_2d(sS, &tmS, bar_load, 0, (int)(slot * 64));
-        if (have_r) tma_load_2d(sR, &tmR, bar_load, 0, (int)(slot * 64));
+        if ((int)blockIdx.x < ntiles) { issue_a(blockIdx.x); issue_b(blockIdx.x); }
     }
     if ((tid >> 5) == 0) tmem_alloc<256>(tmem_slot);
     tc_fence_before();
@@ -610,148 +647,169 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     const Geo g(tmem);
-    const float inv = 1.f / a.den[(int64_t)(grow + g.row) * a.H + h];
-    const float gd = a.gd[(int64_t)(grow + g.row) * a.H + h];
-    if (g.half == 0) sgd[g.row] = gd;
     const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
     const uint64_t dG = smem_desc_sw128(smem_u32(sG)), dS = smem_desc_sw128(smem_u32(sS)), dR = smem_desc_sw128(smem_u32(sR));
     const uint64_t dX = smem_desc_sw128(smem_u32(sX));
-    mbar_wait(bar_load, 0);
-    uint32_t qfr[16], kfr[16];                         // this thread's Qf / Kf values (packed bf16) for phi'
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
-        float f[8];
-        unpack8(*reinterpret_cast<const uint4 *>(sG + off), f);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) f[i] *= inv;
-        *reinterpret_cast<uint4 *>(sG + off) = pack8(f);
-        const uint4 qv = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
-        *reinterpret_cast<uint4 *>(sQ + off) = qv;
-        qfr[4 * cc + 0] = qv.x; qfr[4 * cc + 1] = qv.y; qfr[4 * cc + 2] = qv.z; qfr[4 * cc + 3] = qv.w;
-        const uint4 kv = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
-        *reinterpret_cast<uint4 *>(sK + off) = kv;
-        kfr[4 * cc + 0] = kv.x; kfr[4 * cc + 1] = kv.y; kfr[4 * cc + 2] = kv.z; kfr[4 * cc + 3] = kv.w;
+    // per-row scalars of the first tile; later tiles' are prefetched one tile ahead
+    float inv_n = 0.f, gd_n = 0.f;
+    if ((int)blockIdx.x < ntiles) {
+        int c, nh, grow, col0;
+        tile_coords(blockIdx.x, c, nh, grow, col0);
+        const int64_t ri = (int64_t)(grow + g.row) * a.H + (col0 >> 6);
+        inv_n = 1.f / a.den[ri];
+        gd_n = a.gd[ri];
     }
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- round 1: X = G' V^T
-    if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dG + 2 * k, dV + 2 * k, IDESC_KK128, k > 0);
-        mma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, 0);
-    tc_fence_after();
-    convert_scores<true>(g, TB_X, sX, gd, nullptr);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- round 2: dQf = X Kf (+ G' Sp^T) ; PT = Kf Qf^T
-    if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dK + 128 * k, IDESC_KM64, k > 0);
-        if (have_s) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dG + 2 * k, dS + 2 * k, IDESC_KK64, 1);
+    uint32_t ph_a = 0, ph_b = 0, ph_mma = 0;
+    for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
+        int c, nh, grow, col0;
+        tile_coords(t, c, nh, grow, col0);
+        const bool have_s = c > 0, have_r = c + 1 < a.nchunks;
+        const int64_t slot = (int64_t)nh * a.nchunks + c;
+        const int tn = t + gridDim.x;
+        const float inv = inv_n, gd = gd_n;
+        float z_cur = 0.f, rz_cur = 0.f;                   // tid < 64
+        if (tid < 64) {
+            if (have_s) z_cur = a.zp[slot * 64 + tid];
+            if (have_r) rz_cur = a.rzs[slot * 64 + tid];
         }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dQ + 2 * k, IDESC_KK128, k > 0);
-        mma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, 1);
-    tc_fence_after();
-    {   // dq rows
-        uint32_t r[32];
-        tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
-        tmem_ld_wait();
-        const float *z = a.zp + slot * 64 + 32 * g.half;
-        uint4 o[4];
+        if (tn < ntiles) {                                // next tile's per-row scalars: in flight for the whole tile
+            int c2, nh2, grow2, col2;
+            tile_coords(tn, c2, nh2, grow2, col2);
+            const int64_t ri = (int64_t)(grow2 + g.row) * a.H + (col2 >> 6);
+            inv_n = a.den[ri];
+            gd_n = a.gd[ri];
+        }
+        if (g.half == 0) sgd[g.row] = gd;
+        if (tid < 64) sz[tid] = z_cur;
+        uint32_t qfr[16], kfr[16];                         // this thread's Qf / Kf values (packed bf16) for phi'
+        mbar_wait(bar_a, ph_a);
+        ph_a ^= 1;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-            float f[8], qf[8];
-            unpack8(make_uint4(qfr[4 * cc], qfr[4 * cc + 1], qfr[4 * cc + 2], qfr[4 * cc + 3]), qf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float zz = have_s ? __ldg(z + 8 * cc + i) : 0.f;
-                f[i] = (__uint_as_float(r[8 * cc + i]) + gd * zz) * (qf[i] <= 1.f ? qf[i] : 1.f);
-            }
-            o[cc] = pack8(f);
+            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
+            const uint4 gv = *reinterpret_cast<const uint4 *>(sG + off);
+            *reinterpret_cast<uint4 *>(sG + off) = make_uint4(scale2(gv.x, inv), scale2(gv.y, inv), scale2(gv.z, inv), scale2(gv.w, inv));
+            const uint4 kv = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
+            *reinterpret_cast<uint4 *>(sK + off) = kv;
+            kfr[4 * cc + 0] = kv.x; kfr[4 * cc + 1] = kv.y; kfr[4 * cc + 2] = kv.z; kfr[4 * cc + 3] = kv.w;
         }
-        store_row32(a.gq, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
-    }
-    convert_scores<false>(g, TB_X, sX, 0.f, nullptr);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- round 3: dv = PT G' (+ Kf Rs) ; WT = V G'^T
-    if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            mma_ss(tmem + TB_A2, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
-        if (have_r) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A2, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);
-        }
-#pragma unroll
-        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dV + 2 * k, dG + 2 * k, IDESC_KK128, k > 0);
-        mma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, 0);
-    tc_fence_after();
-    {   // dv rows
-        uint32_t r[32];
-        tmem_ld32(g.t_lane + TB_A2 + 32 * g.half, r);
-        tmem_ld_wait();
-        uint4 o[4];
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, 1.f);
-        store_row32(a.gv, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
-    }
-    convert_scores<false>(g, TB_X, sX, 0.f, sgd);
-    fence_proxy_async();
-    tc_fence_before();
-    __syncthreads();
-    // ---- round 4: dKf = WT Qf (+ v Rs^T)
-    if (tid == 0) {
-        tc_fence_after();
-#pragma unroll
-        for (int k = 0; k < 8; ++k)
-            mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dQ + 128 * k, IDESC_KM64, k > 0);
-        if (have_r) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dV + 2 * k, dR + 2 * k, IDESC_KK64, 1);
-        }
-        mma_commit(bar_mma);
-    }
-    mbar_wait(bar_mma, 1);
-    tc_fence_after();
-    {   // dk rows
-        uint32_t r[32];
-        tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
-        tmem_ld_wait();
-        const float *rz = a.rzs + slot * 64 + 32 * g.half;
-        uint4 o[4];
+        mbar_wait(bar_b, ph_b);
+        ph_b ^= 1;
 #pragma unroll
         for (int cc = 0; cc < 4; ++cc) {
-            float f[8], kf[8];
-            unpack8(make_uint4(kfr[4 * cc], kfr[4 * cc + 1], kfr[4 * cc + 2], kfr[4 * cc + 3]), kf);
-#pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                const float rr = have_r ? __ldg(rz + 8 * cc + i) : 0.f;
-                f[i] = (__uint_as_float(r[8 * cc + i]) + rr) * (kf[i] <= 1.f ? kf[i] : 1.f);
-            }
-            o[cc] = pack8(f);
+            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
+            const uint4 qv = phi8_lean(*reinterpret_cast<const uint4 *>(sQ + off));
+            *reinterpret_cast<uint4 *>(sQ + off) = qv;
+            qfr[4 * cc + 0] = qv.x; qfr[4 * cc + 1] = qv.y; qfr[4 * cc + 2] = qv.z; qfr[4 * cc + 3] = qv.w;
         }
-        store_row32(a.gk, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- round 1: X = G' V^T
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dG + 2 * k, dV + 2 * k, IDESC_KK128, k > 0);
+            mma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        convert_lean<true, true, false>(g, TB_X, sX, gd, nullptr);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- round 2: dQf = X Kf (+ G' Sp^T) ; PT = Kf Qf^T
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dK + 128 * k, IDESC_KM64, k > 0);
+            if (have_s) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dG + 2 * k, dS + 2 * k, IDESC_KK64, 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dQ + 2 * k, IDESC_KK128, k > 0);
+            mma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        {   // dq rows
+            uint32_t r[32];
+            tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
+            tmem_ld_wait();
+            uint4 o[4];
+            grad_row_epilogue<true>(r, qfr, sz + 32 * g.half, gd, o);
+            store_row32(a.gq, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+        }
+        convert_lean<false, false, false>(g, TB_X, sX, 0.f, nullptr);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- round 3: dv = PT G' (+ Kf Rs) ; WT = V G'^T
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                mma_ss(tmem + TB_A2, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
+            if (have_r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A2, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);
+            }
+#pragma unroll
+            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dV + 2 * k, dG + 2 * k, IDESC_KK128, k > 0);
+            mma_commit(bar_mma);
+        }
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        if (tid == 0 && tn < ntiles) issue_a(tn);          // K and G' are dead: refill them a round early
+        {   // dv rows
+            uint32_t r[32];
+            tmem_ld32(g.t_lane + TB_A2 + 32 * g.half, r);
+            tmem_ld_wait();
+            uint4 o[4];
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, 1.f);
+            store_row32(a.gv, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+        }
+        convert_lean<false, false, true>(g, TB_X, sX, 0.f, sgd);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();                                  // every thread is done with sgd (column adds)
+        if (tid < 64) sgd[tid] = rz_cur;                   // the gd slots now carry rz for the dk epilogue
+        // ---- round 4: dKf = WT Qf (+ v Rs^T)
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dQ + 128 * k, IDESC_KM64, k > 0);
+            if (have_r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dV + 2 * k, dR + 2 * k, IDESC_KK64, 1);
+            }
+            mma_commit(bar_mma);
+        }
+        inv_n = 1.f / inv_n;                               // (prefetched den of the next tile)
+        __syncthreads();                                  // rz visible
+        mbar_wait(bar_mma, ph_mma);
+        ph_mma ^= 1;
+        tc_fence_after();
+        if (tid == 0 && tn < ntiles) issue_b(tn);
+        {   // dk rows
+            uint32_t r[32];
+            tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
+            tmem_ld_wait();
+            uint4 o[4];
+            grad_row_epilogue<true>(r, kfr, sgd + 32 * g.half, 1.f, o);
+            store_row32(a.gk, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+        }
+        tc_fence_before();
+        __syncthreads();                                  // TMEM accumulators, sgd, sz are reused by the next tile
+        tc_fence_after();
     }
-    tc_fence_before();
-    __syncthreads();
     if ((tid >> 5) == 0) tmem_dealloc<256>(tmem);
 }
 
@@ -871,8 +929,9 @@ int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const voi
     a.den = den; a.gd = gd;
     a.zp = reinterpret_cast<const float *>(sp_region + state_tiles_bytes(nhc));
     a.rzs = reinterpret_cast<const float *>(rs_region + state_tiles_bytes(nhc));
-    a.gq = gq; a.gk = gk; a.gv = gv; a.ld_g = ld_g; a.L = L; a.H = H; a.nchunks = nchunks;
-    cp_bwd_main_kernel<<<(unsigned)nhc, NTH, B_SMEM, st>>>(tq, tk, tv, tgo, ts, tr, a);
+    a.gq = gq; a.gk = gk; a.gv = gv; a.ld_g = ld_g; a.L = L; a.H = H; a.nchunks = nchunks; a.NH = N * H;
+    const int64_t slots = 2ll * num_sms();
+    cp_bwd_main_kernel<<<(unsigned)(nhc < slots ? nhc : slots), NTH, B_SMEM, st>>>(tq, tk, tv, tgo, ts, tr, a);
     return check_launch("linattn_bwd_cp");
 }
 
