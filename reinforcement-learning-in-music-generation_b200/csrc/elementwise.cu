@@ -278,36 +278,80 @@ __global__ void ln_reduce_partials_kernel(const float *__restrict__ partials, in
 }
 
 // ---------------------------------------------------------------- bias + exact GELU + dropout
-__device__ __forceinline__ float gelu_f(float x) { return 0.5f * x * (1.f + erff(x * 0.70710678118654752f)); }
-__device__ __forceinline__ float dgelu_f(float x) {
-    return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * __expf(-0.5f * x * x);
+// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. exact at fp32-parity tolerance): branch-free,
+// two MUFU ops; e = exp(-x^2/2) is shared with the Gaussian term of the derivative.  (CUDA's erff costs ~2x
+// the instructions; this kernel is instruction-issue bound, ncu: 40 instr/element before, HBM needs <= 14.)
+struct GeluParts { float cdf, e; };            // Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  e = exp(-x^2 / 2)
+__device__ __forceinline__ GeluParts gelu_parts(float x) {
+    const float a = fabsf(x) * 0.70710678118654752f;
+    float t, e;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.f)));
+    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));      // -0.5 * log2(e)
+    float p = fmaf(1.061405429f, t, -1.453152027f);
+    p = fmaf(p, t, 1.421413741f);
+    p = fmaf(p, t, -0.284496736f);
+    p = fmaf(p, t, 0.254829592f);
+    const float half_erfc = 0.5f * p * t * e;                   // 0.5 * erfc(|x| / sqrt 2)
+    GeluParts r;
+    r.cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
+    r.e = e;
+    return r;
 }
+// EXACT (the fp32 parity mode): libdevice erff / expf.
+template <bool EXACT> __device__ __forceinline__ float gelu_f(float x) {
+    if (EXACT) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
+    return x * gelu_parts(x).cdf;
+}
+template <bool EXACT> __device__ __forceinline__ float dgelu_f(float x) {
+    if (EXACT) return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * expf(-0.5f * x * x);
+    const GeluParts g = gelu_parts(x);
+    return fmaf(x * 0.39894228040143268f, g.e, g.cdf);
+}
+// Dropout keep-bits for the 16 elements [16*g, 16*g+16): one Philox4x32-10 block, 8 random bits per element,
+// keep iff bits >= thr8 (drop probability quantised to thr8 / 256).
+__device__ __forceinline__ uint32_t dropout_keep16(uint64_t seed, uint64_t offset, uint64_t g, uint32_t thr8) {
+    const uint64_t ctr = offset + g;
+    const uint4 r = Philox::block(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x44523136u /*"DR16"*/, 0u),
+                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
+    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+    uint32_t keep = 0;
+#pragma unroll
+    for (int i = 0; i < 16; ++i) keep |= (((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) >= thr8 ? 1u : 0u) << i;
+    return keep;
+}
+inline uint32_t dropout_threshold8(float p) {
+    if (p <= 0.f) return 0u;
+    double t = (double)p * 256.0 + 0.5;
+    return t >= 255.0 ? 255u : (t < 1.0 ? 1u : (uint32_t)t);
+}
+inline float dropout_scale8(float p) { uint32_t t = dropout_threshold8(p); return t ? 256.0f / (256.0f - (float)t) : 1.0f; }
 
+// 16 elements per thread and iteration (two 128-bit loads in flight per operand, one Philox block)
 template <typename T, bool BWD>
 __global__ void __launch_bounds__(256) gelu_kernel(const T *__restrict__ x, const float *__restrict__ bias, const T *__restrict__ gy, T *__restrict__ out,
-                                                   int64_t rows, int d, uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset) {
-    const int G = d >> 3;
-    const int64_t total = rows * G;
-    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
-        const int c = (int)(i % G) * 8;
-        Vec8<T> v, g;
-        v.load(x + i * 8);
+                                                   int64_t n_groups, int d, uint32_t thr8, float scale, uint64_t seed, uint64_t rng_offset) {
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += (int64_t)gridDim.x * blockDim.x) {
+        Vec8<T> v0, v1, g0, g1;
+        v0.load(x + i * 16);
+        v1.load(x + i * 16 + 8);
+        if (BWD) { g0.load(gy + i * 16); g1.load(gy + i * 16 + 8); }
         if (bias) {
-            float4 b0 = *reinterpret_cast<const float4 *>(bias + c), b1 = *reinterpret_cast<const float4 *>(bias + c + 4);
-            v.v[0] += b0.x; v.v[1] += b0.y; v.v[2] += b0.z; v.v[3] += b0.w;
-            v.v[4] += b1.x; v.v[5] += b1.y; v.v[6] += b1.z; v.v[7] += b1.w;
+            const int c = (int)((i * 16) % d);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v0.v[j] += bias[c + j]; v1.v[j] += bias[c + 8 + j]; }
         }
-        if (BWD) g.load(gy + i * 8);
-        bool keep[8];
-        if (thr) dropout_mask8(seed, rng_offset, (uint64_t)i, thr, keep);
-        Vec8<T> o;
+        const uint32_t keep = thr8 ? dropout_keep16(seed, rng_offset, (uint64_t)i, thr8) : 0xFFFFu;
+        Vec8<T> o0, o1;
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
-            float r = BWD ? g.v[j] * dgelu_f(v.v[j]) : gelu_f(v.v[j]);
-            if (thr) r = keep[j] ? r * scale : 0.f;
-            o.v[j] = r;
+            constexpr bool EX = sizeof(T) == 4;
+            const float r0 = BWD ? g0.v[j] * dgelu_f<EX>(v0.v[j]) : gelu_f<EX>(v0.v[j]);
+            const float r1 = BWD ? g1.v[j] * dgelu_f<EX>(v1.v[j]) : gelu_f<EX>(v1.v[j]);
+            o0.v[j] = (keep >> j) & 1u ? r0 * scale : 0.f;
+            o1.v[j] = (keep >> (8 + j)) & 1u ? r1 * scale : 0.f;
         }
-        o.store(out + i * 8);
+        o0.store(out + i * 16);
+        o1.store(out + i * 16 + 8);
     }
 }
 
@@ -456,22 +500,24 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
 int cpm_gelu_fwd(const void *x, const float *bias, void *y, int64_t rows, int d, float p_drop, uint64_t seed, uint64_t rng_offset,
                  int dtype, void *stream) {
     CPM_REQUIRE(x && y, CPM_ERR_NULL, "gelu_fwd: NULL pointer");
-    CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0, CPM_ERR_BAD_SHAPE, "gelu_fwd: d=%d", d);
+    CPM_REQUIRE(rows >= 0 && d > 0 && d % 16 == 0, CPM_ERR_BAD_SHAPE, "gelu_fwd: d=%d must be a multiple of 16", d);
     CPM_REQUIRE(aligned16(x) && aligned16(y) && (!bias || aligned16(bias)), CPM_ERR_BAD_ALIGN, "gelu_fwd: alignment");
     if (rows == 0) return CPM_OK;
-    DISPATCH_DTYPE(dtype, gelu_kernel<T, false><<<grid_for(rows * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-                              (const T *)x, bias, nullptr, (T *)y, rows, d, dropout_threshold(p_drop), dropout_scale(p_drop), seed, rng_offset));
+    DISPATCH_DTYPE(dtype, gelu_kernel<T, false><<<grid_for(rows * (d / 16), 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const T *)x, bias, nullptr, (T *)y, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop), seed,
+                              rng_offset));
     return check_launch("gelu_fwd");
 }
 
 int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, int64_t rows, int d, float p_drop, uint64_t seed,
                  uint64_t rng_offset, int dtype, void *stream) {
     CPM_REQUIRE(x && gy && gx, CPM_ERR_NULL, "gelu_bwd: NULL pointer");
-    CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0, CPM_ERR_BAD_SHAPE, "gelu_bwd: d=%d", d);
+    CPM_REQUIRE(rows >= 0 && d > 0 && d % 16 == 0, CPM_ERR_BAD_SHAPE, "gelu_bwd: d=%d must be a multiple of 16", d);
     CPM_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(gx) && (!bias || aligned16(bias)), CPM_ERR_BAD_ALIGN, "gelu_bwd: alignment");
     if (rows == 0) return CPM_OK;
-    DISPATCH_DTYPE(dtype, gelu_kernel<T, true><<<grid_for(rows * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-                              (const T *)x, bias, (const T *)gy, (T *)gx, rows, d, dropout_threshold(p_drop), dropout_scale(p_drop), seed, rng_offset));
+    DISPATCH_DTYPE(dtype, gelu_kernel<T, true><<<grid_for(rows * (d / 16), 256), 256, 0, (cudaStream_t)stream>>>(
+                              (const T *)x, bias, (const T *)gy, (T *)gx, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop), seed,
+                              rng_offset));
     return check_launch("gelu_bwd");
 }
 
