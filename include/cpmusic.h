@@ -274,6 +274,32 @@ int cpm_skinny_linear(const void *A, int64_t lda, const void *W, const void *bia
                       void *xout, int epilogue, const void *residual, int64_t ldr, const float *pe,
                       int pe_max_len, int pos_offset, const int32_t *pos_dev, void *stream);
 
+/* tcgen05 / TMA Linear layer for the rollout token step at any M (256 songs per GPU in the bench), bf16:
+ *     Y[M,N] = epi( LNfold(A)[M,K] . W[N,K]^T )
+ * The LayerNorm of the input is folded algebraically, so no kernel ever materialises a LayerNorm output
+ * (ft RecurrentTransformerEncoderLayer, SURVEY App. A.2: x = norm1(x + attn); y = norm2(x + ffn)):
+ *     LN(a).W^T = rstd_m * ( a.W'^T - mean_m * c1[n] ) + c2[n],  W' = gamma (.) W (bf16, passed as W),
+ *     c1[n] = sum_k W'[n,k],  c2[n] = sum_k beta_k W[n,k] + bias[n]            (fp32, built by the host)
+ *   c1 == NULL: plain  a.W^T + c2  (c2 = bias or NULL).
+ *   stats_in [M][parts_in][2] fp32: per-row partial (sum, sum of squares) of A as written by the producer
+ *   kernel (one partial per N-tile of that producer); mean / rstd are rebuilt from them in a fixed order.
+ *   epilogue CPM_TL_EPI_BIAS | _GELU (exact erf) | _RES (+ R[M,N]) | _RES_LN (+ LayerNorm(R) rebuilt from
+ *   stats_r/gamma_r/beta_r, R = pre-LN sums) | _PE (+ pe[pos,:], pos = pos_offset + (pos_dev ? *pos_dev : 0)).
+ *   stats_out (optional) [M][ceil(N/block_n)][2]: partials of the bf16 values stored in Y.
+ * K % 64 == 0, N % 32 == 0, block_n in {32, 64}; W has w_rows >= N rows of K contiguous bf16.
+ * use_pdl: launch with programmatic stream serialization; the kernel fetches its weight tiles before
+ * griddepcontrol.wait so that only the activation fetch + UMMA + epilogue stay on the critical path. */
+#define CPM_TL_EPI_BIAS 0
+#define CPM_TL_EPI_GELU 1
+#define CPM_TL_EPI_RES 2
+#define CPM_TL_EPI_RES_LN 3
+#define CPM_TL_EPI_PE 4
+int cpm_tc_linear(const void *A, int64_t lda, const void *W, int64_t w_rows, const float *c1, const float *c2,
+                  void *Y, int64_t ldy, int M, int N, int K, int epilogue, const float *stats_in, int parts_in,
+                  float eps, const void *R, int64_t ldr, const float *stats_r, int parts_r, const float *gamma_r,
+                  const float *beta_r, const float *pe, int pe_max, int pos_offset, const int32_t *pos_dev,
+                  float *stats_out, int block_n, int use_pdl, void *stream);
+
 /* Persistent megakernel for ONE recurrent rollout token step (embedding -> all layers -> heads ->
  * sampling -> history/step bookkeeping) as a single cooperative launch: 148 CTAs walk a host-built
  * phase list separated by a software grid barrier (csrc/rollout_mega.cu).  Replaces the ~65-100

@@ -537,3 +537,61 @@ def test_skinny_linear_variants(cuda, cpm, M, N, K):
     _cmp(y, torch.nn.functional.gelu(lin(xout.double())), 2e-2, 2e-2, "LN prologue + gelu")
     with pytest.raises(ValueError):
         ops.skinny_linear(torch.zeros(65, K, device=cuda, dtype=torch.bfloat16), w, b)
+
+
+# ------------------------------------------------------------------ tcgen05 Linear with LayerNorm fold (rollout step)
+def _row_partials(x, width):
+    """(M, parts, 2) fp32 partial (sum, sum of squares) of x's rows over column blocks of `width` (what a producer
+    kernel with N-tiles of `width` columns writes)."""
+    M, N = x.shape
+    xf = x.float().view(M, N // width, width)
+    return torch.stack([xf.sum(-1), (xf * xf).sum(-1)], -1).contiguous()
+
+
+@pytest.mark.parametrize("M,N,K,bn", [(256, 1536, 512, 64), (256, 512, 512, 32), (256, 2048, 512, 64), (256, 512, 2048, 32),
+                                      (256, 512, 1216, 32), (100, 512, 512, 32), (32, 1536, 512, 64), (64, 512, 2048, 64)])
+def test_tc_linear_variants(cuda, cpm, M, N, K, bn):
+    """tcgen05 Linear (bias / GELU / residual / PE epilogues, algebraic LayerNorm fold, on-the-fly LayerNorm residual,
+    row-statistics side output) vs the PyTorch composition in fp64 on the same bf16 inputs.  Tolerance 3e-2 abs +
+    2e-2 rel: bf16 output rounding of O(1-5) values and bf16 rounding of the gamma-scaled weight."""
+    ops = cpm.ops
+    gen = torch.Generator().manual_seed(M + N + K)
+    a = (1.5 * torch.randn(M, K, generator=gen) + 0.3).to(cuda).bfloat16()
+    w = (torch.randn(N, K, generator=gen) / K ** 0.5).to(cuda)
+    b = torch.randn(N, generator=gen).to(cuda)
+    wb = w.bfloat16()
+    ad, wd, bd = a.double(), wb.double(), b.double()
+    lin = ad @ wd.t() + bd
+    for pdl in (False, True):
+        _cmp(ops.tc_linear(a, wb, b, block_n=bn, pdl=pdl), lin, 3e-2, 2e-2, "bias")
+    _cmp(ops.tc_linear(a, wb, None, block_n=bn), ad @ wd.t(), 3e-2, 2e-2, "no bias")
+    _cmp(ops.tc_linear(a, wb, b, epilogue=ops.TL_GELU, block_n=bn), torch.nn.functional.gelu(lin), 3e-2, 2e-2, "gelu")
+    res = torch.randn(M, N, generator=gen).to(cuda).bfloat16()
+    parts = N // bn
+    st = torch.zeros(M, parts, 2, device=cuda)
+    y = ops.tc_linear(a, wb, b, epilogue=ops.TL_RES, residual=res, stats_out=st, block_n=bn)
+    _cmp(y, lin + res.double(), 4e-2, 2e-2, "residual")
+    _cmp(st, _row_partials(y, bn), 2e-2, 1e-3, "row statistics of the stored values")
+    pe = torch.randn(50, N, generator=gen).to(cuda)
+    pos = torch.tensor([11], dtype=torch.int32, device=cuda)
+    _cmp(ops.tc_linear(a, wb, b, epilogue=ops.TL_PE, pe=pe, pos_dev=pos, block_n=bn), lin + pe[11].double(), 4e-2, 2e-2, "pe")
+    # LayerNorm fold: y = LN(a) @ w^T + b computed from the raw a, the gamma-scaled weight and a's row statistics
+    gamma = (1 + 0.2 * torch.randn(K, generator=gen)).to(cuda)
+    beta = (0.2 * torch.randn(K, generator=gen)).to(cuda)
+    wf = (w * gamma[None, :]).bfloat16()
+    c1 = wf.float().sum(1)
+    c2 = w @ beta + b
+    st_a = _row_partials(a, 64)
+    ln = torch.nn.functional.layer_norm(ad, (K,), gamma.double(), beta.double(), 1e-5)
+    y = ops.tc_linear(a, wf, c2, c1=c1, stats_in=st_a, block_n=bn)
+    _cmp(y, ln @ w.double().t() + bd, 4e-2, 2e-2, "LayerNorm fold")
+    y = ops.tc_linear(a, wf, c2, c1=c1, stats_in=st_a, epilogue=ops.TL_GELU, block_n=bn, pdl=True)
+    _cmp(y, torch.nn.functional.gelu(ln @ w.double().t() + bd), 4e-2, 2e-2, "LayerNorm fold + gelu")
+    # residual that is itself a LayerNorm output, rebuilt from the pre-LN sums
+    rs = (1.2 * torch.randn(M, N, generator=gen) - 0.2).to(cuda).bfloat16()
+    g2 = (1 + 0.2 * torch.randn(N, generator=gen)).to(cuda)
+    b2 = (0.2 * torch.randn(N, generator=gen)).to(cuda)
+    y = ops.tc_linear(a, wb, b, epilogue=ops.TL_RES_LN, residual=rs, stats_r=_row_partials(rs, 32), gamma_r=g2, beta_r=b2, block_n=bn)
+    _cmp(y, lin + torch.nn.functional.layer_norm(rs.double(), (N,), g2.double(), b2.double(), 1e-5), 4e-2, 2e-2, "LayerNorm residual")
+    with pytest.raises(ValueError):
+        ops.tc_linear(a, wb[:, :K - 8].contiguous(), b)          # K % 64 != 0 (and mismatched K)
