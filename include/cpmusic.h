@@ -77,6 +77,7 @@ int64_t cpm_linattn_saved_bytes(int N, int L, int H);
 /* Development aid: device buffer (>= 64 int64 per CTA of the chunk-parallel forward kernel) that receives
  * clock64() stamps at its phase boundaries; NULL switches it off (the default). */
 int cpm_debug_linattn_timing(void *device_buffer);
+int cpm_debug_tc_linear_timing(void *device_buffer);    /* 8 int64 per CTA of cpm_tc_linear */
 int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, float *den,
                     int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
                     int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes,
@@ -286,7 +287,9 @@ int cpm_skinny_linear(const void *A, int64_t lda, const void *W, const void *bia
  *   epilogue CPM_TL_EPI_BIAS | _GELU (exact erf) | _RES (+ R[M,N]) | _RES_LN (+ LayerNorm(R) rebuilt from
  *   stats_r/gamma_r/beta_r, R = pre-LN sums) | _PE (+ pe[pos,:], pos = pos_offset + (pos_dev ? *pos_dev : 0)).
  *   stats_out (optional) [M][ceil(N/block_n)][2]: partials of the bf16 values stored in Y.
- * K % 64 == 0, N % 32 == 0, block_n in {32, 64}; W has w_rows >= N rows of K contiguous bf16.
+ * K % 64 == 0, N % 64 == 0, block_n = 64; W has w_rows >= N rows of K contiguous bf16.
+ * split_k in {1,2,4,8}: the K extent of every 128 x block_n tile is split over a thread-block cluster; the
+ *   partial tiles are reduced over distributed shared memory in rank order (deterministic).
  * use_pdl: launch with programmatic stream serialization; the kernel fetches its weight tiles before
  * griddepcontrol.wait so that only the activation fetch + UMMA + epilogue stay on the critical path. */
 #define CPM_TL_EPI_BIAS 0
@@ -298,7 +301,7 @@ int cpm_tc_linear(const void *A, int64_t lda, const void *W, int64_t w_rows, con
                   void *Y, int64_t ldy, int M, int N, int K, int epilogue, const float *stats_in, int parts_in,
                   float eps, const void *R, int64_t ldr, const float *stats_r, int parts_r, const float *gamma_r,
                   const float *beta_r, const float *pe, int pe_max, int pos_offset, const int32_t *pos_dev,
-                  float *stats_out, int block_n, int use_pdl, void *stream);
+                  float *stats_out, int block_n, int split_k, int use_pdl, void *stream);
 
 /* Persistent megakernel for ONE recurrent rollout token step (embedding -> all layers -> heads ->
  * sampling -> history/step bookkeeping) as a single cooperative launch: 148 CTAs walk a host-built

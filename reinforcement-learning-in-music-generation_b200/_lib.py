@@ -37,6 +37,7 @@ SIGNATURES = {
     "cpm_linattn_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "cpm_linattn_saved_bytes": (c_int64, [c_int, c_int, c_int]),
     "cpm_debug_linattn_timing": (c_int, [_P]),
+    "cpm_debug_tc_linear_timing": (c_int, [_P]),
     "cpm_linattn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
                                 c_int, c_float, c_int, _P, c_int64, _P, c_int64, _P]),
     "cpm_linattn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
@@ -44,7 +45,7 @@ SIGNATURES = {
     "cpm_linattn_step": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
                                  c_int, c_float, _P]),
     "cpm_tc_linear": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, c_int64,
-                              _P, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, _P]),
+                              _P, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
     "cpm_embed_fwd": (c_int, [_P, _FPP, _IP, _IP, c_int, c_int64, _P, c_int, _P, _P]),
     "cpm_embed_bwd": (c_int, [_P, _P, _FPP, _IP, _IP, c_int, c_int64, c_int, _P]),
     "cpm_add_pe": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P]),
@@ -84,7 +85,7 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_debug_linattn_timing": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
+    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
     "cpm_linattn_fwd": 3, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2,      # chunk-parallel path: pre-pass, scan, main
 })
 EXTRA_LAUNCHES = [0]          # segment-total / scan kernels of segmented linear attention, graph replays

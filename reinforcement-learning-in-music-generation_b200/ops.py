@@ -708,8 +708,22 @@ def skinny_linear(a, wc, bc, n_out=None, ln=None, xout=None, epilogue=EPI_BIAS, 
 TL_BIAS, TL_GELU, TL_RES, TL_RES_LN, TL_PE = 0, 1, 2, 3, 4
 
 
+def tc_linear_split(M: int, N: int, K: int, block_n: int, target_ctas: int = 160) -> int:
+    """K-split (cluster size) that brings the CTA count near the SM count without dropping below one 64-wide
+    K block per CTA."""
+    import os
+    pol = os.environ.get("CPM_TL_SPLIT", "auto")
+    if pol == "none" or (pol == "k512" and K <= 512):
+        return 1
+    tiles = -(-N // block_n) * -(-M // 128)
+    s = 1
+    while s < 8 and tiles * s * 2 <= target_ctas and (K // 64) // (s * 2) >= 1:
+        s *= 2
+    return s
+
+
 def tc_linear(a, w, c2, n_out=None, c1=None, stats_in=None, eps=EPS_LN, epilogue=TL_BIAS, residual=None, stats_r=None, gamma_r=None,
-              beta_r=None, pe=None, pos_offset=0, pos_dev=None, out=None, stats_out=None, block_n=64, pdl=False):
+              beta_r=None, pe=None, pos_offset=0, pos_dev=None, out=None, stats_out=None, block_n=64, split_k=None, pdl=False):
     """Y = epi(LNfold(a) @ w^T) in ONE tcgen05 launch (no autograd; rollout only).  a (M,K) bf16; w (rows>=N, K) bf16
     (pre-scaled by gamma when c1 is given); c1/c2 (N,) fp32; stats_* (M, parts, 2) fp32 row partials."""
     _cuda(a, w)
@@ -721,9 +735,11 @@ def tc_linear(a, w, c2, n_out=None, c1=None, stats_in=None, eps=EPS_LN, epilogue
     N = w.shape[0] if n_out is None else n_out
     y = out if out is not None else torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
     pe2 = None if pe is None else pe.reshape(-1, pe.shape[-1])
+    if split_k is None:
+        split_k = tc_linear_split(M, N, K, block_n)
     check(_lib.load().cpm_tc_linear(_p(a), a.stride(0), _p(w), w.shape[0], _p(c1), _p(c2), _p(y), y.stride(0), M, N, K, epilogue,
                                     _p(stats_in), 0 if stats_in is None else stats_in.shape[1], eps, _p(residual),
                                     0 if residual is None else residual.stride(0), _p(stats_r), 0 if stats_r is None else stats_r.shape[1],
                                     _p(gamma_r), _p(beta_r), _p(pe2), 0 if pe2 is None else pe2.shape[0], pos_offset, _p(pos_dev),
-                                    _p(stats_out), block_n, 1 if pdl else 0, _st()))
+                                    _p(stats_out), block_n, split_k, 1 if pdl else 0, _st()))
     return y

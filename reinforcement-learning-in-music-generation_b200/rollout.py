@@ -40,7 +40,7 @@ class _MegaGlobals(ctypes.Structure):        # mirrors cpm::MegaGlobals
 class RolloutEngine:
     def __init__(self, model, batch: int, max_steps: int, greedy: bool = False, true_positions: bool = True,
                  temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True,
-                 fused: Optional[bool] = None, mode: Optional[str] = None):
+                 fused: Optional[bool] = None, mode: Optional[str] = None, pdl: bool = False):
         self.model, self.N, self.max_steps = model, batch, max_steps
         self.greedy, self.true_positions = greedy, true_positions
         self.temperature, self.top_p = model.sampling_config(temperature, top_p)
@@ -66,11 +66,15 @@ class RolloutEngine:
             mode = ("fused" if fused else "unfused") if fused is not None else "unfused"
         if mode in ("mega", "fused") and not self.fused_supported():
             raise ValueError("mega / fused rollout steps need bf16 compute, <= 32 sequences and 64-aligned widths <= 2048")
-        if mode not in ("mega", "fused", "unfused"):
+        if mode == "tc" and not self.tc_supported():
+            raise ValueError("the tcgen05 rollout step needs bf16 compute, widths that are multiples of 64 (inputs) / 32 (outputs)")
+        if mode not in ("mega", "fused", "unfused", "tc"):
             raise ValueError(f"unknown rollout mode {mode!r}")
         self.mode = mode
         self.fused = mode == "fused"
+        self.pdl = pdl
         self._mega = None
+        self._tc = None
 
     # ---- logits of the next token for every sequence, given self.cur and the recurrent state -------
     def fused_supported(self) -> bool:
@@ -119,6 +123,90 @@ class RolloutEngine:
         xl = ops.ln_residual(s_prev, None, prev.norm2.weight, prev.norm2.bias, prev.norm2.eps, 0.0)
         wh, bh, _, _ = m._cache.get("heads", m._heads(), dt, 8)
         return ops.skinny_linear(xl, wh, bh, ln=(enc.norm.weight, enc.norm.bias, enc.norm.eps))
+
+    # ---- tcgen05 step: every Linear is one cpm_tc_linear launch, no LayerNorm / GELU / residual kernels ----
+    def tc_supported(self) -> bool:
+        m = self.model
+        ins = (m.d_model, m.d_inner, int(sum(m.emb_sizes)))
+        outs = (m.d_model, 3 * m.d_model, m.d_inner)
+        return m.compute_dtype == torch.bfloat16 and all(w % 64 == 0 for w in ins + outs)
+
+    def _tc_stamp(self):
+        return tuple(p._version for p in self.model.parameters())
+
+    def _tc_refresh(self):
+        """(Re)builds, in place, the bf16 weights with the consumer-side LayerNorm folded in:
+        W' = gamma (.) W,  c1 = rowsum(W'),  c2 = W beta + bias  (include/cpmusic.h, cpm_tc_linear)."""
+        m, enc = self.model, self.model.transformer_encoder
+        stamp = self._tc_stamp()
+        if self._tc is not None and self._tc["stamp"] == stamp:
+            return
+        bf = torch.bfloat16
+        first = self._tc is None
+        packs = {} if first else self._tc["packs"]
+
+        def put(key, w, c1, c2):
+            if first:
+                packs[key] = (w.to(bf).contiguous(), None if c1 is None else c1.float().contiguous(), c2.float().contiguous())
+            else:                                          # same addresses: captured graphs stay valid
+                packs[key][0].copy_(w)
+                if c1 is not None:
+                    packs[key][1].copy_(c1)
+                packs[key][2].copy_(c2)
+
+        def fold(key, linears, norm):
+            w = torch.cat([l.weight for l in linears], 0).float()
+            b = torch.cat([l.bias for l in linears], 0).float()
+            if norm is None:
+                put(key, w, None, b)
+            else:
+                wf = (w * norm.weight.float()[None, :]).to(bf)
+                put(key, wf, wf.float().sum(1), w @ norm.bias.float() + b)
+
+        with torch.no_grad():
+            fold("in", [m.in_linear], None)
+            prev = None
+            for i, layer in enumerate(enc.layers):
+                at = layer.attention
+                fold(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], None if prev is None else prev.norm2)
+                fold(("out", i), [at.out_projection], None)
+                fold(("ff1", i), [layer.linear1], layer.norm1)
+                fold(("ff2", i), [layer.linear2], None)
+                prev = layer
+        self._tc = {"stamp": stamp, "packs": packs}
+
+    def _logits_tc(self):
+        m, enc, N = self.model, self.model.transformer_encoder, self.N
+        dt, H, d, pdl = torch.bfloat16, enc.n_heads, m.d_model, self.pdl
+        P = self._tc["packs"]
+        parts = d // 64
+        emb = ops.cp_embed(self.cur[:, None, :], m._tables(), dt).view(N, -1)
+        w, _, b = P["in"]
+        x0 = ops.tc_linear(emb, w, b, epilogue=ops.TL_PE, pe=m.pos_emb.pe, pos_dev=self.step_dev if self.true_positions else None,
+                           block_n=64, pdl=pdl)
+        s_prev, st_prev, prev = x0, None, None
+        for i, layer in enumerate(enc.layers):
+            w, c1, c2 = P[("qkv", i)]
+            qkv = ops.tc_linear(s_prev, w, c2, c1=c1, stats_in=st_prev, eps=0.0 if prev is None else prev.norm2.eps, block_n=64, pdl=pdl)
+            q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
+            a = ops.linattn_step(q, k, v, self.state[i][0], self.state[i][1]).view(N, H * 64)
+            w, _, c2 = P[("out", i)]
+            st1 = torch.empty(N, parts, 2, dtype=torch.float32, device=a.device)
+            if prev is None:
+                s1 = ops.tc_linear(a, w, c2, epilogue=ops.TL_RES, residual=s_prev, stats_out=st1, block_n=64, pdl=pdl)
+            else:
+                s1 = ops.tc_linear(a, w, c2, epilogue=ops.TL_RES_LN, residual=s_prev, stats_r=st_prev, gamma_r=prev.norm2.weight,
+                                   beta_r=prev.norm2.bias, eps=prev.norm2.eps, stats_out=st1, block_n=64, pdl=pdl)
+            w, c1, c2 = P[("ff1", i)]
+            h = ops.tc_linear(s1, w, c2, c1=c1, stats_in=st1, eps=layer.norm1.eps, epilogue=ops.TL_GELU, block_n=64, pdl=pdl)
+            w, _, c2 = P[("ff2", i)]
+            st2 = torch.empty(N, parts, 2, dtype=torch.float32, device=a.device)
+            s2 = ops.tc_linear(h, w, c2, epilogue=ops.TL_RES_LN, residual=s1, stats_r=st1, gamma_r=layer.norm1.weight, beta_r=layer.norm1.bias,
+                               eps=layer.norm1.eps, stats_out=st2, block_n=64, pdl=pdl)
+            s_prev, st_prev, prev = s2, st2, layer
+        xl = ops.ln_residual(s_prev, None, prev.norm2.weight, prev.norm2.bias, prev.norm2.eps, 0.0)
+        xf = ops.ln_residual(xl, None, enc.norm.weight, enc.norm.bias, enc.norm.eps, 0.0)
+        return m.logits_concat(xf)
 
     # ---- persistent megakernel step -----------------------------------------------------------------
     def _build_mega(self):
@@ -217,7 +305,12 @@ class RolloutEngine:
         m = self.model
         if self.mode == "mega":
             return self._step_mega()
-        lc = self._logits_fused() if self.fused else self._logits_unfused()
+        if self.mode == "tc":
+            if self._tc is None:
+                self._tc_refresh()
+            lc = self._logits_tc()
+        else:
+            lc = self._logits_fused() if self.fused else self._logits_unfused()
         ops.heads_sample(lc, m.seg, self.temperature, self.top_p, greedy=self.greedy, seed=self.seed,
                          seq_base=self.seq_base, step_dev=self.step_dev, tokens_out=self.cur, logp_out=self.logp)
         ops.rollout_advance(self.cur, self.hist_tok, self.logp, self.hist_logp, self.step_dev, self.max_steps)
@@ -263,6 +356,8 @@ class RolloutEngine:
             self._capture()
         self.reset(init_tokens)
         self.model.refresh_packs()          # graph / megakernel read the packed weights by address
+        if self.mode == "tc":
+            self._tc_refresh()
         if mega:
             for _ in range(n_steps):        # one cooperative launch per token step, queued back to back
                 self._step_mega()

@@ -548,8 +548,8 @@ def _row_partials(x, width):
     return torch.stack([xf.sum(-1), (xf * xf).sum(-1)], -1).contiguous()
 
 
-@pytest.mark.parametrize("M,N,K,bn", [(256, 1536, 512, 64), (256, 512, 512, 32), (256, 2048, 512, 64), (256, 512, 2048, 32),
-                                      (256, 512, 1216, 32), (100, 512, 512, 32), (32, 1536, 512, 64), (64, 512, 2048, 64)])
+@pytest.mark.parametrize("M,N,K,bn", [(256, 1536, 512, 64), (256, 512, 512, 64), (256, 2048, 512, 64), (256, 512, 2048, 64),
+                                      (256, 512, 1216, 64), (100, 512, 512, 64), (32, 1536, 512, 64), (64, 128, 128, 64)])
 def test_tc_linear_variants(cuda, cpm, M, N, K, bn):
     """tcgen05 Linear (bias / GELU / residual / PE epilogues, algebraic LayerNorm fold, on-the-fly LayerNorm residual,
     row-statistics side output) vs the PyTorch composition in fp64 on the same bf16 inputs.  Tolerance 3e-2 abs +
@@ -564,14 +564,19 @@ def test_tc_linear_variants(cuda, cpm, M, N, K, bn):
     lin = ad @ wd.t() + bd
     for pdl in (False, True):
         _cmp(ops.tc_linear(a, wb, b, block_n=bn, pdl=pdl), lin, 3e-2, 2e-2, "bias")
+    for sk in (1, 2, 4, 8):                                          # K split over a cluster, reduced through DSMEM
+        y = ops.tc_linear(a, wb, b, block_n=bn, split_k=sk)
+        _cmp(y, lin, 3e-2, 2e-2, f"split_k={sk}")
+        assert torch.equal(y, ops.tc_linear(a, wb, b, block_n=bn, split_k=sk))   # deterministic
     _cmp(ops.tc_linear(a, wb, None, block_n=bn), ad @ wd.t(), 3e-2, 2e-2, "no bias")
     _cmp(ops.tc_linear(a, wb, b, epilogue=ops.TL_GELU, block_n=bn), torch.nn.functional.gelu(lin), 3e-2, 2e-2, "gelu")
     res = torch.randn(M, N, generator=gen).to(cuda).bfloat16()
     parts = N // bn
     st = torch.zeros(M, parts, 2, device=cuda)
-    y = ops.tc_linear(a, wb, b, epilogue=ops.TL_RES, residual=res, stats_out=st, block_n=bn)
-    _cmp(y, lin + res.double(), 4e-2, 2e-2, "residual")
-    _cmp(st, _row_partials(y, bn), 2e-2, 1e-3, "row statistics of the stored values")
+    for sk in (None, 1, 8):
+        y = ops.tc_linear(a, wb, b, epilogue=ops.TL_RES, residual=res, stats_out=st, block_n=bn, split_k=sk)
+        _cmp(y, lin + res.double(), 4e-2, 2e-2, "residual")
+        _cmp(st, _row_partials(y, bn), 2e-2, 1e-3, "row statistics of the stored values")
     pe = torch.randn(50, N, generator=gen).to(cuda)
     pos = torch.tensor([11], dtype=torch.int32, device=cuda)
     _cmp(ops.tc_linear(a, wb, b, epilogue=ops.TL_PE, pe=pe, pos_dev=pos, block_n=bn), lin + pe[11].double(), 4e-2, 2e-2, "pe")
@@ -591,7 +596,7 @@ def test_tc_linear_variants(cuda, cpm, M, N, K, bn):
     rs = (1.2 * torch.randn(M, N, generator=gen) - 0.2).to(cuda).bfloat16()
     g2 = (1 + 0.2 * torch.randn(N, generator=gen)).to(cuda)
     b2 = (0.2 * torch.randn(N, generator=gen)).to(cuda)
-    y = ops.tc_linear(a, wb, b, epilogue=ops.TL_RES_LN, residual=rs, stats_r=_row_partials(rs, 32), gamma_r=g2, beta_r=b2, block_n=bn)
+    y = ops.tc_linear(a, wb, b, epilogue=ops.TL_RES_LN, residual=rs, stats_r=_row_partials(rs, 64), gamma_r=g2, beta_r=b2, block_n=bn)
     _cmp(y, lin + torch.nn.functional.layer_norm(rs.double(), (N,), g2.double(), b2.double(), 1e-5), 4e-2, 2e-2, "LayerNorm residual")
     with pytest.raises(ValueError):
         ops.tc_linear(a, wb[:, :K - 8].contiguous(), b)          # K % 64 != 0 (and mismatched K)

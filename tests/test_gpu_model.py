@@ -314,6 +314,50 @@ def test_rollout_fused_step_matches_unfused_and_oracle(cuda, cpm, golden):
     assert torch.equal(a, b)
 
 
+@pytest.mark.parametrize("pdl", [False, True])
+def test_rollout_tc_step_matches_unfused_and_oracle(cuda, cpm, golden, pdl):
+    """The tcgen05 rollout step (every Linear one cpm_tc_linear launch; LayerNorms folded algebraically into the
+    consumer GEMM, LayerNorm residuals rebuilt on the fly, optionally chained with programmatic dependent launch)
+    against the unfused kernel path and the fp64 oracle recurrence, step by step on the same token stream.
+    bf16: logits within 6e-2 of the oracle, tc vs unfused within 5e-2."""
+    g = golden("model_small")
+    m = _load_small(cpm, g, cuda, dtype=torch.bfloat16).eval()
+    o = mo.OracleCPModel(VOCAB, is_training=False, **SMALL).double().eval()
+    o.load_state_dict({k[4:]: torch.from_numpy(g[k]).double() for k in g.files if k.startswith("sd::")}, strict=False)
+    N, T = 4, 10
+    x = torch.from_numpy(g["x"])[:1, :T].expand(N, T, 6).contiguous()
+    et = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="tc", pdl=pdl)
+    eu = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="unfused")
+    et.reset(x[:, 0].to(cuda))
+    eu.reset(x[:, 0].to(cuda))
+    et._tc_refresh()
+    mem = None
+    with torch.no_grad():
+        for t in range(T):
+            et.cur.copy_(x[:, t].to(cuda))
+            eu.cur.copy_(x[:, t].to(cuda))
+            et.step_dev.fill_(t)
+            eu.step_dev.fill_(t)
+            lt, lu = et._logits_tc(), eu._logits_unfused()
+            h, mem = o.forward_hidden(x[:1, t:t + 1], mem, is_training=False, pos_offset=t)
+            ref = torch.cat(o.forward_output(h), -1)[0]
+            _cmp(lt[0, :339], ref, 6e-2, 3e-2, f"tc vs oracle step {t}")
+            _cmp(lt[:, :339], lu[:, :339].float(), 5e-2, 2e-2, f"tc vs unfused step {t}")
+    # graph-captured generation == eager generation, and the graph sees in-place parameter updates
+    init = x[:, 0].to(cuda)
+    eg = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=True, mode="tc", pdl=pdl)
+    a = eg.generate(init)["tokens"]
+    b = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="tc", pdl=pdl).generate(init)["tokens"]
+    assert torch.equal(a, b)
+    assert torch.equal(eg.generate(init)["tokens"], a)
+    with torch.no_grad():
+        for p in m.parameters():
+            p.add_(0.05 * torch.randn_like(p))
+    after = eg.generate(init)["tokens"]
+    fresh = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="tc", pdl=pdl).generate(init)["tokens"]
+    assert torch.equal(after, fresh) and not torch.equal(after, a)
+
+
 def test_rollout_megakernel_matches_unfused_and_oracle(cuda, cpm, golden):
     """The persistent cooperative megakernel (one launch per token step) against the unfused kernel
     path and the fp64 oracle recurrence, teacher-forced step by step; then free-running generation:

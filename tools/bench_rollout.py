@@ -13,18 +13,21 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--songs", type=int, default=256)
     ap.add_argument("--steps", type=int, default=256)
-    ap.add_argument("--configs", nargs="+", default=["1x1", "2x1", "4x1", "8x1", "4x4", "8x4"])
+    ap.add_argument("--configs", nargs="+", default=["1x1"], help="groups x steps_per_graph")
+    ap.add_argument("--modes", nargs="+", default=["unfused", "tc", "tc+pdl"])
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     torch.manual_seed(0)
     actor = cpmusic.LinearTransformer(VOCAB, dropout=0.1).to(dev)
     init = torch.stack([torch.randint(0, n, (args.songs,)) for n in VOCAB], -1).to(dev)
-    for cfg in args.configs:
+    for cfg in [(c, md) for c in args.configs for md in args.modes]:
+        cfg, md = cfg
         g, spg = (int(x) for x in cfg.split("x"))
+        kw = dict(mode=md.split("+")[0], pdl=md.endswith("+pdl"))
         if g == 1:
-            eng = cpmusic.RolloutEngine(actor, args.songs, args.steps, greedy=False, seed=1)
+            eng = cpmusic.RolloutEngine(actor, args.songs, args.steps, greedy=False, seed=1, **kw)
         else:
-            eng = cpmusic.GroupedRolloutEngine(actor, args.songs, args.steps, groups=g, steps_per_graph=spg, greedy=False, seed=1)
+            eng = cpmusic.GroupedRolloutEngine(actor, args.songs, args.steps, groups=g, steps_per_graph=spg, greedy=False, seed=1, **kw)
         eng.generate(init)
         torch.cuda.synchronize()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -33,7 +36,7 @@ def main():
         b.record()
         torch.cuda.synchronize()
         ms = a.elapsed_time(b)
-        print(json.dumps({"groups": g, "steps_per_graph": spg, "songs": args.songs, "us_per_token_step": round(ms * 1e3 / args.steps, 1),
+        print(json.dumps({"mode": md, "groups": g, "steps_per_graph": spg, "songs": args.songs, "us_per_token_step": round(ms * 1e3 / args.steps, 1),
                           "tokens_per_s": round(args.songs * args.steps / ms * 1e3)}), flush=True)
         del eng
 

@@ -8,16 +8,17 @@ import torch
 import cpmusic
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--mode", default="mega", choices=["mega", "fused", "unfused"])
+ap.add_argument("--mode", default="mega", choices=["mega", "fused", "unfused", "tc"])
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--batch", type=int, default=32)
+ap.add_argument("--pdl", action="store_true")
 args = ap.parse_args()
 VOCAB = [56, 135, 18, 87, 18, 25]
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
 m = cpmusic.LinearTransformer(VOCAB).to(dev).eval()
-eng = cpmusic.RolloutEngine(m, args.batch, max(args.steps, 64), greedy=False, use_graph=args.graph, mode=args.mode)
+eng = cpmusic.RolloutEngine(m, args.batch, max(args.steps, 64), greedy=False, use_graph=args.graph, mode=args.mode, pdl=args.pdl)
 init = torch.stack([torch.randint(0, n, (args.batch,)) for n in VOCAB], -1).to(dev)
 eng.generate(init, args.steps)
 torch.cuda.synchronize()
