@@ -414,6 +414,7 @@ def main():
         run_reference(args, rank)
         return
     if world > 1:
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line (NCCL prints its version there)
         import cpmusic
         cpmusic.dist.init_from_env("nccl")
     run_gpu(args, rank, world)

@@ -303,6 +303,25 @@ int cpm_tc_linear(const void *A, int64_t lda, const void *W, int64_t w_rows, con
                   const float *beta_r, const float *pe, int pe_max, int pos_offset, const int32_t *pos_dev,
                   float *stats_out, int block_n, int split_k, int use_pdl, void *stream);
 
+/* Rollout token step without LayerNorm launches (csrc/rollout_fold.cu).  The post-norm LayerNorms of ft's
+ * RecurrentTransformerEncoderLayer are folded into their consumers: the library GEMM runs on the
+ * raw pre-LayerNorm sums with W' = gamma (.) W and no bias, and
+ *   cpm_linattn_step_fold  applies  q,k,v = rstd*(raw - mean*c1) + c2  on load, performs the recurrent step of
+ *                          cpm_linattn_step, and writes xres = LayerNorm(s_prev) + bias_next (the accumulate-into
+ *                          operand of the out-projection GEMM, beta = 1).  fold = 0: s_prev is the plain layer input
+ *                          (first layer), q,k,v = raw + c2, xres = s_prev + bias_next.
+ *   cpm_gelu_fold          writes h = gelu(rstd*(raw - mean*c1) + c2) (exact erf) and xres = LayerNorm(s) + bias_next
+ *                          (accumulate-into operand of linear2).
+ * c1[n] = sum_k W'[n,k], c2[n] = sum_k beta_k W[n,k] + bias[n] (fp32, host-built); mean / rstd are recomputed from the
+ * bf16 row by every CTA that needs them.  bf16 activations; d = 64*H <= 2048. */
+int cpm_linattn_step_fold(const void *raw_qkv, const void *s_prev, const float *c1, const float *c2,
+                          const float *gamma, const float *beta, const float *bias_next, float *S, float *Z,
+                          void *out, void *xres, int N, int H, int d, int fold, float eps_ln, float eps_attn,
+                          void *stream);
+int cpm_gelu_fold(const void *raw, const void *s, const float *c1, const float *c2, const float *gamma,
+                  const float *beta, const float *bias_next, void *h, void *xres, int N, int d, int dff, float eps,
+                  void *stream);
+
 /* Persistent megakernel for ONE recurrent rollout token step (embedding -> all layers -> heads ->
  * sampling -> history/step bookkeeping) as a single cooperative launch: 148 CTAs walk a host-built
  * phase list separated by a software grid barrier (csrc/rollout_mega.cu).  Replaces the ~65-100

@@ -743,3 +743,31 @@ def tc_linear(a, w, c2, n_out=None, c1=None, stats_in=None, eps=EPS_LN, epilogue
                                     _p(gamma_r), _p(beta_r), _p(pe2), 0 if pe2 is None else pe2.shape[0], pos_offset, _p(pos_dev),
                                     _p(stats_out), block_n, split_k, 1 if pdl else 0, _st()))
     return y
+
+
+# --------------------------------------------------------------------------- rollout step with folded LayerNorms
+def linattn_step_fold(raw_qkv, s_prev, c1, c2, gamma, beta, bias_next, S, Z, n_heads, fold=True, eps_ln=EPS_LN, eps_attn=EPS_ATTN):
+    """Recurrent step on the RAW output of the QKV GEMM (s_prev @ W'^T, no bias): applies the LayerNorm fold to q,k,v,
+    updates S / Z in place and returns (attention output (N, H*64), xres = LayerNorm(s_prev) + bias_next)."""
+    _cuda(raw_qkv, s_prev, S, Z)
+    N, d = s_prev.shape
+    if raw_qkv.dtype != torch.bfloat16 or s_prev.dtype != torch.bfloat16 or not raw_qkv.is_contiguous() or not s_prev.is_contiguous():
+        raise ValueError("linattn_step_fold needs contiguous bf16 activations")
+    if S.shape[0] != N:
+        raise ValueError("The batch size changed during iteration")
+    out = torch.empty(N, d, dtype=torch.bfloat16, device=s_prev.device)
+    xres = torch.empty(N, d, dtype=torch.bfloat16, device=s_prev.device)
+    check(_lib.load().cpm_linattn_step_fold(_p(raw_qkv), _p(s_prev), _p(c1), _p(c2), _p(gamma), _p(beta), _p(bias_next), _p(S), _p(Z),
+                                            _p(out), _p(xres), N, n_heads, d, 1 if fold else 0, eps_ln, eps_attn, _st()))
+    return out, xres
+
+
+def gelu_fold(raw, s, c1, c2, gamma, beta, bias_next, eps=EPS_LN):
+    """h = gelu(LNfold(raw)), xres = LayerNorm(s) + bias_next (see include/cpmusic.h)."""
+    _cuda(raw, s)
+    N, dff = raw.shape
+    d = s.shape[1]
+    h = torch.empty_like(raw)
+    xres = torch.empty_like(s)
+    check(_lib.load().cpm_gelu_fold(_p(raw), _p(s), _p(c1), _p(c2), _p(gamma), _p(beta), _p(bias_next), _p(h), _p(xres), N, d, dff, eps, _st()))
+    return h, xres

@@ -66,9 +66,9 @@ class RolloutEngine:
             mode = ("fused" if fused else "unfused") if fused is not None else "unfused"
         if mode in ("mega", "fused") and not self.fused_supported():
             raise ValueError("mega / fused rollout steps need bf16 compute, <= 32 sequences and 64-aligned widths <= 2048")
-        if mode == "tc" and not self.tc_supported():
+        if mode in ("tc", "fold") and not self.tc_supported():
             raise ValueError("the tcgen05 rollout step needs bf16 compute, widths that are multiples of 64 (inputs) / 32 (outputs)")
-        if mode not in ("mega", "fused", "unfused", "tc"):
+        if mode not in ("mega", "fused", "unfused", "tc", "fold"):
             raise ValueError(f"unknown rollout mode {mode!r}")
         self.mode = mode
         self.fused = mode == "fused"
@@ -208,6 +208,30 @@ class RolloutEngine:
         xf = ops.ln_residual(xl, None, enc.norm.weight, enc.norm.bias, enc.norm.eps, 0.0)
         return m.logits_concat(xf)
 
+    # ---- "fold" step: library GEMMs on raw pre-LayerNorm sums, no LayerNorm launches (csrc/rollout_fold.cu) ----
+    def _logits_fold(self):
+        m, enc, N = self.model, self.model.transformer_encoder, self.N
+        H = enc.n_heads
+        P = self._tc["packs"]
+        x0 = m._embed(self.cur[:, None, :], 0, self.step_dev if self.true_positions else None).view(N, m.d_model)
+        s_prev, prev = x0, None
+        for i, layer in enumerate(enc.layers):
+            w, c1, c2 = P[("qkv", i)]
+            raw = s_prev @ w.t()
+            bo = P[("out", i)][2]
+            a, xres = ops.linattn_step_fold(raw, s_prev, c1, c2, None if prev is None else prev.norm2.weight,
+                                            None if prev is None else prev.norm2.bias, bo, self.state[i][0], self.state[i][1], H,
+                                            fold=prev is not None, eps_ln=0.0 if prev is None else prev.norm2.eps)
+            s1 = torch.addmm(xres, a, P[("out", i)][0].t())
+            w, c1, c2 = P[("ff1", i)]
+            rawh = s1 @ w.t()
+            h, xres2 = ops.gelu_fold(rawh, s1, c1, c2, layer.norm1.weight, layer.norm1.bias, P[("ff2", i)][2], layer.norm1.eps)
+            s_prev = torch.addmm(xres2, h, P[("ff2", i)][0].t())
+            prev = layer
+        xl = ops.ln_residual(s_prev, None, prev.norm2.weight, prev.norm2.bias, prev.norm2.eps, 0.0)
+        xf = ops.ln_residual(xl, None, enc.norm.weight, enc.norm.bias, enc.norm.eps, 0.0)
+        return m.logits_concat(xf)
+
     # ---- persistent megakernel step -----------------------------------------------------------------
     def _build_mega(self):
         m, enc, N = self.model, self.model.transformer_encoder, self.N
@@ -305,10 +329,10 @@ class RolloutEngine:
         m = self.model
         if self.mode == "mega":
             return self._step_mega()
-        if self.mode == "tc":
+        if self.mode in ("tc", "fold"):
             if self._tc is None:
                 self._tc_refresh()
-            lc = self._logits_tc()
+            lc = self._logits_tc() if self.mode == "tc" else self._logits_fold()
         else:
             lc = self._logits_fused() if self.fused else self._logits_unfused()
         ops.heads_sample(lc, m.seg, self.temperature, self.top_p, greedy=self.greedy, seed=self.seed,
@@ -356,7 +380,7 @@ class RolloutEngine:
             self._capture()
         self.reset(init_tokens)
         self.model.refresh_packs()          # graph / megakernel read the packed weights by address
-        if self.mode == "tc":
+        if self.mode in ("tc", "fold"):
             self._tc_refresh()
         if mega:
             for _ in range(n_steps):        # one cooperative launch per token step, queued back to back

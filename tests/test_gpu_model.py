@@ -314,8 +314,8 @@ def test_rollout_fused_step_matches_unfused_and_oracle(cuda, cpm, golden):
     assert torch.equal(a, b)
 
 
-@pytest.mark.parametrize("pdl", [False, True])
-def test_rollout_tc_step_matches_unfused_and_oracle(cuda, cpm, golden, pdl):
+@pytest.mark.parametrize("mode,pdl", [("tc", False), ("tc", True), ("fold", False)])
+def test_rollout_tc_step_matches_unfused_and_oracle(cuda, cpm, golden, mode, pdl):
     """The tcgen05 rollout step (every Linear one cpm_tc_linear launch; LayerNorms folded algebraically into the
     consumer GEMM, LayerNorm residuals rebuilt on the fly, optionally chained with programmatic dependent launch)
     against the unfused kernel path and the fp64 oracle recurrence, step by step on the same token stream.
@@ -326,7 +326,7 @@ def test_rollout_tc_step_matches_unfused_and_oracle(cuda, cpm, golden, pdl):
     o.load_state_dict({k[4:]: torch.from_numpy(g[k]).double() for k in g.files if k.startswith("sd::")}, strict=False)
     N, T = 4, 10
     x = torch.from_numpy(g["x"])[:1, :T].expand(N, T, 6).contiguous()
-    et = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="tc", pdl=pdl)
+    et = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode=mode, pdl=pdl)
     eu = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="unfused")
     et.reset(x[:, 0].to(cuda))
     eu.reset(x[:, 0].to(cuda))
@@ -338,23 +338,23 @@ def test_rollout_tc_step_matches_unfused_and_oracle(cuda, cpm, golden, pdl):
             eu.cur.copy_(x[:, t].to(cuda))
             et.step_dev.fill_(t)
             eu.step_dev.fill_(t)
-            lt, lu = et._logits_tc(), eu._logits_unfused()
+            lt, lu = (et._logits_tc() if mode == "tc" else et._logits_fold()), eu._logits_unfused()
             h, mem = o.forward_hidden(x[:1, t:t + 1], mem, is_training=False, pos_offset=t)
             ref = torch.cat(o.forward_output(h), -1)[0]
             _cmp(lt[0, :339], ref, 6e-2, 3e-2, f"tc vs oracle step {t}")
             _cmp(lt[:, :339], lu[:, :339].float(), 5e-2, 2e-2, f"tc vs unfused step {t}")
     # graph-captured generation == eager generation, and the graph sees in-place parameter updates
     init = x[:, 0].to(cuda)
-    eg = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=True, mode="tc", pdl=pdl)
+    eg = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=True, mode=mode, pdl=pdl)
     a = eg.generate(init)["tokens"]
-    b = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="tc", pdl=pdl).generate(init)["tokens"]
+    b = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode=mode, pdl=pdl).generate(init)["tokens"]
     assert torch.equal(a, b)
     assert torch.equal(eg.generate(init)["tokens"], a)
     with torch.no_grad():
         for p in m.parameters():
             p.add_(0.05 * torch.randn_like(p))
     after = eg.generate(init)["tokens"]
-    fresh = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="tc", pdl=pdl).generate(init)["tokens"]
+    fresh = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode=mode, pdl=pdl).generate(init)["tokens"]
     assert torch.equal(after, fresh) and not torch.equal(after, a)
 
 

@@ -8,7 +8,7 @@ import torch
 import cpmusic
 
 ap = argparse.ArgumentParser()
-ap.add_argument("--mode", default="mega", choices=["mega", "fused", "unfused", "tc"])
+ap.add_argument("--mode", default="mega", choices=["mega", "fused", "unfused", "tc", "fold"])
 ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--batch", type=int, default=32)
