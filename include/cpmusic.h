@@ -98,6 +98,17 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
                      int N, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
                      int dtype, float eps, void *stream);
 
+/* B1, deferred write-back (rollout engine only).  Same arithmetic, bit-identical outputs: the rank-1 updates of the
+ * last (*step_dev % CPM_LAZY_STATE_PERIOD) tokens live in `ring` ((N,H,PERIOD,128) fp32: [Kf | v] per entry) and are
+ * re-applied in registers every step; S is written back only when the ring fills, so a token step moves
+ * 16 KB + 16 KB/PERIOD (+ ring) per (sequence, head) instead of 32 KB.  Z is updated every step.
+ * flush_only != 0: apply the pending entries and write S (no q/k/v/out needed) — call before anyone reads S while
+ * *step_dev % PERIOD != 0.  *step_dev must advance by one per token (cpm_rollout_advance does). */
+#define CPM_LAZY_STATE_PERIOD 8
+int cpm_linattn_step_lazy(const void *q, const void *k, const void *v, float *S, float *Z, float *ring, void *out,
+                          int N, int H, int64_t ld_qkv, int64_t ld_o, int dtype, float eps,
+                          const int32_t *step_dev, int flush_only, void *stream);
+
 /* ------------------------------------------------------------------------------------------
  * C1 — CP embedding gather + sqrt(emb) scale + concat.  Replaces `Embeddings.forward` x6 and
  * `torch.cat` (agent_pretrain.py:185-192,320-335; dqn_policy/model.py:206-221).

@@ -101,6 +101,108 @@ __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__
         out[(int64_t)n * ld_o + h * 64 + tid] = from_f<T>(o / d);
     }
 }
+
+// ------------------------------------------------------------------------------------------
+// B1 (lazy): the same step with the state write-back deferred.  The rank-1 updates of the last p = step % C tokens
+// are kept in a small ring (C x [Kf | v] fp32 per (sequence, head)); every step rebuilds S_eff = S + sum_j Kf_j (x) v_j
+// in registers in the original order (bit-identical to the eager kernel), and only every C-th step writes S back.
+// HBM traffic per (sequence, head, step): 16 KB read + 16 KB / C written + <= C x 512 B of ring, instead of 32 KB.
+// ------------------------------------------------------------------------------------------
+template <typename T, int C>
+__global__ void __launch_bounds__(256) linattn_step_lazy_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v,
+                                                                   float *__restrict__ S, float *__restrict__ Z, float *__restrict__ ring,
+                                                                   T *__restrict__ out, const int *__restrict__ step_dev, int flush_only, int H,
+                                                                   int64_t ld_qkv, int64_t ld_o, float eps) {
+    __shared__ float part[8][68];
+    __shared__ __align__(16) float spend[C][128];        // pending [Kf | v] entries, the newest last
+    const int nh = blockIdx.x, n = nh / H, h = nh % H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e = tid >> 2, m0 = (tid & 3) * 16;
+    // Every load is issued up front and unconditionally (the whole ring, not just the p live entries), so that the
+    // device-side step counter does not add a dependent memory round trip in front of them.
+    float *srow = S + (int64_t)nh * 4096 + e * 64 + m0;
+    float4 s[4];
+    {
+        const F8 lo = ld_stream(srow), hi = ld_stream(srow + 8);
+        s[0] = lo.a; s[1] = lo.b; s[2] = hi.a; s[3] = hi.b;
+    }
+    float *rg = ring + (int64_t)nh * C * 128;
+    float tmp[C / 2];
+#pragma unroll
+    for (int it = 0; it < C / 2; ++it) tmp[it] = rg[tid + 256 * it];
+    const int64_t qoff = (int64_t)n * ld_qkv + h * 64;
+    float newv = 0.f, qraw = 0.f, zold = 0.f;
+    float *zp = Z + (int64_t)nh * 64 + e;
+    if (!flush_only) {
+        if (tid < 64) newv = to_f(k[qoff + tid]);
+        else if (tid < 128) newv = to_f(v[qoff + tid - 64]);
+        qraw = to_f(q[qoff + e]);
+        if ((tid & 3) == 0) zold = *zp;
+    }
+    const int p = *step_dev % C;                          // pending entries already in the ring
+    if (flush_only && p == 0) return;
+#pragma unroll
+    for (int it = 0; it < C / 2; ++it) { const int i = tid + 256 * it; if (i < p * 128) spend[i >> 7][i & 127] = tmp[it]; }
+    int np = p;                                           // entries to apply
+    float qe = 0.f;
+    if (!flush_only) {
+        if (tid < 128) {
+            const float x = tid < 64 ? phi(newv) : newv;
+            spend[p][tid] = x;
+            if (p + 1 < C) rg[p * 128 + tid] = x;         // keep it for the following steps (not needed when flushing now)
+        }
+        qe = phi(qraw);
+        np = p + 1;
+    }
+    __syncthreads();
+    float dpart = 0.f;
+    if (!flush_only && (tid & 3) == 0) {                  // normaliser: Z += Kf (every step); den = Qf.Z + eps
+        const float zn = zold + spend[p][e];
+        *zp = zn;
+        dpart = qe * zn;
+    }
+    for (int j = 0; j < np; ++j) {                        // oldest first: the eager kernel's summation order
+        const float ke = spend[j][e];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const float4 vv = *reinterpret_cast<const float4 *>(&spend[j][64 + m0 + 4 * i]);
+            s[i].x = fmaf(ke, vv.x, s[i].x); s[i].y = fmaf(ke, vv.y, s[i].y);
+            s[i].z = fmaf(ke, vv.z, s[i].z); s[i].w = fmaf(ke, vv.w, s[i].w);
+        }
+    }
+    if (flush_only || np == C) {                          // write the state back once per C steps
+        F8 lo, hi; lo.a = s[0]; lo.b = s[1]; hi.a = s[2]; hi.b = s[3];
+        st_stream(srow, lo); st_stream(srow + 8, hi);
+    }
+    if (flush_only) return;
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc[4 * i + 0] = qe * s[i].x; acc[4 * i + 1] = qe * s[i].y;
+        acc[4 * i + 2] = qe * s[i].z; acc[4 * i + 3] = qe * s[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 4);
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 8);
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 16);
+    if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part[warp][lane * 16 + i] = acc[i];
+        if (lane == 0) part[warp][64] = dpart;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float o = 0.f, d = eps;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { o += part[w][tid]; d += part[w][64]; }
+        out[(int64_t)n * ld_o + h * 64 + tid] = from_f<T>(o / d);
+    }
+}
 }  // namespace
 }  // namespace cpm
 
@@ -223,6 +325,26 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
     else
         return fail(CPM_ERR_BAD_DTYPE, "linattn_step: dtype %d", dtype);
     return check_launch("linattn_step");
+}
+
+int cpm_linattn_step_lazy(const void *q, const void *k, const void *v, float *S, float *Z, float *ring, void *out, int N, int H,
+                          int64_t ld_qkv, int64_t ld_o, int dtype, float eps, const int32_t *step_dev, int flush_only, void *stream) {
+    CPM_REQUIRE(S && Z && ring && step_dev && (flush_only || (q && k && v && out)), CPM_ERR_NULL, "linattn_step_lazy: NULL pointer");
+    CPM_REQUIRE(N > 0 && H > 0, CPM_ERR_BAD_SHAPE, "linattn_step_lazy: N=%d H=%d", N, H);
+    CPM_REQUIRE(flush_only || (ld_qkv >= (int64_t)H * 64 && ld_o >= (int64_t)H * 64), CPM_ERR_BAD_SHAPE, "linattn_step_lazy: strides");
+    CPM_REQUIRE(aligned16(S) && aligned16(ring), CPM_ERR_BAD_ALIGN, "linattn_step_lazy: S / ring must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    constexpr int C = CPM_LAZY_STATE_PERIOD;
+    if (dtype == CPM_F32)
+        linattn_step_lazy_kernel<float, C><<<N * H, 256, 0, st>>>((const float *)q, (const float *)k, (const float *)v, S, Z, ring, (float *)out,
+                                                                  step_dev, flush_only, H, ld_qkv, ld_o, eps);
+    else if (dtype == CPM_BF16)
+        linattn_step_lazy_kernel<__nv_bfloat16, C><<<N * H, 256, 0, st>>>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k,
+                                                                          (const __nv_bfloat16 *)v, S, Z, ring, (__nv_bfloat16 *)out, step_dev,
+                                                                          flush_only, H, ld_qkv, ld_o, eps);
+    else
+        return fail(CPM_ERR_BAD_DTYPE, "linattn_step_lazy: dtype %d", dtype);
+    return check_launch("linattn_step_lazy");
 }
 
 }  // extern "C"

@@ -184,7 +184,10 @@ class TransformerEncoder(nn.Module):
         qkv = cached_linear(c, ("qkv", i), [at.query_projection, at.key_projection, at.value_projection], x, dt)
         N = qkv.shape[0]
         q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
-        a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * 64)
+        if len(st) > 2:          # rollout engine: [S, Z, ring, step_dev] -> deferred state write-back
+            a = ops.linattn_step_lazy(q, k, v, st[0], st[1], st[2], st[3]).view(N, H * 64)
+        else:
+            a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * 64)
         o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
         x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
         h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)

@@ -237,6 +237,34 @@ def linattn_step(q, k, v, S, Z, eps=EPS_ATTN):
     return out
 
 
+LAZY_STATE_PERIOD = 8      # CPM_LAZY_STATE_PERIOD
+
+
+def linattn_step_lazy(q, k, v, S, Z, ring, step_dev, eps=EPS_ATTN):
+    """Recurrent step with deferred state write-back (include/cpmusic.h, cpm_linattn_step_lazy): same outputs as
+    linattn_step bit for bit; S is current only when *step_dev % LAZY_STATE_PERIOD == 0 or after linattn_state_flush."""
+    _cuda(q, k, v, S, Z, ring)
+    N, H, E = q.shape
+    ld = q.stride(0)
+    if not (k.stride(0) == ld and v.stride(0) == ld and q.stride(2) == 1 and q.stride(1) == E):
+        raise ValueError("q,k,v must be (N,H,E) with a common row stride and packed heads")
+    if S.shape[0] != N:
+        raise ValueError("The batch size changed during iteration")
+    if ring.shape != (N, H, LAZY_STATE_PERIOD, 128) or ring.dtype != torch.float32 or not ring.is_contiguous():
+        raise ValueError(f"ring must be contiguous float32 (N,H,{LAZY_STATE_PERIOD},128)")
+    out = torch.empty(N, H, E, dtype=q.dtype, device=q.device)
+    check(_lib.load().cpm_linattn_step_lazy(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(ring), _p(out), N, H, ld, H * E, _dt(q), eps,
+                                            _p(step_dev), 0, _st()))
+    return out
+
+
+def linattn_state_flush(S, Z, ring, step_dev):
+    """Applies the pending ring entries to S (no-op when *step_dev % LAZY_STATE_PERIOD == 0)."""
+    N, H = S.shape[0], S.shape[1]
+    check(_lib.load().cpm_linattn_step_lazy(None, None, None, _p(S), _p(Z), _p(ring), None, N, H, 0, 0, _lib.BF16, EPS_ATTN,
+                                            _p(step_dev), 1, _st()))
+
+
 # --------------------------------------------------------------------------- dense linear (vendor GEMM)
 def _mm_f32_out(a, b):
     """a @ b with fp32 output (bf16 inputs accumulate in fp32 inside cuBLAS either way)."""

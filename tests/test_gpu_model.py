@@ -143,6 +143,25 @@ def test_rollout_engine_graph_equals_eager_equals_teacher_forced(cuda, cpm, gold
     assert not torch.equal(full, other)
 
 
+@pytest.mark.parametrize("T", [16, 27])
+def test_lazy_state_rollout_is_bit_identical(cuda, cpm, golden, T):
+    """Deferred state write-back (S written once per 8 tokens, pending rank-1 updates re-applied in registers in the
+    original order) generates bit-identical tokens, log-probs AND final recurrent state to the eager step kernel —
+    graph replay and eager stepping, sampled decoding, T a multiple of the period or not."""
+    g = golden("model_small")
+    mr = _load_small(cpm, g, cuda, dtype=torch.bfloat16, is_training=False).eval()
+    N = 5
+    init = torch.stack([torch.randint(0, n, (N,), generator=torch.Generator().manual_seed(3)) for n in VOCAB], -1).to(cuda)
+    ref_e = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=False)
+    ref = ref_e.generate(init)
+    for use_graph in (False, True):
+        eng = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=use_graph, lazy_state=True)
+        for _ in range(2):
+            out = eng.generate(init)
+            assert torch.equal(out["tokens"], ref["tokens"]) and torch.equal(out["logp"], ref["logp"])
+            assert torch.equal(eng.S, ref_e.S) and torch.equal(eng.Z, ref_e.Z)
+
+
 @pytest.mark.parametrize("groups,spg", [(2, 1), (3, 4)])
 def test_grouped_rollout_equals_ungrouped(cuda, cpm, golden, groups, spg):
     """The multi-stream grouped engine (parallel graph branches, `spg` token steps per graph) generates

@@ -1,0 +1,24 @@
+import sys; sys.path.insert(0, "/root/repo")
+import torch, cpmusic
+from cpmusic import ops
+dev = torch.device("cuda:0")
+N, H, layers = 256, 8, 12
+S = torch.zeros(layers, N, H, 64, 64, device=dev); Z = torch.zeros(layers, N, H, 64, device=dev)
+ring = torch.zeros(layers, N, H, 8, 128, device=dev)
+qkv = torch.randn(N, 1536, device=dev).bfloat16()
+q, k, v = (qkv[:, j * 512:(j + 1) * 512].unflatten(-1, (H, 64)) for j in range(3))
+flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+step = torch.zeros(1, dtype=torch.int32, device=dev)
+def timeit(fn):
+    for _ in range(2): fn()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g): fn()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    t = 0
+    for _ in range(5):
+        flush.zero_(); a.record(); g.replay(); b.record(); torch.cuda.synchronize(); t += a.elapsed_time(b)
+    return t / 5 / layers * 1e3
+print("eager", round(timeit(lambda: [ops.linattn_step(q, k, v, S[l], Z[l]) for l in range(layers)]), 2), "us/launch")
+for p in range(8):
+    step.fill_(p)
+    print("lazy p =", p, round(timeit(lambda: [ops.linattn_step_lazy(q, k, v, S[l], Z[l], ring[l], step) for l in range(layers)]), 2), "us/launch")

@@ -13,12 +13,13 @@ ap.add_argument("--steps", type=int, default=4)
 ap.add_argument("--graph", action="store_true")
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--pdl", action="store_true")
+ap.add_argument("--lazy", action="store_true")
 args = ap.parse_args()
 VOCAB = [56, 135, 18, 87, 18, 25]
 torch.manual_seed(0)
 dev = torch.device("cuda:0")
 m = cpmusic.LinearTransformer(VOCAB).to(dev).eval()
-eng = cpmusic.RolloutEngine(m, args.batch, max(args.steps, 64), greedy=False, use_graph=args.graph, mode=args.mode, pdl=args.pdl)
+eng = cpmusic.RolloutEngine(m, args.batch, max(args.steps, 64), greedy=False, use_graph=args.graph, mode=args.mode, pdl=args.pdl, lazy_state=args.lazy)
 init = torch.stack([torch.randint(0, n, (args.batch,)) for n in VOCAB], -1).to(dev)
 eng.generate(init, args.steps)
 torch.cuda.synchronize()
