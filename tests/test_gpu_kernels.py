@@ -142,6 +142,38 @@ def test_linattn_properties_full_size(cuda, cpm):
     assert bool((o <= cmax + 3e-2).all()) and bool((o >= cmin - 3e-2).all())
 
 
+def test_linattn_cfg5_long_sequence(cuda, cpm):
+    """BASELINE cfg5 attention shape (1 x 8192 tokens, d_model 1024 = 16 heads x 64, bf16).  Forward and backward of
+    the chunk-parallel tcgen05 kernels (64 chunks per head: the parallel state pre-pass + scan path) against the fp32-math
+    SIMT kernels, plus exact causality of both directions: outputs before t are bit-identical when tokens >= t change,
+    and gradients at positions >= t are exactly zero when the upstream gradient is zero there."""
+    N, L, H = 1, 8192, 16
+    gen = torch.Generator().manual_seed(5)
+    q, k, v, go = (torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16() for _ in range(4))
+    saved = cpm.ops.linattn_saved(N, L, H, cuda)
+    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=3, saved=saved)
+    assert cpm.ops.linattn_last_impl() == "tcgen05-cp"
+    ref, den_ref = cpm.ops.linattn_fwd_raw(q, k, v, impl=1)
+    _cmp(out, ref.float(), 3e-2, 2e-2, "cfg5 fwd vs simt")
+    _cmp(den, den_ref, 1e-3, 1e-2, "cfg5 den vs simt")
+    t = 5000
+    q2, k2, v2 = q.clone(), k.clone(), v.clone()
+    q2[:, t:], k2[:, t:], v2[:, t:] = -0.5, 0.75, 2.0
+    out2, _ = cpm.ops.linattn_fwd_raw(q2, k2, v2, impl=3)
+    assert torch.equal(out[:, :t], out2[:, :t]) and not torch.equal(out[:, t:], out2[:, t:])
+    gq, gk, gv = (torch.empty_like(q) for _ in range(3))
+    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=3, saved=saved)
+    sq, sk, sv = (torch.empty_like(q) for _ in range(3))
+    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, sq, sk, sv, impl=1)
+    for name, a, b in (("gq", gq, sq), ("gk", gk, sk), ("gv", gv, sv)):
+        _cmp(a, b.float(), 4e-2, 3e-2, f"cfg5 bwd vs simt {name}")
+    go2 = go.clone()
+    go2[:, t:] = 0
+    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go2, gq, gk, gv, impl=3, saved=saved)
+    for g in (gq, gk, gv):
+        assert not bool(g[:, t:].any()) and bool(g[:, :t].any())
+
+
 # ------------------------------------------------------------------ embedding / PE / dropout
 def test_embed_fwd_bwd(cuda, cpm):
     emb = [128, 256, 64, 512, 128, 128]
