@@ -230,6 +230,15 @@ int cpm_moments(const float *x, const float *sub, int64_t n, double *out3, void 
 int cpm_zscore(const float *x, const float *sub, float *out, int64_t n, const double *moments3,
                int unbiased, float eps, void *stream);
 
+/* D4 — reward / discriminator head of the PPO reward model (ppo_policy/model.py:474-493: six proj_a, six
+ * eval_a = Linear(n_a, 1), mean over the sequence, sigmoid, average of the six).  The Longformer
+ * body stays outside (HF); this takes its last hidden state h (N,L,d).  eval_a(proj_a(h)).mean(L) is linear in h, so
+ * the host collapses each attribute to u_a = W_a^T w_a (d floats) and c_a = w_a.b_a + bias_a:
+ *     scores[n,a] = sigmoid( mean_l h[n,l,:] . u_a + c_a ),   reward[n] = mean_a scores[n,a].
+ * One launch, h read once.  u (n_attr, d) fp32, c (n_attr) fp32; scores may be NULL. */
+int cpm_reward_head(const void *h, const float *u, const float *c, float *reward, float *scores,
+                    int N, int L, int d, int n_attr, int dtype, void *stream);
+
 /* D2 — PPO losses, forward + backward in one launch (grad of the scalar loss w.r.t. inputs,
  * scaled by grad_scale).
  *   mode CPM_PPO_COMPAT (ppo_train.py:388-396): new_logp (C) broadcast over T rows,

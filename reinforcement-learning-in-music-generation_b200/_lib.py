@@ -49,6 +49,7 @@ SIGNATURES = {
     "cpm_tc_linear": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, c_int64,
                               _P, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
     "cpm_linattn_step_lazy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, _P, c_int, _P]),
+    "cpm_reward_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "cpm_embed_fwd": (c_int, [_P, _FPP, _IP, _IP, c_int, c_int64, _P, c_int, _P, _P]),
     "cpm_embed_bwd": (c_int, [_P, _P, _FPP, _IP, _IP, c_int, c_int64, c_int, _P]),
     "cpm_add_pe": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P]),

@@ -255,6 +255,57 @@ inline int blocks_for(int64_t n, int threads) {
 
 using namespace cpm;
 
+namespace cpm {
+namespace {
+// D4 reward head.  eval_a(proj_a(h)).mean(L) is linear in h, so per attribute it collapses to one d-vector:
+//   score_a[n] = sigmoid( mean_l h[n,l,:] . u_a + c_a ),  u_a = W_a^T w_a,  c_a = w_a . b_a + bias_a     (host-built, fp32)
+// One CTA per sequence: column means of h over L (h is read once), A dot products, sigmoid, average.
+template <typename T>
+__global__ void __launch_bounds__(256) reward_head_kernel(const T *__restrict__ h, const float *__restrict__ u, const float *__restrict__ c,
+                                                          float *__restrict__ reward, float *__restrict__ scores, int L, int d, int A) {
+    __shared__ float red[8][CPM_MAX_ATTR];
+    const int n = blockIdx.x, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const T *hn = h + (int64_t)n * L * d;
+    float dot[CPM_MAX_ATTR];
+#pragma unroll
+    for (int a = 0; a < CPM_MAX_ATTR; ++a) dot[a] = 0.f;
+    for (int g = tid; g < d / 8; g += 256) {              // this thread's 8 columns
+        float s[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+        for (int l = 0; l < L; ++l) {
+            Vec8<T> v;
+            v.load(hn + (int64_t)l * d + g * 8);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) s[i] += v.v[i];
+        }
+#pragma unroll
+        for (int a = 0; a < CPM_MAX_ATTR; ++a) {
+            if (a < A) {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dot[a] = fmaf(s[i], u[a * d + g * 8 + i], dot[a]);
+            }
+        }
+    }
+#pragma unroll
+    for (int a = 0; a < CPM_MAX_ATTR; ++a) {
+        const float w = warp_sum(dot[a]);
+        if (lane == 0) red[warp][a] = w;
+    }
+    __syncthreads();
+    if (tid == 0) {
+        float tot = 0.f;
+        for (int a = 0; a < A; ++a) {
+            float x = 0.f;
+            for (int w = 0; w < 8; ++w) x += red[w][a];
+            const float sc = 1.f / (1.f + __expf(-(x / (float)L + c[a])));
+            if (scores) scores[n * A + a] = sc;
+            tot += sc;
+        }
+        reward[n] = tot / (float)A;
+    }
+}
+}  // namespace
+}  // namespace cpm
+
 extern "C" {
 
 int cpm_returns_scan(const float *rewards, const float *values, const float *dones, const float *last_value, float *ret, float *adv,
@@ -341,6 +392,20 @@ int cpm_rollout_advance(const int64_t *tokens, int64_t *history_tok, int64_t n_t
     CPM_REQUIRE(!history_f || vals, CPM_ERR_NULL, "rollout_advance: vals is NULL");
     rollout_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(tokens, history_tok, n_tok, vals, history_f, n_f, step_dev, max_steps);
     return check_launch("rollout_advance");
+}
+
+int cpm_reward_head(const void *h, const float *u, const float *c, float *reward, float *scores, int N, int L, int d, int n_attr,
+                    int dtype, void *stream) {
+    CPM_REQUIRE(h && u && c && reward, CPM_ERR_NULL, "reward_head: NULL pointer");
+    CPM_REQUIRE(N > 0 && L > 0 && d > 0 && d % 8 == 0 && n_attr >= 1 && n_attr <= CPM_MAX_ATTR, CPM_ERR_BAD_SHAPE,
+                "reward_head: N=%d L=%d d=%d n_attr=%d", N, L, d, n_attr);
+    CPM_REQUIRE(aligned16(h), CPM_ERR_BAD_ALIGN, "reward_head: h must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CPM_F32) cpm::reward_head_kernel<float><<<N, 256, 0, st>>>((const float *)h, u, c, reward, scores, L, d, n_attr);
+    else if (dtype == CPM_BF16)
+        cpm::reward_head_kernel<__nv_bfloat16><<<N, 256, 0, st>>>((const __nv_bfloat16 *)h, u, c, reward, scores, L, d, n_attr);
+    else return cpm::fail(CPM_ERR_BAD_DTYPE, "reward_head: dtype %d", dtype);
+    return cpm::check_launch("reward_head");
 }
 
 }  // extern "C"

@@ -701,6 +701,20 @@ def dqn_td_loss(q_logits, next_logits, action, reward, done, seg, n_actions=25, 
                         _lib.TD_COMPAT if compat else _lib.TD_STANDARD)
 
 
+def reward_head(h, u, c, want_scores=False):
+    """reward (N,) = mean_a sigmoid(mean_l h[n,l,:] . u_a + c_a) in one launch (cpm_reward_head).  h (N,L,d) bf16/fp32,
+    u (A,d) fp32, c (A,) fp32.  No autograd: the reference only reads rewards (ppo_train.py:491)."""
+    _cuda(h, u, c)
+    h = h.contiguous()
+    N, L, d = h.shape
+    A = u.shape[0]
+    reward = torch.empty(N, dtype=torch.float32, device=h.device)
+    scores = torch.empty(N, A, dtype=torch.float32, device=h.device) if want_scores else None
+    check(_lib.load().cpm_reward_head(_p(h), _p(u.float().contiguous()), _p(c.float().contiguous()), _p(reward), _p(scores), N, L, d, A,
+                                      _dt(h), _st()))
+    return (reward, scores) if want_scores else reward
+
+
 def rollout_advance(tokens, history_tok, vals, history_f, step_dev, max_steps):
     n_tok = tokens.numel() if tokens is not None else 0
     n_f = vals.numel() if vals is not None else 0

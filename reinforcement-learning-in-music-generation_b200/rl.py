@@ -108,3 +108,34 @@ def dqn_td_loss(eval_net, target_net, state, next_state, action, reward, done, g
         nq = target_net.logits_concat(target_net.hidden(next_state))
     loss, _ = ops.dqn_td_loss(q, nq, action, reward, done, eval_net.seg, n_actions, gamma, compat)
     return loss
+
+
+# ------------------------------------------------------------------------------------------ reward head
+class RewardHead(torch.nn.Module):
+    """The read-out of the PPO reward model ``LongFormer.token_forward`` (ppo_policy/model.py:459-494) — six ``proj_*``
+    ``Linear(d, n_a)``, six ``eval_*`` ``Linear(n_a, 1)``, mean over the sequence, sigmoid, average — with the reference's
+    parameter names, evaluated by one fused kernel on the body's last hidden state.  The Longformer body itself is out
+    of scope (HF ``transformers``); pass its ``last_hidden_state``."""
+    ATTRS = ("tempo", "chord", "barbeat", "pitch", "duration", "velocity")
+
+    def __init__(self, n_token, d_model=512):
+        super().__init__()
+        if len(n_token) != len(self.ATTRS):
+            raise ValueError("RewardHead follows the reference's 6-attribute layout")
+        for a, n in zip(self.ATTRS, n_token):
+            setattr(self, f"proj_{a}", torch.nn.Linear(d_model, int(n)))
+            setattr(self, f"eval_{a}", torch.nn.Linear(int(n), 1))
+
+    def collapsed(self):
+        """(u (6,d), c (6,)): eval_a(proj_a(h)) == h . u_a + c_a."""
+        us, cs = [], []
+        for a in self.ATTRS:
+            proj, ev = getattr(self, f"proj_{a}"), getattr(self, f"eval_{a}")
+            us.append(ev.weight.float() @ proj.weight.float())                      # (1,d)
+            cs.append(ev.weight.float() @ proj.bias.float() + ev.bias.float())      # (1,)
+        return torch.cat(us, 0), torch.cat(cs, 0)
+
+    @torch.no_grad()
+    def forward(self, hidden, want_scores=False):
+        u, c = self.collapsed()
+        return ops.reward_head(hidden, u, c, want_scores)

@@ -632,3 +632,23 @@ def test_tc_linear_variants(cuda, cpm, M, N, K, bn):
     _cmp(y, lin + torch.nn.functional.layer_norm(rs.double(), (N,), g2.double(), b2.double(), 1e-5), 4e-2, 2e-2, "LayerNorm residual")
     with pytest.raises(ValueError):
         ops.tc_linear(a, wb[:, :K - 8].contiguous(), b)          # K % 64 != 0 (and mismatched K)
+
+
+# ------------------------------------------------------------------ reward head
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-5), (torch.bfloat16, 5e-3)])
+def test_reward_head(cuda, cpm, dtype, tol):
+    """Fused reward read-out vs the reference formula written out (ppo_policy/model.py:474-493) in fp64 on the same
+    hidden states: N=30 windows of 50 tokens, d 512 (ppo_train.py:491)."""
+    torch.manual_seed(8)
+    head = cpm.rl.RewardHead([49, 19, 19, 89, 67, 25], d_model=512).to(cuda)
+    h = torch.randn(30, 50, 512, device=cuda).to(dtype)
+    reward, scores = head(h, want_scores=True)
+    hd, ref_scores = h.double(), []
+    for a in head.ATTRS:
+        proj, ev = getattr(head, f"proj_{a}").double(), getattr(head, f"eval_{a}").double()
+        ref_scores.append(torch.sigmoid(ev(proj(hd)).mean(dim=1)))
+    head.float()
+    ref_scores = torch.cat(ref_scores, -1)
+    _cmp(scores, ref_scores, tol, 0.0, "scores")
+    _cmp(reward, ref_scores.mean(-1), tol, 0.0, "reward")
+    assert reward.shape == (30,) and bool(((reward > 0) & (reward < 1)).all())

@@ -194,3 +194,61 @@ def test_bucketed_allreduce_gloo_world2():
     for p in procs:
         p.join(60)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+def _literal_reward(head, h):
+    """ppo_policy/model.py:474-493 written out: six proj, six eval, mean over the sequence, sigmoid, average."""
+    scores = []
+    for a in head.ATTRS:
+        y = getattr(head, f"proj_{a}")(h)
+        scores.append(torch.sigmoid(getattr(head, f"eval_{a}")(y).mean(dim=1)))
+    return sum(scores) / len(scores), torch.cat(scores, -1)
+
+
+def test_reward_head_collapse_equals_reference_formula(cpm):
+    torch.manual_seed(3)
+    head = cpm.rl.RewardHead([49, 19, 19, 89, 67, 25], d_model=64).double()
+    h = torch.randn(5, 50, 64, dtype=torch.float64)
+    ref, ref_scores = _literal_reward(head, h)
+    u, c = head.collapsed()
+    got = torch.sigmoid(h.mean(1) @ u.double().t() + c.double())
+    assert torch.allclose(got, ref_scores, atol=1e-6) and torch.allclose(got.mean(-1, keepdim=True), ref, atol=1e-6)
+    assert {k.split(".")[0] for k in head.state_dict()} == {f"{p}_{a}" for p in ("proj", "eval") for a in head.ATTRS}
+
+
+def test_cp_npz_loader_and_batches(cpm, tmp_path):
+    rng = np.random.RandomState(0)
+    x = rng.randint(0, 18, size=(10, 64, 7)).astype(np.int32)
+    y = np.roll(x, -1, axis=1)
+    mask = (rng.rand(10, 64) > 0.2).astype(np.float64)
+    np.savez(tmp_path / "train_data_linear.npz", x=x, y=y, mask=mask)
+    d = cpm.data.load_cp_npz(tmp_path / "train_data_linear.npz", pin=False)
+    assert d["x"].shape == (10, 64, 6) and d["x"].dtype == torch.int64 and d["mask"].dtype == torch.float32
+    assert np.array_equal(d["x"].numpy(), np.concatenate((x[:, :, :3], x[:, :, 4:]), axis=2))      # agent_pretrain.py:525-526
+    it = cpm.data.CPBatches(d, batch_size=3, device="cpu", seq_len=50, lo=2, hi=10)
+    got = list(it)
+    assert len(got) == len(it) == 2 and got[0][0].shape == (3, 50, 6) and got[0][2].shape == (3, 50)
+    assert torch.equal(got[1][0], d["x"][5:8, :50]) and torch.equal(got[1][1], d["y"][5:8, :50])
+    with pytest.raises(ValueError):
+        np.savez(tmp_path / "bad.npz", x=x[:, :, :6], y=y[:, :, :6], mask=mask)
+        cpm.data.load_cp_npz(tmp_path / "bad.npz", pin=False)
+
+
+def test_device_resident_memory_mirrors_reference_buffers(cpm):
+    """AgentMemory / ExpertMemory keep the reference's method and field names (ppo_train.py:69-212); log-probs come back
+    truncated by .long() like the reference's sampling()/get() unless the compat switch is off."""
+    mem = cpm.data.AgentMemory(capacity=4, n_states=5, n_actions=2, n_features=6, device="cpu")
+    for t in range(6):                                               # wraps around the ring
+        s = torch.full((5, 6), t)
+        mem.store_transition(s, torch.full((2, 6), t + 10), torch.full((2, 6), -1.7 - t), torch.tensor([[0.5 * t]]),
+                             torch.tensor([0.1 * t]), s + 1, torch.tensor(float(t == 5)))
+    assert mem.memory_counter == 6 and mem.states_agent.shape == (4, 5, 6) and mem.rewards_agent.shape == (4, 1)
+    allp = mem.get()
+    assert set(allp) == {"states", "actions", "log_actions", "values", "rewards", "next_states", "dones"}
+    assert allp["states"][0, 0, 0].item() == 4 and allp["states"][1, 0, 0].item() == 5 and allp["states"][2, 0, 0].item() == 2
+    assert allp["log_actions"].dtype == torch.int64 and allp["log_actions"][1, 0, 0].item() == int(-1.7 - 5)
+    batch = mem.sampling(16)
+    assert batch[0].shape == (16, 5, 6) and batch[3].shape == (16, 1) and batch[6].dtype == torch.int64
+    raw = cpm.data.ExpertMemory(capacity=2, n_states=5, n_actions=2, device="cpu", log_prob_long_compat=False)
+    raw.store_transition(torch.zeros(5, 6), torch.zeros(2, 6), torch.full((2, 6), -0.25), 0.0, 1.0, torch.zeros(5, 6), 0.0)
+    assert raw.get()["log_actions"][0, 0, 0].item() == -0.25 and hasattr(raw, "states_expert")
