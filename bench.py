@@ -162,6 +162,16 @@ def cpu_reference_sample(roll_steps=6, upd_seqs=2, upd_len=256, seed=0):
                       f"causal_product ({num_threads()} OMP threads), fp32"}
 
 
+def workload_config(world):
+    tokens_step = SONGS_PER_GPU * ROLLOUT_LEN * world
+    return {"workload": f"cfg3: PPO rollout ({SONGS_PER_GPU} songs x {ROLLOUT_LEN} CP tokens per GPU, recurrent, per-attribute "
+                        f"temperature/nucleus sampling) + critic values + GAE + one clipped-PPO update (actor+critic, "
+                        f"{SONGS_PER_GPU // MINIBATCH} minibatches of {MINIBATCH}x{ROLLOUT_LEN}, dropout 0.1, grad-clip 3, Adam)",
+            "model": "CP linear transformer 12L d512 h8 ff2048 (38.98M params) x2 (actor, critic)",
+            "tokens_per_step": tokens_step, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (working set > 1 GB/step)",
+            "reward": "synthetic (Longformer reward model out of scope)"}
+
+
 def run_reference(args, rank):
     if rank != 0:
         return
@@ -178,8 +188,8 @@ def run_reference(args, rank):
     line = {"metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": tokens / v * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
             "data": "synthetic", "impl": "reference",
-            "config": {"workload": f"cfg3: PPO rollout ({SONGS_PER_GPU} songs x {ROLLOUT_LEN} CP tokens, recurrent, nucleus) + GAE + clipped "
-                                   "update; CPU arm extrapolated from a bounded sample", "model": "CP linear transformer 12L d512 h8"},
+            "config": dict(workload_config(1), parallelism="cpu", note="CPU arm: per-token costs measured on a bounded sample of this "
+                           "workload (cpu_baseline.sample) and extrapolated to the full iteration"),
             "cpu_baseline": r, "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0, "wall_s": time.perf_counter() - t0}
     print(json.dumps(line), flush=True)
@@ -392,11 +402,7 @@ def run_gpu(args, rank, world):
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
-            "config": {"workload": f"cfg3: PPO rollout ({SONGS_PER_GPU} songs x {ROLLOUT_LEN} CP tokens per GPU, recurrent, per-attribute "
-                                   f"temperature/nucleus sampling) + critic values + GAE + one clipped-PPO update (actor+critic, "
-                                   f"{SONGS_PER_GPU // MINIBATCH} minibatches of {MINIBATCH}x{ROLLOUT_LEN}, dropout 0.1, grad-clip 3, Adam)", "model": "CP linear transformer 12L d512 h8 ff2048 (38.98M params) x2 (actor, critic)",
-                       "tokens_per_step": tokens_step, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (working set > 1 GB/step)",
-                       "reward": "synthetic (Longformer reward model out of scope)"},
+            "config": workload_config(world),
             "roofline": roofline, "roofline_recurrent_step": roofline_step, "cpu_baseline": cpu,
             "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": int(it.init_host.numel() * 8),
                     "d2h_bytes_per_step": int(host_tok.numel() * 8 + 16), "ms_per_step": ms_e2e / args.steps},
