@@ -98,6 +98,14 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
                      int N, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
                      int dtype, float eps, void *stream);
 
+/* B1 split in two launches (rollout engine): cpm_linattn_step_out computes the step's output from S + Kf (x) v formed in
+ * registers (bit-identical to cpm_linattn_step), updates Z and parks [Kf | v] in kv_pending ((N,H,128) fp32);
+ * cpm_linattn_state_update then stores S += Kf (x) v.  The second launch may run on another stream / graph branch; it
+ * must complete before the next cpm_linattn_step_out on the same state. */
+int cpm_linattn_step_out(const void *q, const void *k, const void *v, const float *S, float *Z, float *kv_pending,
+                         void *out, int N, int H, int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream);
+int cpm_linattn_state_update(float *S, const float *kv_pending, int N, int H, void *stream);
+
 /* B1, deferred write-back (rollout engine only).  Same arithmetic, bit-identical outputs: the rank-1 updates of the
  * last (*step_dev % CPM_LAZY_STATE_PERIOD) tokens live in `ring` ((N,H,PERIOD,128) fp32: [Kf | v] per entry) and are
  * re-applied in registers every step; S is written back only when the ring fills, so a token step moves

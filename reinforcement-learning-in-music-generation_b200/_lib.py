@@ -48,6 +48,8 @@ SIGNATURES = {
     "cpm_gelu_fold": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
     "cpm_tc_linear": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, c_int64,
                               _P, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
+    "cpm_linattn_step_out": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, _P]),
+    "cpm_linattn_state_update": (c_int, [_P, _P, c_int, c_int, _P]),
     "cpm_linattn_step_lazy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, _P, c_int, _P]),
     "cpm_reward_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "cpm_embed_fwd": (c_int, [_P, _FPP, _IP, _IP, c_int, c_int64, _P, c_int, _P, _P]),

@@ -103,6 +103,99 @@ __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// B1 (split): the step as two kernels so that the state write-back leaves the token step's critical path.
+//   linattn_step_out_kernel     reads S, forms S + Kf (x) v in registers (same FMA as the fused kernel: bit-identical
+//                               output), writes the attention output, Z, and parks [Kf | v] (512 B) for the second half;
+//   linattn_state_update_kernel re-reads S and the parked [Kf | v], stores S + Kf (x) v.  The rollout engine launches it
+//                               on a side branch of the step graph, where it overlaps the latency-bound GEMM / LayerNorm
+//                               launches that follow; it only has to finish before the same layer's next token.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) linattn_step_out_kernel(const T *__restrict__ q, const T *__restrict__ k, const T *__restrict__ v,
+                                                               const float *__restrict__ S, float *__restrict__ Z, float *__restrict__ kvp,
+                                                               T *__restrict__ out, int H, int64_t ld_qkv, int64_t ld_o, float eps) {
+    __shared__ float part[8][68];
+    const int nh = blockIdx.x, n = nh / H, h = nh % H;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int e = tid >> 2, m0 = (tid & 3) * 16;
+    const float *srow = S + (int64_t)nh * 4096 + e * 64 + m0;
+    float4 s[4];
+    {
+        const F8 lo = ld_stream(srow), hi = ld_stream(srow + 8);
+        s[0] = lo.a; s[1] = lo.b; s[2] = hi.a; s[3] = hi.b;
+    }
+    const int64_t qoff = (int64_t)n * ld_qkv + h * 64;
+    const float ke = phi(to_f(k[qoff + e])), qe = phi(to_f(q[qoff + e]));
+    float vv[16];
+    {
+        Vec8<T> v0, v1;
+        v0.load(v + qoff + m0);
+        v1.load(v + qoff + m0 + 8);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) { vv[i] = v0.v[i]; vv[8 + i] = v1.v[i]; }
+    }
+    float dpart = 0.f;
+    if ((tid & 3) == 0) {
+        float *z = Z + (int64_t)nh * 64 + e;
+        const float zn = *z + ke;
+        *z = zn;
+        dpart = qe * zn;
+        kvp[(int64_t)nh * 128 + e] = ke;                  // park Kf
+    }
+    if (e == 0) {                                          // threads 0..3 park v (16 floats each)
+        float4 *dst = reinterpret_cast<float4 *>(kvp + (int64_t)nh * 128 + 64 + m0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i) dst[i] = make_float4(vv[4 * i], vv[4 * i + 1], vv[4 * i + 2], vv[4 * i + 3]);
+    }
+    float acc[16];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        s[i].x = fmaf(ke, vv[4 * i + 0], s[i].x); s[i].y = fmaf(ke, vv[4 * i + 1], s[i].y);
+        s[i].z = fmaf(ke, vv[4 * i + 2], s[i].z); s[i].w = fmaf(ke, vv[4 * i + 3], s[i].w);
+        acc[4 * i + 0] = qe * s[i].x; acc[4 * i + 1] = qe * s[i].y;
+        acc[4 * i + 2] = qe * s[i].z; acc[4 * i + 3] = qe * s[i].w;
+    }
+#pragma unroll
+    for (int i = 0; i < 16; ++i) {
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
+        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+    }
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 4);
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 8);
+    dpart += __shfl_xor_sync(0xffffffffu, dpart, 16);
+    if (lane < 4) {
+#pragma unroll
+        for (int i = 0; i < 16; ++i) part[warp][lane * 16 + i] = acc[i];
+        if (lane == 0) part[warp][64] = dpart;
+    }
+    __syncthreads();
+    if (tid < 64) {
+        float o = 0.f, d = eps;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) { o += part[w][tid]; d += part[w][64]; }
+        out[(int64_t)n * ld_o + h * 64 + tid] = from_f<T>(o / d);
+    }
+}
+
+__global__ void __launch_bounds__(256) linattn_state_update_kernel(float *__restrict__ S, const float *__restrict__ kvp) {
+    const int nh = blockIdx.x, tid = threadIdx.x;
+    const int e = tid >> 2, m0 = (tid & 3) * 16;
+    float *srow = S + (int64_t)nh * 4096 + e * 64 + m0;
+    const F8 lo = ld_stream(srow), hi = ld_stream(srow + 8);
+    const float ke = kvp[(int64_t)nh * 128 + e];
+    const float4 *vp = reinterpret_cast<const float4 *>(kvp + (int64_t)nh * 128 + 64 + m0);
+    const float4 v0 = vp[0], v1 = vp[1], v2 = vp[2], v3 = vp[3];
+    F8 a, b;
+    a.a = make_float4(fmaf(ke, v0.x, lo.a.x), fmaf(ke, v0.y, lo.a.y), fmaf(ke, v0.z, lo.a.z), fmaf(ke, v0.w, lo.a.w));
+    a.b = make_float4(fmaf(ke, v1.x, lo.b.x), fmaf(ke, v1.y, lo.b.y), fmaf(ke, v1.z, lo.b.z), fmaf(ke, v1.w, lo.b.w));
+    b.a = make_float4(fmaf(ke, v2.x, hi.a.x), fmaf(ke, v2.y, hi.a.y), fmaf(ke, v2.z, hi.a.z), fmaf(ke, v2.w, hi.a.w));
+    b.b = make_float4(fmaf(ke, v3.x, hi.b.x), fmaf(ke, v3.y, hi.b.y), fmaf(ke, v3.z, hi.b.z), fmaf(ke, v3.w, hi.b.w));
+    st_stream(srow, a);
+    st_stream(srow + 8, b);
+}
+
+// ------------------------------------------------------------------------------------------
 // B1 (lazy): the same step with the state write-back deferred.  The rank-1 updates of the last p = step % C tokens
 // are kept in a small ring (C x [Kf | v] fp32 per (sequence, head)); every step rebuilds S_eff = S + sum_j Kf_j (x) v_j
 // in registers in the original order (bit-identical to the eager kernel), and only every C-th step writes S back.
@@ -325,6 +418,31 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
     else
         return fail(CPM_ERR_BAD_DTYPE, "linattn_step: dtype %d", dtype);
     return check_launch("linattn_step");
+}
+
+int cpm_linattn_step_out(const void *q, const void *k, const void *v, const float *S, float *Z, float *kv_pending, void *out, int N, int H,
+                         int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream) {
+    CPM_REQUIRE(q && k && v && S && Z && kv_pending && out, CPM_ERR_NULL, "linattn_step_out: NULL pointer");
+    CPM_REQUIRE(N > 0 && H > 0 && ld_qkv >= (int64_t)H * 64 && ld_o >= (int64_t)H * 64, CPM_ERR_BAD_SHAPE, "linattn_step_out: N=%d H=%d / strides", N, H);
+    CPM_REQUIRE(aligned16(S) && aligned16(kv_pending), CPM_ERR_BAD_ALIGN, "linattn_step_out: S / kv_pending must be 16-byte aligned");
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CPM_F32)
+        linattn_step_out_kernel<float><<<N * H, 256, 0, st>>>((const float *)q, (const float *)k, (const float *)v, S, Z, kv_pending, (float *)out,
+                                                              H, ld_qkv, ld_o, eps);
+    else if (dtype == CPM_BF16)
+        linattn_step_out_kernel<__nv_bfloat16><<<N * H, 256, 0, st>>>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k, (const __nv_bfloat16 *)v, S,
+                                                                      Z, kv_pending, (__nv_bfloat16 *)out, H, ld_qkv, ld_o, eps);
+    else
+        return fail(CPM_ERR_BAD_DTYPE, "linattn_step_out: dtype %d", dtype);
+    return check_launch("linattn_step_out");
+}
+
+int cpm_linattn_state_update(float *S, const float *kv_pending, int N, int H, void *stream) {
+    CPM_REQUIRE(S && kv_pending, CPM_ERR_NULL, "linattn_state_update: NULL pointer");
+    CPM_REQUIRE(N > 0 && H > 0, CPM_ERR_BAD_SHAPE, "linattn_state_update: N=%d H=%d", N, H);
+    CPM_REQUIRE(aligned16(S) && aligned16(kv_pending), CPM_ERR_BAD_ALIGN, "linattn_state_update: alignment");
+    linattn_state_update_kernel<<<N * H, 256, 0, (cudaStream_t)stream>>>(S, kv_pending);
+    return check_launch("linattn_state_update");
 }
 
 int cpm_linattn_step_lazy(const void *q, const void *k, const void *v, float *S, float *Z, float *ring, void *out, int N, int H,

@@ -184,7 +184,9 @@ class TransformerEncoder(nn.Module):
         qkv = cached_linear(c, ("qkv", i), [at.query_projection, at.key_projection, at.value_projection], x, dt)
         N = qkv.shape[0]
         q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
-        if len(st) > 2:          # rollout engine: [S, Z, ring, step_dev] -> deferred state write-back
+        if len(st) > 2 and callable(st[2]):      # rollout engine hook: (q, k, v, S, Z) -> attention output
+            a = st[2](q, k, v, st[0], st[1]).view(N, H * 64)
+        elif len(st) > 2:        # rollout engine: [S, Z, ring, step_dev] -> deferred state write-back
             a = ops.linattn_step_lazy(q, k, v, st[0], st[1], st[2], st[3]).view(N, H * 64)
         else:
             a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * 64)

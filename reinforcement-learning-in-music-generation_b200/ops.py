@@ -237,6 +237,25 @@ def linattn_step(q, k, v, S, Z, eps=EPS_ATTN):
     return out
 
 
+def linattn_step_out(q, k, v, S, Z, kv_pending, eps=EPS_ATTN):
+    """First half of the split step: output + Z update + parked [Kf | v]; S is only read (cpm_linattn_step_out)."""
+    _cuda(q, k, v, S, Z, kv_pending)
+    N, H, E = q.shape
+    ld = q.stride(0)
+    if not (k.stride(0) == ld and v.stride(0) == ld and q.stride(2) == 1 and q.stride(1) == E):
+        raise ValueError("q,k,v must be (N,H,E) with a common row stride and packed heads")
+    if S.shape[0] != N:
+        raise ValueError("The batch size changed during iteration")
+    out = torch.empty(N, H, E, dtype=q.dtype, device=q.device)
+    check(_lib.load().cpm_linattn_step_out(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(kv_pending), _p(out), N, H, ld, H * E, _dt(q), eps, _st()))
+    return out
+
+
+def linattn_state_update(S, kv_pending):
+    """Second half of the split step: S += Kf (x) v from the parked vectors (cpm_linattn_state_update)."""
+    check(_lib.load().cpm_linattn_state_update(_p(S), _p(kv_pending), S.shape[0], S.shape[1], _st()))
+
+
 LAZY_STATE_PERIOD = 8      # CPM_LAZY_STATE_PERIOD
 
 

@@ -40,7 +40,8 @@ class _MegaGlobals(ctypes.Structure):        # mirrors cpm::MegaGlobals
 class RolloutEngine:
     def __init__(self, model, batch: int, max_steps: int, greedy: bool = False, true_positions: bool = True,
                  temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True,
-                 fused: Optional[bool] = None, mode: Optional[str] = None, pdl: bool = False, lazy_state: bool = False):
+                 fused: Optional[bool] = None, mode: Optional[str] = None, pdl: bool = False, lazy_state: bool = False,
+                 split_state: bool = False):
         self.model, self.N, self.max_steps = model, batch, max_steps
         self.greedy, self.true_positions = greedy, true_positions
         self.temperature, self.top_p = model.sampling_config(temperature, top_p)
@@ -61,6 +62,14 @@ class RolloutEngine:
         if self.lazy_state:
             self.ring = torch.zeros(nl, batch, H, ops.LAZY_STATE_PERIOD, 128, dtype=torch.float32, device=dev)
             self.state = [[self.S[i], self.Z[i], self.ring[i], self.step_dev] for i in range(nl)]
+        # split step (unfused mode, opt-in): the S write-back runs as its own kernel on a side branch of the step graph
+        self.split_state = bool(split_state)
+        if self.split_state:
+            if self.lazy_state:
+                raise ValueError("choose one of lazy_state / split_state")
+            self.kvp = torch.zeros(nl, batch, H, 128, dtype=torch.float32, device=dev)
+            self.side = torch.cuda.Stream(device=dev)
+            self.state = [[self.S[i], self.Z[i], self._split_hook(i)] for i in range(nl)]
         self.cur = torch.zeros(batch, A, dtype=torch.int64, device=dev)
         self.logp = torch.zeros(batch, A, dtype=torch.float32, device=dev)
         self.hist_tok = torch.zeros(max_steps, batch, A, dtype=torch.int64, device=dev)
@@ -79,8 +88,8 @@ class RolloutEngine:
             raise ValueError("the tcgen05 rollout step needs bf16 compute, widths that are multiples of 64 (inputs) / 32 (outputs)")
         if mode not in ("mega", "fused", "unfused", "tc", "fold"):
             raise ValueError(f"unknown rollout mode {mode!r}")
-        if self.lazy_state and mode != "unfused":
-            raise ValueError("lazy_state is implemented for the unfused step")
+        if (self.lazy_state or self.split_state) and mode != "unfused":
+            raise ValueError("lazy_state / split_state are implemented for the unfused step")
         self.mode = mode
         self.fused = mode == "fused"
         self.pdl = pdl
@@ -349,6 +358,18 @@ class RolloutEngine:
         ops.heads_sample(lc, m.seg, self.temperature, self.top_p, greedy=self.greedy, seed=self.seed,
                          seq_base=self.seq_base, step_dev=self.step_dev, tokens_out=self.cur, logp_out=self.logp)
         ops.rollout_advance(self.cur, self.hist_tok, self.logp, self.hist_logp, self.step_dev, self.max_steps)
+        if self.split_state:
+            torch.cuda.current_stream().wait_stream(self.side)   # join: all write-backs land before the next token step
+
+    def _split_hook(self, i):
+        def hook(q, k, v, S, Z):
+            out = ops.linattn_step_out(q, k, v, S, Z, self.kvp[i])
+            main = torch.cuda.current_stream()
+            self.side.wait_stream(main)                     # fork: the write-back needs the parked [Kf | v]
+            with torch.cuda.stream(self.side):
+                ops.linattn_state_update(S, self.kvp[i])
+            return out
+        return hook
 
     def flush_state(self):
         """Brings S up to date when the write-back is deferred (no-op otherwise)."""

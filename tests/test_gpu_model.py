@@ -154,8 +154,9 @@ def test_lazy_state_rollout_is_bit_identical(cuda, cpm, golden, T):
     init = torch.stack([torch.randint(0, n, (N,), generator=torch.Generator().manual_seed(3)) for n in VOCAB], -1).to(cuda)
     ref_e = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=False)
     ref = ref_e.generate(init)
-    for use_graph in (False, True):
-        eng = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=use_graph, lazy_state=True)
+    for use_graph, kw in ((False, dict(lazy_state=True)), (True, dict(lazy_state=True)), (False, dict(split_state=True)),
+                          (True, dict(split_state=True))):
+        eng = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=use_graph, **kw)
         for _ in range(2):
             out = eng.generate(init)
             assert torch.equal(out["tokens"], ref["tokens"]) and torch.equal(out["logp"], ref["logp"])
