@@ -92,7 +92,8 @@ COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
     "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
-    "cpm_linattn_fwd": 3, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2,      # chunk-parallel path: pre-pass, scan, main
+    "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
+                                                                                # kernel (ops adds 1 when the scan path runs); bwd = pre-pass, scan, main
 })
 EXTRA_LAUNCHES = [0]          # segment-total / scan kernels of segmented linear attention, graph replays
 

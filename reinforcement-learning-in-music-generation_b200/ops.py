@@ -141,6 +141,8 @@ def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True, saved=None):
     out = torch.empty(N, L, H, E, dtype=q.dtype, device=q.device)
     den = torch.empty(N, L, H, dtype=torch.float32, device=q.device) if need_den else None
     ws = linattn_workspace(N, L, H, q.device)
+    if N * H < 96 and L > 128:
+        _lib.EXTRA_LAUNCHES[0] += 1          # few (batch, head) chains: per-chunk state kernel + scan instead of the streaming kernel
     with KernelTimer.span("linattn_fwd"):
         check(_lib.load().cpm_linattn_fwd(_p(q), _p(k), _p(v), _p(out), _p(den), N, L, H, E, E, ld, H * E,
                                           _dt(q), eps, impl, _p(ws), ws.numel(), _p(saved),
