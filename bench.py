@@ -336,6 +336,12 @@ def run_gpu(args, rank, world):
     for _ in range(max(args.warmup, 3)):
         it.step(it.init_dev)
     barrier()
+    if args.profile_step:                              # ncu --profile-from-start off: one whole iteration, every thread's launches
+        torch.cuda.profiler.start()
+        it.step(it.init_dev)
+        torch.cuda.synchronize()
+        torch.cuda.profiler.stop()
+        return
     # ---- device-resident timed region ------------------------------------------------------
     sampler = ClockSampler(local)
     if rank == 0:
@@ -419,6 +425,8 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cpmusic", choices=["cpmusic", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--profile-step", action="store_true",
+                    help="after the warm-up run ONE iteration between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

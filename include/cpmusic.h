@@ -154,15 +154,18 @@ int cpm_dropout(const void *x, void *y, int64_t n, float p_drop, uint64_t seed,
  * Saves s (dtype, may be NULL for inference), mean, rstd (fp32, may be NULL).  d % 8 == 0,
  * d <= 8192.  bwd: given gy, s, mean, rstd -> gs (grad wrt x), gres (grad wrt res through the
  * dropout mask; may alias NULL when p_drop==0: then gres==gs), and fp32 partial sums for
- * dgamma/dbeta in `partials` (cpm_ln_partials_rows() x 2 x d), reduced into dgamma/dbeta (+=).
+ * dgamma/dbeta(/dres_bias) in `partials` (cpm_ln_partials_rows() x 3 x d), reduced into dgamma/dbeta (+=).
  */
-int cpm_ln_residual_fwd(const void *x, const void *res, const float *gamma, const float *beta,
+/* res_bias (optional, fp32 (d)): bias of the Linear that produced `res`, added before the dropout — lets that GEMM run
+ * bias-less and makes its bias gradient a by-product of the backward kernel: dres_bias (optional) += column sums of the
+ * residual-branch gradient.  partials: cpm_ln_partials_rows() x 3 x d floats. */
+int cpm_ln_residual_fwd(const void *x, const void *res, const float *res_bias, const float *gamma, const float *beta,
                         void *y, void *s_out, float *mean, float *rstd, int64_t rows, int d,
                         float eps, float p_drop, uint64_t seed, uint64_t rng_offset, int dtype,
                         void *stream);
 int cpm_ln_partials_rows(void);
 int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const float *rstd,
-                        const float *gamma, void *gs, void *gres, float *dgamma, float *dbeta,
+                        const float *gamma, void *gs, void *gres, float *dgamma, float *dbeta, float *dres_bias,
                         float *partials, int64_t rows, int d, float p_drop, uint64_t seed,
                         uint64_t rng_offset, int dtype, void *stream);
 
@@ -171,8 +174,11 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
  * bwd: gx = gy * mask/(1-p) * gelu'(x + bias). */
 int cpm_gelu_fwd(const void *x, const float *bias, void *y, int64_t rows, int d, float p_drop,
                  uint64_t seed, uint64_t rng_offset, int dtype, void *stream);
-int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, int64_t rows, int d,
-                 float p_drop, uint64_t seed, uint64_t rng_offset, int dtype, void *stream);
+/* dbias (optional, fp32 (d), +=): fused bias gradient = column sums of gx; needs d | 4096 and
+ * partials of cpm_gelu_bwd_partials_rows(d) x d floats. */
+int cpm_gelu_bwd_partials_rows(int d);
+int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, float *dbias, float *partials,
+                 int64_t rows, int d, float p_drop, uint64_t seed, uint64_t rng_offset, int dtype, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * C3 — per-attribute decode over concatenated head logits.  Replaces

@@ -124,7 +124,8 @@ __global__ void __launch_bounds__(256) dropout_kernel(const T *__restrict__ x, T
 // ---------------------------------------------------------------- C2 residual + dropout + LayerNorm
 // One warp per row; the row lives in registers (MAXV vectors of 8 per lane).
 template <typename T, int MAXV>
-__global__ void __launch_bounds__(128) ln_residual_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, const float *__restrict__ gamma,
+__global__ void __launch_bounds__(128) ln_residual_fwd_kernel(const T *__restrict__ x, const T *__restrict__ res, const float *__restrict__ res_bias,
+                                                              const float *__restrict__ gamma,
                                                               const float *__restrict__ beta, T *__restrict__ y, T *__restrict__ s_out,
                                                               float *__restrict__ mean_out, float *__restrict__ rstd_out, int64_t rows, int d,
                                                               float eps, uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset) {
@@ -143,6 +144,10 @@ __global__ void __launch_bounds__(128) ln_residual_fwd_kernel(const T *__restric
                 if (res) {
                     Vec8<T> rr;
                     rr.load(res + r * d + g * 8);
+                    if (res_bias) {                   // bias of the Linear that produced `res` (its GEMM runs bias-less)
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) rr.v[j] += res_bias[g * 8 + j];
+                    }
                     if (thr) {
                         bool keep[8];
                         dropout_mask8(seed, rng_offset, (uint64_t)(r * G + g), thr, keep);
@@ -188,24 +193,25 @@ __global__ void __launch_bounds__(128) ln_residual_fwd_kernel(const T *__restric
 }
 
 constexpr int LN_BWD_BLOCKS = 296;   // 2 CTAs per SM on 148 SMs
+constexpr int GELU_BWD_BLOCKS = 1184; // 8 CTAs per SM: the fused-bias-gradient variant keeps its partial matrix small
 constexpr int LN_BWD_THREADS = 256;
 
-template <typename T, int MAXV>
+template <typename T, int MAXV, bool WANT_DRES>
 __global__ void __launch_bounds__(LN_BWD_THREADS) ln_residual_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ s, const float *__restrict__ mean,
                                                                          const float *__restrict__ rstd, const float *__restrict__ gamma, T *__restrict__ gs,
                                                                          T *__restrict__ gres, float *__restrict__ partials, int64_t rows, int d, uint32_t thr,
                                                                          float scale, uint64_t seed, uint64_t rng_offset) {
-    extern __shared__ float red[];   // [2][d] block partial sums
+    extern __shared__ float red[];   // [3][d] block partial sums: dgamma | dbeta | column sums of the residual-branch gradient
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = d >> 3;
-    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) red[i] = 0.f;
+    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) red[i] = 0.f;
     __syncthreads();
-    float dg[MAXV][8], db[MAXV][8], gm[MAXV][8];
+    float dg[MAXV][8], db[MAXV][8], dr[MAXV][8], gm[MAXV][8];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
         const int g = lane + 32 * i;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; gm[i][j] = (g < G) ? gamma[g * 8 + j] : 0.f; }
+        for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; dr[i][j] = 0.f; gm[i][j] = (g < G) ? gamma[g * 8 + j] : 0.f; }
     }
     const int64_t warp_global = (int64_t)blockIdx.x * (LN_BWD_THREADS / 32) + warp;
     const int64_t nwarps = (int64_t)gridDim.x * (LN_BWD_THREADS / 32);
@@ -250,6 +256,12 @@ __global__ void __launch_bounds__(LN_BWD_THREADS) ln_residual_bwd_kernel(const T
                     for (int j = 0; j < 8; ++j) o.v[j] = keep[j] ? o.v[j] * scale : 0.f;
                     o.store(gres + r * d + g * 8);
                 }
+                if (WANT_DRES) {                      // d(loss)/d(res_bias) = column sums of the residual-branch gradient
+                    Vec8<T> rounded;                  // as stored (what a reduction over the stored tensor would see)
+                    rounded = o;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) dr[i][j] += to_f(from_f<T>(rounded.v[j]));
+                }
             }
         }
     }
@@ -261,20 +273,39 @@ __global__ void __launch_bounds__(LN_BWD_THREADS) ln_residual_bwd_kernel(const T
             for (int j = 0; j < 8; ++j) {
                 atomicAdd(&red[g * 8 + j], dg[i][j]);
                 atomicAdd(&red[d + g * 8 + j], db[i][j]);
+                if (WANT_DRES) atomicAdd(&red[2 * d + g * 8 + j], dr[i][j]);
             }
         }
     }
     __syncthreads();
-    for (int i = threadIdx.x; i < 2 * d; i += blockDim.x) partials[(int64_t)blockIdx.x * 2 * d + i] = red[i];
+    for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) partials[(int64_t)blockIdx.x * 3 * d + i] = red[i];
 }
 
-__global__ void ln_reduce_partials_kernel(const float *__restrict__ partials, int nblocks, int d, float *__restrict__ dgamma,
-                                          float *__restrict__ dbeta) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 2 * d) return;
-    float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partials[(int64_t)b * 2 * d + c];
-    if (c < d) dgamma[c] += s; else dbeta[c - d] += s;
+// out_k[c] += sum over `nrows` partial rows of width `width` (k = c / d selects dgamma | dbeta | dres_bias; NULL = skip).
+// 32 rows per CTA pass with 4 independent accumulators; one CTA column-slab of 64 columns; fixed order (deterministic).
+__global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__restrict__ partials, int nrows, int width, int d, float *__restrict__ out0,
+                                                              float *__restrict__ out1, float *__restrict__ out2) {
+    __shared__ float sm[4][64];
+    const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;          // 64 columns x 4 row groups
+    const int c = blockIdx.x * 64 + cl;
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    if (c < width) {
+        int r = rg;
+        for (; r + 12 < nrows; r += 16) {
+            a0 += partials[(int64_t)r * width + c];
+            a1 += partials[(int64_t)(r + 4) * width + c];
+            a2 += partials[(int64_t)(r + 8) * width + c];
+            a3 += partials[(int64_t)(r + 12) * width + c];
+        }
+        for (; r < nrows; r += 4) a0 += partials[(int64_t)r * width + c];
+    }
+    sm[rg][cl] = (a0 + a1) + (a2 + a3);
+    __syncthreads();
+    if (rg == 0 && c < width) {
+        const float tot = (sm[0][cl] + sm[1][cl]) + (sm[2][cl] + sm[3][cl]);
+        float *out = c < d ? out0 : (c < 2 * d ? out1 : out2);
+        if (out) out[c % d] += tot;
+    }
 }
 
 // ---------------------------------------------------------------- bias + exact GELU + dropout
@@ -327,18 +358,39 @@ inline uint32_t dropout_threshold8(float p) {
 inline float dropout_scale8(float p) { uint32_t t = dropout_threshold8(p); return t ? 256.0f / (256.0f - (float)t) : 1.0f; }
 
 // 16 elements per thread and iteration (two 128-bit loads in flight per operand, one Philox block)
-template <typename T, bool BWD>
+// dbias_partials (BWD only, optional): row (blockIdx * (4096 / d) + (tid * 16) / d) of a [gridDim * 4096 / d][d] fp32 matrix receives
+// this thread's column sums of the stored gx — valid because 4096 % d == 0 makes a thread's 16 columns the same in every iteration.
+template <typename T, bool BWD, bool DBIAS = false>
 __global__ void __launch_bounds__(256) gelu_kernel(const T *__restrict__ x, const float *__restrict__ bias, const T *__restrict__ gy, T *__restrict__ out,
-                                                   int64_t n_groups, int d, uint32_t thr8, float scale, uint64_t seed, uint64_t rng_offset) {
+                                                   int64_t n_groups, int d, uint32_t thr8, float scale, uint64_t seed, uint64_t rng_offset,
+                                                   float *__restrict__ dbias_partials) {
+    float cs[16], bv[16];
+#pragma unroll
+    for (int j = 0; j < 16; ++j) { cs[j] = 0.f; bv[j] = 0.f; }
+    // 4096 % d == 0: the grid stride (a multiple of 256 threads x 16 elements) is a multiple of the row width, so a thread
+    // sees the same 16 columns in every iteration and its bias values are loaded once.
+    const bool fixed_cols = bias && (4096 % d == 0);
+    if (fixed_cols) {
+        const int c = (threadIdx.x * 16) % d;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) {
+            const float4 b4 = *reinterpret_cast<const float4 *>(bias + c + j);
+            bv[j] = b4.x; bv[j + 1] = b4.y; bv[j + 2] = b4.z; bv[j + 3] = b4.w;
+        }
+    }
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n_groups; i += (int64_t)gridDim.x * blockDim.x) {
         Vec8<T> v0, v1, g0, g1;
         v0.load(x + i * 16);
         v1.load(x + i * 16 + 8);
         if (BWD) { g0.load(gy + i * 16); g1.load(gy + i * 16 + 8); }
-        if (bias) {
+        if (bias && !fixed_cols) {
             const int c = (int)((i * 16) % d);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) { v0.v[j] += bias[c + j]; v1.v[j] += bias[c + 8 + j]; }
+            for (int j = 0; j < 16; ++j) bv[j] = bias[c + j];
+        }
+        if (bias) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { v0.v[j] += bv[j]; v1.v[j] += bv[8 + j]; }
         }
         const uint32_t keep = thr8 ? dropout_keep16(seed, rng_offset, (uint64_t)i, thr8) : 0xFFFFu;
         Vec8<T> o0, o1;
@@ -352,6 +404,16 @@ __global__ void __launch_bounds__(256) gelu_kernel(const T *__restrict__ x, cons
         }
         o0.store(out + i * 16);
         o1.store(out + i * 16 + 8);
+        if (DBIAS) {
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { cs[j] += to_f(from_f<T>(o0.v[j])); cs[8 + j] += to_f(from_f<T>(o1.v[j])); }
+        }
+    }
+    if (DBIAS) {
+        const int per = 4096 / d;
+        float *dst = dbias_partials + ((int64_t)blockIdx.x * per + (threadIdx.x * 16) / d) * d + (threadIdx.x * 16) % d;
+#pragma unroll
+        for (int j = 0; j < 16; j += 4) *reinterpret_cast<float4 *>(dst + j) = make_float4(cs[j], cs[j + 1], cs[j + 2], cs[j + 3]);
     }
 }
 
@@ -462,8 +524,8 @@ int cpm_dropout(const void *x, void *y, int64_t n, float p_drop, uint64_t seed, 
     return check_launch("dropout");
 }
 
-int cpm_ln_residual_fwd(const void *x, const void *res, const float *gamma, const float *beta, void *y, void *s_out, float *mean,
-                        float *rstd, int64_t rows, int d, float eps, float p_drop, uint64_t seed, uint64_t rng_offset, int dtype,
+int cpm_ln_residual_fwd(const void *x, const void *res, const float *res_bias, const float *gamma, const float *beta, void *y, void *s_out,
+                        float *mean, float *rstd, int64_t rows, int d, float eps, float p_drop, uint64_t seed, uint64_t rng_offset, int dtype,
                         void *stream) {
     CPM_REQUIRE(x && gamma && beta && y, CPM_ERR_NULL, "ln_residual_fwd: NULL pointer");
     CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0 && d <= 2048, CPM_ERR_BAD_SHAPE, "ln_residual_fwd: d=%d must be a multiple of 8 and <= 2048", d);
@@ -473,7 +535,7 @@ int cpm_ln_residual_fwd(const void *x, const void *res, const float *gamma, cons
     const uint32_t thr = res ? dropout_threshold(p_drop) : 0u;
     const int grid = grid_for(rows * 32, 128);
     DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_fwd_kernel<T, MAXV><<<grid, 128, 0, (cudaStream_t)stream>>>(
-                                               (const T *)x, (const T *)res, gamma, beta, (T *)y, (T *)s_out, mean, rstd, rows, d, eps, thr,
+                                               (const T *)x, (const T *)res, res ? res_bias : nullptr, gamma, beta, (T *)y, (T *)s_out, mean, rstd, rows, d, eps, thr,
                                                dropout_scale(p_drop), seed, rng_offset)));
     return check_launch("ln_residual_fwd");
 }
@@ -481,7 +543,7 @@ int cpm_ln_residual_fwd(const void *x, const void *res, const float *gamma, cons
 int cpm_ln_partials_rows(void) { return LN_BWD_BLOCKS; }
 
 int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const float *rstd, const float *gamma, void *gs, void *gres,
-                        float *dgamma, float *dbeta, float *partials, int64_t rows, int d, float p_drop, uint64_t seed,
+                        float *dgamma, float *dbeta, float *dres_bias, float *partials, int64_t rows, int d, float p_drop, uint64_t seed,
                         uint64_t rng_offset, int dtype, void *stream) {
     CPM_REQUIRE(gy && s && mean && rstd && gamma && gs && dgamma && dbeta && partials, CPM_ERR_NULL, "ln_residual_bwd: NULL pointer");
     CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0 && d <= 2048, CPM_ERR_BAD_SHAPE, "ln_residual_bwd: d=%d", d);
@@ -489,11 +551,18 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
     const uint32_t thr = dropout_threshold(p_drop);
     CPM_REQUIRE(!thr || gres, CPM_ERR_NULL, "ln_residual_bwd: gres required when p_drop > 0");
     if (rows == 0) return CPM_OK;
-    const size_t smem = 2 * (size_t)d * sizeof(float);
-    DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV><<<LN_BWD_BLOCKS, LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
-                                               (const T *)gy, (const T *)s, mean, rstd, gamma, (T *)gs, (T *)gres, partials, rows, d, thr,
-                                               dropout_scale(p_drop), seed, rng_offset)));
-    ln_reduce_partials_kernel<<<(2 * d + 255) / 256, 256, 0, (cudaStream_t)stream>>>(partials, LN_BWD_BLOCKS, d, dgamma, dbeta);
+    const size_t smem = 3 * (size_t)d * sizeof(float);
+    if (dres_bias) {
+        DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV, true><<<LN_BWD_BLOCKS, LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
+                                                   (const T *)gy, (const T *)s, mean, rstd, gamma, (T *)gs, (T *)gres, partials, rows, d, thr,
+                                                   dropout_scale(p_drop), seed, rng_offset)));
+    } else {
+        DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV, false><<<LN_BWD_BLOCKS, LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
+                                                   (const T *)gy, (const T *)s, mean, rstd, gamma, (T *)gs, (T *)gres, partials, rows, d, thr,
+                                                   dropout_scale(p_drop), seed, rng_offset)));
+    }
+    const int width = (dres_bias ? 3 : 2) * d;
+    reduce_partials_kernel<<<(width + 63) / 64, 256, 0, (cudaStream_t)stream>>>(partials, LN_BWD_BLOCKS, 3 * d, d, dgamma, dbeta, dres_bias);
     return check_launch("ln_residual_bwd");
 }
 
@@ -505,19 +574,29 @@ int cpm_gelu_fwd(const void *x, const float *bias, void *y, int64_t rows, int d,
     if (rows == 0) return CPM_OK;
     DISPATCH_DTYPE(dtype, gelu_kernel<T, false><<<grid_for(rows * (d / 16), 256), 256, 0, (cudaStream_t)stream>>>(
                               (const T *)x, bias, nullptr, (T *)y, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop), seed,
-                              rng_offset));
+                              rng_offset, nullptr));
     return check_launch("gelu_fwd");
 }
 
-int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, int64_t rows, int d, float p_drop, uint64_t seed,
-                 uint64_t rng_offset, int dtype, void *stream) {
+int cpm_gelu_bwd_partials_rows(int d) { return (d > 0 && 4096 % d == 0) ? GELU_BWD_BLOCKS * (4096 / d) : 0; }
+
+int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, float *dbias, float *partials, int64_t rows, int d, float p_drop,
+                 uint64_t seed, uint64_t rng_offset, int dtype, void *stream) {
     CPM_REQUIRE(x && gy && gx, CPM_ERR_NULL, "gelu_bwd: NULL pointer");
     CPM_REQUIRE(rows >= 0 && d > 0 && d % 16 == 0, CPM_ERR_BAD_SHAPE, "gelu_bwd: d=%d must be a multiple of 16", d);
     CPM_REQUIRE(aligned16(x) && aligned16(gy) && aligned16(gx) && (!bias || aligned16(bias)), CPM_ERR_BAD_ALIGN, "gelu_bwd: alignment");
     if (rows == 0) return CPM_OK;
+    if (dbias) {                                    // fused bias gradient: per-thread column sums -> partial rows -> one reduction
+        CPM_REQUIRE(partials && 4096 % d == 0, CPM_ERR_BAD_SHAPE, "gelu_bwd: the fused bias gradient needs d | 4096 (d=%d) and a partials buffer", d);
+        DISPATCH_DTYPE(dtype, gelu_kernel<T, true, true><<<GELU_BWD_BLOCKS, 256, 0, (cudaStream_t)stream>>>(
+                                  (const T *)x, bias, (const T *)gy, (T *)gx, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop),
+                                  seed, rng_offset, partials));
+        reduce_partials_kernel<<<(d + 63) / 64, 256, 0, (cudaStream_t)stream>>>(partials, cpm_gelu_bwd_partials_rows(d), d, d, dbias, nullptr, nullptr);
+        return check_launch("gelu_bwd");
+    }
     DISPATCH_DTYPE(dtype, gelu_kernel<T, true><<<grid_for(rows * (d / 16), 256), 256, 0, (cudaStream_t)stream>>>(
                               (const T *)x, bias, (const T *)gy, (T *)gx, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop), seed,
-                              rng_offset));
+                              rng_offset, nullptr));
     return check_launch("gelu_bwd");
 }
 

@@ -25,6 +25,15 @@ import torch.nn as nn
 from . import ops
 
 
+import os as _os
+# Bias folding (A/B switch for tools/, default off): "all" runs out-projection, linear1 and linear2 bias-less, adds their
+# biases inside the LayerNorm / GELU kernels and takes the bias gradients as by-products of those kernels' backward (no
+# column-sum passes over the gradient tensors); "gelu": linear1 only.  Measured on B200 (update phase of bench.py):
+# off 293-296 ms, gelu 296 ms, all 289-293 ms - the saved reductions (84 us for the (T, 2048) gradient, 21 us for the 512-wide
+# ones) are paid back by the heavier kernels (GELU backward 183 -> 309 us with the fused column sums), so the plain path stays.
+FUSED_BIAS_GRADS = {"0": False, "1": "all"}.get(_os.environ.get("CPM_FUSED_BIAS_GRADS", "0"), _os.environ.get("CPM_FUSED_BIAS_GRADS", "0"))
+
+
 class TriangularCausalMask:
     """``fast_transformers.masking.TriangularCausalMask(N, device=)``: only the
     ``lower_triangular`` flag is consulted by causal-linear attention."""
@@ -106,8 +115,11 @@ class PackCache:
         self._store.clear()
 
 
-def cached_linear(cache: PackCache, key, linears, x, dtype, pad_rows_to=1):
+def cached_linear(cache: PackCache, key, linears, x, dtype, pad_rows_to=1, use_bias=True):
+    """use_bias=False: the GEMM runs bias-less; the caller adds the (fp32 master) bias inside the next fused kernel."""
     wc, bc, rows, masters = cache.get(key, linears, dtype, pad_rows_to)
+    if not use_bias:
+        return ops.packed_linear(x, wc, None, rows, masters[:len(rows)])
     return ops.packed_linear(x, wc, bc, rows, masters)
 
 
@@ -159,10 +171,26 @@ class TransformerEncoder(nn.Module):
         dt, c, at = self.compute_dtype, self._cache, layer.attention
         qkv = cached_linear(c, ("qkv", i), [at.query_projection, at.key_projection, at.value_projection], x, dt)
         a = ops.causal_linear_attention_fused(qkv, self.n_heads, ops.EPS_ATTN, self.attn_impl)
-        o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
-        x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
-        h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)
-        g = ops.gelu_dropout(h, p)
+        # out-projection, linear1 and linear2 run bias-less: their biases are added inside the LayerNorm / GELU kernels,
+        # whose backward kernels return the bias gradients as by-products (no reduction pass over the gradient tensors)
+        if not FUSED_BIAS_GRADS:
+            o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
+            x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
+            h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)
+            g = ops.gelu_dropout(h, p)
+            f = cached_linear(c, ("ff2", i), [layer.linear2], g, dt)
+            return ops.ln_residual(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p)
+        if FUSED_BIAS_GRADS == "all":     # also the two 512-wide biases through the LayerNorm kernels (measured: a wash)
+            o = cached_linear(c, ("out", i), [at.out_projection], a, dt, use_bias=False)
+            x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p, res_bias=at.out_projection.bias)
+        else:
+            o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
+            x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
+        h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt, use_bias=False)
+        g = ops.gelu_dropout(h, p, bias=layer.linear1.bias)
+        if FUSED_BIAS_GRADS == "all":
+            f = cached_linear(c, ("ff2", i), [layer.linear2], g, dt, use_bias=False)
+            return ops.ln_residual(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p, res_bias=layer.linear2.bias)
         f = cached_linear(c, ("ff2", i), [layer.linear2], g, dt)
         return ops.ln_residual(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p)
 

@@ -425,79 +425,93 @@ def add_pe(x, pe, L, pos_offset=0, pos_dev=None, p_drop=0.0):
 # --------------------------------------------------------------------------- residual + LayerNorm
 class _LNResidual(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, res, gamma, beta, eps, p_drop):
+    def forward(ctx, x, res, gamma, beta, eps, p_drop, res_bias):
         _cuda(x, gamma, beta)
         x = x.contiguous()
         res = res.contiguous() if res is not None else None
+        if res_bias is not None and (res is None or res_bias.dtype != torch.float32):
+            raise ValueError("res_bias needs a residual branch and must be float32")
         d = x.shape[-1]
         rows = x.numel() // d
-        need = any(ctx.needs_input_grad[:4])
+        need = any(ctx.needs_input_grad[:4]) or ctx.needs_input_grad[6]
         y = torch.empty_like(x)
         s = torch.empty_like(x) if need else None
         mean = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
         rstd = torch.empty(rows, dtype=torch.float32, device=x.device) if need else None
         use_drop = p_drop > 0 and res is not None
         seed, off = _Rng.take(x.numel()) if use_drop else (0, 0)
-        check(_lib.load().cpm_ln_residual_fwd(_p(x), _p(res), _p(gamma), _p(beta), _p(y), _p(s), _p(mean), _p(rstd), rows, d,
+        check(_lib.load().cpm_ln_residual_fwd(_p(x), _p(res), _p(res_bias), _p(gamma), _p(beta), _p(y), _p(s), _p(mean), _p(rstd), rows, d,
                                               eps, p_drop if use_drop else 0.0, seed, off, _dt(x), _st()))
         if need:
             ctx.save_for_backward(s, mean, rstd, gamma)
-        ctx.cfg = (p_drop if use_drop else 0.0, seed, off, res is not None)
+        ctx.cfg = (p_drop if use_drop else 0.0, seed, off, res is not None, res_bias is not None)
         return y
 
     @staticmethod
     def backward(ctx, gy):
         s, mean, rstd, gamma = ctx.saved_tensors
-        p_drop, seed, off, has_res = ctx.cfg
+        p_drop, seed, off, has_res, has_rb = ctx.cfg
         gy = gy.contiguous()
         d = s.shape[-1]
         rows = s.numel() // d
         lib = _lib.load()
         gs = torch.empty_like(s)
         gres = torch.empty_like(s) if (has_res and p_drop > 0) else None
-        dgamma = torch.zeros(d, dtype=torch.float32, device=s.device)
-        dbeta = torch.zeros(d, dtype=torch.float32, device=s.device)
-        partials = torch.empty(lib.cpm_ln_partials_rows() * 2 * d, dtype=torch.float32, device=s.device)
-        check(lib.cpm_ln_residual_bwd(_p(gy), _p(s), _p(mean), _p(rstd), _p(gamma), _p(gs), _p(gres), _p(dgamma), _p(dbeta),
-                                      _p(partials), rows, d, p_drop, seed, off, _dt(s), _st()))
+        acc = torch.zeros(3, d, dtype=torch.float32, device=s.device)          # dgamma | dbeta | dres_bias
+        partials = torch.empty(lib.cpm_ln_partials_rows() * 3 * d, dtype=torch.float32, device=s.device)
+        check(lib.cpm_ln_residual_bwd(_p(gy), _p(s), _p(mean), _p(rstd), _p(gamma), _p(gs), _p(gres), _p(acc[0]), _p(acc[1]),
+                                      _p(acc[2]) if has_rb else None, _p(partials), rows, d, p_drop, seed, off, _dt(s), _st()))
         g_res = (gres if gres is not None else gs) if has_res else None
-        return gs, g_res, dgamma.to(gamma.dtype), dbeta.to(gamma.dtype), None, None
+        return gs, g_res, acc[0].to(gamma.dtype), acc[1].to(gamma.dtype), None, None, (acc[2] if has_rb else None)
 
 
-def ln_residual(x, res, gamma, beta, eps=EPS_LN, p_drop=0.0):
-    """LayerNorm(x + dropout(res)) with fp32 affine parameters."""
-    return _LNResidual.apply(x, res, gamma, beta, eps, p_drop)
+def ln_residual(x, res, gamma, beta, eps=EPS_LN, p_drop=0.0, res_bias=None):
+    """LayerNorm(x + dropout(res + res_bias)) with fp32 affine parameters.  res_bias (fp32 (d), optional) is the bias of the
+    Linear that produced ``res``: passing it here lets that GEMM run bias-less and makes the bias gradient a by-product of
+    the backward kernel instead of a separate reduction over the gradient tensor."""
+    return _LNResidual.apply(x, res, gamma, beta, eps, p_drop, res_bias)
 
 
 # --------------------------------------------------------------------------- GELU
 class _Gelu(torch.autograd.Function):
     @staticmethod
-    def forward(ctx, x, p_drop):
+    def forward(ctx, x, p_drop, bias):
         _cuda(x)
         x = x.contiguous()
         d = x.shape[-1]
         rows = x.numel() // d
+        if bias is not None and (bias.dtype != torch.float32 or bias.numel() != d):
+            raise ValueError("gelu bias must be float32 of the row width")
         seed, off = _Rng.take(x.numel()) if p_drop > 0 else (0, 0)
         y = torch.empty_like(x)
-        check(_lib.load().cpm_gelu_fwd(_p(x), None, _p(y), rows, d, p_drop, seed, off, _dt(x), _st()))
-        ctx.save_for_backward(x)
+        check(_lib.load().cpm_gelu_fwd(_p(x), _p(bias), _p(y), rows, d, p_drop, seed, off, _dt(x), _st()))
+        ctx.save_for_backward(x, bias)
         ctx.rng = (p_drop, seed, off)
         return y
 
     @staticmethod
     def backward(ctx, gy):
-        (x,) = ctx.saved_tensors
+        x, bias = ctx.saved_tensors
         p_drop, seed, off = ctx.rng
         gy = gy.contiguous()
         d = x.shape[-1]
         gx = torch.empty_like(x)
-        check(_lib.load().cpm_gelu_bwd(_p(x), None, _p(gy), _p(gx), x.numel() // d, d, p_drop, seed, off, _dt(x), _st()))
-        return gx, None
+        lib = _lib.load()
+        dbias = partials = None
+        fused = bias is not None and ctx.needs_input_grad[2] and lib.cpm_gelu_bwd_partials_rows(d) > 0
+        if fused:
+            dbias = torch.zeros(d, dtype=torch.float32, device=x.device)
+            partials = torch.empty(lib.cpm_gelu_bwd_partials_rows(d) * d, dtype=torch.float32, device=x.device)
+        check(lib.cpm_gelu_bwd(_p(x), _p(bias), _p(gy), _p(gx), _p(dbias), _p(partials), x.numel() // d, d, p_drop, seed, off, _dt(x), _st()))
+        if bias is not None and ctx.needs_input_grad[2] and not fused:
+            dbias = gx.reshape(-1, d).sum(0, dtype=torch.float32)
+        return gx, None, dbias
 
 
-def gelu_dropout(x, p_drop=0.0):
-    """dropout(gelu(x)) with the exact-erf GELU ft uses (activation='gelu')."""
-    return _Gelu.apply(x, p_drop)
+def gelu_dropout(x, p_drop=0.0, bias=None):
+    """dropout(gelu(x + bias)) with the exact-erf GELU ft uses (activation='gelu').  bias (fp32, optional): the bias of the
+    Linear that produced x — its gradient is then a by-product of the backward kernel."""
+    return _Gelu.apply(x, p_drop, bias)
 
 
 # --------------------------------------------------------------------------- heads: decode / logp / CE

@@ -250,6 +250,17 @@ def test_ln_residual(cuda, cpm, d, dtype, tol):
     gtol = 2e-3 if dtype == torch.float32 else 0.3
     _cmp(gamma.grad, gr.grad, gtol, 1e-3 if dtype == torch.float32 else 3e-2, "dgamma")
     _cmp(beta.grad, br.grad, gtol, 1e-3 if dtype == torch.float32 else 3e-2, "dbeta")
+    # residual-branch bias folded in (the producing Linear runs bias-less); its gradient is a by-product of the backward
+    rb = (0.5 * torch.randn(d, generator=gen)).to(cuda).requires_grad_()
+    x2, r2 = x.detach().clone().requires_grad_(), r.detach().clone().requires_grad_()
+    y3 = cpm.ops.ln_residual(x2, r2, gamma.detach(), beta.detach(), res_bias=rb)
+    y3.backward(go)
+    xr2, rr2, rbr = x.detach().double().requires_grad_(), r.detach().double().requires_grad_(), rb.detach().double().requires_grad_()
+    yr3 = torch.nn.functional.layer_norm(xr2 + rr2 + rbr, (d,), gr.detach(), br.detach(), 1e-5)
+    yr3.backward(go.double())
+    _cmp(y3, yr3, tol, tol, "y with res_bias")
+    _cmp(r2.grad, rr2.grad, tol * 3, tol * 3, "gres with res_bias")
+    _cmp(rb.grad, rbr.grad, gtol, 1e-3 if dtype == torch.float32 else 3e-2, "dres_bias")
     # no residual (the encoder's final norm)
     y2 = cpm.ops.ln_residual(x.detach(), None, gamma.detach(), beta.detach())
     _cmp(y2, torch.nn.functional.layer_norm(x.detach().double(), (d,), gr.detach(), br.detach(), 1e-5), tol, tol, "y no-res")
@@ -280,6 +291,17 @@ def test_gelu(cuda, cpm, dtype, tol):
     yr.backward(go.double())
     _cmp(y, yr, tol, tol, "gelu")
     _cmp(x.grad, xr.grad, tol * 2, tol * 2, "dgelu")
+    # bias folded in (linear1 runs bias-less); the bias gradient comes out of the backward kernel's column sums
+    b = torch.randn(2048, generator=gen).to(cuda).requires_grad_()
+    x2 = x.detach().clone().requires_grad_()
+    y2 = cpm.ops.gelu_dropout(x2, 0.0, bias=b)
+    y2.backward(go)
+    xr2, brf = x.detach().double().requires_grad_(), b.detach().double().requires_grad_()
+    yr2 = torch.nn.functional.gelu(xr2 + brf)
+    yr2.backward(go.double())
+    _cmp(y2, yr2, tol, tol, "gelu(x + bias)")
+    _cmp(x2.grad, xr2.grad, tol * 2, tol * 2, "dgelu with bias")
+    _cmp(b.grad, brf.grad, 2e-3 if dtype == torch.float32 else 0.3, 1e-3 if dtype == torch.float32 else 3e-2, "dbias (fused column sums)")
 
 
 # ------------------------------------------------------------------ heads: decode / logp / CE

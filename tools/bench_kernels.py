@@ -77,9 +77,16 @@ def main():
     gam, bet = torch.ones(d, device=dev, requires_grad=True), torch.zeros(d, device=dev, requires_grad=True)
     fwd_bwd("ln_residual(+dropout)", lambda: ops.ln_residual(xr, res, gam, bet, 1e-5, 0.1), [xr, res, gam, bet],
             T * d * 2 * 4, T * d * 2 * 4, "fwd: x,res in; y,s out.  bwd: gy,s in; gs,gres out")
+    rb = torch.zeros(d, device=dev, requires_grad=True)
+    fwd_bwd("ln_residual(+bias+dropout)", lambda: ops.ln_residual(xr, res, gam, bet, 1e-5, 0.1, res_bias=rb), [xr, res, gam, bet, rb],
+            T * d * 2 * 4, T * d * 2 * 4, "residual-branch bias folded in; bwd also returns its gradient")
     # ---- GELU + dropout
     h = rnd(T, dff).requires_grad_()
     fwd_bwd("gelu+dropout", lambda: ops.gelu_dropout(h, 0.1), [h], T * dff * 4, T * dff * 6)
+    hb = torch.zeros(dff, device=dev, requires_grad=True)
+    fwd_bwd("gelu+bias+dropout", lambda: ops.gelu_dropout(h, 0.1, bias=hb), [h, hb], T * dff * 4, T * dff * 6, "bwd also returns the bias gradient")
+    gyb = rnd(T, dff)
+    timeit("torch column sum (T x 2048 bf16 -> fp32)", lambda: gyb.sum(0, dtype=torch.float32), T * dff * 2, "what the fused bias gradient replaces")
     # ---- heads: log-prob / entropy, masked CE
     seg = ops.seg_offsets(VOCAB)
     lg = rnd(T, 344).requires_grad_()
