@@ -395,6 +395,134 @@ cp_prefix_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
 }
 
 // =============================================================================================
+// B1s: streaming suffix states (the backward twin of F1s).  One CTA per (batch, head) walks its chunks from the last to
+// the first: G' = go/den, gd = -(go.out)/den (stored per token for B3), R += Qf^T G' and rz += Qf^T gd accumulate in TMEM
+// and are snapshotted after every chunk into the bf16 suffix tile of the PREVIOUS chunk - no fp32 increments, no scan.
+// Operand prep of chunk c-1 overlaps the UMMA of chunk c; q / go / out tiles are double-buffered by TMA.
+// =============================================================================================
+constexpr int SB_STAGES = 2;
+constexpr uint32_t SB_STAGE_BYTES = 3 * TILE_BYTES;                             // q | go | out
+constexpr uint32_t SB_OFF_GD = SB_STAGES * SB_STAGE_BYTES;                      // 2 x [8 rows x 128 tokens] K-major bf16: row 0 gd_hi, row 1 gd_lo
+constexpr uint32_t SB_OFF_BAR = SB_OFF_GD + 2 * 2048, SB_SMEM = SB_OFF_BAR + 64;
+constexpr uint32_t IDESC_RZ = idesc_bf16(64, 8, true, false);                   // A = Qf (MN-major), B = gd tile (K-major)
+constexpr uint32_t TSB_R = 0, TSB_RZ = 64;
+
+__global__ void __launch_bounds__(NTH)
+cp_suffix_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmGo,
+                            const __grid_constant__ CUtensorMap tmO, const float *__restrict__ den, float *__restrict__ gd_out,
+                            uint8_t *__restrict__ tiles, float *__restrict__ rzs, int L, int H, int nchunks) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint8_t *sGd = sm + SB_OFF_GD;
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + SB_OFF_BAR);        // [SB_STAGES]
+    uint64_t *bar_mma = bar_full + SB_STAGES;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_mma + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int nh = blockIdx.x, n = nh / H, h = nh % H;
+    const int row0 = n * L, col0 = h * 64;
+    auto chunk_of = [&](int w) { return nchunks - 1 - w; };                    // work item w = 0 .. C-1 walks the chunks backwards
+    auto issue = [&](int w) {                                                  // tid 0
+        const int s = w % SB_STAGES, c = chunk_of(w);
+        uint8_t *st = sm + s * SB_STAGE_BYTES;
+        mbar_expect_tx(bar_full + s, (c > 0 ? 3 : 2) * TILE_BYTES);
+        tma_load_2d(st + TILE_BYTES, &tmGo, bar_full + s, col0, row0 + c * CHUNK);
+        tma_load_2d(st + 2 * TILE_BYTES, &tmO, bar_full + s, col0, row0 + c * CHUNK);
+        if (c > 0) tma_load_2d(st, &tmQ, bar_full + s, col0, row0 + c * CHUNK);
+    };
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        for (int s = 0; s < SB_STAGES; ++s) mbar_init(bar_full + s, 1);
+        mbar_init(bar_mma, 1);
+        fence_barrier_init();
+        for (int w = 0; w < SB_STAGES && w < nchunks; ++w) issue(w);
+    }
+    if (warp == 0) tmem_alloc<128>(tmem_slot);
+    for (int i = tid; i < 1024; i += NTH) reinterpret_cast<uint32_t *>(sGd)[i] = 0u;      // rows 2..7 of both gd tiles stay zero
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    const int prow = tid >> 1, phalf = tid & 1;                                 // operand prep: two ADJACENT threads per token row
+    const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
+    const int erow = 16 * (warp & 3) + (lane & 15), shalf = warp >> 2;          // snapshot: M=64 accumulator rows, column halves
+    float den_reg = den[(int64_t)(row0 + chunk_of(0) * CHUNK + prow) * H + h];
+    auto prep = [&](int w) {
+        const int s = w % SB_STAGES, c = chunk_of(w);
+        uint8_t *sQ = sm + s * SB_STAGE_BYTES, *sG = sQ + TILE_BYTES, *sO = sQ + 2 * TILE_BYTES;
+        const float inv = 1.f / den_reg;
+        if (w + 1 < nchunks) den_reg = den[(int64_t)(row0 + chunk_of(w + 1) * CHUNK + prow) * H + h];   // in flight during this prep
+        mbar_wait(bar_full + s, (w / SB_STAGES) & 1);
+        float dot = 0.f;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t off = sw128_off(prow, 4 * phalf + cc);
+            float gg[8], o[8];
+            const uint4 graw = *reinterpret_cast<const uint4 *>(sG + off);
+            unpack8(graw, gg);
+            unpack8(*reinterpret_cast<const uint4 *>(sO + off), o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) dot = fmaf(gg[i], o[i], dot);
+            if (c > 0) {
+                *reinterpret_cast<uint4 *>(sG + off) = make_uint4(scale2(graw.x, inv), scale2(graw.y, inv), scale2(graw.z, inv), scale2(graw.w, inv));
+                *reinterpret_cast<uint4 *>(sQ + off) = phi8_lean(*reinterpret_cast<const uint4 *>(sQ + off));
+            }
+        }
+        dot += __shfl_xor_sync(0xffffffffu, dot, 1);
+        const float gd = -inv * dot;
+        if (phalf == 0) {
+            gd_out[(int64_t)(row0 + c * CHUNK + prow) * H + h] = gd;
+            if (c > 0) {
+                const __nv_bfloat16 hi = __float2bfloat16_rn(gd), lo = __float2bfloat16_rn(gd - __bfloat162float(hi));
+                uint8_t *gt = sGd + (w & 1) * 2048 + (prow >> 6) * 1024;
+                const int i63 = prow & 63;
+                *reinterpret_cast<__nv_bfloat16 *>(gt + 0 * 128 + (((i63 >> 3) ^ 0) << 4) + (i63 & 7) * 2) = hi;
+                *reinterpret_cast<__nv_bfloat16 *>(gt + 1 * 128 + (((i63 >> 3) ^ 1) << 4) + (i63 & 7) * 2) = lo;
+            }
+        }
+    };
+    prep(0);
+    fence_proxy_async();
+    tc_fence_before();
+    __syncthreads();
+    for (int w = 0; w + 1 < nchunks; ++w) {                                     // chunks C-1 .. 1 feed the suffixes of chunks C-2 .. 0
+        const int s = w % SB_STAGES, c = chunk_of(w);
+        if (tid == 0) {
+            tc_fence_after();
+            const uint64_t dQ = smem_desc_sw128(smem_u32(sm + s * SB_STAGE_BYTES)), dG = smem_desc_sw128(smem_u32(sm + s * SB_STAGE_BYTES + TILE_BYTES));
+            const uint64_t dGd = smem_desc_sw128(smem_u32(sGd + (w & 1) * 2048));
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem + TSB_R, dQ + 128 * k, dG + 128 * k, IDESC_MM64, (w > 0 || k > 0) ? 1u : 0u);
+#pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem + TSB_RZ, dQ + 128 * k, dGd + (k >> 2) * 64 + 2 * (k & 3), IDESC_RZ, (w > 0 || k > 0) ? 1u : 0u);
+            mma_commit(bar_mma);
+        }
+        prep(w + 1);                                                            // overlaps the UMMA of chunk c
+        mbar_wait(bar_mma, w & 1);
+        tc_fence_after();
+        const int64_t slot = (int64_t)nh * nchunks + c - 1;
+        {
+            uint32_t r[32];
+            tmem_ld32(t_lane + TSB_R + 32 * shalf, r);
+            uint32_t z8[8];
+            if (shalf == 0) tmem_ld8(t_lane + TSB_RZ, z8);
+            tmem_ld_wait();
+            if (lane < 16) {
+                uint8_t *dst = tiles + slot * S_TILE_BYTES + erow * 128 + 64 * shalf;
+#pragma unroll
+                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(dst + 16 * cc) = pack8u(r + 8 * cc, 1.f);
+                if (shalf == 0) rzs[slot * 64 + erow] = __uint_as_float(z8[0]) + __uint_as_float(z8[1]);
+            }
+        }
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();                                                        // TMEM rows read; stage s consumed; prep(w+1) visible
+        if (tid == 0 && w + SB_STAGES < nchunks) issue(w + SB_STAGES);
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 0) tmem_dealloc<128>(tmem);
+}
+
+// =============================================================================================
 // F2 / B2: exclusive prefix (reverse = 0) or exclusive suffix (reverse = 1) of the per-chunk increments over
 // the chunk axis; fp32 accumulation, bf16 state tile + fp32 z out.  One thread = 4 consecutive state floats.
 // =============================================================================================
@@ -918,13 +1046,19 @@ int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const voi
     if ((rc = make_tmap_bf16_2d(&to, out, inner, rows, ld_o, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&ts, sp_region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
     if ((rc = make_tmap_bf16_2d(&tr, rs_region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
-    static bool a1 = false, a3 = false;
+    static bool a1 = false, a3 = false, a5 = false;
     if ((rc = set_smem_once((const void *)cp_state_bwd_kernel, PB_SMEM, &a1, "cp_state_bwd"))) return rc;
     if ((rc = set_smem_once((const void *)cp_bwd_main_kernel, B_SMEM, &a3, "cp_bwd_main"))) return rc;
-    cp_state_bwd_kernel<<<(unsigned)nhc, 128, PB_SMEM, st>>>(tq, tgo, to, den, gd, part, L, H, nchunks);
-    if (nchunks > 1)
-        cp_scan_kernel<<<dim3(N * H, (STATE_FLOATS / 4 + 255) / 256), 256, 0, st>>>(part, rs_region,
-                                                                                    reinterpret_cast<float *>(rs_region + state_tiles_bytes(nhc)), nchunks, 1);
+    if ((rc = set_smem_once((const void *)cp_suffix_stream_bwd_kernel, SB_SMEM, &a5, "cp_suffix_stream_bwd"))) return rc;
+    if (N * H >= 96) {                                  // enough independent (batch, head) chains: stream, no scan
+        cp_suffix_stream_bwd_kernel<<<N * H, NTH, SB_SMEM, st>>>(tq, tgo, to, den, gd, rs_region,
+                                                                 reinterpret_cast<float *>(rs_region + state_tiles_bytes(nhc)), L, H, nchunks);
+    } else {
+        cp_state_bwd_kernel<<<(unsigned)nhc, 128, PB_SMEM, st>>>(tq, tgo, to, den, gd, part, L, H, nchunks);
+        if (nchunks > 1)
+            cp_scan_kernel<<<dim3(N * H, (STATE_FLOATS / 4 + 255) / 256), 256, 0, st>>>(part, rs_region,
+                                                                                        reinterpret_cast<float *>(rs_region + state_tiles_bytes(nhc)), nchunks, 1);
+    }
     BwdMainArgs a;
     a.den = den; a.gd = gd;
     a.zp = reinterpret_cast<const float *>(sp_region + state_tiles_bytes(nhc));
