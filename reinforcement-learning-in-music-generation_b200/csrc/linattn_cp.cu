@@ -10,6 +10,8 @@
 //             F3  cp_out_fwd      per chunk         : P = Qf Kf^T (masked), O = Qf Sp_c + P V, den = rowsum P + Qf.zp_c
 //   backward  B1  cp_state_bwd    per chunk         : G' = go/den, gd = -(go.out)/den, dR_c = Qf_c^T G'_c, drz_c = Qf_c^T gd
 //             B2  cp_scan (reverse)                 : exclusive suffix over c  -> Rs_c (bf16 tile), rzs_c (fp32)
+//             (F1+F2 and B1+B2 are replaced by the streaming kernels F1s / B1s - one CTA per (batch, head) accumulating the
+//              state in TMEM across chunks - whenever there are >= 96 (batch, head) chains to fill the GPU)
 //             B3  cp_bwd_main     per chunk         : dq, dk, dv of the chunk from (q,k,v,go) + Sp_c + Rs_c, all within the CTA
 //
 // HBM traffic per (chunk, head): forward reads q,k,v (48 KB) and writes out (16 KB) + den; k,v are read a
