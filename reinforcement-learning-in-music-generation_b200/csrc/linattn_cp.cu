@@ -692,10 +692,11 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // =============================================================================================
 // B3: dq, dk, dv of one chunk.  256 threads, 256 TMEM columns, 2 CTAs / SM, persistent over tiles.
 //   X[i][j]  = G'[i].v[j] + gd_i   (j <= i)        dQf = X Kf + G' Sp^T + gd z         dq = dQf * phi'(q)
+//                                                  dKf = X^T Qf + v Rs^T + rz          dk = dKf * phi'(k)
 //   PT[j][i] = Kf[j].Qf[i]         (i >= j)        dv  = PT G' + Kf Rs
-//   WT[j][i] = v[j].G'[i] + gd_i   (i >= j)        dKf = WT Qf + v Rs^T + rz           dk = dKf * phi'(k)
-// Loads are split over two barriers so the tiles that die first (K, G' after round 3) are refilled for the next
-// tile a whole round before the rest (Q, V, Sp, Rs after round 4).
+// Three UMMA rounds: X; {dQf, dKf, PT}; dv.  X^T costs nothing: the stored score tile is read as an MN-major A operand.
+// Loads are split over two barriers so the tiles that die first (Q, V, Sp after round 2) are refilled for the next
+// tile a whole round before the rest (K, G', Rs after round 3).
 // =============================================================================================
 constexpr uint32_t B_OFF_Q = 0, B_OFF_K = 16384, B_OFF_V = 32768, B_OFF_G = 49152, B_OFF_S = 65536, B_OFF_R = 73728, B_OFF_X = 81920;
 constexpr uint32_t B_OFF_GD = 114688 /* 128 floats: gd, later rz */, B_OFF_Z = B_OFF_GD + 512 /* 64 floats */, B_OFF_BAR = B_OFF_Z + 256,
@@ -745,23 +746,23 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int n = nh / a.H, h = nh % a.H;
         grow = n * a.L + c * CHUNK; col0 = h * 64;
     };
-    auto issue_a = [&](int t) {                       // tid 0: K and go tiles
+    auto issue_a = [&](int t) {                       // tid 0: the tiles that die last (after round 3): K, go, Rs
         int c, nh, grow, col0;
         tile_coords(t, c, nh, grow, col0);
-        mbar_expect_tx(bar_a, 2 * TILE_BYTES);
+        const bool hr = c + 1 < a.nchunks;
+        mbar_expect_tx(bar_a, 2 * TILE_BYTES + (hr ? S_TILE_BYTES : 0));
         tma_load_2d(sK, &tmK, bar_a, col0, grow);
         tma_load_2d(sG, &tmGo, bar_a, col0, grow);
+        if (hr) tma_load_2d(sR, &tmR, bar_a, 0, (int)(((int64_t)nh * a.nchunks + c) * 64));
     };
-    auto issue_b = [&](int t) {                       // tid 0: Q, V and the two carried-state tiles
+    auto issue_b = [&](int t) {                       // tid 0: the tiles that die after round 2: Q, V, Sp
         int c, nh, grow, col0;
         tile_coords(t, c, nh, grow, col0);
-        const bool hs = c > 0, hr = c + 1 < a.nchunks;
-        const int srow = (int)(((int64_t)nh * a.nchunks + c) * 64);
-        mbar_expect_tx(bar_b, 2 * TILE_BYTES + (hs ? S_TILE_BYTES : 0) + (hr ? S_TILE_BYTES : 0));
+        const bool hs = c > 0;
+        mbar_expect_tx(bar_b, 2 * TILE_BYTES + (hs ? S_TILE_BYTES : 0));
         tma_load_2d(sQ, &tmQ, bar_b, col0, grow);
         tma_load_2d(sV, &tmV, bar_b, col0, grow);
-        if (hs) tma_load_2d(sS, &tmS, bar_b, 0, srow);
-        if (hr) tma_load_2d(sR, &tmR, bar_b, 0, srow);
+        if (hs) tma_load_2d(sS, &tmS, bar_b, 0, (int)(((int64_t)nh * a.nchunks + c) * 64));
     };
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
@@ -769,7 +770,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_init(bar_b, 1);
         mbar_init(bar_mma, 1);
         fence_barrier_init();
-        if ((int)blockIdx.x < ntiles) { issue_a(blockIdx.x); issue_b(blockIdx.x); }
+        if ((int)blockIdx.x < ntiles) { issue_b(blockIdx.x); issue_a(blockIdx.x); }
     }
     if ((tid >> 5) == 0) tmem_alloc<256>(tmem_slot);
     tc_fence_before();
@@ -780,6 +781,11 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
     const uint64_t dG = smem_desc_sw128(smem_u32(sG)), dS = smem_desc_sw128(smem_u32(sS)), dR = smem_desc_sw128(smem_u32(sR));
     const uint64_t dX = smem_desc_sw128(smem_u32(sX));
+    // The masked score tile X (rows i, 64 j contiguous per 128-byte row, two 16 KB blocks for j < 64 / j >= 64) read as an
+    // MN-major A operand IS its transpose: M = j (two 64-wide atoms, LBO = one block apart), K = i.  WT = X^T (same values, same
+    // mask) therefore needs no UMMA and no conversion pass of its own.
+    const uint64_t dXT = smem_desc_sw128(smem_u32(sX), TILE_BYTES, 1024);
+    constexpr uint32_t IDESC_MM128 = idesc_bf16(128, 64, true, true);
     // per-row scalars of the first tile; later tiles' are prefetched one tile ahead
     float inv_n = 0.f, gd_n = 0.f;
     if ((int)blockIdx.x < ntiles) {
@@ -797,10 +803,9 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         const int64_t slot = (int64_t)nh * a.nchunks + c;
         const int tn = t + gridDim.x;
         const float inv = inv_n, gd = gd_n;
-        float z_cur = 0.f, rz_cur = 0.f;                   // tid < 64
-        if (tid < 64) {
-            if (have_s) z_cur = a.zp[slot * 64 + tid];
-            if (have_r) rz_cur = a.rzs[slot * 64 + tid];
+        if (tid < 64) {                                    // z (dq epilogue) and rz (dk epilogue) of this tile
+            sz[tid] = have_s ? a.zp[slot * 64 + tid] : 0.f;
+            sgd[tid] = have_r ? a.rzs[slot * 64 + tid] : 0.f;
         }
         if (tn < ntiles) {                                // next tile's per-row scalars: in flight for the whole tile
             int c2, nh2, grow2, col2;
@@ -809,9 +814,16 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             inv_n = a.den[ri];
             gd_n = a.gd[ri];
         }
-        if (g.half == 0) sgd[g.row] = gd;
-        if (tid < 64) sz[tid] = z_cur;
         uint32_t qfr[16], kfr[16];                         // this thread's Qf / Kf values (packed bf16) for phi'
+        mbar_wait(bar_b, ph_b);
+        ph_b ^= 1;
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
+            const uint4 qv = phi8_lean(*reinterpret_cast<const uint4 *>(sQ + off));
+            *reinterpret_cast<uint4 *>(sQ + off) = qv;
+            qfr[4 * cc + 0] = qv.x; qfr[4 * cc + 1] = qv.y; qfr[4 * cc + 2] = qv.z; qfr[4 * cc + 3] = qv.w;
+        }
         mbar_wait(bar_a, ph_a);
         ph_a ^= 1;
 #pragma unroll
@@ -822,15 +834,6 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             const uint4 kv = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
             *reinterpret_cast<uint4 *>(sK + off) = kv;
             kfr[4 * cc + 0] = kv.x; kfr[4 * cc + 1] = kv.y; kfr[4 * cc + 2] = kv.z; kfr[4 * cc + 3] = kv.w;
-        }
-        mbar_wait(bar_b, ph_b);
-        ph_b ^= 1;
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
-            const uint4 qv = phi8_lean(*reinterpret_cast<const uint4 *>(sQ + off));
-            *reinterpret_cast<uint4 *>(sQ + off) = qv;
-            qfr[4 * cc + 0] = qv.x; qfr[4 * cc + 1] = qv.y; qfr[4 * cc + 2] = qv.z; qfr[4 * cc + 3] = qv.w;
         }
         fence_proxy_async();
         tc_fence_before();
@@ -849,7 +852,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        // ---- round 2: dQf = X Kf (+ G' Sp^T) ; PT = Kf Qf^T
+        // ---- round 2: dQf = X Kf (+ G' Sp^T) ; dKf = X^T Qf (+ v Rs^T) ; PT = Kf Qf^T
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
@@ -860,81 +863,60 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
                 for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dG + 2 * k, dS + 2 * k, IDESC_KK64, 1);
             }
 #pragma unroll
+            for (int k = 0; k < 8; ++k) mma_ss(tmem + TB_A2, dXT + 128 * k, dQ + 128 * k, IDESC_MM128, k > 0);
+            if (have_r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A2, dV + 2 * k, dR + 2 * k, IDESC_KK64, 1);
+            }
+#pragma unroll
             for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dQ + 2 * k, IDESC_KK128, k > 0);
             mma_commit(bar_mma);
         }
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        {   // dq rows
+        if (tid == 0 && tn < ntiles) issue_b(tn);          // Q, V, Sp are dead: refill them a round early
+        {   // dq and dk rows
             uint32_t r[32];
             tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
             tmem_ld_wait();
             uint4 o[4];
             grad_row_epilogue<true>(r, qfr, sz + 32 * g.half, gd, o);
             store_row32(a.gq, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+            tmem_ld32(g.t_lane + TB_A2 + 32 * g.half, r);
+            tmem_ld_wait();
+            grad_row_epilogue<true>(r, kfr, sgd + 32 * g.half, 1.f, o);
+            store_row32(a.gk, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
         }
         convert_lean<false, false, false>(g, TB_X, sX, 0.f, nullptr);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
-        // ---- round 3: dv = PT G' (+ Kf Rs) ; WT = V G'^T
+        // ---- round 3: dv = PT G' (+ Kf Rs)
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
             for (int k = 0; k < 8; ++k)
-                mma_ss(tmem + TB_A2, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
+                mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
             if (have_r) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A2, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);
             }
-#pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dV + 2 * k, dG + 2 * k, IDESC_KK128, k > 0);
             mma_commit(bar_mma);
         }
+        if (tn < ntiles) inv_n = 1.f / inv_n;              // (prefetched den of the next tile)
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
-        if (tid == 0 && tn < ntiles) issue_a(tn);          // K and G' are dead: refill them a round early
+        if (tid == 0 && tn < ntiles) issue_a(tn);
         {   // dv rows
             uint32_t r[32];
-            tmem_ld32(g.t_lane + TB_A2 + 32 * g.half, r);
+            tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
             tmem_ld_wait();
             uint4 o[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, 1.f);
             store_row32(a.gv, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
-        }
-        convert_lean<false, false, true>(g, TB_X, sX, 0.f, sgd);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();                                  // every thread is done with sgd (column adds)
-        if (tid < 64) sgd[tid] = rz_cur;                   // the gd slots now carry rz for the dk epilogue
-        // ---- round 4: dKf = WT Qf (+ v Rs^T)
-        if (tid == 0) {
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dQ + 128 * k, IDESC_KM64, k > 0);
-            if (have_r) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dV + 2 * k, dR + 2 * k, IDESC_KK64, 1);
-            }
-            mma_commit(bar_mma);
-        }
-        inv_n = 1.f / inv_n;                               // (prefetched den of the next tile)
-        __syncthreads();                                  // rz visible
-        mbar_wait(bar_mma, ph_mma);
-        ph_mma ^= 1;
-        tc_fence_after();
-        if (tid == 0 && tn < ntiles) issue_b(tn);
-        {   // dk rows
-            uint32_t r[32];
-            tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
-            tmem_ld_wait();
-            uint4 o[4];
-            grad_row_epilogue<true>(r, kfr, sgd + 32 * g.half, 1.f, o);
-            store_row32(a.gk, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
         }
         tc_fence_before();
         __syncthreads();                                  // TMEM accumulators, sgd, sz are reused by the next tile
