@@ -35,8 +35,8 @@ VOCAB = [56, 135, 18, 87, 18, 25]            # AIlabs-Pop1K7 dictionary without 
 SONGS_PER_GPU, ROLLOUT_LEN = 256, 1024
 MINIBATCH = int(os.environ.get("CPM_MINIBATCH", "64"))          # sequences per update minibatch (gradient accumulation over 256/MINIBATCH)
 # DRAM bytes of one linear-attention fwd+bwd launch group measured with ncu (cold L2), keyed by the update minibatch shape:
-# fwd 117.5+10.0 (prefix) + 231.8+44.0 (output) MB, bwd 195.1+38.2 (pre-pass) + 59.6+0.9 (scan) + 333.6+156.5 (main) MB
-LINATTN_DRAM_BYTES_PER_PAIR = {(64, 1024): 1_187_200_000}
+# fwd 117.5+6.8 (streaming prefix) + 231.8+41.8 (per-chunk output) MB, bwd 195.1+17.4 (streaming suffix) + 334.1+153.9 (main) MB
+LINATTN_DRAM_BYTES_PER_PAIR = {(64, 1024): 1_098_400_000}
 METRIC = "CP tokens/s, PPO rollout+update"
 UNIT = "tokens/s"
 
@@ -398,7 +398,7 @@ def run_gpu(args, rank, world):
     achieved = (bytes_fwd + bytes_bwd) / (ms_pair * 1e-3) / 1e9 if ms_pair > 0 else 0.0
     roofline = {"kernel": f"linattn fwd+bwd ({cpmusic.ops.linattn_last_impl()})", "bound": "hbm", "achieved": achieved, "peak": peak,
                 "unit": "GB/s", "frac": achieved / peak, "traffic": LINATTN_DRAM_BYTES_PER_PAIR.get((MINIBATCH, ROLLOUT_LEN)),
-                "traffic_source": "ncu dram__bytes_read+write per fwd+bwd launch group (profiles/r01_ncu_linattn_cp_{fwd,bwd}_64x1024x8.csv)",
+                "traffic_source": "ncu dram__bytes_read+write per fwd+bwd launch group (profiles/r01_ncu_linattn_cp_final_64x1024x8.csv)",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch_pair": bytes_fwd + bytes_bwd, "ms_fwd": tf / max(nf, 1), "ms_bwd": tb / max(nb, 1),
                 "launch_pairs_timed": n_pairs, "share_of_step": (tf + tb) / ms,
