@@ -1,6 +1,7 @@
 // Per-attribute head kernels over the concatenated CP logits: decode (greedy / temperature /
 // nucleus with Philox inverse-CDF draws), log-prob + entropy (fwd/bwd) and masked cross-entropy
-// (fwd/bwd).  One warp owns one (row, attribute) segment; segments are <= 1024 wide.
+// (fwd/bwd).  One warp owns one (row, attribute) segment (decode, generic layouts) or one whole row of concatenated
+// logits (log-prob / cross-entropy when the row is <= 1024 wide and 16-byte aligned); segments are <= 1024 wide.
 #include "cpm_common.cuh"
 
 namespace cpm {
@@ -250,6 +251,181 @@ __global__ void __launch_bounds__(WARPS * 32) masked_ce_bwd_kernel(const T *__re
     }
 }
 
+// ---------------------------------------------------------------- row-per-warp variants (rows <= MAX_SEG wide, ld % 8 == 0)
+// The (row, attribute)-per-warp kernels above keep one 36-270 byte segment in flight per warp and pay a memory round
+// trip per segment; at 65 536 rows they are latency bound (4-14 % of HBM).  Here a warp fetches the whole row of concatenated
+// logits with 16-byte loads (one round trip), works on all attribute segments out of shared memory, and writes gradient
+// rows back with 16-byte stores.
+template <typename T>
+__device__ __forceinline__ void load_row(const T *__restrict__ row, int width, float *buf, int lane) {
+    const int G = width >> 3;
+    for (int g = lane; g < G; g += 32) {
+        Vec8<T> v;
+        v.load(row + g * 8);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) buf[g * 8 + j] = v.v[j];
+    }
+    for (int i = G * 8 + lane; i < width; i += 32) buf[i] = to_f(row[i]);
+}
+template <typename T>
+__device__ __forceinline__ void store_row(T *__restrict__ row, int ld, const float *buf, int width, int lane) {   // zero-pads [width, ld)
+    for (int g = lane; g < (ld >> 3); g += 32) {
+        Vec8<T> v;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v.v[j] = (g * 8 + j < width) ? buf[g * 8 + j] : 0.f;
+        v.store(row + g * 8);
+    }
+}
+__device__ __forceinline__ void seg_stats(const float *b, int w, int lane, ArgMax &am, float &lse) {
+    ArgMax a{-INFINITY, 0x7fffffff};
+    for (int i = lane; i < w; i += 32) { const float x = b[i]; if (x > a.v) { a.v = x; a.i = i; } }
+    am = warp_argmax(a);
+    float s = 0.f;
+    for (int i = lane; i < w; i += 32) s += __expf(b[i] - am.v);
+    lse = am.v + __logf(warp_sum(s));
+}
+__device__ __forceinline__ int clamp_tok(int64_t t, int w) { return t < 0 ? 0 : (t >= w ? w - 1 : (int)t); }
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) heads_logp_row_kernel(const T *__restrict__ logits, int64_t rows, int64_t ld, SegParams sp,
+                                                                    const int64_t *__restrict__ tokens, float *__restrict__ logp,
+                                                                    float *__restrict__ entropy) {
+    __shared__ __align__(16) float sbuf[WARPS][MAX_SEG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, A = sp.n_attr, width = sp.seg[A];
+    float *buf = sbuf[warp];
+    for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < rows; r += (int64_t)gridDim.x * WARPS) {
+        const int64_t mytok = lane < A ? tokens[r * A + lane] : 0;
+        __syncwarp();
+        load_row(logits + r * ld, width, buf, lane);
+        __syncwarp();
+        for (int a = 0; a < A; ++a) {
+            const float *b = buf + sp.seg[a];
+            const int w = sp.seg[a + 1] - sp.seg[a];
+            ArgMax am;
+            float lse;
+            seg_stats(b, w, lane, am, lse);
+            const int tok = clamp_tok(__shfl_sync(0xffffffffu, mytok, a), w);
+            if (lane == 0 && logp) logp[r * A + a] = b[tok] - lse;
+            if (entropy) {
+                float hx = 0.f;
+                for (int i = lane; i < w; i += 32) { const float lp = b[i] - lse; hx -= __expf(lp) * lp; }
+                hx = warp_sum(hx);
+                if (lane == 0) entropy[r * A + a] = hx;
+            }
+        }
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) heads_logp_bwd_row_kernel(const T *__restrict__ logits, int64_t rows, int64_t ld, SegParams sp,
+                                                                        const int64_t *__restrict__ tokens, const float *__restrict__ glogp,
+                                                                        const float *__restrict__ gent, T *__restrict__ dlogits) {
+    __shared__ __align__(16) float sbuf[WARPS][MAX_SEG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, A = sp.n_attr, width = sp.seg[A];
+    float *buf = sbuf[warp];
+    for (int64_t r = (int64_t)blockIdx.x * WARPS + warp; r < rows; r += (int64_t)gridDim.x * WARPS) {
+        const int64_t mytok = lane < A ? tokens[r * A + lane] : 0;
+        const float mygl = (glogp && lane < A) ? glogp[r * A + lane] : 0.f;
+        const float myge = (gent && lane < A) ? gent[r * A + lane] : 0.f;
+        __syncwarp();
+        load_row(logits + r * ld, width, buf, lane);
+        __syncwarp();
+        for (int a = 0; a < A; ++a) {
+            float *b = buf + sp.seg[a];
+            const int w = sp.seg[a + 1] - sp.seg[a];
+            ArgMax am;
+            float lse;
+            seg_stats(b, w, lane, am, lse);
+            const int tok = clamp_tok(__shfl_sync(0xffffffffu, mytok, a), w);
+            const float gl = __shfl_sync(0xffffffffu, mygl, a), ge = __shfl_sync(0xffffffffu, myge, a);
+            float hx = 0.f;
+            if (gent) {
+                for (int i = lane; i < w; i += 32) { const float lp = b[i] - lse; hx -= __expf(lp) * lp; }
+                hx = warp_sum(hx);
+            }
+            for (int i = lane; i < w; i += 32) {
+                const float lp = b[i] - lse, p = __expf(lp);
+                b[i] = gl * ((i == tok ? 1.f : 0.f) - p) - ge * p * (lp + hx);
+            }
+        }
+        __syncwarp();
+        store_row(dlogits + r * ld, (int)ld, buf, width, lane);
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) masked_ce_fwd_row_kernel(const T *__restrict__ logits, int64_t T_, int64_t ld, SegParams sp,
+                                                                       const int64_t *__restrict__ targets, const float *__restrict__ mask,
+                                                                       float *__restrict__ loss_num, float *__restrict__ mask_sum,
+                                                                       float *__restrict__ lse_out) {
+    __shared__ __align__(16) float sbuf[WARPS][MAX_SEG];
+    __shared__ float sacc[CPM_MAX_ATTR + 1];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, A = sp.n_attr, width = sp.seg[A];
+    if (threadIdx.x <= CPM_MAX_ATTR) sacc[threadIdx.x] = 0.f;
+    __syncthreads();
+    float *buf = sbuf[warp];
+    float acc = 0.f, macc = 0.f;                       // lane a < A accumulates attribute a; lane 0 the mask sum
+    for (int64_t t = (int64_t)blockIdx.x * WARPS + warp; t < T_; t += (int64_t)gridDim.x * WARPS) {
+        const int64_t mytg = lane < A ? targets[t * A + lane] : 0;
+        const float m = mask[t];
+        __syncwarp();
+        load_row(logits + t * ld, width, buf, lane);
+        __syncwarp();
+        for (int a = 0; a < A; ++a) {
+            const float *b = buf + sp.seg[a];
+            const int w = sp.seg[a + 1] - sp.seg[a];
+            ArgMax am;
+            float lse;
+            seg_stats(b, w, lane, am, lse);
+            const int tg = clamp_tok(__shfl_sync(0xffffffffu, mytg, a), w);
+            if (lane == a) {
+                if (lse_out) lse_out[t * A + a] = lse;
+                acc += m * (lse - b[tg]);
+            }
+        }
+        if (lane == 0) macc += m;
+    }
+    if (lane < A) atomicAdd(&sacc[lane], acc);
+    if (lane == 0) atomicAdd(&sacc[CPM_MAX_ATTR], macc);
+    __syncthreads();
+    if (threadIdx.x < A) atomicAdd(&loss_num[threadIdx.x], sacc[threadIdx.x]);
+    if (threadIdx.x == CPM_MAX_ATTR && mask_sum) atomicAdd(mask_sum, sacc[CPM_MAX_ATTR]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(WARPS * 32) masked_ce_bwd_row_kernel(const T *__restrict__ logits, int64_t T_, int64_t ld, SegParams sp,
+                                                                       const int64_t *__restrict__ targets, const float *__restrict__ mask,
+                                                                       const float *__restrict__ lse_in, const float *__restrict__ gscale,
+                                                                       const float *__restrict__ denom, T *__restrict__ dlogits) {
+    __shared__ __align__(16) float sbuf[WARPS][MAX_SEG];
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, A = sp.n_attr, width = sp.seg[A];
+    float *buf = sbuf[warp];
+    const float inv_denom = 1.f / denom[0];
+    const float mygs = lane < A ? gscale[lane] : 0.f;
+    for (int64_t t = (int64_t)blockIdx.x * WARPS + warp; t < T_; t += (int64_t)gridDim.x * WARPS) {
+        const int64_t mytg = lane < A ? targets[t * A + lane] : 0;
+        const float mylse = lane < A ? lse_in[t * A + lane] : 0.f;
+        const float m = mask[t];
+        __syncwarp();
+        load_row(logits + t * ld, width, buf, lane);
+        __syncwarp();
+        for (int a = 0; a < A; ++a) {
+            float *b = buf + sp.seg[a];
+            const int w = sp.seg[a + 1] - sp.seg[a];
+            const int tg = clamp_tok(__shfl_sync(0xffffffffu, mytg, a), w);
+            const float lse = __shfl_sync(0xffffffffu, mylse, a);
+            const float coef = __shfl_sync(0xffffffffu, mygs, a) * m * inv_denom;
+            for (int i = lane; i < w; i += 32) b[i] = coef == 0.f ? 0.f : coef * (__expf(b[i] - lse) - (i == tg ? 1.f : 0.f));
+        }
+        __syncwarp();
+        store_row(dlogits + t * ld, (int)ld, buf, width, lane);
+    }
+}
+
+inline bool row_path_ok(const SegParams &sp, int64_t ld, const void *p0, const void *p1) {
+    return sp.seg[0] == 0 && sp.seg[sp.n_attr] <= MAX_SEG && ld % 8 == 0 && ld <= MAX_SEG && aligned16(p0) && (!p1 || aligned16(p1));
+}
+
 int fill_seg(SegParams &sp, const int *seg, int n_attr, int64_t ld, const float *temperature, const float *top_p) {
     CPM_REQUIRE(seg, CPM_ERR_NULL, "heads: seg_host is NULL");
     CPM_REQUIRE(n_attr >= 1 && n_attr <= CPM_MAX_ATTR, CPM_ERR_BAD_SHAPE, "heads: n_attr=%d out of [1,%d]", n_attr, CPM_MAX_ATTR);
@@ -306,6 +482,11 @@ int cpm_heads_logp(const void *logits, int64_t rows, int64_t ld_logits, const in
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
     if (rc) return rc;
     if (rows <= 0) return rows == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "heads_logp: rows=%lld", (long long)rows);
+    if (row_path_ok(sp, ld_logits, logits, nullptr)) {
+        DISPATCH_DTYPE(dtype, heads_logp_row_kernel<T><<<warp_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                                  (const T *)logits, rows, ld_logits, sp, tokens, logp, entropy));
+        return check_launch("heads_logp");
+    }
     DISPATCH_DTYPE(dtype, heads_logp_kernel<T><<<warp_grid(rows * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
                               (const T *)logits, rows, ld_logits, sp, tokens, logp, entropy));
     return check_launch("heads_logp");
@@ -318,6 +499,11 @@ int cpm_heads_logp_bwd(const void *logits, int64_t rows, int64_t ld_logits, cons
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
     if (rc) return rc;
     if (rows <= 0) return rows == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "heads_logp_bwd: rows=%lld", (long long)rows);
+    if (row_path_ok(sp, ld_logits, logits, dlogits)) {
+        DISPATCH_DTYPE(dtype, heads_logp_bwd_row_kernel<T><<<warp_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                                  (const T *)logits, rows, ld_logits, sp, tokens, glogp, gentropy, (T *)dlogits));
+        return check_launch("heads_logp_bwd");
+    }
     DISPATCH_DTYPE(dtype, heads_logp_bwd_kernel<T><<<warp_grid(rows * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
                               (const T *)logits, rows, ld_logits, sp, tokens, glogp, gentropy, (T *)dlogits));
     return check_launch("heads_logp_bwd");
@@ -330,6 +516,11 @@ int cpm_masked_ce_fwd(const void *logits, int64_t T_, int64_t ld_logits, const i
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
     if (rc) return rc;
     if (T_ <= 0) return T_ == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "masked_ce_fwd: T=%lld", (long long)T_);
+    if (row_path_ok(sp, ld_logits, logits, nullptr)) {
+        DISPATCH_DTYPE(dtype, masked_ce_fwd_row_kernel<T><<<warp_grid(T_), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                                  (const T *)logits, T_, ld_logits, sp, targets, mask, loss_num, mask_sum, lse));
+        return check_launch("masked_ce_fwd");
+    }
     DISPATCH_DTYPE(dtype, masked_ce_fwd_kernel<T><<<warp_grid(T_ * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
                               (const T *)logits, T_, ld_logits, sp, targets, mask, loss_num, mask_sum, lse));
     return check_launch("masked_ce_fwd");
@@ -343,6 +534,11 @@ int cpm_masked_ce_bwd(const void *logits, int64_t T_, int64_t ld_logits, const i
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
     if (rc) return rc;
     if (T_ <= 0) return T_ == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "masked_ce_bwd: T=%lld", (long long)T_);
+    if (row_path_ok(sp, ld_logits, logits, dlogits)) {
+        DISPATCH_DTYPE(dtype, masked_ce_bwd_row_kernel<T><<<warp_grid(T_), WARPS * 32, 0, (cudaStream_t)stream>>>(
+                                  (const T *)logits, T_, ld_logits, sp, targets, mask, lse, gscale, denom, (T *)dlogits));
+        return check_launch("masked_ce_bwd");
+    }
     DISPATCH_DTYPE(dtype, masked_ce_bwd_kernel<T><<<warp_grid(T_ * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
                               (const T *)logits, T_, ld_logits, sp, targets, mask, lse, gscale, denom, (T *)dlogits));
     return check_launch("masked_ce_bwd");
