@@ -1,0 +1,94 @@
+"""Throughput of the other BASELINE.json configurations on one GPU (the headline metric, configs[2], is bench.py):
+  cfg2  teacher-forced pretraining step, bf16, batch 32 x seq 512, 12 layers / d 512 / 8 heads (train_step + Adam + clip 3)
+  cfg4  DQN / AIRL update: Q and target nets on 1024 windows of 50 tokens + fused TD loss + CE term + Adam; reward head on 1024 windows
+  cfg5  long-sequence stress: 24 layers, d_model 1024 (16 heads), seq 8192, batch 1: train_step forward + backward
+CUDA events, 3 warm-up + `--iters` timed iterations.   python tools/bench_configs.py [--iters 10] [--only cfg2]"""
+import argparse, json, os, sys
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+import torch
+import cpmusic
+
+VOCAB = [56, 135, 18, 87, 18, 25]
+
+
+def timed(fn, iters):
+    for _ in range(3):
+        fn()
+    torch.cuda.synchronize()
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a.record()
+    for _ in range(iters):
+        fn()
+    b.record()
+    torch.cuda.synchronize()
+    return a.elapsed_time(b) / iters
+
+
+def batch(N, L, dev, seed=0):
+    g = torch.Generator().manual_seed(seed)
+    x = torch.stack([torch.randint(0, n, (N, L), generator=g) for n in VOCAB], -1).to(dev)
+    mask = torch.ones(N, L, device=dev)
+    return x, x.roll(-1, 1), mask
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--iters", type=int, default=10)
+    ap.add_argument("--only", default=None)
+    args = ap.parse_args()
+    dev = torch.device("cuda:0")
+    torch.manual_seed(0)
+    if not args.only or args.only == "cfg2":
+        m = cpmusic.TransformerModel(VOCAB, dropout=0.1).to(dev).train()
+        opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True)
+        x, y, mask = batch(32, 512, dev)
+
+        def step():
+            losses = m.train_step(x, y, mask)
+            opt.zero_grad(set_to_none=True)
+            (sum(losses) / 6).backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 3.0, foreach=True)
+            opt.step()
+        ms = timed(step, args.iters)
+        tok = 32 * 512
+        print(json.dumps({"config": "cfg2 pretrain step 32x512 bf16 (agent_pretrain.py:557-565)", "ms_per_step": round(ms, 3),
+                          "tokens_per_s": round(tok / ms * 1e3), "model_tflops": round(tok * 236.1e6 / ms / 1e9, 1),
+                          "frac_of_sustained_bf16_peak": round(tok * 236.1e6 / ms / 1e9 / 1402.2, 3)}), flush=True)
+        del m, opt
+    if not args.only or args.only == "cfg4":
+        q = cpmusic.LinearTransformer(VOCAB, dropout=0.1).to(dev).train()
+        tgt = cpmusic.LinearTransformer(VOCAB, dropout=0.1).to(dev).eval()
+        head = cpmusic.rl.RewardHead(VOCAB, d_model=512).to(dev)
+        opt = torch.optim.Adam(q.parameters(), lr=1e-4, fused=True)
+        s, s2, mask = batch(1024, 50, dev, seed=1)
+        act = torch.stack([torch.randint(0, n, (1024, 25), device=dev) for n in VOCAB], -1)
+        done = torch.zeros(1024, device=dev)
+        hidden = torch.randn(1024, 50, 512, device=dev).bfloat16()          # stands in for the Longformer body's last hidden state
+
+        def step():
+            reward = head(hidden)                                            # AIRL reward read-out (fused)
+            td = cpmusic.rl.dqn_td_loss(q, tgt, s, s2, act, reward, done, compat=False)
+            ce = sum(q.train_step(s, s2, mask)) / 6
+            opt.zero_grad(set_to_none=True)
+            (0.3 * td + 0.7 * ce).backward()                                 # IRL_dqn_train.py:335
+            opt.step()
+        ms = timed(step, args.iters)
+        print(json.dumps({"config": "cfg4 DQN/AIRL update, replay batch 1024 x 50 tokens (IRL_dqn_train.py:285-345)", "ms_per_update": round(ms, 3),
+                          "sequences_per_s": round(1024 / ms * 1e3), "tokens_per_s": round(1024 * 50 / ms * 1e3)}), flush=True)
+        del q, tgt, opt
+    if not args.only or args.only == "cfg5":
+        m = cpmusic.TransformerModel(VOCAB, d_model=1024, n_layer=24, n_head=16, d_inner=4096, dropout=0.1).to(dev).train()
+        x, y, mask = batch(1, 8192, dev, seed=2)
+
+        def step():
+            losses = m.train_step(x, y, mask)
+            m.zero_grad(set_to_none=True)
+            (sum(losses) / 6).backward()
+        ms = timed(step, args.iters)
+        print(json.dumps({"config": "cfg5 long sequence: 24 layers, d 1024, 16 heads, seq 8192, batch 1, fwd+bwd", "ms_per_step": round(ms, 3),
+                          "tokens_per_s": round(8192 / ms * 1e3), "params_M": round(sum(p.numel() for p in m.parameters()) / 1e6, 1)}), flush=True)
+
+
+if __name__ == "__main__":
+    main()
