@@ -169,6 +169,12 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
                         float *partials, int64_t rows, int d, float p_drop, uint64_t seed,
                         uint64_t rng_offset, int dtype, void *stream);
 
+/* Device-side dropout RNG base (optional; NULL = off, the default).  When set, every dropout-carrying kernel
+ * (cpm_add_pe, cpm_dropout, cpm_ln_residual_fwd/bwd, cpm_gelu_fwd/bwd) adds *device_counter to its rng_offset
+ * argument, so a CUDA graph that captured those launches (offsets frozen) still draws fresh masks on every replay
+ * as long as the graph advances the counter.  Process-wide; set it before capture and keep the memory alive. */
+int cpm_set_rng_base(const uint64_t *device_counter);
+
 /* bias + exact-erf GELU + dropout (ft activation='gelu' => F.gelu; K6):
  *     y = drop(gelu(x + bias))   (bias fp32 (d) or NULL)
  * bwd: gx = gy * mask/(1-p) * gelu'(x + bias). */

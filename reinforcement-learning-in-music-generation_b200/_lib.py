@@ -52,6 +52,7 @@ SIGNATURES = {
     "cpm_linattn_state_update": (c_int, [_P, _P, c_int, c_int, _P]),
     "cpm_linattn_step_lazy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, _P, c_int, _P]),
     "cpm_reward_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
+    "cpm_set_rng_base": (c_int, [_P]),
     "cpm_embed_fwd": (c_int, [_P, _FPP, _IP, _IP, c_int, c_int64, _P, c_int, _P, _P]),
     "cpm_embed_bwd": (c_int, [_P, _P, _FPP, _IP, _IP, c_int, c_int64, c_int, _P]),
     "cpm_add_pe": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P]),
@@ -92,7 +93,7 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
+    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
     "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
                                                                                 # kernel (ops adds 1 when the scan path runs); bwd = pre-pass, scan, main
 })

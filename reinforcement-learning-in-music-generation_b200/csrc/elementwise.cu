@@ -6,6 +6,17 @@
 namespace cpm {
 namespace {
 
+// ---------------------------------------------------------------- device-side RNG base
+// Dropout masks are a pure function of (seed, offset, element).  The host passes `rng_offset` by value, which a CUDA graph
+// would freeze; cpm_set_rng_base installs a device counter that every dropout kernel adds to its offset, so a captured
+// training step draws fresh masks on every replay (the graph itself advances the counter; see graphs.py).
+const unsigned long long *g_rng_base = nullptr;
+__device__ __forceinline__ uint64_t rng_off(uint64_t host_offset, const unsigned long long *base) {
+    return host_offset + (base ? *base : 0ull);
+}
+
+
+
 struct EmbedParams {
     const float *tables[CPM_MAX_ATTR];
     float *gtables[CPM_MAX_ATTR];
@@ -80,7 +91,8 @@ __global__ void __launch_bounds__(256) embed_bwd_kernel(const int64_t *__restric
 template <typename T>
 __global__ void __launch_bounds__(256) add_pe_kernel(const T *__restrict__ x, const float *__restrict__ pe, T *__restrict__ y, int64_t rows,
                                                      int L, int d, int pos_offset, const int32_t *__restrict__ pos_dev, int max_len,
-                                                     uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset) {
+                                                     uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset_h, const unsigned long long *rng_base) {
+    const uint64_t rng_offset = rng_off(rng_offset_h, rng_base);
     const int G = d >> 3;
     const int64_t total = rows * G;
     const int base = pos_dev ? pos_dev[0] : pos_offset;
@@ -107,7 +119,8 @@ __global__ void __launch_bounds__(256) add_pe_kernel(const T *__restrict__ x, co
 
 template <typename T>
 __global__ void __launch_bounds__(256) dropout_kernel(const T *__restrict__ x, T *__restrict__ y, int64_t n8, uint32_t thr, float scale,
-                                                      uint64_t seed, uint64_t rng_offset) {
+                                                      uint64_t seed, uint64_t rng_offset_h, const unsigned long long *rng_base) {
+    const uint64_t rng_offset = rng_off(rng_offset_h, rng_base);
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n8; i += (int64_t)gridDim.x * blockDim.x) {
         Vec8<T> v;
         v.load(x + i * 8);
@@ -128,7 +141,8 @@ __global__ void __launch_bounds__(128) ln_residual_fwd_kernel(const T *__restric
                                                               const float *__restrict__ gamma,
                                                               const float *__restrict__ beta, T *__restrict__ y, T *__restrict__ s_out,
                                                               float *__restrict__ mean_out, float *__restrict__ rstd_out, int64_t rows, int d,
-                                                              float eps, uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset) {
+                                                              float eps, uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset_h, const unsigned long long *rng_base) {
+    const uint64_t rng_offset = rng_off(rng_offset_h, rng_base);
     const int lane = threadIdx.x & 31;
     const int G = d >> 3;
     const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
@@ -200,7 +214,8 @@ template <typename T, int MAXV, bool WANT_DRES>
 __global__ void __launch_bounds__(LN_BWD_THREADS) ln_residual_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ s, const float *__restrict__ mean,
                                                                          const float *__restrict__ rstd, const float *__restrict__ gamma, T *__restrict__ gs,
                                                                          T *__restrict__ gres, float *__restrict__ partials, int64_t rows, int d, uint32_t thr,
-                                                                         float scale, uint64_t seed, uint64_t rng_offset) {
+                                                                         float scale, uint64_t seed, uint64_t rng_offset_h, const unsigned long long *rng_base) {
+    const uint64_t rng_offset = rng_off(rng_offset_h, rng_base);
     extern __shared__ float red[];   // [3][d] block partial sums: dgamma | dbeta | column sums of the residual-branch gradient
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = d >> 3;
@@ -362,8 +377,9 @@ inline float dropout_scale8(float p) { uint32_t t = dropout_threshold8(p); retur
 // this thread's column sums of the stored gx — valid because 4096 % d == 0 makes a thread's 16 columns the same in every iteration.
 template <typename T, bool BWD, bool DBIAS = false>
 __global__ void __launch_bounds__(256) gelu_kernel(const T *__restrict__ x, const float *__restrict__ bias, const T *__restrict__ gy, T *__restrict__ out,
-                                                   int64_t n_groups, int d, uint32_t thr8, float scale, uint64_t seed, uint64_t rng_offset,
-                                                   float *__restrict__ dbias_partials) {
+                                                   int64_t n_groups, int d, uint32_t thr8, float scale, uint64_t seed, uint64_t rng_offset_h,
+                                                   float *__restrict__ dbias_partials, const unsigned long long *rng_base) {
+    const uint64_t rng_offset = rng_off(rng_offset_h, rng_base);
     float cs[16], bv[16];
 #pragma unroll
     for (int j = 0; j < 16; ++j) { cs[j] = 0.f; bv[j] = 0.f; }
@@ -510,7 +526,7 @@ int cpm_add_pe(const void *x, const float *pe, void *y, int64_t rows, int L, int
     if (rows == 0) return CPM_OK;
     const uint32_t thr = dropout_threshold(p_drop);
     DISPATCH_DTYPE(dtype, add_pe_kernel<T><<<grid_for(rows * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-                              (const T *)x, pe, (T *)y, rows, L, d, pos_offset, pos_dev, max_len, thr, dropout_scale(p_drop), seed, rng_offset));
+                              (const T *)x, pe, (T *)y, rows, L, d, pos_offset, pos_dev, max_len, thr, dropout_scale(p_drop), seed, rng_offset, g_rng_base));
     return check_launch("add_pe");
 }
 
@@ -520,7 +536,7 @@ int cpm_dropout(const void *x, void *y, int64_t n, float p_drop, uint64_t seed, 
     CPM_REQUIRE(aligned16(x) && aligned16(y), CPM_ERR_BAD_ALIGN, "dropout: alignment");
     if (n == 0) return CPM_OK;
     DISPATCH_DTYPE(dtype, dropout_kernel<T><<<grid_for(n / 8, 256), 256, 0, (cudaStream_t)stream>>>(
-                              (const T *)x, (T *)y, n / 8, dropout_threshold(p_drop), dropout_scale(p_drop), seed, rng_offset));
+                              (const T *)x, (T *)y, n / 8, dropout_threshold(p_drop), dropout_scale(p_drop), seed, rng_offset, g_rng_base));
     return check_launch("dropout");
 }
 
@@ -536,11 +552,16 @@ int cpm_ln_residual_fwd(const void *x, const void *res, const float *res_bias, c
     const int grid = grid_for(rows * 32, 128);
     DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_fwd_kernel<T, MAXV><<<grid, 128, 0, (cudaStream_t)stream>>>(
                                                (const T *)x, (const T *)res, res ? res_bias : nullptr, gamma, beta, (T *)y, (T *)s_out, mean, rstd, rows, d, eps, thr,
-                                               dropout_scale(p_drop), seed, rng_offset)));
+                                               dropout_scale(p_drop), seed, rng_offset, g_rng_base)));
     return check_launch("ln_residual_fwd");
 }
 
 int cpm_ln_partials_rows(void) { return LN_BWD_BLOCKS; }
+
+int cpm_set_rng_base(const uint64_t *device_counter) {
+    g_rng_base = reinterpret_cast<const unsigned long long *>(device_counter);
+    return CPM_OK;
+}
 
 int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const float *rstd, const float *gamma, void *gs, void *gres,
                         float *dgamma, float *dbeta, float *dres_bias, float *partials, int64_t rows, int d, float p_drop, uint64_t seed,
@@ -555,11 +576,11 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
     if (dres_bias) {
         DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV, true><<<LN_BWD_BLOCKS, LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
                                                    (const T *)gy, (const T *)s, mean, rstd, gamma, (T *)gs, (T *)gres, partials, rows, d, thr,
-                                                   dropout_scale(p_drop), seed, rng_offset)));
+                                                   dropout_scale(p_drop), seed, rng_offset, g_rng_base)));
     } else {
         DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV, false><<<LN_BWD_BLOCKS, LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
                                                    (const T *)gy, (const T *)s, mean, rstd, gamma, (T *)gs, (T *)gres, partials, rows, d, thr,
-                                                   dropout_scale(p_drop), seed, rng_offset)));
+                                                   dropout_scale(p_drop), seed, rng_offset, g_rng_base)));
     }
     const int width = (dres_bias ? 3 : 2) * d;
     reduce_partials_kernel<<<(width + 63) / 64, 256, 0, (cudaStream_t)stream>>>(partials, LN_BWD_BLOCKS, 3 * d, d, dgamma, dbeta, dres_bias);
@@ -574,7 +595,7 @@ int cpm_gelu_fwd(const void *x, const float *bias, void *y, int64_t rows, int d,
     if (rows == 0) return CPM_OK;
     DISPATCH_DTYPE(dtype, gelu_kernel<T, false><<<grid_for(rows * (d / 16), 256), 256, 0, (cudaStream_t)stream>>>(
                               (const T *)x, bias, nullptr, (T *)y, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop), seed,
-                              rng_offset, nullptr));
+                              rng_offset, nullptr, g_rng_base));
     return check_launch("gelu_fwd");
 }
 
@@ -590,13 +611,13 @@ int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, flo
         CPM_REQUIRE(partials && 4096 % d == 0, CPM_ERR_BAD_SHAPE, "gelu_bwd: the fused bias gradient needs d | 4096 (d=%d) and a partials buffer", d);
         DISPATCH_DTYPE(dtype, gelu_kernel<T, true, true><<<GELU_BWD_BLOCKS, 256, 0, (cudaStream_t)stream>>>(
                                   (const T *)x, bias, (const T *)gy, (T *)gx, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop),
-                                  seed, rng_offset, partials));
+                                  seed, rng_offset, partials, g_rng_base));
         reduce_partials_kernel<<<(d + 63) / 64, 256, 0, (cudaStream_t)stream>>>(partials, cpm_gelu_bwd_partials_rows(d), d, d, dbias, nullptr, nullptr);
         return check_launch("gelu_bwd");
     }
     DISPATCH_DTYPE(dtype, gelu_kernel<T, true><<<grid_for(rows * (d / 16), 256), 256, 0, (cudaStream_t)stream>>>(
                               (const T *)x, bias, (const T *)gy, (T *)gx, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop), seed,
-                              rng_offset, nullptr));
+                              rng_offset, nullptr, g_rng_base));
     return check_launch("gelu_bwd");
 }
 

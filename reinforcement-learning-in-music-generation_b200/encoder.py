@@ -57,18 +57,32 @@ class LengthMask:
         self.max_len = max_len
 
 
+# torch's fused optimizers (``Adam(fused=True)``, with or without ``capturable``) update parameters WITHOUT bumping
+# ``Tensor._version`` (measured: version unchanged across ``step()``), so the version counters alone cannot tell a stale
+# packing.  Every optimizer step - of any optimizer in the process - therefore advances this epoch, which is part of the stamp.
+_OPT_EPOCH = [0]
+
+
+def _optimizer_stepped(*_args, **_kwargs):
+    _OPT_EPOCH[0] += 1
+
+
+from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook  # noqa: E402
+_register_post_hook(_optimizer_stepped)
+
+
 class PackCache:
     """Compute-dtype packings of fp32 master parameters (row-concatenated, optionally zero-padded).
-    A packing is refreshed IN PLACE when a master changes, so its device address is stable — CUDA
-    graphs captured over these buffers (the rollout step) stay valid across optimizer steps; call
-    ``refresh_all()`` before replaying such a graph."""
+    A packing is refreshed IN PLACE when a master changes (in-place write seen through ``_version``, or any optimizer
+    step since), so its device address is stable — CUDA graphs captured over these buffers (the rollout step) stay
+    valid across optimizer steps; call ``refresh_all()`` before replaying such a graph."""
 
     def __init__(self):
         self._store = {}
 
     @staticmethod
     def _stamp(params, dtype):
-        return tuple((p.data_ptr(), p._version) for p in params) + (dtype,)
+        return tuple((p.data_ptr(), p._version) for p in params) + (_OPT_EPOCH[0], dtype)
 
     @staticmethod
     def _fill(wc, bc, ws, bs):
@@ -110,6 +124,12 @@ class PackCache:
                     n = len(rows)
                     self._fill(wc, bc, masters[:n], masters[n:])
                     self._store[key] = (now, packed)
+
+    def invalidate(self):
+        """Marks every packing stale WITHOUT dropping its buffers: the next get() refills it in place.  Used right before
+        a CUDA-graph capture of a training step so that the refill copies are part of the graph."""
+        for key, (stamp, packed) in list(self._store.items()):
+            self._store[key] = (("stale", stamp[-1]), packed)
 
     def clear(self):
         self._store.clear()

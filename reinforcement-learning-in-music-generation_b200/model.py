@@ -134,6 +134,11 @@ class CPLinearTransformer(nn.Module):
         self._cache.refresh_all()
         self.transformer_encoder._cache.refresh_all()
 
+    def invalidate_packs(self):
+        """Force every cached packing to be rebuilt (in place) at its next use — see PackCache.invalidate."""
+        self._cache.invalidate()
+        self.transformer_encoder._cache.invalidate()
+
     def _tables(self):
         return [getattr(self, f"word_emb_{a}").lut.weight for a in self.attrs]
 

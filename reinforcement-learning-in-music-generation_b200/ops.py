@@ -48,6 +48,7 @@ class _Rng:
     """Counter-based dropout RNG state: (seed, running offset in units of 8 elements)."""
     seed = 0x5EED
     offset = 0
+    base_dev = None          # optional device-side counter added by the kernels (enable_device_rng)
 
     @classmethod
     def take(cls, n_elems: int) -> Tuple[int, int]:
@@ -59,6 +60,26 @@ class _Rng:
 def manual_seed(seed: int) -> None:
     _Rng.seed = int(seed) & 0xFFFFFFFFFFFFFFFF
     _Rng.offset = 0
+    if _Rng.base_dev is not None:
+        _Rng.base_dev.zero_()
+
+
+def enable_device_rng(device) -> torch.Tensor:
+    """Installs (once) the device-side counter every dropout kernel adds to its host-side offset (cpm_set_rng_base), so
+    that CUDA graphs captured over dropout kernels draw fresh masks per replay; returns the counter (int64, 1 element)."""
+    if _Rng.base_dev is None:
+        _Rng.base_dev = torch.zeros(1, dtype=torch.int64, device=device)
+        check(_lib.load().cpm_set_rng_base(_Rng.base_dev.data_ptr()))
+    elif _Rng.base_dev.device != torch.device(device):
+        raise RuntimeError("the device RNG base lives on one device per process")
+    return _Rng.base_dev
+
+
+def rng_advance(n_counters: int) -> None:
+    """base += n (a device-side add: capturable; call it at the end of a captured step with the offsets that step used)."""
+    if _Rng.base_dev is None:
+        raise RuntimeError("call enable_device_rng() first")
+    _Rng.base_dev.add_(int(n_counters))
 
 
 # --------------------------------------------------------------------------- in-situ kernel timing

@@ -441,3 +441,43 @@ def test_rollout_megakernel_matches_unfused_and_oracle(cuda, cpm, golden):
     full = cpm.RolloutEngine(m, 5, 30, greedy=False, seed=9, seq_base=0, mode="mega").generate(x[:1, 0].expand(5, 6).to(cuda))["tokens"]
     part = cpm.RolloutEngine(m, 2, 30, greedy=False, seed=9, seq_base=3, mode="mega").generate(x[:1, 0].expand(2, 6).to(cuda))["tokens"]
     assert torch.equal(full[3:], part)                                   # Philox keyed by global sequence id
+
+
+def test_graphed_train_step_equals_eager_and_keeps_dropout_fresh(cuda, cpm, golden):
+    """The whole pretraining step as one CUDA graph: (i) with dropout off, three replays reproduce three eager steps
+    (losses within fp32 round-off of each other, same parameters afterwards to 1e-5); (ii) with dropout on, replays of the
+    same batch give DIFFERENT losses (the device-side RNG base advances inside the graph) and training still descends."""
+    g = golden("model_small")
+    cfgs = dict(SMALL)
+    x = torch.from_numpy(g["x"]).to(cuda)[:2, :128]
+    if x.shape[1] < 128:
+        x = x.repeat(1, 128 // x.shape[1] + 1, 1)[:, :128]
+    y, mask = x.roll(-1, 1), torch.ones(x.shape[:2], device=cuda)
+    ma = _load_small(cpm, g, cuda, dtype=torch.float32).train()
+    mb = _load_small(cpm, g, cuda, dtype=torch.float32).train()
+    oa = torch.optim.Adam(ma.parameters(), lr=1e-3, fused=True, capturable=True)
+    ob = torch.optim.Adam(mb.parameters(), lr=1e-3, fused=True, capturable=True)
+
+    def eager(xx, yy, mm):
+        le = torch.stack(mb.train_step(xx, yy, mm))
+        ob.zero_grad(set_to_none=False)
+        (le.sum() / 6).backward()
+        torch.nn.utils.clip_grad_norm_(mb.parameters(), 3.0, foreach=True)
+        ob.step()
+        return le.detach()
+
+    step = cpm.GraphedTrainStep(ma, oa, batch_size=2, seq_len=128, max_grad_norm=3.0, warmup=2)
+    for _ in range(2):                                         # the constructor's two warm-up steps ran on its zero-filled buffers
+        eager(torch.zeros_like(x), torch.zeros_like(y), mask)
+    for _ in range(3):
+        lg = step(x, y, mask).clone()
+        _cmp(lg, eager(x, y, mask), 2e-4, 1e-4, "graphed vs eager losses")
+    for (k, a), (_, b) in zip(ma.state_dict().items(), mb.state_dict().items()):
+        _cmp(a, b, 2e-4, 1e-3, f"parameters after 3 steps: {k}")
+    # dropout on: masks must differ between replays of the same batch
+    md = cpm.LinearTransformer(VOCAB, compute_dtype=torch.bfloat16, **dict(cfgs, dropout=0.3)).to(cuda).train()
+    od = torch.optim.Adam(md.parameters(), lr=0.0, fused=True, capturable=True)      # lr 0: only the masks change between replays
+    sd = cpm.GraphedTrainStep(md, od, batch_size=2, seq_len=128)
+    l1, l2, l3 = (sd(x, y, mask).clone() for _ in range(3))
+    assert not torch.equal(l1, l2) and not torch.equal(l2, l3)
+    assert sd.rng_counters_per_step > 0

@@ -252,3 +252,25 @@ def test_device_resident_memory_mirrors_reference_buffers(cpm):
     raw = cpm.data.ExpertMemory(capacity=2, n_states=5, n_actions=2, device="cpu", log_prob_long_compat=False)
     raw.store_transition(torch.zeros(5, 6), torch.zeros(2, 6), torch.full((2, 6), -0.25), 0.0, 1.0, torch.zeros(5, 6), 0.0)
     assert raw.get()["log_actions"][0, 0, 0].item() == -0.25 and hasattr(raw, "states_expert")
+
+
+def test_pack_cache_notices_fused_optimizer_steps(cpm):
+    """torch's fused Adam rewrites parameters without bumping Tensor._version; the packed compute copies must still be
+    rebuilt after such a step (PackCache stamps carry a process-wide optimizer-step epoch)."""
+    from cpmusic.encoder import PackCache
+    lin = torch.nn.Linear(8, 4)
+    cache = PackCache()
+    w0 = cache.get("k", [lin], torch.float32)[0].clone()
+    opt = torch.optim.Adam(lin.parameters(), lr=0.1, fused=True)
+    lin.weight.grad, lin.bias.grad = torch.ones_like(lin.weight), torch.ones_like(lin.bias)
+    opt.step()
+    wc, bc = cache.get("k", [lin], torch.float32)[:2]
+    assert not torch.equal(wc, w0)
+    assert torch.equal(wc, lin.weight.detach()) and torch.equal(bc, lin.bias.detach())
+    # in-place refresh keeps the buffer (graphs captured over it stay valid), and invalidate() forces a refill
+    ptr = wc.data_ptr()
+    with torch.no_grad():
+        lin.weight.data.add_(1.0)                      # a version-less write the stamps cannot see
+    cache.invalidate()
+    wc2 = cache.get("k", [lin], torch.float32)[0]
+    assert wc2.data_ptr() == ptr and torch.equal(wc2, lin.weight.detach())
