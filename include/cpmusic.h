@@ -98,6 +98,14 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
                      int N, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
                      int dtype, float eps, void *stream);
 
+/* cpm_linattn_step plus an L2 prefetch: every CTA additionally asks the memory system (cp.async.bulk.prefetch.L2) for the
+ * matching 16 KB tile of S_next - the state the NEXT step kernel of the token step will stream (the following layer's;
+ * the first layer's for the last one).  when = 1: after this tile's write-back, 2: before its loads.  Results are
+ * bit-identical to cpm_linattn_step; E = M = 64 only. */
+int cpm_l2_prefetch(const void *p, int64_t bytes, void *stream);   /* stand-alone: bulk L2 prefetch of [p, p+bytes), 16 KB pieces */
+int cpm_linattn_step_prefetch(const void *q, const void *k, const void *v, float *S, float *Z, void *out, const float *S_next,
+                              int when, int N, int H, int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream);
+
 /* B1 split in two launches (rollout engine): cpm_linattn_step_out computes the step's output from S + Kf (x) v formed in
  * registers (bit-identical to cpm_linattn_step), updates Z and parks [Kf | v] in kv_pending ((N,H,128) fp32);
  * cpm_linattn_state_update then stores S += Kf (x) v.  The second launch may run on another stream / graph branch; it

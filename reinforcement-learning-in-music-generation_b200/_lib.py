@@ -44,6 +44,8 @@ SIGNATURES = {
                                 c_int64, c_int64, c_int64, c_int, c_float, c_int, _P, c_int64, _P, c_int64, _P]),
     "cpm_linattn_step": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
                                  c_int, c_float, _P]),
+    "cpm_l2_prefetch": (c_int, [_P, c_int64, _P]),
+    "cpm_linattn_step_prefetch": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, c_float, _P]),
     "cpm_linattn_step_fold": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
     "cpm_gelu_fold": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
     "cpm_tc_linear": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, c_int64,

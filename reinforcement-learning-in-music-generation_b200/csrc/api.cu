@@ -36,15 +36,30 @@ __device__ __forceinline__ void st_stream(float *p, const F8 &v) {
                  : "memory");
 }
 
-template <typename T>
+// PF: 0 = plain; 1 / 2 = additionally pull the same (sequence, head) tile of ANOTHER state tensor (the next layer's)
+// into L2 with one bulk prefetch per CTA, issued after this tile's write-back (1) or before its loads (2).  The next
+// layer's step runs ~25 us of latency-bound GEMM / LayerNorm kernels later and then finds its 16 KB tiles in L2.
+__device__ __forceinline__ void prefetch_l2_bulk(const void *p, uint32_t bytes) {
+    asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(p), "r"(bytes) : "memory");
+}
+
+// stand-alone prefetch: thread i asks for bytes [16384 i, 16384 (i+1)) of the range (no SM resources beyond the launch)
+__global__ void l2_prefetch_kernel(const char *p, int64_t bytes) {
+    const int64_t off = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 16384;
+    if (off < bytes) prefetch_l2_bulk(p + off, (uint32_t)min((int64_t)16384, bytes - off));
+}
+
+template <typename T, int PF = 0>
 __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__ q, const T *__restrict__ k,
                                                            const T *__restrict__ v, float *__restrict__ S,
                                                            float *__restrict__ Z, T *__restrict__ out, int H,
-                                                           int64_t ld_qkv, int64_t ld_o, float eps) {
+                                                           int64_t ld_qkv, int64_t ld_o, float eps,
+                                                           const float *__restrict__ S_next = nullptr) {
     __shared__ float part[8][68];                      // per warp: 64 output partials + the normaliser partial
     const int nh = blockIdx.x, n = nh / H, h = nh % H;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int e = tid >> 2, m0 = (tid & 3) * 16;
+    if (PF == 2 && tid == 0) prefetch_l2_bulk(S_next + (int64_t)nh * 4096, 16384u);
     // the 16 KB state tile first: its latency overlaps the q/k/v loads below (nothing here depends on them)
     float *srow = S + (int64_t)nh * 4096 + e * 64 + m0;
     float4 s[4];
@@ -78,6 +93,7 @@ __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__
         acc[4 * i + 2] = qe * s[i].z; acc[4 * i + 3] = qe * s[i].w;
     }
     { F8 lo, hi; lo.a = s[0]; lo.b = s[1]; hi.a = s[2]; hi.b = s[3]; st_stream(srow, lo); st_stream(srow + 8, hi); }
+    if (PF == 1 && tid == 0) prefetch_l2_bulk(S_next + (int64_t)nh * 4096, 16384u);
     // reduce over the 8 rows held by this warp (lanes with equal lane%4)
 #pragma unroll
     for (int i = 0; i < 16; ++i) {
@@ -418,6 +434,32 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
     else
         return fail(CPM_ERR_BAD_DTYPE, "linattn_step: dtype %d", dtype);
     return check_launch("linattn_step");
+}
+
+int cpm_l2_prefetch(const void *p, int64_t bytes, void *stream) {
+    CPM_REQUIRE(p, CPM_ERR_NULL, "l2_prefetch: NULL pointer");
+    CPM_REQUIRE(bytes > 0 && bytes % 16 == 0 && aligned16(p), CPM_ERR_BAD_ALIGN, "l2_prefetch: pointer and size must be multiples of 16 bytes");
+    const int64_t pieces = (bytes + 16383) / 16384;
+    l2_prefetch_kernel<<<(unsigned)((pieces + 31) / 32), 32, 0, (cudaStream_t)stream>>>((const char *)p, bytes);
+    return check_launch("l2_prefetch");
+}
+
+int cpm_linattn_step_prefetch(const void *q, const void *k, const void *v, float *S, float *Z, void *out, const float *S_next, int when,
+                              int N, int H, int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream) {
+    CPM_REQUIRE(q && k && v && S && Z && out && S_next, CPM_ERR_NULL, "linattn_step_prefetch: NULL pointer");
+    CPM_REQUIRE(N > 0 && H > 0, CPM_ERR_BAD_SHAPE, "linattn_step_prefetch: N=%d H=%d", N, H);
+    CPM_REQUIRE(when == 1 || when == 2, CPM_ERR_BAD_SHAPE, "linattn_step_prefetch: when=%d (1: after the write-back, 2: first)", when);
+    CPM_REQUIRE(ld_qkv >= (int64_t)H * 64 && ld_o >= (int64_t)H * 64, CPM_ERR_BAD_SHAPE, "linattn_step_prefetch: strides");
+    CPM_REQUIRE(aligned16(S) && aligned16(S_next), CPM_ERR_BAD_ALIGN, "linattn_step_prefetch: S / S_next must be 16-byte aligned");
+    CPM_REQUIRE(dtype == CPM_BF16 || dtype == CPM_F32, CPM_ERR_BAD_DTYPE, "linattn_step_prefetch: dtype %d", dtype);
+    cudaStream_t st = (cudaStream_t)stream;
+#define CPM_STEP_PF(T, PF)                                                                                                         \
+    linattn_step_kernel<T, PF><<<N * H, 256, 0, st>>>((const T *)q, (const T *)k, (const T *)v, S, Z, (T *)out, H, ld_qkv, ld_o, \
+                                                      eps, S_next)
+    if (dtype == CPM_F32) { if (when == 1) CPM_STEP_PF(float, 1); else CPM_STEP_PF(float, 2); }
+    else { if (when == 1) CPM_STEP_PF(__nv_bfloat16, 1); else CPM_STEP_PF(__nv_bfloat16, 2); }
+#undef CPM_STEP_PF
+    return check_launch("linattn_step_prefetch");
 }
 
 int cpm_linattn_step_out(const void *q, const void *k, const void *v, const float *S, float *Z, float *kv_pending, void *out, int N, int H,

@@ -242,9 +242,10 @@ def linattn_last_impl() -> str:
     return _lib.load().cpm_linattn_last_impl().decode()
 
 
-def linattn_step(q, k, v, S, Z, eps=EPS_ATTN):
+def linattn_step(q, k, v, S, Z, eps=EPS_ATTN, prefetch=None, prefetch_when=1):
     """Recurrent step. q,k,v: (N,H,64) views sharing a row stride; S (N,H,64,64), Z (N,H,64) fp32
-    are updated in place; returns (N,H,64)."""
+    are updated in place; returns (N,H,64).  prefetch: another (N,H,64,64) fp32 state (the next layer's) to pull into
+    L2 from inside the kernel (cpm_linattn_step_prefetch; same results)."""
     _cuda(q, k, v, S, Z)
     N, H, E = q.shape
     ld = q.stride(0)
@@ -255,9 +256,21 @@ def linattn_step(q, k, v, S, Z, eps=EPS_ATTN):
     if S.dtype != torch.float32 or Z.dtype != torch.float32 or not S.is_contiguous() or not Z.is_contiguous():
         raise ValueError("recurrent state must be contiguous float32")
     out = torch.empty(N, H, E, dtype=q.dtype, device=q.device)
+    if prefetch is not None:
+        if prefetch.shape != S.shape or prefetch.dtype != torch.float32 or not prefetch.is_contiguous() or E != 64:
+            raise ValueError("prefetch must be a contiguous float32 state of the same shape (E = 64)")
+        check(_lib.load().cpm_linattn_step_prefetch(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), _p(prefetch), int(prefetch_when),
+                                                    N, H, ld, H * E, _dt(q), eps, _st()))
+        return out
     check(_lib.load().cpm_linattn_step(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), N, H, E, E, ld, H * E,
                                        _dt(q), eps, _st()))
     return out
+
+
+def l2_prefetch(t):
+    """Ask the memory system to pull a contiguous CUDA tensor into L2 (cpm_l2_prefetch; returns immediately)."""
+    _cuda(t)
+    check(_lib.load().cpm_l2_prefetch(_p(t), t.numel() * t.element_size(), _st()))
 
 
 def linattn_step_out(q, k, v, S, Z, kv_pending, eps=EPS_ATTN):

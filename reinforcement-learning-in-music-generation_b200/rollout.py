@@ -41,7 +41,7 @@ class RolloutEngine:
     def __init__(self, model, batch: int, max_steps: int, greedy: bool = False, true_positions: bool = True,
                  temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True,
                  fused: Optional[bool] = None, mode: Optional[str] = None, pdl: bool = False, lazy_state: bool = False,
-                 split_state: bool = False):
+                 split_state: bool = False, prefetch_state: int = 0):
         self.model, self.N, self.max_steps = model, batch, max_steps
         self.greedy, self.true_positions = greedy, true_positions
         self.temperature, self.top_p = model.sampling_config(temperature, top_p)
@@ -70,6 +70,13 @@ class RolloutEngine:
             self.kvp = torch.zeros(nl, batch, H, 128, dtype=torch.float32, device=dev)
             self.side = torch.cuda.Stream(device=dev)
             self.state = [[self.S[i], self.Z[i], self._split_hook(i)] for i in range(nl)]
+        # L2 prefetch (unfused mode): layer i's step kernel also pulls layer i+1's state tiles into L2, so that their HBM
+        # read overlaps the latency-bound GEMM / LayerNorm kernels in between (1: after the write-back, 2: first thing)
+        self.prefetch_state = int(prefetch_state)
+        if self.prefetch_state:
+            if self.lazy_state or self.split_state:
+                raise ValueError("choose one of lazy_state / split_state / prefetch_state")
+            self.state = [[self.S[i], self.Z[i], self._prefetch_hook(i, nl)] for i in range(nl)]
         self.cur = torch.zeros(batch, A, dtype=torch.int64, device=dev)
         self.logp = torch.zeros(batch, A, dtype=torch.float32, device=dev)
         self.hist_tok = torch.zeros(max_steps, batch, A, dtype=torch.int64, device=dev)
@@ -88,8 +95,8 @@ class RolloutEngine:
             raise ValueError("the tcgen05 rollout step needs bf16 compute, widths that are multiples of 64 (inputs) / 32 (outputs)")
         if mode not in ("mega", "fused", "unfused", "tc", "fold"):
             raise ValueError(f"unknown rollout mode {mode!r}")
-        if (self.lazy_state or self.split_state) and mode != "unfused":
-            raise ValueError("lazy_state / split_state are implemented for the unfused step")
+        if (self.lazy_state or self.split_state or self.prefetch_state) and mode != "unfused":
+            raise ValueError("lazy_state / split_state / prefetch_state are implemented for the unfused step")
         self.mode = mode
         self.fused = mode == "fused"
         self.pdl = pdl
@@ -358,8 +365,35 @@ class RolloutEngine:
         ops.heads_sample(lc, m.seg, self.temperature, self.top_p, greedy=self.greedy, seed=self.seed,
                          seq_base=self.seq_base, step_dev=self.step_dev, tokens_out=self.cur, logp_out=self.logp)
         ops.rollout_advance(self.cur, self.hist_tok, self.logp, self.hist_logp, self.step_dev, self.max_steps)
-        if self.split_state:
+        if self.split_state or self.prefetch_state == 4:
             torch.cuda.current_stream().wait_stream(self.side)   # join: all write-backs land before the next token step
+            self._pf_pending = False
+
+    def _prefetch_hook(self, i, nl):
+        nxt = self.S[(i + 1) % nl]
+        if self.prefetch_state in (1, 2):
+            return lambda q, k, v, S, Z: ops.linattn_step(q, k, v, S, Z, prefetch=nxt, prefetch_when=self.prefetch_state)
+        if self.prefetch_state == 3:                        # stand-alone prefetch kernel right after the step, same chain
+            def hook3(q, k, v, S, Z):
+                out = ops.linattn_step(q, k, v, S, Z)
+                ops.l2_prefetch(nxt)
+                return out
+            return hook3
+        if not hasattr(self, "side"):
+            self.side = torch.cuda.Stream(device=self.S.device)
+        self._pf_pending = False
+
+        def hook4(q, k, v, S, Z):                           # stand-alone prefetch kernel on a side branch of the step graph
+            main = torch.cuda.current_stream()
+            if self._pf_pending:
+                main.wait_stream(self.side)                 # join: the prefetch of THIS state was issued a layer ago
+            out = ops.linattn_step(q, k, v, S, Z)
+            self.side.wait_stream(main)
+            with torch.cuda.stream(self.side):
+                ops.l2_prefetch(nxt)
+            self._pf_pending = True
+            return out
+        return hook4
 
     def _split_hook(self, i):
         def hook(q, k, v, S, Z):

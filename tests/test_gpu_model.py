@@ -155,7 +155,8 @@ def test_lazy_state_rollout_is_bit_identical(cuda, cpm, golden, T):
     ref_e = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=False)
     ref = ref_e.generate(init)
     for use_graph, kw in ((False, dict(lazy_state=True)), (True, dict(lazy_state=True)), (False, dict(split_state=True)),
-                          (True, dict(split_state=True))):
+                          (True, dict(split_state=True)), (True, dict(prefetch_state=1)), (False, dict(prefetch_state=2)),
+                          (True, dict(prefetch_state=3)), (True, dict(prefetch_state=4)), (False, dict(prefetch_state=4))):
         eng = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=use_graph, **kw)
         for _ in range(2):
             out = eng.generate(init)

@@ -56,6 +56,18 @@ def main():
                           "tokens_per_s": round(tok / ms * 1e3), "model_tflops": round(tok * 236.1e6 / ms / 1e9, 1),
                           "frac_of_sustained_bf16_peak": round(tok * 236.1e6 / ms / 1e9 / 1402.2, 3)}), flush=True)
         del m, opt
+        # the same step captured once as a CUDA graph (cpmusic.GraphedTrainStep): no host launch cost per kernel
+        for (N, L) in ((32, 512), (4, 512)):
+            m = cpmusic.TransformerModel(VOCAB, dropout=0.1).to(dev).train()
+            opt = torch.optim.Adam(m.parameters(), lr=1e-4, fused=True, capturable=True)
+            gs = cpmusic.GraphedTrainStep(m, opt, batch_size=N, seq_len=L, max_grad_norm=3.0)
+            x, y, mask = batch(N, L, dev)
+            ms = timed(lambda: gs(x, y, mask), args.iters)
+            tok = N * L
+            print(json.dumps({"config": f"cfg2 pretrain step {N}x{L} bf16, whole-step CUDA graph", "ms_per_step": round(ms, 3),
+                              "tokens_per_s": round(tok / ms * 1e3), "model_tflops": round(tok * 236.1e6 / ms / 1e9, 1),
+                              "frac_of_sustained_bf16_peak": round(tok * 236.1e6 / ms / 1e9 / 1402.2, 3)}), flush=True)
+            del m, opt, gs
     if not args.only or args.only == "cfg4":
         q = cpmusic.LinearTransformer(VOCAB, dropout=0.1).to(dev).train()
         tgt = cpmusic.LinearTransformer(VOCAB, dropout=0.1).to(dev).eval()

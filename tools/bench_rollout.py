@@ -23,7 +23,8 @@ def main():
     for cfg in [(c, md) for c in args.configs for md in args.modes]:
         cfg, md = cfg
         g, spg = (int(x) for x in cfg.split("x"))
-        kw = dict(mode=md.split("+")[0], pdl=md.endswith("+pdl"), lazy_state=md.endswith("+lazy"), split_state=md.endswith("+split"))
+        kw = dict(mode=md.split("+")[0], pdl=md.endswith("+pdl"), lazy_state=md.endswith("+lazy"), split_state=md.endswith("+split"),
+                  prefetch_state=int(md[-1]) if md[-4:-1] == "+pf" else 0)
         if g == 1:
             eng = cpmusic.RolloutEngine(actor, args.songs, args.steps, greedy=False, seed=1, **kw)
         else:
