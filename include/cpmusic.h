@@ -93,7 +93,9 @@ int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out
  * testing-no-type-cp.py:154,167):
  *     Z += Kf ; S += Kf (x) v ; out = Qf^T S / (Qf.Z + eps)
  * q,k,v: (N,H,E) rows with row stride ld_qkv; out (N,H,M) row stride ld_o;
- * S (N,H,E,M) fp32 and Z (N,H,E) fp32 are updated IN PLACE (as ft does under no_grad). */
+ * S (N,H,E,M) fp32 and Z (N,H,E) fp32 are updated IN PLACE (as ft does under no_grad).
+ * E = M = 64 (the reference's heads) runs the streaming 256-bit kernel; other widths (E <= 256, M in {32, 64, 128}; e.g.
+ * the 8 x 128 variant of BASELINE cfg5) a generic 128-bit one. */
 int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, float *Z, void *out,
                      int N, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
                      int dtype, float eps, void *stream);

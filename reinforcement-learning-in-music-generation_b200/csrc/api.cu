@@ -119,6 +119,57 @@ __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__
 }
 
 // ------------------------------------------------------------------------------------------
+// B1, other head widths (E rows <= 256, M in {32, 64, 128} columns; SURVEY §8 a7 lists 8 heads x 128 for cfg5).  One CTA per
+// (sequence, head); M/4 threads span a state row with 128-bit accesses, the 256/(M/4) row groups stride over the rows; the
+// output is reduced over row groups through shared memory.  Same arithmetic order per element as the 64-wide kernel
+// (fma(Kf_e, v_m, S_em), then Qf_e * S_em), different summation order over e.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void __launch_bounds__(256) linattn_step_wide_kernel(const T *__restrict__ q, const T *__restrict__ k,
+                                                                const T *__restrict__ v, float *__restrict__ S,
+                                                                float *__restrict__ Z, T *__restrict__ out, int H, int E, int M,
+                                                                int64_t ld_qkv, int64_t ld_o, float eps) {
+    extern __shared__ __align__(16) float sm_wide[];
+    float *qf = sm_wide, *kf = qf + E, *vv = kf + E, *part = vv + M;       // part: (row groups, M)
+    __shared__ float dred[8];
+    const int nh = blockIdx.x, n = nh / H, h = nh % H, tid = threadIdx.x;
+    float dpart = 0.f;
+    for (int i = tid; i < E; i += 256) {
+        const float ke = phi(to_f(k[(int64_t)n * ld_qkv + h * E + i])), qe = phi(to_f(q[(int64_t)n * ld_qkv + h * E + i]));
+        float *z = Z + (int64_t)nh * E + i;
+        const float zn = *z + ke;
+        *z = zn;
+        kf[i] = ke; qf[i] = qe;
+        dpart += qe * zn;
+    }
+    for (int i = tid; i < M; i += 256) vv[i] = to_f(v[(int64_t)n * ld_qkv + h * M + i]);
+    dpart = warp_sum(dpart);
+    if ((tid & 31) == 0) dred[tid >> 5] = dpart;
+    __syncthreads();
+    const int tpr = M >> 2, RG = 256 / tpr, c4 = (tid % tpr) * 4, rg = tid / tpr;
+    const float4 v4 = *reinterpret_cast<const float4 *>(vv + c4);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    float *base = S + (int64_t)nh * E * M + c4;
+#pragma unroll 4
+    for (int e = rg; e < E; e += RG) {
+        float4 s = *reinterpret_cast<const float4 *>(base + (int64_t)e * M);
+        const float ke = kf[e], qe = qf[e];
+        s.x = fmaf(ke, v4.x, s.x); s.y = fmaf(ke, v4.y, s.y); s.z = fmaf(ke, v4.z, s.z); s.w = fmaf(ke, v4.w, s.w);
+        *reinterpret_cast<float4 *>(base + (int64_t)e * M) = s;
+        acc.x = fmaf(qe, s.x, acc.x); acc.y = fmaf(qe, s.y, acc.y); acc.z = fmaf(qe, s.z, acc.z); acc.w = fmaf(qe, s.w, acc.w);
+    }
+    *reinterpret_cast<float4 *>(part + rg * M + c4) = acc;
+    __syncthreads();
+    if (tid < M) {
+        float o = 0.f, d = eps;
+        for (int g = 0; g < RG; ++g) o += part[g * M + tid];
+#pragma unroll
+        for (int w = 0; w < 8; ++w) d += dred[w];
+        out[(int64_t)n * ld_o + h * M + tid] = from_f<T>(o / d);
+    }
+}
+
+// ------------------------------------------------------------------------------------------
 // B1 (split): the step as two kernels so that the state write-back leaves the token step's critical path.
 //   linattn_step_out_kernel     reads S, forms S + Kf (x) v in registers (same FMA as the fused kernel: bit-identical
 //                               output), writes the attention output, Z, and parks [Kf | v] (512 B) for the second half;
@@ -420,10 +471,23 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
                      int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream) {
     CPM_REQUIRE(q && k && v && S && Z && out, CPM_ERR_NULL, "linattn_step: NULL pointer");
     CPM_REQUIRE(N > 0 && H > 0, CPM_ERR_BAD_SHAPE, "linattn_step: N=%d H=%d", N, H);
-    CPM_REQUIRE(E == 64 && M == 64, CPM_ERR_BAD_SHAPE, "linattn_step: only E=M=64 (got %d,%d)", E, M);
-    CPM_REQUIRE(ld_qkv >= (int64_t)H * 64 && ld_o >= (int64_t)H * 64, CPM_ERR_BAD_SHAPE, "linattn_step: strides");
+    CPM_REQUIRE(E > 0 && E <= 256 && (M == 32 || M == 64 || M == 128), CPM_ERR_BAD_SHAPE,
+                "linattn_step: E=%d M=%d (supported: E <= 256, M in {32, 64, 128}; E = M = 64 takes the streaming kernel)", E, M);
+    CPM_REQUIRE(ld_qkv >= (int64_t)H * (E > M ? E : M) && ld_o >= (int64_t)H * M, CPM_ERR_BAD_SHAPE, "linattn_step: strides");
     CPM_REQUIRE(aligned16(S), CPM_ERR_BAD_ALIGN, "linattn_step: S must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
+    if (E != 64 || M != 64) {
+        CPM_REQUIRE(dtype == CPM_F32 || dtype == CPM_BF16, CPM_ERR_BAD_DTYPE, "linattn_step: dtype %d", dtype);
+        const size_t smem = (size_t)(2 * E + M + (256 / (M / 4)) * M) * sizeof(float);
+        if (dtype == CPM_F32)
+            linattn_step_wide_kernel<float><<<N * H, 256, smem, st>>>((const float *)q, (const float *)k, (const float *)v, S, Z,
+                                                                      (float *)out, H, E, M, ld_qkv, ld_o, eps);
+        else
+            linattn_step_wide_kernel<__nv_bfloat16><<<N * H, 256, smem, st>>>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k,
+                                                                              (const __nv_bfloat16 *)v, S, Z, (__nv_bfloat16 *)out,
+                                                                              H, E, M, ld_qkv, ld_o, eps);
+        return check_launch("linattn_step (wide)");
+    }
     if (dtype == CPM_F32)
         linattn_step_kernel<float><<<N * H, 256, 0, st>>>((const float *)q, (const float *)k, (const float *)v, S, Z,
                                                           (float *)out, H, ld_qkv, ld_o, eps);

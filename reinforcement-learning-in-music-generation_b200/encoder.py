@@ -148,8 +148,8 @@ class AttentionLayer(nn.Module):
         super().__init__()
         d_keys = d_keys or d_model // n_heads
         d_values = d_values or d_model // n_heads
-        if d_keys != 64 or d_values != 64:
-            raise ValueError("cpmusic kernels implement query_dimensions = value_dimensions = 64 (the reference's)")
+        if d_keys != d_values or d_keys not in (64, 128):
+            raise ValueError("cpmusic kernels implement query_dimensions = value_dimensions = 64 (the reference's) or 128")
         self.n_heads = n_heads
         self.query_projection = nn.Linear(d_model, d_keys * n_heads)
         self.key_projection = nn.Linear(d_model, d_keys * n_heads)
@@ -158,9 +158,9 @@ class AttentionLayer(nn.Module):
 
 
 class TransformerEncoderLayer(nn.Module):
-    def __init__(self, d_model, n_heads, d_ff, dropout=0.1):
+    def __init__(self, d_model, n_heads, d_ff, dropout=0.1, d_head=None):
         super().__init__()
-        self.attention = AttentionLayer(d_model, n_heads)
+        self.attention = AttentionLayer(d_model, n_heads, d_head, d_head)
         self.linear1 = nn.Linear(d_model, d_ff)
         self.linear2 = nn.Linear(d_ff, d_model)
         self.norm1 = nn.LayerNorm(d_model)
@@ -174,12 +174,12 @@ class TransformerEncoder(nn.Module):
     def __init__(self, n_layers=12, n_heads=8, query_dimensions=64, value_dimensions=64,
                  feed_forward_dimensions=2048, dropout=0.1, compute_dtype=torch.bfloat16):
         super().__init__()
-        if query_dimensions != 64 or value_dimensions != 64:
-            raise ValueError("cpmusic kernels implement query_dimensions = value_dimensions = 64")
+        if query_dimensions != value_dimensions or query_dimensions not in (64, 128):
+            raise ValueError("cpmusic kernels implement query_dimensions = value_dimensions = 64 (the reference's) or 128")
         d_model = value_dimensions * n_heads
-        self.d_model, self.n_heads = d_model, n_heads
+        self.d_model, self.n_heads, self.d_head = d_model, n_heads, query_dimensions
         self.layers = nn.ModuleList([
-            TransformerEncoderLayer(d_model, n_heads, feed_forward_dimensions, dropout) for _ in range(n_layers)])
+            TransformerEncoderLayer(d_model, n_heads, feed_forward_dimensions, dropout, query_dimensions) for _ in range(n_layers)])
         self.norm = nn.LayerNorm(d_model)
         self.compute_dtype = compute_dtype
         self.attn_impl = 0            # 0 auto | 1 simt | 2 tcgen05  (cpm_linattn_fwd `impl`)
@@ -222,22 +222,23 @@ class TransformerEncoder(nn.Module):
 
     # ---- recurrent (one token per call) path; shares every parameter with the parallel path ------
     def new_state(self, N, device):
-        H = self.n_heads
-        return [[torch.zeros(N, H, 64, 64, dtype=torch.float32, device=device),
-                 torch.zeros(N, H, 64, dtype=torch.float32, device=device)] for _ in self.layers]
+        H, E = self.n_heads, self.d_head
+        return [[torch.zeros(N, H, E, E, dtype=torch.float32, device=device),
+                 torch.zeros(N, H, E, dtype=torch.float32, device=device)] for _ in self.layers]
 
     def _step_layer(self, i, layer, x, st):
         p = layer.dropout.p if self.training else 0.0
         dt, c, at, H = self.compute_dtype, self._cache, layer.attention, self.n_heads
         qkv = cached_linear(c, ("qkv", i), [at.query_projection, at.key_projection, at.value_projection], x, dt)
         N = qkv.shape[0]
-        q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
+        E = self.d_head
+        q, k, v = (qkv[:, j * H * E:(j + 1) * H * E].unflatten(-1, (H, E)) for j in range(3))
         if len(st) > 2 and callable(st[2]):      # rollout engine hook: (q, k, v, S, Z) -> attention output
-            a = st[2](q, k, v, st[0], st[1]).view(N, H * 64)
+            a = st[2](q, k, v, st[0], st[1]).view(N, H * E)
         elif len(st) > 2:        # rollout engine: [S, Z, ring, step_dev] -> deferred state write-back
-            a = ops.linattn_step_lazy(q, k, v, st[0], st[1], st[2], st[3]).view(N, H * 64)
+            a = ops.linattn_step_lazy(q, k, v, st[0], st[1], st[2], st[3]).view(N, H * E)
         else:
-            a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * 64)
+            a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * E)
         o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
         x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
         h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)

@@ -186,7 +186,7 @@ class _LinAttnFused(torch.autograd.Function):
     """qkv (N,L,3*H*64) fused projection output -> (N,L,H*64)."""
 
     @staticmethod
-    def forward(ctx, qkv, H, eps, impl):
+    def forward(ctx, qkv, H, eps, impl, want_den=False):
         N, L, W = qkv.shape
         E = W // (3 * H)
         qkv = qkv.contiguous()
@@ -196,10 +196,14 @@ class _LinAttnFused(torch.autograd.Function):
         out, den = linattn_fwd_raw(q, k, v, eps, impl, saved=saved)
         ctx.save_for_backward(qkv, out, den, saved)
         ctx.cfg = (H, E, eps, impl)
+        if want_den:                          # the kernel's normaliser as a second, non-differentiable output
+            den_out = den.clone()
+            ctx.mark_non_differentiable(den_out)
+            return out.view(N, L, H * E), den_out
         return out.view(N, L, H * E)
 
     @staticmethod
-    def backward(ctx, gout):
+    def backward(ctx, gout, *_unused):
         qkv, out, den, saved = ctx.saved_tensors
         H, E, eps, impl = ctx.cfg
         N, L, W = qkv.shape
@@ -207,7 +211,7 @@ class _LinAttnFused(torch.autograd.Function):
         gqkv = torch.empty_like(qkv)
         gq, gk, gv = (gqkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
         linattn_bwd_raw(q, k, v, out, den, gout.reshape(N, L, H, E), gq, gk, gv, eps, impl, saved=saved)
-        return gqkv, None, None, None
+        return gqkv, None, None, None, None
 
 
 class _LinAttn(torch.autograd.Function):
@@ -231,10 +235,48 @@ class _LinAttn(torch.autograd.Function):
 
 
 def causal_linear_attention(q, k, v, eps=EPS_ATTN, impl=0):
+    """q,k,v (N,L,H,E) -> (N,L,H,E) (ft's CausalLinearAttention signature); E = 64 or 128."""
+    if q.shape[-1] == 128:
+        N, L, H, _ = q.shape
+        qkv = torch.cat([t.reshape(N, L, H * 128) for t in (q, k, v)], -1)
+        return causal_linear_attention_fused(qkv, H, eps, impl).view(N, L, H, 128)
     return _LinAttn.apply(q, k, v, eps, impl)
 
 
+def _linattn_fused_e128(qkv, H, eps, impl):
+    """128-wide heads (cfg5 may be 8 heads x 128) on the 64-wide kernels.  With the feature-mapped queries /
+    keys split into halves a and the values into halves b,
+        A_ij = A0_ij + A1_ij,   out_i[b] = (num^{0,b}_i + num^{1,b}_i) / (den^0_i + den^1_i - eps),
+    where num^{a,b} = out^{a,b} * den^a is what one 64-wide attention over (q^a, k^a, v^b) returns.  Two kernel passes over
+    2H virtual heads give all four blocks: the buffer as it is (a = b) and with the value halves swapped (a != b).  The
+    per-half normalisers carry their VALUE from the kernels and their GRADIENT from a differentiable restatement
+    (phi(q^a) . cumsum phi(k^a)), so that the recombination is exact in the forward and autograd handles the rest."""
+    N, L, W = qkv.shape
+    d = H * 128
+    q, k, v = qkv[..., :d], qkv[..., d:2 * d], qkv[..., 2 * d:]
+    v_sw = v.unflatten(-1, (H, 2, 64)).flip(-2).flatten(-3)
+    same, den_s = _LinAttnFused.apply(qkv, 2 * H, eps, impl, True)
+    cross, _ = _LinAttnFused.apply(torch.cat([q, k, v_sw], -1), 2 * H, eps, impl, True)
+    # feature-major copies: the running key sum is then a scan along the contiguous axis (an outer-dimension cumsum over
+    # L = 8192 costs 2 ms per call, 10x everything else here)
+    qf = torch.nn.functional.elu(q.transpose(1, 2).contiguous().float()) + 1.0               # (N, H*128, L)
+    kf = torch.nn.functional.elu(k.transpose(1, 2).contiguous().float()) + 1.0
+    den = (qf * kf.cumsum(-1)).unflatten(1, (H, 2, 64)).sum(3) + eps                         # (N,H,2,L)
+    den = den.permute(0, 3, 1, 2).unsqueeze(-1)                                              # (N,L,H,2,1)
+    den = den + (den_s.view(N, L, H, 2, 1) - den).detach()
+    same, cross = same.float().unflatten(-1, (H, 2, 64)), cross.float().unflatten(-1, (H, 2, 64))
+    num = same * den + (cross * den).flip(-2)            # [h, b] = out^{b,b} den^b + out^{1-b,b} den^{1-b}
+    tot = den.sum(-2, keepdim=True) - eps
+    return (num / tot).flatten(-3).to(qkv.dtype)
+
+
 def causal_linear_attention_fused(qkv, n_heads, eps=EPS_ATTN, impl=0):
+    """qkv (N,L,3*H*E) -> (N,L,H*E); E = 64 (one kernel pass) or 128 (two passes over 64-wide virtual heads)."""
+    E = qkv.shape[-1] // (3 * n_heads)
+    if qkv.shape[-1] != 3 * n_heads * E or E not in (64, 128):
+        raise ValueError(f"causal linear attention: head width {E} (supported: 64, 128)")
+    if E == 128:
+        return _linattn_fused_e128(qkv, n_heads, eps, impl)
     return _LinAttnFused.apply(qkv, n_heads, eps, impl)
 
 

@@ -49,8 +49,9 @@ class RolloutEngine:
         dev = next(model.parameters()).device
         enc = model.transformer_encoder
         A, H, nl = len(model.attrs), enc.n_heads, len(enc.layers)
-        self.S = torch.zeros(nl, batch, H, 64, 64, dtype=torch.float32, device=dev)
-        self.Z = torch.zeros(nl, batch, H, 64, dtype=torch.float32, device=dev)
+        E = enc.d_head
+        self.S = torch.zeros(nl, batch, H, E, E, dtype=torch.float32, device=dev)
+        self.Z = torch.zeros(nl, batch, H, E, dtype=torch.float32, device=dev)
         self.state = [[self.S[i], self.Z[i]] for i in range(nl)]
         self.step_dev = torch.zeros(1, dtype=torch.int32, device=dev)
         # deferred state write-back (unfused mode, opt-in): S goes back to HBM once per ops.LAZY_STATE_PERIOD tokens; the
@@ -95,6 +96,8 @@ class RolloutEngine:
             raise ValueError("the tcgen05 rollout step needs bf16 compute, widths that are multiples of 64 (inputs) / 32 (outputs)")
         if mode not in ("mega", "fused", "unfused", "tc", "fold"):
             raise ValueError(f"unknown rollout mode {mode!r}")
+        if E != 64 and (mode != "unfused" or self.lazy_state or self.split_state or self.prefetch_state):
+            raise ValueError("128-wide heads run the plain unfused rollout step only")
         if (self.lazy_state or self.split_state or self.prefetch_state) and mode != "unfused":
             raise ValueError("lazy_state / split_state / prefetch_state are implemented for the unfused step")
         self.mode = mode
@@ -159,7 +162,8 @@ class RolloutEngine:
         return m.compute_dtype == torch.bfloat16 and all(w % 64 == 0 for w in ins + outs)
 
     def _tc_stamp(self):
-        return tuple(p._version for p in self.model.parameters())
+        from .encoder import _OPT_EPOCH                      # fused optimizers do not bump _version (see PackCache)
+        return tuple(p._version for p in self.model.parameters()) + (_OPT_EPOCH[0],)
 
     def _tc_refresh(self):
         """(Re)builds, in place, the bf16 weights with the consumer-side LayerNorm folded in:

@@ -174,6 +174,65 @@ def test_linattn_cfg5_long_sequence(cuda, cpm):
         assert not bool(g[:, t:].any()) and bool(g[:, :t].any())
 
 
+@pytest.mark.parametrize("dtype,impl,shape", [(torch.float32, 1, (2, 150, 3)), (torch.float32, 1, (1, 64, 1)),
+                                              (torch.bfloat16, 0, (2, 256, 4)), (torch.bfloat16, 0, (1, 1024, 8))])
+def test_linattn_head_width_128_vs_oracle(cuda, cpm, dtype, impl, shape):
+    """128-wide heads (cfg5 as 8 heads x 128): two passes of the 64-wide kernels over virtual heads,
+    recombined with the joint normaliser — forward and all three gradients against the fp64 oracle run at E = M = 128.
+    Tolerances as for the 64-wide kernels (fp32 1e-4 class; bf16 storage 2e-2 class, on the same bf16-rounded inputs)."""
+    N, L, H = shape
+    gen = torch.Generator().manual_seed(L + H)
+    q, k, v, go = (torch.randn(N, L, H, 128, generator=gen).to(cuda).to(dtype).requires_grad_() for _ in range(4))
+    out = cpm.ops.causal_linear_attention(q, k, v, impl=impl)
+    assert out.shape == (N, L, H, 128) and out.dtype == dtype
+    if dtype == torch.bfloat16 and L % 128 == 0:
+        assert cpm.ops.linattn_last_impl() == "tcgen05-cp"
+    out.backward(go.detach())
+    ro, rq, rk, rv = _oracle_attn(q.float(), k.float(), v.float(), go.float())
+    if dtype == torch.float32:
+        scale = 1.0 + math.sqrt(L) * 0.02
+        _cmp(out, ro, 5e-5, 2e-5, "out")
+        for name, a, b in (("gq", q.grad, rq), ("gk", k.grad, rk), ("gv", v.grad, rv)):
+            _cmp(a, b, 3e-4 * scale, 2e-4, name)
+    else:
+        _cmp(out, ro, 2e-2, 1e-2, "out")
+        for name, a, b in (("gq", q.grad, rq), ("gk", k.grad, rk), ("gv", v.grad, rv)):
+            _cmp(a, b, 4e-2, 3e-2, name)
+
+
+@pytest.mark.parametrize("E,M", [(128, 128), (32, 64), (96, 32)])
+def test_linattn_step_other_head_widths(cuda, cpm, E, M):
+    """The generic recurrent step (E != 64 or M != 64) against ft's recurrence (oracle, fp64) over 40 tokens, fp32 and
+    bf16 inputs; E = M = 128 additionally equals the chunked path on the same sequence."""
+    T, N, H = 40, 3, 2
+    gen = torch.Generator().manual_seed(E + M)
+    q, k = (torch.randn(T, N, H, E, generator=gen) for _ in range(2))
+    v = torch.randn(T, N, H, M, generator=gen)
+    for dtype, tol in ((torch.float32, 3e-5), (torch.bfloat16, 2e-2)):
+        qd, kd, vd = (t.to(cuda).to(dtype) for t in (q, k, v))
+        S = torch.zeros(N, H, E, M, device=cuda)
+        Z = torch.zeros(N, H, E, device=cuda)
+        lib, W, state = cpm._lib.load(), H * max(E, M), None
+        for t in range(T):
+            o = torch.empty(N, H, M, dtype=dtype, device=cuda)
+            qp, kp, vp = (torch.zeros(N, W, dtype=dtype, device=cuda) for _ in range(3))      # one row stride for q, k and v
+            qp[:, :H * E], kp[:, :H * E], vp[:, :H * M] = qd[t].reshape(N, -1), kd[t].reshape(N, -1), vd[t].reshape(N, -1)
+            rc = lib.cpm_linattn_step(qp.data_ptr(), kp.data_ptr(), vp.data_ptr(), S.data_ptr(), Z.data_ptr(), o.data_ptr(),
+                                      N, H, E, M, W, H * M, cpm.ops._dt(qd), cpm.ops.EPS_ATTN, torch.cuda.current_stream().cuda_stream)
+            assert rc == 0, lib.cpm_last_error_string()
+            ro, state = ft.recurrent_linear_attention(qd[t].double().cpu(), kd[t].double().cpu(), vd[t].double().cpu(), state)
+            _cmp(o, ro, tol, tol, f"step {t} out ({dtype})")
+        _cmp(S, state[0], 1e-4, 1e-5, "S")
+        _cmp(Z, state[1], 1e-4, 1e-5, "Z")
+    if E == M == 128:
+        par = cpm.ops.causal_linear_attention(q.to(cuda).permute(1, 0, 2, 3).contiguous(), k.to(cuda).permute(1, 0, 2, 3).contiguous(),
+                                              v.to(cuda).permute(1, 0, 2, 3).contiguous(), impl=1)
+        S = torch.zeros(N, H, E, M, device=cuda)
+        Z = torch.zeros(N, H, E, device=cuda)
+        rec = torch.stack([cpm.ops.linattn_step(q[t].to(cuda), k[t].to(cuda), v[t].to(cuda), S, Z) for t in range(T)], 1)
+        _cmp(rec, par, 3e-5, 3e-5, "recurrent vs chunked at E = M = 128")
+
+
 # ------------------------------------------------------------------ embedding / PE / dropout
 def test_embed_fwd_bwd(cuda, cpm):
     emb = [128, 256, 64, 512, 128, 128]

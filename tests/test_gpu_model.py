@@ -92,6 +92,43 @@ def test_module_vs_live_oracle_random_weights(cuda, cpm):
     _cmp(cl, ref[3], 2e-4, 1e-4, "compute_loss")
 
 
+def test_module_with_128_wide_heads_vs_live_oracle(cuda, cpm):
+    """BASELINE cfg5's other reading (d_model = heads x 128): the same module surface with query/value dimensions 128 —
+    teacher-forced losses and gradients against the oracle, and the recurrent path (generic step kernel, state
+    (N,H,128,128)) against the parallel one, all in fp32 compute."""
+    torch.manual_seed(17)
+    cfg = dict(d_model=256, n_layer=2, n_head=2, d_inner=256, dropout=0.0)
+    o = mo.OracleCPModel(VOCAB, **cfg).eval()
+    m = cpm.TransformerModel(VOCAB, compute_dtype=torch.float32, **cfg)
+    m.load_state_dict(o.state_dict())
+    m = m.to(cuda)
+    gen = torch.Generator().manual_seed(18)
+    x = torch.stack([torch.randint(0, n, (2, 140), generator=gen) for n in VOCAB], -1)
+    mask = torch.ones(2, 140)
+    mask[0, 90:] = 0
+    ref = torch.stack(o.train_step(x, x.roll(-1, 1), mask))
+    got = torch.stack(m.train_step(x.to(cuda), x.roll(-1, 1).to(cuda), mask.to(cuda)))
+    _cmp(got, ref, 2e-4, 1e-4, "losses")
+    (ref.sum() / 6).backward()
+    (got.sum() / 6).backward()
+    po = dict(o.named_parameters())
+    for name, prm in m.named_parameters():
+        if po[name].grad is not None:
+            r = po[name].grad
+            _cmp(prm.grad, r, 2e-5 + 2e-3 * r.abs().max().item(), 2e-3, f"grad {name}")
+    mr = cpm.TransformerModel(VOCAB, is_training=False, compute_dtype=torch.float32, **cfg)
+    mr.load_state_dict(o.state_dict())
+    mr = mr.to(cuda).eval()
+    with torch.no_grad():
+        par = m.eval().forward_hidden(x[:1, :20].to(cuda))
+        mem, hs = None, []
+        for t in range(20):
+            h, mem = mr.forward_hidden(x[:1, t:t + 1].to(cuda), mem, is_training=False, pos_offset=t)
+            hs.append(h)
+    assert mem[0][0].shape == (1, 2, 128, 128)
+    _cmp(torch.stack(hs, 1), par, 3e-4, 1e-4, "recurrent vs parallel at 128-wide heads")
+
+
 def test_recurrent_forward_hidden(cuda, cpm, golden):
     """Recurrent mode: default reproduces the reference's position-0 quirk; pos_offset
     gives the true position and then matches the parallel path."""
