@@ -22,6 +22,11 @@ from . import ft_oracle as ft
 
 ATTRS = ("tempo", "chord", "barbeat", "pitch", "duration", "velocity")
 EMB_SIZES = (128, 256, 64, 512, 128, 128)
+# seven-attribute layout of the data files (`type` at column 3, agent_pretrain.py:525-526 drops it before the model): the same
+# restatement with one more independent embedding / head pair — the reference has no type-conditioned head
+# (project_concat_type is allocated and never used, dqn_policy/model.py:153), so neither does this.
+ATTRS7 = ("tempo", "chord", "barbeat", "type", "pitch", "duration", "velocity")
+EMB_SIZES7 = (128, 256, 64, 32, 512, 128, 128)
 
 
 class Embeddings(nn.Module):
@@ -61,13 +66,14 @@ class OracleCPModel(nn.Module):
                  n_head=8, d_inner=2048, dropout=0.1):
         super().__init__()
         self.n_token = list(n_token)
+        self.attrs, self.emb_sizes = (ATTRS7, EMB_SIZES7) if len(self.n_token) == 7 else (ATTRS, EMB_SIZES)
         self.d_model, self.n_layer, self.n_head = d_model, n_layer, n_head
         self.variant = variant
         self.loss_func = nn.CrossEntropyLoss(reduction="none")
-        for name, n, e in zip(ATTRS, self.n_token, EMB_SIZES):
+        for name, n, e in zip(self.attrs, self.n_token, self.emb_sizes):
             setattr(self, f"word_emb_{name}", Embeddings(n, e))
         self.pos_emb = PositionalEncoding(d_model, dropout)
-        self.in_linear = nn.Linear(sum(EMB_SIZES), d_model)
+        self.in_linear = nn.Linear(sum(self.emb_sizes), d_model)
         builder = ft.TransformerEncoderBuilder if is_training else ft.RecurrentEncoderBuilder
         self.transformer_encoder = builder.from_kwargs(
             n_layers=n_layer, n_heads=n_head, query_dimensions=d_model // n_head,
@@ -77,12 +83,12 @@ class OracleCPModel(nn.Module):
             self.project_concat_type = nn.Linear(d_model, d_model)   # allocated, unused
         else:
             self.value_funtion = nn.Sequential(nn.Linear(d_model, 128), nn.ReLU(), nn.Linear(128, 1))
-        for name, n in zip(ATTRS, self.n_token):
+        for name, n in zip(self.attrs, self.n_token):
             setattr(self, f"proj_{name}", nn.Linear(d_model, n))
 
     # -- pieces ------------------------------------------------------------- #
     def embed(self, x):
-        embs = [getattr(self, f"word_emb_{a}")(x[..., i]) for i, a in enumerate(ATTRS)]
+        embs = [getattr(self, f"word_emb_{a}")(x[..., i]) for i, a in enumerate(self.attrs)]
         return self.in_linear(torch.cat(embs, dim=-1))
 
     def forward_hidden(self, x, memory=None, is_training=True, pos_offset: int = 0):
@@ -94,7 +100,7 @@ class OracleCPModel(nn.Module):
         return self.transformer_encoder(z, memory=memory)
 
     def forward_output(self, h, y=None):
-        return tuple(getattr(self, f"proj_{a}")(h) for a in ATTRS)
+        return tuple(getattr(self, f"proj_{a}")(h) for a in self.attrs)
 
     def forward(self, x, target=None):
         return self.forward_output(self.forward_hidden(x), target)

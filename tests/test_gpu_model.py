@@ -92,6 +92,45 @@ def test_module_vs_live_oracle_random_weights(cuda, cpm):
     _cmp(cl, ref[3], 2e-4, 1e-4, "compute_loss")
 
 
+def test_seven_attribute_layout_vs_live_oracle(cuda, cpm):
+    """The data files' seven-attribute compound word (`type` kept at column 3): 7 embeddings (Σ = 1248), 7 heads.
+    Losses and gradients against the oracle, greedy recurrent decoding bit-exact against the oracle's argmax."""
+    vocab7 = [56, 135, 18, 4, 87, 18, 25]
+    torch.manual_seed(21)
+    cfg = dict(d_model=128, n_layer=2, n_head=2, d_inner=256, dropout=0.0)
+    o = mo.OracleCPModel(vocab7, **cfg).eval()
+    m = cpm.TransformerModel(vocab7, compute_dtype=torch.float32, **cfg)
+    assert m.attrs[3] == "type" and len(m.state_dict()) == len(o.state_dict())
+    m.load_state_dict(o.state_dict())
+    m = m.to(cuda)
+    gen = torch.Generator().manual_seed(22)
+    x = torch.stack([torch.randint(0, n, (3, 70), generator=gen) for n in vocab7], -1)
+    mask = torch.ones(3, 70)
+    mask[2, 40:] = 0
+    ref = torch.stack(o.train_step(x, x.roll(-1, 1), mask))
+    got = torch.stack(m.train_step(x.to(cuda), x.roll(-1, 1).to(cuda), mask.to(cuda)))
+    assert got.shape == (7,)
+    _cmp(got, ref, 2e-4, 1e-4, "losses")
+    (ref.sum() / 7).backward()
+    (got.sum() / 7).backward()
+    po = dict(o.named_parameters())
+    for name, prm in m.named_parameters():
+        if po[name].grad is not None:
+            r = po[name].grad
+            _cmp(prm.grad, r, 2e-5 + 2e-3 * r.abs().max().item(), 2e-3, f"grad {name}")
+    # greedy decoding, recurrent, true positions: tokens bit-exact against the oracle's parallel argmax on the decoded prefix
+    mr = cpm.TransformerModel(vocab7, is_training=False, compute_dtype=torch.float32, **cfg)
+    mr.load_state_dict(o.state_dict())
+    mr = mr.to(cuda).eval()
+    toks = cpm.RolloutEngine(mr, 2, 12, greedy=True).generate(x[:2, 0].to(cuda))["tokens"].cpu()      # (2, 13, 7)
+    with torch.no_grad():
+        logits = o.forward_output(o.forward_hidden(toks[:, :-1]))
+    for a, lg in enumerate(logits):
+        top2 = lg.topk(2, -1).values
+        sure = (top2[..., 0] - top2[..., 1]) > 1e-3                      # skip numerical near-ties
+        assert torch.equal(lg.argmax(-1)[sure], toks[:, 1:, a][sure]), f"attribute {a}"
+
+
 def test_module_with_128_wide_heads_vs_live_oracle(cuda, cpm):
     """BASELINE cfg5's other reading (d_model = heads x 128): the same module surface with query/value dimensions 128 —
     teacher-forced losses and gradients against the oracle, and the recurrent path (generic step kernel, state
