@@ -64,6 +64,44 @@ def test_train_step_bf16(cuda, cpm, golden):
     assert cos > 0.99, cos
 
 
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 2e-3), (torch.bfloat16, 6e-2)])
+def test_pretraining_loss_curve_matches_oracle(cuda, cpm, golden, dtype, tol):
+    """Reference-matching loss curves (north_star): 10 optimizer steps of the pretraining loop (agent_pretrain.py:557-565:
+    train_step, mean of the six losses, clip_grad_norm_ 3, Adam) on the same batches from the same initial weights —
+    cpmusic on the GPU with torch's FUSED Adam (which updates parameters without bumping their version counters, so this
+    also checks that every step's compute copies see the previous update) against the oracle on the CPU with plain Adam.
+    fp32 compute follows the oracle to 2e-3 over the whole curve; bf16 compute to 6e-2, and both must descend."""
+    g = golden("model_small")
+    m = _load_small(cpm, g, cuda, dtype=dtype).train()
+    o = mo.OracleCPModel(VOCAB, **SMALL).train()
+    o.load_state_dict({k[4:]: torch.from_numpy(g[k]) for k in g.files if k.startswith("sd::")}, strict=False)
+    om = torch.optim.Adam(m.parameters(), lr=1e-3, fused=True)
+    oo = torch.optim.Adam(o.parameters(), lr=1e-3)
+    gen = torch.Generator().manual_seed(31)
+    batches = []
+    for _ in range(2):                                   # two batches, revisited: something to fit, so the curve descends
+        x = torch.stack([torch.randint(0, n, (3, 96), generator=gen) for n in VOCAB], -1)
+        batches.append((x, x.roll(-1, 1), (torch.rand(3, 96, generator=gen) > 0.2).float()))
+    curve_m, curve_o = [], []
+    for step in range(10):
+        x, y, mask = batches[step % 2]
+        lo = sum(o.train_step(x, y, mask)) / 6
+        oo.zero_grad()
+        lo.backward()
+        torch.nn.utils.clip_grad_norm_(o.parameters(), 3.0)
+        oo.step()
+        lm = sum(m.train_step(x.to(cuda), y.to(cuda), mask.to(cuda))) / 6
+        om.zero_grad()
+        lm.backward()
+        torch.nn.utils.clip_grad_norm_(m.parameters(), 3.0)
+        om.step()
+        curve_m.append(lm.item())
+        curve_o.append(lo.item())
+    cm, co = torch.tensor(curve_m), torch.tensor(curve_o)
+    _cmp(cm, co, tol, 0.0, f"loss curve {curve_m} vs {curve_o}")
+    assert co[-2:].mean() < co[:2].mean() - 0.1 and cm[-2:].mean() < cm[:2].mean() - 0.1
+
+
 def test_module_vs_live_oracle_random_weights(cuda, cpm):
     """Fresh random weights (module default init) shared through state_dict — the drop-in contract:
     an oracle/reference checkpoint loads strictly and produces the same numbers."""
