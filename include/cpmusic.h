@@ -183,6 +183,13 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
  * (cpm_add_pe, cpm_dropout, cpm_ln_residual_fwd/bwd, cpm_gelu_fwd/bwd) adds *device_counter to its rng_offset
  * argument, so a CUDA graph that captured those launches (offsets frozen) still draws fresh masks on every replay
  * as long as the graph advances the counter.  Process-wide; set it before capture and keep the memory alive. */
+/* Column sums out[c] = sum_r x[r][c] of a (rows, width) bf16 / fp32 matrix with row stride ld (elements): the bias gradient
+ * of a Linear layer from its output gradient (what autograd's `grad_output.sum(0)` computes for nn.Linear,
+ * agent_pretrain.py:239 / every ft projection).  partials: caller-owned fp32 scratch of cpm_colsum_partials_rows(width) * width
+ * floats.  width must be a multiple of 16 (bf16) / 8 (fp32), ld of 8.  out (width) fp32 is OVERWRITTEN.  Deterministic. */
+int cpm_colsum_partials_rows(int width);
+int cpm_colsum(const void *x, int64_t rows, int width, int64_t ld, float *out, float *partials, int dtype, void *stream);
+
 int cpm_set_rng_base(const uint64_t *device_counter);
 
 /* bias + exact-erf GELU + dropout (ft activation='gelu' => F.gelu; K6):

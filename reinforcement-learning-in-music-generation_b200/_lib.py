@@ -44,6 +44,8 @@ SIGNATURES = {
                                 c_int64, c_int64, c_int64, c_int, c_float, c_int, _P, c_int64, _P, c_int64, _P]),
     "cpm_linattn_step": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
                                  c_int, c_float, _P]),
+    "cpm_colsum_partials_rows": (c_int, [c_int]),
+    "cpm_colsum": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, c_int, _P]),
     "cpm_l2_prefetch": (c_int, [_P, c_int64, _P]),
     "cpm_linattn_step_prefetch": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, c_float, _P]),
     "cpm_linattn_step_fold": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
@@ -95,8 +97,8 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
-    "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
+    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
+    "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2, "cpm_colsum": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
                                                                                 # kernel (ops adds 1 when the scan path runs); bwd = pre-pass, scan, main
 })
 EXTRA_LAUNCHES = [0]          # segment-total / scan kernels of segmented linear attention, graph replays

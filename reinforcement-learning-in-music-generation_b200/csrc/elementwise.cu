@@ -296,30 +296,99 @@ __global__ void __launch_bounds__(LN_BWD_THREADS) ln_residual_bwd_kernel(const T
     for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) partials[(int64_t)blockIdx.x * 3 * d + i] = red[i];
 }
 
-// out_k[c] += sum over `nrows` partial rows of width `width` (k = c / d selects dgamma | dbeta | dres_bias; NULL = skip).
-// 32 rows per CTA pass with 4 independent accumulators; one CTA column-slab of 64 columns; fixed order (deterministic).
+// out_k[c] (+)= sum over `nrows` partial rows of width `width` (k = c / d selects out0 | out1 | out2; NULL = skip).
+// One CTA per 32-column slab, 8 row groups, 8 independent loads in flight per thread; fixed order (deterministic).
+template <bool ACCUM>
 __global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__restrict__ partials, int nrows, int width, int d, float *__restrict__ out0,
                                                               float *__restrict__ out1, float *__restrict__ out2) {
-    __shared__ float sm[4][64];
-    const int cl = threadIdx.x & 63, rg = threadIdx.x >> 6;          // 64 columns x 4 row groups
-    const int c = blockIdx.x * 64 + cl;
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    __shared__ float sm[8][32];
+    const int cl = threadIdx.x & 31, rg = threadIdx.x >> 5;          // 32 columns x 8 row groups
+    const int c = blockIdx.x * 32 + cl;
+    float a[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     if (c < width) {
         int r = rg;
-        for (; r + 12 < nrows; r += 16) {
-            a0 += partials[(int64_t)r * width + c];
-            a1 += partials[(int64_t)(r + 4) * width + c];
-            a2 += partials[(int64_t)(r + 8) * width + c];
-            a3 += partials[(int64_t)(r + 12) * width + c];
+        for (; r + 56 < nrows; r += 64) {
+#pragma unroll
+            for (int i = 0; i < 8; ++i) a[i] += partials[(int64_t)(r + 8 * i) * width + c];
         }
-        for (; r < nrows; r += 4) a0 += partials[(int64_t)r * width + c];
+        for (; r < nrows; r += 8) a[0] += partials[(int64_t)r * width + c];
     }
-    sm[rg][cl] = (a0 + a1) + (a2 + a3);
+    sm[rg][cl] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
     __syncthreads();
     if (rg == 0 && c < width) {
-        const float tot = (sm[0][cl] + sm[1][cl]) + (sm[2][cl] + sm[3][cl]);
+        const float tot = ((sm[0][cl] + sm[1][cl]) + (sm[2][cl] + sm[3][cl])) + ((sm[4][cl] + sm[5][cl]) + (sm[6][cl] + sm[7][cl]));
         float *out = c < d ? out0 : (c < 2 * d ? out1 : out2);
-        if (out) out[c % d] += tot;
+        if (out) out[c % d] = ACCUM ? out[c % d] + tot : tot;
+    }
+}
+
+// ---------------------------------------------------------------- column sums (bias gradients of the Linear layers)
+// out[c] = sum_r x[r][c], x (rows, width) bf16 / fp32 row-major with row stride ld.  Stage 1: CTA (slab, rs) sums its rows of a
+// 1 KB-wide column slab: one warp spans the slab with 256-bit streaming loads (L1 no-allocate, L2 evict-first: measured 5.5-5.9
+// TB/s on a pure read against 4.1-4.6 TB/s for plain 128-bit loads, tools/probes/probe_read_bw.cu), 8 row lanes, 4 loads in
+// flight per thread; it writes one partial row.  Stage 2 is reduce_partials_kernel.  Deterministic; 2 launches.
+// Rows whose address is not 32-byte aligned (odd ld / column offset) take 128-bit loads.
+template <typename T> struct ColsumGeo { static constexpr int CPT = 32 / (int)sizeof(T), SLAB = 32 * CPT; };
+inline int colsum_row_slabs(int width, int slab) {          // ~8 CTAs per SM in total whatever the width
+    const int slabs = (width + slab - 1) / slab, r = (1184 + slabs - 1) / slabs;
+    return r < 1 ? 1 : (r > 256 ? 256 : r);
+}
+template <typename T, bool WIDE>
+__device__ __forceinline__ void colsum_load(const T *p, float (&v)[32 / sizeof(T)]) {
+    constexpr int CPT = 32 / (int)sizeof(T);
+    uint32_t w[8];
+    if (WIDE) {
+        asm volatile("ld.global.L1::no_allocate.L2::evict_first.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+                     : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(p));
+    } else {
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]) : "l"(p));
+        asm volatile("ld.global.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7])
+                     : "l"(reinterpret_cast<const char *>(p) + 16));
+    }
+    if (sizeof(T) == 4) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) v[j % CPT] = __uint_as_float(w[j]);
+    } else {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { v[(2 * j) % CPT] = __uint_as_float(w[j] << 16); v[(2 * j + 1) % CPT] = __uint_as_float(w[j] & 0xFFFF0000u); }
+    }
+}
+template <typename T, bool WIDE>
+__global__ void __launch_bounds__(256) colsum_partial_kernel(const T *__restrict__ x, int64_t rows, int width, int64_t ld, float *__restrict__ partials) {
+    constexpr int CPT = ColsumGeo<T>::CPT, SLAB = ColsumGeo<T>::SLAB;
+    __shared__ float sm[8][SLAB + 4];
+    const int cg = threadIdx.x & 31, rl = threadIdx.x >> 5;
+    const int c0 = blockIdx.x * SLAB + cg * CPT;
+    const int64_t per = (rows + gridDim.y - 1) / gridDim.y;
+    const int64_t r0 = (int64_t)blockIdx.y * per, r1 = min(rows, r0 + per);
+    float acc[CPT];
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) acc[j] = 0.f;
+    if (c0 < width) {                                  // width % CPT == 0: a thread's columns are all in or all out
+        int64_t r = r0 + rl;
+        for (; r + 24 < r1; r += 32) {
+            float v[4][CPT];
+#pragma unroll
+            for (int i = 0; i < 4; ++i) colsum_load<T, WIDE>(x + (r + 8 * i) * ld + c0, v[i]);
+#pragma unroll
+            for (int i = 0; i < 4; ++i)
+#pragma unroll
+                for (int j = 0; j < CPT; ++j) acc[j] += v[i][j];
+        }
+        for (; r < r1; r += 8) {
+            float v[CPT];
+            colsum_load<T, WIDE>(x + r * ld + c0, v);
+#pragma unroll
+            for (int j = 0; j < CPT; ++j) acc[j] += v[j];
+        }
+    }
+#pragma unroll
+    for (int j = 0; j < CPT; ++j) sm[rl][cg * CPT + j] = acc[j];
+    __syncthreads();
+    for (int cl = threadIdx.x; cl < SLAB; cl += 256) {
+        const int c = blockIdx.x * SLAB + cl;
+        if (c < width)
+            partials[(int64_t)blockIdx.y * width + c] = ((sm[0][cl] + sm[1][cl]) + (sm[2][cl] + sm[3][cl])) + ((sm[4][cl] + sm[5][cl]) + (sm[6][cl] + sm[7][cl]));
     }
 }
 
@@ -583,8 +652,32 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
                                                    dropout_scale(p_drop), seed, rng_offset, g_rng_base)));
     }
     const int width = (dres_bias ? 3 : 2) * d;
-    reduce_partials_kernel<<<(width + 63) / 64, 256, 0, (cudaStream_t)stream>>>(partials, LN_BWD_BLOCKS, 3 * d, d, dgamma, dbeta, dres_bias);
+    reduce_partials_kernel<true><<<(width + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, LN_BWD_BLOCKS, 3 * d, d, dgamma, dbeta, dres_bias);
     return check_launch("ln_residual_bwd");
+}
+
+int cpm_colsum_partials_rows(int width) { return width > 0 ? 256 : 0; }      // upper bound of the row slabs for any dtype
+
+int cpm_colsum(const void *x, int64_t rows, int width, int64_t ld, float *out, float *partials, int dtype, void *stream) {
+    CPM_REQUIRE(x && out && partials, CPM_ERR_NULL, "colsum: NULL pointer");
+    CPM_REQUIRE(dtype == CPM_F32 || dtype == CPM_BF16, CPM_ERR_BAD_DTYPE, "colsum: dtype %d", dtype);
+    const int cpt = dtype == CPM_F32 ? 8 : 16, slab = 32 * cpt, esz = dtype == CPM_F32 ? 4 : 2;
+    CPM_REQUIRE(rows >= 0 && width > 0 && width % cpt == 0 && ld >= width && ld % 8 == 0, CPM_ERR_BAD_SHAPE,
+                "colsum: width=%d must be a multiple of %d, ld=%lld of 8", width, cpt, (long long)ld);
+    CPM_REQUIRE(aligned16(x), CPM_ERR_BAD_ALIGN, "colsum: x must be 16-byte aligned");
+    const int R = colsum_row_slabs(width, slab);
+    const dim3 grid((width + slab - 1) / slab, R);
+    const bool wide = (reinterpret_cast<uintptr_t>(x) % 32 == 0) && ((ld * esz) % 32 == 0);
+    cudaStream_t st = (cudaStream_t)stream;
+    if (dtype == CPM_F32) {
+        if (wide) colsum_partial_kernel<float, true><<<grid, 256, 0, st>>>((const float *)x, rows, width, ld, partials);
+        else colsum_partial_kernel<float, false><<<grid, 256, 0, st>>>((const float *)x, rows, width, ld, partials);
+    } else {
+        if (wide) colsum_partial_kernel<__nv_bfloat16, true><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, rows, width, ld, partials);
+        else colsum_partial_kernel<__nv_bfloat16, false><<<grid, 256, 0, st>>>((const __nv_bfloat16 *)x, rows, width, ld, partials);
+    }
+    reduce_partials_kernel<false><<<(width + 31) / 32, 256, 0, st>>>(partials, R, width, width, out, nullptr, nullptr);
+    return check_launch("colsum");
 }
 
 int cpm_gelu_fwd(const void *x, const float *bias, void *y, int64_t rows, int d, float p_drop, uint64_t seed, uint64_t rng_offset,
@@ -612,7 +705,7 @@ int cpm_gelu_bwd(const void *x, const float *bias, const void *gy, void *gx, flo
         DISPATCH_DTYPE(dtype, gelu_kernel<T, true, true><<<GELU_BWD_BLOCKS, 256, 0, (cudaStream_t)stream>>>(
                                   (const T *)x, bias, (const T *)gy, (T *)gx, rows * (d / 16), d, dropout_threshold8(p_drop), dropout_scale8(p_drop),
                                   seed, rng_offset, partials, g_rng_base));
-        reduce_partials_kernel<<<(d + 63) / 64, 256, 0, (cudaStream_t)stream>>>(partials, cpm_gelu_bwd_partials_rows(d), d, d, dbias, nullptr, nullptr);
+        reduce_partials_kernel<true><<<(d + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, cpm_gelu_bwd_partials_rows(d), d, d, dbias, nullptr, nullptr);
         return check_launch("gelu_bwd");
     }
     DISPATCH_DTYPE(dtype, gelu_kernel<T, true><<<grid_for(rows * (d / 16), 256), 256, 0, (cudaStream_t)stream>>>(

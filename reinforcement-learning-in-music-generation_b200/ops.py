@@ -396,7 +396,7 @@ class _PackedLinear(torch.autograd.Function):
         gy2 = gy.reshape(-1, gy.shape[-1])
         gx = (gy2 @ wc).view(ctx.xshape) if ctx.needs_input_grad[0] else None
         gw = _mm_f32_out(gy2.t(), x2)
-        gb = gy2.sum(0, dtype=torch.float32) if ctx.has_bias else None
+        gb = colsum(gy2) if ctx.has_bias else None
         grads, r0 = [], 0
         for r in ctx.rows:
             grads.append(gw[r0:r0 + r])
@@ -407,6 +407,20 @@ class _PackedLinear(torch.autograd.Function):
                 grads.append(gb[r0:r0 + r])
                 r0 += r
         return (gx, None, None, None, *grads)
+
+
+def colsum(x):
+    """fp32 column sums of a 2-D bf16 / fp32 CUDA matrix (row stride free, unit column stride): cpm_colsum."""
+    _cuda(x)
+    rows, width = x.shape
+    if (x.stride(1) != 1 or width % (32 // x.element_size()) or x.stride(0) % 8 or x.dtype not in (torch.float32, torch.bfloat16)
+            or x.data_ptr() % 16):
+        return x.sum(0, dtype=torch.float32)            # odd layouts (e.g. the 344-wide logits are 8-aligned; anything else): library reduction
+    lib = _lib.load()
+    out = torch.empty(width, dtype=torch.float32, device=x.device)
+    partials = torch.empty(lib.cpm_colsum_partials_rows(width), width, dtype=torch.float32, device=x.device)
+    check(lib.cpm_colsum(_p(x), rows, width, x.stride(0), _p(out), _p(partials), _dt(x), _st()))
+    return out
 
 
 def packed_linear(x, wc, bc, rows, masters):

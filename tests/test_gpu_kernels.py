@@ -733,3 +733,17 @@ def test_reward_head(cuda, cpm, dtype, tol):
     _cmp(scores, ref_scores, tol, 0.0, "scores")
     _cmp(reward, ref_scores.mean(-1), tol, 0.0, "reward")
     assert reward.shape == (30,) and bool(((reward > 0) & (reward < 1)).all())
+
+
+@pytest.mark.parametrize("rows,width,dtype", [(65536, 2048, torch.bfloat16), (1000, 512, torch.bfloat16), (37, 344, torch.float32),
+                                              (1, 8, torch.float32), (5000, 1536, torch.bfloat16)])
+def test_colsum_bias_gradient(cuda, cpm, rows, width, dtype):
+    """cpm_colsum (bias gradients of the Linear layers) against an fp64 sum of the same (rounded) values, incl. a strided
+    view (column slice of a wider matrix) and row counts that do not divide the row slabs."""
+    gen = torch.Generator().manual_seed(rows + width)
+    x = torch.randn(rows, width + 16, generator=gen).to(cuda).to(dtype)
+    for view in (x[:, :width].contiguous(), x[:, 8:8 + width]):
+        got = cpm.ops.colsum(view)
+        ref = view.double().sum(0)
+        _cmp(got, ref, 1e-5 * math.sqrt(rows) + 1e-6, 1e-5, "colsum")
+        assert torch.equal(got, cpm.ops.colsum(view))            # deterministic

@@ -86,7 +86,10 @@ def main():
     hb = torch.zeros(dff, device=dev, requires_grad=True)
     fwd_bwd("gelu+bias+dropout", lambda: ops.gelu_dropout(h, 0.1, bias=hb), [h, hb], T * dff * 4, T * dff * 6, "bwd also returns the bias gradient")
     gyb = rnd(T, dff)
-    timeit("torch column sum (T x 2048 bf16 -> fp32)", lambda: gyb.sum(0, dtype=torch.float32), T * dff * 2, "what the fused bias gradient replaces")
+    timeit("torch column sum (T x 2048 bf16 -> fp32)", lambda: gyb.sum(0, dtype=torch.float32), T * dff * 2, "what cpm_colsum replaces")
+    timeit("colsum (T x 2048 bf16 -> fp32)", lambda: ops.colsum(gyb), T * dff * 2, "bias gradient of linear1")
+    gy5 = rnd(T, 1536)[:, :512]
+    timeit("colsum (T x 512 slice of 1536, bf16)", lambda: ops.colsum(gy5), T * 512 * 2, "strided view")
     # ---- heads: log-prob / entropy, masked CE
     seg = ops.seg_offsets(VOCAB)
     lg = rnd(T, 344).requires_grad_()

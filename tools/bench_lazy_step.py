@@ -22,3 +22,9 @@ print("eager", round(timeit(lambda: [ops.linattn_step(q, k, v, S[l], Z[l]) for l
 for p in range(8):
     step.fill_(p)
     print("lazy p =", p, round(timeit(lambda: [ops.linattn_step_lazy(q, k, v, S[l], Z[l], ring[l], step) for l in range(layers)]), 2), "us/launch")
+kvp = torch.zeros(layers, N, H, 128, device=dev)
+print("step_out (S read only)", round(timeit(lambda: [ops.linattn_step_out(q, k, v, S[l], Z[l], kvp[l]) for l in range(layers)]), 2), "us/launch")
+print("state_update (S read+write, no output)", round(timeit(lambda: [ops.linattn_state_update(S[l], kvp[l]) for l in range(layers)]), 2), "us/launch")
+Sc = S.clone()
+print("torch copy S->Sc (read+write 67 MB)", round(timeit(lambda: [Sc[l].copy_(S[l]) for l in range(layers)]), 2), "us/launch")
+print("torch sum(S) (read 33.5 MB)", round(timeit(lambda: [S[l].sum() for l in range(layers)]), 2), "us/launch")
