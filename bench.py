@@ -10,7 +10,7 @@ followed by a GAE plus clipped-loss update"; it fits one GPU, so it is the per-G
 run N such shards — weak scaling): autoregressive RECURRENT rollout of 256 songs x 1024 compound-word
 tokens with the reference's per-attribute temperature / nucleus sampling, critic values, GAE(lambda)
 with globally normalised advantages, then one clipped-PPO update of the 12-layer / d512 / 8-head actor
-and critic over those 256x1024 tokens (4 minibatches of 64x1024 with gradient accumulation, dropout
+and critic over those 256x1024 tokens (2 minibatches of 128x1024 with gradient accumulation, dropout
 0.1, grad-clip 3, Adam, bucketed NCCL gradient all-reduce).  Synthetic data: random-init
 weights, random initial tokens, and a synthetic reward (the reference's Longformer reward model is
 out of scope).  One "step" = one such iteration; value = tokens generated and trained
@@ -33,10 +33,14 @@ if ROOT not in sys.path:
 
 VOCAB = [56, 135, 18, 87, 18, 25]            # AIlabs-Pop1K7 dictionary without 'type' (IRL_dqn_train.py:403)
 SONGS_PER_GPU, ROLLOUT_LEN = 256, 1024
-MINIBATCH = int(os.environ.get("CPM_MINIBATCH", "64"))          # sequences per update minibatch (gradient accumulation over 256/MINIBATCH)
-# DRAM bytes of one linear-attention fwd+bwd launch group measured with ncu (cold L2), keyed by the update minibatch shape:
-# fwd 117.5+6.8 (streaming prefix) + 231.8+41.8 (per-chunk output) MB, bwd 195.1+17.4 (streaming suffix) + 334.1+153.9 (main) MB
-LINATTN_DRAM_BYTES_PER_PAIR = {(64, 1024): 1_098_400_000}
+# sequences per update minibatch (gradient accumulation over 256/MINIBATCH).  Measured on one B200: 64 -> 276 ms per update phase,
+# 128 -> 261 ms, 256 -> 254 ms but +36 ms of allocator churn outside it (63 GB of activations per model), so 128.
+MINIBATCH = int(os.environ.get("CPM_MINIBATCH", "128"))
+# DRAM bytes of one linear-attention fwd+bwd launch group measured with ncu (cold L2), keyed by the update minibatch shape
+# -> (bytes, the committed ncu log).  (64, 1024): fwd 117.5+6.8 (streaming prefix) + 231.8+41.8 (per-chunk output) MB, bwd 195.1+17.4
+# (streaming suffix) + 334.1+153.9 (main) MB.  (128, 1024): fwd 234.9+37.2 + 463.7+110.4 MB, bwd 390.1+48.8 + 668.0+354.6 MB.
+LINATTN_DRAM_BYTES_PER_PAIR = {(64, 1024): (1_098_400_000, "profiles/r01_ncu_linattn_cp_final_64x1024x8.csv"),
+                               (128, 1024): (2_307_700_000, "profiles/r01_ncu_linattn_cp_128x1024x8.csv")}
 METRIC = "CP tokens/s, PPO rollout+update"
 UNIT = "tokens/s"
 
@@ -297,7 +301,7 @@ def time_recurrent_step_kernel(dev, peak):
         cpmusic.ops.linattn_step(q, k, v, S[l], Z[l])
     torch.cuda.synchronize()
     graph = torch.cuda.CUDAGraph()                       # 12 launches captured: GPU time, not Python launch time
-    with torch.cuda.graph(graph):
+    with cpmusic.ops.graph_capture(graph):
         for l in range(layers):
             cpmusic.ops.linattn_step(q, k, v, S[l], Z[l])
     tot = 0.0
@@ -397,8 +401,8 @@ def run_gpu(args, rank, world):
     ms_pair = (tf / max(nf, 1)) + (tb / max(nb, 1))
     achieved = (bytes_fwd + bytes_bwd) / (ms_pair * 1e-3) / 1e9 if ms_pair > 0 else 0.0
     roofline = {"kernel": f"linattn fwd+bwd ({cpmusic.ops.linattn_last_impl()})", "bound": "hbm", "achieved": achieved, "peak": peak,
-                "unit": "GB/s", "frac": achieved / peak, "traffic": LINATTN_DRAM_BYTES_PER_PAIR.get((MINIBATCH, ROLLOUT_LEN)),
-                "traffic_source": "ncu dram__bytes_read+write per fwd+bwd launch group (profiles/r01_ncu_linattn_cp_final_64x1024x8.csv)",
+                "unit": "GB/s", "frac": achieved / peak, "traffic": LINATTN_DRAM_BYTES_PER_PAIR.get((MINIBATCH, ROLLOUT_LEN), (None, None))[0],
+                "traffic_source": "ncu dram__bytes_read+write per fwd+bwd launch group (%s)" % LINATTN_DRAM_BYTES_PER_PAIR.get((MINIBATCH, ROLLOUT_LEN), (None, "not captured for this shape"))[1],
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_launch_pair": bytes_fwd + bytes_bwd, "ms_fwd": tf / max(nf, 1), "ms_bwd": tb / max(nb, 1),
                 "launch_pairs_timed": n_pairs, "share_of_step": (tf + tb) / ms,

@@ -50,6 +50,22 @@ template <> struct Vec8<__nv_bfloat16> {
         *reinterpret_cast<uint4 *>(p) = raw;
     }
 };
+// the raw bits of 8 activations: loads that stay in flight (no conversion, hence no use of the registers) until unpack()
+template <typename T> struct Raw8;
+template <> struct Raw8<float> {
+    float4 a, b;
+    __device__ __forceinline__ void load(const float *p) { a = *reinterpret_cast<const float4 *>(p); b = *reinterpret_cast<const float4 *>(p + 4); }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const { v[0] = a.x; v[1] = a.y; v[2] = a.z; v[3] = a.w; v[4] = b.x; v[5] = b.y; v[6] = b.z; v[7] = b.w; }
+};
+template <> struct Raw8<__nv_bfloat16> {
+    uint4 r;
+    __device__ __forceinline__ void load(const __nv_bfloat16 *p) { r = *reinterpret_cast<const uint4 *>(p); }
+    __device__ __forceinline__ void unpack(float (&v)[8]) const {
+        const uint32_t w[4] = {r.x, r.y, r.z, r.w};
+#pragma unroll
+        for (int i = 0; i < 4; ++i) { v[2 * i] = __uint_as_float(w[i] << 16); v[2 * i + 1] = __uint_as_float(w[i] & 0xFFFF0000u); }
+    }
+};
 __device__ __forceinline__ float to_f(float x) { return x; }
 __device__ __forceinline__ float to_f(__nv_bfloat16 x) { return __bfloat162float(x); }
 template <typename T> __device__ __forceinline__ T from_f(float x);

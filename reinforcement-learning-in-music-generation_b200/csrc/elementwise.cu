@@ -206,47 +206,76 @@ __global__ void __launch_bounds__(128) ln_residual_fwd_kernel(const T *__restric
     }
 }
 
-constexpr int LN_BWD_BLOCKS = 296;   // 2 CTAs per SM on 148 SMs
+constexpr int LN_BWD_BLOCKS = 296;   // 2 CTAs per SM on 148 SMs (126 registers at d = 512; 3 per SM spills and is slower)
+inline int ln_bwd_blocks(int) { return LN_BWD_BLOCKS; }
 constexpr int GELU_BWD_BLOCKS = 1184; // 8 CTAs per SM: the fused-bias-gradient variant keeps its partial matrix small
 constexpr int LN_BWD_THREADS = 256;
 
 template <typename T, int MAXV, bool WANT_DRES>
-__global__ void __launch_bounds__(LN_BWD_THREADS) ln_residual_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ s, const float *__restrict__ mean,
+__global__ void __launch_bounds__(LN_BWD_THREADS, MAXV <= 2 ? 2 : 1) ln_residual_bwd_kernel(const T *__restrict__ gy, const T *__restrict__ s, const float *__restrict__ mean,
                                                                          const float *__restrict__ rstd, const float *__restrict__ gamma, T *__restrict__ gs,
                                                                          T *__restrict__ gres, float *__restrict__ partials, int64_t rows, int d, uint32_t thr,
                                                                          float scale, uint64_t seed, uint64_t rng_offset_h, const unsigned long long *rng_base) {
     const uint64_t rng_offset = rng_off(rng_offset_h, rng_base);
-    extern __shared__ float red[];   // [3][d] block partial sums: dgamma | dbeta | column sums of the residual-branch gradient
+    extern __shared__ __align__(16) float red[];   // [3][d] block partial sums: dgamma | dbeta | column sums of the residual-branch gradient; [d] gamma
+    float *sgam = red + 3 * d;
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int G = d >> 3;
     for (int i = threadIdx.x; i < 3 * d; i += blockDim.x) red[i] = 0.f;
+    for (int i = threadIdx.x; i < d; i += blockDim.x) sgam[i] = gamma[i];
     __syncthreads();
-    float dg[MAXV][8], db[MAXV][8], dr[MAXV][8], gm[MAXV][8];
+    // d <= 512: the NEXT row's gy / s (raw 16-byte words), mean and rstd are fetched before the current row's math, so a
+    // warp always has one row in flight (16 warps per SM at 126 registers: one row per warp is not enough to cover HBM latency)
+    constexpr bool PIPE = MAXV <= 2;
+    float dg[MAXV][8], db[MAXV][8], dr[MAXV][8];
 #pragma unroll
     for (int i = 0; i < MAXV; ++i) {
-        const int g = lane + 32 * i;
 #pragma unroll
-        for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; dr[i][j] = 0.f; gm[i][j] = (g < G) ? gamma[g * 8 + j] : 0.f; }
+        for (int j = 0; j < 8; ++j) { dg[i][j] = 0.f; db[i][j] = 0.f; dr[i][j] = 0.f; }
     }
     const int64_t warp_global = (int64_t)blockIdx.x * (LN_BWD_THREADS / 32) + warp;
     const int64_t nwarps = (int64_t)gridDim.x * (LN_BWD_THREADS / 32);
+    Raw8<T> ng[PIPE ? MAXV : 1], nx[PIPE ? MAXV : 1];
+    float nmu = 0.f, nrs = 0.f;
+    auto fetch = [&](int64_t r) {
+        if (r < rows) {
+            nmu = mean[r];
+            nrs = rstd[r];
+#pragma unroll
+            for (int i = 0; i < (PIPE ? MAXV : 1); ++i) {
+                const int g = lane + 32 * i;
+                if (g < G) { ng[i].load(gy + r * d + g * 8); nx[i].load(s + r * d + g * 8); }
+            }
+        }
+    };
+    if (PIPE) fetch(warp_global);
     for (int64_t r = warp_global; r < rows; r += nwarps) {
-        const float mu = mean[r], rs = rstd[r];
+        const float mu = PIPE ? nmu : mean[r], rs = PIPE ? nrs : rstd[r];
         Vec8<T> g_[MAXV], x_[MAXV];
+        if (PIPE) {
+#pragma unroll
+            for (int i = 0; i < MAXV; ++i)
+                if (lane + 32 * i < G) { ng[i < (PIPE ? MAXV : 1) ? i : 0].unpack(g_[i].v); nx[i < (PIPE ? MAXV : 1) ? i : 0].unpack(x_[i].v); }
+            fetch(r + nwarps);
+        }
         float c1 = 0.f, c2 = 0.f;
 #pragma unroll
         for (int i = 0; i < MAXV; ++i) {
             const int g = lane + 32 * i;
             if (g < G) {
-                g_[i].load(gy + r * d + g * 8);
-                x_[i].load(s + r * d + g * 8);
+                if (!PIPE) {
+                    g_[i].load(gy + r * d + g * 8);
+                    x_[i].load(s + r * d + g * 8);
+                }
+                const float4 gm0 = *reinterpret_cast<const float4 *>(sgam + g * 8), gm1 = *reinterpret_cast<const float4 *>(sgam + g * 8 + 4);
+                const float gm[8] = {gm0.x, gm0.y, gm0.z, gm0.w, gm1.x, gm1.y, gm1.z, gm1.w};
 #pragma unroll
                 for (int j = 0; j < 8; ++j) {
                     const float xh = (x_[i].v[j] - mu) * rs;
                     const float gg = g_[i].v[j];
                     dg[i][j] += gg * xh;
                     db[i][j] += gg;
-                    const float w = gg * gm[i][j];
+                    const float w = gg * gm[j];
                     c1 += w * xh;
                     c2 += w;
                     x_[i].v[j] = xh;
@@ -641,18 +670,18 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
     const uint32_t thr = dropout_threshold(p_drop);
     CPM_REQUIRE(!thr || gres, CPM_ERR_NULL, "ln_residual_bwd: gres required when p_drop > 0");
     if (rows == 0) return CPM_OK;
-    const size_t smem = 3 * (size_t)d * sizeof(float);
+    const size_t smem = 4 * (size_t)d * sizeof(float);
     if (dres_bias) {
-        DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV, true><<<LN_BWD_BLOCKS, LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
+        DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV, true><<<ln_bwd_blocks(d), LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
                                                    (const T *)gy, (const T *)s, mean, rstd, gamma, (T *)gs, (T *)gres, partials, rows, d, thr,
                                                    dropout_scale(p_drop), seed, rng_offset, g_rng_base)));
     } else {
-        DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV, false><<<LN_BWD_BLOCKS, LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
+        DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_bwd_kernel<T, MAXV, false><<<ln_bwd_blocks(d), LN_BWD_THREADS, smem, (cudaStream_t)stream>>>(
                                                    (const T *)gy, (const T *)s, mean, rstd, gamma, (T *)gs, (T *)gres, partials, rows, d, thr,
                                                    dropout_scale(p_drop), seed, rng_offset, g_rng_base)));
     }
     const int width = (dres_bias ? 3 : 2) * d;
-    reduce_partials_kernel<true><<<(width + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, LN_BWD_BLOCKS, 3 * d, d, dgamma, dbeta, dres_bias);
+    reduce_partials_kernel<true><<<(width + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, ln_bwd_blocks(d), 3 * d, d, dgamma, dbeta, dres_bias);
     return check_launch("ln_residual_bwd");
 }
 

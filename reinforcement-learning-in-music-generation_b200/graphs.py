@@ -49,7 +49,7 @@ class GraphedTrainStep:
         model.invalidate_packs()                      # the refresh of every weight packing becomes part of the graph
         self.graph = torch.cuda.CUDAGraph()
         start = ops._Rng.offset
-        with torch.cuda.graph(self.graph):
+        with ops.graph_capture(self.graph):
             self._step()
             ops.rng_advance(ops._Rng.offset - start)  # next replay: same frozen offsets + an advanced device base
         self.rng_counters_per_step = ops._Rng.offset - start

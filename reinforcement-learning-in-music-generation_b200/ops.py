@@ -11,6 +11,9 @@ from __future__ import annotations
 import math
 from typing import List, Optional, Sequence, Tuple
 
+import contextlib
+import gc
+
 import torch
 
 from . import _lib
@@ -130,6 +133,23 @@ class _Null:
 
 
 _NULL = _Null()
+
+
+# --------------------------------------------------------------------------- CUDA graph capture
+@contextlib.contextmanager
+def graph_capture(graph, **kw):
+    """``torch.cuda.graph`` with Python's cyclic garbage collector held off: a collection that runs in the middle of a capture
+    can destroy an older CUDAGraph / free device memory (objects kept alive only by reference cycles, e.g. a discarded
+    rollout engine), and such calls invalidate the capture in progress (cudaErrorStreamCaptureInvalidated)."""
+    gc.collect()
+    was_enabled = gc.isenabled()
+    gc.disable()
+    try:
+        with torch.cuda.graph(graph, **kw):
+            yield
+    finally:
+        if was_enabled:
+            gc.enable()
 
 
 # --------------------------------------------------------------------------- linear attention

@@ -432,7 +432,7 @@ class RolloutEngine:
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         before = _lib.kernel_launches()
-        with torch.no_grad(), torch.cuda.graph(g):
+        with torch.no_grad(), ops.graph_capture(g):
             self._step()
         self.launches_per_step = _lib.kernel_launches() - before      # cpmusic kernels captured per token step
         self.graph = g
@@ -515,7 +515,7 @@ class GroupedRolloutEngine:
         torch.cuda.synchronize()
         g = torch.cuda.CUDAGraph()
         before = _lib.kernel_launches()
-        with torch.no_grad(), torch.cuda.graph(g):
+        with torch.no_grad(), ops.graph_capture(g):
             self._fork_join_steps(self.steps_per_graph)
         self.launches_per_step = (_lib.kernel_launches() - before) // self.steps_per_graph
         self.graph = g

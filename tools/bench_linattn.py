@@ -7,7 +7,7 @@ sys.path.insert(0, ROOT)
 import torch
 import cpmusic
 
-SHAPES = {"cfg2 32x512x8": (32, 512, 8), "ppo-update 16x1024x8": (16, 1024, 8), "bench minibatch 64x1024x8": (64, 1024, 8),
+SHAPES = {"cfg2 32x512x8": (32, 512, 8), "ppo-update 16x1024x8": (16, 1024, 8), "bench minibatch 64x1024x8": (64, 1024, 8), "bench minibatch 128x1024x8": (128, 1024, 8),
           "cfg5 1x8192x16": (1, 8192, 16), "cfg1 4x512x8": (4, 512, 8)}
 
 
