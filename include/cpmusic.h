@@ -104,6 +104,11 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
  * matching 16 KB tile of S_next - the state the NEXT step kernel of the token step will stream (the following layer's;
  * the first layer's for the last one).  when = 1: after this tile's write-back, 2: before its loads.  Results are
  * bit-identical to cpm_linattn_step; E = M = 64 only. */
+/* cpm_linattn_step (E = M = 64) as a persistent kernel: ctas_per_sm (1..3) CTAs per SM walk the (sequence, head) tiles with
+ * the next four 16 KB state tiles always in flight through the bulk-copy engine (cp.async.bulk -> shared memory, mbarrier
+ * completion); same arithmetic and summation order, bit-identical results. */
+int cpm_linattn_step_tma(const void *q, const void *k, const void *v, float *S, float *Z, void *out, int N, int H, int64_t ld_qkv,
+                         int64_t ld_o, int dtype, float eps, int ctas_per_sm, void *stream);
 int cpm_l2_prefetch(const void *p, int64_t bytes, void *stream);   /* stand-alone: bulk L2 prefetch of [p, p+bytes), 16 KB pieces */
 int cpm_linattn_step_prefetch(const void *q, const void *k, const void *v, float *S, float *Z, void *out, const float *S_next,
                               int when, int N, int H, int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream);

@@ -46,6 +46,7 @@ SIGNATURES = {
                                  c_int, c_float, _P]),
     "cpm_colsum_partials_rows": (c_int, [c_int]),
     "cpm_colsum": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, c_int, _P]),
+    "cpm_linattn_step_tma": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, c_int, _P]),
     "cpm_l2_prefetch": (c_int, [_P, c_int64, _P]),
     "cpm_linattn_step_prefetch": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, c_float, _P]),
     "cpm_linattn_step_fold": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P]),

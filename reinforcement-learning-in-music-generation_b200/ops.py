@@ -12,6 +12,7 @@ import math
 from typing import List, Optional, Sequence, Tuple
 
 import contextlib
+import os
 import gc
 
 import torch
@@ -304,7 +305,11 @@ def linattn_last_impl() -> str:
     return _lib.load().cpm_linattn_last_impl().decode()
 
 
-def linattn_step(q, k, v, S, Z, eps=EPS_ATTN, prefetch=None, prefetch_when=1):
+# persistent TMA-staged step kernel: CTAs per SM (0 = the one-CTA-per-tile kernel); A/B switch, see profiles
+STEP_TMA_CTAS = int(os.environ.get("CPM_STEP_TMA", "0"))
+
+
+def linattn_step(q, k, v, S, Z, eps=EPS_ATTN, prefetch=None, prefetch_when=1, tma_ctas=None):
     """Recurrent step. q,k,v: (N,H,64) views sharing a row stride; S (N,H,64,64), Z (N,H,64) fp32
     are updated in place; returns (N,H,64).  prefetch: another (N,H,64,64) fp32 state (the next layer's) to pull into
     L2 from inside the kernel (cpm_linattn_step_prefetch; same results)."""
@@ -323,6 +328,10 @@ def linattn_step(q, k, v, S, Z, eps=EPS_ATTN, prefetch=None, prefetch_when=1):
             raise ValueError("prefetch must be a contiguous float32 state of the same shape (E = 64)")
         check(_lib.load().cpm_linattn_step_prefetch(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), _p(prefetch), int(prefetch_when),
                                                     N, H, ld, H * E, _dt(q), eps, _st()))
+        return out
+    tma_ctas = STEP_TMA_CTAS if tma_ctas is None else tma_ctas
+    if tma_ctas and E == 64:
+        check(_lib.load().cpm_linattn_step_tma(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), N, H, ld, H * E, _dt(q), eps, int(tma_ctas), _st()))
         return out
     check(_lib.load().cpm_linattn_step(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), N, H, E, E, ld, H * E,
                                        _dt(q), eps, _st()))

@@ -747,3 +747,19 @@ def test_colsum_bias_gradient(cuda, cpm, rows, width, dtype):
         ref = view.double().sum(0)
         _cmp(got, ref, 1e-5 * math.sqrt(rows) + 1e-6, 1e-5, "colsum")
         assert torch.equal(got, cpm.ops.colsum(view))            # deterministic
+
+
+@pytest.mark.parametrize("N,H,ctas", [(5, 3, 2), (256, 8, 3), (300, 8, 2), (37, 1, 1)])
+def test_linattn_step_persistent_tma_is_bit_identical(cuda, cpm, N, H, ctas):
+    """The persistent, bulk-copy-staged step kernel against the one-CTA-per-tile kernel over 3 consecutive tokens: outputs, S and
+    Z bit-identical (fewer tiles than CTAs, the rollout shape, a tile count that does not divide the grid), bf16 and fp32 inputs."""
+    gen = torch.Generator().manual_seed(N * H)
+    for dtype in (torch.bfloat16, torch.float32):
+        qkv = torch.randn(3, N, 3 * H * 64, generator=gen).to(cuda).to(dtype)
+        Sa, Za = torch.randn(N, H, 64, 64, generator=gen).to(cuda), torch.rand(N, H, 64, generator=gen).to(cuda)
+        Sb, Zb = Sa.clone(), Za.clone()
+        for t in range(3):
+            q, k, v = (qkv[t][:, i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
+            oa = cpm.ops.linattn_step(q, k, v, Sa, Za, tma_ctas=0)
+            ob = cpm.ops.linattn_step(q, k, v, Sb, Zb, tma_ctas=ctas)
+            assert torch.equal(oa, ob) and torch.equal(Sa, Sb) and torch.equal(Za, Zb), (dtype, t)

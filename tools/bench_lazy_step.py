@@ -28,3 +28,5 @@ print("state_update (S read+write, no output)", round(timeit(lambda: [ops.linatt
 Sc = S.clone()
 print("torch copy S->Sc (read+write 67 MB)", round(timeit(lambda: [Sc[l].copy_(S[l]) for l in range(layers)]), 2), "us/launch")
 print("torch sum(S) (read 33.5 MB)", round(timeit(lambda: [S[l].sum() for l in range(layers)]), 2), "us/launch")
+for c in (1, 2, 3):
+    print("persistent TMA step,", c, "CTAs/SM", round(timeit(lambda: [ops.linattn_step(q, k, v, S[l], Z[l], tma_ctas=c) for l in range(layers)]), 2), "us/launch")
