@@ -36,6 +36,10 @@ SONGS_PER_GPU, ROLLOUT_LEN = 256, 1024
 # sequences per update minibatch (gradient accumulation over 256/MINIBATCH).  Measured on one B200: 64 -> 276 ms per update phase,
 # 128 -> 261 ms, 256 -> 254 ms but +36 ms of allocator churn outside it (63 GB of activations per model), so 128.
 MINIBATCH = int(os.environ.get("CPM_MINIBATCH", "128"))
+# critic update of iteration i under the rollout of i+1 (second stream).  Measured on B200: 333.6 k tokens/s vs 344.9 k sequential
+# (346.6 k with the rollout graph captured at high stream priority): the bulk kernels delay the rollout's dependent small kernels
+# by about as much as they save, and the in-situ attention timings suffer - off by default.
+OVERLAP_CRITIC = os.environ.get("CPM_OVERLAP_CRITIC", "0") == "1"
 # DRAM bytes of one linear-attention fwd+bwd launch group measured with ncu (cold L2), keyed by the update minibatch shape
 # -> (bytes, the committed ncu log).  (64, 1024): fwd 117.5+6.8 (streaming prefix) + 231.8+41.8 (per-chunk output) MB, bwd 195.1+17.4
 # (streaming suffix) + 334.1+153.9 (main) MB.  (128, 1024): fwd 234.9+37.2 + 463.7+110.4 MB, bwd 390.1+48.8 + 668.0+354.6 MB.
@@ -173,7 +177,9 @@ def workload_config(world):
                         f"{SONGS_PER_GPU // MINIBATCH} minibatches of {MINIBATCH}x{ROLLOUT_LEN}, dropout 0.1, grad-clip 3, Adam)",
             "model": "CP linear transformer 12L d512 h8 ff2048 (38.98M params) x2 (actor, critic)",
             "tokens_per_step": tokens_step, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (working set > 1 GB/step)",
-            "reward": "synthetic (Longformer reward model out of scope)"}
+            "reward": "synthetic (Longformer reward model out of scope)",
+            "schedule": ("critic update of iteration i runs on a second stream under the rollout of iteration i+1 (the rollout reads only the "
+                         "actor); the last one is drained inside the timed region" if OVERLAP_CRITIC else "sequential")}
 
 
 def run_reference(args, rank):
@@ -231,15 +237,56 @@ class PPOIteration:
         self.init_host = torch.stack([torch.randint(0, n, (SONGS_PER_GPU,), generator=g) for n in VOCAB], -1).pin_memory()
         self.init_dev = self.init_host.to(dev)
         self.phase_ms = {"rollout": 0.0, "update": 0.0}
+        self.cstream = torch.cuda.Stream(device=dev)
+        self.pending, self._inflight = None, None
+        self.vstat = torch.zeros((), device=dev)
+
+    # The critic's update needs the iteration's returns and trajectories but nothing of it feeds the NEXT rollout (which only
+    # reads the actor): with OVERLAP_CRITIC it is queued on a second stream and runs underneath the next iteration's rollout,
+    # whose dependent chain of small kernels leaves most of the GPU idle.  Same arithmetic in the same order for both
+    # networks (the critic update still completes before the next value pass); flush() drains the last one.
+    def _critic_update(self, x, ret, scale, n_mb):
+        torch = self.torch
+        self.critic.train()
+        self.red_c.zero_grad()
+        vstat = torch.zeros((), device=self.dev)
+        for i in range(0, x.shape[0], MINIBATCH):
+            sl = slice(i, i + MINIBATCH)
+            v = self.critic.value_per_position(x[sl])
+            vloss = torch.nn.functional.mse_loss(v, ret[sl])
+            (vloss * scale).backward()
+            vstat += vloss.detach() * (1.0 / n_mb)
+        self.red_c.finish()
+        self.opt_c.step()
+        return vstat
+
+    def _launch_pending(self):
+        if self.pending is None:
+            return
+        torch = self.torch
+        x, ret, scale, n_mb, ready = self.pending
+        self.pending = None
+        self.cstream.wait_event(ready)
+        with torch.cuda.stream(self.cstream):
+            self.vstat = self._critic_update(x, ret, scale, n_mb)
+        self._inflight = (x, ret)                      # keep the inputs alive until the main stream has joined
+
+    def flush(self):
+        """Runs a deferred critic update (if any) and joins it: call before reading the critic or stopping the clock."""
+        self._launch_pending()
+        self.torch.cuda.current_stream().wait_stream(self.cstream)
+        self._inflight = None
 
     def step(self, init_tokens, time_phases=False):
         torch, cpm = self.torch, self.cpm
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if time_phases else None
         if ev:
+            self.flush()
             ev[0].record()
         torch.cuda.nvtx.range_push("rollout")
         roll = self.engine.generate(init_tokens)                       # tokens (B,T+1,A), logp (B,T,A)
         torch.cuda.nvtx.range_pop()
+        self._launch_pending()                                         # last iteration's critic update, under this rollout
         if ev:
             ev[1].record()
         torch.cuda.nvtx.range_push("update")
@@ -249,16 +296,20 @@ class PPOIteration:
         reward = ((act.sum(-1) % 7).float() / 7.0)                     # synthetic per-token reward
         dones = torch.zeros(B, T, device=self.dev)
         dones[:, -1] = 1.0
+        torch.cuda.current_stream().wait_stream(self.cstream)          # the value pass reads the updated critic
+        self._inflight = None
         self.critic.eval()
         with torch.no_grad():
             values = torch.cat([self.critic.value_per_position(x[i:i + MINIBATCH]) for i in range(0, B, MINIBATCH)], 0)
         adv, ret = cpm.rl.gae(reward, values, dones, torch.zeros(B, device=self.dev), 0.99, 0.95, True, self.group)
         self.actor.train()
-        self.critic.train()
         self.red_a.zero_grad()
-        self.red_c.zero_grad()
         n_mb = B // MINIBATCH
         scale = 1.0 / (n_mb * self.world)                               # mean over the GLOBAL batch; grads are SUM-reduced
+        if OVERLAP_CRITIC:
+            ready = torch.cuda.Event()
+            ready.record()
+            self.pending = (x, ret, scale, n_mb, ready)
         stats = torch.zeros(4, device=self.dev)
         for i in range(0, B, MINIBATCH):
             sl = slice(i, i + MINIBATCH)
@@ -267,15 +318,13 @@ class PPOIteration:
             out = cpm.ops.ppo_loss_standard(new_logp, old_logp[sl], adv[sl, :, None].expand(-1, -1, A), None, None, ent,
                                             clip=0.2, vf_coef=0.0, ent_coef=0.01)
             (out[0] * scale).backward()
-            v = self.critic.value_per_position(x[sl])
-            vloss = torch.nn.functional.mse_loss(v, ret[sl])
-            (vloss * scale).backward()
-            stats += torch.stack([out[0].detach(), out[1].detach(), vloss.detach(), out[3].detach()]) * (1.0 / n_mb)
+            stats += torch.stack([out[0].detach(), out[1].detach(), torch.zeros((), device=self.dev), out[3].detach()]) * (1.0 / n_mb)
         self.red_a.finish()
-        self.red_c.finish()
         torch.nn.utils.clip_grad_norm_(self.actor.parameters(), 3.0, foreach=True)      # reference: clip 3 (agent_pretrain.py:563)
         self.opt_a.step()
-        self.opt_c.step()
+        if not OVERLAP_CRITIC:
+            self.vstat = self._critic_update(x, ret, scale, n_mb)
+        stats[2] = self.vstat                        # value loss of the most recent COMPLETED critic update (one iteration late when overlapped)
         torch.cuda.nvtx.range_pop()
         if ev:
             ev[2].record()
@@ -339,10 +388,12 @@ def run_gpu(args, rank, world):
 
     for _ in range(max(args.warmup, 3)):
         it.step(it.init_dev)
+    it.flush()
     barrier()
     if args.profile_step:                              # ncu --profile-from-start off: one whole iteration, every thread's launches
         torch.cuda.profiler.start()
         it.step(it.init_dev)
+        it.flush()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -357,6 +408,7 @@ def run_gpu(args, rank, world):
     e0.record()
     for _ in range(args.steps):
         it.step(it.init_dev)
+    it.flush()                                          # the last critic update belongs to the timed region
     e1.record()
     torch.cuda.synchronize()
     ms = e0.elapsed_time(e1)
@@ -376,12 +428,20 @@ def run_gpu(args, rank, world):
         host_tok.copy_(tokens, non_blocking=True)
         host_stats.copy_(stats, non_blocking=True)
         torch.cuda.synchronize()                    # the caller reads the result every step
+    it.flush()
     f1.record()
     torch.cuda.synchronize()
     ms_e2e = f0.elapsed_time(f1)
     # phase split (extra untimed step)
     it.phase_ms = {"rollout": 0.0, "update": 0.0}
     it.step(it.init_dev, time_phases=True)
+    if OVERLAP_CRITIC:                                   # the deferred critic update of that step, timed alone
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        c0.record()
+        it.flush()
+        c1.record()
+        torch.cuda.synchronize()
+        it.phase_ms["critic_update_alone"] = c0.elapsed_time(c1)
     if world > 1:
         import torch.distributed as dist
         t = torch.tensor([ms, ms_e2e], device=dev)

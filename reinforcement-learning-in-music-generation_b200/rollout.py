@@ -432,7 +432,9 @@ class RolloutEngine:
         torch.cuda.current_stream().wait_stream(side)
         g = torch.cuda.CUDAGraph()
         before = _lib.kernel_launches()
-        with torch.no_grad(), ops.graph_capture(g):
+        # captured on a high-priority stream: the kernel nodes inherit it, so the token step's small dependent kernels are
+        # scheduled ahead of bulk work queued on other (default-priority) streams
+        with torch.no_grad(), ops.graph_capture(g, stream=torch.cuda.Stream(priority=-1)):
             self._step()
         self.launches_per_step = _lib.kernel_launches() - before      # cpmusic kernels captured per token step
         self.graph = g
