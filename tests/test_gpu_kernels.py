@@ -763,3 +763,29 @@ def test_linattn_step_persistent_tma_is_bit_identical(cuda, cpm, N, H, ctas):
             oa = cpm.ops.linattn_step(q, k, v, Sa, Za, tma_ctas=0)
             ob = cpm.ops.linattn_step(q, k, v, Sb, Zb, tma_ctas=ctas)
             assert torch.equal(oa, ob) and torch.equal(Sa, Sb) and torch.equal(Za, Zb), (dtype, t)
+
+
+@pytest.mark.parametrize("shape", [(3, 50, 4), (2, 130, 2), (1, 1, 1), (1024, 50, 8)])
+def test_linattn_bf16_ragged_lengths_run_padded_on_tensor_cores(cuda, cpm, shape):
+    """bf16 sequences that are not a multiple of 128 tokens (the 50-token DQN windows) are zero-padded at the end and take the
+    tcgen05 kernels: forward and gradients against the fp64 oracle at the TRUE length (small shapes) and against the
+    CUDA-core kernels at the replay-batch size; the padding must not leak into real positions."""
+    N, L, H = shape
+    gen = torch.Generator().manual_seed(L * 3 + H)
+    qkv = torch.randn(N, L, 3 * H * 64, generator=gen).to(cuda).bfloat16().requires_grad_()
+    go = torch.randn(N, L, H * 64, generator=gen).to(cuda).bfloat16()
+    out = cpm.ops.causal_linear_attention_fused(qkv, H)
+    assert cpm.ops.linattn_last_impl() == "tcgen05-cp" and out.shape == (N, L, H * 64)
+    out.backward(go)
+    if N * L <= 4096:
+        q, k, v = (qkv.detach()[..., i * H * 64:(i + 1) * H * 64].reshape(N, L, H, 64).float() for i in range(3))
+        ro, rq, rk, rv = _oracle_attn(q, k, v, go.view(N, L, H, 64).float())
+        _cmp(out.view(N, L, H, 64), ro, 2e-2, 1e-2, "out")
+        _cmp(qkv.grad, torch.cat([t.reshape(N, L, H * 64) for t in (rq, rk, rv)], -1), 4e-2, 3e-2, "gqkv")
+    else:
+        ref_in = qkv.detach().clone().requires_grad_()
+        ref = cpm.ops.causal_linear_attention_fused(ref_in, H, impl=1)
+        assert cpm.ops.linattn_last_impl() == "simt"
+        ref.backward(go)
+        _cmp(out, ref.float(), 3e-2, 2e-2, "out vs simt")
+        _cmp(qkv.grad, ref_in.grad.float(), 4e-2, 3e-2, "gqkv vs simt")
