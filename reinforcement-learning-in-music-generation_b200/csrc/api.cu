@@ -94,19 +94,40 @@ __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__
     }
     { F8 lo, hi; lo.a = s[0]; lo.b = s[1]; hi.a = s[2]; hi.b = s[3]; st_stream(srow, lo); st_stream(srow + 8, hi); }
     if (PF == 1 && tid == 0) prefetch_l2_bulk(S_next + (int64_t)nh * 4096, 16384u);
-    // reduce over the 8 rows held by this warp (lanes with equal lane%4)
+    // reduce over the 8 rows held by this warp (lanes with equal lane%4) by recursive halving: at every level a lane keeps half
+    // of its columns and hands the other half to its partner, 8 + 4 + 2 shuffles instead of 16 x 3.  The additions pair the
+    // same operands in the same tree as the plain butterfly (x + y is commutative bit for bit), so every sum is unchanged.
+    float a8[8], a4[4], a2[2];
+    {
+        const bool up = lane & 4;
 #pragma unroll
-    for (int i = 0; i < 16; ++i) {
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 4);
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 8);
-        acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], 16);
+        for (int j = 0; j < 8; ++j) {
+            const float send = up ? acc[j] : acc[8 + j], keep = up ? acc[8 + j] : acc[j];
+            a8[j] = keep + __shfl_xor_sync(0xffffffffu, send, 4);
+        }
+    }
+    {
+        const bool up = lane & 8;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const float send = up ? a8[j] : a8[4 + j], keep = up ? a8[4 + j] : a8[j];
+            a4[j] = keep + __shfl_xor_sync(0xffffffffu, send, 8);
+        }
+    }
+    {
+        const bool up = lane & 16;
+#pragma unroll
+        for (int j = 0; j < 2; ++j) {
+            const float send = up ? a4[j] : a4[2 + j], keep = up ? a4[2 + j] : a4[j];
+            a2[j] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+        }
     }
     dpart += __shfl_xor_sync(0xffffffffu, dpart, 4);
     dpart += __shfl_xor_sync(0xffffffffu, dpart, 8);
     dpart += __shfl_xor_sync(0xffffffffu, dpart, 16);
-    if (lane < 4) {
-#pragma unroll
-        for (int i = 0; i < 16; ++i) part[warp][lane * 16 + i] = acc[i];
+    {   // this lane now owns columns m0 + 8*[lane bit 2] + 4*[bit 3] + 2*[bit 4] + {0, 1}
+        const int col = m0 + ((lane & 4) ? 8 : 0) + ((lane & 8) ? 4 : 0) + ((lane & 16) ? 2 : 0);
+        *reinterpret_cast<float2 *>(&part[warp][col]) = make_float2(a2[0], a2[1]);
         if (lane == 0) part[warp][64] = dpart;
     }
     __syncthreads();
