@@ -274,3 +274,36 @@ def test_pack_cache_notices_fused_optimizer_steps(cpm):
     cache.invalidate()
     wc2 = cache.get("k", [lin], torch.float32)[0]
     assert wc2.data_ptr() == ptr and torch.equal(wc2, lin.weight.detach())
+
+
+def test_seven_attribute_surface_matches_oracle_keys(cpm):
+    """The seven-attribute layout (`type` at column 3): same parameter names and shapes as the oracle restatement, embedding
+    widths sum to 1248, and the oracle's train_step returns seven finite losses on the CPU."""
+    from oracle import model_oracle as mo
+    vocab7 = [56, 135, 18, 4, 87, 18, 25]
+    cfg = dict(d_model=64, n_layer=1, n_head=1, d_inner=64, dropout=0.0)
+    o = mo.OracleCPModel(vocab7, **cfg)
+    m = cpm.TransformerModel(vocab7, **cfg)
+    assert m.attrs == mo.ATTRS7 and sum(m.emb_sizes) == 1248 == m.in_linear.in_features
+    so, sm = o.state_dict(), m.state_dict()
+    assert set(so) == set(sm) and all(so[k].shape == sm[k].shape for k in so)
+    g = torch.Generator().manual_seed(0)
+    x = torch.stack([torch.randint(0, n, (2, 20), generator=g) for n in vocab7], -1)
+    losses = o.train_step(x, x.roll(-1, 1), torch.ones(2, 20))
+    assert len(losses) == 7 and all(torch.isfinite(l) for l in losses)
+    with pytest.raises(ValueError, match="6 .*or 7"):
+        cpm.TransformerModel([5, 5, 5])
+
+
+def test_head_width_validation(cpm):
+    """Head widths: 64 (the reference) and 128 build; anything else is rejected at construction with a clear message."""
+    from cpmusic.encoder import TransformerEncoderBuilder
+    for ok in (64, 128):
+        enc = TransformerEncoderBuilder.from_kwargs(n_layers=1, n_heads=2, query_dimensions=ok, value_dimensions=ok,
+                                                    feed_forward_dimensions=64, activation="gelu", dropout=0.0,
+                                                    attention_type="causal-linear").get()
+        assert enc.d_head == ok and enc.layers[0].attention.query_projection.out_features == 2 * ok
+        assert [tuple(t.shape) for t in enc.new_state(3, "cpu")[0]] == [(3, 2, ok, ok), (3, 2, ok)]
+    with pytest.raises(ValueError, match="64 .*or 128"):
+        TransformerEncoderBuilder.from_kwargs(n_layers=1, n_heads=2, query_dimensions=32, value_dimensions=32,
+                                              feed_forward_dimensions=64, activation="gelu", dropout=0.0, attention_type="causal-linear").get()
