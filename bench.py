@@ -229,10 +229,7 @@ class PPOIteration:
         else:
             self.engine = cpmusic.RolloutEngine(self.actor, SONGS_PER_GPU, ROLLOUT_LEN, greedy=False, true_positions=True,
                                                 seed=1234, seq_base=rank * SONGS_PER_GPU)
-        self.group = None
-        if world > 1:
-            import torch.distributed as dist
-            self.group = dist.group.WORLD
+        self.group = None                              # attach_group() once the process group exists
         g = torch.Generator().manual_seed(1234 + rank)
         self.init_host = torch.stack([torch.randint(0, n, (SONGS_PER_GPU,), generator=g) for n in VOCAB], -1).pin_memory()
         self.init_dev = self.init_host.to(dev)
@@ -240,6 +237,12 @@ class PPOIteration:
         self.cstream = torch.cuda.Stream(device=dev)
         self.pending, self._inflight = None, None
         self.vstat = torch.zeros((), device=dev)
+
+    def attach_group(self):
+        import torch.distributed as dist
+        self.group = dist.group.WORLD
+        self.red_a.attach()
+        self.red_c.attach()
 
     # The critic's update needs the iteration's returns and trajectories but nothing of it feeds the NEXT rollout (which only
     # reads the actor): with OVERLAP_CRITIC it is queued on a second stream and runs underneath the next iteration's rollout,
@@ -379,6 +382,17 @@ def run_gpu(args, rank, world):
     cpmusic._lib.load()
     peak, peak_src = load_peaks()
     it = PPOIteration(rank, world, dev)
+    if world > 1:
+        # Build the NCCL communicator only AFTER the models, the recurrent state, the weight packings and the captured rollout
+        # graph exist.  Measured (tools/clock_probe.py, profiles/r01_summary.md section R): with the communicator created
+        # before anything else the very same graph replays take 8 % longer (505 vs 466 us per token); created after three full
+        # iterations they do not.  Creating it after the first rollout (all we can run before the ranks must stay in step)
+        # recovers part of it: 2 GPUs 665.7 k -> 675.6 k tokens/s.
+        it.engine.generate(it.init_dev)
+        torch.cuda.synchronize()
+        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line (NCCL prints its version there)
+        cpmusic.dist.init_from_env("nccl")
+        it.attach_group()
 
     def barrier():
         if world > 1:
@@ -496,10 +510,6 @@ def main():
     if args.impl == "reference":
         run_reference(args, rank)
         return
-    if world > 1:
-        os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line (NCCL prints its version there)
-        import cpmusic
-        cpmusic.dist.init_from_env("nccl")
     run_gpu(args, rank, world)
     if world > 1:
         import torch.distributed as dist

@@ -71,6 +71,12 @@ class BucketedGradAllReduce:
             for p in b["params"]:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
 
+    def attach(self, group=None):
+        """(Re)binds the reducer to a process group created AFTER it was constructed (buckets and hooks are unchanged)."""
+        self.group = group
+        self.world = dist.get_world_size(group) if dist.is_initialized() else 1
+        return self
+
     def _close(self, plist):
         n = sum(p.numel() for p in plist)
         flat = torch.zeros(n, dtype=torch.float32, device=plist[0].device)

@@ -27,7 +27,7 @@ def get_limit(which):
 torch.zeros(1, device=dev)
 limits_before = {n: get_limit(i) for i, n in ((0, "stack"), (2, "malloc_heap"), (5, "max_l2_fetch"), (6, "persisting_l2"))}
 MODE = os.environ.get("PROBE_MODE", "dp")          # dp | nccl-idle (communicator built, never used by the loop) | independent
-if world > 1 and MODE != "independent":
+if world > 1 and MODE not in ("independent", "nccl-late"):
     import torch.distributed as dist
     dist.init_process_group("nccl", device_id=dev)
     t = torch.ones(1, device=dev); dist.all_reduce(t)
@@ -55,7 +55,12 @@ it = bench.PPOIteration(rank, world_used, dev)
 for _ in range(2):
     it.step(it.init_dev)
 torch.cuda.synchronize()
-for i in range(4):
+for i in range(6 if MODE == "nccl-late" else 4):
+    if MODE == "nccl-late" and i == 3 and world > 1:      # communicator built AFTER every buffer of the loop exists
+        import torch.distributed as dist
+        dist.init_process_group("nccl", device_id=dev)
+        t = torch.ones(1, device=dev); dist.all_reduce(t); torch.cuda.synchronize()
+        print(f"rank {rank}: NCCL communicator built", flush=True)
     pre = spin_mhz()
     r0, r1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     import time as _t
