@@ -149,17 +149,23 @@ def test_shard_range(cpm):
         assert max(h - l for l, h in spans) - min(h - l for l, h in spans) <= 1
 
 
-def _dp_worker(rank, world, port, q):
+def _dp_worker(rank, world, port, q, late=False):
     import torch.distributed as dist
     sys.path.insert(0, ROOT)
     import cpmusic
     os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
-    cpmusic.dist.init_from_env("gloo")
+    if not late:
+        cpmusic.dist.init_from_env("gloo")
     torch.manual_seed(0)
     net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4), torch.nn.Linear(4, 4))
     for p in net[3].parameters():          # a parameter that never receives a gradient in this loss
         p.requires_grad_(True)
     red = cpmusic.dist.BucketedGradAllReduce(net.parameters(), bucket_mb=0.001)
+    if late:                               # bench.py's order: buffers first, process group afterwards, then attach()
+        assert red.world == 1
+        cpmusic.dist.init_from_env("gloo")
+        red.attach()
+    assert red.world == world
     g = torch.Generator().manual_seed(1)
     X, Y = torch.randn(8, 16, generator=g), torch.randn(8, 4, generator=g)
     lo, hi = cpmusic.dist.shard_range(8, rank, world)
@@ -182,12 +188,13 @@ def _dp_worker(rank, world, port, q):
     dist.destroy_process_group()
 
 
-def test_bucketed_allreduce_gloo_world2():
+@pytest.mark.parametrize("late", [False, True])
+def test_bucketed_allreduce_gloo_world2(late):
     import torch.multiprocessing as mp
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
-    port = 29500 + (os.getpid() % 2000)
-    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q)) for r in range(2)]
+    port = 29500 + (os.getpid() % 2000) + (7 if late else 0)
+    procs = [ctx.Process(target=_dp_worker, args=(r, 2, port, q, late)) for r in range(2)]
     for p in procs:
         p.start()
     res = [q.get(timeout=180) for _ in procs]
