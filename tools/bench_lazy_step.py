@@ -1,4 +1,8 @@
-import sys; sys.path.insert(0, "/root/repo")
+"""Recurrent state kernel variants at the rollout shape (256 sequences x 8 heads x 12 layers, L2 flushed): one-CTA-per-tile (default),
+deferred write-back by pending count, read-only / write-back halves, plain device copies for scale, persistent bulk-copy-staged kernel.
+    python tools/bench_lazy_step.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, cpmusic
 from cpmusic import ops
 dev = torch.device("cuda:0")

@@ -1,4 +1,7 @@
-import sys; sys.path.insert(0, "/root/repo")
+"""Kernel-level breakdown (torch profiler, CUDA activities) of one cfg2 pretraining step: 32 x 512 tokens, bf16, train_step + clip 3 + Adam.
+    python tools/profile_pretrain_step.py"""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch, cpmusic
 VOCAB = [56, 135, 18, 87, 18, 25]
 dev = torch.device("cuda:0")
