@@ -175,7 +175,7 @@ def workload_config(world):
     return {"workload": f"cfg3: PPO rollout ({SONGS_PER_GPU} songs x {ROLLOUT_LEN} CP tokens per GPU, recurrent, per-attribute "
                         f"temperature/nucleus sampling) + critic values + GAE + one clipped-PPO update (actor+critic, "
                         f"{SONGS_PER_GPU // MINIBATCH} minibatches of {MINIBATCH}x{ROLLOUT_LEN}, dropout 0.1, grad-clip 3, Adam)",
-            "model": "CP linear transformer 12L d512 h8 ff2048 (38.98M params) x2 (actor, critic)",
+            "agent": "CP linear transformer 12L d512 h8 ff2048 (38.98M params) x2 (actor, critic)",
             "tokens_per_step": tokens_step, "parallelism": f"dp{world}", "l2": "inputs larger than L2 (working set > 1 GB/step)",
             "reward": "synthetic (Longformer reward model out of scope)",
             "schedule": ("critic update of iteration i runs on a second stream under the rollout of iteration i+1 (the rollout reads only the "
