@@ -139,3 +139,22 @@ class RewardHead(torch.nn.Module):
     def forward(self, hidden, want_scores=False):
         u, c = self.collapsed()
         return ops.reward_head(hidden, u, c, want_scores)
+
+
+class DiscriminatorHead(torch.nn.Module):
+    """The read-out of the DQN-side AIRL discriminator (dqn_policy/AIRL_model.py:91-98,117-120): the Longformer's
+    ``last_hidden_state`` averaged over ALL positions (the reference ignores the attention mask here) followed by
+    ``score_classifier`` = Linear(d,128) -> BatchNorm1d(128) -> Tanh -> Linear(128,64) -> Tanh -> Linear(64,1) -> Sigmoid, with
+    the reference's parameter names (``score_classifier.{0,1,3,5}.*``) so its checkpoints load.  (N, L, d) -> (N, 1) in
+    (0, 1).  Differentiable (the reference trains it with BCE, AIRL.py:61-90); BatchNorm follows ``train()`` / ``eval()``.
+    A few thousand rows of a 128-wide MLP: plain library ops on whatever device ``hidden`` lives on - like
+    ``value_funtion``, not worth a kernel.  The Longformer body is out of scope (HF ``transformers``)."""
+
+    def __init__(self, d_model=512):
+        super().__init__()
+        nn = torch.nn
+        self.score_classifier = nn.Sequential(nn.Linear(d_model, 128), nn.BatchNorm1d(128), nn.Tanh(), nn.Linear(128, 64), nn.Tanh(),
+                                              nn.Linear(64, 1), nn.Sigmoid())
+
+    def forward(self, hidden, masks=None):
+        return self.score_classifier(hidden.to(self.score_classifier[0].weight.dtype).mean(dim=1))      # bf16 body output -> fp32 masters

@@ -314,3 +314,30 @@ def test_head_width_validation(cpm):
     with pytest.raises(ValueError, match="64 .*or 128"):
         TransformerEncoderBuilder.from_kwargs(n_layers=1, n_heads=2, query_dimensions=32, value_dimensions=32,
                                               feed_forward_dimensions=64, activation="gelu", dropout=0.0, attention_type="causal-linear").get()
+
+
+def test_discriminator_head_matches_reference_formula(cpm):
+    """DQN-side AIRL read-out (AIRL_model.py:91-98,117-120): sequence mean over all positions, then the score classifier;
+    parameter names as in the reference, training-mode BatchNorm statistics included."""
+    torch.manual_seed(5)
+    head = cpm.rl.DiscriminatorHead(d_model=48).double()
+    assert sorted(k for k in head.state_dict() if k.endswith("weight")) == [f"score_classifier.{i}.weight" for i in (0, 1, 3, 5)]
+    h = torch.randn(9, 50, 48, dtype=torch.float64)
+    sc = head.score_classifier
+    for mode in (True, False):
+        head.train(mode)
+        m = h.mean(dim=1)                                      # literal restatement, BatchNorm written out
+        z = m @ sc[0].weight.T + sc[0].bias
+        if mode:
+            mu, var = z.mean(0), z.var(0, unbiased=False)
+        else:
+            mu, var = sc[1].running_mean, sc[1].running_var
+        z = (z - mu) / torch.sqrt(var + sc[1].eps) * sc[1].weight + sc[1].bias
+        z = torch.tanh(torch.tanh(z) @ sc[3].weight.T + sc[3].bias)
+        ref = torch.sigmoid(z @ sc[5].weight.T + sc[5].bias)
+        got = head(h)
+        assert got.shape == (9, 1) and torch.allclose(got, ref, atol=1e-6), (mode, (got - ref).abs().max())
+    head.train()
+    h.requires_grad_()
+    torch.nn.functional.binary_cross_entropy(head(h), torch.ones(9, 1, dtype=torch.float64)).backward()      # AIRL.py trains it with BCE
+    assert h.grad is not None and sc[0].weight.grad is not None
