@@ -1,0 +1,40 @@
+"""Deterministic, name-keyed parameter values shared by ``make_ref_golden.py`` (which loads them
+into the REAL reference modules) and ``tests/test_ref_golden.py`` (which loads them into the
+oracle / the CUDA-backed modules).  Independent of module construction order and of torch's
+default-init RNG consumption, so the same state dict can be rebuilt wherever the key names and
+shapes agree."""
+import zlib
+
+import torch
+
+
+def tensor_for(name: str, shape, seed: int) -> torch.Tensor:
+    g = torch.Generator().manual_seed((seed * 1_000_003 + zlib.crc32(name.encode())) % (2 ** 31))
+    shape = tuple(shape)
+    if name.endswith("lut.weight"):                       # embeddings
+        return torch.randn(shape, generator=g) * 0.5
+    if "norm" in name and name.endswith("weight"):        # LayerNorm gains
+        return 1.0 + 0.1 * torch.randn(shape, generator=g)
+    if len(shape) >= 2:                                   # Linear weights (out, in)
+        return torch.randn(shape, generator=g) / (shape[-1] ** 0.5)
+    return 0.1 * torch.randn(shape, generator=g)          # biases
+
+
+def fill_(module: torch.nn.Module, seed: int) -> None:
+    """Overwrites every PARAMETER of ``module`` in place (buffers such as ``pos_emb.pe`` keep the
+    value the module computed for itself)."""
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            p.copy_(tensor_for(name, p.shape, seed).to(p.dtype))
+
+
+def dqn_td_inputs(seed: int, vocab, B: int = 30, L: int = 50, n_actions: int = 25):
+    """Inputs of the DQN TD golden (too large to commit: 2 x B x L x sum(vocab) floats), rebuilt from
+    the seed by the generator script and by the tests."""
+    g = torch.Generator().manual_seed(seed)
+    q = [torch.randn(B, L, n, generator=g).requires_grad_() for n in vocab]
+    nx = [torch.randn(B, L, n, generator=g).requires_grad_() for n in vocab]
+    action = torch.stack([torch.randint(0, n, (B, n_actions), generator=g) for n in vocab], -1)
+    reward = torch.rand(B, 1, generator=g)
+    done = (torch.rand(B, 1, generator=g) < 0.2).long()
+    return q, nx, action, reward, done

@@ -1,0 +1,118 @@
+"""GPU parity against vectors produced by EXECUTING THE REFERENCE'S OWN PYTHON
+(tests/golden/make_ref_golden.py; see tests/test_ref_golden.py for what those vectors pin).
+The CUDA-backed modules are loaded with the same name-keyed weights the reference modules ran with
+and compared in fp32 compute mode (tight) and, for the loss, in the bf16 production mode.
+Nothing here reads /root/reference at run time."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import ref_weights  # noqa: E402
+from oracle import model_oracle as mo  # noqa: E402
+
+pytestmark = pytest.mark.gpu
+VOCAB_DQN = [56, 135, 18, 87, 18, 25]
+VOCAB_PPO = [49, 19, 19, 89, 67, 25]
+SMALL = dict(d_model=128, n_layer=2, n_head=2, d_inner=2048)
+ATTRS = ("tempo", "chord", "barbeat", "pitch", "duration", "velocity")
+
+
+def T(a):
+    return torch.from_numpy(np.asarray(a))
+
+
+def _cmp(a, b, atol, rtol=0.0, what=""):
+    a, b = a.detach().double().cpu(), torch.as_tensor(b).double().cpu()
+    err = (a - b).abs()
+    assert bool((err <= atol + rtol * b.abs()).all()), f"{what}: max err {err.max().item():.3e}, ref scale {b.abs().max().item():.3e}"
+
+
+def _weights(vocab, seed, variant="dqn", critic=False):
+    """State dict with the values the reference module was given (names are the contract, App. A.3)."""
+    o = mo.OracleCritic(vocab, **SMALL) if critic else mo.OracleCPModel(vocab, variant=variant, **SMALL)
+    ref_weights.fill_(o, seed)
+    return o.state_dict()
+
+
+def test_teacher_forced_surface_vs_reference_run(cuda, cpm, golden):
+    g = golden("ref_model")
+    m = cpm.LinearTransformer(VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    m.load_state_dict(_weights(VOCAB_DQN, 11))
+    m = m.to(cuda).train()
+    x, y, mask = (T(g[k]).to(cuda) for k in ("dqn_x", "dqn_y", "dqn_mask"))
+    h = m.forward_hidden(x)
+    _cmp(h, g["dqn_h"], 5e-4, 2e-4, "hidden")
+    for a, lg in zip(ATTRS, m.forward_output(h, y)):
+        _cmp(lg, g[f"dqn_logits_{a}"], 1e-3, 2e-4, f"logits {a}")
+    losses = torch.stack(m.train_step(x, y, mask))
+    _cmp(losses, g["dqn_losses"], 3e-4, 1e-4, "losses")
+    (losses.sum() / 6).backward()
+    for name, key in (("in_linear.weight", "dqn_grad_in_linear"), ("word_emb_pitch.lut.weight", "dqn_grad_lut_pitch"),
+                      ("transformer_encoder.layers.0.attention.query_projection.weight", "dqn_grad_q0"),
+                      ("proj_tempo.weight", "dqn_grad_proj_tempo")):
+        ref = g[key]
+        _cmp(dict(m.named_parameters())[name].grad, ref, 2e-5 + 3e-3 * np.abs(ref).max(), 3e-3, key)
+    # the PPO script's int64 mask (ppo_train.py:207,398)
+    _cmp(torch.stack(m.train_step(x, y, mask.long())), g["dqn_losses_longmask"], 3e-4, 1e-4, "losses, int64 mask")
+
+
+def test_bf16_losses_vs_reference_run(cuda, cpm, golden):
+    """Production dtype; tolerance as in test_gpu_model.test_train_step_bf16."""
+    g = golden("ref_model")
+    m = cpm.LinearTransformer(VOCAB_DQN, True, compute_dtype=torch.bfloat16, dropout=0.0, **SMALL)
+    m.load_state_dict(_weights(VOCAB_DQN, 11))
+    m = m.to(cuda).train()
+    x, y, mask = (T(g[k]).to(cuda) for k in ("dqn_x", "dqn_y", "dqn_mask"))
+    _cmp(torch.stack(m.train_step(x, y, mask)), g["dqn_losses"], 3e-2, 2e-2, "losses bf16")
+
+
+def test_recurrent_protocol_vs_reference_run(cuda, cpm, golden):
+    g = golden("ref_model")
+    m = cpm.LinearTransformer(VOCAB_DQN, False, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    m.load_state_dict(_weights(VOCAB_DQN, 11))
+    m = m.to(cuda).eval()
+    x = T(g["dqn_x"]).to(cuda)
+    mem, hs = None, []
+    with torch.no_grad():
+        for t in range(g["dqn_rec_h"].shape[0]):
+            h, mem = m.forward_hidden(x[:1, t:t + 1], mem, is_training=False)    # testing-no-type-cp.py:157-167
+            hs.append(h)
+    _cmp(torch.stack(hs), g["dqn_rec_h"], 5e-4, 2e-4, "recurrent hidden")
+    _cmp(mem[-1][0], g["dqn_rec_S_last"], 5e-4, 5e-4, "S of the last layer")
+    _cmp(mem[-1][1], g["dqn_rec_Z_last"], 5e-4, 5e-4, "Z of the last layer")
+
+
+def test_actor_critic_and_readouts_vs_reference_run(cuda, cpm, golden):
+    g, gr = golden("ref_model"), golden("ref_rl")
+    x = T(g["ppo_x"]).to(cuda)
+    a = cpm.Actor_Transformer(VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    a.load_state_dict(_weights(VOCAB_PPO, 21, variant="actor"))
+    a = a.to(cuda).eval()
+    c = cpm.Critic_Transformer(VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    c.load_state_dict(_weights(VOCAB_PPO, 22, critic=True))
+    c = c.to(cuda).eval()
+    with torch.no_grad():
+        h = a.forward_hidden(x)
+        _cmp(h, g["ppo_h"], 5e-4, 2e-4, "actor hidden")
+        _cmp(a.value_funtion(h), g["ppo_value_funtion"], 5e-4, 2e-4, "value_funtion")
+        _cmp(c.value_produce(x), g["ppo_value_produce"], 5e-4, 2e-4, "value_produce")
+        act, lp = cpm.rl.ppo_choose_action(a, x[:1])
+        assert torch.equal(act.cpu(), T(gr["ppo_choose_action"]))
+        _cmp(lp, gr["ppo_choose_logp"], 2e-3, 1e-3, "choose_action log-probs")
+        act, lp = cpm.rl.ppo_select_update(a, x)
+        assert torch.equal(act.cpu(), T(gr["ppo_select_action"]))
+        _cmp(lp, gr["ppo_select_logp"], 2e-3, 1e-3, "select_udpate log-probs")
+
+
+def test_reward_head_kernel_vs_reference_run(cuda, cpm, golden):
+    gr = golden("ref_rl")
+    head = cpm.rl.RewardHead(VOCAB_PPO, d_model=64)
+    ref_weights.fill_(head, seed=31)
+    head = head.to(cuda)
+    reward = head(T(gr["rw_hidden"]).to(cuda))
+    assert reward.shape == (5,)
+    _cmp(reward, gr["rw_ppo_score"].reshape(-1), 2e-5, 1e-5, "reward score")
