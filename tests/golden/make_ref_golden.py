@@ -334,6 +334,38 @@ def reward_heads(out):
         out["rw_dqn_score_eval"] = f32(d(xd, torch.ones(5, 50)))
 
 
+def lift_function(path, fn_name, namespace):
+    tree = ast.parse(open(path).read())
+    node = next(n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name == fn_name)
+    exec(compile(ast.Module([node], []), path, "exec"), namespace)
+    return namespace[fn_name]
+
+
+def generation(out):
+    """``inference_from_scratch`` (dqn_policy/testing-no-type-cp.py:126-179) lifted from the script and run on the
+    reference's recurrent ``LinearTransformer`` (small geometry) under the global numpy RNG."""
+    import contextlib
+    import io
+    mod, cfg = import_reference("dqn_policy", "model")
+    cfg.AgentConfig.update(SMALL)
+    with contextlib.redirect_stdout(io.StringIO()):
+        r = mod.LinearTransformer(VOCAB_DQN, is_training=False).eval()
+    ref_weights.fill_(r, seed=11)
+    _, w2e = ref_weights.synthetic_dictionary()
+    fn = lift_function(os.path.join(REF, "dqn_policy", "testing-no-type-cp.py"), "inference_from_scratch",
+                       dict(np=np, torch=torch))
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        np.random.seed(2024)
+        with contextlib.redirect_stdout(io.StringIO()):
+            res = fn(r, w2e, 5)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    out.update(gen_words=np.asarray(res, dtype=np.int64), gen_bar_cond=np.int64(5), gen_np_seed=np.int64(2024))
+    print("generated", res.shape, "words for 5 bars")
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -345,6 +377,7 @@ def main():
     ppo_class(rl_out, actor, critic, x)
     dqn_class(rl_out)
     reward_heads(rl_out)
+    generation(rl_out)
     np.savez_compressed(os.path.join(HERE, "ref_model.npz"), **model_out)
     np.savez_compressed(os.path.join(HERE, "ref_rl.npz"), **rl_out)
     for f in ("ref_model.npz", "ref_rl.npz"):

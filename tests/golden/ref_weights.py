@@ -38,3 +38,21 @@ def dqn_td_inputs(seed: int, vocab, B: int = 30, L: int = 50, n_actions: int = 2
     reward = torch.rand(B, 1, generator=g)
     done = (torch.rand(B, 1, generator=g) < 0.2).long()
     return q, nx, action, reward, done
+
+
+def synthetic_dictionary():
+    """An AIlabs-Pop1K7-shaped ``word2event`` without the ``type`` class (sizes 56,135,18,87,18,25 as in
+    IRL_dqn_train.py:403): event 0 is the padding / ignore event, 'CONTI' continues tempo / chord, bar-beat 1 is 'Bar'."""
+    roots = ["C", "C#", "D", "D#", "E", "F", "F#", "G", "G#", "A", "A#", "B"]
+    quals = ["M", "m", "o", "+", "MM7", "Mm7", "mM7", "mm7", "o7", "%7", "+7"]
+    chords = [f"{r}_{q}" for r in roots for q in quals] + ["N_N"]
+    w2e = {
+        "tempo": {0: 0, 1: "CONTI", **{i + 2: f"Tempo_{32 + 3 * i}" for i in range(54)}},
+        "chord": {0: 0, 1: "CONTI", **{i + 2: chords[i] for i in range(133)}},
+        "bar-beat": {0: 0, 1: "Bar", **{i + 2: f"Beat_{i}" for i in range(16)}},
+        "pitch": {0: 0, **{i + 1: f"Note_Pitch_{22 + i}" for i in range(86)}},
+        "duration": {0: 0, **{i + 1: f"Note_Duration_{120 * i}" for i in range(17)}},
+        "velocity": {0: 0, **{i + 1: f"Note_Velocity_{40 + 3 * i}" for i in range(24)}},
+    }
+    e2w = {k: {e: w for w, e in v.items()} for k, v in w2e.items()}
+    return e2w, w2e

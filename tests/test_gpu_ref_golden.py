@@ -116,3 +116,25 @@ def test_reward_head_kernel_vs_reference_run(cuda, cpm, golden):
     reward = head(T(gr["rw_hidden"]).to(cuda))
     assert reward.shape == (5,)
     _cmp(reward, gr["rw_ppo_score"].reshape(-1), 2e-5, 1e-5, "reward score")
+
+
+def test_generation_drivers_on_the_cuda_model(cuda, cpm, golden):
+    """``inference_from_scratch`` (testing-no-type-cp.py:126-179) and its batched device-resident form on the CUDA model:
+    the device sampler draws from Philox, not numpy, so the words differ from the reference run; the protocol does not —
+    priming bar token, value ranges, and the stop at exactly ``bar_cond`` bars."""
+    _, w2e = ref_weights.synthetic_dictionary()
+    m = cpm.LinearTransformer(VOCAB_DQN, False, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    m.load_state_dict(_weights(VOCAB_DQN, 11))
+    m = m.to(cuda).eval()
+
+    def bars(words):
+        return 1 + sum(1 for w in words[1:] if w2e["bar-beat"][int(w[2])] == "Bar")
+
+    words = cpm.midi.inference_from_scratch(m, w2e, 3, max_tokens=400)
+    assert words.shape[1] == 6 and tuple(words[0]) == cpm.midi.BAR_TOKEN
+    assert all(0 <= int(words[:, a].max()) < VOCAB_DQN[a] and int(words[:, a].min()) >= 0 for a in range(6))
+    assert len(words) == 400 or (bars(words) == 3 and bars(words[:-1]) == 2)
+    songs = cpm.midi.batched_generate(m, w2e, 3, n_songs=4, max_tokens=256, seed=7)
+    assert len(songs) == 4
+    for s in songs:
+        assert tuple(s[0]) == cpm.midi.BAR_TOKEN and (len(s) == 256 or (bars(s) == 3 and bars(s[:-1]) == 2))
