@@ -366,6 +366,90 @@ def generation(out):
     print("generated", res.shape, "words for 5 bars")
 
 
+class _StopTraining(Exception):
+    pass
+
+
+def pretrain_loop(out):
+    """The reference's own ``train()`` (dqn_policy/agent_pretrain.py:485-633: TransformerModel, Adam lr 1e-4, mean of the six
+    losses, clip_grad_norm_ 3) lifted from the script together with the classes it uses and run on a tiny corpus written
+    in the reference's file formats (``train_data_linear.npz`` with the type column, ``dictionary.pkl`` with the type
+    class).  The logging ``Saver`` is a stub which (a) at its first message reaches into ``train()``'s frame to overwrite
+    the freshly initialised weights with the name-keyed ones and to pick the dropout regime, (b) records every 'batch
+    loss', (c) ends the 4000-epoch loop after ``n_batches``.  Two curves: dropout live under torch.manual_seed(71) (CPU
+    RNG stream: only the oracle can follow it) and dropout off via ``net.eval()`` (the CUDA path follows this one)."""
+    import contextlib
+    import io
+    import pickle
+    import tempfile
+    path = os.path.join(REF, "dqn_policy", "agent_pretrain.py")
+    tree = ast.parse(open(path).read())
+    wanted = {"network_paras", "Embeddings", "PositionalEncoding", "TransformerModel", "train"}
+    nodes = [n for n in tree.body if isinstance(n, (ast.ClassDef, ast.FunctionDef)) and n.name in wanted]
+    assert {n.name for n in nodes} == wanted
+    e2w, w2e = ref_weights.synthetic_dictionary()
+    ordered = lambda d: {"tempo": d["tempo"], "chord": d["chord"], "bar-beat": d["bar-beat"],              # noqa: E731
+                         "type": {0: "EOS", 1: "Metrical", 2: "Note"}, "pitch": d["pitch"], "duration": d["duration"],
+                         "velocity": d["velocity"]}
+    corpus = ref_weights.pretrain_corpus()
+    for tag, live_dropout in (("drop", True), ("eval", False)):
+        losses = []
+
+        class Saver:
+            def __init__(self, *a, **k):
+                self.first = True
+
+            def add_summary_msg(self, msg):
+                if self.first:
+                    self.first = False
+                    net = sys._getframe(1).f_locals["net"]
+                    ref_weights.fill_(net, seed=13)
+                    net.train(live_dropout)
+                    torch.manual_seed(71)
+
+            def add_summary(self, key, val, *a, **k):
+                if key == "batch loss":
+                    losses.append(val)
+                    if len(losses) == 10:
+                        raise _StopTraining
+
+            def global_step_increment(self):
+                pass
+
+        with tempfile.TemporaryDirectory() as tmp:
+            os.makedirs(os.path.join(tmp, "ckpt"))
+            np.savez(os.path.join(tmp, "train_data_linear.npz"), **corpus)
+            with open(os.path.join(tmp, "dictionary.pkl"), "wb") as f:
+                pickle.dump((ordered(e2w), ordered(w2e)), f)
+            import datetime
+            import math
+            import time
+            from torch import optim
+            from torch.nn.utils import clip_grad_norm_
+            ns = dict(torch=torch, nn=nn, F=F, np=np, os=os, sys=sys, math=math, time=time, pickle=pickle, optim=optim,
+                      datetime=datetime, clip_grad_norm_=clip_grad_norm_, Saver=Saver,
+                      TransformerEncoderBuilder=ft.TransformerEncoderBuilder, RecurrentEncoderBuilder=ft.RecurrentEncoderBuilder,
+                      TriangularCausalMask=ft.TriangularCausalMask,
+                      D_MODEL=SMALL["D_MODEL"], N_LAYER=SMALL["N_LAYER"], N_HEAD=SMALL["N_HEAD"], batch_size=4, init_lr=0.0001,
+                      path_exp=os.path.join(tmp, "exp"), path_train_data=os.path.join(tmp, "train_data_linear.npz"),
+                      path_dictionary=os.path.join(tmp, "dictionary.pkl"))
+            exec(compile(ast.Module(nodes, []), path, "exec"), ns)
+            cwd, orig_cuda, orig_mcuda = os.getcwd(), torch.Tensor.cuda, nn.Module.cuda
+            torch.Tensor.cuda = lambda self, *a, **k: self
+            nn.Module.cuda = lambda self, *a, **k: self
+            os.chdir(tmp)
+            try:
+                with contextlib.redirect_stdout(io.StringIO()):
+                    ns["train"]()
+            except _StopTraining:
+                pass
+            finally:
+                os.chdir(cwd)
+                torch.Tensor.cuda, nn.Module.cuda = orig_cuda, orig_mcuda
+        out[f"pre_losses_{tag}"] = np.asarray(losses, dtype=np.float64)
+        print("pretrain loop", tag, np.round(losses, 4))
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -378,6 +462,7 @@ def main():
     dqn_class(rl_out)
     reward_heads(rl_out)
     generation(rl_out)
+    pretrain_loop(rl_out)
     np.savez_compressed(os.path.join(HERE, "ref_model.npz"), **model_out)
     np.savez_compressed(os.path.join(HERE, "ref_rl.npz"), **rl_out)
     for f in ("ref_model.npz", "ref_rl.npz"):

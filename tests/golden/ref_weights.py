@@ -56,3 +56,15 @@ def synthetic_dictionary():
     }
     e2w = {k: {e: w for w, e in v.items()} for k, v in w2e.items()}
     return e2w, w2e
+
+
+def pretrain_corpus(n_songs: int = 8, L: int = 48, seed: int = 61):
+    """A tiny ``train_data_linear.npz``-shaped corpus: x, y (n_songs, L, 7) with the ``type`` class at column 3
+    (dropped by the training script, agent_pretrain.py:525-526), mask (n_songs, L) with ragged lengths."""
+    import numpy as np
+    g = torch.Generator().manual_seed(seed)
+    sizes = [56, 135, 18, 3, 87, 18, 25]
+    x = torch.stack([torch.randint(0, n, (n_songs, L + 1), generator=g) for n in sizes], -1)
+    lens = torch.randint(L // 2, L + 1, (n_songs,), generator=g)
+    mask = (torch.arange(L)[None, :] < lens[:, None]).float()
+    return dict(x=x[:, :-1].numpy(), y=x[:, 1:].numpy(), mask=mask.numpy().astype(np.float32))

@@ -138,3 +138,30 @@ def test_generation_drivers_on_the_cuda_model(cuda, cpm, golden):
     assert len(songs) == 4
     for s in songs:
         assert tuple(s[0]) == cpm.midi.BAR_TOKEN and (len(s) == 256 or (bars(s) == 3 and bars(s[:-1]) == 2))
+
+
+@pytest.mark.parametrize("dtype,tol", [(torch.float32, 3e-3), (torch.bfloat16, 8e-2)])
+def test_pretraining_loss_curve_vs_reference_train_loop(cuda, cpm, golden, tmp_path, dtype, tol):
+    """Reference-matching loss curves (north_star): the first 10 'batch loss' values logged by the REFERENCE's own
+    ``train()`` (agent_pretrain.py:485-565 run on files in its formats, dropout off; ``pre_losses_eval``) against the CUDA
+    model fed by ``CPBatches`` from the same npz and stepped by the same loop (mean of six losses, clip 3, Adam 1e-4).
+    Tolerances as test_gpu_model.test_pretraining_loss_curve_matches_oracle, slightly widened for the larger weights."""
+    ref = golden("ref_rl")["pre_losses_eval"]
+    np.savez(tmp_path / "train_data_linear.npz", **ref_weights.pretrain_corpus())
+    d = cpm.data.load_cp_npz(tmp_path / "train_data_linear.npz")
+    m = cpm.TransformerModel(VOCAB_DQN, True, compute_dtype=dtype, dropout=0.0, **SMALL)
+    m.load_state_dict(_weights(VOCAB_DQN, 13))
+    m = m.to(cuda).train()
+    opt = torch.optim.Adam(m.parameters(), lr=0.0001, fused=True)
+    curve = []
+    while len(curve) < len(ref):
+        for x, y, mask in cpm.data.CPBatches(d, batch_size=4, device=cuda):
+            loss = sum(m.train_step(x, y, mask)) / 6
+            opt.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(m.parameters(), 3.0)
+            opt.step()
+            curve.append(loss.item())
+    curve = curve[:len(ref)]
+    _cmp(torch.tensor(curve), ref, tol, 0.0, f"loss curve {curve} vs {ref.tolist()}")
+    assert curve[-1] < curve[0] - 0.3

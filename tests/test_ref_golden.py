@@ -188,3 +188,40 @@ def test_reward_read_outs_match_reference_run(gr, cpm):
     disc.eval()
     with torch.no_grad():
         torch.testing.assert_close(disc(hidden), T(gr["rw_dqn_score_eval"]), rtol=1e-5, atol=1e-6)
+
+
+def _pretrain_curve(model, batches, n, seed=None):
+    """The body of the reference's training loop (agent_pretrain.py:536-565): batches in file order, epoch after epoch."""
+    opt = torch.optim.Adam(model.parameters(), lr=0.0001)
+    if seed is not None:
+        torch.manual_seed(seed)
+    out = []
+    while len(out) < n:
+        for x, y, mask in batches:
+            losses = model.train_step(x, y, mask)
+            loss = sum(losses) / 6
+            model.zero_grad()
+            loss.backward()
+            torch.nn.utils.clip_grad_norm_(model.parameters(), 3)
+            opt.step()
+            out.append(float(loss.detach()))
+            if len(out) == n:
+                break
+    return np.asarray(out)
+
+
+@pytest.mark.parametrize("tag,live_dropout", [("drop", True), ("eval", False)])
+def test_pretraining_loss_curve_matches_reference_train_loop(gr, cpm, tmp_path, tag, live_dropout):
+    """10 optimizer steps of the REFERENCE's own ``train()`` (run from agent_pretrain.py on files in its formats) against
+    the oracle driven by the loop restated above, with the corpus read back through the product's npz loader.  With dropout
+    live the oracle consumes torch's CPU RNG stream exactly as the reference model did (same modules in the same order)."""
+    np.savez(tmp_path / "train_data_linear.npz", **ref_weights.pretrain_corpus())
+    d = cpm.data.load_cp_npz(tmp_path / "train_data_linear.npz", pin=False)
+    batches = list(cpm.data.CPBatches(d, batch_size=4, device="cpu"))
+    assert len(batches) == 2 and batches[0][0].shape == (4, 48, 6)
+    m = mo.OracleCPModel(VOCAB_DQN, is_training=True, variant="dqn", dropout=0.1, **SMALL)
+    ref_weights.fill_(m, seed=13)
+    m.train(live_dropout)
+    got = _pretrain_curve(m, batches, 10, seed=71)
+    np.testing.assert_allclose(got, gr[f"pre_losses_{tag}"], rtol=2e-5, atol=2e-5)
+    assert got[-1] < got[0] - 0.3
