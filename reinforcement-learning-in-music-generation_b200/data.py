@@ -4,9 +4,11 @@
   the ``type`` attribute in column 3, ``mask`` ``(songs, L)``; agent_pretrain.py:491-526, IRL_dqn_train.py:418-434) →
   6-attribute int64 tensors in pinned host memory, and an iterator that keeps one batch in flight to the GPU on a side
   stream (the reference does a blocking ``torch.from_numpy(...).long().cuda()`` per step, agent_pretrain.py:552-554).
-* ``AgentMemory`` / ``ExpertMemory``: the numpy float64 ring buffers of ppo_train.py:69-212 and
-  IRL_dqn_train.py:78-204 as preallocated device tensors with the same method and field names; storing a transition is
-  a handful of device-side copies (the reference does seven ``.detach().cpu().numpy()`` syncs per transition).
+* ``AgentMemory`` / ``ExpertMemory`` (ppo_train.py:69-212) and ``DQNAgentMemory`` / ``DQNExpertMemory``
+  (IRL_dqn_train.py:78-204, where the two classes carry the same names with fewer fields and tuple returns): the numpy
+  float64 ring buffers as preallocated device tensors with the reference's attribute names, ``store_transition``
+  argument orders and ``sampling`` / ``get`` return layouts; storing a transition is a handful of device-side copies
+  (the reference does up to seven ``.detach().cpu().numpy()`` syncs per transition).
 """
 from __future__ import annotations
 
@@ -84,62 +86,102 @@ class CPBatches:
             yield cur
 
 
-class _Memory:
-    """Device ring buffer with the reference's field layout: states / next_states (cap, n_states, n_feat) int64, actions
-    (cap, n_actions, n_feat) int64, log_actions (cap, n_actions, n_feat) float32, value / rewards / dones (cap, 1)."""
-    suffix = "agent"
+class _Ring:
+    """Preallocated device ring buffer.  ``FIELDS`` lists (reference attribute name, per-slot shape key, dtype) in the
+    order ``store_transition`` takes them; shape keys: 's' (n_states, n_features), 'a' (n_actions, n_features), '1' (1,),
+    'm' (n_states,).  Integer-valued fields are int64 and real-valued ones float32 on the device (the reference keeps
+    float64 numpy arrays and converts on every read)."""
+    FIELDS = ()
 
-    def __init__(self, capacity: int, n_states: int = 50, n_actions: int = 25, n_features: int = 6, device="cuda",
-                 log_prob_long_compat: bool = True, seed: int = 0):
+    def __init__(self, capacity: int, n_states: int = 50, n_actions: int = 25, n_features: int = 6, device="cuda", seed: int = 0):
         dev = torch.device(device)
-        z = lambda *s, dt=torch.int64: torch.zeros(*s, dtype=dt, device=dev)
-        s = self.suffix
-        setattr(self, f"states_{s}", z(capacity, n_states, n_features))
-        setattr(self, f"next_states_{s}", z(capacity, n_states, n_features))
-        setattr(self, f"actions_{s}", z(capacity, n_actions, n_features))
-        setattr(self, f"log_actions_{s}", z(capacity, n_actions, n_features, dt=torch.float32))
-        setattr(self, f"value_{s}", z(capacity, 1, dt=torch.float32))
-        setattr(self, f"rewards_{s}", z(capacity, 1, dt=torch.float32))
-        setattr(self, f"dones_{s}", z(capacity, 1, dt=torch.float32))
+        shapes = {"s": (n_states, n_features), "a": (n_actions, n_features), "1": (1,), "m": (n_states,)}
+        for name, key, dt in self.FIELDS:
+            setattr(self, name, torch.zeros((capacity,) + shapes[key], dtype=dt, device=dev))
         self.capacity, self.device, self.memory_counter = capacity, dev, 0
-        # the reference reads log-probs back with .long() (ppo_train.py:135): values truncate to {0,-1,-2,...}
-        self.log_prob_long_compat = log_prob_long_compat
         self.gen = torch.Generator(device=dev).manual_seed(seed)
 
-    def _f(self, name):
-        return getattr(self, f"{name}_{self.suffix}")
-
-    def store_transition(self, state, action, log_action, value_state, reward, next_state, done):
+    def store_transition(self, *values):
+        if len(values) != len(self.FIELDS):
+            raise TypeError(f"store_transition takes {len(self.FIELDS)} values ({', '.join(f[0] for f in self.FIELDS)})")
         i = self.memory_counter % self.capacity
-        self._f("states")[i].copy_(torch.as_tensor(state, device=self.device).reshape(self._f("states")[i].shape))
-        self._f("actions")[i].copy_(torch.as_tensor(action, device=self.device).reshape(self._f("actions")[i].shape))
-        self._f("log_actions")[i].copy_(torch.as_tensor(log_action, device=self.device).reshape(self._f("log_actions")[i].shape))
-        self._f("value")[i].copy_(torch.as_tensor(value_state, device=self.device).reshape(1))
-        self._f("rewards")[i].copy_(torch.as_tensor(reward, device=self.device).reshape(1))
-        self._f("next_states")[i].copy_(torch.as_tensor(next_state, device=self.device).reshape(self._f("next_states")[i].shape))
-        self._f("dones")[i].copy_(torch.as_tensor(done, device=self.device).reshape(1))
+        for (name, _, _), v in zip(self.FIELDS, values):
+            slot = getattr(self, name)[i]
+            slot.copy_(torch.as_tensor(v, device=self.device).reshape(slot.shape))
         self.memory_counter += 1
 
-    def _pack(self, idx):
-        lp = self._f("log_actions")[idx]
-        if self.log_prob_long_compat:
-            lp = lp.long()
-        return (self._f("states")[idx], self._f("actions")[idx], lp, self._f("value")[idx], self._f("rewards")[idx],
-                self._f("next_states")[idx], self._f("dones")[idx].long())
+    def _indices(self, batch_size, idx):
+        """Uniform WITH replacement over the WHOLE buffer, filled or not, like the reference
+        (``np.random.choice(BUFFER_SIZE, batch_size)``); ``idx`` injects the draw (tests, replays)."""
+        if idx is not None:
+            return torch.as_tensor(idx, device=self.device, dtype=torch.int64)
+        return torch.randint(0, self.capacity, (batch_size,), device=self.device, generator=self.gen)
 
-    def sampling(self, batch_size: int):
-        """Uniform over the WHOLE buffer like the reference (``np.random.choice(BUFFER_SIZE, batch_size)``)."""
-        idx = torch.randint(0, self.capacity, (batch_size,), device=self.device, generator=self.gen)
-        return self._pack(idx)
+
+_I, _F = torch.int64, torch.float32
+
+
+class AgentMemory(_Ring):
+    """PPO trajectory buffer, ppo_train.py:69-144.  ``sampling`` -> (states, actions, log_actions, values, rewards,
+    next_states, dones); ``get`` -> dict with the reference's keys.  The reference reads the stored log-probs back with
+    ``.long()`` (ppo_train.py:118,135: values truncate toward zero); ``log_prob_long_compat=False`` returns them as stored."""
+    FIELDS = (("states_agent", "s", _I), ("actions_agent", "a", _I), ("log_actions_agent", "a", _F), ("value_agent", "1", _F),
+              ("rewards_agent", "1", _F), ("next_states_agent", "s", _I), ("dones_agent", "1", _I))
+
+    def __init__(self, capacity: int, *a, log_prob_long_compat: bool = True, **kw):
+        super().__init__(capacity, *a, **kw)
+        self.log_prob_long_compat = log_prob_long_compat
+
+    def _pack(self, idx):
+        lp = self.log_actions_agent[idx]
+        return (self.states_agent[idx], self.actions_agent[idx], lp.long() if self.log_prob_long_compat else lp, self.value_agent[idx],
+                self.rewards_agent[idx], self.next_states_agent[idx], self.dones_agent[idx])
+
+    def sampling(self, batch_size: int, idx=None):
+        return self._pack(self._indices(batch_size, idx))
 
     def get(self):
         s, a, lp, v, r, ns, d = self._pack(slice(None))
         return {"states": s, "actions": a, "log_actions": lp, "values": v, "rewards": r, "next_states": ns, "dones": d}
 
 
-class AgentMemory(_Memory):
-    suffix = "agent"
+class ExpertMemory(_Ring):
+    """PPO expert buffer, ppo_train.py:147-212: no log-probs / values, two loss masks per transition.  ``sampling`` ->
+    (states, actions, rewards, next_states, dones, mask_state, mask_next_state) with float masks; ``get`` -> dict without
+    ``dones`` and with int64 masks (what ``train_step`` is then handed, ppo_train.py:207,398)."""
+    FIELDS = (("states_exp", "s", _I), ("actions_exp", "a", _I), ("rewards_exp", "1", _F), ("next_states_exp", "s", _I),
+              ("dones_exp", "1", _I), ("mask_state", "m", _F), ("mask_next_state", "m", _F))
+
+    def sampling(self, batch_size: int, idx=None):
+        i = self._indices(batch_size, idx)
+        return (self.states_exp[i], self.actions_exp[i], self.rewards_exp[i], self.next_states_exp[i], self.dones_exp[i],
+                self.mask_state[i], self.mask_next_state[i])
+
+    def get(self):
+        return {"states": self.states_exp, "actions": self.actions_exp, "rewards": self.rewards_exp, "next_states": self.next_states_exp,
+                "mask_state": self.mask_state.long(), "mask_next_state": self.mask_next_state.long()}
 
 
-class ExpertMemory(_Memory):
-    suffix = "expert"
+class DQNAgentMemory(_Ring):
+    """DQN replay buffer, IRL_dqn_train.py:78-134 (the script's ``AgentMemory``): five fields, ``sampling`` and ``get``
+    both return (states, actions, rewards, next_states, dones) tuples."""
+    FIELDS = (("states_agent", "s", _I), ("actions_agent", "a", _I), ("rewards_agent", "1", _F), ("next_states_agent", "s", _I),
+              ("dones_agent", "1", _I))
+
+    def _pack(self, idx):
+        return (self.states_agent[idx], self.actions_agent[idx], self.rewards_agent[idx], self.next_states_agent[idx], self.dones_agent[idx])
+
+    def sampling(self, batch_size: int, idx=None):
+        return self._pack(self._indices(batch_size, idx))
+
+    def get(self):
+        return self._pack(slice(None))
+
+
+class DQNExpertMemory(ExpertMemory):
+    """DQN expert buffer, IRL_dqn_train.py:136-204 (the script's ``ExpertMemory``): as the PPO one, but ``get`` returns the
+    7-tuple (states, actions, rewards, next_states, dones, mask_state, mask_next_state) with int64 masks."""
+
+    def get(self):
+        return (self.states_exp, self.actions_exp, self.rewards_exp, self.next_states_exp, self.dones_exp, self.mask_state.long(),
+                self.mask_next_state.long())

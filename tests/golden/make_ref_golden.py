@@ -450,6 +450,44 @@ def pretrain_loop(out):
         print("pretrain loop", tag, np.round(losses, 4))
 
 
+def memory_buffers(out):
+    """AgentMemory / ExpertMemory of both RL scripts (ppo_train.py:69-212, IRL_dqn_train.py:78-204) lifted and driven
+    with one transition stream that wraps the ring (BUFFER_SIZE 30, 37 transitions); ``get()`` and a seeded
+    ``sampling(8)`` are recorded field by field."""
+    stream = ref_weights.transition_stream(37)
+    consts = dict(np=np, torch=torch, object=object, BUFFER_SIZE=30, N_STATES=50, N_FEATURES=6, N_ACTIONS=25,
+                  device=torch.device("cpu"))
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        for tag, script in (("ppo", os.path.join(REF, "ppo_policy", "ppo_train.py")),
+                            ("dqn", os.path.join(REF, "dqn_policy", "IRL_dqn_train.py"))):
+            ns = dict(consts)
+            agent = lift_class(script, "AgentMemory", ns)()
+            expert = lift_class(script, "ExpertMemory", ns)()
+            for tr in stream:
+                if tag == "ppo":
+                    agent.store_transition(tr["state"], tr["action"], tr["log_action"], tr["value"], tr["reward"], tr["next_state"],
+                                           tr["done"])
+                else:
+                    agent.store_transition(tr["state"], tr["action"], tr["reward"], tr["next_state"], tr["done"])
+                expert.store_transition(tr["state"], tr["action"], tr["reward"], tr["next_state"], tr["done"], tr["mask_state"],
+                                        tr["mask_next_state"])
+            for name, mem in (("agent", agent), ("expert", expert)):
+                got = mem.get()
+                items = got.items() if isinstance(got, dict) else enumerate(got)
+                for k, v in items:
+                    out[f"mem_{tag}_{name}_get_{k}"] = v.numpy()
+                np.random.seed(91)
+                for k, v in enumerate(mem.sampling(8)):
+                    out[f"mem_{tag}_{name}_sample_{k}"] = v.numpy()
+                out[f"mem_{tag}_{name}_counter"] = np.int64(mem.memory_counter)
+    finally:
+        torch.Tensor.cuda = orig_cuda
+    np.random.seed(91)
+    out["mem_sample_idx"] = np.random.choice(30, 8)
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -463,6 +501,7 @@ def main():
     reward_heads(rl_out)
     generation(rl_out)
     pretrain_loop(rl_out)
+    memory_buffers(rl_out)
     np.savez_compressed(os.path.join(HERE, "ref_model.npz"), **model_out)
     np.savez_compressed(os.path.join(HERE, "ref_rl.npz"), **rl_out)
     for f in ("ref_model.npz", "ref_rl.npz"):

@@ -68,3 +68,22 @@ def pretrain_corpus(n_songs: int = 8, L: int = 48, seed: int = 61):
     lens = torch.randint(L // 2, L + 1, (n_songs,), generator=g)
     mask = (torch.arange(L)[None, :] < lens[:, None]).float()
     return dict(x=x[:, :-1].numpy(), y=x[:, 1:].numpy(), mask=mask.numpy().astype(np.float32))
+
+
+def transition_stream(n: int, n_states: int = 50, n_actions: int = 25, n_features: int = 6, seed: int = 81):
+    """n synthetic transitions as the RL scripts produce them (ppo_train.py:455-480, IRL_dqn_train.py:455-480): int64 token
+    windows, float log-probs, scalar-shaped value / reward / done tensors, float loss masks."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for t in range(n):
+        out.append(dict(
+            state=torch.randint(0, 18, (1, n_states, n_features), generator=g),
+            action=torch.randint(0, 18, (n_actions, n_features), generator=g),
+            log_action=-3.0 * torch.rand(n_actions, n_features, generator=g),
+            value=torch.randn(1, 1, generator=g),
+            reward=torch.rand(1, generator=g),
+            next_state=torch.randint(0, 18, (1, n_states, n_features), generator=g),
+            done=torch.tensor([float(t % 7 == 6)]),
+            mask_state=(torch.rand(n_states, generator=g) > 0.2).float(),
+            mask_next_state=(torch.rand(n_states, generator=g) > 0.2).float()))
+    return out

@@ -241,24 +241,50 @@ def test_cp_npz_loader_and_batches(cpm, tmp_path):
         cpm.data.load_cp_npz(tmp_path / "bad.npz", pin=False)
 
 
-def test_device_resident_memory_mirrors_reference_buffers(cpm):
-    """AgentMemory / ExpertMemory keep the reference's method and field names (ppo_train.py:69-212); log-probs come back
-    truncated by .long() like the reference's sampling()/get() unless the compat switch is off."""
-    mem = cpm.data.AgentMemory(capacity=4, n_states=5, n_actions=2, n_features=6, device="cpu")
-    for t in range(6):                                               # wraps around the ring
-        s = torch.full((5, 6), t)
-        mem.store_transition(s, torch.full((2, 6), t + 10), torch.full((2, 6), -1.7 - t), torch.tensor([[0.5 * t]]),
-                             torch.tensor([0.1 * t]), s + 1, torch.tensor(float(t == 5)))
-    assert mem.memory_counter == 6 and mem.states_agent.shape == (4, 5, 6) and mem.rewards_agent.shape == (4, 1)
-    allp = mem.get()
-    assert set(allp) == {"states", "actions", "log_actions", "values", "rewards", "next_states", "dones"}
-    assert allp["states"][0, 0, 0].item() == 4 and allp["states"][1, 0, 0].item() == 5 and allp["states"][2, 0, 0].item() == 2
-    assert allp["log_actions"].dtype == torch.int64 and allp["log_actions"][1, 0, 0].item() == int(-1.7 - 5)
-    batch = mem.sampling(16)
-    assert batch[0].shape == (16, 5, 6) and batch[3].shape == (16, 1) and batch[6].dtype == torch.int64
-    raw = cpm.data.ExpertMemory(capacity=2, n_states=5, n_actions=2, device="cpu", log_prob_long_compat=False)
+def test_device_resident_memory_mirrors_reference_buffers(cpm, golden):
+    """The four ring buffers against the REFERENCE's own classes (lifted from ppo_train.py:69-212 and
+    IRL_dqn_train.py:78-204 by tests/golden/make_ref_golden.py, driven with the same 37 transitions into 30 slots):
+    attribute names, store_transition argument orders, get() / sampling() layouts, dtypes and values, incl. the ring
+    wrap-around and the .long() truncation of stored log-probs."""
+    sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
+    import ref_weights
+    g = golden("ref_rl")
+    stream = ref_weights.transition_stream(37)
+    kinds = {("ppo", "agent"): cpm.data.AgentMemory, ("ppo", "expert"): cpm.data.ExpertMemory,
+             ("dqn", "agent"): cpm.data.DQNAgentMemory, ("dqn", "expert"): cpm.data.DQNExpertMemory}
+    for (tag, name), cls in kinds.items():
+        mem = cls(30, device="cpu")
+        for tr in stream:
+            if name == "expert":
+                mem.store_transition(tr["state"], tr["action"], tr["reward"], tr["next_state"], tr["done"], tr["mask_state"], tr["mask_next_state"])
+            elif tag == "ppo":
+                mem.store_transition(tr["state"], tr["action"], tr["log_action"], tr["value"], tr["reward"], tr["next_state"], tr["done"])
+            else:
+                mem.store_transition(tr["state"], tr["action"], tr["reward"], tr["next_state"], tr["done"])
+        assert mem.memory_counter == int(g[f"mem_{tag}_{name}_counter"]) == 37
+        got = mem.get()
+        items = list(got.items() if isinstance(got, dict) else enumerate(got))
+        want = [k for k in g.files if k.startswith(f"mem_{tag}_{name}_get_")]
+        assert [f"mem_{tag}_{name}_get_{k}" for k, _ in items] == want, (tag, name)
+        for k, v in items:
+            ref = torch.from_numpy(g[f"mem_{tag}_{name}_get_{k}"])
+            assert v.dtype == ref.dtype and v.shape == ref.shape and torch.equal(v, ref), (tag, name, k)
+        batch = mem.sampling(8, idx=g["mem_sample_idx"])
+        assert len(batch) == len([k for k in g.files if k.startswith(f"mem_{tag}_{name}_sample_")])
+        for k, v in enumerate(batch):
+            ref = torch.from_numpy(g[f"mem_{tag}_{name}_sample_{k}"])
+            assert v.dtype == ref.dtype and torch.equal(v, ref), (tag, name, "sample", k)
+        own = mem.sampling(16)                                       # own draw: device generator, whole buffer, with replacement
+        assert own[0].shape == (16, 50, 6)
+    for attr in ("states_agent", "value_agent", "actions_agent", "log_actions_agent", "rewards_agent", "next_states_agent", "dones_agent"):
+        assert hasattr(cpm.data.AgentMemory(2, device="cpu"), attr)
+    for attr in ("states_exp", "actions_exp", "rewards_exp", "next_states_exp", "dones_exp", "mask_state", "mask_next_state"):
+        assert hasattr(cpm.data.ExpertMemory(2, device="cpu"), attr)
+    raw = cpm.data.AgentMemory(2, n_states=5, n_actions=2, device="cpu", log_prob_long_compat=False)
     raw.store_transition(torch.zeros(5, 6), torch.zeros(2, 6), torch.full((2, 6), -0.25), 0.0, 1.0, torch.zeros(5, 6), 0.0)
-    assert raw.get()["log_actions"][0, 0, 0].item() == -0.25 and hasattr(raw, "states_expert")
+    assert raw.get()["log_actions"][0, 0, 0].item() == -0.25
+    with pytest.raises(TypeError):
+        raw.store_transition(torch.zeros(5, 6), torch.zeros(2, 6))
 
 
 def test_pack_cache_notices_fused_optimizer_steps(cpm):
