@@ -69,6 +69,13 @@ def test_model_surface_and_state_dict(cpm):
                      "compute_loss", "inference"):
             assert callable(getattr(m, meth))
     assert len(cpm.LinearTransformer(VOCAB).state_dict()) == 217
+    # ... and against the key lists of the REFERENCE's own modules (tests/golden/make_ref_golden.py)
+    gm = np.load(os.path.join(ROOT, "tests", "golden", "ref_model.npz"))
+    small = dict(d_model=128, n_layer=2, n_head=2, d_inner=2048)
+    ppo_vocab = [49, 19, 19, 89, 67, 25]
+    assert sorted(cpm.LinearTransformer(VOCAB, **small).state_dict()) == list(gm["dqn_state_keys"])
+    assert sorted(cpm.Actor_Transformer(ppo_vocab, **small).state_dict()) == list(gm["ppo_actor_keys"])
+    assert sorted(cpm.Critic_Transformer(ppo_vocab, **small).state_dict()) == list(gm["ppo_critic_keys"])
     c = cpm.Critic_Transformer([49, 19, 19, 89, 67, 25])
     assert set(c.state_dict()) == set(mo.OracleCritic([49, 19, 19, 89, 67, 25]).state_dict())
     a = cpm.Actor_Transformer(VOCAB)
@@ -367,3 +374,40 @@ def test_discriminator_head_matches_reference_formula(cpm):
     h.requires_grad_()
     torch.nn.functional.binary_cross_entropy(head(h), torch.ones(9, 1, dtype=torch.float64)).backward()      # AIRL.py trains it with BCE
     assert h.grad is not None and sc[0].weight.grad is not None
+
+
+@pytest.mark.skipif(not os.path.isdir("/root/reference/dqn_policy"), reason="reference tree only exists in the build container")
+def test_unmodified_reference_model_files_import_the_shim(cpm):
+    """with ``install_fast_transformers_shim()`` the reference's own model files import and construct
+    unmodified, their encoders ARE the cpmusic encoders, checkpoints move both ways between the reference classes and
+    the native ones, and a forward without a GPU fails loudly instead of computing on the CPU."""
+    saved = {k: sys.modules.pop(k) for k in list(sys.modules) if k.startswith("fast_transformers") or k in ("config", "model")}
+    try:
+        cpm.install_fast_transformers_shim()
+        for sub, cls_name, native, vocab in (("dqn_policy", "LinearTransformer", cpm.LinearTransformer, VOCAB),
+                                             ("ppo_policy", "Actor_Transformer", cpm.Actor_Transformer, [49, 19, 19, 89, 67, 25]),
+                                             ("ppo_policy", "Critic_Transformer", cpm.Critic_Transformer, [49, 19, 19, 89, 67, 25])):
+            for k in ("config", "model"):
+                sys.modules.pop(k, None)
+            sys.path.insert(0, os.path.join("/root/reference", sub))
+            try:
+                import importlib
+                mod = importlib.import_module("model")
+            finally:
+                sys.path.pop(0)
+            ref = getattr(mod, cls_name)(vocab)
+            assert type(ref.transformer_encoder).__module__.startswith(cpm.__name__)
+            nat = native(vocab)
+            assert {k: tuple(v.shape) for k, v in ref.state_dict().items()} == {k: tuple(v.shape) for k, v in nat.state_dict().items()}
+            nat.load_state_dict(ref.state_dict())
+            ref.load_state_dict(nat.state_dict())
+            x = torch.zeros(1, 8, 6, dtype=torch.long)
+            with pytest.raises(RuntimeError, match="no CPU fallback"):
+                ref.value_produce(x) if cls_name == "Critic_Transformer" else ref.forward_hidden(x)
+        rec = mod.Actor_Transformer([49, 19, 19, 89, 67, 25], is_training=False)           # RecurrentEncoderBuilder path
+        assert hasattr(rec.transformer_encoder, "new_state")
+    finally:
+        for k in list(sys.modules):
+            if k.startswith("fast_transformers") or k in ("config", "model"):
+                sys.modules.pop(k)
+        sys.modules.update(saved)
