@@ -411,3 +411,45 @@ def test_unmodified_reference_model_files_import_the_shim(cpm):
             if k.startswith("fast_transformers") or k in ("config", "model"):
                 sys.modules.pop(k)
         sys.modules.update(saved)
+
+
+def test_ctypes_signatures_match_the_header_prototypes(cpm):
+    """ABI drift guard: every prototype in include/cpmusic.h is parsed (return type, parameter count, parameter C types)
+    and compared with the ctypes signature the Python host binds it with."""
+    src = open(os.path.join(ROOT, "include", "cpmusic.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    src = re.sub(r"//[^\n]*", "", src)
+    protos = re.findall(r"([A-Za-z_][A-Za-z0-9_ ]*?[\s\*]+)(cpm_[a-z0-9_]+)\s*\(([^)]*)\)\s*;", src)
+    assert len(protos) >= 40
+
+    def ctype_of(decl):
+        decl = decl.strip()
+        if "*" in decl:
+            base = decl.replace("const", "").split("*")[0].strip()
+            if decl.count("*") == 2 or "* const *" in decl:
+                return "ptrptr"
+            return {"int": "ptr:int", "float": "ptr:float"}.get(base, "ptr")
+        words = [w for w in decl.replace("const", "").split() if w]
+        t = " ".join(words[:-1]) if len(words) > 1 else words[0]
+        return {"int": "int", "int32_t": "int32", "int64_t": "int64", "uint64_t": "uint64", "float": "float", "double": "double",
+                "long long": "int64", "unsigned long long": "uint64"}[t]
+
+    names = {ctypes.c_int: "int", ctypes.c_int32: "int32", ctypes.c_int64: "int64", ctypes.c_uint64: "uint64", ctypes.c_float: "float",
+             ctypes.c_double: "double", ctypes.c_void_p: "ptr", ctypes.c_char_p: "ptr"}
+    seen = set()
+    for ret, name, params in protos:
+        seen.add(name)
+        res, args = cpm._lib.SIGNATURES[name]
+        params = [p for p in (q.strip() for q in params.split(",")) if p and p != "void"]
+        assert len(params) == len(args), f"{name}: header has {len(params)} parameters, ctypes {len(args)}"
+        for i, (p, a) in enumerate(zip(params, args)):
+            want = ctype_of(p)
+            if a in names:
+                got = names[a]
+            else:                                             # POINTER(c_int) / POINTER(c_float) / POINTER(c_void_p)
+                got = {ctypes.c_int: "ptr:int", ctypes.c_float: "ptr:float", ctypes.c_void_p: "ptrptr"}[a._type_]
+            ok = want == got or (want.startswith("ptr") and got == "ptr") or {want, got} == {"int", "int32"}
+            assert ok, f"{name} parameter {i} ({p!r}): header {want}, ctypes {got}"
+        rwant = "ptr" if "*" in ret else ctype_of(ret + " x")
+        assert rwant == names[res] or {rwant, names[res]} == {"int", "int32"}, f"{name}: return {ret!r} vs {res}"
+    assert seen == set(_declared_symbols()) <= set(cpm._lib.SIGNATURES)
