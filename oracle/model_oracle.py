@@ -1,6 +1,7 @@
 """Oracle restatement of the reference CP agent models (CPU, plain PyTorch).
 
-TEST INFRASTRUCTURE ONLY — see ``oracle/__init__.py``.  PARITY UNPINNED (no ft).
+TEST INFRASTRUCTURE ONLY — see ``oracle/__init__.py``.  PINNED against the executed reference for everything in this file
+(tests/test_ref_golden.py); the encoder it calls (ft_oracle.py) stays unpinned.
 
 Follows, without copying, the reference modules:
 * ``Embeddings`` / ``PositionalEncoding`` — ``dqn_policy/agent_pretrain.py:185-210``

@@ -1,6 +1,7 @@
 """Oracle restatement of the reference's RL arithmetic (PPO + DQN), plain PyTorch.
 
-TEST INFRASTRUCTURE ONLY — see ``oracle/__init__.py``.
+TEST INFRASTRUCTURE ONLY — see ``oracle/__init__.py``.  PINNED against the executed
+reference (tests/golden/make_ref_golden.py -> tests/test_ref_golden.py).
 
 ``*_compat`` functions are transcriptions of what the reference *actually*
 computes, quirks included; ``*_standard`` functions are the

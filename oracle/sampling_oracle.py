@@ -1,6 +1,7 @@
 """Oracle restatement of the reference's host-side numpy samplers.
 
-TEST INFRASTRUCTURE ONLY — see ``oracle/__init__.py``.
+TEST INFRASTRUCTURE ONLY — see ``oracle/__init__.py``.  PINNED against the executed
+reference (tests/golden/make_ref_golden.py -> tests/test_ref_golden.py).
 
 Follows ``dqn_policy/model.py:19-55`` (identical twins at
 ``dqn_policy/agent_pretrain.py:136-172`` and ``ppo_policy/model.py``):

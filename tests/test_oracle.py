@@ -1,6 +1,7 @@
 """CPU: the oracle against its committed golden vectors and against itself (three equivalent forms
 of the causal product, recurrent == parallel, C clone == PyTorch), Philox known-answer vectors,
-RL formula identities.  PARITY UNPINNED w.r.t. the real fast_transformers (absent)."""
+RL formula identities.  The encoder internals are unpinned w.r.t. the real fast_transformers (absent); everything around them
+is held to the executed reference in tests/test_ref_golden.py."""
 import numpy as np
 import pytest
 import torch
