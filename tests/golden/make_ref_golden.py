@@ -488,6 +488,90 @@ def memory_buffers(out):
     out["mem_sample_idx"] = np.random.choice(30, 8)
 
 
+def rl_update_loops(out):
+    """Whole RL updates with REAL networks, executed from the reference:
+    * ``DQN.update`` (IRL_dqn_train.py:267-345) x 4 on the reference's LinearTransformer pair (small geometry, ``eval()`` so
+      dropout is off and the CUDA path can follow), Adam lr 0.01 + MultiStepLR as ``DQN.__init__`` builds them, target-net
+      sync at update 0; recorded per update: MSE, CE, total.
+    * ``PPO.update_policy`` (ppo_train.py:365-416) x 3 single-epoch calls on the reference's Actor / Critic with the
+      script's own AgentMemory / ExpertMemory filled from a transition stream; recorded per call: actor loss (policy + CE)
+      and the critic's value loss (captured at the script's ``F.mse_loss`` call)."""
+    import contextlib
+    import io
+    from torch import optim
+    from tqdm import tqdm
+    quiet = lambda: contextlib.redirect_stdout(io.StringIO())                 # noqa: E731
+    orig_cuda = torch.Tensor.cuda
+    torch.Tensor.cuda = lambda self, *a, **k: self
+    try:
+        # ---------------------------------------------------------------- DQN
+        mod, cfg = import_reference("dqn_policy", "model")
+        cfg.AgentConfig.update(SMALL)
+        with quiet():
+            ev, tg = mod.LinearTransformer(VOCAB_DQN).eval(), mod.LinearTransformer(VOCAB_DQN).eval()
+        ref_weights.fill_(ev, seed=14)
+        ref_weights.fill_(tg, seed=15)
+        ns = dict(torch=torch, nn=nn, F=F, np=np, N_ACTIONS=25, GAMMA=0.95, Target_update=50, object=object, tqdm=tqdm,
+                  wandb=_Obj(log=lambda *a, **k: None), NUM_SONGS=1500, EPISODES=50, num=0)
+        DQN = lift_class(os.path.join(REF, "dqn_policy", "IRL_dqn_train.py"), "DQN", ns)
+        agent = object.__new__(DQN)
+        agent.eval_net, agent.target_net = ev, tg
+        agent.optim = optim.Adam(ev.parameters(), lr=0.01)                                    # IRL_dqn_train.py:225 (init_lr)
+        agent.scheduler = optim.lr_scheduler.MultiStepLR(agent.optim, milestones=[20, 40], gamma=0.1)
+        agent.target_count = agent.cnt_update = agent.record_fore_epoch = 0
+        agent.mse_val = agent.ce_val = agent.total_val = 0.0
+        rows, prev = [], (0.0, 0.0, 0.0)
+        for b in ref_weights.rl_update_batches(4, VOCAB_DQN, seed=95):
+            tr = {"state": b["state"], "nextstate": b["nextstate"], "action": b["action"], "reward": b["reward"], "done": b["done"]}
+            with quiet():
+                agent.update(tr, {"state": b["state"], "nextstate": b["nextstate"]}, b["mask"], False, 0)
+            cur = (agent.mse_val, agent.ce_val, agent.total_val)
+            rows.append([c - p for c, p in zip(cur, prev)])
+            prev = cur
+        out["loop_dqn_mse_ce_total"] = np.asarray(rows, dtype=np.float64)
+        print("DQN.update x4 (mse, ce, total):", np.round(rows, 4).tolist())
+        # ---------------------------------------------------------------- PPO
+        pmod, pcfg = import_reference("ppo_policy", "model")
+        pcfg.ActorConfig.update(SMALL)
+        pcfg.CriticConfig.update(SMALL)
+        with quiet():
+            actor, critic = pmod.Actor_Transformer(VOCAB_PPO).eval(), pmod.Critic_Transformer(VOCAB_PPO).eval()
+        ref_weights.fill_(actor, seed=16)
+        ref_weights.fill_(critic, seed=17)
+        value_losses = []
+
+        def recording_mse(a, b, *args, **kw):
+            v = F.mse_loss(a, b, *args, **kw)
+            value_losses.append(float(v.detach()))
+            return v
+
+        script = os.path.join(REF, "ppo_policy", "ppo_train.py")
+        pns = dict(torch=torch, nn=nn, F=_Obj(mse_loss=recording_mse), np=np, device=torch.device("cpu"), N_ACTIONS=25, tqdm=tqdm,
+                   Load_Pretrain=False, object=object, BUFFER_SIZE=30, N_STATES=50, N_FEATURES=6)
+        PPO = lift_class(script, "PPO", pns)
+        abuf, ebuf = lift_class(script, "AgentMemory", pns)(), lift_class(script, "ExpertMemory", pns)()
+        b = ref_weights.rl_update_batches(1, VOCAB_PPO, seed=96)[0]
+        ref_weights.fill_ppo_buffers(abuf, ebuf, b)
+        ppo = object.__new__(PPO)
+        ppo.actor_net, ppo.critic_net = actor, critic
+        ppo.actor_optim = optim.Adam(actor.parameters(), lr=0.01)                             # ppo_train.py:241-243 (init_lr)
+        ppo.critic_optim = optim.Adam(critic.parameters(), lr=0.01)
+        pns.update(AgentBuffer=abuf, ExpertBuffer=ebuf, Agent=ppo)
+        rewards = abuf.get()["rewards"]
+        values = abuf.get()["values"]
+        returns = ppo.calculate_returns(rewards, 0.99)
+        adv = ppo.calculate_advantages(returns, values)
+        actor_losses = []
+        for _ in range(3):
+            with quiet(), contextlib.redirect_stderr(io.StringIO()):
+                actor_losses.append(ppo.update_policy(1, 0.2, adv, returns))
+        out.update(loop_ppo_actor_loss=np.asarray(actor_losses, dtype=np.float64), loop_ppo_value_loss=np.asarray(value_losses, dtype=np.float64),
+                   loop_ppo_returns=f32(returns), loop_ppo_adv=f32(adv))
+        print("PPO.update_policy x3 actor:", np.round(actor_losses, 4).tolist(), "critic:", np.round(value_losses, 4).tolist())
+    finally:
+        torch.Tensor.cuda = orig_cuda
+
+
 def main():
     torch.manual_seed(0)
     torch.set_num_threads(4)
@@ -502,6 +586,7 @@ def main():
     generation(rl_out)
     pretrain_loop(rl_out)
     memory_buffers(rl_out)
+    rl_update_loops(rl_out)
     np.savez_compressed(os.path.join(HERE, "ref_model.npz"), **model_out)
     np.savez_compressed(os.path.join(HERE, "ref_rl.npz"), **rl_out)
     for f in ("ref_model.npz", "ref_rl.npz"):

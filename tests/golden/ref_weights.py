@@ -87,3 +87,29 @@ def transition_stream(n: int, n_states: int = 50, n_actions: int = 25, n_feature
             mask_state=(torch.rand(n_states, generator=g) > 0.2).float(),
             mask_next_state=(torch.rand(n_states, generator=g) > 0.2).float()))
     return out
+
+
+def rl_update_batches(n_updates: int, vocab, seed: int, B: int = 30, L: int = 50, n_actions: int = 25):
+    """Replay batches as ``DQN.update`` / ``PPO.update_policy`` receive them: token windows, greedy-action-shaped indices,
+    rewards in (0,1), sparse dones, ragged loss masks."""
+    g = torch.Generator().manual_seed(seed)
+    out = []
+    for _ in range(n_updates):
+        tok = lambda rows: torch.stack([torch.randint(0, n, (B, rows), generator=g) for n in vocab], -1)      # noqa: E731
+        lens = torch.randint(L // 2, L + 1, (B,), generator=g)
+        out.append(dict(state=tok(L), nextstate=tok(L), action=tok(n_actions), reward=torch.rand(B, 1, generator=g),
+                        done=(torch.rand(B, 1, generator=g) < 0.15).long(),
+                        mask=(torch.arange(L)[None, :] < lens[:, None]).float()))
+    return out
+
+
+def fill_ppo_buffers(abuf, ebuf, b, seed: int = 97):
+    """Stores the 30 transitions of replay batch ``b`` through ``store_transition`` — the reference's buffers and the
+    device-resident ones take the same arguments in the same order."""
+    g = torch.Generator().manual_seed(seed)
+    for i in range(b["state"].shape[0]):
+        logp = -3.0 * torch.rand(25, 6, generator=g)
+        abuf.store_transition(b["state"][i], b["action"][i], logp, torch.randn(1, generator=g), b["reward"][i], b["nextstate"][i],
+                              b["done"][i].float())
+        ebuf.store_transition(b["nextstate"][i], b["action"][i], b["reward"][i], b["state"][i], b["done"][i].float(), b["mask"][i],
+                              b["mask"][i])

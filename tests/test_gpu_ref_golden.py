@@ -165,3 +165,88 @@ def test_pretraining_loss_curve_vs_reference_train_loop(cuda, cpm, golden, tmp_p
     curve = curve[:len(ref)]
     _cmp(torch.tensor(curve), ref, tol, 0.0, f"loss curve {curve} vs {ref.tolist()}")
     assert curve[-1] < curve[0] - 0.3
+
+
+def test_dqn_td_kernel_vs_reference_dqn_update(cuda, cpm, golden):
+    """The fused TD kernel on the logits the reference's ``DQN.update`` was fed (stub nets, seed-rebuilt), model layout
+    (six segments concatenated, padded to a multiple of 8 columns): MSE and dQ against the executed reference."""
+    gr = golden("ref_rl")
+    q, nx, action, reward, done = ref_weights.dqn_td_inputs(int(gr["dqnrl_seed"]), VOCAB_DQN)
+    seg = [0]
+    for n in VOCAB_DQN:
+        seg.append(seg[-1] + n)
+    pad = (-seg[-1]) % 8
+    cat = lambda parts: torch.nn.functional.pad(torch.cat([p.detach() for p in parts], -1), (0, pad)).to(cuda)      # noqa: E731
+    ql = cat(q).requires_grad_()
+    loss, _ = cpm.ops.dqn_td_loss(ql, cat(nx), action.to(cuda), reward.to(cuda), done.to(cuda), seg, 25, 0.95, True)
+    (0.3 * loss).backward()                                                     # IRL_dqn_train.py:335: alpha = 0.3
+    _cmp(loss, float(gr["dqnrl_mse"]), 1e-4, 1e-5, "TD MSE")
+    _cmp(ql.grad[..., seg[3]:seg[4]], gr["dqnrl_grad_q_pitch"], 1e-8, 1e-4, "dQ (pitch segment)")
+
+
+def test_dqn_update_loop_vs_reference_run(cuda, cpm, golden):
+    """Four whole ``DQN.update`` calls (IRL_dqn_train.py:267-345, executed from the reference with real networks) against the
+    CUDA path: ``rl.dqn_td_loss`` + ``train_step`` + Adam 0.01.  Update 0 is tight; later ones carry three Adam steps of
+    lr 0.01 of fp32 divergence."""
+    ref = golden("ref_rl")["loop_dqn_mse_ce_total"]
+    ev = cpm.LinearTransformer(VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    tg = cpm.LinearTransformer(VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    ev.load_state_dict(_weights(VOCAB_DQN, 14))
+    tg.load_state_dict(_weights(VOCAB_DQN, 15))
+    ev, tg = ev.to(cuda).train(), tg.to(cuda).train()
+    opt = torch.optim.Adam(ev.parameters(), lr=0.01)
+    rows = []
+    for u, b in enumerate(ref_weights.rl_update_batches(4, VOCAB_DQN, seed=95)):
+        b = {k: v.to(cuda) for k, v in b.items()}
+        if u % 50 == 0:
+            tg.load_state_dict(ev.state_dict())
+        mse = cpm.rl.dqn_td_loss(ev, tg, b["state"], b["nextstate"], b["action"], b["reward"], b["done"], gamma=0.95)
+        ce = sum(ev.train_step(b["state"], b["nextstate"], b["mask"])) / 6
+        total = 0.3 * mse + 0.7 * ce
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        rows.append([mse.item(), ce.item(), total.item()])
+    _cmp(torch.tensor(rows[0]), ref[0], 2e-3, 2e-4, f"update 0: {rows[0]} vs {ref[0].tolist()}")
+    _cmp(torch.tensor(rows), ref, 5e-2, 3e-2, f"DQN loss curve {rows} vs {ref.tolist()}")
+
+
+def test_ppo_update_loop_vs_reference_run(cuda, cpm, golden):
+    """Three ``PPO.update_policy`` epochs (ppo_train.py:365-416, executed from the reference with real networks and its own
+    buffers) against the CUDA path: device-resident AgentMemory / ExpertMemory, ``rl.ppo_select_update``, the compat
+    surrogate kernel, ``train_step`` with the int64 mask, ``value_produce``, two Adam optimizers at 0.01."""
+    gr = golden("ref_rl")
+    actor = cpm.Actor_Transformer(VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    critic = cpm.Critic_Transformer(VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    actor.load_state_dict(_weights(VOCAB_PPO, 16, variant="actor"))
+    critic.load_state_dict(_weights(VOCAB_PPO, 17, critic=True))
+    actor, critic = actor.to(cuda).train(), critic.to(cuda).train()
+    abuf, ebuf = cpm.data.AgentMemory(30, device=cuda), cpm.data.ExpertMemory(30, device=cuda)
+    ref_weights.fill_ppo_buffers(abuf, ebuf, ref_weights.rl_update_batches(1, VOCAB_PPO, seed=96)[0])
+    agent_all, expert_all = abuf.get(), ebuf.get()
+    returns = cpm.rl.calculate_returns_compat(agent_all["rewards"], 0.99)
+    adv = cpm.rl.calculate_advantages_compat(returns, agent_all["values"])
+    _cmp(returns, gr["loop_ppo_returns"], 1e-4, 1e-4, "returns")
+    _cmp(adv, gr["loop_ppo_adv"], 1e-4, 1e-4, "advantages")
+    a_opt, c_opt = torch.optim.Adam(actor.parameters(), lr=0.01), torch.optim.Adam(critic.parameters(), lr=0.01)
+    actor_losses, value_losses = [], []
+    for _ in range(3):
+        states = agent_all["states"]
+        _, new_logp = cpm.rl.ppo_select_update(actor, states)
+        value_pred = critic.value_produce(states)
+        policy_loss = cpm.rl.ppo_policy_loss_compat(new_logp, agent_all["log_actions"], adv)
+        ce = sum(actor.train_step(states, expert_all["states"], expert_all["mask_state"])) / 6
+        actor_loss = policy_loss + ce
+        value_loss = cpm.rl.value_loss_compat(returns.detach(), value_pred)
+        a_opt.zero_grad()
+        actor_loss.backward()
+        a_opt.step()
+        c_opt.zero_grad()
+        value_loss.backward()
+        c_opt.step()
+        actor_losses.append(actor_loss.item())
+        value_losses.append(value_loss.item())
+    _cmp(torch.tensor(actor_losses[:1]), gr["loop_ppo_actor_loss"][:1], 2e-3, 2e-4, "epoch 0 actor loss")
+    _cmp(torch.tensor(value_losses[:1]), gr["loop_ppo_value_loss"][:1], 2e-3, 2e-4, "epoch 0 value loss")
+    _cmp(torch.tensor(actor_losses), gr["loop_ppo_actor_loss"], 5e-2, 3e-2, f"actor losses {actor_losses}")
+    _cmp(torch.tensor(value_losses), gr["loop_ppo_value_loss"], 5e-2, 8e-2, f"value losses {value_losses}")

@@ -225,3 +225,64 @@ def test_pretraining_loss_curve_matches_reference_train_loop(gr, cpm, tmp_path, 
     got = _pretrain_curve(m, batches, 10, seed=71)
     np.testing.assert_allclose(got, gr[f"pre_losses_{tag}"], rtol=2e-5, atol=2e-5)
     assert got[-1] < got[0] - 0.3
+
+
+def test_dqn_update_loop_matches_reference_run(gr):
+    """Four whole ``DQN.update`` calls of the reference (real eval / target networks, Adam 0.01 + MultiStepLR, target sync at
+    update 0) against the oracle driven by the update restated from IRL_dqn_train.py:267-345."""
+    ev = mo.OracleCPModel(VOCAB_DQN, variant="dqn", **SMALL).eval()
+    tg = mo.OracleCPModel(VOCAB_DQN, variant="dqn", **SMALL).eval()
+    ref_weights.fill_(ev, seed=14)
+    ref_weights.fill_(tg, seed=15)
+    opt = torch.optim.Adam(ev.parameters(), lr=0.01)
+    sched = torch.optim.lr_scheduler.MultiStepLR(opt, milestones=[20, 40], gamma=0.1)
+    rows = []
+    for u, b in enumerate(ref_weights.rl_update_batches(4, VOCAB_DQN, seed=95)):
+        if u % 50 == 0:
+            tg.load_state_dict(ev.state_dict())
+        mse = rl.dqn_td_loss_compat(ev(b["state"]), tg(b["nextstate"]), b["action"], b["reward"], b["done"], gamma=0.95)
+        ce = sum(ev.train_step(b["state"], b["nextstate"], b["mask"])) / 6
+        total = 0.3 * mse + 0.7 * ce
+        opt.zero_grad()
+        total.backward()
+        opt.step()
+        sched.step()
+        rows.append([float(mse.detach()), float(ce.detach()), float(total.detach())])
+    np.testing.assert_allclose(np.asarray(rows), gr["loop_dqn_mse_ce_total"], rtol=2e-4, atol=2e-4)
+
+
+def test_ppo_update_loop_matches_reference_run(gr, cpm):
+    """Three ``PPO.update_policy`` epochs of the reference (real actor / critic, the script's own AgentMemory / ExpertMemory)
+    against the oracle + the product's device-resident buffers (on the CPU here) driven by the update restated from
+    ppo_train.py:365-416."""
+    actor = mo.OracleCPModel(VOCAB_PPO, variant="actor", **SMALL).eval()
+    critic = mo.OracleCritic(VOCAB_PPO, **SMALL).eval()
+    ref_weights.fill_(actor, seed=16)
+    ref_weights.fill_(critic, seed=17)
+    abuf, ebuf = cpm.data.AgentMemory(30, device="cpu"), cpm.data.ExpertMemory(30, device="cpu")
+    ref_weights.fill_ppo_buffers(abuf, ebuf, ref_weights.rl_update_batches(1, VOCAB_PPO, seed=96)[0])
+    agent_all, expert_all = abuf.get(), ebuf.get()
+    returns = rl.calculate_returns_compat(agent_all["rewards"], 0.99)
+    adv = rl.calculate_advantages_compat(returns, agent_all["values"])
+    torch.testing.assert_close(returns, T(gr["loop_ppo_returns"]), rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(adv, T(gr["loop_ppo_adv"]), rtol=1e-5, atol=1e-5)
+    a_opt, c_opt = torch.optim.Adam(actor.parameters(), lr=0.01), torch.optim.Adam(critic.parameters(), lr=0.01)
+    actor_losses, value_losses = [], []
+    for _ in range(3):
+        states = agent_all["states"]
+        _, new_logp = rl.ppo_select_update_compat(actor.forward_output(actor.forward_hidden(states)))
+        value_pred = critic.value_produce(states)
+        policy_loss = rl.ppo_policy_loss_compat(new_logp, agent_all["log_actions"], adv)
+        ce = sum(actor.train_step(states, expert_all["states"], expert_all["mask_state"])) / 6
+        actor_loss = policy_loss + ce
+        value_loss = rl.value_loss_compat(returns, value_pred)
+        a_opt.zero_grad()
+        actor_loss.backward()
+        a_opt.step()
+        c_opt.zero_grad()
+        value_loss.backward()
+        c_opt.step()
+        actor_losses.append(float(actor_loss.detach()))
+        value_losses.append(float(value_loss.detach()))
+    np.testing.assert_allclose(actor_losses, gr["loop_ppo_actor_loss"], rtol=2e-4, atol=2e-4)
+    np.testing.assert_allclose(value_losses, gr["loop_ppo_value_loss"], rtol=2e-3, atol=2e-4)
