@@ -388,7 +388,26 @@ def run_gpu(args, rank, world):
         # before anything else the very same graph replays take 8 % longer (505 vs 466 us per token); created after three full
         # iterations they do not.  Creating it after the first rollout (all we can run before the ranks must stay in step)
         # recovers part of it: 2 GPUs 665.7 k -> 675.6 k tokens/s.
-        it.engine.generate(it.init_dev)
+        if os.environ.get("CPM_BENCH_PREWARM", "0") == "1":
+            # Opt-in experiment (not yet measured): one whole throw-away iteration on this rank alone, so
+            # that the optimizer state, cuBLAS workspaces and the allocator's activation segments of the update phase exist before
+            # the communicator too; parameters are then put back and the Adam state zeroed IN PLACE (addresses stay stable for the
+            # packed weights and the captured graph), so every rank still starts the measured run from identical weights.
+            keep = [p.detach().clone() for m in (it.actor, it.critic) for p in m.parameters()]
+            it.step(it.init_dev)
+            it.flush()
+            torch.cuda.synchronize()
+            with torch.no_grad():
+                for p, k in zip((p for m in (it.actor, it.critic) for p in m.parameters()), keep):
+                    p.copy_(k)
+                for opt in (it.opt_a, it.opt_c):
+                    for st in opt.state.values():
+                        for v in st.values():
+                            if torch.is_tensor(v):
+                                v.zero_()
+            del keep
+        else:
+            it.engine.generate(it.init_dev)
         torch.cuda.synchronize()
         os.environ.setdefault("NCCL_DEBUG_FILE", "/dev/stderr")      # keep stdout to the one JSON line (NCCL prints its version there)
         cpmusic.dist.init_from_env("nccl")
