@@ -182,7 +182,9 @@ class TransformerEncoder(nn.Module):
             TransformerEncoderLayer(d_model, n_heads, feed_forward_dimensions, dropout, query_dimensions) for _ in range(n_layers)])
         self.norm = nn.LayerNorm(d_model)
         self.compute_dtype = compute_dtype
-        self.attn_impl = 0            # 0 auto | 1 simt | 2 tcgen05  (cpm_linattn_fwd `impl`)
+        # 0 auto | 1 simt | 2 tcgen05, one CTA per (batch, head, segment) | 3 tcgen05 chunk-parallel (cpm_linattn_fwd `impl`);
+        # CPM_LINATTN_IMPL overrides the default for whole-run A/B measurements (explicit 2 / 3 need bf16 and L % 128 == 0)
+        self.attn_impl = int(_os.environ.get("CPM_LINATTN_IMPL", "0"))
         self._cache = PackCache()
 
     # ---- fused path used by the CP model (stays in compute dtype) -------------------------

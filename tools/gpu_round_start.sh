@@ -12,3 +12,5 @@ python bench.py > gpurun_out/bench_1gpu.json 2> gpurun_out/bench_1gpu.err && tai
 ncu --metrics gpu__time_duration.sum --clock-control none --profile-from-start off --launch-skip 105800 -c 9000 --csv \
     --log-file gpurun_out/launches_update_phase.csv python bench.py --steps 1 --warmup 3 --no-cpu-baseline --profile-step \
     > gpurun_out/ncu_launches.log 2>&1; echo "ncu exit $?"
+# whole-bench A/B of the single-pass attention kernels (only meaningful if the micro-benchmark above favours impl 2)
+CPM_LINATTN_IMPL=2 python bench.py --no-cpu-baseline > gpurun_out/bench_1gpu_impl2.json 2> gpurun_out/bench_1gpu_impl2.err && tail -c 600 gpurun_out/bench_1gpu_impl2.json
