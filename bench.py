@@ -111,11 +111,12 @@ class ClockSampler:
 # --------------------------------------------------------------------------------------------
 # CPU arm: the oracle port of the reference path, bounded sample
 # --------------------------------------------------------------------------------------------
-def cpu_reference_sample(roll_steps=6, upd_seqs=2, upd_len=256, seed=0):
-    """Times, on the host cores, (a) batch-32 recurrent rollout steps with host numpy sampling as
-    the reference does (testing-no-type-cp.py:157-167) and (b) a teacher-forced fwd+bwd+Adam update
-    (actor with the C causal-product clone + critic) on upd_seqs x upd_len tokens; returns the
-    tokens/s of one PPO iteration extrapolated from the per-token costs."""
+def cpu_reference_sample(roll_steps=6, upd_seqs=4, upd_len=512, seed=0):
+    """Times, on the host cores, (a) batched recurrent rollout steps with host numpy sampling as
+    the reference does (testing-no-type-cp.py:157-167), (b) a teacher-forced value pass + fwd + bwd
+    (actor with the C causal-product clone + critic) on upd_seqs x upd_len tokens and (c) one Adam
+    step per network; returns the tokens/s of one PPO iteration of the bench workload extrapolated
+    from the per-token costs plus the once-per-iteration optimizer cost."""
     import numpy as np
     import torch
     from oracle import model_oracle as mo, sampling_oracle as so
@@ -146,27 +147,39 @@ def cpu_reference_sample(roll_steps=6, upd_seqs=2, upd_len=256, seed=0):
                 nxt[b] = so.forward_output_sampling({a: logits[i][b].numpy() for i, a in enumerate(so.ATTRS)}, rng)
             cur = torch.from_numpy(nxt)
         t_roll = (time.perf_counter() - t0) / (roll_steps * B)                   # s per generated token
-    # (b) update
+    # (b) update: forward + backward cost per token, and the two Adam steps once per iteration (the GPU arm accumulates the
+    #     whole iteration's minibatches into ONE optimizer step per network, so their cost must not be charged per sample token)
     x = torch.stack([torch.randint(0, n, (upd_seqs, upd_len)) for n in VOCAB], -1)
     opt_a = torch.optim.Adam(actor.parameters(), lr=1e-5)
     opt_c = torch.optim.Adam(critic.parameters(), lr=1e-5)
-    t0 = time.perf_counter()
-    with torch.no_grad():
-        critic.value_produce(x)                                                   # rollout-time critic values
-    logits = actor.forward_output(actor.forward_hidden(x))
-    lp = sum(torch.log_softmax(l, -1).gather(-1, x[..., i:i + 1]).mean() for i, l in enumerate(logits))
-    opt_a.zero_grad()
-    (-lp).backward()
-    opt_a.step()
-    v = critic.value_produce(x)
-    opt_c.zero_grad()
-    (v ** 2).mean().backward()
+
+    def fwd_bwd(xs):
+        with torch.no_grad():
+            critic.value_produce(xs)                                              # rollout-time critic values
+        logits = actor.forward_output(actor.forward_hidden(xs))
+        lp = sum(torch.log_softmax(l, -1).gather(-1, xs[..., i:i + 1]).mean() for i, l in enumerate(logits))
+        opt_a.zero_grad()
+        (-lp).backward()
+        v = critic.value_produce(xs)
+        opt_c.zero_grad()
+        (v ** 2).mean().backward()
+
+    fwd_bwd(x)                                                                    # warm-up at full sample size: primitive creation,
+    opt_a.step()                                                                  # allocator growth, Adam state
     opt_c.step()
-    t_upd = (time.perf_counter() - t0) / (upd_seqs * upd_len)
-    tokens_per_s = 1.0 / (t_roll + t_upd)
+    t0 = time.perf_counter()
+    fwd_bwd(x)
+    t_fb = (time.perf_counter() - t0) / (upd_seqs * upd_len)
+    t0 = time.perf_counter()
+    opt_a.step()
+    opt_c.step()
+    t_adam = time.perf_counter() - t0                                             # s per iteration
+    tokens_iter = SONGS_PER_GPU * ROLLOUT_LEN
+    tokens_per_s = tokens_iter / (tokens_iter * (t_roll + t_fb) + t_adam)
     return {"value": tokens_per_s, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": f"{roll_steps} batch-{B} recurrent steps + numpy sampling ({t_roll * 1e3:.2f} ms/token) and one actor+critic "
-                      f"fwd+bwd+Adam on {upd_seqs}x{upd_len} tokens ({t_upd * 1e3:.2f} ms/token), oracle port with C/OpenMP "
+            "sample": f"{roll_steps} batch-{B} recurrent steps + numpy sampling ({t_roll * 1e3:.2f} ms/token), one actor+critic "
+                      f"value pass + fwd + bwd on {upd_seqs}x{upd_len} tokens ({t_fb * 1e3:.2f} ms/token) and one Adam step per network "
+                      f"({t_adam:.2f} s, charged once per {tokens_iter}-token iteration); oracle port with C/OpenMP "
                       f"causal_product ({num_threads()} OMP threads), fp32"}
 
 
