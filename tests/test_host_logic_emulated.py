@@ -85,3 +85,107 @@ def test_module_level_gpu_tests_on_stand_ins(emu, golden, name):
     fn = getattr(tm, name)
     have = {"cuda": CPU, "cpm": emu, "golden": golden}
     fn(**{p: have[p] for p in inspect.signature(fn).parameters})
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# The reference's own training-script classes, UNMODIFIED, driving the product's models (CPU stand-ins for the kernels).
+# Needs the reference tree, which only exists in the build container.
+needs_reference = pytest.mark.skipif(not os.path.isdir("/root/reference/ppo_policy"), reason="reference tree only exists in the build container")
+
+
+def _golden_tools():
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import make_ref_golden as mk
+    import ref_weights
+    return mk, ref_weights
+
+
+@needs_reference
+def test_reference_dqn_class_drives_the_product_models(emu, golden, monkeypatch):
+    """``DQN.update`` lifted from IRL_dqn_train.py, with ``eval_net`` / ``target_net`` = cpmusic.LinearTransformer: the four
+    updates reproduce the losses the same class produced on the reference's own networks."""
+    import contextlib
+    import io
+    import numpy as np
+    from tqdm import tqdm
+    import torch.nn as nn
+    import torch.nn.functional as F
+    mk, rw = _golden_tools()
+    ns = dict(torch=torch, nn=nn, F=F, np=np, N_ACTIONS=25, GAMMA=0.95, Target_update=50, object=object, tqdm=tqdm,
+              wandb=mk._Obj(log=lambda *a, **k: None), NUM_SONGS=1500, EPISODES=50, num=0)
+    DQN = mk.lift_class("/root/reference/dqn_policy/IRL_dqn_train.py", "DQN", ns)
+    ev = emu.LinearTransformer(twins.VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    tg = emu.LinearTransformer(twins.VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    ev.load_state_dict(twins._weights(twins.VOCAB_DQN, 14))
+    tg.load_state_dict(twins._weights(twins.VOCAB_DQN, 15))
+    agent = object.__new__(DQN)
+    agent.eval_net, agent.target_net = ev.train(), tg.train()
+    agent.optim = torch.optim.Adam(ev.parameters(), lr=0.01)
+    agent.scheduler = torch.optim.lr_scheduler.MultiStepLR(agent.optim, milestones=[20, 40], gamma=0.1)
+    agent.target_count = agent.cnt_update = agent.record_fore_epoch = 0
+    agent.mse_val = agent.ce_val = agent.total_val = 0.0
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    rows, prev = [], (0.0, 0.0, 0.0)
+    for b in rw.rl_update_batches(4, twins.VOCAB_DQN, seed=95):
+        tr = {"state": b["state"], "nextstate": b["nextstate"], "action": b["action"], "reward": b["reward"], "done": b["done"]}
+        with contextlib.redirect_stdout(io.StringIO()):
+            agent.update(tr, {"state": b["state"], "nextstate": b["nextstate"]}, b["mask"], False, 0)
+        cur = (agent.mse_val, agent.ce_val, agent.total_val)
+        rows.append([c - p for c, p in zip(cur, prev)])
+        prev = cur
+    np.testing.assert_allclose(np.asarray(rows), golden("ref_rl")["loop_dqn_mse_ce_total"], rtol=3e-4, atol=3e-4)
+    assert torch.equal(agent.choose_action(b["state"][:1], None), emu.rl.dqn_choose_action(ev, b["state"][:1]))
+
+
+@needs_reference
+def test_reference_ppo_class_drives_the_product_models(emu, golden):
+    """``PPO.choose_action`` / ``select_udpate`` / ``update_policy`` and the script's own AgentMemory / ExpertMemory lifted
+    from ppo_train.py, with ``actor_net`` / ``critic_net`` = cpmusic.Actor_Transformer / Critic_Transformer."""
+    import contextlib
+    import io
+    import numpy as np
+    from tqdm import tqdm
+    import torch.nn as nn
+    import torch.nn.functional as F
+    mk, rw = _golden_tools()
+    gr = golden("ref_rl")
+    actor = emu.Actor_Transformer(twins.VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    critic = emu.Critic_Transformer(twins.VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    actor.load_state_dict(twins._weights(twins.VOCAB_PPO, 16, variant="actor"))
+    critic.load_state_dict(twins._weights(twins.VOCAB_PPO, 17, critic=True))
+    value_losses = []
+
+    def recording_mse(a, b, *args, **kw):
+        v = F.mse_loss(a, b, *args, **kw)
+        value_losses.append(float(v.detach()))
+        return v
+
+    script = "/root/reference/ppo_policy/ppo_train.py"
+    ns = dict(torch=torch, nn=nn, F=mk._Obj(mse_loss=recording_mse), np=np, device=CPU, N_ACTIONS=25, tqdm=tqdm, Load_Pretrain=False,
+              object=object, BUFFER_SIZE=30, N_STATES=50, N_FEATURES=6)
+    PPO = mk.lift_class(script, "PPO", ns)
+    abuf, ebuf = mk.lift_class(script, "AgentMemory", ns)(), mk.lift_class(script, "ExpertMemory", ns)()
+    rw.fill_ppo_buffers(abuf, ebuf, rw.rl_update_batches(1, twins.VOCAB_PPO, seed=96)[0])
+    ppo = object.__new__(PPO)
+    ppo.actor_net, ppo.critic_net = actor.train(), critic.train()
+    ppo.actor_optim = torch.optim.Adam(actor.parameters(), lr=0.01)
+    ppo.critic_optim = torch.optim.Adam(critic.parameters(), lr=0.01)
+    ns.update(AgentBuffer=abuf, ExpertBuffer=ebuf, Agent=ppo)
+    states = abuf.get()["states"]
+    with torch.no_grad():                                              # the script's own read-outs == the fused ones
+        act, logp = ppo.choose_action(states[:1])
+        act2, logp2 = emu.rl.ppo_choose_action(actor, states[:1])
+        assert torch.equal(act, act2)
+        torch.testing.assert_close(logp, logp2, rtol=1e-5, atol=1e-5)
+        act, logp, value = ppo.select_udpate(states)
+        act2, logp2 = emu.rl.ppo_select_update(actor, states)
+        assert torch.equal(act, act2)
+        torch.testing.assert_close(logp, logp2, rtol=1e-5, atol=1e-5)
+    returns = ppo.calculate_returns(abuf.get()["rewards"], 0.99)
+    adv = ppo.calculate_advantages(returns, abuf.get()["values"])
+    actor_losses = []
+    for _ in range(3):
+        with contextlib.redirect_stdout(io.StringIO()), contextlib.redirect_stderr(io.StringIO()):
+            actor_losses.append(ppo.update_policy(1, 0.2, adv, returns))
+    np.testing.assert_allclose(actor_losses, gr["loop_ppo_actor_loss"], rtol=3e-4, atol=3e-4)
+    np.testing.assert_allclose(value_losses, gr["loop_ppo_value_loss"], rtol=3e-3, atol=3e-4)
