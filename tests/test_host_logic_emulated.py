@@ -189,3 +189,77 @@ def test_reference_ppo_class_drives_the_product_models(emu, golden):
             actor_losses.append(ppo.update_policy(1, 0.2, adv, returns))
     np.testing.assert_allclose(actor_losses, gr["loop_ppo_actor_loss"], rtol=3e-4, atol=3e-4)
     np.testing.assert_allclose(value_losses, gr["loop_ppo_value_loss"], rtol=3e-3, atol=3e-4)
+
+
+@needs_reference
+def test_reference_train_and_generation_functions_drive_the_product_model(emu, golden, tmp_path, monkeypatch):
+    """``train()`` from agent_pretrain.py and ``inference_from_scratch`` from testing-no-type-cp.py, lifted unmodified, with
+    ``TransformerModel`` / ``model`` = the cpmusic classes: the training loop logs the loss curve it logged on the
+    reference's own model; the generation loop runs to its bar condition on the product's recurrent surface."""
+    import ast
+    import contextlib
+    import datetime
+    import io
+    import math
+    import pickle
+    import time
+    import numpy as np
+    import torch.nn as nn
+    import torch.nn.functional as F
+    mk, rw = _golden_tools()
+    path = "/root/reference/dqn_policy/agent_pretrain.py"
+    tree = ast.parse(open(path).read())
+    nodes = [n for n in tree.body if isinstance(n, ast.FunctionDef) and n.name in ("network_paras", "train")]
+    losses = []
+
+    class Saver:
+        first = True
+
+        def __init__(self, *a, **k):
+            pass
+
+        def add_summary_msg(self, msg):
+            if Saver.first:
+                Saver.first = False
+                net = sys._getframe(1).f_locals["net"]
+                rw.fill_(net, seed=13)
+
+        def add_summary(self, key, val, *a, **k):
+            if key == "batch loss":
+                losses.append(val)
+                if len(losses) == 10:
+                    raise mk._StopTraining
+
+        def global_step_increment(self):
+            pass
+
+    e2w, w2e = rw.synthetic_dictionary()
+    full = lambda d: {"tempo": d["tempo"], "chord": d["chord"], "bar-beat": d["bar-beat"], "type": {0: "EOS", 1: "Metrical", 2: "Note"},    # noqa: E731
+                      "pitch": d["pitch"], "duration": d["duration"], "velocity": d["velocity"]}
+    np.savez(tmp_path / "train_data_linear.npz", **rw.pretrain_corpus())
+    (tmp_path / "dictionary.pkl").write_bytes(pickle.dumps((full(e2w), full(w2e))))
+    (tmp_path / "ckpt").mkdir()
+    product = lambda n_class: emu.TransformerModel(n_class, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)    # noqa: E731
+    ns = dict(torch=torch, nn=nn, F=F, np=np, os=os, sys=sys, math=math, time=time, pickle=pickle, optim=torch.optim, datetime=datetime,
+              clip_grad_norm_=torch.nn.utils.clip_grad_norm_, Saver=Saver, TransformerModel=product, batch_size=4, init_lr=0.0001,
+              path_exp=str(tmp_path / "exp"), path_train_data=str(tmp_path / "train_data_linear.npz"),
+              path_dictionary=str(tmp_path / "dictionary.pkl"))
+    exec(compile(ast.Module(nodes, []), path, "exec"), ns)
+    monkeypatch.setattr(torch.Tensor, "cuda", lambda self, *a, **k: self)
+    monkeypatch.setattr(torch.nn.Module, "cuda", lambda self, *a, **k: self)
+    monkeypatch.chdir(tmp_path)
+    with contextlib.redirect_stdout(io.StringIO()), pytest.raises(mk._StopTraining):
+        ns["train"]()
+    np.testing.assert_allclose(losses, golden("ref_rl")["pre_losses_eval"], rtol=3e-4, atol=3e-4)
+    # generation loop of the reference on the product's recurrent model (device sampler: Philox, not numpy)
+    fn = mk.lift_function("/root/reference/dqn_policy/testing-no-type-cp.py", "inference_from_scratch", dict(np=np, torch=torch))
+    m = emu.LinearTransformer(twins.VOCAB_DQN, False, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    m.load_state_dict(twins._weights(twins.VOCAB_DQN, 11))
+    np.random.seed(3)
+    with contextlib.redirect_stdout(io.StringIO()):
+        res = fn(m.eval(), w2e, 3)
+    bars = 1 + sum(1 for w in res[1:] if w2e["bar-beat"][int(w[2])] == "Bar")
+    assert res.shape[1] == 6 and bars == 3 and tuple(res[0]) == emu.midi.BAR_TOKEN
+    np.random.seed(3)
+    m._sample_step = 0
+    assert np.array_equal(emu.midi.inference_from_scratch(m, w2e, 3), res)       # the product's driver is the same loop
