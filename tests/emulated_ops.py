@@ -6,7 +6,6 @@ onto the module only inside ``emulated()`` by tests, and they say nothing about 
 on the GPU)."""
 import contextlib
 
-import numpy as np
 import torch
 import torch.nn.functional as F
 
@@ -167,4 +166,4 @@ def emulated(cpm):
             setattr(cpm.ops, k, fn)
 
 
-__all__ = ["emulated", "EMULATED", "np"]
+__all__ = ["emulated", "EMULATED"]
