@@ -4,7 +4,7 @@
 #   /usr/local/graft/bin/gpurun --timeout 2400 -- 'bash tools/gpu_round_start.sh'
 set -u
 mkdir -p gpurun_out
-python -m pytest tests -m gpu -q -x --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
+python -m pytest tests -m gpu -q --timeout 900 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest exit $?" | tee -a gpurun_out/pytest_gpu.log
 tail -5 gpurun_out/pytest_gpu.log
 python tools/bench_linattn.py --impl 2 3 --shape "1024x8" --iters 20 > gpurun_out/linattn_impl2_vs_cp.jsonl 2>gpurun_out/linattn_impl2_vs_cp.err
 cat gpurun_out/linattn_impl2_vs_cp.jsonl
