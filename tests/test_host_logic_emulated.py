@@ -263,3 +263,87 @@ def test_reference_train_and_generation_functions_drive_the_product_model(emu, g
     np.random.seed(3)
     m._sample_step = 0
     assert np.array_equal(emu.midi.inference_from_scratch(m, w2e, 3), res)       # the product's driver is the same loop
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# Data parallel on the product model, world_size 2 over gloo: rank shards of one batch, the loss defined over the
+# GLOBAL mask sum, gradients summed by BucketedGradAllReduce == the single-process full-batch gradients.
+def _group_masked_ce(logits, targets, mask, seg, group=None):
+    """Stand-in with the contract of ops.masked_ce under a process group: the returned value is the GLOBAL loss, the gradient
+    is this rank's tokens' share of it (numerator local, denominator global)."""
+    import torch.distributed as dist
+    import torch.nn.functional as F
+    A = len(seg) - 1
+    l2 = logits.reshape(-1, logits.shape[-1]).float()
+    tg, m = targets.reshape(-1, A), mask.reshape(-1).float()
+    ce = torch.stack([F.cross_entropy(l2[:, seg[a]:seg[a + 1]], tg[:, a], reduction="none") for a in range(A)], -1)
+    num, msum = (ce * m[:, None]).sum(0), m.sum()
+    if group is None:
+        return num / msum
+    packed = torch.cat([num.detach(), msum[None]])
+    dist.all_reduce(packed, group=group)
+    local = num / packed[A]
+    return local + (packed[:A] / packed[A] - local).detach()
+
+
+def _dp_model_worker(rank, world, port, q):
+    import numpy as np
+    import torch.distributed as dist
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path[:0] = [root, os.path.join(root, "tests"), os.path.join(root, "tests", "golden")]
+    import cpmusic
+    import emulated_ops as emo
+    import ref_weights
+    from oracle import model_oracle as mo
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    torch.set_num_threads(2)
+    vocab, small = [56, 135, 18, 87, 18, 25], dict(d_model=128, n_layer=2, n_head=2, d_inner=256)
+    o = mo.OracleCPModel(vocab, **small)
+    ref_weights.fill_(o, seed=19)
+    g = np.load(os.path.join(root, "tests", "golden", "ref_model.npz"))
+    x, y, mask = (torch.from_numpy(g[k]) for k in ("dqn_x", "dqn_y", "dqn_mask"))             # 3 ragged sequences
+    with emo.emulated(cpmusic):
+        cpmusic.ops.masked_ce = _group_masked_ce
+        m = cpmusic.LinearTransformer(vocab, True, compute_dtype=torch.float32, dropout=0.0, **small)
+        m.load_state_dict(o.state_dict())
+        m.train()
+        red = cpmusic.dist.BucketedGradAllReduce(m.parameters(), bucket_mb=0.25)           # several buckets
+        cpmusic.dist.init_from_env("gloo")
+        red.attach()
+        lo, hi = cpmusic.dist.shard_range(x.shape[0], rank, world)                          # 2 + 1 sequences
+        red.zero_grad()
+        losses = torch.stack(m.train_step(x[lo:hi], y[lo:hi], mask[lo:hi], group=dist.group.WORLD))
+        (losses.sum() / 6).backward()
+        red.finish()
+        got = {n: p.grad.clone() for n, p in m.named_parameters() if p.grad is not None}
+        # single process, whole batch
+        full = cpmusic.LinearTransformer(vocab, True, compute_dtype=torch.float32, dropout=0.0, **small)
+        full.load_state_dict(o.state_dict())
+        full.train()
+        ref_losses = torch.stack(full.train_step(x, y, mask))
+        (ref_losses.sum() / 6).backward()
+    ok = torch.allclose(losses, ref_losses, atol=1e-5) and len(red.buckets) > 1
+    worst = 0.0
+    for n, p in full.named_parameters():
+        if p.grad is None:
+            ok = ok and float(got[n].abs().max()) == 0.0 if n in got else ok
+            continue
+        err = float((got[n] - p.grad).abs().max())
+        worst = max(worst, err)
+        ok = ok and err <= 1e-5 + 1e-4 * float(p.grad.abs().max())
+    q.put((rank, bool(ok), worst))
+    dist.destroy_process_group()
+
+
+def test_data_parallel_product_model_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 23
+    procs = [ctx.Process(target=_dp_model_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=300) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert [r[:2] for r in res] == [(0, True), (1, True)], res
