@@ -155,7 +155,10 @@ EMULATED = dict(cp_embed=cp_embed, add_pe=add_pe, ln_residual=ln_residual, gelu_
 
 @contextlib.contextmanager
 def emulated(cpm):
-    """Patches the stand-ins onto ``cpm.ops`` for the duration of the block."""
+    """Patches the stand-ins onto ``cpm.ops`` for the duration of the block.  Refuses to do so where a GPU exists: there the
+    real kernels are what gets tested, and nothing may stand in for them."""
+    if torch.cuda.is_available():
+        raise RuntimeError("emulated_ops is for GPU-less hosts only; on a GPU box run the -m gpu tests against the real kernels")
     saved = {k: getattr(cpm.ops, k) for k in EMULATED}
     try:
         for k, fn in EMULATED.items():

@@ -15,6 +15,7 @@ import emulated_ops  # noqa: E402
 import test_gpu_ref_golden as twins  # noqa: E402
 
 CPU = torch.device("cpu")
+pytestmark = pytest.mark.skipif(torch.cuda.is_available(), reason="GPU present: the real kernels are tested by -m gpu, nothing stands in for them")
 
 
 @pytest.fixture()
