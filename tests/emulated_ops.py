@@ -22,10 +22,11 @@ def cp_embed(idx, tables, dtype=torch.bfloat16):
 
 
 def add_pe(x, pe, L, pos_offset=0, pos_dev=None, p_drop=0.0):
-    assert p_drop == 0.0 and pos_dev is None, "emulation covers the deterministic path"
+    assert p_drop == 0.0, "emulation covers the deterministic path"
     d = x.shape[-1]
     rows = x.numel() // d
-    pos = (torch.arange(rows) % L) + pos_offset                         # row r of the flattened (.., L, d) tensor
+    base = int(pos_dev[0]) if pos_dev is not None else pos_offset       # the kernel reads the device-side step counter
+    pos = ((torch.arange(rows) % L) + base).clamp(max=pe.reshape(-1, d).shape[0] - 1)
     return (x.reshape(rows, d).float() + pe.reshape(-1, d)[pos]).to(x.dtype).view(x.shape)
 
 
@@ -64,7 +65,9 @@ def linattn_step(q, k, v, S, Z, eps=1e-6, **_kw):
 
 def heads_sample(logits, seg, temperature=None, top_p=None, greedy=True, seed=0, seq_base=0, step=0, step_dev=None,
                  want_logp=False, want_entropy=False, tokens_out=None, logp_out=None):
-    assert step_dev is None
+    if step_dev is not None:
+        step = int(step_dev[0])
+    want_logp = want_logp or logp_out is not None
     A = len(seg) - 1
     l2 = logits.reshape(-1, logits.shape[-1]).float()
     rows = l2.shape[0]
@@ -142,6 +145,16 @@ def dqn_td_loss(q_logits, next_logits, action, reward, done, seg, n_actions=25, 
     return loss, None
 
 
+def rollout_advance(tokens, history_tok, vals, history_f, step_dev, max_steps):
+    step = int(step_dev[0])
+    if step < max_steps:
+        if history_tok is not None:
+            history_tok[step].copy_(tokens.view_as(history_tok[step]))
+        if history_f is not None:
+            history_f[step].copy_(vals.view_as(history_f[step]))
+    step_dev += 1
+
+
 def reward_head(h, u, c, want_scores=False):
     scores = torch.sigmoid(h.float().mean(1) @ u.t() + c)
     return (scores.mean(-1), scores) if want_scores else scores.mean(-1)
@@ -150,7 +163,7 @@ def reward_head(h, u, c, want_scores=False):
 EMULATED = dict(cp_embed=cp_embed, add_pe=add_pe, ln_residual=ln_residual, gelu_dropout=gelu_dropout, colsum=colsum,
                 causal_linear_attention_fused=causal_linear_attention_fused, linattn_step=linattn_step, heads_sample=heads_sample,
                 heads_logp=heads_logp, masked_ce=masked_ce, returns_scan=returns_scan, zscore=zscore, ppo_loss_compat=ppo_loss_compat,
-                dqn_td_loss=dqn_td_loss, reward_head=reward_head)
+                dqn_td_loss=dqn_td_loss, reward_head=reward_head, rollout_advance=rollout_advance)
 
 
 @contextlib.contextmanager

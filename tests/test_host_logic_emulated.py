@@ -348,3 +348,31 @@ def test_data_parallel_product_model_gloo_world2():
     for p in procs:
         p.join(60)
     assert [r[:2] for r in res] == [(0, True), (1, True)], res
+
+
+def test_rollout_engine_host_logic(emu, golden):
+    """RolloutEngine without its CUDA graph (``use_graph=False``) on the stand-ins: device-side step counter driving the
+    positions, history buffers, per-song Philox streams keyed by the GLOBAL song id (shard invariance), greedy roll-out ==
+    teacher-forced argmax on the generated tokens, and ``midi.batched_generate`` on top of it."""
+    import ref_weights
+    m = emu.LinearTransformer(twins.VOCAB_DQN, False, compute_dtype=torch.float32, dropout=0.0, reference_compat=False, **twins.SMALL)
+    m.load_state_dict(twins._weights(twins.VOCAB_DQN, 11))
+    m.eval()
+    init = torch.from_numpy(golden("ref_model")["dqn_x"][:, 0]).repeat(2, 1)[:4]                 # 4 songs
+    full = emu.RolloutEngine(m, 4, 12, greedy=False, true_positions=True, seed=5, seq_base=0, use_graph=False).generate(init, 12)
+    assert full["tokens"].shape == (4, 13, 6) and full["logp"].shape == (4, 12, 6)
+    for lo in (0, 2):                                                    # two "ranks" of two songs each
+        part = emu.RolloutEngine(m, 2, 12, greedy=False, true_positions=True, seed=5, seq_base=lo, use_graph=False).generate(init[lo:lo + 2], 12)
+        assert torch.equal(part["tokens"], full["tokens"][lo:lo + 2])
+        torch.testing.assert_close(part["logp"], full["logp"][lo:lo + 2])
+    greedy = emu.RolloutEngine(m, 4, 10, greedy=True, true_positions=True, use_graph=False).generate(init, 10)["tokens"]
+    par = emu.LinearTransformer(twins.VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    par.load_state_dict(m.state_dict())
+    with torch.no_grad():
+        logits = par.eval().forward_output(par.forward_hidden(greedy[:, :-1]))
+    assert torch.equal(torch.stack([lg.argmax(-1) for lg in logits], -1), greedy[:, 1:])
+    _, w2e = ref_weights.synthetic_dictionary()
+    songs = emu.midi.batched_generate(m, w2e, 3, n_songs=3, max_tokens=40, seed=7, use_graph=False)
+    for s in songs:
+        bars = 1 + sum(1 for w in s[1:] if w2e["bar-beat"][int(w[2])] == "Bar")
+        assert tuple(s[0]) == emu.midi.BAR_TOKEN and (len(s) == 40 or bars == 3)
