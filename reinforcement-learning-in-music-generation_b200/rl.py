@@ -158,3 +158,109 @@ class DiscriminatorHead(torch.nn.Module):
 
     def forward(self, hidden, masks=None):
         return self.score_classifier(hidden.to(self.score_classifier[0].weight.dtype).mean(dim=1))      # bf16 body output -> fp32 masters
+
+
+# ------------------------------------------------------------------------------------------ the scripts' policy classes
+class PPO:
+    """The ``PPO`` class of ppo_train.py:217-416 with the same method names and return values, on the fused read-outs and
+    loss kernels: ``choose_action`` / ``select_udpate`` without the Python loops over positions and batch elements,
+    ``calculate_returns`` / ``calculate_advantages`` as device scans, ``update_policy`` with the clipped-surrogate kernel.
+    The script's module globals become constructor arguments: the two networks (it builds them itself, :219-220), the two
+    buffers (``AgentBuffer`` / ``ExpertBuffer``, :428-429) and ``init_lr`` (:58).  ``compat=True`` keeps the reference's
+    arithmetic exactly.  ``last_policy_loss`` / ``last_ce_loss`` / ``last_value_loss`` hold the most
+    recent epoch's terms as device scalars (the script only prints them)."""
+
+    def __init__(self, actor_net, critic_net, agent_buffer=None, expert_buffer=None, lr: float = 0.01, n_actions: int = N_ACTIONS,
+                 compat: bool = True, fused_optim: bool = False):
+        self.actor_net, self.critic_net = actor_net, critic_net
+        self.agent_buffer, self.expert_buffer = agent_buffer, expert_buffer
+        self.n_actions, self.compat = n_actions, compat
+        self.actor_optim = torch.optim.Adam(actor_net.parameters(), lr=lr, fused=fused_optim)
+        self.critic_optim = torch.optim.Adam(critic_net.parameters(), lr=lr, fused=fused_optim)
+        self.last_policy_loss = self.last_ce_loss = self.last_value_loss = None
+
+    def choose_action(self, state_x):
+        """state_x (1,L,A) -> (action (n_actions,A) int64, log_prob (n_actions,A)); ppo_train.py:251-290."""
+        return ppo_choose_action(self.actor_net, state_x, self.n_actions, self.compat)
+
+    def select_udpate(self, state_x):
+        """state_x (B,L,A) -> (action, log_prob, value_state (B,1)); the reference's spelling and its last-batch-element
+        return (ppo_train.py:293-346)."""
+        action, logp = ppo_select_update(self.actor_net, state_x, self.n_actions, self.compat)
+        return action, logp, self.critic_net.value_produce(state_x)
+
+    def calculate_returns(self, rewards, discount_factor, normalize=True):
+        return calculate_returns_compat(rewards, discount_factor, normalize)
+
+    def calculate_advantages(self, returns, values, normalize=True):
+        return calculate_advantages_compat(returns, values, normalize)
+
+    def update_policy(self, ppo_steps, ppo_clip, advantages, returns):
+        """ppo_train.py:365-416: ``ppo_steps`` epochs over the whole agent buffer; actor loss = surrogate + mean of the six CE
+        terms of the actor on (agent states -> expert states, int64 mask); critic loss = ``mse(returns, V).sum()``.
+        Returns the mean actor loss as a Python float like the reference."""
+        agent_all, expert_all = self.agent_buffer.get(), self.expert_buffer.get()
+        log_actions = agent_all["log_actions"].detach()
+        advantages, returns = advantages.detach(), returns.detach()
+        total = torch.zeros((), device=returns.device)
+        for _ in range(ppo_steps):
+            states = agent_all["states"]
+            _, new_logp, value_pred = self.select_udpate(states)
+            self.last_policy_loss = ppo_policy_loss_compat(new_logp, log_actions, advantages, ppo_clip)
+            ce = self.actor_net.train_step(states, expert_all["states"], expert_all["mask_state"])
+            self.last_ce_loss = sum(ce) / len(ce)
+            actor_loss = self.last_policy_loss + self.last_ce_loss
+            self.last_value_loss = value_loss_compat(returns, value_pred)
+            self.actor_optim.zero_grad()
+            actor_loss.backward()
+            self.actor_optim.step()
+            self.critic_optim.zero_grad()
+            self.last_value_loss.backward()
+            self.critic_optim.step()
+            total += actor_loss.detach()
+        return float(total / ppo_steps)
+
+
+class DQN:
+    """The ``DQN`` class of IRL_dqn_train.py:209-345 with the same method names: ``choose_action`` (greedy tokens at positions
+    [0,-1,...,-24]) and ``update`` (target-network sync every ``target_update`` calls, fused TD kernel over both networks'
+    logits, ``alpha*MSE + (1-alpha)*CE``, Adam + MultiStepLR([20,40]) stepped per update).  Script globals (``Target_update``,
+    ``GAMMA``, ``init_lr``) are constructor arguments; the running sums ``mse_val`` / ``ce_val`` / ``total_val`` and
+    ``cnt_update`` are kept like the script's, as device scalars (no ``.item()`` per update)."""
+
+    def __init__(self, eval_net, target_net, lr: float = 0.01, target_update: int = 50, gamma: float = 0.95, alpha: float = 0.3,
+                 n_actions: int = N_ACTIONS, compat: bool = True, fused_optim: bool = False):
+        self.eval_net, self.target_net = eval_net, target_net
+        self.target_update, self.gamma, self.alpha, self.n_actions, self.compat = target_update, gamma, alpha, n_actions, compat
+        self.optim = torch.optim.Adam(eval_net.parameters(), lr=lr, fused=fused_optim)
+        self.scheduler = torch.optim.lr_scheduler.MultiStepLR(self.optim, milestones=[20, 40], gamma=0.1)
+        self.target_count = self.cnt_update = 0
+        dev = next(eval_net.parameters()).device
+        self.mse_val, self.ce_val, self.total_val = (torch.zeros((), device=dev) for _ in range(3))
+
+    def choose_action(self, x, target=None):
+        return dqn_choose_action(self.eval_net, x, self.n_actions, self.compat)
+
+    def update(self, agent_transition, expert_transition, mask_next_states, update_flag=False, epoch=0):
+        """-> (MSEloss, CEloss, total_loss) of this update as device scalars."""
+        if self.target_count % self.target_update == 0:
+            self.target_net.load_state_dict(self.eval_net.state_dict())
+        self.target_count += 1
+        dev = self.mse_val.device
+        state = agent_transition["state"].long().to(dev)
+        next_state = agent_transition["nextstate"].long().to(dev)
+        mse = dqn_td_loss(self.eval_net, self.target_net, state, next_state, agent_transition["action"].long().to(dev),
+                          agent_transition["reward"].float().to(dev), agent_transition["done"].to(dev), self.gamma, self.n_actions,
+                          self.compat)
+        ce = self.eval_net.train_step(state, expert_transition["nextstate"].long().to(dev), mask_next_states.to(dev))
+        ce = sum(ce) / len(ce)
+        total = self.alpha * mse + (1 - self.alpha) * ce
+        self.optim.zero_grad()
+        total.backward()
+        self.optim.step()
+        self.scheduler.step()
+        self.cnt_update += 1
+        self.mse_val += mse.detach()
+        self.ce_val += ce.detach()
+        self.total_val += total.detach()
+        return mse.detach(), ce.detach(), total.detach()

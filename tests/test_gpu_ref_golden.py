@@ -250,3 +250,39 @@ def test_ppo_update_loop_vs_reference_run(cuda, cpm, golden):
     _cmp(torch.tensor(value_losses[:1]), gr["loop_ppo_value_loss"][:1], 2e-3, 2e-4, "epoch 0 value loss")
     _cmp(torch.tensor(actor_losses), gr["loop_ppo_actor_loss"], 5e-2, 3e-2, f"actor losses {actor_losses}")
     _cmp(torch.tensor(value_losses), gr["loop_ppo_value_loss"], 5e-2, 8e-2, f"value losses {value_losses}")
+
+
+def test_policy_classes_vs_reference_run(cuda, cpm, golden):
+    """``cpmusic.rl.PPO`` / ``cpmusic.rl.DQN`` (the scripts' classes on the fused kernels, same method names) against the losses
+    the reference's own classes produced: three ``update_policy`` epochs, four ``update`` calls."""
+    gr = golden("ref_rl")
+    actor = cpm.Actor_Transformer(VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    critic = cpm.Critic_Transformer(VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    actor.load_state_dict(_weights(VOCAB_PPO, 16, variant="actor"))
+    critic.load_state_dict(_weights(VOCAB_PPO, 17, critic=True))
+    abuf, ebuf = cpm.data.AgentMemory(30, device=cuda), cpm.data.ExpertMemory(30, device=cuda)
+    ref_weights.fill_ppo_buffers(abuf, ebuf, ref_weights.rl_update_batches(1, VOCAB_PPO, seed=96)[0])
+    ppo = cpm.rl.PPO(actor.to(cuda).train(), critic.to(cuda).train(), abuf, ebuf, lr=0.01)
+    returns = ppo.calculate_returns(abuf.get()["rewards"], 0.99)
+    adv = ppo.calculate_advantages(returns, abuf.get()["values"])
+    actor_losses, value_losses = [], []
+    for _ in range(3):
+        actor_losses.append(ppo.update_policy(1, 0.2, adv, returns))
+        value_losses.append(ppo.last_value_loss.item())
+    _cmp(torch.tensor(actor_losses), gr["loop_ppo_actor_loss"], 5e-2, 3e-2, f"actor losses {actor_losses}")
+    _cmp(torch.tensor(value_losses), gr["loop_ppo_value_loss"], 5e-2, 8e-2, f"value losses {value_losses}")
+    act, logp = ppo.choose_action(abuf.get()["states"][:1])
+    assert act.shape == (25, 6) and logp.shape == (25, 6)
+
+    ev = cpm.LinearTransformer(VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    tg = cpm.LinearTransformer(VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **SMALL)
+    ev.load_state_dict(_weights(VOCAB_DQN, 14))
+    tg.load_state_dict(_weights(VOCAB_DQN, 15))
+    dqn = cpm.rl.DQN(ev.to(cuda).train(), tg.to(cuda).train(), lr=0.01)
+    rows = []
+    for b in ref_weights.rl_update_batches(4, VOCAB_DQN, seed=95):
+        tr = {"state": b["state"], "nextstate": b["nextstate"], "action": b["action"], "reward": b["reward"], "done": b["done"]}
+        rows.append([t.item() for t in dqn.update(tr, {"state": b["state"], "nextstate": b["nextstate"]}, b["mask"])])
+    _cmp(torch.tensor(rows), gr["loop_dqn_mse_ce_total"], 5e-2, 3e-2, f"DQN loss curve {rows}")
+    _cmp(dqn.total_val, gr["loop_dqn_mse_ce_total"][:, 2].sum(), 1e-1, 3e-2, "running total like the script's total_val")
+    assert dqn.cnt_update == 4 and dqn.choose_action(b["state"][:1].to(cuda)).shape == (25, 6)

@@ -376,3 +376,37 @@ def test_rollout_engine_host_logic(emu, golden):
     for s in songs:
         bars = 1 + sum(1 for w in s[1:] if w2e["bar-beat"][int(w[2])] == "Bar")
         assert tuple(s[0]) == emu.midi.BAR_TOKEN and (len(s) == 40 or bars == 3)
+
+
+def test_policy_classes(emu, golden):
+    twins.test_policy_classes_vs_reference_run(CPU, emu, golden)
+
+
+def test_policy_classes_tight(emu, golden):
+    """The same classes at CPU-fp32 tolerances (the shared body above carries the GPU tolerances)."""
+    import numpy as np
+    import ref_weights
+    gr = golden("ref_rl")
+    ev = emu.LinearTransformer(twins.VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    tg = emu.LinearTransformer(twins.VOCAB_DQN, True, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    ev.load_state_dict(twins._weights(twins.VOCAB_DQN, 14))
+    tg.load_state_dict(twins._weights(twins.VOCAB_DQN, 15))
+    dqn = emu.rl.DQN(ev.train(), tg.train(), lr=0.01)
+    rows = []
+    for b in ref_weights.rl_update_batches(4, twins.VOCAB_DQN, seed=95):
+        tr = {k: b[k] for k in ("state", "nextstate", "action", "reward", "done")}
+        rows.append([float(t) for t in dqn.update(tr, {"state": b["state"], "nextstate": b["nextstate"]}, b["mask"])])
+    np.testing.assert_allclose(rows, gr["loop_dqn_mse_ce_total"], rtol=3e-4, atol=3e-4)
+    actor = emu.Actor_Transformer(twins.VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    critic = emu.Critic_Transformer(twins.VOCAB_PPO, compute_dtype=torch.float32, dropout=0.0, **twins.SMALL)
+    actor.load_state_dict(twins._weights(twins.VOCAB_PPO, 16, variant="actor"))
+    critic.load_state_dict(twins._weights(twins.VOCAB_PPO, 17, critic=True))
+    abuf, ebuf = emu.data.AgentMemory(30, device="cpu"), emu.data.ExpertMemory(30, device="cpu")
+    ref_weights.fill_ppo_buffers(abuf, ebuf, ref_weights.rl_update_batches(1, twins.VOCAB_PPO, seed=96)[0])
+    ppo = emu.rl.PPO(actor.train(), critic.train(), abuf, ebuf, lr=0.01)
+    returns = ppo.calculate_returns(abuf.get()["rewards"], 0.99)
+    adv = ppo.calculate_advantages(returns, abuf.get()["values"])
+    got = [(ppo.update_policy(1, 0.2, adv, returns), float(ppo.last_value_loss.detach())) for _ in range(3)]
+    np.testing.assert_allclose([g[0] for g in got], gr["loop_ppo_actor_loss"], rtol=3e-4, atol=3e-4)
+    np.testing.assert_allclose([g[1] for g in got], gr["loop_ppo_value_loss"], rtol=3e-3, atol=3e-4)
+    assert ppo.update_policy(2, 0.2, adv, returns) > 0                  # several epochs in one call, mean returned
