@@ -264,7 +264,7 @@ class PPOIteration:
     def _critic_update(self, x, ret, scale, n_mb):
         torch = self.torch
         self.critic.train()
-        self.red_c.zero_grad()
+        self.red_c.zero_grad(n_micro=-(-x.shape[0] // MINIBATCH))      # reduce after the LAST micro-batch's gradients
         vstat = torch.zeros((), device=self.dev)
         for i in range(0, x.shape[0], MINIBATCH):
             sl = slice(i, i + MINIBATCH)
@@ -319,8 +319,8 @@ class PPOIteration:
             values = torch.cat([self.critic.value_per_position(x[i:i + MINIBATCH]) for i in range(0, B, MINIBATCH)], 0)
         adv, ret = cpm.rl.gae(reward, values, dones, torch.zeros(B, device=self.dev), 0.99, 0.95, True, self.group)
         self.actor.train()
-        self.red_a.zero_grad()
         n_mb = B // MINIBATCH
+        self.red_a.zero_grad(n_micro=n_mb)
         scale = 1.0 / (n_mb * self.world)                               # mean over the GLOBAL batch; grads are SUM-reduced
         if OVERLAP_CRITIC:
             ready = torch.cuda.Event()

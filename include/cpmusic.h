@@ -197,6 +197,33 @@ int cpm_colsum(const void *x, int64_t rows, int width, int64_t ld, float *out, f
 
 int cpm_set_rng_base(const uint64_t *device_counter);
 
+/* ---- Dense Linear layers on tcgen05 (csrc/tc_gemm.cu) ---------------------------------------------------------------
+ * Replaces the cuBLAS GEMMs behind every nn.Linear of the reference agent: in_linear (agent_pretrain.py:239,337), ft's
+ * query/key/value/out projections and linear1/linear2 (agent_pretrain.py:244-253 -> fast_transformers AttentionLayer /
+ * TransformerEncoderLayer) and the output heads (agent_pretrain.py:360-375), forward AND backward.
+ * bf16 operands, fp32 accumulation in tensor memory, 2-CTA UMMA (256 x 256 tiles), TMA-fed.  Row-major matrices with a
+ * row stride in elements (multiple of 8) and 16-byte aligned bases; ragged M / N / K are handled by TMA (zero fill on
+ * loads, clipping on stores).
+ *
+ * cpm_gemm_nt:  D[M x N] = epilogue(A[M x K] . B[N x K]^T).   Forward: A = activations, B = weight (out x in).  Data
+ *   gradient: A = dY, B = the transposed weight copy (in x out).  Epilogues:
+ *     CPM_GEMM_EPI_BIAS   D = acc + bias                                   (bias fp32 [N] or NULL)
+ *     CPM_GEMM_EPI_GELU   D = h = bf16(acc + bias);  D2 = dropout(gelu(h))  exact-erf GELU (ft activation='gelu'); D must be
+ *                         dense (ldd == N); the dropout mask is the one cpm_gelu_fwd draws for (seed, rng_offset)
+ *     CPM_GEMM_EPI_DGELU  D = acc * gelu'(aux) * dropout mask               aux = the stored pre-activation h (M x N, dense);
+ *                         same mask as the forward for the same (seed, rng_offset): what cpm_gelu_bwd computes
+ * cpm_gemm_tn:  dW[N x K] += dY[T x N]^T . X[T x K] (fp32, row stride ldw) and, if dbias != NULL, dbias[N] += column sums of
+ *   dY.  ACCUMULATES with fp32 atomics (zero the buffers for a fresh gradient): summation order over token ranges is not
+ *   fixed, so results are reproducible to fp32 rounding, not bitwise. */
+#define CPM_GEMM_EPI_BIAS 0
+#define CPM_GEMM_EPI_GELU 1
+#define CPM_GEMM_EPI_DGELU 2
+int cpm_gemm_nt(const void *A, int64_t lda, const void *B, int64_t ldb, void *D, int64_t ldd, void *D2, int64_t ldd2,
+                int M, int N, int K, const float *bias, int epilogue, const void *aux, int64_t ld_aux,
+                float p_drop, uint64_t seed, uint64_t rng_offset, void *stream);
+int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *dW, int64_t ldw, float *dbias,
+                int T, int N, int K, void *stream);
+
 /* bias + exact-erf GELU + dropout (ft activation='gelu' => F.gelu; K6):
  *     y = drop(gelu(x + bias))   (bias fp32 (d) or NULL)
  * bwd: gx = gy * mask/(1-p) * gelu'(x + bias). */

@@ -58,6 +58,9 @@ SIGNATURES = {
     "cpm_linattn_step_lazy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, _P, c_int, _P]),
     "cpm_reward_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "cpm_set_rng_base": (c_int, [_P]),
+    "cpm_gemm_nt": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, c_int, _P, c_int64,
+                            c_float, c_uint64, c_uint64, _P]),
+    "cpm_gemm_tn": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, _P]),
     "cpm_embed_fwd": (c_int, [_P, _FPP, _IP, _IP, c_int, c_int64, _P, c_int, _P, _P]),
     "cpm_embed_bwd": (c_int, [_P, _P, _FPP, _IP, _IP, c_int, c_int64, c_int, _P]),
     "cpm_add_pe": (c_int, [_P, _P, _P, c_int64, c_int, c_int, c_int, _P, c_int, c_float, c_uint64, c_uint64, c_int, _P]),

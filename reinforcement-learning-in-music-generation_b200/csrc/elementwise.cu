@@ -4,16 +4,12 @@
 #include "cpm_common.cuh"
 
 namespace cpm {
-namespace {
-
 // ---------------------------------------------------------------- device-side RNG base
 // Dropout masks are a pure function of (seed, offset, element).  The host passes `rng_offset` by value, which a CUDA graph
 // would freeze; cpm_set_rng_base installs a device counter that every dropout kernel adds to its offset, so a captured
 // training step draws fresh masks on every replay (the graph itself advances the counter; see graphs.py).
-const unsigned long long *g_rng_base = nullptr;
-__device__ __forceinline__ uint64_t rng_off(uint64_t host_offset, const unsigned long long *base) {
-    return host_offset + (base ? *base : 0ull);
-}
+const unsigned long long *g_rng_base = nullptr;      // declared in cpm_common.cuh (the GEMM epilogues draw from the same streams)
+namespace {
 
 
 
@@ -421,55 +417,7 @@ __global__ void __launch_bounds__(256) colsum_partial_kernel(const T *__restrict
     }
 }
 
-// ---------------------------------------------------------------- bias + exact GELU + dropout
-// erf by Abramowitz & Stegun 7.1.26 (|error| <= 1.5e-7, i.e. exact at fp32-parity tolerance): branch-free,
-// two MUFU ops; e = exp(-x^2/2) is shared with the Gaussian term of the derivative.  (CUDA's erff costs ~2x
-// the instructions; this kernel is instruction-issue bound, ncu: 40 instr/element before, HBM needs <= 14.)
-struct GeluParts { float cdf, e; };            // Phi(x) = 0.5 (1 + erf(x / sqrt 2)),  e = exp(-x^2 / 2)
-__device__ __forceinline__ GeluParts gelu_parts(float x) {
-    const float a = fabsf(x) * 0.70710678118654752f;
-    float t, e;
-    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(t) : "f"(fmaf(0.3275911f, a, 1.f)));
-    asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(x * x * -0.72134752044448170f));      // -0.5 * log2(e)
-    float p = fmaf(1.061405429f, t, -1.453152027f);
-    p = fmaf(p, t, 1.421413741f);
-    p = fmaf(p, t, -0.284496736f);
-    p = fmaf(p, t, 0.254829592f);
-    const float half_erfc = 0.5f * p * t * e;                   // 0.5 * erfc(|x| / sqrt 2)
-    GeluParts r;
-    r.cdf = x >= 0.f ? 1.f - half_erfc : half_erfc;
-    r.e = e;
-    return r;
-}
-// EXACT (the fp32 parity mode): libdevice erff / expf.
-template <bool EXACT> __device__ __forceinline__ float gelu_f(float x) {
-    if (EXACT) return 0.5f * x * (1.f + erff(x * 0.70710678118654752f));
-    return x * gelu_parts(x).cdf;
-}
-template <bool EXACT> __device__ __forceinline__ float dgelu_f(float x) {
-    if (EXACT) return 0.5f * (1.f + erff(x * 0.70710678118654752f)) + x * 0.39894228040143268f * expf(-0.5f * x * x);
-    const GeluParts g = gelu_parts(x);
-    return fmaf(x * 0.39894228040143268f, g.e, g.cdf);
-}
-// Dropout keep-bits for the 16 elements [16*g, 16*g+16): one Philox4x32-10 block, 8 random bits per element,
-// keep iff bits >= thr8 (drop probability quantised to thr8 / 256).
-__device__ __forceinline__ uint32_t dropout_keep16(uint64_t seed, uint64_t offset, uint64_t g, uint32_t thr8) {
-    const uint64_t ctr = offset + g;
-    const uint4 r = Philox::block(make_uint4((uint32_t)ctr, (uint32_t)(ctr >> 32), 0x44523136u /*"DR16"*/, 0u),
-                                  make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-    const uint32_t w[4] = {r.x, r.y, r.z, r.w};
-    uint32_t keep = 0;
-#pragma unroll
-    for (int i = 0; i < 16; ++i) keep |= (((w[i >> 2] >> (8 * (i & 3))) & 0xFFu) >= thr8 ? 1u : 0u) << i;
-    return keep;
-}
-inline uint32_t dropout_threshold8(float p) {
-    if (p <= 0.f) return 0u;
-    double t = (double)p * 256.0 + 0.5;
-    return t >= 255.0 ? 255u : (t < 1.0 ? 1u : (uint32_t)t);
-}
-inline float dropout_scale8(float p) { uint32_t t = dropout_threshold8(p); return t ? 256.0f / (256.0f - (float)t) : 1.0f; }
-
+// ---------------------------------------------------------------- bias + exact GELU + dropout (helpers: cpm_common.cuh)
 // 16 elements per thread and iteration (two 128-bit loads in flight per operand, one Philox block)
 // dbias_partials (BWD only, optional): row (blockIdx * (4096 / d) + (tid * 16) / d) of a [gridDim * 4096 / d][d] fp32 matrix receives
 // this thread's column sums of the stored gx — valid because 4096 % d == 0 makes a thread's 16 columns the same in every iteration.

@@ -1,0 +1,447 @@
+// The Linear layers of the CP transformer (in_linear, q/k/v/out projections, linear1/linear2, the output heads:
+// agent_pretrain.py:239,244-253,337,360-375 and ft's AttentionLayer / TransformerEncoderLayer) as
+// hand-written tcgen05 GEMMs for sm_100a.  bf16 operands, fp32 accumulation in tensor memory.
+//
+//   cpm_gemm_nt :  D[M x N] = epilogue( A[M x K] . B[N x K]^T )        forward (B = W) and data gradient (B = W^T copy)
+//   cpm_gemm_tn :  dW[N x K] += dY[T x N]^T . X[T x K]  (fp32),  db[N] += column sums of dY      weight / bias gradient
+//
+// Both run on CTA PAIRS (cta_group::2): a cluster of two CTAs owns a 256 x 256 output tile; each CTA stages its 128 rows of
+// A and its 128 rows of B per 64-wide K block (32 KB per CTA and stage, 5-stage TMA ring), the leader issues 256 x 256 x 16
+// UMMAs for both SMs, each CTA's tensor memory holds its 128 x 256 half of the accumulator.  Compared with one-CTA tiles the
+// B operand crosses L2 -> shared memory once per pair instead of once per CTA and every UMMA reads half as much shared
+// memory per SM (B300_MICROARCH: 2-CTA mode is what reaches the tensor floor).
+//
+// cpm_gemm_nt is persistent (one pair per 2 SMs, static round-robin over tiles, N-tile fastest so that the A rows of a
+// tile row are re-read from L2) with TWO accumulator stages of 256 TMEM columns: the epilogue of tile i (tcgen05.ld ->
+// registers -> bf16 -> swizzled shared-memory staging -> TMA store) overlaps the UMMAs of tile i+1.
+// Warp roles: 0 TMA producer, 1 UMMA issuer (leader CTA only), 2 TMEM allocator, 4-7 epilogue (TMEM lane quarter = warp % 4).
+// Epilogues: bias; bias + exact-erf GELU + dropout writing BOTH the pre-activation (kept for backward) and the activation
+// (what the gelu kernel did in a second pass over HBM); GELU backward (dgrad of linear2 times gelu'(h) and the regenerated
+// dropout mask, what the gelu backward kernel did).
+//
+// cpm_gemm_tn reads both operands MN-major straight from the row-major activations (no transposes): the contraction index
+// is the token, so a [64 tokens x 64 columns] TMA box is one SWIZZLE_128B MN-major atom column.  The token range is split
+// over clusters (one (tile, split) work item per cluster) and the partial tiles are accumulated into the fp32 gradient with
+// vector red.global.add - which is also the gradient ACCUMULATION across micro-batches.  The bias gradient comes from the
+// same UMMA stream: one extra N = 16 instruction per K step against a constant tile of ones (db = dY^T . 1).
+#include "cpm_common.cuh"
+#include "tc_common.cuh"
+
+namespace cpm {
+namespace {
+using namespace tc;
+
+constexpr int GM_THREADS = 256, GM_NS = 5;
+constexpr uint32_t GM_A_BYTES = 16384, GM_STAGE = 32768;                 // per CTA: A half 128 x 64, B half 128 x 64 (bf16)
+constexpr uint32_t GM_OFF_STG = GM_NS * GM_STAGE;                        // epilogue staging: 4 warps x 2 buffers x [32 rows x 128 B]
+constexpr uint32_t GM_OFF_ONES = GM_OFF_STG;                             // (tn kernel) [64 x 128 B] of bf16 ones instead of staging
+constexpr uint32_t GM_OFF_BAR = GM_OFF_STG + 32768;
+constexpr uint32_t GM_SMEM = GM_OFF_BAR + 256;                           // full[5] empty[5] tfull[2] tempty[2] + TMEM slot
+
+constexpr uint32_t IDESC_NT = idesc_bf16(256, 256, false, false);
+constexpr uint32_t IDESC_TN = idesc_bf16(256, 256, true, true);
+constexpr uint32_t IDESC_TN_ONES = idesc_bf16(256, 16, true, true);
+
+struct GemmNtArgs {
+    const float *bias;                 // [N] fp32 or NULL
+    const __nv_bfloat16 *aux;          // CPM_GEMM_EPI_DGELU: pre-activation h (M x N)
+    int64_t ld_aux;
+    int M, N, K;
+    uint32_t thr8;                     // dropout of the GELU epilogues: 8 random bits per element, 16-element Philox groups
+    float scale;                       //   (the streams of elementwise.cu's gelu kernel: fused and unfused paths draw the same masks)
+    uint64_t seed, rng_offset;
+    const unsigned long long *rng_base;
+};
+
+struct GemmTnArgs {
+    float *dW;                         // [N x K] fp32, accumulated
+    float *dbias;                      // [N] fp32, accumulated (or NULL)
+    int64_t ldw;
+    int T, N, K, splits, kb_per;
+};
+
+__device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
+    asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(p), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
+}
+
+__device__ __forceinline__ void gemm_setup(uint8_t *sm, uint64_t *bars, uint32_t *tmem_slot, int tid, int warp, const CUtensorMap *m0,
+                                           const CUtensorMap *m1, const CUtensorMap *m2, const CUtensorMap *m3) {
+    uint64_t *bar_full = bars, *bar_empty = bars + GM_NS, *bar_tfull = bar_empty + GM_NS, *bar_tempty = bar_tfull + 2;
+    cluster_sync_all();                                   // both CTAs of the pair are resident before anything touches the peer
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        for (int s = 0; s < GM_NS; ++s) { mbar_init(bar_full + s, 2); mbar_init(bar_empty + s, 1); }     // full: one arrival per producer
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, 8); }      // tempty: 4 warps x 2 CTAs
+        fence_barrier_init();
+        tma_prefetch_desc(m0);
+        tma_prefetch_desc(m1);
+        if (m2) tma_prefetch_desc(m2);
+        if (m3) tma_prefetch_desc(m3);
+    }
+    if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+}
+
+// ---------------------------------------------------------------- epilogue value transforms (32 accumulator columns of one row)
+template <int EPI>
+__device__ __forceinline__ void nt_epilogue_half(const uint32_t (&r)[32], const GemmNtArgs &a, int64_t row, int n0, uint64_t rng_offset,
+                                                 uint32_t (&o0)[16], uint32_t (&o1)[16]) {
+    float v[32];
+#pragma unroll
+    for (int j = 0; j < 32; ++j) v[j] = __uint_as_float(r[j]);
+    if (EPI != CPM_GEMM_EPI_DGELU && a.bias) {
+#pragma unroll
+        for (int j = 0; j < 32; j += 4) {
+            if (n0 + j + 4 <= a.N) {
+                const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + j));
+                v[j] += b.x; v[j + 1] += b.y; v[j + 2] += b.z; v[j + 3] += b.w;
+            }
+        }
+    }
+    if (EPI == CPM_GEMM_EPI_BIAS) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) o0[j] = pack_bf16(v[2 * j], v[2 * j + 1]);
+        return;
+    }
+    // ---- GELU forward / backward: two 16-element dropout groups per half
+    uint32_t keep[2] = {0xFFFFu, 0xFFFFu};
+    if (a.thr8) {
+        const uint64_t g = (uint64_t)(row * a.N + n0) >> 4;
+        keep[0] = dropout_keep16(a.seed, rng_offset, g, a.thr8);
+        keep[1] = dropout_keep16(a.seed, rng_offset, g + 1, a.thr8);
+    }
+    if (EPI == CPM_GEMM_EPI_GELU) {
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const uint32_t hb = pack_bf16(v[2 * j], v[2 * j + 1]);          // the stored pre-activation; GELU acts on what backward will read
+            o0[j] = hb;
+            const float h0 = __uint_as_float(hb << 16), h1 = __uint_as_float(hb & 0xFFFF0000u);
+            const float g0 = (keep[j >> 3] >> ((2 * j) & 15)) & 1u ? gelu_f<false>(h0) * a.scale : 0.f;
+            const float g1 = (keep[j >> 3] >> ((2 * j + 1) & 15)) & 1u ? gelu_f<false>(h1) * a.scale : 0.f;
+            o1[j] = pack_bf16(g0, g1);
+        }
+    } else {                                                                 // CPM_GEMM_EPI_DGELU
+        uint32_t hw[16];
+        const __nv_bfloat16 *hp = a.aux + row * a.ld_aux + n0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+            uint4 t = make_uint4(0u, 0u, 0u, 0u);
+            if (row < a.M && n0 + 8 * q + 8 <= a.N) t = __ldg(reinterpret_cast<const uint4 *>(hp + 8 * q));
+            hw[4 * q] = t.x; hw[4 * q + 1] = t.y; hw[4 * q + 2] = t.z; hw[4 * q + 3] = t.w;
+        }
+#pragma unroll
+        for (int j = 0; j < 16; ++j) {
+            const float h0 = __uint_as_float(hw[j] << 16), h1 = __uint_as_float(hw[j] & 0xFFFF0000u);
+            const float g0 = (keep[j >> 3] >> ((2 * j) & 15)) & 1u ? v[2 * j] * dgelu_f<false>(h0) * a.scale : 0.f;
+            const float g1 = (keep[j >> 3] >> ((2 * j + 1) & 15)) & 1u ? v[2 * j + 1] * dgelu_f<false>(h1) * a.scale : 0.f;
+            o0[j] = pack_bf16(g0, g1);
+        }
+    }
+}
+
+__device__ __forceinline__ void stage_half(uint8_t *buf, int lane, int half, const uint32_t (&o)[16]) {
+#pragma unroll
+    for (int q = 0; q < 4; ++q)
+        *reinterpret_cast<uint4 *>(buf + sw128_off(lane, 4 * half + q)) = make_uint4(o[4 * q], o[4 * q + 1], o[4 * q + 2], o[4 * q + 3]);
+}
+
+// =====================================================================================================================
+// D = epilogue(A . B^T), persistent over 256 x 256 tiles
+// =====================================================================================================================
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+               const __grid_constant__ CUtensorMap tmD2, const GemmNtArgs a) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + GM_OFF_BAR);
+    uint64_t *bar_full = bars, *bar_empty = bars + GM_NS, *bar_tfull = bar_empty + GM_NS, *bar_tempty = bar_tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_tempty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int NB = (a.N + 255) >> 8, MB = (a.M + 255) >> 8, KB = (a.K + 63) >> 6, tiles = MB * NB;
+    gemm_setup(sm, bars, tmem_slot, tid, warp, &tmA, &tmB, &tmD, EPI == CPM_GEMM_EPI_GELU ? &tmD2 : nullptr);
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer (one per CTA; transaction bytes land on the leader's barrier)
+            const uint32_t full0 = mapa_u32(smem_u32(bar_full), 0);
+            uint32_t s = 0, ph = 0;
+            for (int t = pair; t < tiles; t += npairs) {
+                const int nb = t % NB, mb = t / NB;
+                const int row_a = mb * 256 + (int)rank * 128, row_b = nb * 256 + (int)rank * 128;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar_empty + s, ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(bar_full + s, 2 * GM_STAGE);
+                    else mbar_arrive_cluster(full0 + 8 * s);
+                    tma_load_2d_2sm(sm + s * GM_STAGE, &tmA, full0 + 8 * s, kb * 64, row_a);
+                    tma_load_2d_2sm(sm + s * GM_STAGE + GM_A_BYTES, &tmB, full0 + 8 * s, kb * 64, row_b);
+                    if (++s == GM_NS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {                      // ---- UMMA issuer (leader CTA, one thread, both SMs' tensor cores)
+            uint32_t s = 0, ph = 0, ti = 0;
+            for (int t = pair; t < tiles; t += npairs, ++ti) {
+                const uint32_t as = ti & 1, aph = (ti >> 1) & 1;
+                mbar_wait(bar_tempty + as, aph ^ 1);       // the epilogues of both CTAs drained this accumulator stage
+                tc_fence_after();
+                const uint32_t d = tmem + as * 256;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar_full + s, ph);
+                    tc_fence_after();
+                    const uint64_t dA = smem_desc_sw128(smem_u32(sm + s * GM_STAGE)), dB = smem_desc_sw128(smem_u32(sm + s * GM_STAGE + GM_A_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) mma_ss_2sm(d, dA + 2 * k, dB + 2 * k, IDESC_NT, (kb > 0 || k > 0) ? 1u : 0u);
+                    mma_commit_2sm(bar_empty + s, 3);      // frees this stage in BOTH CTAs once the UMMAs retire
+                    if (++s == GM_NS) { s = 0; ph ^= 1; }
+                }
+                mma_commit_2sm(bar_tfull + as, 3);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: warp w owns accumulator rows [32 w, 32 w + 32) of this CTA's half tile
+        const int w = warp - 4;
+        uint8_t *stg = sm + GM_OFF_STG + w * 8192;
+        const uint32_t tempty0 = mapa_u32(smem_u32(bar_tempty), 0);
+        const uint64_t rng_offset = rng_off(a.rng_offset, a.rng_base);
+        uint32_t ti = 0, buf = 0;
+        for (int t = pair; t < tiles; t += npairs, ++ti) {
+            const uint32_t as = ti & 1, aph = (ti >> 1) & 1;
+            const int nb = t % NB, mb = t / NB;
+            const int grow0 = mb * 256 + (int)rank * 128 + w * 32;
+            mbar_wait(bar_tfull + as, aph);
+            tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(w * 32) << 16) + as * 256;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+                const int n0 = nb * 256 + c * 64;
+                uint32_t r[32], o0[16], o1[16];
+                const bool live = n0 < a.N && grow0 < a.M;                    // warp-uniform: the chunk holds at least one real element
+                if (live) {                                                      // the staging buffer(s) must have been read by their last store
+                    if (lane == 0) { if (EPI == CPM_GEMM_EPI_GELU) tma_store_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
+                    __syncwarp();
+                }
+                uint8_t *b0 = stg + (EPI == CPM_GEMM_EPI_GELU ? 0u : buf * 4096u), *b1 = stg + 4096;
+#pragma unroll
+                for (int h = 0; h < 2; ++h) {
+                    tmem_ld32(tbase + c * 64 + h * 32, r);
+                    tmem_ld_wait();
+                    if (c == 3 && h == 1) {                                      // last read of this accumulator stage: hand it back to the issuer
+                        tc_fence_before();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * as);
+                    }
+                    if (live && n0 + h * 32 < a.N) {
+                        nt_epilogue_half<EPI>(r, a, (int64_t)grow0 + lane, n0 + h * 32, rng_offset, o0, o1);
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 16; ++j) { o0[j] = 0u; o1[j] = 0u; }
+                    }
+                    if (live) {
+                        stage_half(b0, lane, h, o0);
+                        if (EPI == CPM_GEMM_EPI_GELU) stage_half(b1, lane, h, o1);
+                    }
+                }
+                if (live) {
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) {                                             // TMA clips the box at the tensor edge (ragged M, N)
+                        tma_store_2d(&tmD, b0, n0, grow0);
+                        if (EPI == CPM_GEMM_EPI_GELU) tma_store_2d(&tmD2, b1, n0, grow0);
+                        tma_store_commit();
+                    }
+                    buf ^= 1;
+                }
+            }
+        }
+        if (lane == 0) tma_store_wait_all0();
+    }
+    tc_fence_before();
+    cluster_sync_all();                                    // nobody leaves while the peer may still signal into its shared memory
+    if (warp == 2) tmem_dealloc_2sm<512>(tmem);
+}
+
+// =====================================================================================================================
+// dW += dY^T . X over one token range; one (tile, split) per cluster
+// =====================================================================================================================
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const GemmTnArgs a) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + GM_OFF_BAR);
+    uint64_t *bar_full = bars, *bar_empty = bars + GM_NS, *bar_tfull = bar_empty + GM_NS, *bar_tempty = bar_tfull + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_tempty + 2);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int item = blockIdx.x >> 1;
+    const int NB = (a.K + 255) >> 8;                       // output tile columns index the INPUT features
+    const int split = item % a.splits, tile = item / a.splits, nb = tile % NB, mb = tile / NB;
+    const int kb_all = (a.T + 63) >> 6, kb0 = split * a.kb_per, kb1 = min(kb_all, kb0 + a.kb_per), KB = max(kb1 - kb0, 0);
+    const bool with_bias = a.dbias != nullptr && nb == 0;
+    for (int i = tid; i < 8192 / 16; i += GM_THREADS)     // a [64 x 128 B] tile of bf16 ones: any swizzle of it is still all ones
+        reinterpret_cast<uint4 *>(sm + GM_OFF_ONES)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
+    fence_proxy_async();
+    gemm_setup(sm, bars, tmem_slot, tid, warp, &tmY, &tmX, nullptr, nullptr);
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer: per stage two 64-column panels of dY and of X
+            const uint32_t full0 = mapa_u32(smem_u32(bar_full), 0);
+            const int col_y = mb * 256 + (int)rank * 128, col_x = nb * 256 + (int)rank * 128;
+            uint32_t s = 0, ph = 0;
+            for (int kb = kb0; kb < kb1; ++kb) {
+                mbar_wait(bar_empty + s, ph ^ 1);
+                if (rank == 0) mbar_expect_tx(bar_full + s, 2 * GM_STAGE);
+                else mbar_arrive_cluster(full0 + 8 * s);
+                uint8_t *st = sm + s * GM_STAGE;
+                tma_load_2d_2sm(st, &tmY, full0 + 8 * s, col_y, kb * 64);
+                tma_load_2d_2sm(st + 8192, &tmY, full0 + 8 * s, col_y + 64, kb * 64);
+                tma_load_2d_2sm(st + GM_A_BYTES, &tmX, full0 + 8 * s, col_x, kb * 64);
+                tma_load_2d_2sm(st + GM_A_BYTES + 8192, &tmX, full0 + 8 * s, col_x + 64, kb * 64);
+                if (++s == GM_NS) { s = 0; ph ^= 1; }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0 && KB > 0) {            // ---- UMMA issuer
+            const uint64_t dOnes = smem_desc_sw128(smem_u32(sm + GM_OFF_ONES), 8192, 1024);
+            uint32_t s = 0, ph = 0;
+            for (int i = 0; i < KB; ++i) {
+                mbar_wait(bar_full + s, ph);
+                tc_fence_after();
+                // MN-major SWIZZLE_128B operands: 64-column atoms 8192 B apart (LBO), 8-token groups 1024 B apart (SBO);
+                // 16 tokens further along K = 2048 B = 128 descriptor units
+                const uint64_t dA = smem_desc_sw128(smem_u32(sm + s * GM_STAGE), 8192, 1024);
+                const uint64_t dB = smem_desc_sw128(smem_u32(sm + s * GM_STAGE + GM_A_BYTES), 8192, 1024);
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                    const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
+                    mma_ss_2sm(tmem, dA + 128 * k, dB + 128 * k, IDESC_TN, acc);
+                    if (with_bias) mma_ss_2sm(tmem + 256, dA + 128 * k, dOnes, IDESC_TN_ONES, acc);
+                }
+                mma_commit_2sm(bar_empty + s, 3);
+                if (++s == GM_NS) { s = 0; ph ^= 1; }
+            }
+            mma_commit_2sm(bar_tfull, 3);
+        }
+    } else if (warp >= 4 && KB > 0) {
+        // ---- epilogue: accumulate this split's partial tile into the fp32 gradient
+        const int w = warp - 4;
+        const int m = mb * 256 + (int)rank * 128 + w * 32 + lane;            // output row = output feature
+        mbar_wait(bar_tfull, 0);
+        tc_fence_after();
+        const uint32_t tbase = tmem + ((uint32_t)(w * 32) << 16);
+        float *dst = a.dW + (int64_t)m * a.ldw + nb * 256;
+#pragma unroll 1
+        for (int c = 0; c < 8; ++c) {
+            uint32_t r[32];
+            tmem_ld32(tbase + c * 32, r);
+            tmem_ld_wait();
+            const int n0 = nb * 256 + c * 32;
+            if (m < a.N) {
+#pragma unroll
+                for (int j = 0; j < 32; j += 4)
+                    if (n0 + j + 4 <= a.K)
+                        red_add_v4(dst + c * 32 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+            }
+        }
+        if (with_bias) {
+            uint32_t r[8];
+            tmem_ld8(tbase + 256, r);
+            tmem_ld_wait();
+            if (m < a.N) atomicAdd(a.dbias + m, __uint_as_float(r[0]));
+        }
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_2sm<512>(tmem);
+}
+
+template <typename K>
+int set_smem(K kernel, const char *name) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)GM_SMEM);
+    if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "%s shared-memory attribute: %s", name, cudaGetErrorString(e));
+    return CPM_OK;
+}
+
+template <int EPI>
+int launch_nt(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &tD, const CUtensorMap &tD2, const GemmNtArgs &a, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        int rc = set_smem(gemm_nt_kernel<EPI>, "gemm_nt");
+        if (rc) return rc;
+        attr = true;
+    }
+    const int tiles = ((a.M + 255) / 256) * ((a.N + 255) / 256);
+    const int pairs = min(tiles, num_sms() / 2);
+    gemm_nt_kernel<EPI><<<2 * pairs, GM_THREADS, GM_SMEM, st>>>(tA, tB, tD, tD2, a);
+    return check_launch("gemm_nt");
+}
+
+}  // namespace
+}  // namespace cpm
+
+using namespace cpm;
+
+extern "C" int cpm_gemm_nt(const void *A, int64_t lda, const void *B, int64_t ldb, void *D, int64_t ldd, void *D2, int64_t ldd2, int M, int N,
+                           int K, const float *bias, int epilogue, const void *aux, int64_t ld_aux, float p_drop, uint64_t seed,
+                           uint64_t rng_offset, void *stream) {
+    CPM_REQUIRE(A && B && D, CPM_ERR_NULL, "gemm_nt: A/B/D must be non-NULL");
+    CPM_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0, CPM_ERR_BAD_SHAPE, "gemm_nt: M=%d N=%d K=%d (N, K multiples of 8)", M, N, K);
+    CPM_REQUIRE(lda >= K && ldb >= K && ldd >= N && lda % 8 == 0 && ldb % 8 == 0 && ldd % 8 == 0, CPM_ERR_BAD_SHAPE, "gemm_nt: row strides must be >= the row width and multiples of 8 elements");
+    CPM_REQUIRE(aligned16(A) && aligned16(B) && aligned16(D) && (!bias || aligned16(bias)), CPM_ERR_BAD_ALIGN, "gemm_nt: operands must be 16-byte aligned");
+    CPM_REQUIRE(epilogue >= CPM_GEMM_EPI_BIAS && epilogue <= CPM_GEMM_EPI_DGELU, CPM_ERR_BAD_SHAPE, "gemm_nt: epilogue %d", epilogue);
+    if (epilogue == CPM_GEMM_EPI_GELU)
+        CPM_REQUIRE(D2 && ldd2 >= N && ldd2 % 8 == 0 && aligned16(D2) && N % 16 == 0 && ldd == N, CPM_ERR_BAD_SHAPE, "gemm_nt: the GELU epilogue needs a second output, N %% 16 == 0 and a dense pre-activation");
+    if (epilogue == CPM_GEMM_EPI_DGELU)
+        CPM_REQUIRE(aux && ld_aux == N && aligned16(aux) && N % 16 == 0, CPM_ERR_BAD_SHAPE, "gemm_nt: the GELU-backward epilogue needs the dense pre-activation (M x N)");
+    CUtensorMap tA, tB, tD, tD2;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tB, B, (uint64_t)K, (uint64_t)N, (uint64_t)ldb, 128))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tD, D, (uint64_t)N, (uint64_t)M, (uint64_t)ldd, 32))) return rc;
+    tD2 = tD;
+    if (epilogue == CPM_GEMM_EPI_GELU && (rc = make_tmap_bf16_2d(&tD2, D2, (uint64_t)N, (uint64_t)M, (uint64_t)ldd2, 32))) return rc;
+    GemmNtArgs a;
+    a.bias = bias; a.aux = (const __nv_bfloat16 *)aux; a.ld_aux = ld_aux; a.M = M; a.N = N; a.K = K;
+    const bool drop = epilogue != CPM_GEMM_EPI_BIAS && p_drop > 0.f;
+    a.thr8 = drop ? dropout_threshold8(p_drop) : 0u;
+    a.scale = drop ? dropout_scale8(p_drop) : 1.f;
+    a.seed = seed; a.rng_offset = rng_offset; a.rng_base = g_rng_base;
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (epilogue) {
+    case CPM_GEMM_EPI_BIAS: return launch_nt<CPM_GEMM_EPI_BIAS>(tA, tB, tD, tD2, a, st);
+    case CPM_GEMM_EPI_GELU: return launch_nt<CPM_GEMM_EPI_GELU>(tA, tB, tD, tD2, a, st);
+    default: return launch_nt<CPM_GEMM_EPI_DGELU>(tA, tB, tD, tD2, a, st);
+    }
+}
+
+extern "C" int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *dW, int64_t ldw, float *dbias, int T, int N, int K,
+                           void *stream) {
+    CPM_REQUIRE(dY && X && dW, CPM_ERR_NULL, "gemm_tn: dY/X/dW must be non-NULL");
+    CPM_REQUIRE(T > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, CPM_ERR_BAD_SHAPE, "gemm_tn: T=%d N=%d K=%d (N, K multiples of 8)", T, N, K);
+    CPM_REQUIRE(ldy >= N && ldx >= K && ldw >= K && ldy % 8 == 0 && ldx % 8 == 0 && ldw % 4 == 0, CPM_ERR_BAD_SHAPE, "gemm_tn: row strides");
+    CPM_REQUIRE(aligned16(dY) && aligned16(X) && aligned16(dW), CPM_ERR_BAD_ALIGN, "gemm_tn: operands must be 16-byte aligned");
+    CUtensorMap tY, tX;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&tY, dY, (uint64_t)N, (uint64_t)T, (uint64_t)ldy, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tX, X, (uint64_t)K, (uint64_t)T, (uint64_t)ldx, 64))) return rc;
+    static bool attr = false;
+    if (!attr) {
+        if ((rc = set_smem(gemm_tn_kernel, "gemm_tn"))) return rc;
+        attr = true;
+    }
+    GemmTnArgs a;
+    a.dW = dW; a.dbias = dbias; a.ldw = ldw; a.T = T; a.N = N; a.K = K;
+    const int tiles = ((N + 255) / 256) * ((K + 255) / 256), kb_all = (T + 63) / 64;
+    int splits = (num_sms() / 2 * 2) / tiles;              // two waves of clusters when the token range is long enough
+    if (splits < 1) splits = 1;
+    if (splits > (kb_all + 7) / 8) splits = (kb_all + 7) / 8;   // at least 8 K blocks per work item
+    if (splits < 1) splits = 1;
+    a.kb_per = (kb_all + splits - 1) / splits;
+    a.splits = (kb_all + a.kb_per - 1) / a.kb_per;
+    gemm_tn_kernel<<<2 * tiles * a.splits, GM_THREADS, GM_SMEM, (cudaStream_t)stream>>>(tY, tX, a);
+    return check_launch("gemm_tn");
+}

@@ -48,7 +48,13 @@ class BucketedGradAllReduce:
     """Flat fp32 gradient buckets (~bucket_mb each, reverse parameter order so the first bucket to
     fill is the last layer's); ``p.grad`` are views into the buckets, so autograd accumulates in
     place and a bucket is all-reduced (SUM, async on the communication stream) the moment its last
-    gradient lands — overlapping with the rest of backward."""
+    gradient lands — overlapping with the rest of backward.
+
+    Gradient accumulation: tell the reducer how many backward passes make up one optimizer step
+    (``zero_grad(n_micro=k)`` or ``begin(k)``).  A bucket is reduced when its last gradient of the
+    LAST micro-batch lands; the earlier passes only accumulate locally.  (Reducing at the end of the
+    first pass - what a plain per-backward counter does - would race later local accumulation with
+    the in-flight collective and never reduce the later micro-batches.)"""
 
     def __init__(self, params, bucket_mb: float = 25.0, group=None):
         self.group = group
@@ -67,6 +73,7 @@ class BucketedGradAllReduce:
             self._close(cur)
         self._handles = []
         self._hooks = []
+        self.n_micro = 1
         for bi, b in enumerate(self.buckets):
             for p in b["params"]:
                 self._hooks.append(p.register_post_accumulate_grad_hook(self._make_hook(bi)))
@@ -84,14 +91,18 @@ class BucketedGradAllReduce:
         for p in plist:
             p.grad = flat[off:off + p.numel()].view_as(p)
             off += p.numel()
-        self.buckets.append({"params": plist, "flat": flat, "pending": len(plist), "launched": False})
+        self.buckets.append({"params": plist, "flat": flat, "pending": len(plist), "launched": False, "round": 0})
 
     def _make_hook(self, bi):
         def hook(_p):
             b = self.buckets[bi]
             b["pending"] -= 1
             if b["pending"] == 0:
-                self._launch(b)
+                b["round"] += 1
+                if b["round"] >= self.n_micro:
+                    self._launch(b)
+                else:                                   # more micro-batches to come: keep accumulating locally
+                    b["pending"] = len(b["params"])
         return hook
 
     def _launch(self, b):
@@ -109,9 +120,20 @@ class BucketedGradAllReduce:
             h.wait()
         self._handles.clear()
         for b in self.buckets:
-            b["pending"], b["launched"] = len(b["params"]), False
+            b["pending"], b["launched"], b["round"] = len(b["params"]), False, 0
 
-    def zero_grad(self):
+    def begin(self, n_micro: int = 1):
+        """Number of backward passes (micro-batches) that accumulate into the buckets before ``finish()``."""
+        if n_micro < 1:
+            raise ValueError("n_micro must be >= 1")
+        self.n_micro = int(n_micro)
+        for b in self.buckets:
+            b["pending"], b["launched"], b["round"] = len(b["params"]), False, 0
+        return self
+
+    def zero_grad(self, n_micro: int = None):
+        if n_micro is not None:
+            self.begin(n_micro)
         for b in self.buckets:
             b["flat"].zero_()
             off = 0

@@ -85,12 +85,16 @@ class PackCache:
         return tuple((p.data_ptr(), p._version) for p in params) + (_OPT_EPOCH[0], dtype)
 
     @staticmethod
-    def _fill(wc, bc, ws, bs):
+    def _fill(wc, bc, ws, bs, wt=None, b32=None):
         r0 = 0
         for w, b in zip(ws, bs):
             wc[r0:r0 + w.shape[0]].copy_(w)
             bc[r0:r0 + w.shape[0]].copy_(b)
+            if b32 is not None:
+                b32[r0:r0 + w.shape[0]].copy_(b)
             r0 += w.shape[0]
+        if wt is not None:
+            wt.copy_(wc.t())
 
     def get(self, key, linears, dtype, pad_rows_to: int = 1):
         ws = [l.weight for l in linears]
@@ -104,25 +108,34 @@ class PackCache:
             padded = -(-sum(rows) // pad_rows_to) * pad_rows_to
             if (hit is not None and hit[1][0].dtype == dtype and hit[1][0].device == ws[0].device
                     and hit[1][0].shape == (padded, ws[0].shape[1])):
-                wc, bc = hit[1][0], hit[1][1]                       # same buffers, new values
+                wc, bc, wt, b32 = hit[1][0], hit[1][1], hit[1][4], hit[1][5]       # same buffers, new values
             else:
                 wc = torch.zeros(padded, ws[0].shape[1], dtype=dtype, device=ws[0].device)
                 bc = torch.zeros(padded, dtype=dtype, device=ws[0].device)
-            self._fill(wc, bc, ws, bs)
-        packed = (wc, bc, tuple(rows), tuple(ws + bs))
+                # operands of the own GEMMs: the transposed copy feeds the data-gradient GEMM (dX = dY . W as an "NT" product
+                # against W^T), the fp32 bias its epilogue
+                wt = torch.zeros(ws[0].shape[1], padded, dtype=dtype, device=ws[0].device) if dtype == torch.bfloat16 else None
+                b32 = torch.zeros(padded, dtype=torch.float32, device=ws[0].device) if dtype == torch.bfloat16 else None
+            self._fill(wc, bc, ws, bs, wt, b32)
+        packed = (wc, bc, tuple(rows), tuple(ws + bs), wt, b32)
         self._store[key] = (stamp, packed)
         return packed
+
+    def get_gemm_pack(self, key, linears, dtype, pad_rows_to: int = 1):
+        """(wc (N,K), wt (K,N), b32 (N,), rows), masters  -  the operand set of ops.tc_linear_packed / ops.tc_ffn."""
+        wc, _bc, rows, masters, wt, b32 = self.get(key, linears, dtype, pad_rows_to)
+        return (wc, wt, b32, rows), masters
 
     def refresh_all(self):
         """Re-sync every existing packing with its masters (in place)."""
         with torch.no_grad():
             for key, (stamp, packed) in list(self._store.items()):
-                wc, bc, rows, masters = packed
+                wc, bc, rows, masters, wt, b32 = packed
                 dtype = stamp[-1]
                 now = self._stamp(masters, dtype)
                 if now != stamp:
                     n = len(rows)
-                    self._fill(wc, bc, masters[:n], masters[n:])
+                    self._fill(wc, bc, masters[:n], masters[n:], wt, b32)
                     self._store[key] = (now, packed)
 
     def invalidate(self):
@@ -137,7 +150,9 @@ class PackCache:
 
 def cached_linear(cache: PackCache, key, linears, x, dtype, pad_rows_to=1, use_bias=True):
     """use_bias=False: the GEMM runs bias-less; the caller adds the (fp32 master) bias inside the next fused kernel."""
-    wc, bc, rows, masters = cache.get(key, linears, dtype, pad_rows_to)
+    wc, bc, rows, masters, wt, b32 = cache.get(key, linears, dtype, pad_rows_to)
+    if ops.use_own_gemm(x) and wt is not None and wc.shape[0] % 8 == 0:
+        return ops.tc_linear_packed(x, (wc, wt, b32, rows), masters if use_bias else masters[:len(rows)], use_bias)
     if not use_bias:
         return ops.packed_linear(x, wc, None, rows, masters[:len(rows)])
     return ops.packed_linear(x, wc, bc, rows, masters)
@@ -198,6 +213,13 @@ class TransformerEncoder(nn.Module):
         if not FUSED_BIAS_GRADS:
             o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
             x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
+            if ops.use_own_gemm(x) and dt == torch.bfloat16:
+                # linear1 + GELU + dropout + linear2 on the own GEMMs: the activation runs in linear1's epilogue, its backward in
+                # the epilogue of linear2's data gradient
+                pack1, _ = c.get_gemm_pack(("ff1", i), [layer.linear1], dt)
+                pack2, _ = c.get_gemm_pack(("ff2", i), [layer.linear2], dt)
+                f = ops.tc_ffn(x, pack1, pack2, p, layer.linear1, layer.linear2)
+                return ops.ln_residual(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p)
             h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)
             g = ops.gelu_dropout(h, p)
             f = cached_linear(c, ("ff2", i), [layer.linear2], g, dt)

@@ -412,6 +412,177 @@ def linattn_state_flush(S, Z, ring, step_dev):
                                             _p(step_dev), 1, _st()))
 
 
+# --------------------------------------------------------------------------- dense linear: own tcgen05 GEMMs (csrc/tc_gemm.cu)
+GEMM_BIAS, GEMM_GELU, GEMM_DGELU = 0, 1, 2
+
+
+def _gemm_operand(t, what):
+    if t.dtype != torch.bfloat16 or t.dim() != 2:
+        raise ValueError(f"{what} must be a 2-D bfloat16 matrix")
+    if t.stride(1) != 1 or t.stride(0) % 8 or t.data_ptr() % 16:
+        t = t.contiguous()
+    return t
+
+
+def gemm_nt(a, b, bias=None, epilogue=GEMM_BIAS, aux=None, p_drop=0.0, seed=0, rng_offset=0, out=None):
+    """epilogue(a @ b.T): a (M,K), b (N,K) bf16 -> (M,N) bf16 on the 2-CTA tcgen05 GEMM (cpm_gemm_nt).  bias: fp32 (N,).
+    GEMM_GELU returns (h, dropout(gelu(h))); GEMM_DGELU multiplies by gelu'(aux) and the regenerated dropout mask."""
+    _cuda(a, b, bias, aux)
+    a, b = _gemm_operand(a, "a"), _gemm_operand(b, "b")
+    M, K = a.shape
+    N = b.shape[0]
+    if b.shape[1] != K:
+        raise ValueError(f"gemm_nt: a (M,{K}) against b {tuple(b.shape)}")
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
+        raise ValueError("gemm_nt: bias must be contiguous float32 (N,)")
+    d = out if out is not None else torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    d2 = torch.empty(M, N, dtype=torch.bfloat16, device=a.device) if epilogue == GEMM_GELU else None
+    if aux is not None:
+        aux = _gemm_operand(aux, "aux")
+    check(_lib.load().cpm_gemm_nt(_p(a), a.stride(0), _p(b), b.stride(0), _p(d), d.stride(0), _p(d2), 0 if d2 is None else d2.stride(0),
+                                  M, N, K, _p(bias), epilogue, _p(aux), 0 if aux is None else aux.stride(0), p_drop, seed, rng_offset, _st()))
+    return (d, d2) if epilogue == GEMM_GELU else d
+
+
+def gemm_tn_acc(dy, x, dw, dbias=None):
+    """dw (N,K) fp32 += dy (T,N).T @ x (T,K); dbias (N,) fp32 += dy.sum(0) - the weight / bias gradient of a Linear layer,
+    accumulated in place (cpm_gemm_tn: operands read MN-major from the row-major activations, no transposes)."""
+    _cuda(dy, x, dw, dbias)
+    dy, x = _gemm_operand(dy, "dy"), _gemm_operand(x, "x")
+    T, N = dy.shape
+    K = x.shape[1]
+    if x.shape[0] != T or dw.shape != (N, K) or dw.dtype != torch.float32 or dw.stride(1) != 1:
+        raise ValueError(f"gemm_tn_acc: dy {tuple(dy.shape)}, x {tuple(x.shape)}, dw {tuple(dw.shape)} {dw.dtype}")
+    if dbias is not None and (dbias.dtype != torch.float32 or dbias.numel() != N or not dbias.is_contiguous()):
+        raise ValueError("gemm_tn_acc: dbias must be contiguous float32 (N,)")
+    check(_lib.load().cpm_gemm_tn(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(dw), dw.stride(0), _p(dbias), T, N, K, _st()))
+    return dw
+
+
+# How the Linear layers run: "own" (default) = the tcgen05 GEMMs above for bf16 activations; "lib" = cuBLASLt through torch
+# (kept for A/B measurements and as the fp32 parity mode's GEMM).  Token counts below OWN_GEMM_MIN_ROWS (the rollout step's
+# M = batch rows) stay on the library path until the small-M kernel lands.
+GEMM_IMPL = os.environ.get("CPM_GEMM", "own")
+OWN_GEMM_MIN_ROWS = int(os.environ.get("CPM_GEMM_MIN_ROWS", "1024"))
+
+
+def use_own_gemm(x) -> bool:
+    return GEMM_IMPL == "own" and x.dtype == torch.bfloat16 and x.is_cuda and x.numel() // x.shape[-1] >= OWN_GEMM_MIN_ROWS
+
+
+def _fire_grad_hooks(p):
+    """A gradient was accumulated into ``p.grad`` outside autograd's AccumulateGrad node: run the parameter's
+    post-accumulate-grad hooks (the bucketed all-reduce of dist.py counts gradients through them)."""
+    hooks = getattr(p, "_post_accumulate_grad_hooks", None)
+    if hooks:
+        for h in list(hooks.values()):
+            h(p)
+
+
+def _wgrad_into_masters(gy2, x2, rows, masters, has_bias):
+    """dW_i (+)= gy[:, rows_i]^T x and db_i (+)= colsum(gy[:, rows_i]) for the masters packed behind one GEMM.  Masters whose
+    ``.grad`` already exists (gradient accumulation; the flat buckets of dist.BucketedGradAllReduce) are accumulated IN PLACE by
+    the kernel's fp32 atomics - no separate add kernels - and report ``None`` to autograd; fresh gradients are returned."""
+    n_w = len(rows)
+    out = [None] * (2 * n_w if has_bias else n_w)
+    aligned = all(r % 8 == 0 for r in rows)
+    if not aligned:                       # ragged row counts (the six output heads): one packed GEMM, split afterwards
+        N = gy2.shape[1]
+        gw = torch.zeros(N, x2.shape[1], dtype=torch.float32, device=gy2.device)
+        gb = torch.zeros(N, dtype=torch.float32, device=gy2.device) if has_bias else None
+        gemm_tn_acc(gy2, x2, gw, gb)
+        r0 = 0
+        for i, r in enumerate(rows):
+            out[i] = gw[r0:r0 + r]
+            if has_bias:
+                out[n_w + i] = gb[r0:r0 + r]
+            r0 += r
+        return out
+    r0 = 0
+    for i, r in enumerate(rows):
+        w = masters[i]
+        b = masters[n_w + i] if has_bias else None
+        gw_t = w.grad if (w.grad is not None and w.grad.dtype == torch.float32 and w.grad.is_contiguous()) else None
+        gb_t = b.grad if (b is not None and b.grad is not None and b.grad.dtype == torch.float32 and b.grad.is_contiguous()) else None
+        in_place_w, in_place_b = gw_t is not None, gb_t is not None
+        if gw_t is None:
+            gw_t = torch.zeros(r, x2.shape[1], dtype=torch.float32, device=gy2.device)
+        if b is not None and gb_t is None:
+            gb_t = torch.zeros(r, dtype=torch.float32, device=gy2.device)
+        gemm_tn_acc(gy2[:, r0:r0 + r], x2, gw_t, gb_t)
+        if in_place_w:
+            _fire_grad_hooks(w)
+        else:
+            out[i] = gw_t
+        if has_bias:
+            if in_place_b:
+                _fire_grad_hooks(b)
+            else:
+                out[n_w + i] = gb_t
+        r0 += r
+    return out
+
+
+class _TcLinear(torch.autograd.Function):
+    """y = x @ Wc^T + b on the own GEMMs.  ``pack`` = (wc (N,K) bf16, wt (K,N) bf16, b32 (N,) fp32 | None, rows): the packed
+    compute copies of the fp32 masters (encoder.PackCache)."""
+
+    @staticmethod
+    def forward(ctx, x, pack, use_bias, *masters):
+        wc, wt, b32, rows = pack
+        x2 = x.reshape(-1, x.shape[-1])
+        y = gemm_nt(x2, wc, b32 if use_bias else None)
+        ctx.save_for_backward(x2)
+        ctx.pack, ctx.use_bias, ctx.xshape, ctx.masters = pack, use_bias, x.shape, masters
+        return y.view(*x.shape[:-1], wc.shape[0])
+
+    @staticmethod
+    def backward(ctx, gy):
+        (x2,) = ctx.saved_tensors
+        wc, wt, b32, rows = ctx.pack
+        gy2 = gy.reshape(-1, gy.shape[-1])
+        gx = gemm_nt(gy2, wt).view(ctx.xshape) if ctx.needs_input_grad[0] else None
+        grads = _wgrad_into_masters(gy2, x2, rows, ctx.masters, ctx.use_bias)
+        grads += [None] * (len(ctx.masters) - len(grads))
+        return (gx, None, None, *grads)
+
+
+def tc_linear_packed(x, pack, masters, use_bias=True):
+    return _TcLinear.apply(x, pack, use_bias, *masters)
+
+
+class _TcFFN(torch.autograd.Function):
+    """ft's feed-forward block  linear2(dropout(gelu(linear1(x))))  (linear1/linear2 of
+    agent_pretrain.py:244-253's builder) as two GEMM launches forward and four backward: bias + exact GELU + dropout run in
+    linear1's epilogue (which also keeps the pre-activation), GELU backward + the regenerated dropout mask in the epilogue of
+    linear2's data gradient - no element-wise pass over the (T, 2048) tensors in either direction."""
+
+    @staticmethod
+    def forward(ctx, x, pack1, pack2, p_drop, w1, b1, w2, b2):
+        x2 = x.reshape(-1, x.shape[-1])
+        seed, off = _Rng.take(x2.shape[0] * pack1[0].shape[0]) if p_drop > 0 else (0, 0)
+        h, g = gemm_nt(x2, pack1[0], pack1[2], epilogue=GEMM_GELU, p_drop=p_drop, seed=seed, rng_offset=off)
+        f = gemm_nt(g, pack2[0], pack2[2])
+        ctx.save_for_backward(x2, h, g)
+        ctx.cfg = (pack1, pack2, p_drop, seed, off, x.shape, (w1, b1, w2, b2))
+        return f.view(*x.shape[:-1], pack2[0].shape[0])
+
+    @staticmethod
+    def backward(ctx, gf):
+        x2, h, g = ctx.saved_tensors
+        pack1, pack2, p_drop, seed, off, xshape, (w1, b1, w2, b2) = ctx.cfg
+        gf2 = gf.reshape(-1, gf.shape[-1])
+        dh = gemm_nt(gf2, pack2[1], epilogue=GEMM_DGELU, aux=h, p_drop=p_drop, seed=seed, rng_offset=off)
+        g2 = _wgrad_into_masters(gf2, g, pack2[3], (w2, b2), True)
+        gx = gemm_nt(dh, pack1[1]).view(xshape) if ctx.needs_input_grad[0] else None
+        g1 = _wgrad_into_masters(dh, x2, pack1[3], (w1, b1), True)
+        return gx, None, None, None, g1[0], g1[1], g2[0], g2[1]
+
+
+def tc_ffn(x, pack1, pack2, p_drop, lin1, lin2):
+    return _TcFFN.apply(x, pack1, pack2, p_drop, lin1.weight, lin1.bias, lin2.weight, lin2.bias)
+
+
 # --------------------------------------------------------------------------- dense linear (vendor GEMM)
 def _mm_f32_out(a, b):
     """a @ b with fp32 output (bf16 inputs accumulate in fp32 inside cuBLAS either way)."""

@@ -127,13 +127,13 @@ class RolloutEngine:
         m, enc, N = self.model, self.model.transformer_encoder, self.N
         dt, H = torch.bfloat16, enc.n_heads
         emb = ops.cp_embed(self.cur[:, None, :], m._tables(), dt).view(N, -1)
-        w, b, _, _ = m._cache.get("in", [m.in_linear], dt)
+        w, b, _, _ = m._cache.get("in", [m.in_linear], dt)[:4]
         x = ops.skinny_linear(emb, w, b, epilogue=ops.EPI_PE, pe=m.pos_emb.pe,
                               pos_dev=self.step_dev if self.true_positions else None)
         s_prev, prev = None, None
         for i, layer in enumerate(enc.layers):
             at = layer.attention
-            wq, bq, _, _ = enc._cache.get(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], dt)
+            wq, bq, _, _ = enc._cache.get(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], dt)[:4]
             if i == 0:
                 xin, qkv = x, ops.skinny_linear(x, wq, bq)
             else:
@@ -141,17 +141,17 @@ class RolloutEngine:
                 qkv = ops.skinny_linear(s_prev, wq, bq, ln=(prev.norm2.weight, prev.norm2.bias, prev.norm2.eps), xout=xin)
             q, k, v = (qkv[:, j * H * 64:(j + 1) * H * 64].unflatten(-1, (H, 64)) for j in range(3))
             a = ops.linattn_step(q, k, v, self.state[i][0], self.state[i][1]).view(N, H * 64)
-            wo, bo, _, _ = enc._cache.get(("out", i), [at.out_projection], dt)
+            wo, bo, _, _ = enc._cache.get(("out", i), [at.out_projection], dt)[:4]
             s1 = ops.skinny_linear(a, wo, bo, epilogue=ops.EPI_RESIDUAL, residual=xin)
-            w1, b1, _, _ = enc._cache.get(("ff1", i), [layer.linear1], dt)
+            w1, b1, _, _ = enc._cache.get(("ff1", i), [layer.linear1], dt)[:4]
             x1 = torch.empty(N, m.d_model, dtype=dt, device=x.device)
             hmid = ops.skinny_linear(s1, w1, b1, ln=(layer.norm1.weight, layer.norm1.bias, layer.norm1.eps), xout=x1,
                                      epilogue=ops.EPI_GELU)
-            w2, b2, _, _ = enc._cache.get(("ff2", i), [layer.linear2], dt)
+            w2, b2, _, _ = enc._cache.get(("ff2", i), [layer.linear2], dt)[:4]
             s_prev = ops.skinny_linear(hmid, w2, b2, epilogue=ops.EPI_RESIDUAL, residual=x1)
             prev = layer
         xl = ops.ln_residual(s_prev, None, prev.norm2.weight, prev.norm2.bias, prev.norm2.eps, 0.0)
-        wh, bh, _, _ = m._cache.get("heads", m._heads(), dt, 8)
+        wh, bh, _, _ = m._cache.get("heads", m._heads(), dt, 8)[:4]
         return ops.skinny_linear(xl, wh, bh, ln=(enc.norm.weight, enc.norm.bias, enc.norm.eps))
 
     # ---- tcgen05 step: every Linear is one cpm_tc_linear launch, no LayerNorm / GELU / residual kernels ----
@@ -296,12 +296,12 @@ class RolloutEngine:
                 ph.gamma2, ph.beta2 = ln2[0].data_ptr(), ln2[1].data_ptr()
             phases.append(ph)
 
-        w, b, _, _ = m._cache.get("in", [m.in_linear], dt)
+        w, b, _, _ = m._cache.get("in", [m.in_linear], dt)[:4]
         gemm(None, w, b, sc["x0"], d, E, pro=3, epi=3)
         prev = None
         for i, layer in enumerate(enc.layers):
             at = layer.attention
-            wq, bq, _, _ = enc._cache.get(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], dt)
+            wq, bq, _, _ = enc._cache.get(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], dt)[:4]
             if i == 0:
                 gemm(sc["x0"], wq, bq, sc["qkv"], 3 * d, d)
                 xin = sc["x0"]
@@ -312,14 +312,14 @@ class RolloutEngine:
             ph.type, ph.M, ph.H, ph.lda, ph.ldy, ph.eps = 1, N, H, 3 * d, d, ops.EPS_ATTN
             ph.A, ph.Y, ph.S, ph.Z = sc["qkv"].data_ptr(), sc["a"].data_ptr(), self.S[i].data_ptr(), self.Z[i].data_ptr()
             phases.append(ph)
-            wo, bo, _, _ = enc._cache.get(("out", i), [at.out_projection], dt)
+            wo, bo, _, _ = enc._cache.get(("out", i), [at.out_projection], dt)[:4]
             gemm(sc["a"], wo, bo, sc["s1"], d, d, epi=2, R=xin)
-            w1, b1, _, _ = enc._cache.get(("ff1", i), [layer.linear1], dt)
+            w1, b1, _, _ = enc._cache.get(("ff1", i), [layer.linear1], dt)[:4]
             gemm(sc["s1"], w1, b1, sc["h"], di, d, pro=1, epi=1, ln=(layer.norm1.weight, layer.norm1.bias, layer.norm1.eps), xout=sc["x1"])
-            w2, b2, _, _ = enc._cache.get(("ff2", i), [layer.linear2], dt)
+            w2, b2, _, _ = enc._cache.get(("ff2", i), [layer.linear2], dt)[:4]
             gemm(sc["h"], w2, b2, sc["s2"], d, di, epi=2, R=sc["x1"])
             prev = layer
-        wh, bh, _, _ = m._cache.get("heads", m._heads(), dt, 8)
+        wh, bh, _, _ = m._cache.get("heads", m._heads(), dt, 8)[:4]
         gemm(sc["s2"], wh, bh, sc["logits"], m.logits_width, d, pro=2, ln=(prev.norm2.weight, prev.norm2.bias, prev.norm2.eps),
              ln2=(enc.norm.weight, enc.norm.bias, enc.norm.eps))
         ph = _MegaPhase()

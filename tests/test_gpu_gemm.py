@@ -1,0 +1,151 @@
+"""GPU parity tests of the tcgen05 GEMM family (csrc/tc_gemm.cu) through the C-ABI (cpmusic.ops.gemm_nt / gemm_tn_acc).
+
+Oracle: the same contraction in float64 on the CPU from the SAME bf16 operand values (numpy / torch CPU matmul — the
+restatement of what nn.Linear computes for the reference's Linear layers, agent_pretrain.py:239,244-253,360-375).  The GEMM
+accumulates in fp32 and rounds once to bf16, so the tolerance is bf16's half-ulp (2^-8 relative) plus fp32 accumulation noise.
+The GELU epilogues are held to the exact-erf GELU (torch.nn.functional.gelu in float64, what ft's activation='gelu' calls) and
+their dropout masks to the standalone cpm_gelu_fwd / cpm_gelu_bwd kernels, which draw from the same Philox streams."""
+import math
+
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _bf16(shape, gen, scale=1.0):
+    return (torch.randn(*shape, generator=gen) * scale).to(torch.bfloat16)
+
+
+def _assert_close_bf16(got, ref, what, extra_abs=0.0):
+    got, ref = got.double().cpu(), ref.double().cpu()
+    tol = ref.abs() * 2.0 ** -8 + 1e-3 + extra_abs
+    err = (got - ref).abs()
+    bad = err > tol
+    assert not bool(bad.any()), f"{what}: {int(bad.sum())} of {bad.numel()} elements off, max err {err.max().item():.4e}, ref scale {ref.abs().max().item():.3e}"
+
+
+# (M, N, K): the agent's layer shapes at small token counts, ragged edges in every dimension, multi-tile / multi-wave cases
+NT_SHAPES = [(256, 256, 64), (256, 512, 512), (512, 1536, 512), (384, 2048, 512), (300, 512, 2048), (1000, 344, 512), (130, 512, 1216),
+             (77, 264, 344), (8, 512, 512), (256 * 80, 512, 512), (256 * 150 + 40, 256, 128)]
+
+
+@pytest.mark.parametrize("shape", NT_SHAPES)
+def test_gemm_nt_bias_vs_fp64(cuda, cpm, shape):
+    M, N, K = shape
+    gen = torch.Generator().manual_seed(M * 31 + N * 7 + K)
+    a, b = _bf16((M, K), gen), _bf16((N, K), gen, 1.0 / math.sqrt(K))
+    bias = torch.randn(N, generator=gen)
+    ref = a.double() @ b.double().t() + bias.double()
+    got = cpm.ops.gemm_nt(a.to(cuda), b.to(cuda), bias.to(cuda))
+    assert got.shape == (M, N) and got.dtype == torch.bfloat16
+    _assert_close_bf16(got, ref, f"gemm_nt {shape}")
+    got2 = cpm.ops.gemm_nt(a.to(cuda), b.to(cuda))                         # no bias
+    _assert_close_bf16(got2, ref - bias.double(), f"gemm_nt {shape} (no bias)")
+
+
+def test_gemm_nt_strided_operands_and_output_slice(cuda, cpm):
+    """A as a column slice of a wider buffer (row stride > K) and D written into a column slice of a wider buffer: how q,k,v
+    slices of the fused projection output and their gradients are addressed."""
+    gen = torch.Generator().manual_seed(5)
+    M, N, K = 640, 512, 512
+    wide = _bf16((M, 3 * K), gen).to(cuda)
+    b = _bf16((N, K), gen, 1.0 / math.sqrt(K)).to(cuda)
+    out = torch.full((M, 2 * N), 7.0, dtype=torch.bfloat16, device=cuda)
+    a = wide[:, K:2 * K]
+    cpm.ops.gemm_nt(a, b, out=out[:, N:])
+    ref = a.double().cpu() @ b.double().cpu().t()
+    _assert_close_bf16(out[:, N:], ref, "strided gemm_nt")
+    assert bool((out[:, :N] == 7.0).all()), "columns outside the output slice were touched"
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+@pytest.mark.parametrize("shape", [(256, 2048, 512), (1000, 2048, 512), (96, 256, 64)])
+def test_gemm_nt_gelu_epilogue(cuda, cpm, shape, p_drop):
+    """h = bf16(a W^T + b) and g = dropout(gelu(h)) in one launch == the GEMM followed by cpm_gelu_fwd (same Philox stream ->
+    same mask), and gelu itself == the exact-erf GELU in float64."""
+    M, N, K = shape
+    gen = torch.Generator().manual_seed(N + K)
+    a, b = _bf16((M, K), gen).to(cuda), _bf16((N, K), gen, 1.0 / math.sqrt(K)).to(cuda)
+    bias = torch.randn(N, generator=gen).to(cuda)
+    seed, off = 1234, 96
+    h, g = cpm.ops.gemm_nt(a, b, bias, epilogue=cpm.ops.GEMM_GELU, p_drop=p_drop, seed=seed, rng_offset=off)
+    ref_h = a.double().cpu() @ b.double().cpu().t() + bias.double().cpu()
+    _assert_close_bf16(h, ref_h, "pre-activation")
+    # the standalone kernel on the stored pre-activation, same (seed, offset)
+    g_ref = torch.empty_like(h)
+    lib = cpm._lib.load()
+    cpm._lib.check(lib.cpm_gelu_fwd(h.data_ptr(), None, g_ref.data_ptr(), M, N, p_drop, seed, off, cpm._lib.BF16, torch.cuda.current_stream().cuda_stream))
+    assert torch.equal(g, g_ref), f"fused GELU epilogue differs from cpm_gelu_fwd in {int((g != g_ref).sum())} elements"
+    if p_drop == 0.0:
+        exact = torch.nn.functional.gelu(h.double().cpu())
+        _assert_close_bf16(g, exact, "gelu vs exact erf")
+    else:
+        kept = (g != 0).float().mean().item()
+        assert abs(kept - 230 / 256) < 0.02, f"kept fraction {kept}"           # thr8 = 26 of 256 for p = 0.1
+
+
+@pytest.mark.parametrize("p_drop", [0.0, 0.1])
+def test_gemm_nt_dgelu_epilogue(cuda, cpm, p_drop):
+    """dgrad of linear2 with the GELU backward fused: (dy W) * gelu'(h) * mask == GEMM then cpm_gelu_bwd."""
+    M, N, K = 700, 2048, 512
+    gen = torch.Generator().manual_seed(9)
+    dy, wt = _bf16((M, K), gen).to(cuda), _bf16((N, K), gen, 1.0 / math.sqrt(K)).to(cuda)
+    h = _bf16((M, N), gen).to(cuda)
+    seed, off = 77, 1 << 20
+    got = cpm.ops.gemm_nt(dy, wt, epilogue=cpm.ops.GEMM_DGELU, aux=h, p_drop=p_drop, seed=seed, rng_offset=off)
+    acc = dy.double().cpu() @ wt.double().cpu().t()
+    hd = h.double().cpu()
+    dgelu = 0.5 * (1 + torch.erf(hd / math.sqrt(2))) + hd * torch.exp(-0.5 * hd * hd) / math.sqrt(2 * math.pi)
+    ref = acc * dgelu
+    if p_drop > 0:
+        # the mask of the standalone backward kernel on a gradient of ones: nonzero <=> kept
+        ones, gx = torch.ones_like(h), torch.empty_like(h)
+        lib = cpm._lib.load()
+        cpm._lib.check(lib.cpm_gelu_bwd(h.data_ptr(), None, ones.data_ptr(), gx.data_ptr(), None, None, M, N, p_drop, seed, off,
+                                        cpm._lib.BF16, torch.cuda.current_stream().cuda_stream))
+        keep = (gx != 0).double().cpu()
+        # gelu'(h) is exactly 0 only where h is far negative; treat those as kept-or-dropped alike
+        scale = 256.0 / (256.0 - round(p_drop * 256.0))
+        ref = ref * keep * scale
+        sure = (dgelu.abs() > 1e-3)
+        _assert_close_bf16(torch.where(sure.to(cuda), got, torch.zeros_like(got)), torch.where(sure, ref, torch.zeros_like(ref)), "dgelu+dropout")
+    else:
+        _assert_close_bf16(got, ref, "dgelu", extra_abs=2e-3)
+
+
+TN_SHAPES = [(256, 256, 256), (4096, 512, 512), (5000, 1536, 512), (3000, 2048, 512), (2000, 512, 2048), (1500, 344, 512), (900, 512, 1216),
+             (100, 264, 344), (70000, 512, 512)]
+
+
+@pytest.mark.parametrize("shape", TN_SHAPES)
+def test_gemm_tn_weight_and_bias_gradient(cuda, cpm, shape):
+    """dW += dY^T X and db += colsum(dY), accumulated onto existing values (gradient accumulation)."""
+    T, N, K = shape
+    gen = torch.Generator().manual_seed(T + N + K)
+    dy, x = _bf16((T, N), gen), _bf16((T, K), gen)
+    dw0, db0 = torch.randn(N, K, generator=gen), torch.randn(N, generator=gen)
+    dw, db = dw0.clone().to(cuda), db0.clone().to(cuda)
+    cpm.ops.gemm_tn_acc(dy.to(cuda), x.to(cuda), dw, db)
+    ref_w = dw0.double() + dy.double().t() @ x.double()
+    ref_b = db0.double() + dy.double().sum(0)
+    tol = 1e-5 * math.sqrt(T) * 4 + 1e-4            # fp32 accumulation over T terms of O(1) products
+    assert (dw.double().cpu() - ref_w).abs().max().item() <= tol * max(1.0, ref_w.abs().max().item() / 8), \
+        f"dW max err {(dw.double().cpu() - ref_w).abs().max().item():.3e} (tol {tol:.1e})"
+    assert (db.double().cpu() - ref_b).abs().max().item() <= tol * max(1.0, ref_b.abs().max().item() / 8), \
+        f"db max err {(db.double().cpu() - ref_b).abs().max().item():.3e}"
+    dw2 = torch.zeros(N, K, device=cuda)
+    cpm.ops.gemm_tn_acc(dy.to(cuda), x.to(cuda), dw2)                         # without the bias gradient
+    assert (dw2.double().cpu() - (ref_w - dw0.double())).abs().max().item() <= tol * max(1.0, ref_w.abs().max().item() / 8)
+
+
+def test_gemm_tn_strided_operands(cuda, cpm):
+    """dY and X as column slices (the q/k/v gradient slices of one fused buffer)."""
+    gen = torch.Generator().manual_seed(3)
+    T = 2304
+    gbuf, xbuf = _bf16((T, 1536), gen).to(cuda), _bf16((T, 1024), gen).to(cuda)
+    dy, x = gbuf[:, 512:1024], xbuf[:, 512:]
+    dw = torch.zeros(512, 512, device=cuda)
+    cpm.ops.gemm_tn_acc(dy, x, dw)
+    ref = dy.double().cpu().t() @ x.double().cpu()
+    assert (dw.double().cpu() - ref).abs().max().item() < 2e-3

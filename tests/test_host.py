@@ -210,6 +210,58 @@ def test_bucketed_allreduce_gloo_world2(late):
     assert sorted(res) == [(0, True), (1, True)]
 
 
+def _dp_accum_worker(rank, world, port, q):
+    """Two micro-batches per optimizer step (what bench.py's update does): the buckets must be reduced ONCE, after the last
+    micro-batch, and equal the single-process full-batch gradient."""
+    import torch.distributed as dist
+    sys.path.insert(0, ROOT)
+    import cpmusic
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    cpmusic.dist.init_from_env("gloo")
+    torch.manual_seed(0)
+    net = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4))
+    red = cpmusic.dist.BucketedGradAllReduce(net.parameters(), bucket_mb=0.001)
+    g = torch.Generator().manual_seed(1)
+    X, Y = torch.randn(16, 16, generator=g), torch.randn(16, 4, generator=g)
+    lo, hi = cpmusic.dist.shard_range(16, rank, world)
+    launches = []
+    orig = red._launch
+    red._launch = lambda b: ((launches.append(b["round"]) if not b["launched"] else None), orig(b))[1]
+    ok = True
+    for n_micro in (2, 4, 1):                              # also: the counter state is clean again after finish()
+        red.zero_grad(n_micro=n_micro)
+        launches.clear()
+        step = (hi - lo) // n_micro
+        for m in range(n_micro):
+            sl = slice(lo + m * step, lo + (m + 1) * step)
+            (((net(X[sl]) - Y[sl]) ** 2).sum() / 16).backward()
+            if m < n_micro - 1:
+                ok = ok and not launches                   # nothing is reduced before the last micro-batch
+        red.finish()
+        ok = ok and all(r == n_micro for r in launches) and len(launches) == len(red.buckets)
+        grads = [p.grad.clone() for p in net.parameters()]
+        ref = torch.nn.Sequential(torch.nn.Linear(16, 32), torch.nn.Tanh(), torch.nn.Linear(32, 4))
+        ref.load_state_dict(net.state_dict())
+        (((ref(X) - Y) ** 2).sum() / 16).backward()
+        ok = ok and all(torch.allclose(a, b.grad, atol=1e-6) for a, b in zip(grads, ref.parameters()))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+def test_bucketed_allreduce_gradient_accumulation_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000) + 13
+    procs = [ctx.Process(target=_dp_accum_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=180) for _ in procs]
+    for p in procs:
+        p.join(60)
+    assert sorted(res) == [(0, True), (1, True)]
+
+
 def _literal_reward(head, h):
     """ppo_policy/model.py:474-493 written out: six proj, six eval, mean over the sequence, sigmoid, average."""
     scores = []
