@@ -195,6 +195,15 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
 int cpm_colsum_partials_rows(int width);
 int cpm_colsum(const void *x, int64_t rows, int width, int64_t ld, float *out, float *partials, int dtype, void *stream);
 
+/* Row dot out[r] = h[r,:] . u + *c (fp32 out; c may be NULL): the critic's value read-out collapsed to one d-vector,
+ * Critic_Transformer.value_produce (ppo_policy/model.py:345-394: six Linear(512, n_a) heads, six Linear(n_a, 1) value heads,
+ * average over attributes) is linear in h.  Backward: dh[r,:] = g[r] u (may be NULL) and du[:] = sum_r g[r] h[r,:]
+ * (OVERWRITTEN; partials = caller-owned fp32 scratch of cpm_rowdot_partials_rows() * d floats; deterministic). d % 8 == 0, <= 1024. */
+int cpm_rowdot_partials_rows(void);
+int cpm_rowdot_fwd(const void *h, const float *u, const float *c, float *out, int64_t rows, int d, int dtype, void *stream);
+int cpm_rowdot_bwd(const void *h, const float *g, const float *u, void *dh, float *du, float *partials, int64_t rows, int d,
+                   int dtype, void *stream);
+
 int cpm_set_rng_base(const uint64_t *device_counter);
 
 /* ---- Dense Linear layers on tcgen05 (csrc/tc_gemm.cu) ---------------------------------------------------------------

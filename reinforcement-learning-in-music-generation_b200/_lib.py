@@ -58,6 +58,9 @@ SIGNATURES = {
     "cpm_linattn_step_lazy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, _P, c_int, _P]),
     "cpm_reward_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "cpm_set_rng_base": (c_int, [_P]),
+    "cpm_rowdot_partials_rows": (c_int, []),
+    "cpm_rowdot_fwd": (c_int, [_P, _P, _P, _P, c_int64, c_int, c_int, _P]),
+    "cpm_rowdot_bwd": (c_int, [_P, _P, _P, _P, _P, _P, c_int64, c_int, c_int, _P]),
     "cpm_gemm_nt": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, c_int, _P, c_int64,
                             c_float, c_uint64, c_uint64, _P]),
     "cpm_gemm_tn": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, _P, c_int, c_int, c_int, _P]),
@@ -101,8 +104,8 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
-    "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2, "cpm_colsum": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
+    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_rowdot_partials_rows": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
+    "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2, "cpm_colsum": 2, "cpm_rowdot_bwd": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
                                                                                 # kernel (ops adds 1 when the scan path runs); bwd = pre-pass, scan, main
 })
 EXTRA_LAUNCHES = [0]          # segment-total / scan kernels of segmented linear attention, graph replays

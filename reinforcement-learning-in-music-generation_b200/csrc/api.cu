@@ -451,7 +451,9 @@ int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, floa
                 (long long)saved_bytes, (long long)cpm_linattn_saved_bytes(N, L, H));
     if (impl == 3 || (impl == 0 && tc_ok)) {
         rc = linattn_fwd_cp_launch(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, workspace, saved, st);
-        if (rc != CPM_ERR_UNSUPPORTED || impl == 3) { g_linattn_impl = "tcgen05-cp"; return rc; }
+        // "-stream": one CTA per (batch, head) chain carries S / z in tensor memory across chunks (N*H >= 96); otherwise the
+        // per-chunk state kernels + scan
+        if (rc != CPM_ERR_UNSUPPORTED || impl == 3) { g_linattn_impl = (N * H >= 96 && L > 128) ? "tcgen05-cp-stream" : "tcgen05-cp"; return rc; }
     }
     if (impl == 2 || (impl == 0 && tc_ok)) {
         rc = linattn_fwd_tc_launch(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, workspace, st);
@@ -478,7 +480,7 @@ int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out
                 (long long)saved_bytes, (long long)cpm_linattn_saved_bytes(N, L, H));
     if (impl == 3 || (impl == 0 && tc_ok)) {
         rc = linattn_bwd_cp_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, workspace, saved, st);
-        if (rc != CPM_ERR_UNSUPPORTED || impl == 3) { g_linattn_impl = "tcgen05-cp"; return rc; }
+        if (rc != CPM_ERR_UNSUPPORTED || impl == 3) { g_linattn_impl = N * H >= 96 ? "tcgen05-cp-stream" : "tcgen05-cp"; return rc; }
     }
     if (impl == 2 || (impl == 0 && tc_ok)) {
         rc = linattn_bwd_tc_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, eps, workspace, st);

@@ -347,6 +347,81 @@ __global__ void __launch_bounds__(256) reduce_partials_kernel(const float *__res
     }
 }
 
+// ---------------------------------------------------------------- row dot: out[r] = h[r,:] . u + c   (collapsed critic value head)
+// Critic_Transformer.value_produce (ppo_policy/model.py:345-394) applies six Linear(512 -> n_a) heads and six Linear(n_a -> 1)
+// value heads and averages: linear in h, so value[r] = h[r,:] . u + c with u = sum_a W_a^T w_a / 6 (model.py builds u, c with
+// autograd through that tiny product).  One warp per row, 128-bit loads; fp32 result.  Backward: dh[r,:] = g[r] u (compute
+// dtype) and du = sum_r g[r] h[r,:] through per-CTA partial rows + reduce_partials_kernel (deterministic).
+constexpr int ROWDOT_BWD_BLOCKS = 592;
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) rowdot_fwd_kernel(const T *__restrict__ h, const float *__restrict__ u, const float *__restrict__ c,
+                                                         float *__restrict__ out, int64_t rows, int d) {
+    const int lane = threadIdx.x & 31, G = d >> 3;
+    float uv[MAXV][8];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int g = lane + 32 * i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) uv[i][j] = g < G ? u[g * 8 + j] : 0.f;
+    }
+    const float c0 = c ? *c : 0.f;
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp_global; r < rows; r += nwarps) {
+        float acc = 0.f;
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int g = lane + 32 * i;
+            if (g < G) {
+                Vec8<T> v;
+                v.load(h + r * d + g * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) acc = fmaf(v.v[j], uv[i][j], acc);
+            }
+        }
+        acc = warp_sum(acc);
+        if (lane == 0) out[r] = acc + c0;
+    }
+}
+template <typename T, int MAXV>
+__global__ void __launch_bounds__(256) rowdot_bwd_kernel(const T *__restrict__ h, const float *__restrict__ g, const float *__restrict__ u,
+                                                         T *__restrict__ dh, float *__restrict__ partials, int64_t rows, int d) {
+    __shared__ float red[8][32 * MAXV * 8 + 8];
+    const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5, G = d >> 3;
+    float uv[MAXV][8], du[MAXV][8];
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i) {
+        const int gi = lane + 32 * i;
+#pragma unroll
+        for (int j = 0; j < 8; ++j) { uv[i][j] = gi < G ? u[gi * 8 + j] : 0.f; du[i][j] = 0.f; }
+    }
+    const int64_t warp_global = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5, nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+    for (int64_t r = warp_global; r < rows; r += nwarps) {
+        const float gr = g[r];
+#pragma unroll
+        for (int i = 0; i < MAXV; ++i) {
+            const int gi = lane + 32 * i;
+            if (gi < G) {
+                Vec8<T> v, o;
+                v.load(h + r * d + gi * 8);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) { du[i][j] = fmaf(gr, v.v[j], du[i][j]); o.v[j] = gr * uv[i][j]; }
+                if (dh) o.store(dh + r * d + gi * 8);
+            }
+        }
+    }
+#pragma unroll
+    for (int i = 0; i < MAXV; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) red[wib][(lane + 32 * i) * 8 + j] = du[i][j];
+    __syncthreads();
+    for (int c = threadIdx.x; c < d; c += 256) {
+        float t = 0.f;
+#pragma unroll
+        for (int w = 0; w < 8; ++w) t += red[w][c];
+        partials[(int64_t)blockIdx.x * d + c] = t;
+    }
+}
+
 // ---------------------------------------------------------------- column sums (bias gradients of the Linear layers)
 // out[c] = sum_r x[r][c], x (rows, width) bf16 / fp32 row-major with row stride ld.  Stage 1: CTA (slab, rs) sums its rows of a
 // 1 KB-wide column slab: one warp spans the slab with 256-bit streaming loads (L1 no-allocate, L2 evict-first: measured 5.5-5.9
@@ -603,6 +678,30 @@ int cpm_ln_residual_fwd(const void *x, const void *res, const float *res_bias, c
 }
 
 int cpm_ln_partials_rows(void) { return LN_BWD_BLOCKS; }
+
+int cpm_rowdot_partials_rows(void) { return ROWDOT_BWD_BLOCKS; }
+
+int cpm_rowdot_fwd(const void *h, const float *u, const float *c, float *out, int64_t rows, int d, int dtype, void *stream) {
+    CPM_REQUIRE(h && u && out, CPM_ERR_NULL, "rowdot_fwd: NULL pointer");
+    CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0 && d <= 1024, CPM_ERR_BAD_SHAPE, "rowdot_fwd: d=%d must be a multiple of 8 and <= 1024", d);
+    CPM_REQUIRE(aligned16(h), CPM_ERR_BAD_ALIGN, "rowdot_fwd: h must be 16-byte aligned");
+    if (rows == 0) return CPM_OK;
+    const int grid = grid_for(rows * 32, 256);
+    if (d <= 512) { DISPATCH_DTYPE(dtype, (rowdot_fwd_kernel<T, 2><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)h, u, c, out, rows, d))); }
+    else { DISPATCH_DTYPE(dtype, (rowdot_fwd_kernel<T, 4><<<grid, 256, 0, (cudaStream_t)stream>>>((const T *)h, u, c, out, rows, d))); }
+    return check_launch("rowdot_fwd");
+}
+
+int cpm_rowdot_bwd(const void *h, const float *g, const float *u, void *dh, float *du, float *partials, int64_t rows, int d, int dtype,
+                   void *stream) {
+    CPM_REQUIRE(h && g && u && du && partials, CPM_ERR_NULL, "rowdot_bwd: NULL pointer");
+    CPM_REQUIRE(rows >= 0 && d > 0 && d % 8 == 0 && d <= 1024, CPM_ERR_BAD_SHAPE, "rowdot_bwd: d=%d must be a multiple of 8 and <= 1024", d);
+    CPM_REQUIRE(aligned16(h) && (!dh || aligned16(dh)), CPM_ERR_BAD_ALIGN, "rowdot_bwd: alignment");
+    if (d <= 512) { DISPATCH_DTYPE(dtype, (rowdot_bwd_kernel<T, 2><<<ROWDOT_BWD_BLOCKS, 256, 0, (cudaStream_t)stream>>>((const T *)h, g, u, (T *)dh, partials, rows, d))); }
+    else { DISPATCH_DTYPE(dtype, (rowdot_bwd_kernel<T, 4><<<ROWDOT_BWD_BLOCKS, 256, 0, (cudaStream_t)stream>>>((const T *)h, g, u, (T *)dh, partials, rows, d))); }
+    reduce_partials_kernel<false><<<(d + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, ROWDOT_BWD_BLOCKS, d, d, du, nullptr, nullptr);
+    return check_launch("rowdot_bwd");
+}
 
 int cpm_set_rng_base(const uint64_t *device_counter) {
     g_rng_base = reinterpret_cast<const unsigned long long *>(device_counter);

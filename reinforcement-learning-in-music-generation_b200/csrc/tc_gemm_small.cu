@@ -1,0 +1,164 @@
+// The Linear layers of the RECURRENT token step (M = songs in flight, 256 in the bench) on tcgen05:
+//
+//     D[M x N] = epilogue( A[M x K] . W[N x K]^T + bias )            bf16 in / out, fp32 accumulation in TMEM
+//
+// One token step of the rollout (testing-no-type-cp.py:157-167 batched) is a chain of ~90 dependent small kernels; each
+// GEMM in it has 0.3 us of math and is bound by (a) the launch / drain gap to its neighbours and (b) how fast ONE SM can
+// pull its operand tiles out of L2 (measured ~48 B/clk per SM).  This kernel is shaped for that regime, not for FLOPs:
+//
+//  * small tiles, many CTAs: 64 rows x 32 columns per CTA (UMMA M = 64, N = 32), so M = 256 spreads over 4 x N/32 CTAs and
+//    the activation tile a CTA must ingest is 64 x K;
+//  * < 100 KB of shared memory and 32 TMEM columns per CTA: two CTAs per SM, and - with programmatic dependent launch - the
+//    NEXT kernel's CTAs become resident while this one still runs;
+//  * PDL: everything that does not depend on the previous kernel (barrier init, TMEM allocation, tensor-map prefetch and the
+//    whole WEIGHT tile stream) is issued before griddepcontrol.wait; only the activation fetch, the UMMAs and the epilogue stay
+//    on the critical path.  griddepcontrol.launch_dependents is issued right after the set-up;
+//  * epilogues: bias, or bias + exact-erf GELU on the bf16-rounded pre-activation (bit-identical to the GEMM + gelu kernel
+//    pair of the teacher-forced path).
+//
+// K is streamed in 64-wide blocks through an 8-deep ring (12 KB per stage); for K <= 512 every block has its own stage and the
+// producer never waits.  Warps 0-3: epilogue (M = 64 accumulator layout: warp w holds rows 16w..16w+15 in lanes 0..15),
+// warp 4: TMA producer, warp 5: UMMA issuer.
+#include "cpm_common.cuh"
+#include "tc_common.cuh"
+
+namespace cpm {
+namespace {
+using namespace tc;
+
+constexpr int SG_BM = 64, SG_BN = 32, SG_NS = 8, SG_THREADS = 192;
+constexpr uint32_t SG_A_BYTES = SG_BM * 128, SG_W_BYTES = SG_BN * 128, SG_STAGE = SG_A_BYTES + SG_W_BYTES;      // 8 KB + 4 KB
+constexpr uint32_t SG_OFF_BAR = SG_NS * SG_STAGE;                                                                // 98304
+constexpr uint32_t SG_SMEM = SG_OFF_BAR + 256;
+constexpr uint32_t IDESC_SG = idesc_bf16(SG_BM, SG_BN, false, false);
+
+struct SmallArgs {
+    const float *bias;
+    __nv_bfloat16 *D;
+    int64_t ldd;
+    int M, N, K;
+};
+
+template <int EPI>
+__global__ void __launch_bounds__(SG_THREADS, 2)
+gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const SmallArgs a) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + SG_OFF_BAR), *bar_empty = bar_full + SG_NS, *bar_done = bar_empty + SG_NS;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_done + 1);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int n0 = blockIdx.x * SG_BN, m0 = blockIdx.y * SG_BM, KB = (a.K + 63) >> 6;
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        for (int s = 0; s < SG_NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
+        mbar_init(bar_done, 1);
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmW);
+    }
+    if (warp == 4) tmem_alloc<32>(tmem_slot);
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+    if (tid == 0) griddep_launch();                      // the next kernel may start its own set-up / weight prefetch
+
+    if (warp == 4) {
+        if (lane == 0) {                                 // ---- TMA producer
+            const int pre = KB < SG_NS ? KB : SG_NS;
+            for (int i = 0; i < pre; ++i) {              // weights first: they do not depend on the previous kernel
+                mbar_expect_tx(bar_full + i, SG_STAGE);
+                tma_load_2d(sm + i * SG_STAGE + SG_A_BYTES, &tmW, bar_full + i, i * 64, n0);
+            }
+            griddep_wait();                              // the activations (and every buffer this kernel writes) belong to the chain
+            for (int i = 0; i < pre; ++i) tma_load_2d(sm + i * SG_STAGE, &tmA, bar_full + i, i * 64, m0);
+            for (int i = pre; i < KB; ++i) {
+                const int s = i % SG_NS;
+                mbar_wait(bar_empty + s, ((i / SG_NS) - 1) & 1);
+                mbar_expect_tx(bar_full + s, SG_STAGE);
+                tma_load_2d(sm + s * SG_STAGE + SG_A_BYTES, &tmW, bar_full + s, i * 64, n0);
+                tma_load_2d(sm + s * SG_STAGE, &tmA, bar_full + s, i * 64, m0);
+            }
+        }
+    } else if (warp == 5) {
+        if (lane == 0) {                                 // ---- UMMA issuer
+            for (int i = 0; i < KB; ++i) {
+                const int s = i % SG_NS;
+                mbar_wait(bar_full + s, (i / SG_NS) & 1);
+                tc_fence_after();
+                const uint64_t dA = smem_desc_sw128(smem_u32(sm + s * SG_STAGE)), dW = smem_desc_sw128(smem_u32(sm + s * SG_STAGE + SG_A_BYTES));
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem, dA + 2 * k, dW + 2 * k, IDESC_SG, (i > 0 || k > 0) ? 1u : 0u);
+                mma_commit(bar_empty + s);
+            }
+            mma_commit(bar_done);
+        }
+    } else {
+        // ---- epilogue: lanes 0..15 of warp w own accumulator rows 16w + lane, 32 columns each
+        const int row = m0 + 16 * warp + (lane & 15);
+        float bv[32];
+#pragma unroll
+        for (int j = 0; j < 32; ++j) bv[j] = (a.bias && n0 + j < a.N) ? __ldg(a.bias + n0 + j) : 0.f;       // weights: no dependency
+        mbar_wait(bar_done, 0);                          // the UMMAs ran after the producer's griddepcontrol.wait: ordered behind the chain
+        tc_fence_after();
+        uint32_t r[32];
+        tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), r);
+        tmem_ld_wait();
+        if (lane < 16 && row < a.M) {
+            __nv_bfloat16 *dst = a.D + (int64_t)row * a.ldd + n0;
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                uint32_t w[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                    float x0 = __uint_as_float(r[8 * q + 2 * j]) + bv[8 * q + 2 * j], x1 = __uint_as_float(r[8 * q + 2 * j + 1]) + bv[8 * q + 2 * j + 1];
+                    if (EPI == CPM_GEMM_EPI_GELU) {      // GELU of the bf16-rounded pre-activation, like the GEMM + gelu kernel pair
+                        x0 = gelu_f<false>(bf16_round(x0));
+                        x1 = gelu_f<false>(bf16_round(x1));
+                    }
+                    w[j] = pack_bf16(x0, x1);
+                }
+                if (n0 + 8 * q + 8 <= a.N) *reinterpret_cast<uint4 *>(dst + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 4) tmem_dealloc<32>(tmem);
+}
+
+template <int EPI>
+int launch_small(const CUtensorMap &tA, const CUtensorMap &tW, const SmallArgs &a, cudaStream_t st) {
+    static bool attr = false;
+    if (!attr) {
+        cudaError_t e = cudaFuncSetAttribute(gemm_small_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM);
+        if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_small shared-memory attribute: %s", cudaGetErrorString(e));
+        attr = true;
+    }
+    const dim3 grid((a.N + SG_BN - 1) / SG_BN, (a.M + SG_BM - 1) / SG_BM);
+    cudaError_t e = launch_chain(gemm_small_kernel<EPI>, grid, dim3(SG_THREADS), SG_SMEM, st, tA, tW, a);
+    if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_small launch: %s", cudaGetErrorString(e));
+    return CPM_OK;
+}
+
+}  // namespace
+}  // namespace cpm
+
+using namespace cpm;
+
+extern "C" int cpm_gemm_nt_small(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int M, int N, int K,
+                                 const float *bias, int epilogue, void *stream) {
+    CPM_REQUIRE(A && W && D, CPM_ERR_NULL, "gemm_nt_small: A/W/D must be non-NULL");
+    CPM_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0, CPM_ERR_BAD_SHAPE, "gemm_nt_small: M=%d N=%d K=%d (N, K multiples of 8)", M, N, K);
+    CPM_REQUIRE(lda >= K && ldw >= K && ldd >= N && lda % 8 == 0 && ldw % 8 == 0 && ldd % 8 == 0, CPM_ERR_BAD_SHAPE, "gemm_nt_small: row strides");
+    CPM_REQUIRE(aligned16(A) && aligned16(W) && aligned16(D), CPM_ERR_BAD_ALIGN, "gemm_nt_small: operands must be 16-byte aligned");
+    CPM_REQUIRE(epilogue == CPM_GEMM_EPI_BIAS || epilogue == CPM_GEMM_EPI_GELU, CPM_ERR_BAD_SHAPE, "gemm_nt_small: epilogue %d", epilogue);
+    CUtensorMap tA, tW;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, SG_BM))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tW, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, SG_BN))) return rc;
+    SmallArgs a;
+    a.bias = bias; a.D = (__nv_bfloat16 *)D; a.ldd = ldd; a.M = M; a.N = N; a.K = K;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (epilogue == CPM_GEMM_EPI_GELU) return launch_small<CPM_GEMM_EPI_GELU>(tA, tW, a, st);
+    return launch_small<CPM_GEMM_EPI_BIAS>(tA, tW, a, st);
+}

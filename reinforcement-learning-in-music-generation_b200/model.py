@@ -277,16 +277,21 @@ class Critic_Transformer(CPLinearTransformer):
         for a, n in zip(self.attrs, self.n_token):
             setattr(self, f"{a}_value", nn.Linear(n, 1))
 
+    def value_collapse(self):
+        """The read-out is linear in the hidden state: mean_a(value_a(proj_a(h))) = h . u + c with
+        u = mean_a(W_a^T w_a) (d,) and c = mean_a(w_a . b_a + beta_a).  Built with autograd through these tiny products, so
+        the gradients reach proj_* and *_value exactly as through the six logits tensors - which are never formed."""
+        u, c = 0.0, 0.0
+        for a in self.attrs:
+            proj, val = getattr(self, f"proj_{a}"), getattr(self, f"{a}_value")
+            u = u + val.weight[0] @ proj.weight
+            c = c + val.weight[0] @ proj.bias + val.bias[0]
+        return u / len(self.attrs), c / len(self.attrs)
+
     def value_per_position(self, x):
-        """(N,L,A) -> (N,L) fp32: mean_a( Linear_a(logits_a) ) — one GEMV over the concatenated logits."""
-        lc = self.logits_concat(self.hidden(x)).float()
-        w = torch.zeros(self.logits_width, dtype=torch.float32, device=lc.device)
-        b = 0.0
-        for i, a in enumerate(self.attrs):
-            lin = getattr(self, f"{a}_value")
-            w = w.index_put((torch.arange(self.seg[i], self.seg[i + 1], device=lc.device),), lin.weight[0])
-            b = b + lin.bias[0]
-        return (lc @ w + b) / len(self.attrs)
+        """(N,L,A) -> (N,L) fp32: mean_a( Linear_a(logits_a) ), evaluated as one row dot of the hidden state (no logits GEMM)."""
+        u, c = self.value_collapse()
+        return ops.rowdot(self.hidden(x), u, c)
 
     def value_produce(self, x):
         return self.value_per_position(x).mean(dim=1, keepdim=True)

@@ -1061,6 +1061,40 @@ def reward_head(h, u, c, want_scores=False):
     return (reward, scores) if want_scores else reward
 
 
+class _RowDot(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, h, u, c):
+        _cuda(h, u, c)
+        h = h.contiguous()
+        d = h.shape[-1]
+        rows = h.numel() // d
+        u32 = u.detach().to(torch.float32).contiguous()
+        c32 = None if c is None else c.detach().to(torch.float32).reshape(1).contiguous()
+        out = torch.empty(h.shape[:-1], dtype=torch.float32, device=h.device)
+        check(_lib.load().cpm_rowdot_fwd(_p(h), _p(u32), _p(c32), _p(out), rows, d, _dt(h), _st()))
+        ctx.save_for_backward(h, u32)
+        ctx.has_c = c is not None
+        return out
+
+    @staticmethod
+    def backward(ctx, g):
+        h, u32 = ctx.saved_tensors
+        d = h.shape[-1]
+        rows = h.numel() // d
+        g = g.to(torch.float32).contiguous()
+        lib = _lib.load()
+        dh = torch.empty_like(h) if ctx.needs_input_grad[0] else None
+        du = torch.empty(d, dtype=torch.float32, device=h.device)
+        partials = torch.empty(lib.cpm_rowdot_partials_rows() * d, dtype=torch.float32, device=h.device)
+        check(lib.cpm_rowdot_bwd(_p(h), _p(g), _p(u32), _p(dh), _p(du), _p(partials), rows, d, _dt(h), _st()))
+        return dh, du, (g.sum().reshape(()) if ctx.has_c else None)
+
+
+def rowdot(h, u, c=None):
+    """out[...] = h[..., :] . u + c in fp32 (cpm_rowdot_fwd/bwd): differentiable in h, u (d,) and the scalar tensor c."""
+    return _RowDot.apply(h, u, c)
+
+
 def rollout_advance(tokens, history_tok, vals, history_f, step_dev, max_steps):
     n_tok = tokens.numel() if tokens is not None else 0
     n_f = vals.numel() if vals is not None else 0

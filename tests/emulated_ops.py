@@ -160,7 +160,12 @@ def reward_head(h, u, c, want_scores=False):
     return (scores.mean(-1), scores) if want_scores else scores.mean(-1)
 
 
-EMULATED = dict(cp_embed=cp_embed, add_pe=add_pe, ln_residual=ln_residual, gelu_dropout=gelu_dropout, colsum=colsum,
+def rowdot(h, u, c=None):
+    out = h.float() @ u.float()
+    return out if c is None else out + c
+
+
+EMULATED = dict(rowdot=rowdot, cp_embed=cp_embed, add_pe=add_pe, ln_residual=ln_residual, gelu_dropout=gelu_dropout, colsum=colsum,
                 causal_linear_attention_fused=causal_linear_attention_fused, linattn_step=linattn_step, heads_sample=heads_sample,
                 heads_logp=heads_logp, masked_ce=masked_ce, returns_scan=returns_scan, zscore=zscore, ppo_loss_compat=ppo_loss_compat,
                 dqn_td_loss=dqn_td_loss, reward_head=reward_head, rollout_advance=rollout_advance)

@@ -563,7 +563,7 @@ def test_linattn_tc_fwd(cuda, cpm, shape, impl):
     gen = torch.Generator().manual_seed(L + H)
     q, k, v = (torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16() for _ in range(3))
     out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=impl)
-    assert cpm.ops.linattn_last_impl() == ("tcgen05" if impl == 2 else "tcgen05-cp")
+    assert cpm.ops.linattn_last_impl() == ("tcgen05" if impl == 2 else ("tcgen05-cp-stream" if N * H >= 96 else "tcgen05-cp"))
     torch.cuda.synchronize()
     ref_simt, den_simt = cpm.ops.linattn_fwd_raw(q, k, v, impl=1)
     _cmp(out, ref_simt.float(), 3e-2, 2e-2, "tc vs simt")
@@ -601,7 +601,7 @@ def test_linattn_tc_bwd(cuda, cpm, shape, impl):
     out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=impl, saved=saved)
     gq, gk, gv = (torch.empty_like(q) for _ in range(3))
     cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=impl)
-    assert cpm.ops.linattn_last_impl() == ("tcgen05" if impl == 2 else "tcgen05-cp")
+    assert cpm.ops.linattn_last_impl() == ("tcgen05" if impl == 2 else ("tcgen05-cp-stream" if N * H >= 96 else "tcgen05-cp"))
     torch.cuda.synchronize()
     if impl == 3:          # same result when backward reads the forward's saved prefix states
         tq, tk, tv = (torch.empty_like(q) for _ in range(3))
@@ -616,6 +616,80 @@ def test_linattn_tc_bwd(cuda, cpm, shape, impl):
         _, rq, rk, rv = _oracle_attn(q.float(), k.float(), v.float(), go.float())
         for name, a, b in (("gq", gq, rq), ("gk", gk, rk), ("gv", gv, rv)):
             _cmp(a, b, 4e-2, 3e-2, f"tc vs oracle {name}")
+
+
+def _oracle_chains(q, k, v, go, pairs):
+    """fp64 oracle (ft CausalLinearAttention restated, oracle/ft_oracle.py) on selected (batch, head) chains only: chains are
+    independent, so any subset can be checked at sizes where the whole tensor would not fit the quadratic restatement."""
+    sel = lambda t: torch.stack([t[n, :, h] for n, h in pairs], 0)[:, :, None, :].float()      # (P, L, 1, 64)
+    return _oracle_attn(sel(q), sel(k), sel(v), sel(go))
+
+
+@pytest.mark.parametrize("shape", [(16, 256, 8), (12, 384, 8), (100, 128 * 3, 1)])
+def test_linattn_streaming_kernels_vs_oracle(cuda, cpm, shape):
+    """The DEFAULT bench path: with N*H >= 96 chains the forward prefix and backward suffix states come from the STREAMING
+    kernels (cp_prefix_stream_fwd / cp_suffix_stream_bwd: one CTA per chain, S and z carried in tensor memory), not from the
+    per-chunk state kernels + scan the small shapes above exercise.  Held directly to the fp64 oracle on every chain."""
+    N, L, H = shape
+    gen = torch.Generator().manual_seed(N * 5 + L)
+    q, k, v, go = (torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16() for _ in range(4))
+    saved = cpm.ops.linattn_saved(N, L, H, cuda)
+    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=0, saved=saved)
+    assert cpm.ops.linattn_last_impl() == "tcgen05-cp-stream"
+    gq, gk, gv = (torch.empty_like(q) for _ in range(3))
+    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=0, saved=saved)
+    assert cpm.ops.linattn_last_impl() == "tcgen05-cp-stream"
+    pairs = [(n, h) for n in range(N) for h in range(H)]
+    for i in range(0, len(pairs), 32):
+        pp = pairs[i:i + 32]
+        ro, rq, rk, rv = _oracle_chains(q, k, v, go, pp)
+        pick = lambda t: torch.stack([t[n, :, h] for n, h in pp], 0)[:, :, None, :]
+        _cmp(pick(out), ro, 3e-2, 2e-2, "out vs oracle")
+        for name, a, b in (("gq", gq, rq), ("gk", gk, rk), ("gv", gv, rv)):
+            _cmp(pick(a), b, 4e-2, 3e-2, f"{name} vs oracle")
+
+
+@pytest.mark.parametrize("shape,n_chains", [((128, 1024, 8), 12), ((32, 512, 8), 12), ((1, 8192, 16), 2)])
+def test_linattn_full_size_sampled_chains_vs_oracle(cuda, cpm, shape, n_chains):
+    """BASELINE shapes as the bench runs them - the update minibatch 128 x 1024 x 8 (cfg3), the pretraining batch 32 x 512 x 8
+    (cfg2) and the long sequence 8192 x 16 heads (cfg5) - compared with the fp64 oracle on a seeded sample of (batch, head)
+    chains (forward and all three gradients).  cfg5 has 16 chains -> per-chunk state kernels + scan; the others stream."""
+    N, L, H = shape
+    gen = torch.Generator().manual_seed(L + 17 * N)
+    q, k, v, go = (torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16() for _ in range(4))
+    saved = cpm.ops.linattn_saved(N, L, H, cuda)
+    out, den = cpm.ops.linattn_fwd_raw(q, k, v, impl=0, saved=saved)
+    gq, gk, gv = (torch.empty_like(q) for _ in range(3))
+    cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, impl=0, saved=saved)
+    assert cpm.ops.linattn_last_impl() == ("tcgen05-cp-stream" if N * H >= 96 else "tcgen05-cp")
+    idx = torch.randperm(N * H, generator=gen)[:n_chains].tolist()
+    scale = 1.0 + math.sqrt(L / 1024.0)          # gradients accumulate over the sequence: absolute tolerance grows ~ sqrt(L)
+    for i in idx:
+        pp = [(i // H, i % H)]
+        ro, rq, rk, rv = _oracle_chains(q, k, v, go, pp)
+        pick = lambda t: t[pp[0][0], :, pp[0][1]][None, :, None, :]
+        _cmp(pick(out), ro, 3e-2, 2e-2, f"out chain {pp}")
+        for name, a, b in (("gq", gq, rq), ("gk", gk, rk), ("gv", gv, rv)):
+            _cmp(pick(a), b, 4e-2 * scale, 3e-2, f"{name} chain {pp}")
+
+
+def test_rowdot_fwd_bwd(cuda, cpm):
+    """out = h . u + c (fp32) and its gradients vs float64 (the collapsed critic read-out)."""
+    gen = torch.Generator().manual_seed(4)
+    for dtype, tol in ((torch.float32, 1e-4), (torch.bfloat16, 2e-2)):
+        h = torch.randn(3, 700, 512, generator=gen).to(cuda).to(dtype).requires_grad_()
+        u = (torch.randn(512, generator=gen) / 20).to(cuda).requires_grad_()
+        c = torch.tensor(0.3, device=cuda, requires_grad=True)
+        g = torch.randn(3, 700, generator=gen).to(cuda)
+        out = cpm.ops.rowdot(h, u, c)
+        out.backward(g)
+        hd, ud, cd = h.detach().double().cpu().requires_grad_(), u.detach().double().cpu().requires_grad_(), c.detach().double().cpu().requires_grad_()
+        ref = hd @ ud + cd
+        ref.backward(g.double().cpu())
+        _cmp(out, ref, 1e-4, 1e-5, "rowdot")
+        _cmp(h.grad, hd.grad, tol * 0.1, tol, "dh")
+        _cmp(u.grad, ud.grad, 2e-3, 1e-4, "du")
+        _cmp(c.grad, cd.grad, 1e-3, 1e-5, "dc")
 
 
 # ------------------------------------------------------------------ fused skinny linear (rollout step)
