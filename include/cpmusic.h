@@ -221,17 +221,36 @@ int cpm_set_rng_base(const uint64_t *device_counter);
  *                         dense (ldd == N); the dropout mask is the one cpm_gelu_fwd draws for (seed, rng_offset)
  *     CPM_GEMM_EPI_DGELU  D = acc * gelu'(aux) * dropout mask               aux = the stored pre-activation h (M x N, dense);
  *                         same mask as the forward for the same (seed, rng_offset): what cpm_gelu_bwd computes
- * cpm_gemm_tn:  dW[N x K] += dY[T x N]^T . X[T x K] (fp32, row stride ldw) and, if dbias != NULL, dbias[N] += column sums of
- *   dY.  ACCUMULATES with fp32 atomics (zero the buffers for a fresh gradient): summation order over token ranges is not
- *   fixed, so results are reproducible to fp32 rounding, not bitwise. */
+ * cpm_gemm_tn:  dW[N x K] += dY[T x N]^T . X[T x K] (fp32): the weight gradient of a Linear layer, both operands read
+ *   MN-major from the row-major activations (no transposes), 256 x 512 output tiles, the token range split over clusters.
+ *   Output rows are routed to n_dst destination matrices of rows_per_dst rows each (row stride ldw): the separate q / k / v
+ *   master gradients behind ONE fused projection GEMM; n_dst = 1, rows_per_dst = N for a plain layer.  dW_host: host array
+ *   of n_dst device pointers.  ACCUMULATES with fp32 atomics (zero the buffers for a fresh gradient; this is also the
+ *   accumulation across micro-batches): summation order over token ranges is not fixed, so results are reproducible to fp32
+ *   rounding, not bitwise.  (Bias gradients: cpm_colsum.) */
+#define CPM_GEMM_TN_MAX_DST 4
 #define CPM_GEMM_EPI_BIAS 0
 #define CPM_GEMM_EPI_GELU 1
 #define CPM_GEMM_EPI_DGELU 2
+/* Schedule override for cpm_gemm_nt (A/B measurements and tests): 0 auto | 1 stream (A and B tiles both streamed, one
+ * 256 x 256 tile at a time) | 3 wide 256 x 512 tile (N <= 512).  Unsupported requests fall back to auto. */
+int cpm_gemm_set_mode(int mode);
 int cpm_gemm_nt(const void *A, int64_t lda, const void *B, int64_t ldb, void *D, int64_t ldd, void *D2, int64_t ldd2,
                 int M, int N, int K, const float *bias, int epilogue, const void *aux, int64_t ld_aux,
                 float p_drop, uint64_t seed, uint64_t rng_offset, void *stream);
-int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *dW, int64_t ldw, float *dbias,
-                int T, int N, int K, void *stream);
+int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *const *dW_host, int n_dst, int rows_per_dst,
+                int64_t ldw, int T, int N, int K, void *stream);
+
+/* The same product for the recurrent token step (M = sequences in flight): 64 x 32 tiles, two CTAs per SM, programmatic
+ * dependent launch (the weight tiles are fetched before griddepcontrol.wait).  Epilogues CPM_GEMM_EPI_BIAS, CPM_GEMM_EPI_GELU
+ * (single output: gelu of the bf16-rounded pre-activation; no dropout - generation runs in eval mode).
+ * Reference loop being served: testing-no-type-cp.py:157-167 (forward_hidden(..., is_training=False) + forward_output). */
+int cpm_gemm_nt_small(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int M, int N, int K,
+                      const float *bias, int epilogue, void *stream);
+/* 1: launch the token-step kernels (cpm_gemm_nt_small, cpm_linattn_step, cpm_ln_residual_fwd, cpm_embed_fwd, cpm_add_pe,
+ * cpm_heads_sample, cpm_rollout_advance) with the programmatic-stream-serialization attribute, so each overlaps its set-up
+ * with its predecessor's tail; they all block in griddepcontrol.wait before touching chain data.  0 (default): plain launches. */
+int cpm_set_chain_pdl(int on);
 
 /* bias + exact-erf GELU + dropout (ft activation='gelu' => F.gelu; K6):
  *     y = drop(gelu(x + bias))   (bias fp32 (d) or NULL)

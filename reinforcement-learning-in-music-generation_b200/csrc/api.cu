@@ -5,6 +5,7 @@
 namespace cpm {
 thread_local char g_err[512] = "";
 thread_local const char *g_linattn_impl = "none";
+int g_chain_pdl = 0;
 
 int fail(int code, const char *fmt, ...) {
     va_list ap;
@@ -67,6 +68,10 @@ __global__ void __launch_bounds__(256) linattn_step_kernel(const T *__restrict__
         const F8 lo = ld_stream(srow), hi = ld_stream(srow + 8);
         s[0] = lo.a; s[1] = lo.b; s[2] = hi.a; s[3] = hi.b;
     }
+    // Chain kernel (cpm_common.cuh): the state tile above belongs to this layer alone (last touched a whole token step ago), so
+    // its HBM latency may overlap the tail of the q/k/v projection; q, k, v are the predecessor's output.
+    griddep_launch();
+    griddep_wait();
     const int64_t qoff = (int64_t)n * ld_qkv + h * 64;
     const float ke = phi(to_f(k[qoff + e])), qe = phi(to_f(q[qoff + e]));
     float vv[16];
@@ -392,6 +397,7 @@ using namespace cpm;
 extern "C" {
 
 int cpm_version(void) { return CPM_VERSION; }
+int cpm_set_chain_pdl(int on) { g_chain_pdl = on ? 1 : 0; return CPM_OK; }
 const char *cpm_last_error_string(void) { return g_err; }
 const char *cpm_linattn_last_impl(void) { return g_linattn_impl; }
 const char *cpm_error_name(int code) {
@@ -512,12 +518,11 @@ int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, floa
         return check_launch("linattn_step (wide)");
     }
     if (dtype == CPM_F32)
-        linattn_step_kernel<float><<<N * H, 256, 0, st>>>((const float *)q, (const float *)k, (const float *)v, S, Z,
-                                                          (float *)out, H, ld_qkv, ld_o, eps);
+        launch_chain(linattn_step_kernel<float, 0>, dim3(N * H), dim3(256), 0, st, (const float *)q, (const float *)k, (const float *)v, S, Z,
+                     (float *)out, H, ld_qkv, ld_o, eps, (const float *)nullptr);
     else if (dtype == CPM_BF16)
-        linattn_step_kernel<__nv_bfloat16><<<N * H, 256, 0, st>>>((const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k,
-                                                                  (const __nv_bfloat16 *)v, S, Z, (__nv_bfloat16 *)out, H,
-                                                                  ld_qkv, ld_o, eps);
+        launch_chain(linattn_step_kernel<__nv_bfloat16, 0>, dim3(N * H), dim3(256), 0, st, (const __nv_bfloat16 *)q, (const __nv_bfloat16 *)k,
+                     (const __nv_bfloat16 *)v, S, Z, (__nv_bfloat16 *)out, H, ld_qkv, ld_o, eps, (const float *)nullptr);
     else
         return fail(CPM_ERR_BAD_DTYPE, "linattn_step: dtype %d", dtype);
     return check_launch("linattn_step");

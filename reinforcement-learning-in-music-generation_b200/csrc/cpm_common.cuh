@@ -179,6 +179,32 @@ inline uint32_t dropout_threshold8(float p) {
 inline float dropout_scale8(float p) { uint32_t t = dropout_threshold8(p); return t ? 256.0f / (256.0f - (float)t) : 1.0f; }
 
 
+// ---------------------------------------------------------------- programmatic dependent launch (the rollout token step)
+// The token step is a chain of small dependent kernels.  With cpm_set_chain_pdl(1) every kernel of the chain is launched with
+// the programmatic-stream-serialization attribute: it may become resident while its predecessor still runs, executes its
+// set-up, and blocks in griddep_wait() until the predecessor has completed and flushed.  RULE for every chain kernel: call
+// griddep_wait() before the first access to anything another kernel of the chain produces OR still reads (buffers are recycled
+// by the allocator, so writes are ordered too); only constant data (weights, tables) may be touched before it.
+__device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+extern int g_chain_pdl;
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    if (g_chain_pdl) {
+        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[0].val.programmaticStreamSerializationAllowed = 1;
+        cfg.attrs = at;
+        cfg.numAttrs = 1;
+    }
+    return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
 inline int num_sms() {
     static int n = 0;
     if (!n) { int dev = 0; cudaGetDevice(&dev); cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev); if (n <= 0) n = 148; }

@@ -27,6 +27,8 @@ struct EmbedParams {
 template <typename T>
 __global__ void __launch_bounds__(256) embed_fwd_kernel(const int64_t *__restrict__ idx, EmbedParams p, int64_t T_, T *__restrict__ out,
                                                         int *err_flag) {
+    griddep_launch();
+    griddep_wait();                                     // chain kernel: idx is the previous token step's sample
     const int width = p.off[p.n_attr], G = width >> 3;
     const int64_t total = T_ * G;
     for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
@@ -88,6 +90,8 @@ template <typename T>
 __global__ void __launch_bounds__(256) add_pe_kernel(const T *__restrict__ x, const float *__restrict__ pe, T *__restrict__ y, int64_t rows,
                                                      int L, int d, int pos_offset, const int32_t *__restrict__ pos_dev, int max_len,
                                                      uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset_h, const unsigned long long *rng_base) {
+    griddep_launch();
+    griddep_wait();
     const uint64_t rng_offset = rng_off(rng_offset_h, rng_base);
     const int G = d >> 3;
     const int64_t total = rows * G;
@@ -138,6 +142,8 @@ __global__ void __launch_bounds__(128) ln_residual_fwd_kernel(const T *__restric
                                                               const float *__restrict__ beta, T *__restrict__ y, T *__restrict__ s_out,
                                                               float *__restrict__ mean_out, float *__restrict__ rstd_out, int64_t rows, int d,
                                                               float eps, uint32_t thr, float scale, uint64_t seed, uint64_t rng_offset_h, const unsigned long long *rng_base) {
+    griddep_launch();
+    griddep_wait();
     const uint64_t rng_offset = rng_off(rng_offset_h, rng_base);
     const int lane = threadIdx.x & 31;
     const int G = d >> 3;
@@ -609,7 +615,7 @@ int cpm_embed_fwd(const int64_t *idx, const float *const *tables_host, const int
     if (rc) return rc;
     CPM_REQUIRE(aligned16(out), CPM_ERR_BAD_ALIGN, "embed_fwd: out not 16-byte aligned");
     const int64_t items = T_ * (p.off[n_attr] / 8);
-    DISPATCH_DTYPE(dtype, embed_fwd_kernel<T><<<grid_for(items, 256), 256, 0, (cudaStream_t)stream>>>(idx, p, T_, (T *)out, err_flag));
+    DISPATCH_DTYPE(dtype, launch_chain(embed_fwd_kernel<T>, dim3(grid_for(items, 256)), dim3(256), 0, (cudaStream_t)stream, idx, p, T_, (T *)out, err_flag));
     return check_launch("embed_fwd");
 }
 
@@ -646,8 +652,8 @@ int cpm_add_pe(const void *x, const float *pe, void *y, int64_t rows, int L, int
     CPM_REQUIRE(aligned16(x) && aligned16(y) && aligned16(pe), CPM_ERR_BAD_ALIGN, "add_pe: alignment");
     if (rows == 0) return CPM_OK;
     const uint32_t thr = dropout_threshold(p_drop);
-    DISPATCH_DTYPE(dtype, add_pe_kernel<T><<<grid_for(rows * (d / 8), 256), 256, 0, (cudaStream_t)stream>>>(
-                              (const T *)x, pe, (T *)y, rows, L, d, pos_offset, pos_dev, max_len, thr, dropout_scale(p_drop), seed, rng_offset, g_rng_base));
+    DISPATCH_DTYPE(dtype, launch_chain(add_pe_kernel<T>, dim3(grid_for(rows * (d / 8), 256)), dim3(256), 0, (cudaStream_t)stream,
+                                       (const T *)x, pe, (T *)y, rows, L, d, pos_offset, pos_dev, max_len, thr, dropout_scale(p_drop), seed, rng_offset, g_rng_base));
     return check_launch("add_pe");
 }
 
@@ -671,7 +677,7 @@ int cpm_ln_residual_fwd(const void *x, const void *res, const float *res_bias, c
     if (rows == 0) return CPM_OK;
     const uint32_t thr = res ? dropout_threshold(p_drop) : 0u;
     const int grid = grid_for(rows * 32, 128);
-    DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, ln_residual_fwd_kernel<T, MAXV><<<grid, 128, 0, (cudaStream_t)stream>>>(
+    DISPATCH_DTYPE(dtype, DISPATCH_MAXV(d, launch_chain(ln_residual_fwd_kernel<T, MAXV>, dim3(grid), dim3(128), 0, (cudaStream_t)stream,
                                                (const T *)x, (const T *)res, res ? res_bias : nullptr, gamma, beta, (T *)y, (T *)s_out, mean, rstd, rows, d, eps, thr,
                                                dropout_scale(p_drop), seed, rng_offset, g_rng_base)));
     return check_launch("ln_residual_fwd");

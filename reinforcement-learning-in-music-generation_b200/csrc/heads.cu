@@ -49,6 +49,8 @@ __global__ void __launch_bounds__(WARPS * 32) heads_sample_kernel(const T *__res
                                                                   uint64_t seed, int64_t seq_base, int step, const int32_t *__restrict__ step_dev,
                                                                   int64_t *__restrict__ tokens, float *__restrict__ logp, float *__restrict__ entropy) {
     __shared__ float sbuf[WARPS][MAX_SEG];
+    griddep_launch();
+    griddep_wait();                                     // chain kernel: the logits are the heads GEMM's output
     __shared__ float sprob[WARPS][MAX_SEG];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     float *buf = sbuf[warp], *pr = sprob[warp];
@@ -470,8 +472,8 @@ int cpm_heads_sample(const void *logits, int64_t rows, int64_t ld_logits, const 
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, temperature_host, top_p_host);
     if (rc) return rc;
     if (rows <= 0) return rows == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "heads_sample: rows=%lld", (long long)rows);
-    DISPATCH_DTYPE(dtype, heads_sample_kernel<T><<<warp_grid(rows * n_attr), WARPS * 32, 0, (cudaStream_t)stream>>>(
-                              (const T *)logits, rows, ld_logits, sp, mode, seed, seq_base, step, step_dev, tokens, logp, entropy));
+    DISPATCH_DTYPE(dtype, launch_chain(heads_sample_kernel<T>, dim3(warp_grid(rows * n_attr)), dim3(WARPS * 32), 0, (cudaStream_t)stream,
+                                       (const T *)logits, rows, ld_logits, sp, mode, seed, seq_base, step, step_dev, tokens, logp, entropy));
     return check_launch("heads_sample");
 }
 

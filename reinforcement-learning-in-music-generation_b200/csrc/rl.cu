@@ -234,6 +234,8 @@ __global__ void __launch_bounds__(256) dqn_td_kernel(const T *__restrict__ q_log
 __global__ void __launch_bounds__(256) rollout_advance_kernel(const int64_t *__restrict__ tokens, int64_t *__restrict__ htok, int64_t n_tok,
                                                               const float *__restrict__ vals, float *__restrict__ hf, int64_t n_f,
                                                               int32_t *step_dev, int32_t max_steps) {
+    griddep_launch();
+    griddep_wait();
     const int32_t step = *step_dev;
     if (step < max_steps) {
         if (htok) for (int64_t i = threadIdx.x; i < n_tok; i += blockDim.x) htok[(int64_t)step * n_tok + i] = tokens[i];
@@ -390,7 +392,7 @@ int cpm_rollout_advance(const int64_t *tokens, int64_t *history_tok, int64_t n_t
     CPM_REQUIRE(step_dev, CPM_ERR_NULL, "rollout_advance: step_dev is NULL");
     CPM_REQUIRE(!history_tok || tokens, CPM_ERR_NULL, "rollout_advance: tokens is NULL");
     CPM_REQUIRE(!history_f || vals, CPM_ERR_NULL, "rollout_advance: vals is NULL");
-    rollout_advance_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(tokens, history_tok, n_tok, vals, history_f, n_f, step_dev, max_steps);
+    launch_chain(rollout_advance_kernel, dim3(1), dim3(256), 0, (cudaStream_t)stream, tokens, history_tok, n_tok, vals, history_f, n_f, step_dev, max_steps);
     return check_launch("rollout_advance");
 }
 

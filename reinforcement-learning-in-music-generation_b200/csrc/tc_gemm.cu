@@ -34,13 +34,11 @@ using namespace tc;
 constexpr int GM_THREADS = 256, GM_NS = 5;
 constexpr uint32_t GM_A_BYTES = 16384, GM_STAGE = 32768;                 // per CTA: A half 128 x 64, B half 128 x 64 (bf16)
 constexpr uint32_t GM_OFF_STG = GM_NS * GM_STAGE;                        // epilogue staging: 4 warps x 2 buffers x [32 rows x 128 B]
-constexpr uint32_t GM_OFF_ONES = GM_OFF_STG;                             // (tn kernel) [64 x 128 B] of bf16 ones instead of staging
 constexpr uint32_t GM_OFF_BAR = GM_OFF_STG + 32768;
 constexpr uint32_t GM_SMEM = GM_OFF_BAR + 256;                           // full[5] empty[5] tfull[2] tempty[2] + TMEM slot
 
 constexpr uint32_t IDESC_NT = idesc_bf16(256, 256, false, false);
 constexpr uint32_t IDESC_TN = idesc_bf16(256, 256, true, true);
-constexpr uint32_t IDESC_TN_ONES = idesc_bf16(256, 16, true, true);
 
 struct GemmNtArgs {
     const float *bias;                 // [N] fp32 or NULL
@@ -54,10 +52,9 @@ struct GemmNtArgs {
 };
 
 struct GemmTnArgs {
-    float *dW;                         // [N x K] fp32, accumulated
-    float *dbias;                      // [N] fp32, accumulated (or NULL)
+    float *dW[CPM_GEMM_TN_MAX_DST];    // destination(s): output rows [i * rows_per_dst, (i + 1) * rows_per_dst) -> dW[i] (rows_per_dst x K fp32)
     int64_t ldw;
-    int T, N, K, splits, kb_per;
+    int T, N, K, rows_per_dst, splits, kb_per;
 };
 
 __device__ __forceinline__ void red_add_v4(float *p, float a, float b, float c, float d) {
@@ -266,92 +263,257 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 }
 
 // =====================================================================================================================
-// dW += dY^T . X over one token range; one (tile, split) per cluster
+// Operand-stationary schedules.  Measured (profiles/r02_gemm_microbench_v1_stream.jsonl): the kernel above runs every layer
+// shape at 660-680 TFLOP/s = 5.3 TB/s of L2 -> shared-memory operand traffic at its 128 flop/B (64 KB per pair and K block
+// for 256 x 256 x 64 MACs) - the aggregate L2 -> SM ingest is the bound, not the tensor pipe.  Two schedules raise the
+// The WIDE schedule raises the flop/B without changing the UMMA shape: one 256 x 512 tile per pair - all 512 TMEM columns, two
+// N = 256 UMMAs per K step, 96 KB per pair and K block -> 175 flop/B.  Measured (profiles/r02_gemm_microbench_v2_modes.jsonl):
+// 1000-1050 TFLOP/s on the N = 512 layers against 590-680 streamed.  Its price is a single accumulator stage (the epilogue
+// of a tile is not hidden behind the next tile's UMMAs), paid back many times over at these K.  8 epilogue warps (two per
+// TMEM lane quarter, splitting the columns), one 4 KB staging buffer per warp.
+// (Also measured and dropped: an A-stationary schedule for K <= 512 - A resident in shared memory, only B streamed, 256
+// flop/B on paper - ran SLOWER than streaming, 585 vs 660 TFLOP/s: with 128 KB pinned by A only 64 KB of B fits in flight per
+// CTA, too little to cover the loaded L2 latency.  And GELU in the epilogue: see ops.py / profiles.)
 // =====================================================================================================================
-__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(GM_THREADS, 1)
-gemm_tn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const GemmTnArgs a) {
+constexpr int G2_THREADS = 384;                                              // warps 0-3 as above, warps 4-11 epilogue
+constexpr uint32_t G2_OFF_STG = 196608, G2_OFF_BAR = 229376, G2_SMEM = G2_OFF_BAR + 256;
+constexpr int WD_NS = 4;                                                     // wide: ring 4 x (A 16 KB + B 32 KB) | staging
+constexpr uint32_t WD_STAGE = 49152;
+
+// one 64-column chunk of this warp's 32 accumulator rows: TMEM -> epilogue -> swizzled staging -> TMA store
+template <int EPI>
+__device__ __forceinline__ void epilogue_chunk(uint32_t taddr, const GemmNtArgs &a, const CUtensorMap *tmD, const CUtensorMap *tmD2, int grow0,
+                                               int n0, int lane, uint8_t *stg, uint64_t rng_offset, bool last_read, uint32_t tempty_addr) {
+    const bool live = n0 < a.N && grow0 < a.M;
+    uint32_t r[32], o0[16], o1[16], g0[16];
+    if (live) {
+        if (lane == 0) tma_store_wait_read0();
+        __syncwarp();
+    }
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+        tmem_ld32(taddr + h * 32, r);
+        tmem_ld_wait();
+        if (last_read && h == 1) {
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_addr);
+        }
+        if (live && n0 + h * 32 < a.N) {
+            nt_epilogue_half<EPI>(r, a, (int64_t)grow0 + lane, n0 + h * 32, rng_offset, o0, o1);
+        } else {
+#pragma unroll
+            for (int j = 0; j < 16; ++j) { o0[j] = 0u; o1[j] = 0u; }
+        }
+        if (live) stage_half(stg, lane, h, o0);
+        if (EPI == CPM_GEMM_EPI_GELU && h == 0) {         // second output (the activation) of half 0: parked until the first store has read the buffer
+#pragma unroll
+            for (int j = 0; j < 16; ++j) g0[j] = o1[j];
+        }
+    }
+    if (!live) return;
+    fence_proxy_async();
+    __syncwarp();
+    if (EPI == CPM_GEMM_EPI_GELU) {
+        if (lane == 0) { tma_store_2d(tmD, stg, n0, grow0); tma_store_commit(); tma_store_wait_read0(); }
+        __syncwarp();
+        stage_half(stg, lane, 0, g0);
+        stage_half(stg, lane, 1, o1);
+        fence_proxy_async();
+        __syncwarp();
+        if (lane == 0) { tma_store_2d(tmD2, stg, n0, grow0); tma_store_commit(); }
+    } else {
+        if (lane == 0) { tma_store_2d(tmD, stg, n0, grow0); tma_store_commit(); }
+    }
+}
+
+__device__ __forceinline__ void g2_setup(uint8_t *sm, uint64_t *bars, int n_full_a, int n_ring, int tempty_count, uint32_t *tmem_slot, int tid,
+                                         int warp, const CUtensorMap *m0, const CUtensorMap *m1, const CUtensorMap *m2, const CUtensorMap *m3) {
+    // layout of `bars`: a_full[8] a_empty[8] full[4] empty[4] tfull[2] tempty[2]
+    cluster_sync_all();
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        for (int s = 0; s < n_full_a; ++s) { mbar_init(bars + s, 2); mbar_init(bars + 8 + s, 1); }
+        for (int s = 0; s < n_ring; ++s) { mbar_init(bars + 16 + s, 2); mbar_init(bars + 20 + s, 1); }
+        for (int s = 0; s < 2; ++s) { mbar_init(bars + 24 + s, 1); mbar_init(bars + 26 + s, tempty_count); }
+        fence_barrier_init();
+        tma_prefetch_desc(m0);
+        tma_prefetch_desc(m1);
+        tma_prefetch_desc(m2);
+        if (m3) tma_prefetch_desc(m3);
+    }
+    if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+}
+
+template <int EPI>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_nt_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                    const __grid_constant__ CUtensorMap tmD2, const GemmNtArgs a) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + GM_OFF_BAR);
-    uint64_t *bar_full = bars, *bar_empty = bars + GM_NS, *bar_tfull = bar_empty + GM_NS, *bar_tempty = bar_tfull + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_tempty + 2);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + G2_OFF_BAR);
+    uint64_t *bar_full = bars + 16, *bar_empty = bars + 20, *bar_tfull = bars + 24, *bar_tempty = bars + 26;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
-    const int item = blockIdx.x >> 1;
-    const int NB = (a.K + 255) >> 8;                       // output tile columns index the INPUT features
-    const int split = item % a.splits, tile = item / a.splits, nb = tile % NB, mb = tile / NB;
-    const int kb_all = (a.T + 63) >> 6, kb0 = split * a.kb_per, kb1 = min(kb_all, kb0 + a.kb_per), KB = max(kb1 - kb0, 0);
-    const bool with_bias = a.dbias != nullptr && nb == 0;
-    for (int i = tid; i < 8192 / 16; i += GM_THREADS)     // a [64 x 128 B] tile of bf16 ones: any swizzle of it is still all ones
-        reinterpret_cast<uint4 *>(sm + GM_OFF_ONES)[i] = make_uint4(0x3F803F80u, 0x3F803F80u, 0x3F803F80u, 0x3F803F80u);
-    fence_proxy_async();
-    gemm_setup(sm, bars, tmem_slot, tid, warp, &tmY, &tmX, nullptr, nullptr);
+    const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
+    const int MB = (a.M + 255) >> 8, KB = (a.K + 63) >> 6, NB2 = (a.N + 511) >> 9, tiles = MB * NB2;     // 256 x 512 tiles, N tile fastest
+    g2_setup(sm, bars, 0, WD_NS, 8, tmem_slot, tid, warp, &tmA, &tmB, &tmD, EPI == CPM_GEMM_EPI_GELU ? &tmD2 : nullptr);
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
-        if (lane == 0) {                                   // ---- TMA producer: per stage two 64-column panels of dY and of X
+        if (lane == 0) {                                   // ---- TMA producer: A half + both 128-row halves of B's two 256-row slabs
             const uint32_t full0 = mapa_u32(smem_u32(bar_full), 0);
-            const int col_y = mb * 256 + (int)rank * 128, col_x = nb * 256 + (int)rank * 128;
+            uint32_t s = 0, ph = 0;
+            for (int t = pair; t < tiles; t += npairs) {
+                const int row_a = (t / NB2) * 256 + (int)rank * 128, row_b = (t % NB2) * 512 + (int)rank * 128;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar_empty + s, ph ^ 1);
+                    if (rank == 0) mbar_expect_tx(bar_full + s, 2 * WD_STAGE);
+                    else mbar_arrive_cluster(full0 + 8 * s);
+                    uint8_t *st = sm + s * WD_STAGE;
+                    tma_load_2d_2sm(st, &tmA, full0 + 8 * s, kb * 64, row_a);
+                    tma_load_2d_2sm(st + GM_A_BYTES, &tmB, full0 + 8 * s, kb * 64, row_b);
+                    tma_load_2d_2sm(st + 2 * GM_A_BYTES, &tmB, full0 + 8 * s, kb * 64, row_b + 256);
+                    if (++s == WD_NS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {                      // ---- UMMA issuer: two N = 256 instructions per K step
+            uint32_t s = 0, ph = 0, ti = 0;
+            for (int t = pair; t < tiles; t += npairs, ++ti) {
+                mbar_wait(bar_tempty + 0, (ti & 1) ^ 1);   // both column halves drained by the previous tile's epilogue
+                mbar_wait(bar_tempty + 1, (ti & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar_full + s, ph);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(sm + s * WD_STAGE);
+                    const uint64_t dA = smem_desc_sw128(base), dB0 = smem_desc_sw128(base + GM_A_BYTES), dB1 = smem_desc_sw128(base + 2 * GM_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        mma_ss_2sm(tmem, dA + 2 * k, dB0 + 2 * k, IDESC_NT, acc);
+                        mma_ss_2sm(tmem + 256, dA + 2 * k, dB1 + 2 * k, IDESC_NT, acc);
+                    }
+                    mma_commit_2sm(bar_empty + s, 3);
+                    if (++s == WD_NS) { s = 0; ph ^= 1; }
+                }
+                mma_commit_2sm(bar_tfull, 3);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: lane quarter q, slab ch (columns 256 ch ..): four 64-column chunks per warp and tile
+        const int q = warp & 3, ch = (warp - 4) >> 2;
+        uint8_t *stg = sm + G2_OFF_STG + (warp - 4) * 4096;
+        const uint32_t tempty0 = mapa_u32(smem_u32(bar_tempty), 0);
+        const uint64_t rng_offset = rng_off(a.rng_offset, a.rng_base);
+        uint32_t ti = 0;
+        for (int t = pair; t < tiles; t += npairs, ++ti) {
+            const int grow0 = (t / NB2) * 256 + (int)rank * 128 + q * 32, ncol0 = (t % NB2) * 512 + ch * 256;
+            mbar_wait(bar_tfull, ti & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + ch * 256;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c)
+                epilogue_chunk<EPI>(tbase + c * 64, a, &tmD, &tmD2, grow0, ncol0 + c * 64, lane, stg, rng_offset, c == 3, tempty0 + 8 * ch);
+        }
+        if (lane == 0) tma_store_wait_all0();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_2sm<512>(tmem);
+}
+
+// =====================================================================================================================
+// dW += dY^T . X over one token range; one (256 x 512 tile, split) per cluster
+// =====================================================================================================================
+// Both operands are read MN-major straight from the row-major activations: the contraction index is the token, a [64 tokens x
+// 64 columns] TMA box is one SWIZZLE_128B MN-major atom column (atoms 8192 B apart = LBO, 8-token groups 1024 B apart = SBO).
+// Per stage and CTA: 128 output-feature columns of dY (2 boxes) and 256 input-feature columns of X (4 boxes) = 48 KB; two
+// N = 256 UMMAs per K step fill all 512 TMEM columns (175 flop per operand byte, like the wide forward tile).  The epilogue
+// adds the partial tile into the fp32 gradient with vector red.global.add - which is also the accumulation across
+// micro-batches.  Output rows may be routed to several destination matrices (the q / k / v masters behind one fused GEMM).
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
+gemm_tn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ CUtensorMap tmX, const GemmTnArgs a) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + G2_OFF_BAR);
+    uint64_t *bar_full = bars + 16, *bar_empty = bars + 20, *bar_tfull = bars + 24;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t rank = cluster_ctarank();
+    const int item = blockIdx.x >> 1;
+    const int NB2 = (a.K + 511) >> 9;                      // output tile columns index the INPUT features
+    const int split = item % a.splits, tile = item / a.splits, nb = tile % NB2, mb = tile / NB2;
+    const int kb_all = (a.T + 63) >> 6, kb0 = split * a.kb_per, kb1 = min(kb_all, kb0 + a.kb_per), KB = max(kb1 - kb0, 0);
+    g2_setup(sm, bars, 0, WD_NS, 8, tmem_slot, tid, warp, &tmY, &tmX, &tmX, nullptr);
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer
+            const uint32_t full0 = mapa_u32(smem_u32(bar_full), 0);
+            const int col_y = mb * 256 + (int)rank * 128, col_x = nb * 512 + (int)rank * 128;
             uint32_t s = 0, ph = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(bar_empty + s, ph ^ 1);
-                if (rank == 0) mbar_expect_tx(bar_full + s, 2 * GM_STAGE);
+                if (rank == 0) mbar_expect_tx(bar_full + s, 2 * WD_STAGE);
                 else mbar_arrive_cluster(full0 + 8 * s);
-                uint8_t *st = sm + s * GM_STAGE;
+                uint8_t *st = sm + s * WD_STAGE;
                 tma_load_2d_2sm(st, &tmY, full0 + 8 * s, col_y, kb * 64);
                 tma_load_2d_2sm(st + 8192, &tmY, full0 + 8 * s, col_y + 64, kb * 64);
-                tma_load_2d_2sm(st + GM_A_BYTES, &tmX, full0 + 8 * s, col_x, kb * 64);
-                tma_load_2d_2sm(st + GM_A_BYTES + 8192, &tmX, full0 + 8 * s, col_x + 64, kb * 64);
-                if (++s == GM_NS) { s = 0; ph ^= 1; }
+#pragma unroll
+                for (int j = 0; j < 2; ++j) {              // slab j = tile columns [256 j, 256 j + 256): this CTA's 128 of them
+                    tma_load_2d_2sm(st + GM_A_BYTES + j * 16384, &tmX, full0 + 8 * s, col_x + 256 * j, kb * 64);
+                    tma_load_2d_2sm(st + GM_A_BYTES + j * 16384 + 8192, &tmX, full0 + 8 * s, col_x + 256 * j + 64, kb * 64);
+                }
+                if (++s == WD_NS) { s = 0; ph ^= 1; }
             }
         }
     } else if (warp == 1) {
         if (rank == 0 && lane == 0 && KB > 0) {            // ---- UMMA issuer
-            const uint64_t dOnes = smem_desc_sw128(smem_u32(sm + GM_OFF_ONES), 8192, 1024);
             uint32_t s = 0, ph = 0;
             for (int i = 0; i < KB; ++i) {
                 mbar_wait(bar_full + s, ph);
                 tc_fence_after();
-                // MN-major SWIZZLE_128B operands: 64-column atoms 8192 B apart (LBO), 8-token groups 1024 B apart (SBO);
-                // 16 tokens further along K = 2048 B = 128 descriptor units
-                const uint64_t dA = smem_desc_sw128(smem_u32(sm + s * GM_STAGE), 8192, 1024);
-                const uint64_t dB = smem_desc_sw128(smem_u32(sm + s * GM_STAGE + GM_A_BYTES), 8192, 1024);
+                const uint32_t base = smem_u32(sm + s * WD_STAGE);
+                const uint64_t dA = smem_desc_sw128(base, 8192, 1024), dB0 = smem_desc_sw128(base + GM_A_BYTES, 8192, 1024),
+                               dB1 = smem_desc_sw128(base + GM_A_BYTES + 16384, 8192, 1024);
 #pragma unroll
-                for (int k = 0; k < 4; ++k) {
+                for (int k = 0; k < 4; ++k) {              // 16 tokens further along K = 2048 B = 128 descriptor units
                     const uint32_t acc = (i > 0 || k > 0) ? 1u : 0u;
-                    mma_ss_2sm(tmem, dA + 128 * k, dB + 128 * k, IDESC_TN, acc);
-                    if (with_bias) mma_ss_2sm(tmem + 256, dA + 128 * k, dOnes, IDESC_TN_ONES, acc);
+                    mma_ss_2sm(tmem, dA + 128 * k, dB0 + 128 * k, IDESC_TN, acc);
+                    mma_ss_2sm(tmem + 256, dA + 128 * k, dB1 + 128 * k, IDESC_TN, acc);
                 }
                 mma_commit_2sm(bar_empty + s, 3);
-                if (++s == GM_NS) { s = 0; ph ^= 1; }
+                if (++s == WD_NS) { s = 0; ph ^= 1; }
             }
             mma_commit_2sm(bar_tfull, 3);
         }
     } else if (warp >= 4 && KB > 0) {
-        // ---- epilogue: accumulate this split's partial tile into the fp32 gradient
-        const int w = warp - 4;
-        const int m = mb * 256 + (int)rank * 128 + w * 32 + lane;            // output row = output feature
+        // ---- epilogue: lane quarter q, slab ch; accumulate this split's partial tile into the fp32 gradient(s)
+        const int q = warp & 3, ch = (warp - 4) >> 2;
+        const int m = mb * 256 + (int)rank * 128 + q * 32 + lane;            // output row = output feature
         mbar_wait(bar_tfull, 0);
         tc_fence_after();
-        const uint32_t tbase = tmem + ((uint32_t)(w * 32) << 16);
-        float *dst = a.dW + (int64_t)m * a.ldw + nb * 256;
+        const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + ch * 256;
+        const int dsti = m / a.rows_per_dst;
+        float *dst = (m < a.N) ? a.dW[dsti] + (int64_t)(m - dsti * a.rows_per_dst) * a.ldw : nullptr;
+        const int ncol0 = nb * 512 + ch * 256;
 #pragma unroll 1
         for (int c = 0; c < 8; ++c) {
             uint32_t r[32];
             tmem_ld32(tbase + c * 32, r);
             tmem_ld_wait();
-            const int n0 = nb * 256 + c * 32;
-            if (m < a.N) {
+            const int n0 = ncol0 + c * 32;
+            if (dst) {
 #pragma unroll
                 for (int j = 0; j < 32; j += 4)
                     if (n0 + j + 4 <= a.K)
-                        red_add_v4(dst + c * 32 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
+                        red_add_v4(dst + n0 + j, __uint_as_float(r[j]), __uint_as_float(r[j + 1]), __uint_as_float(r[j + 2]), __uint_as_float(r[j + 3]));
             }
-        }
-        if (with_bias) {
-            uint32_t r[8];
-            tmem_ld8(tbase + 256, r);
-            tmem_ld_wait();
-            if (m < a.N) atomicAdd(a.dbias + m, __uint_as_float(r[0]));
         }
     }
     tc_fence_before();
@@ -366,17 +528,28 @@ int set_smem(K kernel, const char *name) {
     return CPM_OK;
 }
 
+int g_gemm_mode = 0;          // 0 auto | 1 stream | 3 wide   (cpm_gemm_set_mode: A/B measurements)
+
 template <int EPI>
 int launch_nt(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &tD, const CUtensorMap &tD2, const GemmNtArgs &a, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         int rc = set_smem(gemm_nt_kernel<EPI>, "gemm_nt");
         if (rc) return rc;
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_wide_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
+        if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_nt shared-memory attribute: %s", cudaGetErrorString(e));
         attr = true;
     }
-    const int tiles = ((a.M + 255) / 256) * ((a.N + 255) / 256);
-    const int pairs = min(tiles, num_sms() / 2);
-    gemm_nt_kernel<EPI><<<2 * pairs, GM_THREADS, GM_SMEM, st>>>(tA, tB, tD, tD2, a);
+    const int MB = (a.M + 255) / 256, NB = (a.N + 255) / 256, NB2 = (a.N + 511) / 512, max_pairs = num_sms() / 2;
+    int mode = g_gemm_mode;
+    // auto: wide tiles once they fill the machine and N spans more than one 256-column slab; small problems keep the finer
+    // 256 x 256 tiles (more of them to spread over the pairs)
+    if (mode != 1 && mode != 3) mode = (NB > 1 && MB * NB2 >= max_pairs) ? 3 : 1;
+    if (mode == 3) {
+        gemm_nt_wide_kernel<EPI><<<2 * min(MB * NB2, max_pairs), G2_THREADS, G2_SMEM, st>>>(tA, tB, tD, tD2, a);
+        return check_launch("gemm_nt (wide)");
+    }
+    gemm_nt_kernel<EPI><<<2 * min(MB * NB, max_pairs), GM_THREADS, GM_SMEM, st>>>(tA, tB, tD, tD2, a);
     return check_launch("gemm_nt");
 }
 
@@ -384,6 +557,12 @@ int launch_nt(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &t
 }  // namespace cpm
 
 using namespace cpm;
+
+extern "C" int cpm_gemm_set_mode(int mode) {
+    CPM_REQUIRE(mode >= 0 && mode <= 3, CPM_ERR_BAD_SHAPE, "gemm_set_mode: %d", mode);
+    g_gemm_mode = mode;
+    return CPM_OK;
+}
 
 extern "C" int cpm_gemm_nt(const void *A, int64_t lda, const void *B, int64_t ldb, void *D, int64_t ldd, void *D2, int64_t ldd2, int M, int N,
                            int K, const float *bias, int epilogue, const void *aux, int64_t ld_aux, float p_drop, uint64_t seed,
@@ -418,30 +597,37 @@ extern "C" int cpm_gemm_nt(const void *A, int64_t lda, const void *B, int64_t ld
     }
 }
 
-extern "C" int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *dW, int64_t ldw, float *dbias, int T, int N, int K,
-                           void *stream) {
-    CPM_REQUIRE(dY && X && dW, CPM_ERR_NULL, "gemm_tn: dY/X/dW must be non-NULL");
+extern "C" int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *const *dW_host, int n_dst, int rows_per_dst,
+                           int64_t ldw, int T, int N, int K, void *stream) {
+    CPM_REQUIRE(dY && X && dW_host, CPM_ERR_NULL, "gemm_tn: dY/X/dW must be non-NULL");
     CPM_REQUIRE(T > 0 && N > 0 && K > 0 && N % 8 == 0 && K % 8 == 0, CPM_ERR_BAD_SHAPE, "gemm_tn: T=%d N=%d K=%d (N, K multiples of 8)", T, N, K);
+    CPM_REQUIRE(n_dst >= 1 && n_dst <= CPM_GEMM_TN_MAX_DST && rows_per_dst > 0 && (int64_t)n_dst * rows_per_dst >= N, CPM_ERR_BAD_SHAPE,
+                "gemm_tn: %d destinations of %d rows for N=%d", n_dst, rows_per_dst, N);
     CPM_REQUIRE(ldy >= N && ldx >= K && ldw >= K && ldy % 8 == 0 && ldx % 8 == 0 && ldw % 4 == 0, CPM_ERR_BAD_SHAPE, "gemm_tn: row strides");
-    CPM_REQUIRE(aligned16(dY) && aligned16(X) && aligned16(dW), CPM_ERR_BAD_ALIGN, "gemm_tn: operands must be 16-byte aligned");
+    CPM_REQUIRE(aligned16(dY) && aligned16(X), CPM_ERR_BAD_ALIGN, "gemm_tn: operands must be 16-byte aligned");
+    GemmTnArgs a;
+    for (int i = 0; i < CPM_GEMM_TN_MAX_DST; ++i) {
+        a.dW[i] = i < n_dst ? dW_host[i] : nullptr;
+        CPM_REQUIRE(i >= n_dst || (a.dW[i] && aligned16(a.dW[i])), CPM_ERR_BAD_ALIGN, "gemm_tn: destination %d must be non-NULL and 16-byte aligned", i);
+    }
     CUtensorMap tY, tX;
     int rc;
     if ((rc = make_tmap_bf16_2d(&tY, dY, (uint64_t)N, (uint64_t)T, (uint64_t)ldy, 64))) return rc;
     if ((rc = make_tmap_bf16_2d(&tX, X, (uint64_t)K, (uint64_t)T, (uint64_t)ldx, 64))) return rc;
     static bool attr = false;
     if (!attr) {
-        if ((rc = set_smem(gemm_tn_kernel, "gemm_tn"))) return rc;
+        cudaError_t e = cudaFuncSetAttribute(gemm_tn_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
+        if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_tn shared-memory attribute: %s", cudaGetErrorString(e));
         attr = true;
     }
-    GemmTnArgs a;
-    a.dW = dW; a.dbias = dbias; a.ldw = ldw; a.T = T; a.N = N; a.K = K;
-    const int tiles = ((N + 255) / 256) * ((K + 255) / 256), kb_all = (T + 63) / 64;
+    a.ldw = ldw; a.T = T; a.N = N; a.K = K; a.rows_per_dst = rows_per_dst;
+    const int tiles = ((N + 255) / 256) * ((K + 511) / 512), kb_all = (T + 63) / 64;
     int splits = (num_sms() / 2 * 2) / tiles;              // two waves of clusters when the token range is long enough
     if (splits < 1) splits = 1;
     if (splits > (kb_all + 7) / 8) splits = (kb_all + 7) / 8;   // at least 8 K blocks per work item
     if (splits < 1) splits = 1;
     a.kb_per = (kb_all + splits - 1) / splits;
     a.splits = (kb_all + a.kb_per - 1) / a.kb_per;
-    gemm_tn_kernel<<<2 * tiles * a.splits, GM_THREADS, GM_SMEM, (cudaStream_t)stream>>>(tY, tX, a);
+    gemm_tn_kernel<<<2 * tiles * a.splits, G2_THREADS, G2_SMEM, (cudaStream_t)stream>>>(tY, tX, a);
     return check_launch("gemm_tn");
 }

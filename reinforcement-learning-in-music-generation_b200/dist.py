@@ -64,11 +64,11 @@ class BucketedGradAllReduce:
         self.buckets: List[dict] = []
         cur, cur_n = [], 0
         for p in reversed(self.params):
-            if cur and cur_n + p.numel() > cap:
+            if cur and cur_n + self._padded(p.numel()) > cap:
                 self._close(cur)
                 cur, cur_n = [], 0
             cur.append(p)
-            cur_n += p.numel()
+            cur_n += self._padded(p.numel())
         if cur:
             self._close(cur)
         self._handles = []
@@ -84,13 +84,20 @@ class BucketedGradAllReduce:
         self.world = dist.get_world_size(group) if dist.is_initialized() else 1
         return self
 
+    ALIGN = 32          # floats: every gradient view starts on a 128-byte boundary (the GEMM kernels accumulate into them with
+                        # 16-byte vector atomics; odd-sized parameters such as a 135-wide value head would misalign the rest)
+
+    @classmethod
+    def _padded(cls, n):
+        return -(-n // cls.ALIGN) * cls.ALIGN
+
     def _close(self, plist):
-        n = sum(p.numel() for p in plist)
+        n = sum(self._padded(p.numel()) for p in plist)
         flat = torch.zeros(n, dtype=torch.float32, device=plist[0].device)
         off = 0
         for p in plist:
             p.grad = flat[off:off + p.numel()].view_as(p)
-            off += p.numel()
+            off += self._padded(p.numel())
         self.buckets.append({"params": plist, "flat": flat, "pending": len(plist), "launched": False, "round": 0})
 
     def _make_hook(self, bi):
@@ -140,7 +147,7 @@ class BucketedGradAllReduce:
             for p in b["params"]:          # re-attach views if an optimizer dropped them
                 if p.grad is None or p.grad.data_ptr() != b["flat"].data_ptr() + 4 * off:
                     p.grad = b["flat"][off:off + p.numel()].view_as(p)
-                off += p.numel()
+                off += self._padded(p.numel())
 
     def grad_bytes(self) -> int:
         return sum(b["flat"].numel() * 4 for b in self.buckets)

@@ -34,6 +34,14 @@ import os as _os
 FUSED_BIAS_GRADS = {"0": False, "1": "all"}.get(_os.environ.get("CPM_FUSED_BIAS_GRADS", "0"), _os.environ.get("CPM_FUSED_BIAS_GRADS", "0"))
 
 
+# GELU (+ dropout) inside the GEMM epilogues (CPM_FUSED_GELU=1; default off).  Measured on B200 at T = 131072 tokens
+# (profiles/r02_gemm_microbench_v2_modes.jsonl): linear1 with the fused epilogue 865 us against 462 us for the same GEMM with a
+# bias epilogue plus 279 us for the stand-alone GELU kernel; linear2's data gradient with the fused GELU backward 894 us against
+# 468 + 350.  ~40 instructions per element (erf + Philox) issued by the 8 epilogue warps of a CTA cannot keep up with what
+# 64 resident warps per SM do in the stand-alone kernels; the epilogue, not the tensor pipe, then sets the tile time.
+FUSED_GELU_EPILOGUE = _os.environ.get("CPM_FUSED_GELU", "0") == "1"
+
+
 class TriangularCausalMask:
     """``fast_transformers.masking.TriangularCausalMask(N, device=)``: only the
     ``lower_triangular`` flag is consulted by causal-linear attention."""
@@ -213,9 +221,9 @@ class TransformerEncoder(nn.Module):
         if not FUSED_BIAS_GRADS:
             o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
             x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
-            if ops.use_own_gemm(x) and dt == torch.bfloat16:
-                # linear1 + GELU + dropout + linear2 on the own GEMMs: the activation runs in linear1's epilogue, its backward in
-                # the epilogue of linear2's data gradient
+            if FUSED_GELU_EPILOGUE and ops.use_own_gemm(x) and dt == torch.bfloat16:
+                # linear1 + GELU + dropout + linear2 with the activation in linear1's epilogue and its backward in the epilogue of
+                # linear2's data gradient (opt-in: measured slower than the separate GELU kernels, see FUSED_GELU_EPILOGUE)
                 pack1, _ = c.get_gemm_pack(("ff1", i), [layer.linear1], dt)
                 pack2, _ = c.get_gemm_pack(("ff2", i), [layer.linear2], dt)
                 f = ops.tc_ffn(x, pack1, pack2, p, layer.linear1, layer.linear2)
@@ -265,8 +273,13 @@ class TransformerEncoder(nn.Module):
             a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * E)
         o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
         x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
-        h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)
-        g = ops.gelu_dropout(h, p)
+        if p == 0.0 and ops.use_own_gemm(x) and x.shape[0] < ops.SMALL_GEMM_ROWS and not torch.is_grad_enabled():
+            # generation: GELU in linear1's epilogue (one launch less per layer; bit-identical to GEMM + gelu kernel)
+            pack1, _ = c.get_gemm_pack(("ff1", i), [layer.linear1], dt)
+            g = ops.gemm_nt_small(x, pack1[0], pack1[2], gelu=True)
+        else:
+            h = cached_linear(c, ("ff1", i), [layer.linear1], x, dt)
+            g = ops.gelu_dropout(h, p)
         f = cached_linear(c, ("ff2", i), [layer.linear2], g, dt)
         return ops.ln_residual(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p)
 

@@ -414,6 +414,7 @@ def linattn_state_flush(S, Z, ring, step_dev):
 
 # --------------------------------------------------------------------------- dense linear: own tcgen05 GEMMs (csrc/tc_gemm.cu)
 GEMM_BIAS, GEMM_GELU, GEMM_DGELU = 0, 1, 2
+SMALL_GEMM_ROWS = int(os.environ.get("CPM_SMALL_GEMM_ROWS", "1024"))      # below: cpm_gemm_nt_small
 
 
 def _gemm_operand(t, what):
@@ -436,6 +437,9 @@ def gemm_nt(a, b, bias=None, epilogue=GEMM_BIAS, aux=None, p_drop=0.0, seed=0, r
     if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N or not bias.is_contiguous()):
         raise ValueError("gemm_nt: bias must be contiguous float32 (N,)")
     d = out if out is not None else torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    if M < SMALL_GEMM_ROWS and epilogue == GEMM_BIAS:      # few rows (token step, small batches): the 64 x 32-tile kernel
+        check(_lib.load().cpm_gemm_nt_small(_p(a), a.stride(0), _p(b), b.stride(0), _p(d), d.stride(0), M, N, K, _p(bias), GEMM_BIAS, _st()))
+        return d
     d2 = torch.empty(M, N, dtype=torch.bfloat16, device=a.device) if epilogue == GEMM_GELU else None
     if aux is not None:
         aux = _gemm_operand(aux, "aux")
@@ -444,30 +448,59 @@ def gemm_nt(a, b, bias=None, epilogue=GEMM_BIAS, aux=None, p_drop=0.0, seed=0, r
     return (d, d2) if epilogue == GEMM_GELU else d
 
 
-def gemm_tn_acc(dy, x, dw, dbias=None):
-    """dw (N,K) fp32 += dy (T,N).T @ x (T,K); dbias (N,) fp32 += dy.sum(0) - the weight / bias gradient of a Linear layer,
-    accumulated in place (cpm_gemm_tn: operands read MN-major from the row-major activations, no transposes)."""
-    _cuda(dy, x, dw, dbias)
+def gemm_set_mode(mode: int) -> None:
+    """cpm_gemm_set_mode: 0 auto | 1 stream | 2 A-stationary | 3 wide (tests and A/B measurements)."""
+    check(_lib.load().cpm_gemm_set_mode(int(mode)))
+
+
+def gemm_nt_small(a, w, bias=None, gelu=False, out=None):
+    """epilogue(a @ w.T + bias) for the recurrent token step (cpm_gemm_nt_small): a (M,K), w (N,K) bf16; bias fp32 (N,)."""
+    _cuda(a, w, bias)
+    a, w = _gemm_operand(a, "a"), _gemm_operand(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"gemm_nt_small: a (M,{K}) against w {tuple(w.shape)}")
+    d = out if out is not None else torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    check(_lib.load().cpm_gemm_nt_small(_p(a), a.stride(0), _p(w), w.stride(0), _p(d), d.stride(0), M, N, K, _p(bias),
+                                        GEMM_GELU if gelu else GEMM_BIAS, _st()))
+    return d
+
+
+def set_chain_pdl(on: bool) -> None:
+    check(_lib.load().cpm_set_chain_pdl(1 if on else 0))
+
+
+def gemm_tn_acc(dy, x, dws):
+    """dW (N,K) fp32 += dy (T,N).T @ x (T,K): the weight gradient of a Linear layer, accumulated in place (cpm_gemm_tn: operands
+    read MN-major from the row-major activations, no transposes).  ``dws``: one (N,K) fp32 matrix, or a list of up to 4 equally
+    tall matrices that receive consecutive row blocks (the q / k / v masters behind one fused projection)."""
+    if torch.is_tensor(dws):
+        dws = [dws]
+    _cuda(dy, x, *dws)
     dy, x = _gemm_operand(dy, "dy"), _gemm_operand(x, "x")
     T, N = dy.shape
     K = x.shape[1]
-    if x.shape[0] != T or dw.shape != (N, K) or dw.dtype != torch.float32 or dw.stride(1) != 1:
-        raise ValueError(f"gemm_tn_acc: dy {tuple(dy.shape)}, x {tuple(x.shape)}, dw {tuple(dw.shape)} {dw.dtype}")
-    if dbias is not None and (dbias.dtype != torch.float32 or dbias.numel() != N or not dbias.is_contiguous()):
-        raise ValueError("gemm_tn_acc: dbias must be contiguous float32 (N,)")
-    check(_lib.load().cpm_gemm_tn(_p(dy), dy.stride(0), _p(x), x.stride(0), _p(dw), dw.stride(0), _p(dbias), T, N, K, _st()))
-    return dw
+    rows = dws[0].shape[0]
+    if x.shape[0] != T or len(dws) > 4 or rows * len(dws) != N:
+        raise ValueError(f"gemm_tn_acc: dy {tuple(dy.shape)}, x {tuple(x.shape)}, {len(dws)} destinations of {rows} rows")
+    ldw = dws[0].stride(0)
+    for w in dws:
+        if w.shape != (rows, K) or w.dtype != torch.float32 or w.stride(1) != 1 or w.stride(0) != ldw:
+            raise ValueError(f"gemm_tn_acc: destinations must be float32 ({rows},{K}) with a common row stride")
+    check(_lib.load().cpm_gemm_tn(_p(dy), dy.stride(0), _p(x), x.stride(0), _lib.ptr_array([w.data_ptr() for w in dws]), len(dws), rows,
+                                  ldw, T, N, K, _st()))
+    return dws
 
 
-# How the Linear layers run: "own" (default) = the tcgen05 GEMMs above for bf16 activations; "lib" = cuBLASLt through torch
-# (kept for A/B measurements and as the fp32 parity mode's GEMM).  Token counts below OWN_GEMM_MIN_ROWS (the rollout step's
-# M = batch rows) stay on the library path until the small-M kernel lands.
+# How the Linear layers run: "own" (default) = the tcgen05 GEMMs above for bf16 activations (the 2-CTA kernels from
+# SMALL_GEMM_ROWS rows up, the 64 x 32-tile kernel below that: the rollout token step and small batches); "lib" = cuBLASLt
+# through torch, kept for A/B measurements and as the fp32 parity mode's GEMM.
 GEMM_IMPL = os.environ.get("CPM_GEMM", "own")
-OWN_GEMM_MIN_ROWS = int(os.environ.get("CPM_GEMM_MIN_ROWS", "1024"))
 
 
 def use_own_gemm(x) -> bool:
-    return GEMM_IMPL == "own" and x.dtype == torch.bfloat16 and x.is_cuda and x.numel() // x.shape[-1] >= OWN_GEMM_MIN_ROWS
+    return GEMM_IMPL == "own" and x.dtype == torch.bfloat16 and x.is_cuda
 
 
 def _fire_grad_hooks(p):
@@ -480,46 +513,33 @@ def _fire_grad_hooks(p):
 
 
 def _wgrad_into_masters(gy2, x2, rows, masters, has_bias):
-    """dW_i (+)= gy[:, rows_i]^T x and db_i (+)= colsum(gy[:, rows_i]) for the masters packed behind one GEMM.  Masters whose
-    ``.grad`` already exists (gradient accumulation; the flat buckets of dist.BucketedGradAllReduce) are accumulated IN PLACE by
-    the kernel's fp32 atomics - no separate add kernels - and report ``None`` to autograd; fresh gradients are returned."""
+    """dW_i (+)= gy[:, rows_i]^T x for the masters packed behind one GEMM, bias gradients as column sums of gy (cpm_colsum).
+    Weight masters whose ``.grad`` already exists (gradient accumulation; the flat buckets of dist.BucketedGradAllReduce) are
+    accumulated IN PLACE by the kernel's fp32 atomics - no separate add kernels - and report ``None`` to autograd; fresh
+    gradients are returned."""
     n_w = len(rows)
     out = [None] * (2 * n_w if has_bias else n_w)
-    aligned = all(r % 8 == 0 for r in rows)
-    if not aligned:                       # ragged row counts (the six output heads): one packed GEMM, split afterwards
-        N = gy2.shape[1]
-        gw = torch.zeros(N, x2.shape[1], dtype=torch.float32, device=gy2.device)
-        gb = torch.zeros(N, dtype=torch.float32, device=gy2.device) if has_bias else None
-        gemm_tn_acc(gy2, x2, gw, gb)
+    N, K = gy2.shape[1], x2.shape[1]
+    ws = masters[:n_w]
+    in_place = (len(set(rows)) == 1 and rows[0] % 8 == 0 and n_w <= 4 and sum(rows) == N
+                and all(w.grad is not None and w.grad.dtype == torch.float32 and w.grad.is_contiguous() and w.grad.data_ptr() % 16 == 0 for w in ws))
+    if in_place:
+        gemm_tn_acc(gy2, x2, [w.grad for w in ws])
+        for w in ws:
+            _fire_grad_hooks(w)
+    else:                                 # fresh gradients (or ragged row counts, e.g. the six output heads): one packed buffer
+        gw = torch.zeros(N, K, dtype=torch.float32, device=gy2.device)
+        gemm_tn_acc(gy2, x2, gw)
         r0 = 0
         for i, r in enumerate(rows):
             out[i] = gw[r0:r0 + r]
-            if has_bias:
-                out[n_w + i] = gb[r0:r0 + r]
             r0 += r
-        return out
-    r0 = 0
-    for i, r in enumerate(rows):
-        w = masters[i]
-        b = masters[n_w + i] if has_bias else None
-        gw_t = w.grad if (w.grad is not None and w.grad.dtype == torch.float32 and w.grad.is_contiguous()) else None
-        gb_t = b.grad if (b is not None and b.grad is not None and b.grad.dtype == torch.float32 and b.grad.is_contiguous()) else None
-        in_place_w, in_place_b = gw_t is not None, gb_t is not None
-        if gw_t is None:
-            gw_t = torch.zeros(r, x2.shape[1], dtype=torch.float32, device=gy2.device)
-        if b is not None and gb_t is None:
-            gb_t = torch.zeros(r, dtype=torch.float32, device=gy2.device)
-        gemm_tn_acc(gy2[:, r0:r0 + r], x2, gw_t, gb_t)
-        if in_place_w:
-            _fire_grad_hooks(w)
-        else:
-            out[i] = gw_t
-        if has_bias:
-            if in_place_b:
-                _fire_grad_hooks(b)
-            else:
-                out[n_w + i] = gb_t
-        r0 += r
+    if has_bias:
+        gb = colsum(gy2)
+        r0 = 0
+        for i, r in enumerate(rows):
+            out[n_w + i] = gb[r0:r0 + r]
+            r0 += r
     return out
 
 

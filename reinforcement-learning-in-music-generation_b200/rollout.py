@@ -103,6 +103,9 @@ class RolloutEngine:
         self.mode = mode
         self.fused = mode == "fused"
         self.pdl = pdl
+        import os
+        self.chain_pdl = (mode == "unfused" and model.compute_dtype == torch.bfloat16 and ops.GEMM_IMPL == "own"
+                          and os.environ.get("CPM_CHAIN_PDL", "1") == "1")
         self._mega = None
         self._tc = None
 
@@ -357,6 +360,18 @@ class RolloutEngine:
 
     # one token for every sequence: reads self.cur, overwrites self.cur with the sampled token
     def _step(self):
+        """One token for every sequence.  In the default mode every kernel of the step is a chain kernel (csrc/cpm_common.cuh):
+        with ``chain_pdl`` they are launched with programmatic dependent launch, each overlapping its set-up (and the GEMMs
+        their weight fetch) with its predecessor's tail."""
+        if self.chain_pdl:
+            ops.set_chain_pdl(True)
+            try:
+                return self._step_inner()
+            finally:
+                ops.set_chain_pdl(False)
+        return self._step_inner()
+
+    def _step_inner(self):
         m = self.model
         if self.mode == "mega":
             return self._step_mega()

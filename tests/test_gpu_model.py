@@ -601,10 +601,11 @@ def test_graphed_train_step_equals_eager_and_keeps_dropout_fresh(cuda, cpm, gold
 def test_greedy_rollout_tokens_equal_oracle_recurrent_decode(cuda, cpm, golden):
     """north_star: sampled token indices bit-exact under greedy decoding.  The RolloutEngine's greedy tokens (fp32 compute,
     CUDA-graph step, true positions) against the ORACLE's own recurrent greedy decode (ft RecurrentLinearAttention restated,
-    oracle/ft_oracle.py + model_oracle.py; argmax per attribute as testing-no-type-cp.py's loop with t -> 0) on the CPU,
-    token by token.  Margin filter: a step whose top-2 oracle logit gap in some attribute is below 2e-3 (fp32 accumulation
-    order can flip such a near-tie) ends the comparison of that sequence there; everything before it must be bit-exact, and
-    at least 95 % of all generated tokens must have been compared."""
+    oracle/ft_oracle.py + model_oracle.py; argmax per attribute, the t -> 0 limit of testing-no-type-cp.py's sampling loop) on
+    the CPU, token by token.  The oracle is stepped on the tokens the kernels produced, so every one of the N x T x 6
+    sub-tokens is checked against the oracle's argmax for the SAME history.  A difference is tolerated only where the oracle's
+    own top-2 logit gap for that attribute is below 2e-3 (fp32 accumulation order can flip such a near-tie; a random-init model
+    has many); everywhere else the indices must be bit-exact, and at least 97 % of all sub-tokens must agree outright."""
     g = golden("model_small")
     mr = _load_small(cpm, g, cuda, is_training=False).eval()
     o = mo.OracleCPModel(VOCAB, is_training=False, **SMALL).eval()
@@ -613,22 +614,23 @@ def test_greedy_rollout_tokens_equal_oracle_recurrent_decode(cuda, cpm, golden):
     init = torch.stack([torch.randint(0, n, (N,), generator=torch.Generator().manual_seed(3)) for n in VOCAB], -1)
     got = cpm.RolloutEngine(mr, N, T, greedy=True, true_positions=True, use_graph=True).generate(init.to(cuda))["tokens"].cpu()
     assert torch.equal(got[:, 0], init)
-    compared = 0
+    agree = total = 0
     for n in range(N):
-        cur, mem = init[n:n + 1], None
+        mem = None
         with torch.no_grad():
             for t in range(T):
-                z = o.pos_emb(o.embed(cur[:, None, :]), t).squeeze(1)
+                z = o.pos_emb(o.embed(got[n:n + 1, t][:, None, :]), t).squeeze(1)
                 h, mem = o.transformer_encoder(z, memory=mem)
-                logits = o.forward_output(h)
-                top2 = [lg[0].topk(2).values for lg in logits]
-                if min(float(v[0] - v[1]) for v in top2) < 2e-3:
-                    break
-                nxt = torch.stack([lg[0].argmax() for lg in logits])
-                assert torch.equal(got[n, t + 1], nxt), f"sequence {n} step {t}: kernel {got[n, t + 1].tolist()} vs oracle {nxt.tolist()}"
-                compared += 1
-                cur = nxt[None]
-    assert compared >= 0.95 * N * T, f"only {compared} of {N * T} greedy tokens were outside the near-tie margin"
+                for a, lg in enumerate(o.forward_output(h)):
+                    top2 = lg[0].topk(2)
+                    total += 1
+                    if int(got[n, t + 1, a]) == int(top2.indices[0]):
+                        agree += 1
+                    else:
+                        gap = float(top2.values[0] - top2.values[1])
+                        assert gap < 2e-3 and int(got[n, t + 1, a]) == int(top2.indices[1]), \
+                            f"sequence {n} step {t} attribute {a}: kernel {int(got[n, t + 1, a])} vs oracle {int(top2.indices[0])} (top-2 gap {gap:.2e})"
+    assert agree >= 0.97 * total, f"{agree} of {total} greedy sub-tokens bit-exact"
 
 
 def test_train_step_cfg2_shape_bf16_vs_oracle(cuda, cpm):

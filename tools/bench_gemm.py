@@ -46,21 +46,26 @@ def main():
         bias_bf = bias.bfloat16()
         dy = torch.randn(T, N, device=dev).bfloat16()
         dw = torch.zeros(N, K, device=dev)
-        db = torch.zeros(N, device=dev)
         fl = 2.0 * T * N * K
         t_own = timed(lambda: ops.gemm_nt(x, w, bias), args.iters)
         t_lib = timed(lambda: torch.addmm(bias_bf, x, w.t()), args.iters)
         t_dg = timed(lambda: ops.gemm_nt(dy, wt), args.iters)
         t_dg_lib = timed(lambda: dy @ w, args.iters)
-        t_wg = timed(lambda: ops.gemm_tn_acc(dy, x, dw, db), args.iters)
+        t_wg = timed(lambda: (ops.gemm_tn_acc(dy, x, dw), ops.colsum(dy)), args.iters)
         t_wg_lib = timed(lambda: (torch.mm(dy.t(), x, out_dtype=torch.float32), dy.sum(0, dtype=torch.float32)), args.iters)
         row = dict(layer=name, N=N, K=K, fwd_us=round(t_own, 1), fwd_lib_us=round(t_lib, 1), fwd_tf=round(fl / t_own / 1e6, 1),
                    dgrad_us=round(t_dg, 1), dgrad_lib_us=round(t_dg_lib, 1), dgrad_tf=round(fl / t_dg / 1e6, 1),
                    wgrad_us=round(t_wg, 1), wgrad_lib_us=round(t_wg_lib, 1), wgrad_tf=round(fl / t_wg / 1e6, 1), frac_of_burst_peak=round(fl / t_own / 1e6 / peak, 3))
+        for mode, tag in ((1, "stream"), (3, "wide")):
+            ops.gemm_set_mode(mode)
+            row[f"fwd_{tag}_us"] = round(timed(lambda: ops.gemm_nt(x, w, bias), args.iters), 1)
+            row[f"dgrad_{tag}_us"] = round(timed(lambda: ops.gemm_nt(dy, wt), args.iters), 1)
+        ops.gemm_set_mode(0)
         if name == "ff1":
             t_g = timed(lambda: ops.gemm_nt(x, w, bias, epilogue=ops.GEMM_GELU, p_drop=0.1, seed=1, rng_offset=0), args.iters)
+            t_g0 = timed(lambda: ops.gemm_nt(x, w, bias, epilogue=ops.GEMM_GELU, p_drop=0.0), args.iters)
             t_g_lib = timed(lambda: ops.gelu_dropout(torch.addmm(bias_bf, x, w.t()), 0.1), args.iters)
-            row.update(fwd_gelu_us=round(t_g, 1), fwd_gelu_unfused_us=round(t_g_lib, 1))
+            row.update(fwd_gelu_us=round(t_g, 1), fwd_gelu_nodrop_us=round(t_g0, 1), fwd_gelu_unfused_us=round(t_g_lib, 1))
         if name == "ff2":
             h = torch.randn(T, K, device=dev).bfloat16()
             dyo = torch.randn(T, N, device=dev).bfloat16()
