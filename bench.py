@@ -234,14 +234,8 @@ class PPOIteration:
         self.opt_c = torch.optim.Adam(self.critic.parameters(), lr=lr, fused=True)
         self.red_a = cpmusic.dist.BucketedGradAllReduce(self.actor.parameters(), 25.0)
         self.red_c = cpmusic.dist.BucketedGradAllReduce(self.critic.parameters(), 25.0)
-        groups = int(os.environ.get("CPM_ROLLOUT_GROUPS", "1"))
-        if groups > 1:      # parallel graph branches: latency-bound kernels of one group overlap the others' state updates
-            self.engine = cpmusic.GroupedRolloutEngine(self.actor, SONGS_PER_GPU, ROLLOUT_LEN, groups=groups,
-                                                       steps_per_graph=int(os.environ.get("CPM_ROLLOUT_SPG", "4")), greedy=False,
-                                                       true_positions=True, seed=1234, seq_base=rank * SONGS_PER_GPU)
-        else:
-            self.engine = cpmusic.RolloutEngine(self.actor, SONGS_PER_GPU, ROLLOUT_LEN, greedy=False, true_positions=True,
-                                                seed=1234, seq_base=rank * SONGS_PER_GPU)
+        self.engine = cpmusic.RolloutEngine(self.actor, SONGS_PER_GPU, ROLLOUT_LEN, greedy=False, true_positions=True,
+                                            seed=1234, seq_base=rank * SONGS_PER_GPU)
         self.group = None                              # attach_group() once the process group exists
         g = torch.Generator().manual_seed(1234 + rank)
         self.init_host = torch.stack([torch.randint(0, n, (SONGS_PER_GPU,), generator=g) for n in VOCAB], -1).pin_memory()

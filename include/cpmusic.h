@@ -65,8 +65,8 @@ const char *cpm_linattn_last_impl(void);
  * out / gout are (N,L,H,M) with token stride `ld_o`; gq,gk,gv have token stride `ld_g`.
  * den is (N,L,H) fp32, written by fwd and read by bwd.  E = M = 64 (the reference) only.
  * impl: 0 = auto (chunk-parallel tcgen05 when dtype==BF16 and L%128==0, else simt), 1 = simt,
- *       2 = tcgen05, one CTA per (batch, head[, segment]) walking its chunks in order,
- *       3 = tcgen05, chunk-parallel (one CTA per 128-token chunk; state pre-pass + prefix scan).
+ *       3 = tcgen05, chunk-parallel (one CTA per 128-token chunk; streaming state pre-pass, or per-chunk states + scan
+ *           when there are fewer than 96 (batch, head) chains).
  * Workspace: cpm_linattn_workspace_bytes(N,L,H) bytes (segment / chunk states), scratch only.
  * saved (optional, impl 3): cpm_linattn_saved_bytes(N,L,H) bytes that fwd fills with the per-chunk
  * prefix states (bf16 tiles + fp32 key sums) and bwd reads back instead of rebuilding them — the
@@ -77,7 +77,6 @@ int64_t cpm_linattn_saved_bytes(int N, int L, int H);
 /* Development aid: device buffer (>= 64 int64 per CTA of the chunk-parallel forward kernel) that receives
  * clock64() stamps at its phase boundaries; NULL switches it off (the default). */
 int cpm_debug_linattn_timing(void *device_buffer);
-int cpm_debug_tc_linear_timing(void *device_buffer);    /* 8 int64 per CTA of cpm_tc_linear */
 int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, float *den,
                     int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
                     int dtype, float eps, int impl, void *workspace, int64_t workspace_bytes,
@@ -99,38 +98,6 @@ int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out
 int cpm_linattn_step(const void *q, const void *k, const void *v, float *S, float *Z, void *out,
                      int N, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,
                      int dtype, float eps, void *stream);
-
-/* cpm_linattn_step plus an L2 prefetch: every CTA additionally asks the memory system (cp.async.bulk.prefetch.L2) for the
- * matching 16 KB tile of S_next - the state the NEXT step kernel of the token step will stream (the following layer's;
- * the first layer's for the last one).  when = 1: after this tile's write-back, 2: before its loads.  Results are
- * bit-identical to cpm_linattn_step; E = M = 64 only. */
-/* cpm_linattn_step (E = M = 64) as a persistent kernel: ctas_per_sm (1..3) CTAs per SM walk the (sequence, head) tiles with
- * the next four 16 KB state tiles always in flight through the bulk-copy engine (cp.async.bulk -> shared memory, mbarrier
- * completion); same arithmetic and summation order, bit-identical results. */
-int cpm_linattn_step_tma(const void *q, const void *k, const void *v, float *S, float *Z, void *out, int N, int H, int64_t ld_qkv,
-                         int64_t ld_o, int dtype, float eps, int ctas_per_sm, void *stream);
-int cpm_l2_prefetch(const void *p, int64_t bytes, void *stream);   /* stand-alone: bulk L2 prefetch of [p, p+bytes), 16 KB pieces */
-int cpm_linattn_step_prefetch(const void *q, const void *k, const void *v, float *S, float *Z, void *out, const float *S_next,
-                              int when, int N, int H, int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream);
-
-/* B1 split in two launches (rollout engine): cpm_linattn_step_out computes the step's output from S + Kf (x) v formed in
- * registers (bit-identical to cpm_linattn_step), updates Z and parks [Kf | v] in kv_pending ((N,H,128) fp32);
- * cpm_linattn_state_update then stores S += Kf (x) v.  The second launch may run on another stream / graph branch; it
- * must complete before the next cpm_linattn_step_out on the same state. */
-int cpm_linattn_step_out(const void *q, const void *k, const void *v, const float *S, float *Z, float *kv_pending,
-                         void *out, int N, int H, int64_t ld_qkv, int64_t ld_o, int dtype, float eps, void *stream);
-int cpm_linattn_state_update(float *S, const float *kv_pending, int N, int H, void *stream);
-
-/* B1, deferred write-back (rollout engine only).  Same arithmetic, bit-identical outputs: the rank-1 updates of the
- * last (*step_dev % CPM_LAZY_STATE_PERIOD) tokens live in `ring` ((N,H,PERIOD,128) fp32: [Kf | v] per entry) and are
- * re-applied in registers every step; S is written back only when the ring fills, so a token step moves
- * 16 KB + 16 KB/PERIOD (+ ring) per (sequence, head) instead of 32 KB.  Z is updated every step.
- * flush_only != 0: apply the pending entries and write S (no q/k/v/out needed) — call before anyone reads S while
- * *step_dev % PERIOD != 0.  *step_dev must advance by one per token (cpm_rollout_advance does). */
-#define CPM_LAZY_STATE_PERIOD 8
-int cpm_linattn_step_lazy(const void *q, const void *k, const void *v, float *S, float *Z, float *ring, void *out,
-                          int N, int H, int64_t ld_qkv, int64_t ld_o, int dtype, float eps,
-                          const int32_t *step_dev, int flush_only, void *stream);
 
 /* ------------------------------------------------------------------------------------------
  * C1 — CP embedding gather + sqrt(emb) scale + concat.  Replaces `Embeddings.forward` x6 and
@@ -376,79 +343,6 @@ int cpm_dqn_td_fwd_bwd(const void *q_logits, const void *next_logits, const int6
 int cpm_rollout_advance(const int64_t *tokens, int64_t *history_tok, int64_t n_tok, const float *vals,
                         float *history_f, int64_t n_f, int32_t *step_dev, int32_t max_steps,
                         void *stream);
-
-/* Fused skinny linear layer for the recurrent rollout step (M = sequences <= 64, bf16):
- *     Y[M,N] = epi( pro(A)[M,K] . W[N,K]^T + bias )
- *   prologue 0: A as is;  1: LayerNorm(A) with fp32 gamma/beta (the post-norm of the previous
- *               sub-layer folded into its consumer); xout (optional) receives the normalised A.
- *   epilogue 0: +bias;  1: +bias, exact-erf GELU;  2: +bias + residual[M,N];
- *            3: +bias + pe[pos,:] with pos = pos_dev ? *pos_dev : pos_offset (PositionalEncoding).
- * Replaces, per token step, the Linear / LayerNorm / GELU / residual launches of ft's
- * RecurrentTransformerEncoderLayer with one launch per Linear.
- * W is the packed bf16 weight (rows = output features, K contiguous), bias bf16 (may be NULL).
- * K % 64 == 0, K <= 2048, and 16*ceil(M/16)*(K+8)*2 bytes of shared memory must fit (<= 200 KB). */
-int cpm_skinny_linear(const void *A, int64_t lda, const void *W, const void *bias, void *Y, int64_t ldy,
-                      int M, int N, int K, int prologue, const float *gamma, const float *beta, float eps,
-                      void *xout, int epilogue, const void *residual, int64_t ldr, const float *pe,
-                      int pe_max_len, int pos_offset, const int32_t *pos_dev, void *stream);
-
-/* tcgen05 / TMA Linear layer for the rollout token step at any M (256 songs per GPU in the bench), bf16:
- *     Y[M,N] = epi( LNfold(A)[M,K] . W[N,K]^T )
- * The LayerNorm of the input is folded algebraically, so no kernel ever materialises a LayerNorm output
- * (ft RecurrentTransformerEncoderLayer, SURVEY App. A.2: x = norm1(x + attn); y = norm2(x + ffn)):
- *     LN(a).W^T = rstd_m * ( a.W'^T - mean_m * c1[n] ) + c2[n],  W' = gamma (.) W (bf16, passed as W),
- *     c1[n] = sum_k W'[n,k],  c2[n] = sum_k beta_k W[n,k] + bias[n]            (fp32, built by the host)
- *   c1 == NULL: plain  a.W^T + c2  (c2 = bias or NULL).
- *   stats_in [M][parts_in][2] fp32: per-row partial (sum, sum of squares) of A as written by the producer
- *   kernel (one partial per N-tile of that producer); mean / rstd are rebuilt from them in a fixed order.
- *   epilogue CPM_TL_EPI_BIAS | _GELU (exact erf) | _RES (+ R[M,N]) | _RES_LN (+ LayerNorm(R) rebuilt from
- *   stats_r/gamma_r/beta_r, R = pre-LN sums) | _PE (+ pe[pos,:], pos = pos_offset + (pos_dev ? *pos_dev : 0)).
- *   stats_out (optional) [M][ceil(N/block_n)][2]: partials of the bf16 values stored in Y.
- * K % 64 == 0, N % 64 == 0, block_n = 64; W has w_rows >= N rows of K contiguous bf16.
- * split_k in {1,2,4,8}: the K extent of every 128 x block_n tile is split over a thread-block cluster; the
- *   partial tiles are reduced over distributed shared memory in rank order (deterministic).
- * use_pdl: launch with programmatic stream serialization; the kernel fetches its weight tiles before
- * griddepcontrol.wait so that only the activation fetch + UMMA + epilogue stay on the critical path. */
-#define CPM_TL_EPI_BIAS 0
-#define CPM_TL_EPI_GELU 1
-#define CPM_TL_EPI_RES 2
-#define CPM_TL_EPI_RES_LN 3
-#define CPM_TL_EPI_PE 4
-int cpm_tc_linear(const void *A, int64_t lda, const void *W, int64_t w_rows, const float *c1, const float *c2,
-                  void *Y, int64_t ldy, int M, int N, int K, int epilogue, const float *stats_in, int parts_in,
-                  float eps, const void *R, int64_t ldr, const float *stats_r, int parts_r, const float *gamma_r,
-                  const float *beta_r, const float *pe, int pe_max, int pos_offset, const int32_t *pos_dev,
-                  float *stats_out, int block_n, int split_k, int use_pdl, void *stream);
-
-/* Rollout token step without LayerNorm launches (csrc/rollout_fold.cu).  The post-norm LayerNorms of ft's
- * RecurrentTransformerEncoderLayer are folded into their consumers: the library GEMM runs on the
- * raw pre-LayerNorm sums with W' = gamma (.) W and no bias, and
- *   cpm_linattn_step_fold  applies  q,k,v = rstd*(raw - mean*c1) + c2  on load, performs the recurrent step of
- *                          cpm_linattn_step, and writes xres = LayerNorm(s_prev) + bias_next (the accumulate-into
- *                          operand of the out-projection GEMM, beta = 1).  fold = 0: s_prev is the plain layer input
- *                          (first layer), q,k,v = raw + c2, xres = s_prev + bias_next.
- *   cpm_gelu_fold          writes h = gelu(rstd*(raw - mean*c1) + c2) (exact erf) and xres = LayerNorm(s) + bias_next
- *                          (accumulate-into operand of linear2).
- * c1[n] = sum_k W'[n,k], c2[n] = sum_k beta_k W[n,k] + bias[n] (fp32, host-built); mean / rstd are recomputed from the
- * bf16 row by every CTA that needs them.  bf16 activations; d = 64*H <= 2048. */
-int cpm_linattn_step_fold(const void *raw_qkv, const void *s_prev, const float *c1, const float *c2,
-                          const float *gamma, const float *beta, const float *bias_next, float *S, float *Z,
-                          void *out, void *xres, int N, int H, int d, int fold, float eps_ln, float eps_attn,
-                          void *stream);
-int cpm_gelu_fold(const void *raw, const void *s, const float *c1, const float *c2, const float *gamma,
-                  const float *beta, const float *bias_next, void *h, void *xres, int N, int d, int dff, float eps,
-                  void *stream);
-
-/* Persistent megakernel for ONE recurrent rollout token step (embedding -> all layers -> heads ->
- * sampling -> history/step bookkeeping) as a single cooperative launch: 148 CTAs walk a host-built
- * phase list separated by a software grid barrier (csrc/rollout_mega.cu).  Replaces the ~65-100
- * launch-bound kernels per token of the unfused path (and the reference's batch-1 host loop,
- * testing-no-type-cp.py:157-167).  `globals_dev` / `phases_dev` are device copies of the
- * MegaGlobals / MegaPhase structs (layout checked with cpm_mega_sizes; built by rollout.py).
- * <= 32 sequences, bf16, widths multiples of 64 and <= 2048. */
-int cpm_mega_sizes(int *globals_bytes, int *phase_bytes);
-int64_t cpm_mega_smem_bytes(void);
-int cpm_rollout_step_mega(const void *globals_dev, const void *phases_dev, void *stream);
 
 #ifdef __cplusplus
 }

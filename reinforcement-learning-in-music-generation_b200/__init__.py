@@ -8,7 +8,7 @@ from .encoder import (TransformerEncoderBuilder, RecurrentEncoderBuilder, Triang
                       install_fast_transformers_shim)
 from .model import (CPLinearTransformer, TransformerModel, LinearTransformer, Actor_Transformer,  # noqa: F401
                     Critic_Transformer)
-from .rollout import RolloutEngine, GroupedRolloutEngine  # noqa: F401
+from .rollout import RolloutEngine  # noqa: F401
 from .graphs import GraphedTrainStep  # noqa: F401
 from .ops import manual_seed  # noqa: F401
 

@@ -37,7 +37,6 @@ SIGNATURES = {
     "cpm_linattn_workspace_bytes": (c_int64, [c_int, c_int, c_int]),
     "cpm_linattn_saved_bytes": (c_int64, [c_int, c_int, c_int]),
     "cpm_debug_linattn_timing": (c_int, [_P]),
-    "cpm_debug_tc_linear_timing": (c_int, [_P]),
     "cpm_linattn_fwd": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, c_int64, c_int64,
                                 c_int, c_float, c_int, _P, c_int64, _P, c_int64, _P]),
     "cpm_linattn_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int,
@@ -46,16 +45,6 @@ SIGNATURES = {
                                  c_int, c_float, _P]),
     "cpm_colsum_partials_rows": (c_int, [c_int]),
     "cpm_colsum": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, c_int, _P]),
-    "cpm_linattn_step_tma": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, c_int, _P]),
-    "cpm_l2_prefetch": (c_int, [_P, c_int64, _P]),
-    "cpm_linattn_step_prefetch": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int64, c_int64, c_int, c_float, _P]),
-    "cpm_linattn_step_fold": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_float, c_float, _P]),
-    "cpm_gelu_fold": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_float, _P]),
-    "cpm_tc_linear": (c_int, [_P, c_int64, _P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, c_int, c_float, _P, c_int64,
-                              _P, c_int, _P, _P, _P, c_int, c_int, _P, _P, c_int, c_int, c_int, _P]),
-    "cpm_linattn_step_out": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, _P]),
-    "cpm_linattn_state_update": (c_int, [_P, _P, c_int, c_int, _P]),
-    "cpm_linattn_step_lazy": (c_int, [_P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, c_int64, c_int, c_float, _P, c_int, _P]),
     "cpm_reward_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
     "cpm_set_rng_base": (c_int, [_P]),
     "cpm_rowdot_partials_rows": (c_int, []),
@@ -93,11 +82,6 @@ SIGNATURES = {
     "cpm_dqn_td_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, _IP, c_int, c_int,
                                    c_float, c_float, c_int, c_int, _P]),
     "cpm_rollout_advance": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int32, _P]),
-    "cpm_mega_sizes": (c_int, [_IP, _IP]),
-    "cpm_mega_smem_bytes": (c_int64, []),
-    "cpm_rollout_step_mega": (c_int, [_P, _P, _P]),
-    "cpm_skinny_linear": (c_int, [_P, c_int64, _P, _P, _P, c_int64, c_int, c_int, c_int, c_int, _P, _P, c_float, _P, c_int,
-                                  _P, c_int64, _P, c_int, c_int, _P, _P]),
 }
 
 _lib = None
@@ -107,7 +91,7 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_debug_tc_linear_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_rowdot_partials_rows": 0, "cpm_gemm_set_mode": 0, "cpm_set_chain_pdl": 0, "cpm_mega_sizes": 0, "cpm_mega_smem_bytes": 0,
+    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_rowdot_partials_rows": 0, "cpm_gemm_set_mode": 0, "cpm_set_chain_pdl": 0, 
     "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2, "cpm_colsum": 2, "cpm_rowdot_bwd": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
                                                                                 # kernel (ops adds 1 when the scan path runs); bwd = pre-pass, scan, main
 })

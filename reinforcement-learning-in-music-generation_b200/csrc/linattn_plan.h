@@ -35,13 +35,6 @@ int linattn_bwd_simt_launch(const void *q, const void *k, const void *v, const v
 int linattn_segment_states_launch(const void *q, const void *k, const void *v, const void *out, const float *den,
                                   const void *gout, int N, int L, int H, int64_t ld_qkv, int64_t ld_o, int dtype, void *ws,
                                   bool reverse_too, cudaStream_t st);
-// tcgen05 path (bf16, L % 128 == 0); returns CPM_ERR_UNSUPPORTED when it cannot take the shape.
-int linattn_fwd_tc_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H,
-                          int64_t ld_qkv, int64_t ld_o, float eps, void *ws, cudaStream_t st);
-int linattn_bwd_tc_launch(const void *q, const void *k, const void *v, const void *out, const float *den,
-                          const void *gout, void *gq, void *gk, void *gv, int N, int L, int H, int64_t ld_qkv,
-                          int64_t ld_o, int64_t ld_g, float eps, void *ws, cudaStream_t st);
-
 // chunk-parallel tcgen05 path (linattn_cp.cu)
 int64_t linattn_cp_workspace_bytes(int N, int L, int H);
 int64_t linattn_cp_saved_bytes(int N, int L, int H);

@@ -326,14 +326,9 @@ def linattn_last_impl() -> str:
     return _lib.load().cpm_linattn_last_impl().decode()
 
 
-# persistent TMA-staged step kernel: CTAs per SM (0 = the one-CTA-per-tile kernel); A/B switch, see profiles
-STEP_TMA_CTAS = int(os.environ.get("CPM_STEP_TMA", "0"))
-
-
-def linattn_step(q, k, v, S, Z, eps=EPS_ATTN, prefetch=None, prefetch_when=1, tma_ctas=None):
+def linattn_step(q, k, v, S, Z, eps=EPS_ATTN):
     """Recurrent step. q,k,v: (N,H,64) views sharing a row stride; S (N,H,64,64), Z (N,H,64) fp32
-    are updated in place; returns (N,H,64).  prefetch: another (N,H,64,64) fp32 state (the next layer's) to pull into
-    L2 from inside the kernel (cpm_linattn_step_prefetch; same results)."""
+    are updated in place; returns (N,H,64)."""
     _cuda(q, k, v, S, Z)
     N, H, E = q.shape
     ld = q.stride(0)
@@ -344,72 +339,9 @@ def linattn_step(q, k, v, S, Z, eps=EPS_ATTN, prefetch=None, prefetch_when=1, tm
     if S.dtype != torch.float32 or Z.dtype != torch.float32 or not S.is_contiguous() or not Z.is_contiguous():
         raise ValueError("recurrent state must be contiguous float32")
     out = torch.empty(N, H, E, dtype=q.dtype, device=q.device)
-    if prefetch is not None:
-        if prefetch.shape != S.shape or prefetch.dtype != torch.float32 or not prefetch.is_contiguous() or E != 64:
-            raise ValueError("prefetch must be a contiguous float32 state of the same shape (E = 64)")
-        check(_lib.load().cpm_linattn_step_prefetch(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), _p(prefetch), int(prefetch_when),
-                                                    N, H, ld, H * E, _dt(q), eps, _st()))
-        return out
-    tma_ctas = STEP_TMA_CTAS if tma_ctas is None else tma_ctas
-    if tma_ctas and E == 64:
-        check(_lib.load().cpm_linattn_step_tma(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), N, H, ld, H * E, _dt(q), eps, int(tma_ctas), _st()))
-        return out
     check(_lib.load().cpm_linattn_step(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(out), N, H, E, E, ld, H * E,
                                        _dt(q), eps, _st()))
     return out
-
-
-def l2_prefetch(t):
-    """Ask the memory system to pull a contiguous CUDA tensor into L2 (cpm_l2_prefetch; returns immediately)."""
-    _cuda(t)
-    check(_lib.load().cpm_l2_prefetch(_p(t), t.numel() * t.element_size(), _st()))
-
-
-def linattn_step_out(q, k, v, S, Z, kv_pending, eps=EPS_ATTN):
-    """First half of the split step: output + Z update + parked [Kf | v]; S is only read (cpm_linattn_step_out)."""
-    _cuda(q, k, v, S, Z, kv_pending)
-    N, H, E = q.shape
-    ld = q.stride(0)
-    if not (k.stride(0) == ld and v.stride(0) == ld and q.stride(2) == 1 and q.stride(1) == E):
-        raise ValueError("q,k,v must be (N,H,E) with a common row stride and packed heads")
-    if S.shape[0] != N:
-        raise ValueError("The batch size changed during iteration")
-    out = torch.empty(N, H, E, dtype=q.dtype, device=q.device)
-    check(_lib.load().cpm_linattn_step_out(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(kv_pending), _p(out), N, H, ld, H * E, _dt(q), eps, _st()))
-    return out
-
-
-def linattn_state_update(S, kv_pending):
-    """Second half of the split step: S += Kf (x) v from the parked vectors (cpm_linattn_state_update)."""
-    check(_lib.load().cpm_linattn_state_update(_p(S), _p(kv_pending), S.shape[0], S.shape[1], _st()))
-
-
-LAZY_STATE_PERIOD = 8      # CPM_LAZY_STATE_PERIOD
-
-
-def linattn_step_lazy(q, k, v, S, Z, ring, step_dev, eps=EPS_ATTN):
-    """Recurrent step with deferred state write-back (include/cpmusic.h, cpm_linattn_step_lazy): same outputs as
-    linattn_step bit for bit; S is current only when *step_dev % LAZY_STATE_PERIOD == 0 or after linattn_state_flush."""
-    _cuda(q, k, v, S, Z, ring)
-    N, H, E = q.shape
-    ld = q.stride(0)
-    if not (k.stride(0) == ld and v.stride(0) == ld and q.stride(2) == 1 and q.stride(1) == E):
-        raise ValueError("q,k,v must be (N,H,E) with a common row stride and packed heads")
-    if S.shape[0] != N:
-        raise ValueError("The batch size changed during iteration")
-    if ring.shape != (N, H, LAZY_STATE_PERIOD, 128) or ring.dtype != torch.float32 or not ring.is_contiguous():
-        raise ValueError(f"ring must be contiguous float32 (N,H,{LAZY_STATE_PERIOD},128)")
-    out = torch.empty(N, H, E, dtype=q.dtype, device=q.device)
-    check(_lib.load().cpm_linattn_step_lazy(_p(q), _p(k), _p(v), _p(S), _p(Z), _p(ring), _p(out), N, H, ld, H * E, _dt(q), eps,
-                                            _p(step_dev), 0, _st()))
-    return out
-
-
-def linattn_state_flush(S, Z, ring, step_dev):
-    """Applies the pending ring entries to S (no-op when *step_dev % LAZY_STATE_PERIOD == 0)."""
-    N, H = S.shape[0], S.shape[1]
-    check(_lib.load().cpm_linattn_step_lazy(None, None, None, _p(S), _p(Z), _p(ring), None, N, H, 0, 0, _lib.BF16, EPS_ATTN,
-                                            _p(step_dev), 1, _st()))
 
 
 # --------------------------------------------------------------------------- dense linear: own tcgen05 GEMMs (csrc/tc_gemm.cu)
@@ -1120,96 +1052,3 @@ def rollout_advance(tokens, history_tok, vals, history_f, step_dev, max_steps):
     n_f = vals.numel() if vals is not None else 0
     check(_lib.load().cpm_rollout_advance(_p(tokens), _p(history_tok), n_tok, _p(vals), _p(history_f), n_f, _p(step_dev),
                                           max_steps, _st()))
-
-
-# --------------------------------------------------------------------------- fused skinny linear (rollout step)
-EPI_BIAS, EPI_GELU, EPI_RESIDUAL, EPI_PE = 0, 1, 2, 3
-
-
-def skinny_linear(a, wc, bc, n_out=None, ln=None, xout=None, epilogue=EPI_BIAS, residual=None, pe=None, pos_offset=0,
-                  pos_dev=None, out=None):
-    """Y = epi(pro(a) @ wc^T + bc) in ONE launch (no autograd; inference / rollout only).
-    a (M,K) bf16, wc (N_pad,K) bf16 packed weight, bc (N_pad) bf16.  ln = (gamma, beta, eps) applies
-    LayerNorm to `a` first (and writes it to `xout` if given)."""
-    _cuda(a, wc)
-    if a.dtype != torch.bfloat16 or wc.dtype != torch.bfloat16:
-        raise ValueError("skinny_linear is bf16 only")
-    M, K = a.shape
-    N = wc.shape[0] if n_out is None else n_out
-    y = out if out is not None else torch.empty(M, wc.shape[0], dtype=torch.bfloat16, device=a.device)
-    gamma, beta, eps = (ln if ln is not None else (None, None, 0.0))
-    pe2 = None if pe is None else pe.reshape(-1, pe.shape[-1])
-    check(_lib.load().cpm_skinny_linear(_p(a), a.stride(0), _p(wc), _p(bc), _p(y), y.stride(0), M, N, K,
-                                        0 if ln is None else 1, _p(gamma), _p(beta), eps, _p(xout), epilogue,
-                                        _p(residual), 0 if residual is None else residual.stride(0), _p(pe2),
-                                        0 if pe2 is None else pe2.shape[0], pos_offset, _p(pos_dev), _st()))
-    return y
-
-
-# --------------------------------------------------------------------------- tcgen05 Linear with LayerNorm fold (rollout step)
-TL_BIAS, TL_GELU, TL_RES, TL_RES_LN, TL_PE = 0, 1, 2, 3, 4
-
-
-def tc_linear_split(M: int, N: int, K: int, block_n: int, target_ctas: int = 160) -> int:
-    """K-split (cluster size) that brings the CTA count near the SM count without dropping below one 64-wide
-    K block per CTA."""
-    import os
-    pol = os.environ.get("CPM_TL_SPLIT", "auto")
-    if pol == "none" or (pol == "k512" and K <= 512):
-        return 1
-    tiles = -(-N // block_n) * -(-M // 128)
-    s = 1
-    while s < 8 and tiles * s * 2 <= target_ctas and (K // 64) // (s * 2) >= 1:
-        s *= 2
-    return s
-
-
-def tc_linear(a, w, c2, n_out=None, c1=None, stats_in=None, eps=EPS_LN, epilogue=TL_BIAS, residual=None, stats_r=None, gamma_r=None,
-              beta_r=None, pe=None, pos_offset=0, pos_dev=None, out=None, stats_out=None, block_n=64, split_k=None, pdl=False):
-    """Y = epi(LNfold(a) @ w^T) in ONE tcgen05 launch (no autograd; rollout only).  a (M,K) bf16; w (rows>=N, K) bf16
-    (pre-scaled by gamma when c1 is given); c1/c2 (N,) fp32; stats_* (M, parts, 2) fp32 row partials."""
-    _cuda(a, w)
-    if a.dtype != torch.bfloat16 or w.dtype != torch.bfloat16:
-        raise ValueError("tc_linear is bf16 only")
-    M, K = a.shape
-    if w.shape[1] != K or a.stride(1) != 1 or not w.is_contiguous():
-        raise ValueError(f"tc_linear: a (M,{K}) needs a contiguous weight (N,{K}), got {tuple(w.shape)}")
-    N = w.shape[0] if n_out is None else n_out
-    y = out if out is not None else torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
-    pe2 = None if pe is None else pe.reshape(-1, pe.shape[-1])
-    if split_k is None:
-        split_k = tc_linear_split(M, N, K, block_n)
-    check(_lib.load().cpm_tc_linear(_p(a), a.stride(0), _p(w), w.shape[0], _p(c1), _p(c2), _p(y), y.stride(0), M, N, K, epilogue,
-                                    _p(stats_in), 0 if stats_in is None else stats_in.shape[1], eps, _p(residual),
-                                    0 if residual is None else residual.stride(0), _p(stats_r), 0 if stats_r is None else stats_r.shape[1],
-                                    _p(gamma_r), _p(beta_r), _p(pe2), 0 if pe2 is None else pe2.shape[0], pos_offset, _p(pos_dev),
-                                    _p(stats_out), block_n, split_k, 1 if pdl else 0, _st()))
-    return y
-
-
-# --------------------------------------------------------------------------- rollout step with folded LayerNorms
-def linattn_step_fold(raw_qkv, s_prev, c1, c2, gamma, beta, bias_next, S, Z, n_heads, fold=True, eps_ln=EPS_LN, eps_attn=EPS_ATTN):
-    """Recurrent step on the RAW output of the QKV GEMM (s_prev @ W'^T, no bias): applies the LayerNorm fold to q,k,v,
-    updates S / Z in place and returns (attention output (N, H*64), xres = LayerNorm(s_prev) + bias_next)."""
-    _cuda(raw_qkv, s_prev, S, Z)
-    N, d = s_prev.shape
-    if raw_qkv.dtype != torch.bfloat16 or s_prev.dtype != torch.bfloat16 or not raw_qkv.is_contiguous() or not s_prev.is_contiguous():
-        raise ValueError("linattn_step_fold needs contiguous bf16 activations")
-    if S.shape[0] != N:
-        raise ValueError("The batch size changed during iteration")
-    out = torch.empty(N, d, dtype=torch.bfloat16, device=s_prev.device)
-    xres = torch.empty(N, d, dtype=torch.bfloat16, device=s_prev.device)
-    check(_lib.load().cpm_linattn_step_fold(_p(raw_qkv), _p(s_prev), _p(c1), _p(c2), _p(gamma), _p(beta), _p(bias_next), _p(S), _p(Z),
-                                            _p(out), _p(xres), N, n_heads, d, 1 if fold else 0, eps_ln, eps_attn, _st()))
-    return out, xres
-
-
-def gelu_fold(raw, s, c1, c2, gamma, beta, bias_next, eps=EPS_LN):
-    """h = gelu(LNfold(raw)), xres = LayerNorm(s) + bias_next (see include/cpmusic.h)."""
-    _cuda(raw, s)
-    N, dff = raw.shape
-    d = s.shape[1]
-    h = torch.empty_like(raw)
-    xres = torch.empty_like(s)
-    check(_lib.load().cpm_gelu_fold(_p(raw), _p(s), _p(c1), _p(c2), _p(gamma), _p(beta), _p(bias_next), _p(h), _p(xres), N, d, dff, eps, _st()))
-    return h, xres

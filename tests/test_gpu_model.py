@@ -257,44 +257,6 @@ def test_rollout_engine_graph_equals_eager_equals_teacher_forced(cuda, cpm, gold
     assert not torch.equal(full, other)
 
 
-@pytest.mark.parametrize("T", [16, 27])
-def test_lazy_state_rollout_is_bit_identical(cuda, cpm, golden, T):
-    """Deferred state write-back (S written once per 8 tokens, pending rank-1 updates re-applied in registers in the
-    original order) generates bit-identical tokens, log-probs AND final recurrent state to the eager step kernel —
-    graph replay and eager stepping, sampled decoding, T a multiple of the period or not."""
-    g = golden("model_small")
-    mr = _load_small(cpm, g, cuda, dtype=torch.bfloat16, is_training=False).eval()
-    N = 5
-    init = torch.stack([torch.randint(0, n, (N,), generator=torch.Generator().manual_seed(3)) for n in VOCAB], -1).to(cuda)
-    ref_e = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=False)
-    ref = ref_e.generate(init)
-    for use_graph, kw in ((False, dict(lazy_state=True)), (True, dict(lazy_state=True)), (False, dict(split_state=True)),
-                          (True, dict(split_state=True)), (True, dict(prefetch_state=1)), (False, dict(prefetch_state=2)),
-                          (True, dict(prefetch_state=3)), (True, dict(prefetch_state=4)), (False, dict(prefetch_state=4))):
-        eng = cpm.RolloutEngine(mr, N, T, greedy=False, seed=11, use_graph=use_graph, **kw)
-        for _ in range(2):
-            out = eng.generate(init)
-            assert torch.equal(out["tokens"], ref["tokens"]) and torch.equal(out["logp"], ref["logp"])
-            assert torch.equal(eng.S, ref_e.S) and torch.equal(eng.Z, ref_e.Z)
-
-
-@pytest.mark.parametrize("groups,spg", [(2, 1), (3, 4)])
-def test_grouped_rollout_equals_ungrouped(cuda, cpm, golden, groups, spg):
-    """The multi-stream grouped engine (parallel graph branches, `spg` token steps per graph) generates
-    bit-identical tokens and log-probs to the single-chain engine, greedy and sampled."""
-    g = golden("model_small")
-    mr = _load_small(cpm, g, cuda, is_training=False).eval()
-    N, T = 6, 26
-    init = torch.stack([torch.randint(0, n, (N,), generator=torch.Generator().manual_seed(5)) for n in VOCAB], -1).to(cuda)
-    for greedy in (True, False):
-        ref = cpm.RolloutEngine(mr, N, T, greedy=greedy, seed=77, seq_base=10, use_graph=False).generate(init)
-        eng = cpm.GroupedRolloutEngine(mr, N, T, groups=groups, steps_per_graph=spg, greedy=greedy, seed=77, seq_base=10)
-        for _ in range(2):                                           # second call: replay after reset
-            out = eng.generate(init)
-            assert torch.equal(out["tokens"], ref["tokens"])
-            assert torch.equal(out["logp"], ref["logp"])
-
-
 def test_ppo_and_dqn_readouts(cuda, cpm, golden):
     g = golden("model_small")
     m = _load_small(cpm, g, cuda, cls=cpm.LinearTransformer).eval()
@@ -432,130 +394,6 @@ def test_rollout_graph_sees_optimizer_updates(cuda, cpm, golden):
     after_eager = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False).generate(init)["tokens"]
     assert torch.equal(after_graph, after_eager)
     assert not torch.equal(before, after_graph)          # lr 0.5 really changed the policy
-
-
-def test_rollout_fused_step_matches_unfused_and_oracle(cuda, cpm, golden):
-    """The fused rollout step (one launch per Linear: LayerNorm prologue, bias/GELU/residual/PE
-    epilogues) against the unfused kernel path and the fp64 oracle recurrence, step by step on the
-    same token stream.  bf16: logits within 6e-2 of the oracle, fused vs unfused within 4e-2."""
-    g = golden("model_small")
-    m = _load_small(cpm, g, cuda, dtype=torch.bfloat16).eval()
-    o = mo.OracleCPModel(VOCAB, is_training=False, **SMALL).double().eval()
-    o.load_state_dict({k[4:]: torch.from_numpy(g[k]).double() for k in g.files if k.startswith("sd::")}, strict=False)
-    N, T = 4, 10
-    x = torch.from_numpy(g["x"])[:1, :T].expand(N, T, 6).contiguous()
-    ef = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, fused=True)
-    eu = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, fused=False)
-    assert ef.fused_supported()
-    ef.reset(x[:, 0].to(cuda))
-    eu.reset(x[:, 0].to(cuda))
-    mem = None
-    with torch.no_grad():
-        for t in range(T):
-            ef.cur.copy_(x[:, t].to(cuda))
-            eu.cur.copy_(x[:, t].to(cuda))
-            ef.step_dev.fill_(t)
-            eu.step_dev.fill_(t)
-            lf, lu = ef._logits_fused(), eu._logits_unfused()
-            h, mem = o.forward_hidden(x[:1, t:t + 1], mem, is_training=False, pos_offset=t)
-            ref = torch.cat(o.forward_output(h), -1)[0]
-            _cmp(lf[0, :339], ref, 6e-2, 3e-2, f"fused vs oracle step {t}")
-            _cmp(lf[:, :339], lu[:, :339].float(), 4e-2, 2e-2, f"fused vs unfused step {t}")
-    # graph-captured fused generation == eager fused generation
-    init = x[:, 0].to(cuda)
-    a = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=True, fused=True).generate(init)["tokens"]
-    b = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, fused=True).generate(init)["tokens"]
-    assert torch.equal(a, b)
-
-
-@pytest.mark.parametrize("mode,pdl", [("tc", False), ("tc", True), ("fold", False)])
-def test_rollout_tc_step_matches_unfused_and_oracle(cuda, cpm, golden, mode, pdl):
-    """The tcgen05 rollout step (every Linear one cpm_tc_linear launch; LayerNorms folded algebraically into the
-    consumer GEMM, LayerNorm residuals rebuilt on the fly, optionally chained with programmatic dependent launch)
-    against the unfused kernel path and the fp64 oracle recurrence, step by step on the same token stream.
-    bf16: logits within 6e-2 of the oracle, tc vs unfused within 5e-2."""
-    g = golden("model_small")
-    m = _load_small(cpm, g, cuda, dtype=torch.bfloat16).eval()
-    o = mo.OracleCPModel(VOCAB, is_training=False, **SMALL).double().eval()
-    o.load_state_dict({k[4:]: torch.from_numpy(g[k]).double() for k in g.files if k.startswith("sd::")}, strict=False)
-    N, T = 4, 10
-    x = torch.from_numpy(g["x"])[:1, :T].expand(N, T, 6).contiguous()
-    et = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode=mode, pdl=pdl)
-    eu = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="unfused")
-    et.reset(x[:, 0].to(cuda))
-    eu.reset(x[:, 0].to(cuda))
-    et._tc_refresh()
-    mem = None
-    with torch.no_grad():
-        for t in range(T):
-            et.cur.copy_(x[:, t].to(cuda))
-            eu.cur.copy_(x[:, t].to(cuda))
-            et.step_dev.fill_(t)
-            eu.step_dev.fill_(t)
-            lt, lu = (et._logits_tc() if mode == "tc" else et._logits_fold()), eu._logits_unfused()
-            h, mem = o.forward_hidden(x[:1, t:t + 1], mem, is_training=False, pos_offset=t)
-            ref = torch.cat(o.forward_output(h), -1)[0]
-            _cmp(lt[0, :339], ref, 6e-2, 3e-2, f"tc vs oracle step {t}")
-            _cmp(lt[:, :339], lu[:, :339].float(), 5e-2, 2e-2, f"tc vs unfused step {t}")
-    # graph-captured generation == eager generation, and the graph sees in-place parameter updates
-    init = x[:, 0].to(cuda)
-    eg = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=True, mode=mode, pdl=pdl)
-    a = eg.generate(init)["tokens"]
-    b = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode=mode, pdl=pdl).generate(init)["tokens"]
-    assert torch.equal(a, b)
-    assert torch.equal(eg.generate(init)["tokens"], a)
-    with torch.no_grad():
-        for p in m.parameters():
-            p.add_(0.05 * torch.randn_like(p))
-    after = eg.generate(init)["tokens"]
-    fresh = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode=mode, pdl=pdl).generate(init)["tokens"]
-    assert torch.equal(after, fresh) and not torch.equal(after, a)
-
-
-def test_rollout_megakernel_matches_unfused_and_oracle(cuda, cpm, golden):
-    """The persistent cooperative megakernel (one launch per token step) against the unfused kernel
-    path and the fp64 oracle recurrence, teacher-forced step by step; then free-running generation:
-    greedy tokens agree with the unfused path except at bf16 near-ties, history / log-probs /
-    step counter bookkeeping is right, and sampled rollouts are shard-invariant."""
-    g = golden("model_small")
-    m = _load_small(cpm, g, cuda, dtype=torch.bfloat16).eval()
-    o = mo.OracleCPModel(VOCAB, is_training=False, **SMALL).double().eval()
-    o.load_state_dict({k[4:]: torch.from_numpy(g[k]).double() for k in g.files if k.startswith("sd::")}, strict=False)
-    N, T = 4, 10
-    x = torch.from_numpy(g["x"])[:1, :T + 1].expand(N, T + 1, 6).contiguous()
-    em = cpm.RolloutEngine(m, N, T, greedy=True, mode="mega")
-    eu = cpm.RolloutEngine(m, N, T, greedy=True, use_graph=False, mode="unfused")
-    em.reset(x[:, 0].to(cuda))
-    eu.reset(x[:, 0].to(cuda))
-    m.refresh_packs()
-    mem = None
-    with torch.no_grad():
-        for t in range(T):
-            em.cur.copy_(x[:, t].to(cuda))
-            eu.cur.copy_(x[:, t].to(cuda))
-            em.step_dev.fill_(t)
-            eu.step_dev.fill_(t)
-            em._step_mega()
-            lm = em._mega["keep"][0]["logits"].float()
-            lu = eu._logits_unfused().float()
-            h, mem = o.forward_hidden(x[:1, t:t + 1], mem, is_training=False, pos_offset=t)
-            ref = torch.cat(o.forward_output(h), -1)[0]
-            _cmp(lm[0, :339], ref, 6e-2, 3e-2, f"mega vs oracle step {t}")
-            _cmp(lm[:, :339], lu[:, :339], 4e-2, 2e-2, f"mega vs unfused step {t}")
-            assert int(em.step_dev.item()) == t + 1                      # the kernel advances the step counter itself
-            tok_ref, lp_ref, _ = cpm.ops.heads_sample(lm.bfloat16(), m.seg, greedy=True, want_logp=True)
-            assert torch.equal(em.cur, tok_ref) and torch.equal(em.hist_tok[t], tok_ref)
-            _cmp(em.hist_logp[t], lp_ref, 1e-4, 1e-4, "log-prob history")
-    init = x[:, 0].to(cuda)
-    a = cpm.RolloutEngine(m, N, 40, greedy=True, mode="mega").generate(init)
-    b = cpm.RolloutEngine(m, N, 40, greedy=True, mode="unfused", use_graph=False).generate(init)
-    assert a["tokens"].shape == (N, 41, 6)
-    first_rows = (a["tokens"][:, :6] == b["tokens"][:, :6]).float().mean().item()
-    assert first_rows > 0.95, first_rows
-    assert torch.equal(cpm.RolloutEngine(m, N, 40, greedy=True, mode="mega").generate(init)["tokens"], a["tokens"])   # deterministic
-    full = cpm.RolloutEngine(m, 5, 30, greedy=False, seed=9, seq_base=0, mode="mega").generate(x[:1, 0].expand(5, 6).to(cuda))["tokens"]
-    part = cpm.RolloutEngine(m, 2, 30, greedy=False, seed=9, seq_base=3, mode="mega").generate(x[:1, 0].expand(2, 6).to(cuda))["tokens"]
-    assert torch.equal(full[3:], part)                                   # Philox keyed by global sequence id
 
 
 def test_graphed_train_step_equals_eager_and_keeps_dropout_fresh(cuda, cpm, golden):

@@ -47,7 +47,7 @@ def test_argument_validation_without_gpu(cpm):
     p += (-p) % 16
     rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 64, 1, 32, 32, 64, 64, 0, 1e-6, 0, None, 0, None, 0, None)
     assert rc == -1 and b"E=M=64" in lib.cpm_last_error_string()
-    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 2, p, 1 << 20, None, 0, None)
+    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 128, 1, 64, 64, 64, 64, 0, 1e-6, 3, p, 1 << 20, None, 0, None)
     assert rc == -7                                                   # tcgen05 path refuses fp32
     rc = lib.cpm_linattn_fwd(p + 2, p, p, p, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 0, p, 1 << 20, None, 0, None)
     assert rc == -2
