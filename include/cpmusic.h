@@ -344,6 +344,68 @@ int cpm_rollout_advance(const int64_t *tokens, int64_t *history_tok, int64_t n_t
                         float *history_f, int64_t n_f, int32_t *step_dev, int32_t max_steps,
                         void *stream);
 
+/* ------------------------------------------------------------------------------------------
+ * The whole recurrent token step as ONE persistent cooperative kernel (csrc/rollout_step.cu).
+ * Replaces the reference's host-driven generation loop (testing-no-type-cp.py:157-167: forward_hidden(is_training=False)
+ * -> forward_output -> six numpy samplers, one token of one song per trip) for `batch` songs at once:
+ *   embedding gather + in_linear + positional encoding -> n_layers x [QKV projection, recurrent linear-attention state
+ *   update (S += phi(k) v^T, z += phi(k), out = phi(q) S / (phi(q).z + eps)), out-projection + residual, LayerNorm + linear1
+ *   + GELU, linear2 + residual] -> LayerNorm, final LayerNorm, 6/7 output heads -> temperature / nucleus sampling with the
+ *   Philox stream of (seed, seq_base + row, step, attribute) -> history + step counter,
+ * `n_steps` tokens per launch.  One CTA per SM; the phases are separated by a device-wide barrier; every CTA streams the
+ * weight tiles of ITS output tiles through a TMA ring that runs ahead of the barriers (weights do not depend on the chain),
+ * the Linear layers run as tcgen05 tiles with the weight rows on the UMMA M axis and 16 / 32 songs on the N axis, LayerNorm
+ * is applied while the activation tile is staged.  bf16 activations and weights, fp32 accumulation / statistics / state.
+ * All pointers are device pointers that must stay valid (and at the same address) until cpm_rollout_destroy; weights are
+ * read on every run, so in-place updates of the packed copies are picked up.
+ * The only allocation is the small host-side handle; the device-side plan lives in the caller's `plan_dev` buffer.
+ * cpm_rollout_create validates the configuration (CPM_ERR_UNSUPPORTED for shapes outside d_head = 64, d_model <= 512,
+ * d_model % 64 == 0, d_ff % 64 == 0, segments <= 256 wide) and builds the tensor maps and the device-side phase table. */
+#define CPM_ROLLOUT_MAX_LAYERS 32
+typedef struct CpmRolloutLayer {
+    const void *w_qkv; const float *b_qkv;          /* (3 d_model, d_model) bf16 ; (3 d_model) fp32 : [q; k; v] rows */
+    const void *w_out; const float *b_out;          /* (d_model, d_model) */
+    const float *ln1_g, *ln1_b;                     /* norm1 */
+    const void *w_ff1; const float *b_ff1;          /* (d_ff, d_model) */
+    const void *w_ff2; const float *b_ff2;          /* (d_model, d_ff) */
+    const float *ln2_g, *ln2_b;                     /* norm2 */
+    float *S, *Z;                                   /* recurrent state (batch, H, 64, 64), (batch, H, 64) fp32, updated in place */
+} CpmRolloutLayer;
+typedef struct CpmRolloutConfig {
+    int batch, d_model, n_heads, d_ff, n_layers, n_attr;
+    int n_tokens[CPM_MAX_ATTR], emb[CPM_MAX_ATTR];  /* vocabulary and embedding width per attribute */
+    const float *tables[CPM_MAX_ATTR];              /* embedding tables (n_tokens[a], emb[a]) fp32 */
+    const void *w_in; const float *b_in;            /* in_linear (d_model, sum emb) bf16 ; fp32 bias */
+    const float *pe; int pe_len;                    /* positional encoding (pe_len, d_model) fp32 */
+    int true_positions;                             /* 1: position = step counter; 0: position 0 every step (reference quirk) */
+    CpmRolloutLayer layer[CPM_ROLLOUT_MAX_LAYERS];
+    const float *lnf_g, *lnf_b;                     /* the encoder's final LayerNorm */
+    const void *w_heads; const float *b_heads;      /* concatenated heads (logits_ld rows, d_model) bf16 (rows beyond seg[n_attr] zero) */
+    int seg[CPM_MAX_ATTR + 1]; int logits_ld;       /* column offsets of the attributes in the concatenated logits; row stride */
+    float temperature[CPM_MAX_ATTR], top_p[CPM_MAX_ATTR];
+    int greedy;                                     /* 1: argmax; 0: sample */
+    float ln_eps, attn_eps;
+    uint64_t seed; int64_t seq_base;
+    int64_t *cur;                                   /* (batch, n_attr) current token per song: input of the step, overwritten by the sample */
+    float *logp;                                    /* (batch, n_attr) log-prob (T = 1 policy) of the sampled sub-tokens */
+    int64_t *hist_tok; float *hist_logp;            /* (max_steps, batch, n_attr) histories, written at row *step_dev */
+    int32_t *step_dev; int32_t max_steps;           /* device step counter, advanced by one per token */
+    /* scratch owned by the caller, bf16: x (batch, d_model) x3, qkv (batch, 3 d_model), attn (batch, d_model),
+     * g (batch, d_ff), logits (batch, logits_ld) */
+    void *x0, *x1, *y, *qkv, *attn, *g, *logits;
+    unsigned long long *barrier;                    /* 1 counter, zero-initialised once by the caller */
+    int *err_flag;                                  /* set to 1 on an out-of-range token id (optional) */
+} CpmRolloutConfig;
+int64_t cpm_rollout_plan_bytes(void);              /* size of the device-side plan buffer the caller provides (256-byte aligned) */
+int cpm_rollout_create(const CpmRolloutConfig *cfg_host, void *plan_dev, void **handle_out);
+int cpm_rollout_run(void *handle, int n_steps, void *stream);
+int cpm_rollout_phases(void *handle);               /* device-wide phases per token (diagnostics) */
+/* Development aid: device buffer of (SMs x 4 steps x phases x 8) uint64 that receives %globaltimer stamps of every CTA
+ * ("stage work done", "barrier passed", "activation tile staged", "accumulator ready") for the first 4 steps of each run;
+ * NULL switches it off (the default). */
+int cpm_debug_rollout_timing(void *device_buffer);
+int cpm_rollout_destroy(void *handle);
+
 #ifdef __cplusplus
 }
 #endif

@@ -82,7 +82,36 @@ SIGNATURES = {
     "cpm_dqn_td_fwd_bwd": (c_int, [_P, _P, _P, _P, _P, _P, _P, _P, c_int, c_int, c_int64, _IP, c_int, c_int,
                                    c_float, c_float, c_int, c_int, _P]),
     "cpm_rollout_advance": (c_int, [_P, _P, c_int64, _P, _P, c_int64, _P, c_int32, _P]),
+    "cpm_rollout_plan_bytes": (c_int64, []),
+    "cpm_rollout_create": (c_int, [_P, _P, POINTER(c_void_p)]),
+    "cpm_rollout_run": (c_int, [_P, c_int, _P]),
+    "cpm_rollout_phases": (c_int, [_P]),
+    "cpm_debug_rollout_timing": (c_int, [_P]),
+    "cpm_rollout_destroy": (c_int, [_P]),
 }
+
+ROLLOUT_MAX_LAYERS = 32
+
+
+class RolloutLayer(ctypes.Structure):
+    """CpmRolloutLayer (include/cpmusic.h)."""
+    _fields_ = [(n, c_void_p) for n in ("w_qkv", "b_qkv", "w_out", "b_out", "ln1_g", "ln1_b", "w_ff1", "b_ff1", "w_ff2", "b_ff2",
+                                        "ln2_g", "ln2_b", "S", "Z")]
+
+
+class RolloutConfig(ctypes.Structure):
+    """CpmRolloutConfig (include/cpmusic.h), field for field."""
+    _fields_ = [("batch", c_int), ("d_model", c_int), ("n_heads", c_int), ("d_ff", c_int), ("n_layers", c_int), ("n_attr", c_int),
+                ("n_tokens", c_int * MAX_ATTR), ("emb", c_int * MAX_ATTR), ("tables", c_void_p * MAX_ATTR),
+                ("w_in", c_void_p), ("b_in", c_void_p), ("pe", c_void_p), ("pe_len", c_int), ("true_positions", c_int),
+                ("layer", RolloutLayer * ROLLOUT_MAX_LAYERS), ("lnf_g", c_void_p), ("lnf_b", c_void_p),
+                ("w_heads", c_void_p), ("b_heads", c_void_p), ("seg", c_int * (MAX_ATTR + 1)), ("logits_ld", c_int),
+                ("temperature", c_float * MAX_ATTR), ("top_p", c_float * MAX_ATTR), ("greedy", c_int),
+                ("ln_eps", c_float), ("attn_eps", c_float), ("seed", c_uint64), ("seq_base", c_int64),
+                ("cur", c_void_p), ("logp", c_void_p), ("hist_tok", c_void_p), ("hist_logp", c_void_p),
+                ("step_dev", c_void_p), ("max_steps", c_int32),
+                ("x0", c_void_p), ("x1", c_void_p), ("y", c_void_p), ("qkv", c_void_p), ("attn", c_void_p), ("g", c_void_p),
+                ("logits", c_void_p), ("barrier", c_void_p), ("err_flag", c_void_p)]
 
 _lib = None
 
@@ -91,7 +120,9 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_rowdot_partials_rows": 0, "cpm_gemm_set_mode": 0, "cpm_set_chain_pdl": 0, 
+    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_rowdot_partials_rows": 0, "cpm_gemm_set_mode": 0, "cpm_set_chain_pdl": 0,
+    "cpm_rollout_plan_bytes": 0, "cpm_debug_rollout_timing": 0, "cpm_rollout_create": 0, "cpm_rollout_phases": 0, "cpm_rollout_destroy": 0,
+
     "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2, "cpm_colsum": 2, "cpm_rowdot_bwd": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
                                                                                 # kernel (ops adds 1 when the scan path runs); bwd = pre-pass, scan, main
 })
@@ -143,6 +174,7 @@ def load() -> ctypes.CDLL:
             raise RuntimeError(
                 f"{LIB_PATH} not found: build it with `python __graft_entry__.py` (or "
                 f"`python {os.path.join(_HERE, 'build.py')}`); this package has no CPU fallback.")
+        import torch  # noqa: F401  (its libcudart.so.12 is the runtime the library binds to; the toolkit's copy otherwise)
         _lib = _Counted(ctypes.CDLL(LIB_PATH))
     return _lib
 

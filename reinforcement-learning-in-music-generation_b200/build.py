@@ -52,8 +52,9 @@ def build(force: bool = False, verbose: bool = False) -> str:
                 if verbose and log:
                     print(log)
     if jobs or force or not _newer(OUT, objs):
-        cmd = [NVCC, "-shared", "-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-o", OUT] + objs
+        # the CUDA runtime is linked dynamically (libcudart.so.12: the copy torch has already loaded, else the toolkit's)
+        cmd = [NVCC, "-shared", "-cudart", "shared", "-ccbin", "/usr/bin/g++", "-gencode", "arch=compute_100a,code=sm_100a",
+               "-Xlinker", "-rpath=/usr/local/cuda/lib64", "-o", OUT] + objs
         r = subprocess.run(cmd, capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"link failed:\n{r.stdout}\n{r.stderr}")

@@ -3,6 +3,7 @@
 // (fwd/bwd).  One warp owns one (row, attribute) segment (decode, generic layouts) or one whole row of concatenated
 // logits (log-prob / cross-entropy when the row is <= 1024 wide and 16-byte aligned); segments are <= 1024 wide.
 #include "cpm_common.cuh"
+#include "heads_dev.cuh"
 
 namespace cpm {
 namespace {
@@ -10,37 +11,11 @@ namespace {
 constexpr int MAX_SEG = 1024;
 constexpr int WARPS = 4;
 
-struct SegParams {
-    int seg[CPM_MAX_ATTR + 1];
-    float temperature[CPM_MAX_ATTR];
-    float top_p[CPM_MAX_ATTR];
-    int n_attr;
-};
-
-struct ArgMax { float v; int i; };
-__device__ __forceinline__ ArgMax warp_argmax(ArgMax a) {
-#pragma unroll
-    for (int o = 16; o > 0; o >>= 1) {
-        float ov = __shfl_xor_sync(0xffffffffu, a.v, o);
-        int oi = __shfl_xor_sync(0xffffffffu, a.i, o);
-        if (ov > a.v || (ov == a.v && oi < a.i)) { a.v = ov; a.i = oi; }
-    }
-    return a;
-}
-
 // loads the segment into buf (fp32), returns first-index argmax and logsumexp (T=1)
 template <typename T>
 __device__ __forceinline__ void load_segment(const T *__restrict__ row, int w, float *buf, int lane, ArgMax &am, float &lse) {
-    ArgMax a{-INFINITY, 0x7fffffff};
-    for (int i = lane; i < w; i += 32) {
-        float x = to_f(row[i]);
-        buf[i] = x;
-        if (x > a.v) { a.v = x; a.i = i; }
-    }
-    am = warp_argmax(a);
-    float s = 0.f;
-    for (int i = lane; i < w; i += 32) s += __expf(buf[i] - am.v);
-    lse = am.v + __logf(warp_sum(s));
+    for (int i = lane; i < w; i += 32) buf[i] = to_f(row[i]);
+    segment_stats(buf, w, lane, am, lse);          // each lane reads back only what it wrote
 }
 
 // ---------------------------------------------------------------- C3 decode
@@ -66,50 +41,8 @@ __global__ void __launch_bounds__(WARPS * 32) heads_sample_kernel(const T *__res
         load_segment(logits + r * ld + sp.seg[a], w, buf, lane, am, lse);
         __syncwarp();
         int tok = am.i;
-        if (mode == 1) {
-            const float invt = 1.f / sp.temperature[a];
-            float s = 0.f;
-            for (int i = lane; i < w; i += 32) { float e = __expf((buf[i] - am.v) * invt); pr[i] = e; s += e; }
-            s = warp_sum(s);
-            const float top_p = sp.top_p[a];
-            const bool use_nucleus = top_p > 0.f && top_p < 1.f;
-            // reference: softmax, then nucleus divides by (sum + 1e-5); weighted_sampling by sum.
-            const float norm = use_nucleus ? 1.f / (s * (1.f + 1e-5f)) : 1.f / s;
-            __syncwarp();
-            for (int i = lane; i < w; i += 32) pr[i] *= norm;
-            __syncwarp();
-            // exclusive mass of everything ranked before element i in descending order
-            float zkeep = 0.f;
-            float ex[MAX_SEG / 32];
-#pragma unroll 1
-            for (int c = 0; c * 32 + lane < w; ++c) {
-                const int i = c * 32 + lane;
-                const float pi = pr[i];
-                float e = 0.f;
-                for (int j = 0; j < w; ++j) {
-                    const float pj = pr[j];
-                    e += (pj > pi || (pj == pi && j < i)) ? pj : 0.f;
-                }
-                const bool keep = !(use_nucleus && e > top_p);
-                ex[c] = keep ? e : -1.f;
-                zkeep += keep ? pi : 0.f;
-            }
-            zkeep = warp_sum(zkeep);
-            // Philox uniform for (sequence, step, attribute)
-            const uint64_t sid = (uint64_t)(seq_base + r);
-            uint4 rnd = Philox::block(make_uint4((uint32_t)sid, (uint32_t)cur_step, (uint32_t)a, (uint32_t)(sid >> 32)),
-                                      make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
-            const float u = (float)(rnd.x >> 8) * (1.0f / 16777216.0f);
-            const float target = u * zkeep;
-            ArgMax best{-1.f, 0x7fffffff};     // largest exclusive mass <= target among kept
-#pragma unroll 1
-            for (int c = 0; c * 32 + lane < w; ++c) {
-                const float e = ex[c];
-                if (e >= 0.f && e <= target && e > best.v) { best.v = e; best.i = c * 32 + lane; }
-            }
-            best = warp_argmax(best);
-            tok = best.i == 0x7fffffff ? am.i : best.i;
-        }
+        if (mode == 1)
+            tok = sample_segment<MAX_SEG / 32>(buf, pr, w, lane, am, sp.temperature[a], sp.top_p[a], seed, (uint64_t)(seq_base + r), cur_step, a);
         if (lane == 0) {
             tokens[it] = tok;
             if (logp) logp[it] = buf[tok] - lse;

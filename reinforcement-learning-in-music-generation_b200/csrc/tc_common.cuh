@@ -113,6 +113,22 @@ __device__ __forceinline__ void mma_ss(uint32_t tmem_d, uint64_t adesc, uint64_t
         "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The four K = 16 slices of one 64-wide SWIZZLE_128B k-block (descriptor start address + 2 per slice), accumulating; only the
+// first slice may start a fresh accumulator.  One asm block: a single issuing thread otherwise spends ~100 cycles per UMMA on
+// descriptor arithmetic and predicate set-up, twice the 46-cycle floor of a small-N UMMA (tools/probes/umma_small_n.cu).
+__device__ __forceinline__ void mma_ss_kblock(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate_first) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t.reg .b64 a1, a2, a3, b1, b2, b3;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "add.s64 a1, %1, 2;\n\tadd.s64 a2, %1, 4;\n\tadd.s64 a3, %1, 6;\n\t"
+        "add.s64 b1, %2, 2;\n\tadd.s64 b2, %2, 4;\n\tadd.s64 b3, %2, 6;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a1, b1, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a2, b2, %3, 1;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], a3, b3, %3, 1;\n\t}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate_first)
+        : "memory");
+}
 // arrive on an mbarrier when all previously issued MMAs of this thread complete
 __device__ __forceinline__ void mma_commit(uint64_t *bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar)) : "memory");

@@ -81,14 +81,14 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
     } else if (warp == 5) {
         if (lane == 0) {                                 // ---- UMMA issuer
+            const uint64_t dA0 = smem_desc_sw128(smem_u32(sm)), dW0 = smem_desc_sw128(smem_u32(sm + SG_A_BYTES));
+            int s = 0, ph = 0;
             for (int i = 0; i < KB; ++i) {
-                const int s = i % SG_NS;
-                mbar_wait(bar_full + s, (i / SG_NS) & 1);
+                mbar_wait(bar_full + s, ph);
                 tc_fence_after();
-                const uint64_t dA = smem_desc_sw128(smem_u32(sm + s * SG_STAGE)), dW = smem_desc_sw128(smem_u32(sm + s * SG_STAGE + SG_A_BYTES));
-#pragma unroll
-                for (int k = 0; k < 4; ++k) mma_ss(tmem, dA + 2 * k, dW + 2 * k, IDESC_SG, (i > 0 || k > 0) ? 1u : 0u);
+                mma_ss_kblock(tmem, dA0 + (uint64_t)(s * (SG_STAGE >> 4)), dW0 + (uint64_t)(s * (SG_STAGE >> 4)), IDESC_SG, i > 0 ? 1u : 0u);
                 mma_commit(bar_empty + s);
+                if (++s == SG_NS) { s = 0; ph ^= 1; }
             }
             mma_commit(bar_done);
         }

@@ -265,12 +265,7 @@ class TransformerEncoder(nn.Module):
         N = qkv.shape[0]
         E = self.d_head
         q, k, v = (qkv[:, j * H * E:(j + 1) * H * E].unflatten(-1, (H, E)) for j in range(3))
-        if len(st) > 2 and callable(st[2]):      # rollout engine hook: (q, k, v, S, Z) -> attention output
-            a = st[2](q, k, v, st[0], st[1]).view(N, H * E)
-        elif len(st) > 2:        # rollout engine: [S, Z, ring, step_dev] -> deferred state write-back
-            a = ops.linattn_step_lazy(q, k, v, st[0], st[1], st[2], st[3]).view(N, H * E)
-        else:
-            a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * E)
+        a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * E)
         o = cached_linear(c, ("out", i), [at.out_projection], a, dt)
         x = ops.ln_residual(x, o, layer.norm1.weight, layer.norm1.bias, layer.norm1.eps, p)
         if p == 0.0 and ops.use_own_gemm(x) and x.shape[0] < ops.SMALL_GEMM_ROWS and not torch.is_grad_enabled():

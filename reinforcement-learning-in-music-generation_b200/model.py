@@ -150,6 +150,7 @@ class CPLinearTransformer(nn.Module):
         if x.dtype != torch.int64:
             x = x.long()
         e = ops.cp_embed(x, self._tables(), self.compute_dtype)
+        ops.IndexGuard.poll(x.device)       # out-of-range ids raise IndexError (one call late, without stalling the stream)
         z = cached_linear(self._cache, "in", [self.in_linear], e, self.compute_dtype)
         p = self.pos_emb.dropout.p if self.training else 0.0
         return ops.add_pe(z, self.pos_emb.pe, x.shape[-2] if x.dim() >= 2 else 1, pos_offset, pos_dev, p)

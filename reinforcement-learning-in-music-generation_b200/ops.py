@@ -601,6 +601,55 @@ def packed_linear(x, wc, bc, rows, masters):
 
 
 # --------------------------------------------------------------------------- embedding
+class IndexGuard:
+    """Out-of-range token ids.  nn.Embedding raises IndexError on them (the reference: agent_pretrain.py:185-196); the gather
+    kernel instead writes a zero row and sets a sticky per-device flag.  The flag is read back WITHOUT stalling the stream: each
+    ``poll()`` queues an asynchronous copy into pinned memory and raises for any earlier copy that has landed with the flag set,
+    so a corrupted dataset or a vocabulary mismatch surfaces one step late instead of never.  ``check()`` is the blocking form
+    for natural sync points (end of a rollout, end of an epoch, tests)."""
+    _flags = {}
+    _pending = {}
+
+    @classmethod
+    def flag(cls, device) -> torch.Tensor:
+        device = torch.device(device)
+        key = (device.type, device.index if device.index is not None else torch.cuda.current_device())
+        f = cls._flags.get(key)
+        if f is None:
+            f = cls._flags[key] = torch.zeros(1, dtype=torch.int32, device=device)
+        return f
+
+    @classmethod
+    def _raise(cls, f):
+        f.zero_()
+        raise IndexError("index out of range in self: a CP token id lies outside its attribute's vocabulary (cpm_embed_fwd)")
+
+    @classmethod
+    def poll(cls, device) -> None:
+        if os.environ.get("CPM_CHECK_INDICES", "1") == "0" or torch.cuda.is_current_stream_capturing():
+            return
+        f = cls.flag(device)
+        prev = cls._pending.get(id(f))
+        if prev is not None and prev[1].query():
+            host, _ = cls._pending.pop(id(f))
+            if int(host[0]) != 0:
+                cls._raise(f)
+            prev = None
+        if prev is None:
+            host = torch.empty(1, dtype=torch.int32, pin_memory=True)
+            host.copy_(f, non_blocking=True)
+            ev = torch.cuda.Event()
+            ev.record()
+            cls._pending[id(f)] = (host, ev)
+
+    @classmethod
+    def check(cls, device) -> None:
+        f = cls.flag(device)
+        cls._pending.pop(id(f), None)
+        if int(f.item()) != 0:
+            cls._raise(f)
+
+
 def _embed_meta(tables):
     n_tok = [int(t.shape[0]) for t in tables]
     emb = [int(t.shape[1]) for t in tables]
@@ -621,7 +670,7 @@ def embed_fwd_raw(idx, tables, dtype):
     n_tok, emb = _embed_meta(tables)
     T = idx.numel() // n_attr
     out = torch.empty(*idx.shape[:-1], sum(emb), dtype=dtype, device=idx.device)
-    err = torch.zeros(1, dtype=torch.int32, device=idx.device)
+    err = IndexGuard.flag(idx.device)
     check(_lib.load().cpm_embed_fwd(_p(idx), _lib.ptr_array([t.data_ptr() for t in tables]), _lib.int_array(n_tok),
                                     _lib.int_array(emb), n_attr, T, _p(out), _dt(out), _p(err), _st()))
     return out, err

@@ -4,30 +4,39 @@ Replaces the reference's batch-1 host-driven loop (testing-no-type-cp.py:126-179
 ``.cpu()`` syncs, numpy sampling, one H2D copy) with: per-sequence recurrent state resident in HBM,
 sampling on the device (Philox stream keyed by (seed, sequence id, step, attribute) so results do
 not depend on how sequences are sharded over GPUs), a device-side step counter, and the whole
-one-token step (embedding -> 12 layers -> heads -> sample -> bookkeeping) captured once in a CUDA graph
-and replayed with no host synchronisation.  Every kernel of the step is one of this library's own
-(small-M tcgen05 GEMMs with the GELU in linear1's epilogue, the recurrent state kernel, fused
-residual + LayerNorm, embedding gather, sampler) and is launched with programmatic dependent launch,
-so each kernel's set-up - and each GEMM's weight fetch - overlaps its predecessor's tail.
+one-token step (embedding -> 12 layers -> heads -> sample -> bookkeeping) run with no host synchronisation.
 
-(Round 1 also carried a cooperative megakernel, skinny-GEMM, LayerNorm-fold, deferred / split state
-write-back, L2-prefetch and grouped-graph variants of the step; all measured slower than this one and
-were removed - the write-ups are profiles/r01_summary.md sections F, K, M.)
+Two executions of the step, same arithmetic:
+  * ``mode="chain"`` (default): the step as 91 kernels of this library (small-M tcgen05 GEMMs with the GELU in linear1's
+    epilogue, the recurrent state kernel, fused residual + LayerNorm, embedding gather, sampler) launched with programmatic
+    dependent launch - each kernel's set-up and each GEMM's weight fetch overlap its predecessor's tail - and captured once in
+    a CUDA graph.  511 us per token step at 256 songs on B200.
+  * ``mode="persistent"`` (opt-in, bf16 models with 64-wide heads; also CPM_ROLLOUT_MODE=persistent): ONE cooperative kernel
+    for the whole rollout (csrc/rollout_step.cu, cpm_rollout_run): one CTA per SM, the 63 dependent stages of a token separated
+    by a device-wide barrier, every CTA streaming the weight tiles of its own output tiles ahead of the barriers through a TMA
+    ring, tcgen05 tiles with the weight rows on the UMMA M axis, LayerNorm applied while the activation tile is staged.
+    735 us per token step: measured slower, kept as the one non-default mode with its per-stage timeline (see its header).
+
+(Round 1 also carried a first cooperative megakernel, skinny-GEMM, LayerNorm-fold, deferred / split state write-back,
+L2-prefetch and grouped-graph variants of the step; all measured slower than the chain and were removed - the write-ups
+are profiles/r01_summary.md sections F, K, M.)
 """
 from __future__ import annotations
 
+import ctypes
 import os
 from typing import Optional
 
 import torch
 
 from . import _lib, ops
+from ._lib import check
 
 
 class RolloutEngine:
     def __init__(self, model, batch: int, max_steps: int, greedy: bool = False, true_positions: bool = True,
                  temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True,
-                 chain_pdl: Optional[bool] = None):
+                 chain_pdl: Optional[bool] = None, mode: Optional[str] = None):
         self.model, self.N, self.max_steps = model, batch, max_steps
         self.greedy, self.true_positions = greedy, true_positions
         self.temperature, self.top_p = model.sampling_config(temperature, top_p)
@@ -51,6 +60,102 @@ class RolloutEngine:
         # programmatic dependent launch needs every kernel of the step to be a chain kernel (csrc/cpm_common.cuh): true when
         # the Linear layers run on the own GEMMs (bf16); library GEMMs in between would simply not overlap
         self.chain_pdl = bool(chain_pdl) and model.compute_dtype == torch.bfloat16 and ops.GEMM_IMPL == "own"
+        mode = mode or os.environ.get("CPM_ROLLOUT_MODE", "chain")
+        if mode not in ("persistent", "chain"):
+            raise ValueError("mode must be 'persistent' or 'chain'")
+        if mode == "persistent" and (model.compute_dtype != torch.bfloat16 or not use_graph):
+            mode = "chain"                    # fp32 parity mode / eager debugging: the kernel chain
+        self.mode = mode
+        self._plan = None                     # (handle, plan buffer, scratch, seed) of the persistent kernel
+
+    # ------------------------------------------------------------------ persistent kernel (csrc/rollout_step.cu)
+    def _build_plan(self):
+        m, enc, dev = self.model, self.model.transformer_encoder, self.cur.device
+        lib = _lib.load()
+        dt = torch.bfloat16
+        B, d, A = self.N, m.d_model, len(m.attrs)
+        cfg = _lib.RolloutConfig()
+        keep = []                             # tensors the plan points at
+
+        def ptr(t):
+            keep.append(t)
+            return t.data_ptr()
+
+        cfg.batch, cfg.d_model, cfg.n_heads, cfg.d_ff = B, d, enc.n_heads, enc.layers[0].linear1.out_features
+        cfg.n_layers, cfg.n_attr = len(enc.layers), A
+        for a, t in enumerate(m._tables()):
+            cfg.n_tokens[a], cfg.emb[a], cfg.tables[a] = t.shape[0], t.shape[1], ptr(t)
+        wc, _bc, _rows, _ms, _wt, b32 = m._cache.get("in", [m.in_linear], dt)
+        cfg.w_in, cfg.b_in = ptr(wc), ptr(b32)
+        pe = m.pos_emb.pe[0]
+        cfg.pe, cfg.pe_len, cfg.true_positions = ptr(pe), pe.shape[0], int(self.true_positions)
+        for i, layer in enumerate(enc.layers):
+            at, L = layer.attention, cfg.layer[i]
+            for key, lins, wn, bn in ((("qkv", i), [at.query_projection, at.key_projection, at.value_projection], "w_qkv", "b_qkv"),
+                                      (("out", i), [at.out_projection], "w_out", "b_out"),
+                                      (("ff1", i), [layer.linear1], "w_ff1", "b_ff1"), (("ff2", i), [layer.linear2], "w_ff2", "b_ff2")):
+                wc, _bc, _rows, _ms, _wt, b32 = enc._cache.get(key, lins, dt)
+                setattr(L, wn, ptr(wc))
+                setattr(L, bn, ptr(b32))
+            L.ln1_g, L.ln1_b, L.ln2_g, L.ln2_b = ptr(layer.norm1.weight), ptr(layer.norm1.bias), ptr(layer.norm2.weight), ptr(layer.norm2.bias)
+            L.S, L.Z = self.S[i].data_ptr(), self.Z[i].data_ptr()
+        cfg.lnf_g, cfg.lnf_b = ptr(enc.norm.weight), ptr(enc.norm.bias)
+        wc, _bc, _rows, _ms, _wt, b32 = m._cache.get("heads", m._heads(), dt, 8)
+        cfg.w_heads, cfg.b_heads = ptr(wc), ptr(b32)
+        for a, s0 in enumerate(m.seg):
+            cfg.seg[a] = s0
+        cfg.logits_ld = m.logits_width
+        for a in range(A):
+            cfg.temperature[a] = float(self.temperature[a])
+            cfg.top_p[a] = float(self.top_p[a]) if self.top_p[a] is not None else 0.0
+        cfg.greedy = int(self.greedy)
+        cfg.ln_eps, cfg.attn_eps = enc.norm.eps, ops.EPS_ATTN
+        cfg.seed, cfg.seq_base = self.seed, self.seq_base
+        cfg.cur, cfg.logp = self.cur.data_ptr(), self.logp.data_ptr()
+        cfg.hist_tok, cfg.hist_logp = self.hist_tok.data_ptr(), self.hist_logp.data_ptr()
+        cfg.step_dev, cfg.max_steps = self.step_dev.data_ptr(), self.max_steps
+        scratch = {n: torch.zeros(B, w, dtype=dt, device=dev) for n, w in
+                   (("x0", d), ("x1", d), ("y", d), ("qkv", 3 * d), ("attn", d), ("g", cfg.d_ff), ("logits", m.logits_width))}
+        for n, t in scratch.items():
+            setattr(cfg, n, t.data_ptr())
+        barrier = torch.zeros(1, dtype=torch.int64, device=dev)
+        cfg.barrier, cfg.err_flag = barrier.data_ptr(), ops.IndexGuard.flag(dev).data_ptr()
+        plan = torch.zeros(int(lib.cpm_rollout_plan_bytes()) + 256, dtype=torch.uint8, device=dev)
+        plan_ptr = (plan.data_ptr() + 255) // 256 * 256
+        handle = ctypes.c_void_p()
+        check(lib.cpm_rollout_create(ctypes.byref(cfg), plan_ptr, ctypes.byref(handle)))
+        self._plan = {"handle": handle, "plan": plan, "scratch": scratch, "barrier": barrier, "keep": keep, "seed": self.seed,
+                      "stamp": tuple(t.data_ptr() for t in keep), "phases": int(lib.cpm_rollout_phases(handle))}
+
+    def _drop_plan(self):
+        if self._plan is not None:
+            _lib.load().cpm_rollout_destroy(self._plan["handle"])
+            self._plan = None
+
+    def __del__(self):
+        try:
+            self._drop_plan()
+        except Exception:
+            pass
+
+    def _run_persistent(self, n_steps):
+        m = self.model
+        m.refresh_packs()                    # in place: the plan reads the packed weights by address
+        if self._plan is not None and (self._plan["seed"] != self.seed
+                                       or self._plan["stamp"] != tuple(t.data_ptr() for t in self._plan["keep"])):
+            self._drop_plan()                # new seed, or a pack / parameter was re-allocated (model.to(), set_compute_dtype())
+        if self._plan is None:
+            try:
+                self._build_plan()
+            except _lib.CpmError as e:
+                if e.code != -7:             # CPM_ERR_UNSUPPORTED: shapes the persistent kernel does not take
+                    raise
+                self.mode = "chain"
+                return False
+        self._plan["barrier"].zero_()
+        check(_lib.load().cpm_rollout_run(self._plan["handle"], n_steps, ops._st()))
+        self.launches_per_step = self._plan["phases"]
+        return True
 
     def _logits(self):
         """Logits of the next token for every sequence, given self.cur and the recurrent state."""
@@ -107,6 +212,11 @@ class RolloutEngine:
             raise ValueError(f"n_steps {n_steps} > max_steps {self.max_steps}")
         if seed is not None and seed != self.seed:
             self.seed, self.graph = seed, None
+        if self.mode == "persistent":
+            self.reset(init_tokens)
+            if self._run_persistent(n_steps):
+                toks = torch.cat([init_tokens.to(self.cur.device, torch.int64)[None], self.hist_tok[:n_steps]], 0)
+                return {"tokens": toks.permute(1, 0, 2).contiguous(), "logp": self.hist_logp[:n_steps].permute(1, 0, 2).contiguous()}
         was_training = self.model.training
         self.model.eval()
         if self.use_graph and self.graph is None:

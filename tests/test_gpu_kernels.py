@@ -750,3 +750,27 @@ def test_linattn_bf16_ragged_lengths_run_padded_on_tensor_cores(cuda, cpm, shape
         ref.backward(go)
         _cmp(out, ref.float(), 3e-2, 2e-2, "out vs simt")
         _cmp(qkv.grad, ref_in.grad.float(), 4e-2, 3e-2, "gqkv vs simt")
+
+
+def test_out_of_range_token_ids_raise_index_error(cuda, cpm):
+    """nn.Embedding raises IndexError on an id outside the vocabulary (agent_pretrain.py:185-196); the gather kernel flags it
+    and the host raises at the next poll / check instead of training silently on zero rows."""
+    m = cpm.TransformerModel([56, 135, 18, 87, 18, 25], d_model=128, n_layer=1, n_head=2, d_inner=256, dropout=0.0).to(cuda)
+    x = torch.zeros(2, 8, 6, dtype=torch.int64, device=cuda)
+    m.train_step(x, x, torch.ones(2, 8, device=cuda))
+    cpm.ops.IndexGuard.check(cuda)                       # clean input: nothing raised
+    x[1, 3, 1] = 135
+    m.train_step(x, x.clamp(max=17), torch.ones(2, 8, device=cuda))
+    with pytest.raises(IndexError):
+        cpm.ops.IndexGuard.check(cuda)
+    x[1, 3, 1] = 0
+    m.train_step(x, x, torch.ones(2, 8, device=cuda))
+    torch.cuda.synchronize()
+    with pytest.raises(IndexError):                      # the non-blocking poll reports a flag raised by an earlier call
+        x[0, 0, 0] = -1
+        m.train_step(x, x.clamp(min=0), torch.ones(2, 8, device=cuda))
+        torch.cuda.synchronize()
+        for _ in range(3):
+            cpm.ops.IndexGuard.poll(cuda)
+            torch.cuda.synchronize()
+    cpm.ops.IndexGuard.check(cuda)
