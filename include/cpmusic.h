@@ -214,6 +214,20 @@ int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *
  * Reference loop being served: testing-no-type-cp.py:157-167 (forward_hidden(..., is_training=False) + forward_output). */
 int cpm_gemm_nt_small(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int M, int N, int K,
                       const float *bias, int epilogue, void *stream);
+/* The token-step Linear with the LayerNorm around it folded in - no LayerNorm kernels in the rollout chain.  ft's recurrent
+ * encoder layer is  x = norm1(x + out_proj(attn));  y = linear2(gelu(linear1(x)));  x = norm2(x + y).
+ * Exactly one of two forms per call:
+ *  FOLD (fold_c1 != NULL): A holds RAW pre-norm rows y, W holds gamma o W (bf16), bias holds c2 = W beta + b, fold_c1 = row sums
+ *    of the bf16 gamma o W:   D = epilogue( rstd (A W^T - mean c1) + c2 ),  mean / rstd of each row of A computed in the kernel
+ *    from the activation tile it holds (K <= 512; one-pass fp32 sum and sum of squares, eps = ln_eps) and, if stats_out != NULL,
+ *    written there as (mean, rstd) float pairs (M x 2).  Epilogues CPM_GEMM_EPI_BIAS / CPM_GEMM_EPI_GELU as above.
+ *  RESIDUAL (R != NULL):   D = bf16(A W^T + bias) + res,  res = R (bf16, row stride ldr) when r_stats == NULL, else
+ *    res = bf16( (R - mean) rstd r_gamma + r_beta ) with (mean, rstd) = r_stats[row]: the LayerNorm output rebuilt from the
+ *    pre-norm rows its consumer normalised.  D is the next pre-norm row.
+ * Reference: the same loop as cpm_gemm_nt_small (testing-no-type-cp.py:157-167). */
+int cpm_gemm_nt_small_ln(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int M, int N, int K,
+                         const float *bias, int epilogue, const float *fold_c1, float *stats_out, float ln_eps, const void *R, int64_t ldr,
+                         const float *r_stats, const float *r_gamma, const float *r_beta, void *stream);
 /* 1: launch the token-step kernels (cpm_gemm_nt_small, cpm_linattn_step, cpm_ln_residual_fwd, cpm_embed_fwd, cpm_add_pe,
  * cpm_heads_sample, cpm_rollout_advance) with the programmatic-stream-serialization attribute, so each overlaps its set-up
  * with its predecessor's tail; they all block in griddepcontrol.wait before touching chain data.  0 (default): plain launches. */

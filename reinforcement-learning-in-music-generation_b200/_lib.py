@@ -55,6 +55,8 @@ SIGNATURES = {
     "cpm_gemm_set_mode": (c_int, [c_int]),
     "cpm_set_chain_pdl": (c_int, [c_int]),
     "cpm_gemm_nt_small": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, c_int, _P]),
+    "cpm_gemm_nt_small_ln": (c_int, [_P, c_int64, _P, c_int64, _P, c_int64, c_int, c_int, c_int, _P, c_int, _P, _P, c_float, _P, c_int64,
+                                     _P, _P, _P, _P]),
     "cpm_gemm_tn": (c_int, [_P, c_int64, _P, c_int64, _FPP, c_int, c_int, c_int64, c_int, c_int, c_int, _P]),
     "cpm_embed_fwd": (c_int, [_P, _FPP, _IP, _IP, c_int, c_int64, _P, c_int, _P, _P]),
     "cpm_embed_bwd": (c_int, [_P, _P, _FPP, _IP, _IP, c_int, c_int64, c_int, _P]),

@@ -16,6 +16,14 @@
 //  * epilogues: bias, or bias + exact-erf GELU on the bf16-rounded pre-activation (bit-identical to the GEMM + gelu kernel
 //    pair of the teacher-forced path).
 //
+//  * LayerNorm without LayerNorm kernels (cpm_gemm_nt_small_ln, the rollout chain): a Linear that consumes LayerNorm(y) runs on
+//    the RAW pre-norm rows y with gamma folded into the weights,
+//        LN(y) W^T + b  =  rstd (y (gamma o W)^T - mean c1) + c2,    c1_n = sum_k (gamma o W)_nk,  c2_n = sum_k beta_k W_nk + b_n,
+//    the row statistics coming from the activation tile the CTA holds in shared memory anyway (K <= 512: every k-block has its
+//    own ring stage), computed by the epilogue warps while the UMMAs run; a Linear whose output is added to the residual stream
+//    writes the pre-norm sum y' = (acc + b) + residual, the residual being either a plain tensor or LayerNorm(y_prev) rebuilt
+//    from y_prev and the statistics its consumer left in global memory.
+//
 // K is streamed in 64-wide blocks through an 8-deep ring (12 KB per stage); for K <= 512 every block has its own stage and the
 // producer never waits.  Warps 0-3: epilogue (M = 64 accumulator layout: warp w holds rows 16w..16w+15 in lanes 0..15),
 // warp 4: TMA producer, warp 5: UMMA issuer.
@@ -37,9 +45,17 @@ struct SmallArgs {
     __nv_bfloat16 *D;
     int64_t ldd;
     int M, N, K;
+    // ---- LayerNorm folding (cpm_gemm_nt_small_ln); all NULL / 0 for the plain entry point
+    const float *c1;                   // [N] fold: sum_k (gamma o W)_nk; `bias` then holds c2
+    float2 *stats_out;                 // [M] (mean, rstd) of the rows of A, written by the CTAs of the first column tile
+    float ln_eps;
+    const __nv_bfloat16 *R;            // [M x N] residual added to the output (row stride ldr) ...
+    int64_t ldr;
+    const float2 *r_stats;             // ... through LayerNorm(R) with these row statistics and r_gamma / r_beta when non-NULL
+    const float *r_gamma, *r_beta;
 };
 
-template <int EPI>
+template <int EPI, bool FOLD = false, bool RESID = false>
 __global__ void __launch_bounds__(SG_THREADS, 2)
 gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const SmallArgs a) {
     extern __shared__ __align__(1024) uint8_t sm[];
@@ -98,6 +114,50 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         float bv[32];
 #pragma unroll
         for (int j = 0; j < 32; ++j) bv[j] = (a.bias && n0 + j < a.N) ? __ldg(a.bias + n0 + j) : 0.f;       // weights: no dependency
+        float mean = 0.f, rstd = 1.f;
+        if (FOLD) {
+            // Row statistics of the raw activation tile, straight from the ring (K <= 512: block i sits in stage i): lanes l and
+            // l + 16 take the two 64-byte halves of row 16 w + (l & 15) in every k-block; one pass (sum, sum of squares, fp32).
+            const int r = 16 * warp + (lane & 15), half = lane >> 4;
+            float sx = 0.f, sxx = 0.f;
+            for (int i = 0; i < KB; ++i) {
+                mbar_wait(bar_full + i, 0);
+                const uint8_t *rp = sm + i * SG_STAGE + r * 128;
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    const uint4 q = *reinterpret_cast<const uint4 *>(rp + (((4 * half + c) ^ (r & 7)) << 4));
+                    const uint32_t w4[4] = {q.x, q.y, q.z, q.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const float x0 = __uint_as_float(w4[j] << 16), x1 = __uint_as_float(w4[j] & 0xFFFF0000u);
+                        sx += x0 + x1;
+                        sxx = fmaf(x0, x0, fmaf(x1, x1, sxx));
+                    }
+                }
+            }
+            sx += __shfl_xor_sync(0xffffffffu, sx, 16);
+            sxx += __shfl_xor_sync(0xffffffffu, sxx, 16);
+            mean = sx / (float)a.K;
+            rstd = rsqrtf(fmaxf(sxx / (float)a.K - mean * mean, 0.f) + a.ln_eps);
+            if (a.stats_out && blockIdx.x == 0 && lane < 16 && row < a.M) a.stats_out[row] = make_float2(mean, rstd);
+        }
+        float c1v[FOLD ? 32 : 1];
+        if (FOLD) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) c1v[j] = (n0 + j < a.N) ? __ldg(a.c1 + n0 + j) : 0.f;
+        }
+        // the residual tile is chain data: fetched behind this thread's own griddepcontrol.wait, while the UMMAs run
+        uint4 rraw[RESID ? 4 : 1];
+        float2 rs = make_float2(0.f, 1.f);
+        if (RESID) {
+            griddep_wait();
+            if (lane < 16 && row < a.M) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    rraw[q] = (n0 + 8 * q + 8 <= a.N) ? *reinterpret_cast<const uint4 *>(a.R + (int64_t)row * a.ldr + n0 + 8 * q) : make_uint4(0u, 0u, 0u, 0u);
+                if (a.r_stats) rs = a.r_stats[row];
+            }
+        }
         mbar_wait(bar_done, 0);                          // the UMMAs ran after the producer's griddepcontrol.wait: ordered behind the chain
         tc_fence_after();
         uint32_t r[32];
@@ -108,9 +168,31 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t w[4];
+                float res[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+                if (RESID && n0 + 8 * q + 8 <= a.N) {    // the residual stream: a plain tensor, or LayerNorm(R) rebuilt (bf16, like the LayerNorm kernel's output)
+                    const uint4 rq = rraw[q];
+                    const uint32_t w4[4] = {rq.x, rq.y, rq.z, rq.w};
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) { res[2 * j] = __uint_as_float(w4[j] << 16); res[2 * j + 1] = __uint_as_float(w4[j] & 0xFFFF0000u); }
+                    if (a.r_stats) {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j)
+                            res[j] = bf16_round((res[j] - rs.x) * rs.y * __ldg(a.r_gamma + n0 + 8 * q + j) + __ldg(a.r_beta + n0 + 8 * q + j));
+                    }
+                }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {
-                    float x0 = __uint_as_float(r[8 * q + 2 * j]) + bv[8 * q + 2 * j], x1 = __uint_as_float(r[8 * q + 2 * j + 1]) + bv[8 * q + 2 * j + 1];
+                    float x0 = __uint_as_float(r[8 * q + 2 * j]), x1 = __uint_as_float(r[8 * q + 2 * j + 1]);
+                    if (FOLD) {
+                        x0 = rstd * (x0 - mean * c1v[8 * q + 2 * j]);
+                        x1 = rstd * (x1 - mean * c1v[8 * q + 2 * j + 1]);
+                    }
+                    x0 += bv[8 * q + 2 * j];
+                    x1 += bv[8 * q + 2 * j + 1];
+                    if (RESID) {
+                        x0 = bf16_round(x0) + res[2 * j];
+                        x1 = bf16_round(x1) + res[2 * j + 1];
+                    }
                     if (EPI == CPM_GEMM_EPI_GELU) {      // GELU of the bf16-rounded pre-activation, like the GEMM + gelu kernel pair
                         x0 = gelu_f<false>(bf16_round(x0));
                         x1 = gelu_f<false>(bf16_round(x1));
@@ -126,16 +208,16 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 4) tmem_dealloc<32>(tmem);
 }
 
-template <int EPI>
+template <int EPI, bool FOLD = false, bool RESID = false>
 int launch_small(const CUtensorMap &tA, const CUtensorMap &tW, const SmallArgs &a, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
-        cudaError_t e = cudaFuncSetAttribute(gemm_small_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_small_kernel<EPI, FOLD, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM);
         if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_small shared-memory attribute: %s", cudaGetErrorString(e));
         attr = true;
     }
     const dim3 grid((a.N + SG_BN - 1) / SG_BN, (a.M + SG_BM - 1) / SG_BM);
-    cudaError_t e = launch_chain(gemm_small_kernel<EPI>, grid, dim3(SG_THREADS), SG_SMEM, st, tA, tW, a);
+    cudaError_t e = launch_chain(gemm_small_kernel<EPI, FOLD, RESID>, grid, dim3(SG_THREADS), SG_SMEM, st, tA, tW, a);
     if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_small launch: %s", cudaGetErrorString(e));
     return CPM_OK;
 }
@@ -156,9 +238,38 @@ extern "C" int cpm_gemm_nt_small(const void *A, int64_t lda, const void *W, int6
     int rc;
     if ((rc = make_tmap_bf16_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, SG_BM))) return rc;
     if ((rc = make_tmap_bf16_2d(&tW, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, SG_BN))) return rc;
-    SmallArgs a;
+    SmallArgs a = {};
     a.bias = bias; a.D = (__nv_bfloat16 *)D; a.ldd = ldd; a.M = M; a.N = N; a.K = K;
     cudaStream_t st = (cudaStream_t)stream;
     if (epilogue == CPM_GEMM_EPI_GELU) return launch_small<CPM_GEMM_EPI_GELU>(tA, tW, a, st);
     return launch_small<CPM_GEMM_EPI_BIAS>(tA, tW, a, st);
+}
+
+extern "C" int cpm_gemm_nt_small_ln(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int M, int N, int K,
+                                    const float *bias, int epilogue, const float *fold_c1, float *stats_out, float ln_eps, const void *R, int64_t ldr,
+                                    const float *r_stats, const float *r_gamma, const float *r_beta, void *stream) {
+    CPM_REQUIRE(A && W && D, CPM_ERR_NULL, "gemm_nt_small_ln: A/W/D must be non-NULL");
+    CPM_REQUIRE(M > 0 && N > 0 && K > 0 && K % 8 == 0 && N % 8 == 0, CPM_ERR_BAD_SHAPE, "gemm_nt_small_ln: M=%d N=%d K=%d (N, K multiples of 8)", M, N, K);
+    CPM_REQUIRE(lda >= K && ldw >= K && ldd >= N && lda % 8 == 0 && ldw % 8 == 0 && ldd % 8 == 0, CPM_ERR_BAD_SHAPE, "gemm_nt_small_ln: row strides");
+    CPM_REQUIRE(aligned16(A) && aligned16(W) && aligned16(D), CPM_ERR_BAD_ALIGN, "gemm_nt_small_ln: operands must be 16-byte aligned");
+    CPM_REQUIRE(epilogue == CPM_GEMM_EPI_BIAS || epilogue == CPM_GEMM_EPI_GELU, CPM_ERR_BAD_SHAPE, "gemm_nt_small_ln: epilogue %d", epilogue);
+    const bool fold = fold_c1 != nullptr, resid = R != nullptr;
+    CPM_REQUIRE(fold != resid, CPM_ERR_BAD_SHAPE, "gemm_nt_small_ln: exactly one of the LayerNorm fold (fold_c1) and the residual (R) must be given");
+    if (fold) CPM_REQUIRE(K <= 64 * SG_NS && bias, CPM_ERR_BAD_SHAPE, "gemm_nt_small_ln: the fold needs K <= %d and the folded bias c2", 64 * SG_NS);
+    if (resid) {
+        CPM_REQUIRE(epilogue == CPM_GEMM_EPI_BIAS && ldr >= N && ldr % 8 == 0 && aligned16(R), CPM_ERR_BAD_SHAPE, "gemm_nt_small_ln: residual layout");
+        CPM_REQUIRE(!r_stats || (r_gamma && r_beta), CPM_ERR_NULL, "gemm_nt_small_ln: r_stats needs r_gamma and r_beta");
+    }
+    CUtensorMap tA, tW;
+    int rc;
+    if ((rc = make_tmap_bf16_2d(&tA, A, (uint64_t)K, (uint64_t)M, (uint64_t)lda, SG_BM))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tW, W, (uint64_t)K, (uint64_t)N, (uint64_t)ldw, SG_BN))) return rc;
+    SmallArgs a = {};
+    a.bias = bias; a.D = (__nv_bfloat16 *)D; a.ldd = ldd; a.M = M; a.N = N; a.K = K;
+    a.c1 = fold_c1; a.stats_out = (float2 *)stats_out; a.ln_eps = ln_eps;
+    a.R = (const __nv_bfloat16 *)R; a.ldr = ldr; a.r_stats = (const float2 *)r_stats; a.r_gamma = r_gamma; a.r_beta = r_beta;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (resid) return launch_small<CPM_GEMM_EPI_BIAS, false, true>(tA, tW, a, st);
+    if (epilogue == CPM_GEMM_EPI_GELU) return launch_small<CPM_GEMM_EPI_GELU, true, false>(tA, tW, a, st);
+    return launch_small<CPM_GEMM_EPI_BIAS, true, false>(tA, tW, a, st);
 }

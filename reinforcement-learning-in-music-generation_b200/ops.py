@@ -399,6 +399,27 @@ def gemm_nt_small(a, w, bias=None, gelu=False, out=None):
     return d
 
 
+def gemm_nt_small_ln(a, w, bias, gelu=False, fold_c1=None, stats_out=None, ln_eps=EPS_LN, resid=None, r_stats=None, r_gamma=None,
+                     r_beta=None, out=None):
+    """cpm_gemm_nt_small_ln: the token-step Linear with the LayerNorm around it folded in.  FOLD form (``fold_c1``): ``a`` holds raw
+    pre-norm rows, ``w`` = gamma o W, ``bias`` = c2, the row statistics are computed in the kernel (and written to ``stats_out``
+    (M,2) fp32 if given).  RESIDUAL form (``resid``): out = bf16(a w^T + bias) + resid, resid optionally passed through the
+    LayerNorm described by (r_stats, r_gamma, r_beta)."""
+    _cuda(a, w, bias, fold_c1, stats_out, resid, r_stats, r_gamma, r_beta)
+    a, w = _gemm_operand(a, "a"), _gemm_operand(w, "w")
+    M, K = a.shape
+    N = w.shape[0]
+    if w.shape[1] != K:
+        raise ValueError(f"gemm_nt_small_ln: a (M,{K}) against w {tuple(w.shape)}")
+    d = out if out is not None else torch.empty(M, N, dtype=torch.bfloat16, device=a.device)
+    if resid is not None:
+        resid = _gemm_operand(resid, "resid")
+    check(_lib.load().cpm_gemm_nt_small_ln(_p(a), a.stride(0), _p(w), w.stride(0), _p(d), d.stride(0), M, N, K, _p(bias),
+                                           GEMM_GELU if gelu else GEMM_BIAS, _p(fold_c1), _p(stats_out), ln_eps, _p(resid),
+                                           0 if resid is None else resid.stride(0), _p(r_stats), _p(r_gamma), _p(r_beta), _st()))
+    return d
+
+
 def set_chain_pdl(on: bool) -> None:
     check(_lib.load().cpm_set_chain_pdl(1 if on else 0))
 
@@ -641,6 +662,12 @@ class IndexGuard:
             ev = torch.cuda.Event()
             ev.record()
             cls._pending[id(f)] = (host, ev)
+
+    @classmethod
+    def reset(cls, device) -> None:
+        f = cls.flag(device)
+        cls._pending.pop(id(f), None)
+        f.zero_()
 
     @classmethod
     def check(cls, device) -> None:

@@ -36,7 +36,7 @@ from ._lib import check
 class RolloutEngine:
     def __init__(self, model, batch: int, max_steps: int, greedy: bool = False, true_positions: bool = True,
                  temperature=None, top_p=None, seed: int = 0, seq_base: int = 0, use_graph: bool = True,
-                 chain_pdl: Optional[bool] = None, mode: Optional[str] = None):
+                 chain_pdl: Optional[bool] = None, mode: Optional[str] = None, fold_ln: Optional[bool] = None):
         self.model, self.N, self.max_steps = model, batch, max_steps
         self.greedy, self.true_positions = greedy, true_positions
         self.temperature, self.top_p = model.sampling_config(temperature, top_p)
@@ -67,6 +67,12 @@ class RolloutEngine:
             mode = "chain"                    # fp32 parity mode / eager debugging: the kernel chain
         self.mode = mode
         self._plan = None                     # (handle, plan buffer, scratch, seed) of the persistent kernel
+        # LayerNorm folded into the chain's Linear kernels (cpm_gemm_nt_small_ln): 25 LayerNorm launches per token become 1.
+        # Needs the own bf16 GEMMs, 64-wide-or-not heads alike, and d_model <= 512 (the statistics come from the K <= 512 tile).
+        fold = os.environ.get("CPM_ROLLOUT_FOLD", "1") == "1" if fold_ln is None else bool(fold_ln)
+        self.fold = (fold and model.compute_dtype == torch.bfloat16 and ops.GEMM_IMPL == "own" and model.d_model <= 512
+                     and model.d_model % 8 == 0 and batch < ops.SMALL_GEMM_ROWS)
+        self._folded = None
 
     # ------------------------------------------------------------------ persistent kernel (csrc/rollout_step.cu)
     def _build_plan(self):
@@ -157,8 +163,73 @@ class RolloutEngine:
         self.launches_per_step = self._plan["phases"]
         return True
 
+    # ------------------------------------------------------------------ LayerNorm folded into the chain's Linear kernels
+    def _fold_refresh(self):
+        """(gamma o W) bf16, c1 = row sums of it, c2 = W beta + b for every Linear that consumes a LayerNorm: linear1 (norm1),
+        the next layer's QKV projection (norm2) and the heads (the encoder's final norm).  Buffers are allocated once and
+        refilled in place (the captured graph reads them by address)."""
+        m, enc = self.model, self.model.transformer_encoder
+        with torch.no_grad():
+            if self._folded is None:
+                self._folded = {}
+            def fold(key, lins, norm, pad_to=1):
+                W = torch.cat([l.weight for l in lins], 0).float()
+                b = torch.cat([l.bias for l in lins], 0).float()
+                rows = -(-W.shape[0] // pad_to) * pad_to
+                ent = self._folded.get(key)
+                if ent is None:
+                    dev = W.device
+                    ent = self._folded[key] = (torch.zeros(rows, W.shape[1], dtype=torch.bfloat16, device=dev),
+                                               torch.zeros(rows, dtype=torch.float32, device=dev), torch.zeros(rows, dtype=torch.float32, device=dev))
+                wf, c1, c2 = ent
+                wf[:W.shape[0]].copy_(W * norm.weight.float()[None, :])
+                c1[:W.shape[0]].copy_(wf[:W.shape[0]].float().sum(1))
+                c2[:W.shape[0]].copy_((W * norm.bias.float()[None, :]).sum(1) + b)
+            for i, layer in enumerate(enc.layers):
+                at = layer.attention
+                fold(("ff1", i), [layer.linear1], layer.norm1)
+                if i > 0:
+                    fold(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], enc.layers[i - 1].norm2)
+            fold("heads", m._heads(), enc.norm, 8)
+
+    def _logits_fold(self):
+        m, enc = self.model, self.model.transformer_encoder
+        dt, c, H, E, N = torch.bfloat16, enc._cache, enc.n_heads, enc.d_head, self.N
+        z = m._embed(self.cur[:, None, :], 0, self.step_dev if self.true_positions else None)
+        x = z.view(N, m.d_model)                       # layer 0: the residual stream is a plain tensor
+        y = stats2 = prev = None                       # later layers: pre-norm rows of the previous layer + their statistics
+        for i, (layer, st) in enumerate(zip(enc.layers, self.state)):
+            at = layer.attention
+            if i == 0:
+                pk, _ = c.get_gemm_pack(("qkv", i), [at.query_projection, at.key_projection, at.value_projection], dt)
+                qkv = ops.gemm_nt_small(x, pk[0], pk[2])
+            else:
+                wf, c1, c2 = self._folded[("qkv", i)]
+                stats2 = torch.empty(N, 2, dtype=torch.float32, device=x.device)
+                qkv = ops.gemm_nt_small_ln(y, wf, c2, fold_c1=c1, stats_out=stats2, ln_eps=prev.norm2.eps)
+            q, k, v = (qkv[:, j * H * E:(j + 1) * H * E].unflatten(-1, (H, E)) for j in range(3))
+            a = ops.linattn_step(q, k, v, st[0], st[1]).view(N, H * E)
+            pk, _ = c.get_gemm_pack(("out", i), [at.out_projection], dt)
+            if i == 0:
+                y1 = ops.gemm_nt_small_ln(a, pk[0], pk[2], resid=x)
+            else:
+                y1 = ops.gemm_nt_small_ln(a, pk[0], pk[2], resid=y, r_stats=stats2, r_gamma=prev.norm2.weight, r_beta=prev.norm2.bias)
+            wf, c1, c2 = self._folded[("ff1", i)]
+            stats1 = torch.empty(N, 2, dtype=torch.float32, device=x.device)
+            g = ops.gemm_nt_small_ln(y1, wf, c2, gelu=True, fold_c1=c1, stats_out=stats1, ln_eps=layer.norm1.eps)
+            pk, _ = c.get_gemm_pack(("ff2", i), [layer.linear2], dt)
+            y = ops.gemm_nt_small_ln(g, pk[0], pk[2], resid=y1, r_stats=stats1, r_gamma=layer.norm1.weight, r_beta=layer.norm1.bias)
+            prev = layer
+        xl = ops.ln_residual(y, None, prev.norm2.weight, prev.norm2.bias, prev.norm2.eps, 0.0)      # the last norm2 stays a kernel
+        wf, c1, c2 = self._folded["heads"]
+        return ops.gemm_nt_small_ln(xl, wf, c2, fold_c1=c1, ln_eps=enc.norm.eps)
+
     def _logits(self):
         """Logits of the next token for every sequence, given self.cur and the recurrent state."""
+        if self.fold:
+            if self._folded is None:
+                self._fold_refresh()
+            return self._logits_fold()
         m = self.model
         z = m._embed(self.cur[:, None, :], 0, self.step_dev if self.true_positions else None)
         h, _ = m.transformer_encoder.step_fused(z.view(self.N, m.d_model), self.state)
@@ -223,6 +294,8 @@ class RolloutEngine:
             self._capture()
         self.reset(init_tokens)
         self.model.refresh_packs()          # the graph reads the packed weights by address
+        if self.fold:
+            self._fold_refresh()
         if self.use_graph:
             for _ in range(n_steps):
                 self.graph.replay()

@@ -757,6 +757,7 @@ def test_out_of_range_token_ids_raise_index_error(cuda, cpm):
     and the host raises at the next poll / check instead of training silently on zero rows."""
     m = cpm.TransformerModel([56, 135, 18, 87, 18, 25], d_model=128, n_layer=1, n_head=2, d_inner=256, dropout=0.0).to(cuda)
     x = torch.zeros(2, 8, 6, dtype=torch.int64, device=cuda)
+    cpm.ops.IndexGuard.reset(cuda)                       # earlier tests feed bad ids to the raw kernel on purpose
     m.train_step(x, x, torch.ones(2, 8, device=cuda))
     cpm.ops.IndexGuard.check(cuda)                       # clean input: nothing raised
     x[1, 3, 1] = 135

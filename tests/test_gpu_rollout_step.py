@@ -20,7 +20,7 @@ def _model(cpm, cuda, seed=3, **cfg):
 
 def _pair(cpm, m, N, T, **kw):
     p = cpm.RolloutEngine(m, N, T, mode="persistent", **kw)
-    c = cpm.RolloutEngine(m, N, T, mode="chain", **kw)
+    c = cpm.RolloutEngine(m, N, T, mode="chain", fold_ln=False, **kw)       # like with like: the chain with its LayerNorm kernels
     assert p.mode == "persistent" and c.mode == "chain"
     return p, c
 
@@ -131,7 +131,58 @@ def test_unsupported_shapes_fall_back_to_the_chain_and_bad_tokens_raise(cuda, cp
     m = _model(cpm, cuda, d_model=128, n_layer=1, n_head=2, d_inner=256)
     bad = _init(4, 1).to(cuda)
     bad[2, 1] = 999
+    cpm.ops.IndexGuard.reset(cuda)
     cpm.RolloutEngine(m, 4, 2, greedy=True, mode="persistent").generate(bad)
     with pytest.raises(IndexError):
         cpm.ops.IndexGuard.check(cuda)
     cpm.ops.IndexGuard.check(cuda)                                   # the flag is cleared once reported
+
+
+# ---------------------------------------------------------------- the default chain: LayerNorm folded into the Linear kernels
+@pytest.mark.parametrize("N,cfg", [(5, dict(d_model=128, n_layer=2, n_head=2, d_inner=256)), (256, dict()), (300, dict())])
+def test_folded_chain_one_step_vs_layernorm_kernels(cuda, cpm, N, cfg):
+    """cpm_gemm_nt_small_ln: the step with LayerNorm folded into the Linear kernels (raw rows times gamma o W, statistics from
+    the activation tile, residual LayerNorm rebuilt in the epilogue) against the same chain with its LayerNorm kernels: logits
+    within bf16 noise, the recurrent state likewise, nearly all greedy tokens equal."""
+    m = _model(cpm, cuda, seed=13, **cfg)
+    init = _init(N, 3).to(cuda)
+    f = cpm.RolloutEngine(m, N, 4, greedy=True, mode="chain", fold_ln=True)
+    c = cpm.RolloutEngine(m, N, 4, greedy=True, mode="chain", fold_ln=False)
+    assert f.fold and not c.fold
+    for e in (f, c):
+        e.reset(init)
+    with torch.no_grad():
+        m.refresh_packs()
+        f._fold_refresh()
+        lf, lc = f._logits().float()[:, :m.seg[-1]], c._logits().float()[:, :m.seg[-1]]
+    assert (lf - lc).abs().max() < 0.12 and (lf - lc).abs().mean() < 0.012, ((lf - lc).abs().max(), (lf - lc).abs().mean())
+    rel = lambda x, y: ((x - y).norm() / y.norm()).item()
+    assert rel(f.S, c.S) < 2e-2 and rel(f.Z, c.Z) < 1e-2, (rel(f.S, c.S), rel(f.Z, c.Z))
+    a, b = f.generate(init, n_steps=1), c.generate(init, n_steps=1)
+    assert _agree(a["tokens"], b["tokens"]) > 0.9                  # random-weight logits are nearly flat: near-ties flip
+    assert f.launches_per_step == c.launches_per_step - 2 * len(m.transformer_encoder.layers)      # two LayerNorm launches per layer gone
+
+
+def test_folded_chain_greedy_equals_teacher_forced_argmax(cuda, cpm):
+    """The default rollout (LayerNorm-folded chain, CUDA graph) against the PARALLEL model run teacher-forced over the tokens it
+    generated: every greedy choice with a clear top-2 margin is the parallel model's arg-max; recorded log-probs agree."""
+    m = _model(cpm, cuda, seed=8)
+    mp = cpm.TransformerModel(VOCAB, dropout=0.0).to(cuda).eval()
+    mp.load_state_dict(m.state_dict())
+    N, T = 64, 128
+    init = _init(N, 4).to(cuda)
+    eng = cpm.RolloutEngine(m, N, T, greedy=True)
+    assert eng.mode == "chain" and eng.fold
+    out = eng.generate(init)
+    with torch.no_grad():
+        lc = mp.logits_concat(mp.hidden(out["tokens"][:, :-1])).float()
+    ok = tot = 0
+    for a in range(6):
+        seg = lc[..., mp.seg[a]:mp.seg[a + 1]]
+        top2 = seg.topk(2, -1).values
+        sure = (top2[..., 0] - top2[..., 1]) > 0.12
+        ok += ((seg.argmax(-1) == out["tokens"][:, 1:, a]) & sure).sum().item()
+        tot += sure.sum().item()
+    assert tot > 0.4 * N * T * 6 and ok >= tot - 2, (ok, tot)
+    lp, _ = cpm.ops.heads_logp(lc.bfloat16(), out["tokens"][:, 1:], mp.seg, False)
+    assert (out["logp"] - lp).abs().max() < 0.15 and (out["logp"] - lp).abs().mean() < 0.02
