@@ -647,7 +647,7 @@ class IndexGuard:
 
     @classmethod
     def poll(cls, device) -> None:
-        if os.environ.get("CPM_CHECK_INDICES", "1") == "0" or torch.cuda.is_current_stream_capturing():
+        if torch.device(device).type != "cuda" or os.environ.get("CPM_CHECK_INDICES", "1") == "0" or torch.cuda.is_current_stream_capturing():
             return
         f = cls.flag(device)
         prev = cls._pending.get(id(f))
