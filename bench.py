@@ -222,11 +222,13 @@ def run_reference(args, rank):
 # GPU arm
 # --------------------------------------------------------------------------------------------
 class PPOIteration:
-    def __init__(self, rank, world, dev, dropout=0.1, lr=1e-5, seed=0):
+    def __init__(self, rank, world, dev, dropout=0.1, lr=1e-5, seed=0, songs=None, minibatch=None):
         import torch
         import cpmusic
         self.torch, self.cpm = torch, cpmusic
         self.rank, self.world, self.dev = rank, world, dev
+        self.songs = SONGS_PER_GPU if songs is None else songs
+        self.mb = min(MINIBATCH if minibatch is None else minibatch, self.songs)
         torch.manual_seed(seed)                       # identical initial weights on every rank
         self.actor = cpmusic.LinearTransformer(VOCAB, dropout=dropout).to(dev)
         self.critic = cpmusic.Critic_Transformer(VOCAB, dropout=dropout).to(dev)
@@ -234,11 +236,11 @@ class PPOIteration:
         self.opt_c = torch.optim.Adam(self.critic.parameters(), lr=lr, fused=True)
         self.red_a = cpmusic.dist.BucketedGradAllReduce(self.actor.parameters(), 25.0)
         self.red_c = cpmusic.dist.BucketedGradAllReduce(self.critic.parameters(), 25.0)
-        self.engine = cpmusic.RolloutEngine(self.actor, SONGS_PER_GPU, ROLLOUT_LEN, greedy=False, true_positions=True,
-                                            seed=1234, seq_base=rank * SONGS_PER_GPU)
+        self.engine = cpmusic.RolloutEngine(self.actor, self.songs, ROLLOUT_LEN, greedy=False, true_positions=True,
+                                            seed=1234, seq_base=rank * self.songs)
         self.group = None                              # attach_group() once the process group exists
         g = torch.Generator().manual_seed(1234 + rank)
-        self.init_host = torch.stack([torch.randint(0, n, (SONGS_PER_GPU,), generator=g) for n in VOCAB], -1).pin_memory()
+        self.init_host = torch.stack([torch.randint(0, n, (self.songs,), generator=g) for n in VOCAB], -1).pin_memory()
         self.init_dev = self.init_host.to(dev)
         self.phase_ms = {"rollout": 0.0, "update": 0.0}
         self.cstream = torch.cuda.Stream(device=dev)
@@ -258,10 +260,10 @@ class PPOIteration:
     def _critic_update(self, x, ret, scale, n_mb):
         torch = self.torch
         self.critic.train()
-        self.red_c.zero_grad(n_micro=-(-x.shape[0] // MINIBATCH))      # reduce after the LAST micro-batch's gradients
+        self.red_c.zero_grad(n_micro=-(-x.shape[0] // self.mb))        # reduce after the LAST micro-batch's gradients
         vstat = torch.zeros((), device=self.dev)
-        for i in range(0, x.shape[0], MINIBATCH):
-            sl = slice(i, i + MINIBATCH)
+        for i in range(0, x.shape[0], self.mb):
+            sl = slice(i, i + self.mb)
             v = self.critic.value_per_position(x[sl])
             vloss = torch.nn.functional.mse_loss(v, ret[sl])
             (vloss * scale).backward()
@@ -310,10 +312,10 @@ class PPOIteration:
         self._inflight = None
         self.critic.eval()
         with torch.no_grad():
-            values = torch.cat([self.critic.value_per_position(x[i:i + MINIBATCH]) for i in range(0, B, MINIBATCH)], 0)
+            values = torch.cat([self.critic.value_per_position(x[i:i + self.mb]) for i in range(0, B, self.mb)], 0)
         adv, ret = cpm.rl.gae(reward, values, dones, torch.zeros(B, device=self.dev), 0.99, 0.95, True, self.group)
         self.actor.train()
-        n_mb = B // MINIBATCH
+        n_mb = B // self.mb
         self.red_a.zero_grad(n_micro=n_mb)
         scale = 1.0 / (n_mb * self.world)                               # mean over the GLOBAL batch; grads are SUM-reduced
         if OVERLAP_CRITIC:
@@ -321,8 +323,8 @@ class PPOIteration:
             ready.record()
             self.pending = (x, ret, scale, n_mb, ready)
         stats = torch.zeros(4, device=self.dev)
-        for i in range(0, B, MINIBATCH):
-            sl = slice(i, i + MINIBATCH)
+        for i in range(0, B, self.mb):
+            sl = slice(i, i + self.mb)
             lc = self.actor.logits_concat(self.actor.hidden(x[sl]))
             new_logp, ent = cpm.ops.heads_logp(lc, act[sl], self.actor.seg, True)
             out = cpm.ops.ppo_loss_standard(new_logp, old_logp[sl], adv[sl, :, None].expand(-1, -1, A), None, None, ent,
@@ -344,9 +346,13 @@ class PPOIteration:
         return tokens, stats
 
 
+def tokens_per_s_weak(ms, steps, world):
+    return SONGS_PER_GPU * ROLLOUT_LEN * world * steps / (ms * 1e-3)
+
+
 def time_recurrent_step_kernel(dev, peak):
     """Standalone HBM roofline of the recurrent attention step kernel at the rollout shape
-    (32 sequences x 8 heads x 12 layers' states = 50 MB touched per pass, L2 flushed between)."""
+    (256 sequences x 8 heads x 12 layers' states = 830 MB touched per pass, L2 flushed between)."""
     import torch
     import cpmusic
     N, H, layers = SONGS_PER_GPU, 8, 12
@@ -487,6 +493,33 @@ def run_gpu(args, rank, world):
         t = torch.tensor([ms, ms_e2e], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, ms_e2e = float(t[0]), float(t[1])
+    # ---- cfg3 as BASELINE.json words it: 256 songs IN TOTAL, 256 / N per GPU (strong scaling) --------------------------
+    strong = {"songs_total": SONGS_PER_GPU, "songs_per_gpu": SONGS_PER_GPU // world, "tokens_per_s": tokens_per_s_weak(ms, args.steps, 1),
+              "ms_per_step": ms / args.steps, "note": "identical to the headline at 1 GPU"}
+    if world > 1 and SONGS_PER_GPU % world == 0:
+        it_s = PPOIteration(rank, world, dev, songs=SONGS_PER_GPU // world)
+        it_s.attach_group()
+        for _ in range(2):
+            it_s.step(it_s.init_dev)
+        it_s.flush()
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n_s = max(2, min(args.steps, 5))
+        g0.record()
+        for _ in range(n_s):
+            it_s.step(it_s.init_dev)
+        it_s.flush()
+        g1.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([g0.elapsed_time(g1)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_s = float(t[0]) / n_s
+        it_s.phase_ms = {"rollout": 0.0, "update": 0.0}
+        it_s.step(it_s.init_dev, time_phases=True)
+        strong = {"songs_total": SONGS_PER_GPU, "songs_per_gpu": SONGS_PER_GPU // world, "tokens_per_s": SONGS_PER_GPU * ROLLOUT_LEN / (ms_s * 1e-3),
+                  "ms_per_step": ms_s, "steps": n_s, "phase_ms": {k: round(v, 3) for k, v in it_s.phase_ms.items()},
+                  "minibatch": it_s.mb, "note": "256 songs x 1024 tokens in total, sharded over the GPUs; max over ranks"}
+        del it_s
     if rank != 0:
         return
     tokens_step = SONGS_PER_GPU * ROLLOUT_LEN * world
@@ -509,6 +542,11 @@ def run_gpu(args, rank, world):
                 "tensor_frac_of_measured_bf16": (tok_call * 8 * 49152) / (ms_pair * 1e-3) / 1e12 / 1651.8 if ms_pair > 0 else 0.0}
     roofline_step = time_recurrent_step_kernel(dev, peak)
     cpu = cpu_reference_sample() if world >= 1 and not args.no_cpu_baseline else None
+    diag = {"rollout_us_per_token": round(it.phase_ms["rollout"] * 1e3 / ROLLOUT_LEN, 1), "rollout_mode": it.engine.mode,
+            "rollout_layernorm_folded": bool(it.engine.fold), "under_torchrun": "TORCHELASTIC_RUN_ID" in os.environ,
+            "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "omp_num_threads": os.environ.get("OMP_NUM_THREADS"),
+            "cpu_affinity": len(os.sched_getaffinity(0)), "state_base_mod_2MiB": int(it.engine.S.data_ptr() % (2 << 20)),
+            "allocator_reserved_GB": round(torch.cuda.memory_reserved(dev) / 2**30, 2), "gpu_name": torch.cuda.get_device_name(dev)}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",
@@ -518,7 +556,15 @@ def run_gpu(args, rank, world):
                     "d2h_bytes_per_step": int(host_tok.numel() * 8 + 16), "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches, "clocks": clocks,
             "phase_ms": {k: round(v, 3) for k, v in it.phase_ms.items()},
-            "rollout_kernels_per_token_step": it.engine.launches_per_step}
+            "rollout_kernels_per_token_step": it.engine.launches_per_step, "diag": diag,
+            "strong_scaling": strong, "configs": None}
+    if world == 1 and not args.no_configs:
+        # BASELINE.json's other configurations on this GPU, a few timed iterations each (tools/bench_configs.py)
+        del it
+        torch.cuda.empty_cache()
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import bench_configs as bc
+        line["configs"] = bc.run_cfg2(dev, 10) + bc.run_cfg4(dev, 5) + bc.run_cfg5(dev, 3)
     print(json.dumps(line), flush=True)
 
 
@@ -529,6 +575,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="cpmusic", choices=["cpmusic", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-configs", action="store_true", help="skip the cfg2 / cfg4 / cfg5 timings appended at 1 GPU")
     ap.add_argument("--profile-step", action="store_true",
                     help="after the warm-up run ONE iteration between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()

@@ -542,9 +542,12 @@ int launch_nt(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &t
     }
     const int MB = (a.M + 255) / 256, NB = (a.N + 255) / 256, NB2 = (a.N + 511) / 512, max_pairs = num_sms() / 2;
     int mode = g_gemm_mode;
-    // auto: wide tiles once they fill the machine and N spans more than one 256-column slab; small problems keep the finer
-    // 256 x 256 tiles (more of them to spread over the pairs)
-    if (mode != 1 && mode != 3) mode = (NB > 1 && MB * NB2 >= max_pairs) ? 3 : 1;
+    // auto: whichever schedule needs less time under "waves x time per tile", a 256 x 512 tile costing 4/3 of a 256 x 256 one
+    // (twice the flops at the measured 1000 vs 660 TFLOP/s).  Wide tiles need N to span more than one 256-column slab.
+    if (mode != 1 && mode != 3) {
+        const int waves_wide = (MB * NB2 + max_pairs - 1) / max_pairs, waves_stream = (MB * NB + max_pairs - 1) / max_pairs;
+        mode = (NB > 1 && 4 * waves_wide <= 3 * waves_stream) ? 3 : 1;
+    }
     if (mode == 3) {
         gemm_nt_wide_kernel<EPI><<<2 * min(MB * NB2, max_pairs), G2_THREADS, G2_SMEM, st>>>(tA, tB, tD, tD2, a);
         return check_launch("gemm_nt (wide)");
