@@ -437,9 +437,17 @@ def run_gpu(args, rank, world):
     it.flush()
     barrier()
     if args.profile_step:                              # ncu --profile-from-start off: one whole iteration, every thread's launches
-        torch.cuda.profiler.start()
-        it.step(it.init_dev)
-        it.flush()
+        if args.profile_step == "rollout":
+            torch.cuda.profiler.start()
+            it.engine.generate(it.init_dev, n_steps=8)
+        else:
+            if args.profile_step == "update":          # the update phase alone: the rollout it consumes is generated beforehand
+                roll = it.engine.generate(it.init_dev)
+                torch.cuda.synchronize()
+                it.engine.generate = lambda *_a, **_k: roll
+            torch.cuda.profiler.start()
+            it.step(it.init_dev)
+            it.flush()
         torch.cuda.synchronize()
         torch.cuda.profiler.stop()
         return
@@ -576,8 +584,9 @@ def main():
     ap.add_argument("--impl", default="cpmusic", choices=["cpmusic", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-configs", action="store_true", help="skip the cfg2 / cfg4 / cfg5 timings appended at 1 GPU")
-    ap.add_argument("--profile-step", action="store_true",
-                    help="after the warm-up run ONE iteration between cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
+    ap.add_argument("--profile-step", nargs="?", const="all", default=None, choices=["all", "update", "rollout"],
+                    help="after the warm-up run ONE iteration (or only its update phase / 8 token steps of its rollout) between "
+                         "cudaProfilerStart/Stop and exit (for ncu --profile-from-start off)")
     args = ap.parse_args()
     rank, world = int(os.environ.get("RANK", 0)), int(os.environ.get("WORLD_SIZE", 1))
     if args.impl == "reference":

@@ -285,8 +285,8 @@ class Critic_Transformer(CPLinearTransformer):
         u, c = 0.0, 0.0
         for a in self.attrs:
             proj, val = getattr(self, f"proj_{a}"), getattr(self, f"{a}_value")
-            u = u + val.weight[0] @ proj.weight
-            c = c + val.weight[0] @ proj.bias + val.bias[0]
+            u = u + (val.weight[0][:, None] * proj.weight).sum(0)       # (n_a,) x (n_a, d): element-wise, no library GEMV
+            c = c + (val.weight[0] * proj.bias).sum() + val.bias[0]
         return u / len(self.attrs), c / len(self.attrs)
 
     def value_per_position(self, x):

@@ -182,3 +182,44 @@ def test_gemm_nt_small_token_step_shapes(cuda, cpm, shape, pdl):
     _assert_close_bf16(nb, ref - bias.double().cpu(), "no bias")
     exact = torch.nn.functional.gelu(outs[0].double().cpu())
     _assert_close_bf16(g, exact, "gelu epilogue vs exact erf of the bf16 pre-activation")
+
+
+@pytest.mark.parametrize("shape", [(256, 512, 2048), (256, 512, 1216), (70, 96, 2048), (300, 344, 512)])
+@pytest.mark.parametrize("pdl", [False, True])
+def test_gemm_nt_small_layernorm_forms(cuda, cpm, shape, pdl):
+    """cpm_gemm_nt_small_ln: the residual and LayerNorm-rebuilt-residual epilogues against the plain product plus the residual
+    (fp64), and the FOLD form - raw rows times gamma o W with the row statistics taken from the activation tile - against
+    LayerNorm followed by the product, statistics included."""
+    M, N, K = shape
+    gen = torch.Generator().manual_seed(7 * M + N + K)
+    a, w = _bf16((M, K), gen).to(cuda), _bf16((N, K), gen, 1.0 / math.sqrt(K)).to(cuda)
+    bias = torch.randn(N, generator=gen).to(cuda)
+    res = _bf16((M, N), gen).to(cuda)
+    cpm.ops.set_chain_pdl(pdl)
+    try:
+        plain = cpm.ops.gemm_nt_small(a, w, bias)
+        r1 = cpm.ops.gemm_nt_small_ln(a, w, bias, resid=res)
+        stats = torch.stack([res.float().mean(1), torch.rsqrt(res.float().var(1, unbiased=False) + 1e-5)], 1).contiguous()
+        gam, bet = torch.randn(N, generator=gen).to(cuda), torch.randn(N, generator=gen).to(cuda)
+        r2 = cpm.ops.gemm_nt_small_ln(a, w, bias, resid=res, r_stats=stats, r_gamma=gam, r_beta=bet)
+        # FOLD: LayerNorm(y) W^T + b on raw rows (K = 512: the statistics come from the resident activation tile)
+        y = (_bf16((M, 512), gen) * 1.7 + 0.4).to(cuda)
+        W = _bf16((N, 512), gen, 1.0 / math.sqrt(512)).to(cuda)
+        g2, b2 = (torch.randn(512, generator=gen) * 0.2 + 1.0).to(cuda), (torch.randn(512, generator=gen) * 0.1).to(cuda)
+        wf = (W.float() * g2[None, :]).bfloat16()
+        c1, c2 = wf.float().sum(1), (W.float() * b2[None, :]).sum(1) + bias
+        st = torch.empty(M, 2, device=cuda)
+        out = cpm.ops.gemm_nt_small_ln(y, wf, c2, fold_c1=c1, stats_out=st, ln_eps=1e-5)
+        outg = cpm.ops.gemm_nt_small_ln(y, wf, c2, gelu=True, fold_c1=c1, ln_eps=1e-5)
+    finally:
+        cpm.ops.set_chain_pdl(False)
+    torch.cuda.synchronize()
+    _assert_close_bf16(r1, plain.double().cpu() + res.double().cpu(), "residual epilogue")
+    ln = torch.nn.functional.layer_norm(res.float(), (N,), gam, bet, 1e-5).bfloat16()
+    # the rebuilt LayerNorm value is rounded to bf16 like the LayerNorm kernel's output: one ulp of it may differ from torch's
+    _assert_close_bf16(r2, plain.double().cpu() + ln.double().cpu(), "LayerNorm-rebuilt residual epilogue", extra_abs=ln.float().abs().max().item() * 2.0 ** -7)
+    want = torch.nn.functional.layer_norm(y.double().cpu(), (512,), g2.double().cpu(), b2.double().cpu(), 1e-5) @ W.double().cpu().t() + bias.double().cpu()
+    assert (out.double().cpu() - want).abs().max() < 0.06 and (out.double().cpu() - want).abs().mean() < 6e-3
+    _assert_close_bf16(outg, torch.nn.functional.gelu(out.double().cpu()), "fold + gelu")
+    assert (st[:, 0].cpu() - y.float().mean(1).cpu()).abs().max() < 1e-4
+    assert ((st[:, 1].cpu() - torch.rsqrt(y.float().var(1, unbiased=False) + 1e-5).cpu()).abs() / st[:, 1].cpu()).max() < 1e-3
