@@ -117,7 +117,25 @@ def recurrent_linear_attention(q, k, v, state=None, eps: float = EPS):
 
 
 # --------------------------------------------------------------------------- #
-# masks (only the flag the reference uses)
+# masks (only the flag the reference uses, plus ft's LengthMask for the key-padding path the encoder signature carries)
+class LengthMask:
+    """``fast_transformers.masking.LengthMask`` restated: ``float_matrix[n, l] = 1 if l < lengths[n] else 0``."""
+
+    def __init__(self, lengths, max_len=None, device=None):
+        self.lengths = torch.as_tensor(lengths).long()
+        self.max_len = int(max_len) if max_len is not None else int(self.lengths.max())
+        self.lower_triangular = False
+
+    @property
+    def bool_matrix(self):
+        return torch.arange(self.max_len)[None, :] < self.lengths[:, None]
+
+    @property
+    def float_matrix(self):
+        return self.bool_matrix.float()
+
+
+
 # --------------------------------------------------------------------------- #
 class TriangularCausalMask:
     """``fast_transformers.masking.TriangularCausalMask`` restated: carries the
@@ -150,7 +168,7 @@ class AttentionLayer(nn.Module):
         self.value_projection = nn.Linear(d_model, d_values * n_heads)
         self.out_projection = nn.Linear(d_values * n_heads, d_model)
 
-    def forward(self, x, attn_mask, product=causal_dot_product_quadratic):
+    def forward(self, x, attn_mask, product=causal_dot_product_quadratic, key_lengths_mask=None):
         if not getattr(attn_mask, "lower_triangular", False):
             raise RuntimeError("CausalLinearAttention only supports full lower triangular masks")
         N, L, _ = x.shape
@@ -158,7 +176,7 @@ class AttentionLayer(nn.Module):
         q = self.query_projection(x).view(N, L, H, -1)
         k = self.key_projection(x).view(N, L, H, -1)
         v = self.value_projection(x).view(N, L, H, -1)
-        a = causal_linear_attention(q, k, v, product=product).reshape(N, L, -1)
+        a = causal_linear_attention(q, k, v, key_lengths_mask=key_lengths_mask, product=product).reshape(N, L, -1)
         return self.out_projection(a)
 
     def step(self, x, state):
@@ -191,8 +209,8 @@ class TransformerEncoderLayer(nn.Module):
         y = self.dropout(self.linear2(y))
         return self.norm2(x + y)
 
-    def forward(self, x, attn_mask, product=causal_dot_product_quadratic):
-        return self._tail(x, self.attention(x, attn_mask, product))
+    def forward(self, x, attn_mask, product=causal_dot_product_quadratic, key_lengths_mask=None):
+        return self._tail(x, self.attention(x, attn_mask, product, key_lengths_mask))
 
     def step(self, x, state):
         a, state = self.attention.step(x, state)
@@ -215,8 +233,11 @@ class TransformerEncoder(nn.Module):
 
     def forward(self, x, attn_mask=None, length_mask=None):
         attn_mask = attn_mask or FullMask(x.shape[1])
+        klm = None                                   # ft: K = K * k_len.float_matrix[:, :, None, None] in every layer (App. A.1)
+        if length_mask is not None:
+            klm = length_mask.float_matrix if hasattr(length_mask, "float_matrix") else torch.as_tensor(length_mask).float()
         for layer in self.layers:
-            x = layer(x, attn_mask, self.product)
+            x = layer(x, attn_mask, self.product, klm)
         return self.norm(x)
 
 

@@ -4,7 +4,7 @@ Importable as ``cpmusic`` (repo-root shim) or via
 ``importlib.import_module("reinforcement-learning-in-music-generation_b200")``.
 """
 from . import _lib, ops, encoder, model, rl, rollout, dist, data, graphs, midi  # noqa: F401
-from .encoder import (TransformerEncoderBuilder, RecurrentEncoderBuilder, TriangularCausalMask,  # noqa: F401
+from .encoder import (TransformerEncoderBuilder, RecurrentEncoderBuilder, TriangularCausalMask, LengthMask, FullMask,  # noqa: F401
                       install_fast_transformers_shim)
 from .model import (CPLinearTransformer, TransformerModel, LinearTransformer, Actor_Transformer,  # noqa: F401
                     Critic_Transformer)

@@ -60,9 +60,21 @@ class FullMask:
 
 
 class LengthMask:
+    """``fast_transformers.masking.LengthMask``: sequences of ``lengths[n]`` valid tokens padded to ``max_len``."""
+
     def __init__(self, lengths, max_len=None, device=None):
+        lengths = torch.as_tensor(lengths, device=device).long()
         self.lengths = lengths
-        self.max_len = max_len
+        self.max_len = int(max_len) if max_len is not None else int(lengths.max())
+        self.lower_triangular = False
+
+    @property
+    def bool_matrix(self):
+        return torch.arange(self.max_len, device=self.lengths.device)[None, :] < self.lengths[:, None]
+
+    @property
+    def float_matrix(self):
+        return self.bool_matrix.float()
 
 
 # torch's fused optimizers (``Adam(fused=True)``, with or without ``capturable``) update parameters WITHOUT bumping
@@ -211,11 +223,11 @@ class TransformerEncoder(nn.Module):
         self._cache = PackCache()
 
     # ---- fused path used by the CP model (stays in compute dtype) -------------------------
-    def _layer(self, i, layer, x):
+    def _layer(self, i, layer, x, key_mask=None):
         p = layer.dropout.p if self.training else 0.0
         dt, c, at = self.compute_dtype, self._cache, layer.attention
         qkv = cached_linear(c, ("qkv", i), [at.query_projection, at.key_projection, at.value_projection], x, dt)
-        a = ops.causal_linear_attention_fused(qkv, self.n_heads, ops.EPS_ATTN, self.attn_impl)
+        a = ops.causal_linear_attention_fused(qkv, self.n_heads, ops.EPS_ATTN, self.attn_impl, key_mask)
         # out-projection, linear1 and linear2 run bias-less: their biases are added inside the LayerNorm / GELU kernels,
         # whose backward kernels return the bias gradients as by-products (no reduction pass over the gradient tensors)
         if not FUSED_BIAS_GRADS:
@@ -246,10 +258,10 @@ class TransformerEncoder(nn.Module):
         f = cached_linear(c, ("ff2", i), [layer.linear2], g, dt)
         return ops.ln_residual(x, f, layer.norm2.weight, layer.norm2.bias, layer.norm2.eps, p)
 
-    def forward_fused(self, x):
-        """x (N,L,d) in compute dtype -> (N,L,d) in compute dtype."""
+    def forward_fused(self, x, key_mask=None):
+        """x (N,L,d) in compute dtype -> (N,L,d) in compute dtype.  key_mask (N,L): ft's key-padding (length) mask or None."""
         for i, layer in enumerate(self.layers):
-            x = self._layer(i, layer, x)
+            x = self._layer(i, layer, x, key_mask)
         return ops.ln_residual(x, None, self.norm.weight, self.norm.bias, self.norm.eps, 0.0)
 
     # ---- recurrent (one token per call) path; shares every parameter with the parallel path ------
@@ -292,9 +304,12 @@ class TransformerEncoder(nn.Module):
     def forward(self, x, attn_mask=None, length_mask=None):
         if attn_mask is None or not getattr(attn_mask, "lower_triangular", False):
             raise RuntimeError("CausalLinearAttention only supports full lower triangular masks")
-        if length_mask is not None:
-            raise NotImplementedError("length_mask is never passed by the reference (SURVEY App. A.1); not implemented")
-        return self.forward_fused(x.to(self.compute_dtype)).to(x.dtype)
+        key_mask = None
+        if length_mask is not None:                # K = K * k_len.float_matrix; the reference never passes one
+            key_mask = length_mask.bool_matrix if hasattr(length_mask, "bool_matrix") else torch.as_tensor(length_mask).bool()
+            if key_mask.shape != x.shape[:2]:
+                raise ValueError(f"length_mask covers {tuple(key_mask.shape)}, the input is {tuple(x.shape[:2])}")
+        return self.forward_fused(x.to(self.compute_dtype), key_mask).to(x.dtype)
 
     def _apply(self, fn, *a, **k):
         self._cache.clear()

@@ -312,11 +312,26 @@ def _linattn_fused_e128(qkv, H, eps, impl):
     return (num / tot).flatten(-3).to(qkv.dtype)
 
 
-def causal_linear_attention_fused(qkv, n_heads, eps=EPS_ATTN, impl=0):
-    """qkv (N,L,3*H*E) -> (N,L,H*E); E = 64 (one kernel pass) or 128 (two passes over 64-wide virtual heads)."""
+KEY_MASK_FILL = -30000.0        # elu(x) + 1 = exp(x) underflows to exactly 0 in fp32 (and so does its derivative)
+
+
+def causal_linear_attention_fused(qkv, n_heads, eps=EPS_ATTN, impl=0, key_mask=None):
+    """qkv (N,L,3*H*E) -> (N,L,H*E); E = 64 (one kernel pass) or 128 (two passes over 64-wide virtual heads).
+    ``key_mask`` (N,L) bool / 0-1: ft's key-padding mask, ``K = K * k_len.float_matrix``.  A padded key must
+    feed neither the KV state nor the normaliser; the kernels apply the feature map themselves, so the padded keys are sent in as
+    a large negative number, whose feature value (and derivative) is exactly zero - the same outputs and the same (zero) key
+    gradients as the multiplication."""
     E = qkv.shape[-1] // (3 * n_heads)
     if qkv.shape[-1] != 3 * n_heads * E or E not in (64, 128):
         raise ValueError(f"causal linear attention: head width {E} (supported: 64, 128)")
+    if key_mask is not None:
+        if key_mask.shape != qkv.shape[:2]:
+            raise ValueError(f"key_mask {tuple(key_mask.shape)} against qkv {tuple(qkv.shape)}")
+        HE = n_heads * E
+        is_key = torch.zeros(3 * HE, dtype=torch.bool, device=qkv.device)
+        is_key[HE:2 * HE] = True
+        drop = (~key_mask.to(device=qkv.device).bool())[..., None] & is_key
+        qkv = torch.where(drop, torch.full((), KEY_MASK_FILL, dtype=qkv.dtype, device=qkv.device), qkv)
     if E == 128:
         return _linattn_fused_e128(qkv, n_heads, eps, impl)
     return _LinAttnFused.apply(qkv, n_heads, eps, impl)

@@ -502,3 +502,36 @@ def test_train_step_cfg2_shape_bf16_vs_oracle(cuda, cpm):
         cos = float((a * b).sum() / (a.norm() * b.norm()))
         assert cos > 0.98, f"{name}: gradient cosine {cos:.4f}"
         assert 0.9 < float(a.norm() / b.norm()) < 1.1, f"{name}: gradient norm ratio {float(a.norm() / b.norm()):.3f}"
+
+
+@pytest.mark.parametrize("dtype,atol", [(torch.float32, 3e-4), (torch.bfloat16, 6e-2)])
+def test_encoder_length_mask_vs_oracle(cuda, cpm, dtype, atol):
+    """ft's key-padding path: ``encoder(x, TriangularCausalMask, LengthMask(lengths))`` multiplies the feature-mapped keys by
+    the length matrix in every layer.  Outputs at every position (valid and padded) and the input gradient
+    against the oracle; the padded keys really are excluded (the output changes when the mask is dropped)."""
+    from oracle import ft_oracle
+    torch.manual_seed(31)
+    kw = dict(n_layers=2, n_heads=2, query_dimensions=64, value_dimensions=64, feed_forward_dimensions=256,
+              activation="gelu", dropout=0.0, attention_type="causal-linear")
+    ref = ft_oracle.TransformerEncoderBuilder.from_kwargs(**kw).get().eval()
+    enc = cpm.TransformerEncoderBuilder.from_kwargs(compute_dtype=dtype, **kw).get()
+    enc.load_state_dict(ref.state_dict())
+    enc = enc.to(cuda).eval()
+    N, L = 3, 256
+    lengths = torch.tensor([256, 130, 17])
+    x = torch.randn(N, L, 128)
+    xr = x.clone().requires_grad_()
+    xg = x.clone().to(cuda).requires_grad_()
+    yr = ref(xr, ft_oracle.TriangularCausalMask(L), ft_oracle.LengthMask(lengths, L))
+    yg = enc(xg, cpm.TriangularCausalMask(L, device=cuda), cpm.LengthMask(lengths.to(cuda), L))
+    _cmp(yg, yr, atol, atol, "encoder output under a length mask")
+    w = torch.randn(N, L, 128)
+    (yr * w).sum().backward()
+    (yg * w.to(cuda)).sum().backward()
+    _cmp(xg.grad, xr.grad, 20 * atol, 5e-2, "input gradient under a length mask")
+    with torch.no_grad():
+        y_nomask = enc(x.to(cuda), cpm.TriangularCausalMask(L, device=cuda))
+    assert (y_nomask[1, 200] - yg[1, 200]).abs().max() > 1e-2           # position 200 of song 1 saw padded keys without the mask
+    assert (y_nomask[0] - yg[0]).abs().max() < atol                     # song 0 has no padding
+    with pytest.raises(ValueError):
+        enc(x.to(cuda), cpm.TriangularCausalMask(L, device=cuda), cpm.LengthMask(lengths.to(cuda), L + 1))
