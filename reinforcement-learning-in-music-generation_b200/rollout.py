@@ -7,15 +7,15 @@ not depend on how sequences are sharded over GPUs), a device-side step counter, 
 one-token step (embedding -> 12 layers -> heads -> sample -> bookkeeping) run with no host synchronisation.
 
 Two executions of the step, same arithmetic:
-  * ``mode="chain"`` (default): the step as 91 kernels of this library (small-M tcgen05 GEMMs with the GELU in linear1's
-    epilogue, the recurrent state kernel, fused residual + LayerNorm, embedding gather, sampler) launched with programmatic
+  * ``mode="chain"`` (default): the step as 67 kernels of this library (small-M tcgen05 GEMMs with LayerNorm folded in and
+    the GELU in linear1's epilogue, the recurrent state kernel, embedding gather, sampler) launched with programmatic
     dependent launch - each kernel's set-up and each GEMM's weight fetch overlap its predecessor's tail - and captured once in
-    a CUDA graph.  511 us per token step at 256 songs on B200.
+    a CUDA graph.  492 us per token step at 256 songs on B200.
   * ``mode="persistent"`` (opt-in, bf16 models with 64-wide heads; also CPM_ROLLOUT_MODE=persistent): ONE cooperative kernel
     for the whole rollout (csrc/rollout_step.cu, cpm_rollout_run): one CTA per SM, the 63 dependent stages of a token separated
     by a device-wide barrier, every CTA streaming the weight tiles of its own output tiles ahead of the barriers through a TMA
     ring, tcgen05 tiles with the weight rows on the UMMA M axis, LayerNorm applied while the activation tile is staged.
-    735 us per token step: measured slower, kept as the one non-default mode with its per-stage timeline (see its header).
+    700-760 us per token step: measured slower, kept as the one non-default mode with its per-stage timeline (see its header).
 
 (Round 1 also carried a first cooperative megakernel, skinny-GEMM, LayerNorm-fold, deferred / split state write-back,
 L2-prefetch and grouped-graph variants of the step; all measured slower than the chain and were removed - the write-ups
