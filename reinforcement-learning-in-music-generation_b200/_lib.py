@@ -12,7 +12,7 @@ import os
 from ctypes import c_char_p, c_double, c_float, c_int, c_int32, c_int64, c_uint64, c_void_p, POINTER
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libcpmusic.so")
+LIB_PATH = os.environ.get("CPM_LIB_PATH", os.path.join(_HERE, "libcpmusic.so"))      # override: A/B runs of kernel variants
 
 F32, BF16 = 0, 1
 RET_COMPAT, RET_TOGO, RET_GAE = 0, 1, 2

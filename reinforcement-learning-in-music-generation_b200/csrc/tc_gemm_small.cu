@@ -35,6 +35,10 @@ namespace {
 using namespace tc;
 
 constexpr int SG_BM = 64, SG_BN = 32, SG_NS = 8, SG_THREADS = 192;
+#ifndef SG_GRP
+#define SG_GRP 4
+#endif
+constexpr int GRP = SG_GRP;                                      // k-blocks per barrier in resident mode (K <= 512)
 constexpr uint32_t SG_A_BYTES = SG_BM * 128, SG_W_BYTES = SG_BN * 128, SG_STAGE = SG_A_BYTES + SG_W_BYTES;      // 8 KB + 4 KB
 constexpr uint32_t SG_OFF_BAR = SG_NS * SG_STAGE;                                                                // 98304
 constexpr uint32_t SG_SMEM = SG_OFF_BAR + 256;
@@ -81,12 +85,17 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     if (warp == 4) {
         if (lane == 0) {                                 // ---- TMA producer
             const int pre = KB < SG_NS ? KB : SG_NS;
+            // K <= 512: every k-block has its own stage and nothing is recycled, so the blocks report in GROUPS of four on the
+            // barrier of the group's first stage - the UMMA thread (and the statistics pass) pays two mbarrier round trips, not eight
+            const bool grouped = KB <= SG_NS;
             for (int i = 0; i < pre; ++i) {              // weights first: they do not depend on the previous kernel
-                mbar_expect_tx(bar_full + i, SG_STAGE);
-                tma_load_2d(sm + i * SG_STAGE + SG_A_BYTES, &tmW, bar_full + i, i * 64, n0);
+                uint64_t *bar = bar_full + (grouped ? (i / GRP) * GRP : i);
+                if (!grouped) mbar_expect_tx(bar, SG_STAGE);
+                else if (i % GRP == 0) mbar_expect_tx(bar, (uint32_t)min(GRP, KB - i) * SG_STAGE);
+                tma_load_2d(sm + i * SG_STAGE + SG_A_BYTES, &tmW, bar, i * 64, n0);
             }
             griddep_wait();                              // the activations (and every buffer this kernel writes) belong to the chain
-            for (int i = 0; i < pre; ++i) tma_load_2d(sm + i * SG_STAGE, &tmA, bar_full + i, i * 64, m0);
+            for (int i = 0; i < pre; ++i) tma_load_2d(sm + i * SG_STAGE, &tmA, bar_full + (grouped ? (i / GRP) * GRP : i), i * 64, m0);
             for (int i = pre; i < KB; ++i) {
                 const int s = i % SG_NS;
                 mbar_wait(bar_empty + s, ((i / SG_NS) - 1) & 1);
@@ -98,13 +107,20 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     } else if (warp == 5) {
         if (lane == 0) {                                 // ---- UMMA issuer
             const uint64_t dA0 = smem_desc_sw128(smem_u32(sm)), dW0 = smem_desc_sw128(smem_u32(sm + SG_A_BYTES));
-            int s = 0, ph = 0;
-            for (int i = 0; i < KB; ++i) {
-                mbar_wait(bar_full + s, ph);
-                tc_fence_after();
-                mma_ss_kblock(tmem, dA0 + (uint64_t)(s * (SG_STAGE >> 4)), dW0 + (uint64_t)(s * (SG_STAGE >> 4)), IDESC_SG, i > 0 ? 1u : 0u);
-                mma_commit(bar_empty + s);
-                if (++s == SG_NS) { s = 0; ph ^= 1; }
+            if (KB <= SG_NS) {                           // resident: groups of four k-blocks per barrier, no stage recycling
+                for (int i = 0; i < KB; ++i) {
+                    if (i % GRP == 0) { mbar_wait(bar_full + i, 0); tc_fence_after(); }
+                    mma_ss_kblock(tmem, dA0 + (uint64_t)(i * (SG_STAGE >> 4)), dW0 + (uint64_t)(i * (SG_STAGE >> 4)), IDESC_SG, i > 0 ? 1u : 0u);
+                }
+            } else {
+                int s = 0, ph = 0;
+                for (int i = 0; i < KB; ++i) {
+                    mbar_wait(bar_full + s, ph);
+                    tc_fence_after();
+                    mma_ss_kblock(tmem, dA0 + (uint64_t)(s * (SG_STAGE >> 4)), dW0 + (uint64_t)(s * (SG_STAGE >> 4)), IDESC_SG, i > 0 ? 1u : 0u);
+                    mma_commit(bar_empty + s);
+                    if (++s == SG_NS) { s = 0; ph ^= 1; }
+                }
             }
             mma_commit(bar_done);
         }
@@ -121,7 +137,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const int r = 16 * warp + (lane & 15), half = lane >> 4;
             float sx = 0.f, sxx = 0.f;
             for (int i = 0; i < KB; ++i) {
-                mbar_wait(bar_full + i, 0);
+                if (i % GRP == 0) mbar_wait(bar_full + i, 0);         // FOLD implies K <= 512: grouped barriers
                 const uint8_t *rp = sm + i * SG_STAGE + r * 128;
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
