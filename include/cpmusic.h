@@ -214,6 +214,11 @@ int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *
  * Reference loop being served: testing-no-type-cp.py:157-167 (forward_hidden(..., is_training=False) + forward_output). */
 int cpm_gemm_nt_small(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int M, int N, int K,
                       const float *bias, int epilogue, void *stream);
+/* Development aid: device log {uint64 count; uint64 stamps[capacity][8]} (zero-filled by the caller) to which block (0,0) of
+ * every cpm_gemm_nt_small[_ln] launch appends %globaltimer stamps (kernel entry, set-up done, griddepcontrol.wait returned,
+ * first activation block landed, accumulator ready, epilogue stored) and N, K.  The pointer is read at LAUNCH time, so it is
+ * baked into captured graphs.  NULL switches it off (the default). */
+int cpm_debug_small_timing(void *device_log, int capacity);
 /* The token-step Linear with the LayerNorm around it folded in - no LayerNorm kernels in the rollout chain.  ft's recurrent
  * encoder layer is  x = norm1(x + out_proj(attn));  y = linear2(gelu(linear1(x)));  x = norm2(x + y).
  * Exactly one of two forms per call:

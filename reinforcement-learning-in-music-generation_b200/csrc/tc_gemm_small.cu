@@ -44,6 +44,15 @@ constexpr uint32_t SG_OFF_BAR = SG_NS * SG_STAGE;                               
 constexpr uint32_t SG_SMEM = SG_OFF_BAR + 256;
 constexpr uint32_t IDESC_SG = idesc_bf16(SG_BM, SG_BN, false, false);
 
+// development aid (cpm_debug_small_timing): CTA (0,0) of every launch appends 6 %globaltimer stamps - kernel entry, set-up done,
+// griddepcontrol.wait returned, first activation block landed, accumulator ready, epilogue stored - to a device log
+struct SmallTiming { unsigned long long count; unsigned long long stamps[1]; };
+__device__ __forceinline__ unsigned long long gtimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+
 struct SmallArgs {
     const float *bias;
     __nv_bfloat16 *D;
@@ -57,6 +66,8 @@ struct SmallArgs {
     int64_t ldr;
     const float2 *r_stats;             // ... through LayerNorm(R) with these row statistics and r_gamma / r_beta when non-NULL
     const float *r_gamma, *r_beta;
+    SmallTiming *timing;               // NULL unless cpm_debug_small_timing installed a log
+    int timing_cap;
 };
 
 template <int EPI, bool FOLD = false, bool RESID = false>
@@ -67,6 +78,14 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_done + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int n0 = blockIdx.x * SG_BN, m0 = blockIdx.y * SG_BM, KB = (a.K + 63) >> 6;
+    __shared__ unsigned long long *s_log;
+    if (a.timing && tid == 0) {
+        s_log = nullptr;
+        if (blockIdx.x == 0 && blockIdx.y == 0) {
+            const unsigned long long slot = atomicAdd(&a.timing->count, 1ull);
+            if (slot < (unsigned long long)a.timing_cap) { s_log = a.timing->stamps + slot * 8; s_log[0] = gtimer(); s_log[6] = (unsigned long long)a.N; s_log[7] = (unsigned long long)a.K; }
+        }
+    }
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         for (int s = 0; s < SG_NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }
@@ -81,6 +100,8 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     if (tid == 0) griddep_launch();                      // the next kernel may start its own set-up / weight prefetch
+    unsigned long long *logp = a.timing ? s_log : nullptr;
+    if (logp && tid == 0) logp[1] = gtimer();
 
     if (warp == 4) {
         if (lane == 0) {                                 // ---- TMA producer
@@ -95,6 +116,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 tma_load_2d(sm + i * SG_STAGE + SG_A_BYTES, &tmW, bar, i * 64, n0);
             }
             griddep_wait();                              // the activations (and every buffer this kernel writes) belong to the chain
+            if (logp) logp[2] = gtimer();
             for (int i = 0; i < pre; ++i) tma_load_2d(sm + i * SG_STAGE, &tmA, bar_full + (grouped ? (i / GRP) * GRP : i), i * 64, m0);
             for (int i = pre; i < KB; ++i) {
                 const int s = i % SG_NS;
@@ -109,7 +131,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             const uint64_t dA0 = smem_desc_sw128(smem_u32(sm)), dW0 = smem_desc_sw128(smem_u32(sm + SG_A_BYTES));
             if (KB <= SG_NS) {                           // resident: groups of four k-blocks per barrier, no stage recycling
                 for (int i = 0; i < KB; ++i) {
-                    if (i % GRP == 0) { mbar_wait(bar_full + i, 0); tc_fence_after(); }
+                    if (i % GRP == 0) { mbar_wait(bar_full + i, 0); tc_fence_after(); if (logp && i == 0) logp[3] = gtimer(); }
                     mma_ss_kblock(tmem, dA0 + (uint64_t)(i * (SG_STAGE >> 4)), dW0 + (uint64_t)(i * (SG_STAGE >> 4)), IDESC_SG, i > 0 ? 1u : 0u);
                 }
             } else {
@@ -176,6 +198,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         mbar_wait(bar_done, 0);                          // the UMMAs ran after the producer's griddepcontrol.wait: ordered behind the chain
         tc_fence_after();
+        if (logp && tid == 0) logp[4] = gtimer();
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), r);
         tmem_ld_wait();
@@ -221,8 +244,12 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
     }
     tc_fence_before();
     __syncthreads();
+    if (logp && tid == 0) logp[5] = gtimer();
     if (warp == 4) tmem_dealloc<32>(tmem);
 }
+
+SmallTiming *g_small_timing = nullptr;
+int g_small_timing_cap = 0;
 
 template <int EPI, bool FOLD = false, bool RESID = false>
 int launch_small(const CUtensorMap &tA, const CUtensorMap &tW, const SmallArgs &a, cudaStream_t st) {
@@ -233,7 +260,10 @@ int launch_small(const CUtensorMap &tA, const CUtensorMap &tW, const SmallArgs &
         attr = true;
     }
     const dim3 grid((a.N + SG_BN - 1) / SG_BN, (a.M + SG_BM - 1) / SG_BM);
-    cudaError_t e = launch_chain(gemm_small_kernel<EPI, FOLD, RESID>, grid, dim3(SG_THREADS), SG_SMEM, st, tA, tW, a);
+    SmallArgs b = a;
+    b.timing = g_small_timing;
+    b.timing_cap = g_small_timing_cap;
+    cudaError_t e = launch_chain(gemm_small_kernel<EPI, FOLD, RESID>, grid, dim3(SG_THREADS), SG_SMEM, st, tA, tW, b);
     if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_small launch: %s", cudaGetErrorString(e));
     return CPM_OK;
 }
@@ -259,6 +289,12 @@ extern "C" int cpm_gemm_nt_small(const void *A, int64_t lda, const void *W, int6
     cudaStream_t st = (cudaStream_t)stream;
     if (epilogue == CPM_GEMM_EPI_GELU) return launch_small<CPM_GEMM_EPI_GELU>(tA, tW, a, st);
     return launch_small<CPM_GEMM_EPI_BIAS>(tA, tW, a, st);
+}
+
+extern "C" int cpm_debug_small_timing(void *device_log, int capacity) {
+    g_small_timing = (SmallTiming *)device_log;
+    g_small_timing_cap = device_log ? capacity : 0;
+    return CPM_OK;
 }
 
 extern "C" int cpm_gemm_nt_small_ln(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int M, int N, int K,

@@ -79,12 +79,17 @@ class LengthMask:
 
 # torch's fused optimizers (``Adam(fused=True)``, with or without ``capturable``) update parameters WITHOUT bumping
 # ``Tensor._version`` (measured: version unchanged across ``step()``), so the version counters alone cannot tell a stale
-# packing.  Every optimizer step - of any optimizer in the process - therefore advances this epoch, which is part of the stamp.
-_OPT_EPOCH = [0]
+# packing.  Every optimizer step therefore advances an epoch kept PER PARAMETER (only the parameters the stepping optimizer
+# owns: a frozen target network, or the critic while the actor steps, keeps its packings), and the epochs are part of the stamp.
+# Parameters are keyed by their storage address, which is what a packing was filled from.
+_PARAM_EPOCH = {}
 
 
-def _optimizer_stepped(*_args, **_kwargs):
-    _OPT_EPOCH[0] += 1
+def _optimizer_stepped(optimizer, *_args, **_kwargs):
+    for group in getattr(optimizer, "param_groups", ()):
+        for p in group.get("params", ()):
+            key = p.data_ptr()
+            _PARAM_EPOCH[key] = _PARAM_EPOCH.get(key, 0) + 1
 
 
 from torch.optim.optimizer import register_optimizer_step_post_hook as _register_post_hook  # noqa: E402
@@ -102,7 +107,7 @@ class PackCache:
 
     @staticmethod
     def _stamp(params, dtype):
-        return tuple((p.data_ptr(), p._version) for p in params) + (_OPT_EPOCH[0], dtype)
+        return tuple((p.data_ptr(), p._version, _PARAM_EPOCH.get(p.data_ptr(), 0)) for p in params) + (dtype,)
 
     @staticmethod
     def _fill(wc, bc, ws, bs, wt=None, b32=None):

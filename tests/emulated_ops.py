@@ -47,11 +47,12 @@ def colsum(x):
     return x.sum(0, dtype=torch.float32)
 
 
-def causal_linear_attention_fused(qkv, n_heads, eps=1e-6, impl=0):
+def causal_linear_attention_fused(qkv, n_heads, eps=1e-6, impl=0, key_mask=None):
     N, L, W = qkv.shape
     E = W // (3 * n_heads)
     q, k, v = (qkv[..., j * n_heads * E:(j + 1) * n_heads * E].reshape(N, L, n_heads, E).float() for j in range(3))
-    return ft.causal_linear_attention(q, k, v, eps=eps).reshape(N, L, n_heads * E).to(qkv.dtype)
+    klm = None if key_mask is None else key_mask.float()
+    return ft.causal_linear_attention(q, k, v, key_lengths_mask=klm, eps=eps).reshape(N, L, n_heads * E).to(qkv.dtype)
 
 
 def linattn_step(q, k, v, S, Z, eps=1e-6, **_kw):

@@ -348,7 +348,8 @@ def test_device_resident_memory_mirrors_reference_buffers(cpm, golden):
 
 def test_pack_cache_notices_fused_optimizer_steps(cpm):
     """torch's fused Adam rewrites parameters without bumping Tensor._version; the packed compute copies must still be
-    rebuilt after such a step (PackCache stamps carry a process-wide optimizer-step epoch)."""
+    rebuilt after such a step (PackCache stamps carry an optimizer-step epoch per parameter), while the packings of a model
+    that no optimizer touched - a frozen target network, the critic while the actor steps - stay valid."""
     from cpmusic.encoder import PackCache
     lin = torch.nn.Linear(8, 4)
     cache = PackCache()
@@ -359,6 +360,14 @@ def test_pack_cache_notices_fused_optimizer_steps(cpm):
     wc, bc = cache.get("k", [lin], torch.float32)[:2]
     assert not torch.equal(wc, w0)
     assert torch.equal(wc, lin.weight.detach()) and torch.equal(bc, lin.bias.detach())
+    # another model's optimizer stepping does not stale this cache: same stamp, no refill
+    other = torch.nn.Linear(8, 4)
+    stamp = cache._store["k"][0]
+    opt2 = torch.optim.Adam(other.parameters(), lr=0.1, fused=True)
+    other.weight.grad, other.bias.grad = torch.ones_like(other.weight), torch.ones_like(other.bias)
+    opt2.step()
+    cache.get("k", [lin], torch.float32)
+    assert cache._store["k"][0] == stamp
     # in-place refresh keeps the buffer (graphs captured over it stay valid), and invalidate() forces a refill
     ptr = wc.data_ptr()
     with torch.no_grad():
