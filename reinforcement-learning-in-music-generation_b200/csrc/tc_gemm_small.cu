@@ -193,7 +193,26 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
                     rraw[q] = (n0 + 8 * q + 8 <= a.N) ? *reinterpret_cast<const uint4 *>(a.R + (int64_t)row * a.ldr + n0 + 8 * q) : make_uint4(0u, 0u, 0u, 0u);
-                if (a.r_stats) rs = a.r_stats[row];
+                if (a.r_stats) {
+                    // LayerNorm(R) rebuilt NOW, while the UMMAs run; the value is rounded to bf16 (as the LayerNorm kernel's output
+                    // is), so it goes back into the same 16 registers without loss
+                    rs = a.r_stats[row];
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) {
+                        if (n0 + 8 * q + 8 > a.N) continue;
+                        const float4 g0 = __ldg(reinterpret_cast<const float4 *>(a.r_gamma + n0 + 8 * q)), g1 = __ldg(reinterpret_cast<const float4 *>(a.r_gamma + n0 + 8 * q + 4));
+                        const float4 b0 = __ldg(reinterpret_cast<const float4 *>(a.r_beta + n0 + 8 * q)), b1 = __ldg(reinterpret_cast<const float4 *>(a.r_beta + n0 + 8 * q + 4));
+                        const float gm[8] = {g0.x, g0.y, g0.z, g0.w, g1.x, g1.y, g1.z, g1.w}, bt[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                        uint32_t w4[4] = {rraw[q].x, rraw[q].y, rraw[q].z, rraw[q].w};
+#pragma unroll
+                        for (int j = 0; j < 4; ++j) {
+                            const float lo = (__uint_as_float(w4[j] << 16) - rs.x) * rs.y * gm[2 * j] + bt[2 * j];
+                            const float hi = (__uint_as_float(w4[j] & 0xFFFF0000u) - rs.x) * rs.y * gm[2 * j + 1] + bt[2 * j + 1];
+                            w4[j] = pack_bf16(lo, hi);
+                        }
+                        rraw[q] = make_uint4(w4[0], w4[1], w4[2], w4[3]);
+                    }
+                }
             }
         }
         mbar_wait(bar_done, 0);                          // the UMMAs ran after the producer's griddepcontrol.wait: ordered behind the chain
@@ -213,11 +232,6 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     const uint32_t w4[4] = {rq.x, rq.y, rq.z, rq.w};
 #pragma unroll
                     for (int j = 0; j < 4; ++j) { res[2 * j] = __uint_as_float(w4[j] << 16); res[2 * j + 1] = __uint_as_float(w4[j] & 0xFFFF0000u); }
-                    if (a.r_stats) {
-#pragma unroll
-                        for (int j = 0; j < 8; ++j)
-                            res[j] = bf16_round((res[j] - rs.x) * rs.y * __ldg(a.r_gamma + n0 + 8 * q + j) + __ldg(a.r_beta + n0 + 8 * q + j));
-                    }
                 }
 #pragma unroll
                 for (int j = 0; j < 4; ++j) {

@@ -35,7 +35,11 @@ for i in range(per):
     e, s_, d, a, c, st = (step[i, j] for j in range(6))
     gap = (d - step[i - 1, 5]) / 1e3 if i else float("nan")
     if i < 14 or i >= per - 3:
-        print(f"{i:4d} {int(step[i, 6]):5d} {int(step[i, 7]):5d} | {0:5.2f} {(s_ - e) / 1e3:6.2f} {(d - e) / 1e3:8.2f} {(a - e) / 1e3:9.2f} {(c - e) / 1e3:10.2f} {(st - e) / 1e3:7.2f} | gap {gap:6.2f}")
-    tot["dep->A"] += (a - d) / 1e3; tot["A->acc"] += (c - a) / 1e3; tot["acc->stored"] += (st - c) / 1e3
+        print(f"{i:4d} {int(step[i, 6]):5d} {int(step[i, 7]):5d} | {0:5.2f} {(s_ - e) / 1e3:6.2f} {(d - e) / 1e3:8.2f} {((a - e) / 1e3 if a > 0 else float("nan")):9.2f} {(c - e) / 1e3:10.2f} {(st - e) / 1e3:7.2f} | gap {gap:6.2f}")
+    if a > 0:                                            # K > 512 launches stream through the ring and do not stamp "A landed"
+        tot["dep->A"] += (a - d) / 1e3; tot["A->acc"] += (c - a) / 1e3
+    else:
+        tot["A->acc"] += (c - d) / 1e3
+    tot["acc->stored"] += (st - c) / 1e3
     if i: tot["gap"] += gap
 print("sums over the step (us):", {k: round(float(v), 1) for k, v in tot.items() if k != "entry->dep"})
