@@ -214,6 +214,10 @@ int cpm_gemm_tn(const void *dY, int64_t ldy, const void *X, int64_t ldx, float *
  * Reference loop being served: testing-no-type-cp.py:157-167 (forward_hidden(..., is_training=False) + forward_output). */
 int cpm_gemm_nt_small(const void *A, int64_t lda, const void *W, int64_t ldw, void *D, int64_t ldd, int M, int N, int K,
                       const float *bias, int epilogue, void *stream);
+/* cpm_gemm_nt_small[_ln] split a long K (>= 16 k-blocks of 64, an even number: linear2's K = 2048) in two over a thread-block
+ * cluster per output tile; the leader CTA adds the other slice's fp32 tile from its shared memory and runs the epilogue
+ * (deterministic).  0 switches the split off (A/B runs); default on. */
+int cpm_gemm_small_set_split(int on);
 /* Development aid: device log {uint64 count; uint64 stamps[capacity][8]} (zero-filled by the caller) to which block (0,0) of
  * every cpm_gemm_nt_small[_ln] launch appends %globaltimer stamps (kernel entry, set-up done, griddepcontrol.wait returned,
  * first activation block landed, accumulator ready, epilogue stored) and N, K.  The pointer is read at LAUNCH time, so it is

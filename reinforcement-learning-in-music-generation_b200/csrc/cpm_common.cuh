@@ -189,20 +189,33 @@ __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wa
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 extern int g_chain_pdl;
 template <typename... KArgs, typename... Args>
-inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+inline cudaError_t launch_chain_cluster(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, dim3 cluster, Args &&...args) {
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = grid;
     cfg.blockDim = block;
     cfg.dynamicSmemBytes = smem;
     cfg.stream = st;
-    cudaLaunchAttribute at[1];
+    cudaLaunchAttribute at[2];
+    int n = 0;
     if (g_chain_pdl) {
-        at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-        at[0].val.programmaticStreamSerializationAllowed = 1;
-        cfg.attrs = at;
-        cfg.numAttrs = 1;
+        at[n].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+        at[n].val.programmaticStreamSerializationAllowed = 1;
+        ++n;
     }
+    if (cluster.x * cluster.y * cluster.z > 1) {          // thread-block cluster (the K slices of one output tile)
+        at[n].id = cudaLaunchAttributeClusterDimension;
+        at[n].val.clusterDim.x = cluster.x;
+        at[n].val.clusterDim.y = cluster.y;
+        at[n].val.clusterDim.z = cluster.z;
+        ++n;
+    }
+    cfg.attrs = n ? at : nullptr;
+    cfg.numAttrs = n;
     return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_chain(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, Args &&...args) {
+    return launch_chain_cluster(kernel, grid, block, smem, st, dim3(1, 1, 1), static_cast<Args &&>(args)...);
 }
 
 inline int num_sms() {

@@ -70,18 +70,21 @@ struct SmallArgs {
     int timing_cap;
 };
 
-template <int EPI, bool FOLD = false, bool RESID = false>
+// SPLIT: the two halves of K as a cluster (1, 1, 2) per output tile; slice 1 drops its fp32 tile into a buffer behind slice 0's
+// ring (st.shared::cluster), one cluster barrier, slice 0 adds it and runs the epilogue.
+template <int EPI, bool FOLD = false, bool RESID = false, bool SPLIT = false>
 __global__ void __launch_bounds__(SG_THREADS, 2)
 gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW, const SmallArgs a) {
     extern __shared__ __align__(1024) uint8_t sm[];
     uint64_t *bar_full = reinterpret_cast<uint64_t *>(sm + SG_OFF_BAR), *bar_empty = bar_full + SG_NS, *bar_done = bar_empty + SG_NS;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_done + 1);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.x * SG_BN, m0 = blockIdx.y * SG_BM, KB = (a.K + 63) >> 6;
+    const int n0 = blockIdx.x * SG_BN, m0 = blockIdx.y * SG_BM, KB = SPLIT ? (((a.K + 63) >> 6) >> 1) : ((a.K + 63) >> 6);
+    const int kb0 = SPLIT ? (int)blockIdx.z * KB : 0;                  // SPLIT requires an even number of k-blocks
     __shared__ unsigned long long *s_log;
     if (a.timing && tid == 0) {
         s_log = nullptr;
-        if (blockIdx.x == 0 && blockIdx.y == 0) {
+        if (blockIdx.x == 0 && blockIdx.y == 0 && blockIdx.z == 0) {
             const unsigned long long slot = atomicAdd(&a.timing->count, 1ull);
             if (slot < (unsigned long long)a.timing_cap) { s_log = a.timing->stamps + slot * 8; s_log[0] = gtimer(); s_log[6] = (unsigned long long)a.N; s_log[7] = (unsigned long long)a.K; }
         }
@@ -113,17 +116,17 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                 uint64_t *bar = bar_full + (grouped ? (i / GRP) * GRP : i);
                 if (!grouped) mbar_expect_tx(bar, SG_STAGE);
                 else if (i % GRP == 0) mbar_expect_tx(bar, (uint32_t)min(GRP, KB - i) * SG_STAGE);
-                tma_load_2d(sm + i * SG_STAGE + SG_A_BYTES, &tmW, bar, i * 64, n0);
+                tma_load_2d(sm + i * SG_STAGE + SG_A_BYTES, &tmW, bar, (kb0 + i) * 64, n0);
             }
             griddep_wait();                              // the activations (and every buffer this kernel writes) belong to the chain
             if (logp) logp[2] = gtimer();
-            for (int i = 0; i < pre; ++i) tma_load_2d(sm + i * SG_STAGE, &tmA, bar_full + (grouped ? (i / GRP) * GRP : i), i * 64, m0);
+            for (int i = 0; i < pre; ++i) tma_load_2d(sm + i * SG_STAGE, &tmA, bar_full + (grouped ? (i / GRP) * GRP : i), (kb0 + i) * 64, m0);
             for (int i = pre; i < KB; ++i) {
                 const int s = i % SG_NS;
                 mbar_wait(bar_empty + s, ((i / SG_NS) - 1) & 1);
                 mbar_expect_tx(bar_full + s, SG_STAGE);
-                tma_load_2d(sm + s * SG_STAGE + SG_A_BYTES, &tmW, bar_full + s, i * 64, n0);
-                tma_load_2d(sm + s * SG_STAGE, &tmA, bar_full + s, i * 64, m0);
+                tma_load_2d(sm + s * SG_STAGE + SG_A_BYTES, &tmW, bar_full + s, (kb0 + i) * 64, n0);
+                tma_load_2d(sm + s * SG_STAGE, &tmA, bar_full + s, (kb0 + i) * 64, m0);
             }
         }
     } else if (warp == 5) {
@@ -221,7 +224,31 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         uint32_t r[32];
         tmem_ld32(tmem + ((uint32_t)(warp * 32) << 16), r);
         tmem_ld_wait();
-        if (lane < 16 && row < a.M) {
+        if (SPLIT) {
+            const uint32_t rank = cluster_ctarank();
+            uint8_t *part = sm + SG_SMEM;                  // 8 KB behind the ring and the barriers: slice 1's fp32 tile
+            if (rank == 1 && lane < 16) {
+                const uint32_t dst0 = mapa_u32(smem_u32(part) + (uint32_t)(16 * warp + lane) * 128u, 0);
+#pragma unroll
+                for (int q = 0; q < 8; ++q)
+                    asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(dst0 + 16 * q), "r"(r[4 * q]), "r"(r[4 * q + 1]), "r"(r[4 * q + 2]),
+                                 "r"(r[4 * q + 3])
+                                 : "memory");
+            }
+            cluster_sync_all();
+            if (rank == 0 && lane < 16) {
+                const uint4 *src = reinterpret_cast<const uint4 *>(part + (uint32_t)(16 * warp + lane) * 128u);
+#pragma unroll
+                for (int q = 0; q < 8; ++q) {
+                    const uint4 t = src[q];
+                    r[4 * q] = __float_as_uint(__uint_as_float(r[4 * q]) + __uint_as_float(t.x));
+                    r[4 * q + 1] = __float_as_uint(__uint_as_float(r[4 * q + 1]) + __uint_as_float(t.y));
+                    r[4 * q + 2] = __float_as_uint(__uint_as_float(r[4 * q + 2]) + __uint_as_float(t.z));
+                    r[4 * q + 3] = __float_as_uint(__uint_as_float(r[4 * q + 3]) + __uint_as_float(t.w));
+                }
+            }
+        }
+        if ((!SPLIT || cluster_ctarank() == 0) && lane < 16 && row < a.M) {
             __nv_bfloat16 *dst = a.D + (int64_t)row * a.ldd + n0;
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
@@ -256,6 +283,10 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
             }
         }
     }
+    if (SPLIT && warp >= 4) {                            // the producer / UMMA warps take part in the cluster barrier of the reduction
+        __syncwarp();
+        cluster_sync_all();
+    }
     tc_fence_before();
     __syncthreads();
     if (logp && tid == 0) logp[5] = gtimer();
@@ -265,19 +296,29 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
 SmallTiming *g_small_timing = nullptr;
 int g_small_timing_cap = 0;
 
+int g_small_split = 1;        // cpm_gemm_small_set_split(0): never split K (A/B runs)
+
 template <int EPI, bool FOLD = false, bool RESID = false>
 int launch_small(const CUtensorMap &tA, const CUtensorMap &tW, const SmallArgs &a, cudaStream_t st) {
     static bool attr = false;
     if (!attr) {
         cudaError_t e = cudaFuncSetAttribute(gemm_small_kernel<EPI, FOLD, RESID>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM);
+        if (e == cudaSuccess && !FOLD)
+            e = cudaFuncSetAttribute(gemm_small_kernel<EPI, false, RESID, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)SG_SMEM + 8192);
         if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_small shared-memory attribute: %s", cudaGetErrorString(e));
         attr = true;
     }
-    const dim3 grid((a.N + SG_BN - 1) / SG_BN, (a.M + SG_BM - 1) / SG_BM);
+    const int gx = (a.N + SG_BN - 1) / SG_BN, gy = (a.M + SG_BM - 1) / SG_BM, KB_all = (a.K + 63) / 64;
+    const dim3 grid(gx, gy);
     SmallArgs b = a;
     b.timing = g_small_timing;
     b.timing_cap = g_small_timing_cap;
-    cudaError_t e = launch_chain(gemm_small_kernel<EPI, FOLD, RESID>, grid, dim3(SG_THREADS), SG_SMEM, st, tA, tW, b);
+    cudaError_t e;
+    // long K on few output tiles (linear2: 64 CTAs x 128 small UMMAs x 384 KB of operands): two K slices per tile as a cluster
+    if (!FOLD && g_small_split && KB_all >= 16 && KB_all % 2 == 0 && 2 * gx * gy <= 2 * num_sms())
+        e = launch_chain_cluster(gemm_small_kernel<EPI, false, RESID, true>, dim3(gx, gy, 2), dim3(SG_THREADS), SG_SMEM + 8192, st, dim3(1, 1, 2), tA, tW, b);
+    else
+        e = launch_chain(gemm_small_kernel<EPI, FOLD, RESID>, grid, dim3(SG_THREADS), SG_SMEM, st, tA, tW, b);
     if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_small launch: %s", cudaGetErrorString(e));
     return CPM_OK;
 }
@@ -303,6 +344,11 @@ extern "C" int cpm_gemm_nt_small(const void *A, int64_t lda, const void *W, int6
     cudaStream_t st = (cudaStream_t)stream;
     if (epilogue == CPM_GEMM_EPI_GELU) return launch_small<CPM_GEMM_EPI_GELU>(tA, tW, a, st);
     return launch_small<CPM_GEMM_EPI_BIAS>(tA, tW, a, st);
+}
+
+extern "C" int cpm_gemm_small_set_split(int on) {
+    g_small_split = on ? 1 : 0;
+    return CPM_OK;
 }
 
 extern "C" int cpm_debug_small_timing(void *device_log, int capacity) {

@@ -223,3 +223,34 @@ def test_gemm_nt_small_layernorm_forms(cuda, cpm, shape, pdl):
     _assert_close_bf16(outg, torch.nn.functional.gelu(out.double().cpu()), "fold + gelu")
     assert (st[:, 0].cpu() - y.float().mean(1).cpu()).abs().max() < 1e-4
     assert ((st[:, 1].cpu() - torch.rsqrt(y.float().var(1, unbiased=False) + 1e-5).cpu()).abs() / st[:, 1].cpu()).max() < 1e-3
+
+
+@pytest.mark.parametrize("shape", [(256, 512, 2048), (70, 96, 2048), (300, 512, 4096), (256, 512, 1024)])
+def test_gemm_nt_small_split_k_cluster(cuda, cpm, shape):
+    """Long K on the token-step GEMM: two K slices per output tile as a thread-block cluster, the leader adds the other slice's
+    fp32 tile from its shared memory.  Against the fp64 product, against the unsplit kernel (same values up to fp32 summation
+    order: equal after bf16 rounding almost everywhere), identical from launch to launch, under PDL back to back."""
+    M, N, K = shape
+    gen = torch.Generator().manual_seed(11 * M + N + K)
+    a, w = _bf16((M, K), gen).to(cuda), _bf16((N, K), gen, 1.0 / math.sqrt(K)).to(cuda)
+    bias = torch.randn(N, generator=gen).to(cuda)
+    res = _bf16((M, N), gen).to(cuda)
+    ref = a.double().cpu() @ w.double().cpu().t() + bias.double().cpu()
+    lib = cpm._lib.load()
+    lib.cpm_gemm_small_set_split(0)
+    try:
+        unsplit = cpm.ops.gemm_nt_small(a, w, bias)
+    finally:
+        lib.cpm_gemm_small_set_split(1)
+    cpm.ops.set_chain_pdl(True)
+    try:
+        outs = [cpm.ops.gemm_nt_small(a, w, bias) for _ in range(6)]
+        r = cpm.ops.gemm_nt_small_ln(a, w, bias, resid=res)
+    finally:
+        cpm.ops.set_chain_pdl(False)
+    torch.cuda.synchronize()
+    for o in outs:
+        _assert_close_bf16(o, ref, f"split-K gemm_nt_small {shape}")
+        assert torch.equal(o, outs[0])
+    assert (outs[0] != unsplit).float().mean() < 0.02
+    _assert_close_bf16(r, outs[0].double().cpu() + res.double().cpu(), "split K + residual epilogue")
