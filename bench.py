@@ -36,10 +36,12 @@ SONGS_PER_GPU, ROLLOUT_LEN = 256, 1024
 # sequences per update minibatch (gradient accumulation over 256/MINIBATCH).  Measured on one B200: 64 -> 276 ms per update phase,
 # 128 -> 261 ms, 256 -> 254 ms but +36 ms of allocator churn outside it (63 GB of activations per model), so 128.
 MINIBATCH = int(os.environ.get("CPM_MINIBATCH", "128"))
-# critic update of iteration i under the rollout of i+1 (second stream).  Measured on B200: 333.6 k tokens/s vs 344.9 k sequential
-# (346.6 k with the rollout graph captured at high stream priority): the bulk kernels delay the rollout's dependent small kernels
-# by about as much as they save, and the in-situ attention timings suffer - off by default.
-OVERLAP_CRITIC = os.environ.get("CPM_OVERLAP_CRITIC", "0") == "1"
+# critic update of iteration i under the rollout of i+1 (second stream; the rollout reads only the actor, and its chain of small
+# dependent kernels leaves most of the GPU idle).  Round 1 (library GEMMs, 103 launches per token): 333.6 k tokens/s vs 344.9 k
+# sequential - off.  Round 2 (own kernels, 67 launches per token, rollout graph on a high-priority stream): 366 k vs 348 k - ON.
+# The in-situ roofline timing of the attention kernels leaves the overlapped stream out (its launches share the GPU with the
+# rollout); CPM_OVERLAP_CRITIC=0 gives the strictly sequential iteration.
+OVERLAP_CRITIC = os.environ.get("CPM_OVERLAP_CRITIC", "1") == "1"
 # DRAM bytes of one linear-attention fwd+bwd launch group measured with ncu (cold L2), keyed by the update minibatch shape
 # -> (bytes, the committed ncu log).  (64, 1024): fwd 117.5+6.8 (streaming prefix) + 231.8+41.8 (per-chunk output) MB, bwd 195.1+17.4
 # (streaming suffix) + 334.1+153.9 (main) MB.  (128, 1024): fwd 234.9+37.2 + 463.7+110.4 MB, bwd 390.1+48.8 + 668.0+354.6 MB.
@@ -244,6 +246,8 @@ class PPOIteration:
         self.init_dev = self.init_host.to(dev)
         self.phase_ms = {"rollout": 0.0, "update": 0.0}
         self.cstream = torch.cuda.Stream(device=dev)
+        if OVERLAP_CRITIC:
+            cpmusic.ops.KernelTimer.exclude_streams.add(self.cstream.cuda_stream)
         self.pending, self._inflight = None, None
         self.vstat = torch.zeros((), device=dev)
 

@@ -92,6 +92,7 @@ class KernelTimer:
     (bench.py's live roofline measurement).  Disabled by default; zero cost when off."""
     enabled = False
     events = {}
+    exclude_streams = set()          # cuda_stream handles whose launches are not timed (work overlapped with another stream's)
 
     @classmethod
     def start(cls):
@@ -108,7 +109,9 @@ class KernelTimer:
 
     @classmethod
     def span(cls, name):
-        return _Span(name) if cls.enabled else _NULL
+        if not cls.enabled or (cls.exclude_streams and torch.cuda.current_stream().cuda_stream in cls.exclude_streams):
+            return _NULL
+        return _Span(name)
 
 
 class _Span:
