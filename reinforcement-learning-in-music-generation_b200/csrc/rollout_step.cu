@@ -1,6 +1,6 @@
 // The recurrent token step of the rollout as ONE persistent cooperative kernel  (cpm_rollout_create / cpm_rollout_run).
 // OPT-IN (RolloutEngine(mode="persistent") / CPM_ROLLOUT_MODE=persistent): measured on B200 at 256 songs it runs a token step in
-// 700-760 us against 492 us for the default chain of 67 kernels (profiles/r02_summary.md, "persistent rollout step"); it is kept as
+// 700-760 us against 442 us for the default chain of 67 kernels (profiles/r02_summary.md, "persistent rollout step"); it is kept as
 // the one non-default rollout mode because it is complete, parity-tested, and the per-stage timeline it records
 // (cpm_debug_rollout_timing, tools/phase_timing_rollout.py) is the measurement that explains where a token step's time goes.
 //

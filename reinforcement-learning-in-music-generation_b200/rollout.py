@@ -10,7 +10,7 @@ Two executions of the step, same arithmetic:
   * ``mode="chain"`` (default): the step as 67 kernels of this library (small-M tcgen05 GEMMs with LayerNorm folded in and
     the GELU in linear1's epilogue, the recurrent state kernel, embedding gather, sampler) launched with programmatic
     dependent launch - each kernel's set-up and each GEMM's weight fetch overlap its predecessor's tail - and captured once in
-    a CUDA graph.  492 us per token step at 256 songs on B200.
+    a CUDA graph.  442 us per token step at 256 songs on B200.
   * ``mode="persistent"`` (opt-in, bf16 models with 64-wide heads; also CPM_ROLLOUT_MODE=persistent): ONE cooperative kernel
     for the whole rollout (csrc/rollout_step.cu, cpm_rollout_run): one CTA per SM, the 63 dependent stages of a token separated
     by a device-wide barrier, every CTA streaming the weight tiles of its own output tiles ahead of the barriers through a TMA
