@@ -357,6 +357,192 @@ __global__ void __launch_bounds__(WARPS * 32) masked_ce_bwd_row_kernel(const T *
     }
 }
 
+// ---------------------------------------------------------------- one THREAD per row (ld % 8 == 0, 16-byte aligned rows)
+// The warp-per-row kernels above spend ~2000 warp instructions per row and an eight-lanes-per-row variant still 440: narrow
+// segments leave most lanes of a cross-lane reduction idle; staging 32 rows per warp in shared memory removes the reductions
+// but leaves 8 warps per SM (profiles/r02_summary.md, section I).  Here every THREAD streams its own row from global memory in
+// 16-byte pieces (the 128-byte lines it touches stay in L1 for the 8 consecutive reads that consume them) and keeps ONE open
+// segment's running (max, sum, sum x) in registers with the online-softmax update - the segment layout is the same for every
+// row, so all 32 threads take the same branches at the same column: no shuffles, no divergence, no shared memory, full
+// occupancy.  About 90 warp instructions per row.
+template <typename V> __device__ __forceinline__ V tpr_pick(const V (&v)[CPM_MAX_ATTR], int a) {   // v[a], a warp-uniform
+    V r = v[0];
+#pragma unroll
+    for (int j = 1; j < CPM_MAX_ATTR; ++j) r = (a == j) ? v[j] : r;
+    return r;
+}
+template <typename V> __device__ __forceinline__ void tpr_put(V (&v)[CPM_MAX_ATTR], int a, V x) {
+#pragma unroll
+    for (int j = 0; j < CPM_MAX_ATTR; ++j) v[j] = (a == j) ? x : v[j];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) heads_logp_tpr_kernel(const T *__restrict__ logits, int64_t rows, int64_t ld, SegParams sp,
+                                                             const int64_t *__restrict__ tokens, float *__restrict__ logp,
+                                                             float *__restrict__ entropy) {
+    const int A = sp.n_attr;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const T *row = logits + r * ld;
+    auto emit = [&](int a, float m, float s, float sx) {
+        const float lse = m + __logf(s);
+        if (logp) {
+            const int tok = clamp_tok(tokens[r * A + a], sp.seg[a + 1] - sp.seg[a]);
+            logp[r * A + a] = to_f(row[sp.seg[a] + tok]) - lse;
+        }
+        if (entropy) entropy[r * A + a] = lse - sx / s;
+    };
+    if (entropy) tpr_row_stats<T, 2>(row, (int)ld, sp, A, emit); else tpr_row_stats<T, 1>(row, (int)ld, sp, A, emit);
+}
+
+// gradient chunks: out[k] = f(x[k], column) for k in [k0, k1) of the open segment
+template <typename F> __device__ __forceinline__ void tpr_apply(const float (&x)[8], float (&out)[8], int c0, int k0, int k1, F f) {
+    if (k0 == 0 && k1 == 8) {
+#pragma unroll
+        for (int k = 0; k < 8; ++k) out[k] = f(x[k], c0 + k);
+    } else {
+#pragma unroll
+        for (int k = 0; k < 8; ++k)
+            if (k >= k0 && k < k1) out[k] = f(x[k], c0 + k);
+    }
+}
+// second walk: writes all ld columns of the gradient row (zeros behind the last segment); open(a) loads segment a's parameters
+template <typename T, typename Open, typename F>
+__device__ __forceinline__ void tpr_row_grad(const T *__restrict__ row, T *__restrict__ drow, int ld, const SegParams &sp, int A, Open open, F f) {
+    const int width = sp.seg[A];
+    int a = 0, hi = sp.seg[1];
+    open(0);
+    RowStream<T> rs(row, ld);
+    constexpr int CPS = RowStream<T>::CPS;
+    for (int span = 0; span * CPS * 8 < ld; ++span) {
+        rs.advance(span);
+        auto body = [&](int c0, const float (&x)[8]) {
+            float out[8];
+#pragma unroll
+            for (int k = 0; k < 8; ++k) out[k] = 0.f;
+            int k0 = 0;
+            while (k0 < 8 && a < A && c0 < width) {
+                const int k1 = min(8, hi - c0);
+                tpr_apply(x, out, c0, k0, k1, f);
+                if (hi <= c0 + 8) {
+                    ++a;
+                    hi = a < A ? sp.seg[a + 1] : 0x7fffffff;
+                    if (a < A) open(a);
+                    k0 = k1;
+                } else {
+                    k0 = 8;
+                }
+            }
+            tpr_store8(drow + c0, out);
+        };
+        float x[8];
+#define CPM_TPR_CHUNK(J)                                                   \
+        if (J < CPS && (span * CPS + J) * 8 < ld) {                        \
+            rs.template chunk<(J < CPS ? J : 0)>(x);                       \
+            body((span * CPS + J) * 8, x);                                 \
+        }
+        CPM_TPR_CHUNK(0) CPM_TPR_CHUNK(1) CPM_TPR_CHUNK(2) CPM_TPR_CHUNK(3)
+        CPM_TPR_CHUNK(4) CPM_TPR_CHUNK(5) CPM_TPR_CHUNK(6) CPM_TPR_CHUNK(7)
+#undef CPM_TPR_CHUNK
+    }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) heads_logp_bwd_tpr_kernel(const T *__restrict__ logits, int64_t rows, int64_t ld, SegParams sp,
+                                                                 const int64_t *__restrict__ tokens, const float *__restrict__ glogp,
+                                                                 const float *__restrict__ gent, T *__restrict__ dlogits) {
+    const int A = sp.n_attr;
+    const int64_t r = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (r >= rows) return;
+    const T *row = logits + r * ld;
+    float lse[CPM_MAX_ATTR], hx[CPM_MAX_ATTR];
+#pragma unroll
+    for (int j = 0; j < CPM_MAX_ATTR; ++j) { lse[j] = 0.f; hx[j] = 0.f; }
+    auto emit = [&](int a, float m, float s, float sx) {
+        const float l = m + __logf(s);
+        tpr_put(lse, a, l);
+        tpr_put(hx, a, l - sx / s);
+    };
+    if (gent) tpr_row_stats<T, 2>(row, (int)ld, sp, A, emit); else tpr_row_stats<T, 1>(row, (int)ld, sp, A, emit);
+    float c_lse = 0.f, c_hx = 0.f, c_gl = 0.f, c_ge = 0.f;
+    int c_tok = 0;
+    auto open = [&](int a) {
+        c_lse = tpr_pick(lse, a);
+        c_hx = tpr_pick(hx, a);
+        c_gl = glogp ? glogp[r * A + a] : 0.f;
+        c_ge = gent ? gent[r * A + a] : 0.f;
+        c_tok = sp.seg[a] + clamp_tok(tokens[r * A + a], sp.seg[a + 1] - sp.seg[a]);
+    };
+    tpr_row_grad(row, dlogits + r * ld, (int)ld, sp, A, open, [&](float x, int i) {
+        const float lp = x - c_lse, p = tpr_ex2(lp * TPR_LOG2E);
+        return c_gl * ((i == c_tok ? 1.f : 0.f) - p) - c_ge * p * (lp + c_hx);
+    });
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) masked_ce_fwd_tpr_kernel(const T *__restrict__ logits, int64_t T_, int64_t ld, SegParams sp,
+                                                                const int64_t *__restrict__ targets, const float *__restrict__ mask,
+                                                                float *__restrict__ loss_num, float *__restrict__ mask_sum,
+                                                                float *__restrict__ lse_out) {
+    __shared__ float sacc[CPM_MAX_ATTR + 1];
+    const int A = sp.n_attr, lane = threadIdx.x & 31;
+    if (threadIdx.x <= CPM_MAX_ATTR) sacc[threadIdx.x] = 0.f;
+    __syncthreads();
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live = t < T_;
+    const int64_t tt = live ? t : T_ - 1;                  // dead threads walk the last row (uniform control flow) and add nothing
+    const T *row = logits + tt * ld;
+    const float m_ = live ? mask[tt] : 0.f;
+    float acc[CPM_MAX_ATTR];
+#pragma unroll
+    for (int j = 0; j < CPM_MAX_ATTR; ++j) acc[j] = 0.f;
+    tpr_row_stats<T, 1>(row, (int)ld, sp, A, [&](int a, float m, float s, float) {
+        const float lse = m + __logf(s);
+        if (live && lse_out) lse_out[tt * A + a] = lse;
+        const int tg = clamp_tok(targets[tt * A + a], sp.seg[a + 1] - sp.seg[a]);
+        tpr_put(acc, a, m_ * (lse - to_f(row[sp.seg[a] + tg])));
+    });
+#pragma unroll
+    for (int j = 0; j < CPM_MAX_ATTR; ++j) {
+        if (j < A) {
+            const float v = warp_sum(acc[j]);
+            if (lane == 0) atomicAdd(&sacc[j], v);
+        }
+    }
+    const float mm = warp_sum(m_);
+    if (lane == 0) atomicAdd(&sacc[CPM_MAX_ATTR], mm);
+    __syncthreads();
+    if (threadIdx.x < A) atomicAdd(&loss_num[threadIdx.x], sacc[threadIdx.x]);
+    if (threadIdx.x == CPM_MAX_ATTR && mask_sum) atomicAdd(mask_sum, sacc[CPM_MAX_ATTR]);
+}
+
+template <typename T>
+__global__ void __launch_bounds__(128) masked_ce_bwd_tpr_kernel(const T *__restrict__ logits, int64_t T_, int64_t ld, SegParams sp,
+                                                                const int64_t *__restrict__ targets, const float *__restrict__ mask,
+                                                                const float *__restrict__ lse_in, const float *__restrict__ gscale,
+                                                                const float *__restrict__ denom, T *__restrict__ dlogits) {
+    const int A = sp.n_attr;
+    const int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= T_) return;
+    const T *row = logits + t * ld;
+    const float mk = mask[t] * (1.f / denom[0]);
+    float c_lse = 0.f, c_coef = 0.f;
+    int c_tg = 0;
+    auto open = [&](int a) {
+        c_lse = lse_in[t * A + a];
+        c_coef = gscale[a] * mk;
+        c_tg = sp.seg[a] + clamp_tok(targets[t * A + a], sp.seg[a + 1] - sp.seg[a]);
+    };
+    tpr_row_grad(row, dlogits + t * ld, (int)ld, sp, A, open, [&](float x, int i) {
+        return c_coef == 0.f ? 0.f : c_coef * (tpr_ex2((x - c_lse) * TPR_LOG2E) - (i == c_tg ? 1.f : 0.f));
+    });
+}
+
+inline bool tpr_path_ok(const SegParams &sp, int64_t ld, const void *p0, const void *p1) {
+    return sp.seg[0] == 0 && ld % 8 == 0 && aligned16(p0) && (!p1 || aligned16(p1));
+}
+inline int tpr_grid(int64_t rows) { return (int)((rows + 127) / 128); }
+
 inline bool row_path_ok(const SegParams &sp, int64_t ld, const void *p0, const void *p1) {
     return sp.seg[0] == 0 && sp.seg[sp.n_attr] <= MAX_SEG && ld % 8 == 0 && ld <= MAX_SEG && aligned16(p0) && (!p1 || aligned16(p1));
 }
@@ -417,6 +603,10 @@ int cpm_heads_logp(const void *logits, int64_t rows, int64_t ld_logits, const in
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
     if (rc) return rc;
     if (rows <= 0) return rows == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "heads_logp: rows=%lld", (long long)rows);
+    if (tpr_path_ok(sp, ld_logits, logits, nullptr)) {
+        DISPATCH_DTYPE(dtype, heads_logp_tpr_kernel<T><<<tpr_grid(rows), 128, 0, (cudaStream_t)stream>>>((const T *)logits, rows, ld_logits, sp, tokens, logp, entropy));
+        return check_launch("heads_logp");
+    }
     if (row_path_ok(sp, ld_logits, logits, nullptr)) {
         DISPATCH_DTYPE(dtype, heads_logp_row_kernel<T><<<warp_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
                                   (const T *)logits, rows, ld_logits, sp, tokens, logp, entropy));
@@ -434,6 +624,10 @@ int cpm_heads_logp_bwd(const void *logits, int64_t rows, int64_t ld_logits, cons
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
     if (rc) return rc;
     if (rows <= 0) return rows == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "heads_logp_bwd: rows=%lld", (long long)rows);
+    if (tpr_path_ok(sp, ld_logits, logits, dlogits)) {
+        DISPATCH_DTYPE(dtype, heads_logp_bwd_tpr_kernel<T><<<tpr_grid(rows), 128, 0, (cudaStream_t)stream>>>((const T *)logits, rows, ld_logits, sp, tokens, glogp, gentropy, (T *)dlogits));
+        return check_launch("heads_logp_bwd");
+    }
     if (row_path_ok(sp, ld_logits, logits, dlogits)) {
         DISPATCH_DTYPE(dtype, heads_logp_bwd_row_kernel<T><<<warp_grid(rows), WARPS * 32, 0, (cudaStream_t)stream>>>(
                                   (const T *)logits, rows, ld_logits, sp, tokens, glogp, gentropy, (T *)dlogits));
@@ -451,6 +645,10 @@ int cpm_masked_ce_fwd(const void *logits, int64_t T_, int64_t ld_logits, const i
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
     if (rc) return rc;
     if (T_ <= 0) return T_ == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "masked_ce_fwd: T=%lld", (long long)T_);
+    if (tpr_path_ok(sp, ld_logits, logits, nullptr)) {
+        DISPATCH_DTYPE(dtype, masked_ce_fwd_tpr_kernel<T><<<tpr_grid(T_), 128, 0, (cudaStream_t)stream>>>((const T *)logits, T_, ld_logits, sp, targets, mask, loss_num, mask_sum, lse));
+        return check_launch("masked_ce_fwd");
+    }
     if (row_path_ok(sp, ld_logits, logits, nullptr)) {
         DISPATCH_DTYPE(dtype, masked_ce_fwd_row_kernel<T><<<warp_grid(T_), WARPS * 32, 0, (cudaStream_t)stream>>>(
                                   (const T *)logits, T_, ld_logits, sp, targets, mask, loss_num, mask_sum, lse));
@@ -469,6 +667,10 @@ int cpm_masked_ce_bwd(const void *logits, int64_t T_, int64_t ld_logits, const i
     int rc = fill_seg(sp, seg_host, n_attr, ld_logits, nullptr, nullptr);
     if (rc) return rc;
     if (T_ <= 0) return T_ == 0 ? CPM_OK : fail(CPM_ERR_BAD_SHAPE, "masked_ce_bwd: T=%lld", (long long)T_);
+    if (tpr_path_ok(sp, ld_logits, logits, dlogits)) {
+        DISPATCH_DTYPE(dtype, masked_ce_bwd_tpr_kernel<T><<<tpr_grid(T_), 128, 0, (cudaStream_t)stream>>>((const T *)logits, T_, ld_logits, sp, targets, mask, lse, gscale, denom, (T *)dlogits));
+        return check_launch("masked_ce_bwd");
+    }
     if (row_path_ok(sp, ld_logits, logits, dlogits)) {
         DISPATCH_DTYPE(dtype, masked_ce_bwd_row_kernel<T><<<warp_grid(T_), WARPS * 32, 0, (cudaStream_t)stream>>>(
                                   (const T *)logits, T_, ld_logits, sp, targets, mask, lse, gscale, denom, (T *)dlogits));
