@@ -24,6 +24,7 @@
 // over clusters (one (tile, split) work item per cluster) and the partial tiles are accumulated into the fp32 gradient with
 // vector red.global.add - which is also the gradient ACCUMULATION across micro-batches.  The bias gradient comes from the
 // same UMMA stream: one extra N = 16 instruction per K step against a constant tile of ones (db = dY^T . 1).
+#include <stdlib.h>
 #include "cpm_common.cuh"
 #include "tc_common.cuh"
 
@@ -67,7 +68,7 @@ __device__ __forceinline__ void gemm_setup(uint8_t *sm, uint64_t *bars, uint32_t
     cluster_sync_all();                                   // both CTAs of the pair are resident before anything touches the peer
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-        for (int s = 0; s < GM_NS; ++s) { mbar_init(bar_full + s, 2); mbar_init(bar_empty + s, 1); }     // full: one arrival per producer
+        for (int s = 0; s < GM_NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }     // full: the leader's expect_tx is the only arrival
         for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, 8); }      // tempty: 4 warps x 2 CTAs
         fence_barrier_init();
         tma_prefetch_desc(m0);
@@ -171,8 +172,9 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int row_a = mb * 256 + (int)rank * 128, row_b = nb * 256 + (int)rank * 128;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(bar_empty + s, ph ^ 1);
+                    // only the leader arrives (announcing the bytes of both CTAs): a remote arrive per K block is a release at cluster
+                    // scope and stalled the peer's producer for longer than the K block's UMMAs take (tools/probes/tma_ingest.cu)
                     if (rank == 0) mbar_expect_tx(bar_full + s, 2 * GM_STAGE);
-                    else mbar_arrive_cluster(full0 + 8 * s);
                     tma_load_2d_2sm(sm + s * GM_STAGE, &tmA, full0 + 8 * s, kb * 64, row_a);
                     tma_load_2d_2sm(sm + s * GM_STAGE + GM_A_BYTES, &tmB, full0 + 8 * s, kb * 64, row_b);
                     if (++s == GM_NS) { s = 0; ph ^= 1; }
@@ -277,17 +279,23 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // =====================================================================================================================
 constexpr int G2_THREADS = 384;                                              // warps 0-3 as above, warps 4-11 epilogue
 constexpr uint32_t G2_OFF_STG = 196608, G2_OFF_BAR = 229376, G2_SMEM = G2_OFF_BAR + 256;
-constexpr int WD_NS = 4;                                                     // wide: ring 4 x (A 16 KB + B 32 KB) | staging
+constexpr int WD_NS = 4;                                                     // weight gradient: ring 4 x (A 16 KB + B 32 KB)
 constexpr uint32_t WD_STAGE = 49152;
+// wide forward tile: ring 3 x 48 KB | staging 8 warps x 2 x 4 KB (the TMA store of one 64-column chunk reads its buffer while the
+// next chunk is converted into the other one)
+constexpr int WN_NS = 3;
+constexpr uint32_t WN_OFF_STG = WN_NS * WD_STAGE, WN_OFF_BAR = WN_OFF_STG + 65536, WN_SMEM = WN_OFF_BAR + 256;
 
 // one 64-column chunk of this warp's 32 accumulator rows: TMEM -> epilogue -> swizzled staging -> TMA store
 template <int EPI>
 __device__ __forceinline__ void epilogue_chunk(uint32_t taddr, const GemmNtArgs &a, const CUtensorMap *tmD, const CUtensorMap *tmD2, int grow0,
                                                int n0, int lane, uint8_t *stg, uint64_t rng_offset, bool last_read, uint32_t tempty_addr) {
+    // `stg` is this chunk's 4 KB staging buffer: the caller alternates between two, so only the store before the previous one
+    // must have finished reading (the GELU epilogue stores twice from one buffer and drains it completely)
     const bool live = n0 < a.N && grow0 < a.M;
     uint32_t r[32], o0[16], o1[16], g0[16];
     if (live) {
-        if (lane == 0) tma_store_wait_read0();
+        if (lane == 0) { if (EPI == CPM_GEMM_EPI_GELU) tma_store_wait_read0(); else asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
         __syncwarp();
     }
 #pragma unroll
@@ -333,8 +341,8 @@ __device__ __forceinline__ void g2_setup(uint8_t *sm, uint64_t *bars, int n_full
     cluster_sync_all();
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
-        for (int s = 0; s < n_full_a; ++s) { mbar_init(bars + s, 2); mbar_init(bars + 8 + s, 1); }
-        for (int s = 0; s < n_ring; ++s) { mbar_init(bars + 16 + s, 2); mbar_init(bars + 20 + s, 1); }
+        for (int s = 0; s < n_full_a; ++s) { mbar_init(bars + s, 1); mbar_init(bars + 8 + s, 1); }
+        for (int s = 0; s < n_ring; ++s) { mbar_init(bars + 16 + s, 1); mbar_init(bars + 20 + s, 1); }      // full: the leader's expect_tx only (see below)
         for (int s = 0; s < 2; ++s) { mbar_init(bars + 24 + s, 1); mbar_init(bars + 26 + s, tempty_count); }
         fence_barrier_init();
         tma_prefetch_desc(m0);
@@ -353,14 +361,14 @@ __global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(G2_THREADS, 1)
 gemm_nt_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
                     const __grid_constant__ CUtensorMap tmD2, const GemmNtArgs a) {
     extern __shared__ __align__(1024) uint8_t sm[];
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + G2_OFF_BAR);
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + WN_OFF_BAR);
     uint64_t *bar_full = bars + 16, *bar_empty = bars + 20, *bar_tfull = bars + 24, *bar_tempty = bars + 26;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28);
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const uint32_t rank = cluster_ctarank();
     const int pair = blockIdx.x >> 1, npairs = gridDim.x >> 1;
     const int MB = (a.M + 255) >> 8, KB = (a.K + 63) >> 6, NB2 = (a.N + 511) >> 9, tiles = MB * NB2;     // 256 x 512 tiles, N tile fastest
-    g2_setup(sm, bars, 0, WD_NS, 8, tmem_slot, tid, warp, &tmA, &tmB, &tmD, EPI == CPM_GEMM_EPI_GELU ? &tmD2 : nullptr);
+    g2_setup(sm, bars, 0, WN_NS, 8, tmem_slot, tid, warp, &tmA, &tmB, &tmD, EPI == CPM_GEMM_EPI_GELU ? &tmD2 : nullptr);
     const uint32_t tmem = *tmem_slot;
 
     if (warp == 0) {
@@ -371,13 +379,12 @@ gemm_nt_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                 const int row_a = (t / NB2) * 256 + (int)rank * 128, row_b = (t % NB2) * 512 + (int)rank * 128;
                 for (int kb = 0; kb < KB; ++kb) {
                     mbar_wait(bar_empty + s, ph ^ 1);
-                    if (rank == 0) mbar_expect_tx(bar_full + s, 2 * WD_STAGE);
-                    else mbar_arrive_cluster(full0 + 8 * s);
+                    if (rank == 0) mbar_expect_tx(bar_full + s, 2 * WD_STAGE);          // the leader alone arrives, for both CTAs' bytes
                     uint8_t *st = sm + s * WD_STAGE;
                     tma_load_2d_2sm(st, &tmA, full0 + 8 * s, kb * 64, row_a);
                     tma_load_2d_2sm(st + GM_A_BYTES, &tmB, full0 + 8 * s, kb * 64, row_b);
                     tma_load_2d_2sm(st + 2 * GM_A_BYTES, &tmB, full0 + 8 * s, kb * 64, row_b + 256);
-                    if (++s == WD_NS) { s = 0; ph ^= 1; }
+                    if (++s == WN_NS) { s = 0; ph ^= 1; }
                 }
             }
         }
@@ -400,7 +407,7 @@ gemm_nt_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
                         mma_ss_2sm(tmem + 256, dA + 2 * k, dB1 + 2 * k, IDESC_NT, acc);
                     }
                     mma_commit_2sm(bar_empty + s, 3);
-                    if (++s == WD_NS) { s = 0; ph ^= 1; }
+                    if (++s == WN_NS) { s = 0; ph ^= 1; }
                 }
                 mma_commit_2sm(bar_tfull, 3);
             }
@@ -408,7 +415,8 @@ gemm_nt_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     } else if (warp >= 4) {
         // ---- epilogue: lane quarter q, slab ch (columns 256 ch ..): four 64-column chunks per warp and tile
         const int q = warp & 3, ch = (warp - 4) >> 2;
-        uint8_t *stg = sm + G2_OFF_STG + (warp - 4) * 4096;
+        uint8_t *stg = sm + WN_OFF_STG + (warp - 4) * 8192;
+        uint32_t buf = 0;
         const uint32_t tempty0 = mapa_u32(smem_u32(bar_tempty), 0);
         const uint64_t rng_offset = rng_off(a.rng_offset, a.rng_base);
         uint32_t ti = 0;
@@ -418,8 +426,165 @@ gemm_nt_wide_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + ch * 256;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c)
-                epilogue_chunk<EPI>(tbase + c * 64, a, &tmD, &tmD2, grow0, ncol0 + c * 64, lane, stg, rng_offset, c == 3, tempty0 + 8 * ch);
+            for (int c = 0; c < 4; ++c) {
+                epilogue_chunk<EPI>(tbase + c * 64, a, &tmD, &tmD2, grow0, ncol0 + c * 64, lane, stg + (EPI == CPM_GEMM_EPI_GELU ? 0u : buf * 4096u),
+                                    rng_offset, c == 3, tempty0 + 8 * ch);
+                if (ncol0 + c * 64 < a.N && grow0 < a.M) buf ^= 1;          // a chunk that stored: the next one takes the other buffer
+            }
+        }
+        if (lane == 0) tma_store_wait_all0();
+    }
+    tc_fence_before();
+    cluster_sync_all();
+    if (warp == 2) tmem_dealloc_2sm<512>(tmem);
+}
+
+// =====================================================================================================================
+// Wide tile, bias epilogue, EARLY accumulator release.  The kernel above keeps the single 512-column accumulator busy for the
+// whole epilogue (about 4 us per tile against 7 us of UMMAs at K = 512): each of its 8 epilogue warps converts, stages and
+// TMA-stores chunk after chunk and hands the tensor memory back after its last read.  Here 16 epilogue warps (four per TMEM
+// lane quarter, 128 columns each) first drain their part of the accumulator into 64 registers of packed bf16 (bias added on the
+// way) and release the tensor memory - the next tile's UMMAs start then - and only afterwards swizzle the parked values
+// into the staging buffer and store them.
+// =====================================================================================================================
+constexpr int G3_THREADS = 640;                                              // warps 0-3 as above, warps 4-19 epilogue
+
+// PAIRS = 2: a cluster of FOUR CTAs = two pairs on neighbouring 256-row M tiles of the same 512-column N tile.  The B operand is
+// the same for both pairs, so every CTA fetches only ONE of its two 128-row B slab halves and multicasts it to its counterpart
+// in the other pair: 64 KB instead of 96 KB leave L2 per pair and K block (262 flop per L2 byte; the 2-CTA kernels saturate at
+// about 5.3 TB/s of L2 -> shared-memory traffic, profiles/r02_summary.md section B).  A ring stage is free when BOTH pairs'
+// UMMAs have retired (their commits are multicast to all four CTAs), so the two pairs walk the K loop in lock step.
+template <int PAIRS>
+__global__ void __cluster_dims__(2 * PAIRS, 1, 1) __launch_bounds__(G3_THREADS, 1)
+gemm_nt_wide_bias_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const __grid_constant__ CUtensorMap tmD,
+                         const GemmNtArgs a) {
+    extern __shared__ __align__(1024) uint8_t sm[];
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sm + WN_OFF_BAR);
+    uint64_t *bar_full = bars + 16, *bar_empty = bars + 20, *bar_tfull = bars + 24, *bar_tempty = bars + 26;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bars + 28);
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const uint32_t crank = cluster_ctarank(), rank = crank & 1u, pr = crank >> 1, lead = crank & ~1u;      // rank inside the pair; pair; leader CTA
+    const int cl = blockIdx.x / (2 * PAIRS), ncl = gridDim.x / (2 * PAIRS);
+    const int MBS = (a.M + 256 * PAIRS - 1) / (256 * PAIRS), KB = (a.K + 63) >> 6, NB2 = (a.N + 511) >> 9, tiles = MBS * NB2;
+    cluster_sync_all();
+    if (tid == 0) {
+        if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
+        for (int s = 0; s < WN_NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, PAIRS); }      // full: the leader's expect_tx is the only arrival
+        mbar_init(bar_tfull, 1);
+        for (int s = 0; s < 2; ++s) mbar_init(bar_tempty + s, 16);            // 8 warps x 2 CTAs per 256-column slab
+        fence_barrier_init();
+        tma_prefetch_desc(&tmA);
+        tma_prefetch_desc(&tmB);
+        tma_prefetch_desc(&tmD);
+    }
+    if (warp == 2) tmem_alloc_2sm<512>(tmem_slot);
+    tc_fence_before();
+    cluster_sync_all();
+    tc_fence_after();
+    const uint32_t tmem = *tmem_slot;
+
+    if (warp == 0) {
+        if (lane == 0) {                                   // ---- TMA producer
+            const uint32_t full_lead = mapa_u32(smem_u32(bar_full), lead);
+            const uint16_t mc_mask = (uint16_t)((1u << rank) | (1u << (rank + 2)));    // this CTA and its counterpart in the other pair
+            uint32_t s = 0, ph = 0;
+            for (int t = cl; t < tiles; t += ncl) {
+                const int row_a = ((t / NB2) * PAIRS + (int)pr) * 256 + (int)rank * 128, row_b = (t % NB2) * 512 + (int)rank * 128;
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar_empty + s, ph ^ 1);
+                    // The leader announces the bytes of BOTH CTAs; the peer does not arrive at all (its bytes may land first - the
+                    // transaction count then runs negative until the leader's expect_tx, the phase cannot complete before that
+                    // arrival).  A remote arrive per K block is a release at cluster scope: it stalled the peer's producer for
+                    // longer than a K block's UMMAs take (tools/probes/tma_ingest.cu).
+                    if (rank == 0) mbar_expect_tx(bar_full + s, 2 * WD_STAGE);
+                    uint8_t *st = sm + s * WD_STAGE;
+                    tma_load_2d_2sm(st, &tmA, full_lead + 8 * s, kb * 64, row_a);
+                    if (PAIRS == 1) {
+                        tma_load_2d_2sm(st + GM_A_BYTES, &tmB, full_lead + 8 * s, kb * 64, row_b);
+                        tma_load_2d_2sm(st + 2 * GM_A_BYTES, &tmB, full_lead + 8 * s, kb * 64, row_b + 256);
+                    } else {                                // slab `pr` for both pairs
+                        tma_load_2d_2sm_mc(st + GM_A_BYTES + pr * GM_A_BYTES, &tmB, full_lead + 8 * s, mc_mask, kb * 64, row_b + 256 * (int)pr);
+                    }
+                    if (++s == WN_NS) { s = 0; ph ^= 1; }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        if (rank == 0 && lane == 0) {                      // ---- UMMA issuer (the leader of each pair)
+            const uint16_t pair_mask = (uint16_t)(3u << (2 * pr)), all_mask = (uint16_t)((1u << (2 * PAIRS)) - 1u);
+            uint32_t s = 0, ph = 0, ti = 0;
+            for (int t = cl; t < tiles; t += ncl, ++ti) {
+                mbar_wait(bar_tempty + 0, (ti & 1) ^ 1);
+                mbar_wait(bar_tempty + 1, (ti & 1) ^ 1);
+                tc_fence_after();
+                for (int kb = 0; kb < KB; ++kb) {
+                    mbar_wait(bar_full + s, ph);
+                    tc_fence_after();
+                    const uint32_t base = smem_u32(sm + s * WD_STAGE);
+                    const uint64_t dA = smem_desc_sw128(base), dB0 = smem_desc_sw128(base + GM_A_BYTES), dB1 = smem_desc_sw128(base + 2 * GM_A_BYTES);
+#pragma unroll
+                    for (int k = 0; k < 4; ++k) {
+                        const uint32_t acc = (kb > 0 || k > 0) ? 1u : 0u;
+                        mma_ss_2sm(tmem, dA + 2 * k, dB0 + 2 * k, IDESC_NT, acc);
+                        mma_ss_2sm(tmem + 256, dA + 2 * k, dB1 + 2 * k, IDESC_NT, acc);
+                    }
+                    mma_commit_2sm(bar_empty + s, all_mask);   // every CTA that writes into this stage anywhere in the cluster
+                    if (++s == WN_NS) { s = 0; ph ^= 1; }
+                }
+                mma_commit_2sm(bar_tfull, pair_mask);
+            }
+        }
+    } else if (warp >= 4) {
+        // ---- epilogue: lane quarter q, column group cg (columns 128 cg .. 128 cg + 127 of the tile)
+        const int q = warp & 3, cg = (warp - 4) >> 2;
+        uint8_t *stg = sm + WN_OFF_STG + (warp - 4) * 4096;
+        const uint32_t tempty_lead = mapa_u32(smem_u32(bar_tempty), lead);
+        uint32_t ti = 0;
+        for (int t = cl; t < tiles; t += ncl, ++ti) {
+            const int grow0 = ((t / NB2) * PAIRS + (int)pr) * 256 + (int)rank * 128 + q * 32, ncol0 = (t % NB2) * 512 + cg * 128;
+            mbar_wait(bar_tfull, ti & 1);
+            tc_fence_after();
+            const uint32_t tbase = tmem + ((uint32_t)(q * 32) << 16) + cg * 128;
+            uint32_t pk[64];                                // this thread's row: 128 columns of packed bf16
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                uint32_t r[16];
+                tmem_ld16(tbase + 16 * i, r);
+                tmem_ld_wait();
+                const int n0 = ncol0 + 16 * i;
+                if (a.bias) {
+#pragma unroll
+                    for (int j = 0; j < 16; j += 4) {
+                        if (n0 + j + 4 <= a.N) {
+                            const float4 b = __ldg(reinterpret_cast<const float4 *>(a.bias + n0 + j));
+                            r[j] = __float_as_uint(__uint_as_float(r[j]) + b.x);
+                            r[j + 1] = __float_as_uint(__uint_as_float(r[j + 1]) + b.y);
+                            r[j + 2] = __float_as_uint(__uint_as_float(r[j + 2]) + b.z);
+                            r[j + 3] = __float_as_uint(__uint_as_float(r[j + 3]) + b.w);
+                        }
+                    }
+                }
+#pragma unroll
+                for (int j = 0; j < 8; ++j) pk[8 * i + j] = pack_bf16(__uint_as_float(r[2 * j]), __uint_as_float(r[2 * j + 1]));
+            }
+            tc_fence_before();                               // the accumulator columns are read: the next tile's UMMAs may overwrite them
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(tempty_lead + 8 * (cg >> 1));
+#pragma unroll
+            for (int c = 0; c < 2; ++c) {
+                const int n0 = ncol0 + 64 * c;
+                if (n0 < a.N && grow0 < a.M) {              // warp-uniform
+                    if (lane == 0) tma_store_wait_read0();   // the previous store has read the staging buffer
+                    __syncwarp();
+#pragma unroll
+                    for (int ch = 0; ch < 8; ++ch)
+                        *reinterpret_cast<uint4 *>(stg + sw128_off(lane, ch)) =
+                            make_uint4(pk[32 * c + 4 * ch], pk[32 * c + 4 * ch + 1], pk[32 * c + 4 * ch + 2], pk[32 * c + 4 * ch + 3]);
+                    fence_proxy_async();
+                    __syncwarp();
+                    if (lane == 0) { tma_store_2d(&tmD, stg, n0, grow0); tma_store_commit(); }
+                }
+            }
         }
         if (lane == 0) tma_store_wait_all0();
     }
@@ -459,8 +624,7 @@ gemm_tn_kernel(const __grid_constant__ CUtensorMap tmY, const __grid_constant__ 
             uint32_t s = 0, ph = 0;
             for (int kb = kb0; kb < kb1; ++kb) {
                 mbar_wait(bar_empty + s, ph ^ 1);
-                if (rank == 0) mbar_expect_tx(bar_full + s, 2 * WD_STAGE);
-                else mbar_arrive_cluster(full0 + 8 * s);
+                if (rank == 0) mbar_expect_tx(bar_full + s, 2 * WD_STAGE);              // the leader alone arrives, for both CTAs' bytes
                 uint8_t *st = sm + s * WD_STAGE;
                 tma_load_2d_2sm(st, &tmY, full0 + 8 * s, col_y, kb * 64);
                 tma_load_2d_2sm(st + 8192, &tmY, full0 + 8 * s, col_y + 64, kb * 64);
@@ -529,6 +693,8 @@ int set_smem(K kernel, const char *name) {
 }
 
 int g_gemm_mode = 0;          // 0 auto | 1 stream | 3 wide   (cpm_gemm_set_mode: A/B measurements)
+const bool g_gemm_late_release = getenv("CPM_GEMM_LATE_RELEASE") != nullptr;      // A/B: the 8-warp epilogue that holds the accumulator
+const bool g_gemm_no_multicast = getenv("CPM_GEMM_NO_MULTICAST") != nullptr;      // A/B: pairs fetch all of B themselves
 
 template <int EPI>
 int launch_nt(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &tD, const CUtensorMap &tD2, const GemmNtArgs &a, cudaStream_t st) {
@@ -536,20 +702,48 @@ int launch_nt(const CUtensorMap &tA, const CUtensorMap &tB, const CUtensorMap &t
     if (!attr) {
         int rc = set_smem(gemm_nt_kernel<EPI>, "gemm_nt");
         if (rc) return rc;
-        cudaError_t e = cudaFuncSetAttribute(gemm_nt_wide_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)G2_SMEM);
+        cudaError_t e = cudaFuncSetAttribute(gemm_nt_wide_kernel<EPI>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WN_SMEM);
         if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_nt shared-memory attribute: %s", cudaGetErrorString(e));
         attr = true;
     }
-    const int MB = (a.M + 255) / 256, NB = (a.N + 255) / 256, NB2 = (a.N + 511) / 512, max_pairs = num_sms() / 2;
+    const int MB = (a.M + 255) / 256, NB = (a.N + 255) / 256, NB2 = (a.N + 511) / 512;
+    static const int pair_cap = getenv("CPM_GEMM_MAX_PAIRS") ? atoi(getenv("CPM_GEMM_MAX_PAIRS")) : 0;      // A/B: leave SMs idle
+    const int max_pairs = pair_cap > 0 ? min(pair_cap, num_sms() / 2) : num_sms() / 2;
     int mode = g_gemm_mode;
-    // auto: whichever schedule needs less time under "waves x time per tile", a 256 x 512 tile costing 4/3 of a 256 x 256 one
-    // (twice the flops at the measured 1000 vs 660 TFLOP/s).  Wide tiles need N to span more than one 256-column slab.
-    if (mode != 1 && mode != 3) {
-        const int waves_wide = (MB * NB2 + max_pairs - 1) / max_pairs, waves_stream = (MB * NB + max_pairs - 1) / max_pairs;
-        mode = (NB > 1 && 4 * waves_wide <= 3 * waves_stream) ? 3 : 1;
-    }
+    // auto (interleaved A/B at the update shapes, tools/probes/gemm_modes_ab.py, after the full barriers lost their remote arrival): the
+    // two-stage 256 x 256 schedule is as fast as or faster than the 256 x 512 one (its epilogue hides behind the next tile) except
+    // for very short K, where halving the number of tiles pays
+    if (mode != 1 && mode != 3) mode = (NB > 1 && a.K <= 384) ? 3 : 1;
     if (mode == 3) {
-        gemm_nt_wide_kernel<EPI><<<2 * min(MB * NB2, max_pairs), G2_THREADS, G2_SMEM, st>>>(tA, tB, tD, tD2, a);
+        if (EPI == CPM_GEMM_EPI_BIAS && !g_gemm_late_release) {
+            static bool attr3 = false;
+            static int max_quads = 0;                       // co-resident 4-CTA clusters (a GPC may leave SMs over)
+            if (!attr3) {
+                cudaError_t e = cudaFuncSetAttribute(gemm_nt_wide_bias_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WN_SMEM);
+                if (e == cudaSuccess) e = cudaFuncSetAttribute(gemm_nt_wide_bias_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)WN_SMEM);
+                if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "gemm_nt shared-memory attribute: %s", cudaGetErrorString(e));
+                cudaLaunchConfig_t cfg = {};
+                cfg.gridDim = dim3(4 * (num_sms() / 4));
+                cfg.blockDim = dim3(G3_THREADS);
+                cfg.dynamicSmemBytes = WN_SMEM;
+                cudaLaunchAttribute at[1];
+                at[0].id = cudaLaunchAttributeClusterDimension;
+                at[0].val.clusterDim.x = 4; at[0].val.clusterDim.y = 1; at[0].val.clusterDim.z = 1;
+                cfg.attrs = at; cfg.numAttrs = 1;
+                if (cudaOccupancyMaxActiveClusters(&max_quads, gemm_nt_wide_bias_kernel<2>, &cfg) != cudaSuccess) { max_quads = 0; cudaGetLastError(); }
+                if (getenv("CPM_GEMM_VERBOSE")) fprintf(stderr, "cpmusic: gemm_nt wide: %d co-resident 4-CTA clusters on %d SMs\n", max_quads, num_sms());
+                attr3 = true;
+            }
+            const int MBS = (a.M + 511) / 512;
+            // the 4-CTA cluster pays when two M tiles exist per N tile and (nearly) every SM can be part of a quad
+            if (!g_gemm_no_multicast && a.M > 256 && max_quads > 0 && (max_quads >= (num_sms() / 4) - 2 || getenv("CPM_GEMM_FORCE_MULTICAST"))) {
+                gemm_nt_wide_bias_kernel<2><<<4 * min(MBS * NB2, max_quads), G3_THREADS, WN_SMEM, st>>>(tA, tB, tD, a);
+                return check_launch("gemm_nt (wide, B multicast over two pairs)");
+            }
+            gemm_nt_wide_bias_kernel<1><<<2 * min(MB * NB2, max_pairs), G3_THREADS, WN_SMEM, st>>>(tA, tB, tD, a);
+            return check_launch("gemm_nt (wide, early release)");
+        }
+        gemm_nt_wide_kernel<EPI><<<2 * min(MB * NB2, max_pairs), G2_THREADS, WN_SMEM, st>>>(tA, tB, tD, tD2, a);
         return check_launch("gemm_nt (wide)");
     }
     gemm_nt_kernel<EPI><<<2 * min(MB * NB, max_pairs), GM_THREADS, GM_SMEM, st>>>(tA, tB, tD, tD2, a);
