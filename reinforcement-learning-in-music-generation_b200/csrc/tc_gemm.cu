@@ -32,10 +32,10 @@ namespace cpm {
 namespace {
 using namespace tc;
 
-constexpr int GM_THREADS = 256, GM_NS = 5;
+constexpr int GM_THREADS = 384, GM_NS = 5;                                  // warps 0-3: TMA / UMMA / TMEM allocator / idle; 4-11 epilogue
 constexpr uint32_t GM_A_BYTES = 16384, GM_STAGE = 32768;                 // per CTA: A half 128 x 64, B half 128 x 64 (bf16)
-constexpr uint32_t GM_OFF_STG = GM_NS * GM_STAGE;                        // epilogue staging: 4 warps x 2 buffers x [32 rows x 128 B]
-constexpr uint32_t GM_OFF_BAR = GM_OFF_STG + 32768;
+constexpr uint32_t GM_OFF_STG = GM_NS * GM_STAGE;                        // epilogue staging: 8 warps x 2 buffers x [32 rows x 128 B]
+constexpr uint32_t GM_OFF_BAR = GM_OFF_STG + 65536;
 constexpr uint32_t GM_SMEM = GM_OFF_BAR + 256;                           // full[5] empty[5] tfull[2] tempty[2] + TMEM slot
 
 constexpr uint32_t IDESC_NT = idesc_bf16(256, 256, false, false);
@@ -69,7 +69,7 @@ __device__ __forceinline__ void gemm_setup(uint8_t *sm, uint64_t *bars, uint32_t
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         for (int s = 0; s < GM_NS; ++s) { mbar_init(bar_full + s, 1); mbar_init(bar_empty + s, 1); }     // full: the leader's expect_tx is the only arrival
-        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, 8); }      // tempty: 4 warps x 2 CTAs
+        for (int s = 0; s < 2; ++s) { mbar_init(bar_tfull + s, 1); mbar_init(bar_tempty + s, 16); }     // tempty: 8 warps x 2 CTAs
         fence_barrier_init();
         tma_prefetch_desc(m0);
         tma_prefetch_desc(m1);
@@ -202,9 +202,10 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
         }
     } else if (warp >= 4) {
-        // ---- epilogue: warp w owns accumulator rows [32 w, 32 w + 32) of this CTA's half tile
-        const int w = warp - 4;
-        uint8_t *stg = sm + GM_OFF_STG + w * 8192;
+        // ---- epilogue: 8 warps, two per TMEM lane quarter: warp owns accumulator rows [32 w, 32 w + 32) of this CTA's half tile and
+        // the column half `ch` (two 64-column chunks).  With 4 warps the epilogue of a K = 512 tile (4.8 us) was longer than its UMMAs.
+        const int w = warp & 3, ch = (warp - 4) >> 2;
+        uint8_t *stg = sm + GM_OFF_STG + (warp - 4) * 8192;
         const uint32_t tempty0 = mapa_u32(smem_u32(bar_tempty), 0);
         const uint64_t rng_offset = rng_off(a.rng_offset, a.rng_base);
         uint32_t ti = 0, buf = 0;
@@ -216,7 +217,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             tc_fence_after();
             const uint32_t tbase = tmem + ((uint32_t)(w * 32) << 16) + as * 256;
 #pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
+            for (int c = 2 * ch; c < 2 * ch + 2; ++c) {
                 const int n0 = nb * 256 + c * 64;
                 uint32_t r[32], o0[16], o1[16];
                 const bool live = n0 < a.N && grow0 < a.M;                    // warp-uniform: the chunk holds at least one real element
@@ -229,7 +230,7 @@ gemm_nt_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 for (int h = 0; h < 2; ++h) {
                     tmem_ld32(tbase + c * 64 + h * 32, r);
                     tmem_ld_wait();
-                    if (c == 3 && h == 1) {                                      // last read of this accumulator stage: hand it back to the issuer
+                    if (c == 2 * ch + 1 && h == 1) {                             // this warp's last read of the accumulator stage: hand it back to the issuer
                         tc_fence_before();
                         __syncwarp();
                         if (lane == 0) mbar_arrive_cluster(tempty0 + 8 * as);
