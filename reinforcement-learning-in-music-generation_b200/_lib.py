@@ -127,8 +127,8 @@ KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_rowdot_partials_rows": 0, "cpm_gemm_set_mode": 0, "cpm_set_chain_pdl": 0,
     "cpm_rollout_plan_bytes": 0, "cpm_debug_rollout_timing": 0, "cpm_debug_small_timing": 0, "cpm_gemm_small_set_split": 0, "cpm_rollout_create": 0, "cpm_rollout_phases": 0, "cpm_rollout_destroy": 0,
 
-    "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 3, "cpm_ln_residual_bwd": 2, "cpm_colsum": 2, "cpm_rowdot_bwd": 2,      # chunk-parallel path: fwd = streaming prefix + per-chunk
-                                                                                # kernel (ops adds 1 when the scan path runs); bwd = pre-pass, scan, main
+    "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 2, "cpm_ln_residual_bwd": 2, "cpm_colsum": 2, "cpm_rowdot_bwd": 2,      # chunk-parallel path: streaming state kernel + per-chunk
+                                                                                # kernel (ops adds the scan when the per-chunk state path runs)
 })
 EXTRA_LAUNCHES = [0]          # segment-total / scan kernels of segmented linear attention, graph replays
 

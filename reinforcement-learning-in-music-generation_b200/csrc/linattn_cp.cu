@@ -876,7 +876,26 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         ph_mma ^= 1;
         tc_fence_after();
         if (tid == 0 && tn < ntiles) issue_b(tn);          // Q, V, Sp are dead: refill them a round early
+        // The transposed score tile goes to shared memory FIRST, so that round 3 can start; the dq / dk rows (accumulators A1 / A2,
+        // untouched by round 3, whose dv lands on the just-converted score columns) are then written out while its UMMAs run.
+        convert_lean<false, false, false>(g, TB_X, sX, 0.f, nullptr);
+        fence_proxy_async();
+        tc_fence_before();
+        __syncthreads();
+        // ---- round 3: dv = PT G' (+ Kf Rs)
+        if (tid == 0) {
+            tc_fence_after();
+#pragma unroll
+            for (int k = 0; k < 8; ++k)
+                mma_ss(tmem + TB_X, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
+            if (have_r) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);
+            }
+            mma_commit(bar_mma);
+        }
         {   // dq and dk rows
+            tc_fence_after();
             uint32_t r[32];
             tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
             tmem_ld_wait();
@@ -888,22 +907,6 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             grad_row_epilogue<true>(r, kfr, sgd + 32 * g.half, 1.f, o);
             store_row32(a.gk, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
         }
-        convert_lean<false, false, false>(g, TB_X, sX, 0.f, nullptr);
-        fence_proxy_async();
-        tc_fence_before();
-        __syncthreads();
-        // ---- round 3: dv = PT G' (+ Kf Rs)
-        if (tid == 0) {
-            tc_fence_after();
-#pragma unroll
-            for (int k = 0; k < 8; ++k)
-                mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
-            if (have_r) {
-#pragma unroll
-                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);
-            }
-            mma_commit(bar_mma);
-        }
         if (tn < ntiles) inv_n = 1.f / inv_n;              // (prefetched den of the next tile)
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
@@ -911,7 +914,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         if (tid == 0 && tn < ntiles) issue_a(tn);
         {   // dv rows
             uint32_t r[32];
-            tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
+            tmem_ld32(g.t_lane + TB_X + 32 * g.half, r);
             tmem_ld_wait();
             uint4 o[4];
 #pragma unroll

@@ -178,6 +178,17 @@ def linattn_saved(N: int, L: int, H: int, device) -> Optional[torch.Tensor]:
     return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
 
 
+def _linattn_extra_launches(N, L, H, bwd=False):
+    """Kernels of one chunk-parallel call beyond the nominal two (launch accounting of bench.py).  Many (batch, head) chains:
+    streaming state kernel + per-chunk kernel.  Few: per-chunk state kernel, scan, per-chunk kernel.  A single chunk has no
+    prefix state to build (the backward still runs its pre-pass for the per-token normaliser gradients)."""
+    if L % 128 != 0:
+        return 0                                  # CUDA-core path
+    if L == 128:
+        return 0 if bwd else -1
+    return 1 if N * H < 96 else 0
+
+
 def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True, saved=None):
     """q,k,v: (N,L,H,64) views (may be column slices of one fused QKV buffer).  `saved`: optional
     buffer from linattn_saved() that receives the prefix states for linattn_bwd_raw."""
@@ -186,8 +197,7 @@ def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True, saved=None):
     out = torch.empty(N, L, H, E, dtype=q.dtype, device=q.device)
     den = torch.empty(N, L, H, dtype=torch.float32, device=q.device) if need_den else None
     ws = linattn_workspace(N, L, H, q.device)
-    if N * H < 96 and L > 128:
-        _lib.EXTRA_LAUNCHES[0] += 1          # few (batch, head) chains: per-chunk state kernel + scan instead of the streaming kernel
+    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H)
     with KernelTimer.span("linattn_fwd"):
         check(_lib.load().cpm_linattn_fwd(_p(q), _p(k), _p(v), _p(out), _p(den), N, L, H, E, E, ld, H * E,
                                           _dt(q), eps, impl, _p(ws), ws.numel(), _p(saved),
@@ -200,6 +210,7 @@ def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0, s
     _, _, _, _, ldg = _check_qkv_layout(gq, gk, gv)
     gout = gout.contiguous()
     ws = linattn_workspace(N, L, H, q.device)
+    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H, bwd=True)
     with KernelTimer.span("linattn_bwd"):
         check(_lib.load().cpm_linattn_bwd(_p(q), _p(k), _p(v), _p(out), _p(den), _p(gout), _p(gq), _p(gk), _p(gv),
                                           N, L, H, E, E, ld, H * E, ldg, _dt(q), eps, impl, _p(ws), ws.numel(),
