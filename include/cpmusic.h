@@ -74,8 +74,9 @@ const char *cpm_linattn_last_impl(void);
  * ------------------------------------------------------------------------------------------ */
 int64_t cpm_linattn_workspace_bytes(int N, int L, int H);
 int64_t cpm_linattn_saved_bytes(int N, int L, int H);
-/* Development aid: device buffer (>= 64 int64 per CTA of the chunk-parallel forward kernel) that receives
- * clock64() stamps at its phase boundaries; NULL switches it off (the default). */
+/* Development aid: device buffer that receives clock64() stamps of the chunk-parallel kernels at their phase boundaries -
+ * 64 int64 per CTA of the forward per-chunk kernel, 128 int64 per CTA of the backward one (whichever runs while the buffer
+ * is installed; size it for 128 x 3 x SMs); NULL switches it off (the default). */
 int cpm_debug_linattn_timing(void *device_buffer);
 int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, float *den,
                     int N, int L, int H, int E, int M, int64_t ld_qkv, int64_t ld_o,

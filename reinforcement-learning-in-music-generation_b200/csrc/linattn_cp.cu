@@ -154,6 +154,32 @@ __device__ __forceinline__ float convert_lean(const Geo &g, uint32_t tm_col, uin
     return rowsum;
 }
 
+// 64 contiguous bytes (32 bf16 of one output row, or half a row of a state tile) as TWO 256-bit stores when the address is
+// 32-byte aligned: with a 128-bit store per lane a warp instruction puts half a sector per row on the wire, and the rows of a
+// warp are 128 B - 3 KB apart.  The stores, not the arithmetic, were the longest phase of the per-chunk kernels
+// (tools/phase_timing_linattn_bwd.py: 20.4 k -> 15.6 k cycles per backward tile; 128 x 1024 x 8 fwd 200 -> 187 us, bwd 423 -> 346).
+#ifndef CPM_STORE256
+#define CPM_STORE256 1
+#endif
+__device__ __forceinline__ void store64(void *dst, const uint4 (&v)[4]) {
+#if CPM_STORE256
+    if ((reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+#pragma unroll
+        for (int i = 0; i < 2; ++i)
+            asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(reinterpret_cast<uint8_t *>(dst) + 32 * i), "r"(v[2 * i].x),
+                         "r"(v[2 * i].y), "r"(v[2 * i].z), "r"(v[2 * i].w), "r"(v[2 * i + 1].x), "r"(v[2 * i + 1].y), "r"(v[2 * i + 1].z),
+                         "r"(v[2 * i + 1].w)
+                         : "memory");
+        return;
+    }
+#endif
+#pragma unroll
+    for (int i = 0; i < 4; ++i) reinterpret_cast<uint4 *>(dst)[i] = v[i];
+}
+__device__ __forceinline__ void store_row32(void *base, int64_t ld_elems, int64_t row, int col, const uint4 (&v)[4]) {
+    store64(reinterpret_cast<__nv_bfloat16 *>(base) + row * ld_elems + col, v);
+}
+
 // =============================================================================================
 // F1: per-chunk state increments  dS = Kf^T V, dz = colsum Kf        (128 threads, 64 TMEM columns)
 // =============================================================================================
@@ -375,9 +401,10 @@ cp_prefix_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __gri
             if (half == 0) tmem_ld8(t_lane + TS_Z, z8);
             tmem_ld_wait();
             if (lane < 16) {
-                uint8_t *dst = tiles + slot * S_TILE_BYTES + erow * 128 + 64 * half;
+                uint4 o[4];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(dst + 16 * cc) = pack8u(r + 8 * cc, 1.f);
+                for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, 1.f);
+                store64(tiles + slot * S_TILE_BYTES + erow * 128 + 64 * half, o);
                 if (half == 0) zs[slot * 64 + erow] = __uint_as_float(z8[0]);
             }
         }
@@ -508,9 +535,10 @@ cp_suffix_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
             if (shalf == 0) tmem_ld8(t_lane + TSB_RZ, z8);
             tmem_ld_wait();
             if (lane < 16) {
-                uint8_t *dst = tiles + slot * S_TILE_BYTES + erow * 128 + 64 * shalf;
+                uint4 o[4];
 #pragma unroll
-                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(dst + 16 * cc) = pack8u(r + 8 * cc, 1.f);
+                for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, 1.f);
+                store64(tiles + slot * S_TILE_BYTES + erow * 128 + 64 * shalf, o);
                 if (shalf == 0) rzs[slot * 64 + erow] = __uint_as_float(z8[0]) + __uint_as_float(z8[1]);
             }
         }
@@ -558,21 +586,21 @@ constexpr uint32_t F_OFF_Q = 0, F_OFF_V = 16384, F_OFF_S = 32768, F_OFF_K = 4096
 constexpr uint32_t F_OFF_Z = 73728 /* 64 floats */, F_OFF_DP = F_OFF_Z + 256 /* 2 x 128 floats */, F_OFF_BAR = F_OFF_DP + 1024,
                    F_SMEM = F_OFF_BAR + 32;
 
-__device__ __forceinline__ void store_row32(void *base, int64_t ld_elems, int64_t row, int col, const uint4 (&v)[4]) {
-    uint4 *d = reinterpret_cast<uint4 *>(reinterpret_cast<__nv_bfloat16 *>(base) + row * ld_elems + col);
-#pragma unroll
-    for (int i = 0; i < 4; ++i) d[i] = v[i];
-}
-
+#ifndef CPM_TMA_STORE
+#define CPM_TMA_STORE 1       // output rows leave through a swizzled shared-memory tile and ONE bulk tensor store (whole 128-byte lines)
+#endif
 __global__ void __launch_bounds__(NTH, 3)
 cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
-                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmS, const float *__restrict__ zp,
+                  const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmS,
+                  const __grid_constant__ CUtensorMap tmO, const float *__restrict__ zp,
                   void *__restrict__ out, float *__restrict__ den, int L, int H, int nchunks, int NH, int64_t ld_o, float eps,
                   long long *__restrict__ dbg) {
     // Persistent: CTA b handles tiles b, b + gridDim.x, ... in chunk-major order (tile t = chunk t / NH of pair t % NH),
     // so barrier / TMEM set-up is paid once and the next tile's TMA loads fly while this tile's epilogue runs.
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sQ = sm + F_OFF_Q, *sK = sm + F_OFF_K, *sV = sm + F_OFF_V, *sS = sm + F_OFF_S, *sP = sm + F_OFF_P;
+    uint8_t *sOut = sP + TILE_BYTES;                  // output staging: the score tile's second block - dead after the second UMMA round
+                                                      // and, unlike K's tile under its first block, not a target of the next tile's loads
     float *sz = reinterpret_cast<float *>(sm + F_OFF_Z), *sdp = reinterpret_cast<float *>(sm + F_OFF_DP);
     uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + F_OFF_BAR), *bar_mma = bar_load + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
@@ -629,6 +657,9 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             *reinterpret_cast<uint4 *>(sQ + off) = phi8_dot(*reinterpret_cast<const uint4 *>(sQ + off), sz + 8 * ch, den_part);
             *reinterpret_cast<uint4 *>(sK + off) = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
         }
+#if CPM_TMA_STORE
+        if (tid == 0) tma_store_wait_read0();             // the previous tile's output store has read its staging block (long ago)
+#endif
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
@@ -678,14 +709,26 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             uint4 o[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, inv);
+#if CPM_TMA_STORE
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sOut + sw128_off(g.row, 4 * g.half + cc)) = o[cc];
+            fence_proxy_async();
+#else
             store_row32(out, ld_o, grow + g.row, col0 + 32 * g.half, o);
+#endif
         }
         tc_fence_before();
         __syncthreads();                                  // TMEM columns, sz and sdp are reused by the next tile
         tc_fence_after();
+#if CPM_TMA_STORE
+        if (tid == 0) { tma_store_2d(&tmO, sOut, col0, grow); tma_store_commit(); }
+#endif
         CPM_STAMP();
     }
 #undef CPM_STAMP
+#if CPM_TMA_STORE
+    if (tid == 0) tma_store_wait_all0();
+#endif
     if ((tid >> 5) == 0) tmem_dealloc<128>(tmem);
 }
 
@@ -708,6 +751,7 @@ struct BwdMainArgs {
     void *gq, *gk, *gv;
     int64_t ld_g;
     int L, H, nchunks, NH;
+    long long *dbg;                                  // development aid: clock64 stamps of thread 0 at the phase boundaries (128 per CTA), or NULL
 };
 
 // acc (32 fp32 TMEM values) + add[c] (+ rowscale * vec[c]) then * phi'(f) -> 32 bf16
@@ -732,7 +776,8 @@ __device__ __forceinline__ void grad_row_epilogue(const uint32_t (&r)[32], const
 __global__ void __launch_bounds__(NTH, 2)
 cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmGo,
-                   const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmR, BwdMainArgs a) {
+                   const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmR,
+                   const __grid_constant__ CUtensorMap tmGq, const __grid_constant__ CUtensorMap tmGk, BwdMainArgs a) {
     extern __shared__ __align__(1024) uint8_t sm[];
     uint8_t *sQ = sm + B_OFF_Q, *sK = sm + B_OFF_K, *sV = sm + B_OFF_V, *sG = sm + B_OFF_G, *sS = sm + B_OFF_S, *sR = sm + B_OFF_R;
     uint8_t *sX = sm + B_OFF_X;
@@ -796,6 +841,9 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         gd_n = a.gd[ri];
     }
     uint32_t ph_a = 0, ph_b = 0, ph_mma = 0;
+    int dbg_i = 0;
+#define CPM_STAMP() do { if (a.dbg && tid == 0 && dbg_i < 128) a.dbg[(int64_t)blockIdx.x * 128 + dbg_i++] = clock64(); } while (0)
+    CPM_STAMP();
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         int c, nh, grow, col0;
         tile_coords(t, c, nh, grow, col0);
@@ -824,6 +872,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             *reinterpret_cast<uint4 *>(sQ + off) = qv;
             qfr[4 * cc + 0] = qv.x; qfr[4 * cc + 1] = qv.y; qfr[4 * cc + 2] = qv.z; qfr[4 * cc + 3] = qv.w;
         }
+        CPM_STAMP();                                       // 1: Q, V, Sp landed; phi(Q) done
         mbar_wait(bar_a, ph_a);
         ph_a ^= 1;
 #pragma unroll
@@ -835,9 +884,13 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             *reinterpret_cast<uint4 *>(sK + off) = kv;
             kfr[4 * cc + 0] = kv.x; kfr[4 * cc + 1] = kv.y; kfr[4 * cc + 2] = kv.z; kfr[4 * cc + 3] = kv.w;
         }
+#if CPM_TMA_STORE
+        if (tid == 0) tma_store_wait_read0();              // the previous tile's dq / dk stores have read the score buffer (long ago)
+#endif
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        CPM_STAMP();                                       // 2: K, go, Rs landed; G', phi(K) done; CTA in step
         // ---- round 1: X = G' V^T
         if (tid == 0) {
             tc_fence_after();
@@ -848,10 +901,12 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        CPM_STAMP();                                       // 3: round 1 done
         convert_lean<true, true, false>(g, TB_X, sX, gd, nullptr);
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        CPM_STAMP();                                       // 4: X converted; CTA in step
         // ---- round 2: dQf = X Kf (+ G' Sp^T) ; dKf = X^T Qf (+ v Rs^T) ; PT = Kf Qf^T
         if (tid == 0) {
             tc_fence_after();
@@ -875,6 +930,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        CPM_STAMP();                                       // 5: round 2 done
         if (tid == 0 && tn < ntiles) issue_b(tn);          // Q, V, Sp are dead: refill them a round early
         // The transposed score tile goes to shared memory FIRST, so that round 3 can start; the dq / dk rows (accumulators A1 / A2,
         // untouched by round 3, whose dv lands on the just-converted score columns) are then written out while its UMMAs run.
@@ -882,6 +938,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
+        CPM_STAMP();                                       // 6: PT converted; CTA in step
         // ---- round 3: dv = PT G' (+ Kf Rs)
         if (tid == 0) {
             tc_fence_after();
@@ -894,6 +951,21 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             }
             mma_commit(bar_mma);
         }
+#if CPM_TMA_STORE
+        // dq / dk rows: finished in registers while round 3 runs; once it is done the score buffer is free and stages them
+        // (swizzled, block 0 = dq, block 1 = dk) for two bulk tensor stores - whole lines instead of 32-byte pieces per lane.
+        uint4 oq[4], ok[4];
+        {
+            tc_fence_after();
+            uint32_t r[32];
+            tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
+            tmem_ld_wait();
+            grad_row_epilogue<true>(r, qfr, sz + 32 * g.half, gd, oq);
+            tmem_ld32(g.t_lane + TB_A2 + 32 * g.half, r);
+            tmem_ld_wait();
+            grad_row_epilogue<true>(r, kfr, sgd + 32 * g.half, 1.f, ok);
+        }
+#else
         {   // dq and dk rows
             tc_fence_after();
             uint32_t r[32];
@@ -907,11 +979,23 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             grad_row_epilogue<true>(r, kfr, sgd + 32 * g.half, 1.f, o);
             store_row32(a.gk, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
         }
+#endif
         if (tn < ntiles) inv_n = 1.f / inv_n;              // (prefetched den of the next tile)
+        CPM_STAMP();                                       // 7: dq, dk rows computed (stored, without the bulk store)
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
+        CPM_STAMP();                                       // 8: round 3 done
         if (tid == 0 && tn < ntiles) issue_a(tn);
+#if CPM_TMA_STORE
+#pragma unroll
+        for (int cc = 0; cc < 4; ++cc) {
+            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
+            *reinterpret_cast<uint4 *>(sX + off) = oq[cc];
+            *reinterpret_cast<uint4 *>(sX + TILE_BYTES + off) = ok[cc];
+        }
+        fence_proxy_async();
+#endif
         {   // dv rows
             uint32_t r[32];
             tmem_ld32(g.t_lane + TB_X + 32 * g.half, r);
@@ -924,7 +1008,19 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_before();
         __syncthreads();                                  // TMEM accumulators, sgd, sz are reused by the next tile
         tc_fence_after();
+#if CPM_TMA_STORE
+        if (tid == 0) {
+            tma_store_2d(&tmGq, sX, col0, grow);
+            tma_store_2d(&tmGk, sX + TILE_BYTES, col0, grow);
+            tma_store_commit();
+        }
+#endif
+        CPM_STAMP();                                       // 9: dv rows stored; CTA in step
     }
+#undef CPM_STAMP
+#if CPM_TMA_STORE
+    if (tid == 0) tma_store_wait_all0();
+#endif
     if ((tid >> 5) == 0) tmem_dealloc<256>(tmem);
 }
 
@@ -991,17 +1087,18 @@ int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out
     uint8_t *region = saved ? reinterpret_cast<uint8_t *>(saved) : reinterpret_cast<uint8_t *>(ws) + nhc * STATE_FLOATS * 4;
     int rc;
     if ((rc = prefix_states(k, v, N, L, H, ld_qkv, part, region, st))) return rc;
-    CUtensorMap tq, tk, tv, ts;
+    CUtensorMap tq, tk, tv, ts, to;
     const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
     if ((rc = make_tmap_bf16_2d(&tq, q, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&to, out, inner, rows, ld_o, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&ts, region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
     static bool a3 = false;
     if ((rc = set_smem_once((const void *)cp_out_fwd_kernel, F_SMEM, &a3, "cp_out_fwd"))) return rc;
     const int64_t slots = 3ll * num_sms();
     cp_out_fwd_kernel<<<(unsigned)(nhc < slots ? nhc : slots), NTH, F_SMEM, st>>>(
-        tq, tk, tv, ts, reinterpret_cast<const float *>(region + state_tiles_bytes(nhc)), out, den, L, H, nchunks, N * H, ld_o, eps,
+        tq, tk, tv, ts, to, reinterpret_cast<const float *>(region + state_tiles_bytes(nhc)), out, den, L, H, nchunks, N * H, ld_o, eps,
         g_cp_timing);
     return check_launch("linattn_fwd_cp");
 }
@@ -1024,13 +1121,15 @@ int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const voi
     } else {
         sp_region = const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(saved));
     }
-    CUtensorMap tq, tk, tv, tgo, to, ts, tr;
+    CUtensorMap tq, tk, tv, tgo, to, ts, tr, tgq, tgk;
     const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
     if ((rc = make_tmap_bf16_2d(&tq, q, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tgo, gout, inner, rows, ld_o, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&to, out, inner, rows, ld_o, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tgq, gq, inner, rows, ld_g, CHUNK))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tgk, gk, inner, rows, ld_g, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&ts, sp_region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
     if ((rc = make_tmap_bf16_2d(&tr, rs_region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
     static bool a1 = false, a3 = false, a5 = false;
@@ -1051,8 +1150,9 @@ int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const voi
     a.zp = reinterpret_cast<const float *>(sp_region + state_tiles_bytes(nhc));
     a.rzs = reinterpret_cast<const float *>(rs_region + state_tiles_bytes(nhc));
     a.gq = gq; a.gk = gk; a.gv = gv; a.ld_g = ld_g; a.L = L; a.H = H; a.nchunks = nchunks; a.NH = N * H;
+    a.dbg = g_cp_timing;
     const int64_t slots = 2ll * num_sms();
-    cp_bwd_main_kernel<<<(unsigned)(nhc < slots ? nhc : slots), NTH, B_SMEM, st>>>(tq, tk, tv, tgo, ts, tr, a);
+    cp_bwd_main_kernel<<<(unsigned)(nhc < slots ? nhc : slots), NTH, B_SMEM, st>>>(tq, tk, tv, tgo, ts, tr, tgq, tgk, a);
     return check_launch("linattn_bwd_cp");
 }
 
