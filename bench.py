@@ -43,10 +43,10 @@ MINIBATCH = int(os.environ.get("CPM_MINIBATCH", "128"))
 # rollout); CPM_OVERLAP_CRITIC=0 gives the strictly sequential iteration.
 OVERLAP_CRITIC = os.environ.get("CPM_OVERLAP_CRITIC", "1") == "1"
 # DRAM bytes of one linear-attention fwd+bwd launch group measured with ncu (cold L2), keyed by the update minibatch shape
-# -> (bytes, the committed ncu log).  (64, 1024): fwd 117.5+6.8 (streaming prefix) + 231.8+41.8 (per-chunk output) MB, bwd 195.1+17.4
-# (streaming suffix) + 334.1+153.9 (main) MB.  (128, 1024): fwd 234.9+37.2 + 463.7+110.4 MB, bwd 390.1+48.8 + 668.0+354.6 MB.
+# -> (bytes, the committed ncu log).  (128, 1024), final kernels of round 2: fwd 234.9+41.3 (streaming prefix) + 463.2+120.0 (per-chunk
+# output) MB, bwd 390.1+53.1 (streaming suffix) + 666.6+361.3 (main) MB.  (64, 1024): round-1 capture (same passes over the data).
 LINATTN_DRAM_BYTES_PER_PAIR = {(64, 1024): (1_098_400_000, "profiles/r01_ncu_linattn_cp_final_64x1024x8.csv"),
-                               (128, 1024): (2_307_700_000, "profiles/r01_ncu_linattn_cp_128x1024x8.csv")}
+                               (128, 1024): (2_330_500_000, "profiles/r02_ncu_linattn_fwd_bwd_128x1024x8_final.csv")}
 METRIC = "CP tokens/s, PPO rollout+update"
 UNIT = "tokens/s"
 
@@ -390,6 +390,50 @@ def time_recurrent_step_kernel(dev, peak):
             "note": "standalone CUDA graph of 12 launches (one per layer state), L2 flushed before each replay"}
 
 
+def time_linattn_standalone(dev, peak):
+    """The chunked attention kernels alone at the update shape (MINIBATCH x ROLLOUT_LEN x 8 heads, fused QKV layout, prefix states
+    kept for the backward as in training): one CUDA graph per direction, L2 flushed before each replay.  Reported next to the
+    in-situ figure because the two differ by the SM clock: inside the update phase the GEMMs before and after hold the chip at
+    its power cap (SM clocks near 1.3-1.5 GHz instead of 1.95), and these kernels - a chain of short phases per tile - scale
+    with it (tools/bench_linattn.py --hot 40 reproduces the in-situ times)."""
+    import torch
+    import cpmusic
+    N, L, H = MINIBATCH, ROLLOUT_LEN, 8
+    gen = torch.Generator().manual_seed(0)
+    qkv = torch.randn(N, L, 3 * H * 64, generator=gen).to(dev).bfloat16()
+    q, k, v = (qkv[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
+    go = torch.randn(N, L, H, 64, generator=gen).to(dev).bfloat16()
+    gqkv = torch.empty_like(qkv)
+    gq, gk, gv = (gqkv[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
+    saved = cpmusic.ops.linattn_saved(N, L, H, dev)
+    out, den = cpmusic.ops.linattn_fwd_raw(q, k, v, saved=saved)
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)
+    a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    res = {}
+    for name, fn in (("ms_fwd", lambda: cpmusic.ops.linattn_fwd_raw(q, k, v, saved=saved)),
+                     ("ms_bwd", lambda: cpmusic.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv, saved=saved))):
+        fn()
+        torch.cuda.synchronize()
+        graph = torch.cuda.CUDAGraph()
+        with cpmusic.ops.graph_capture(graph):
+            fn()
+        tot, reps = 0.0, 10
+        for r in range(reps + 2):
+            flush.zero_()
+            a.record()
+            graph.replay()
+            b.record()
+            torch.cuda.synchronize()
+            if r >= 2:
+                tot += a.elapsed_time(b)
+        res[name] = tot / reps
+    byt = N * L * H * 1408
+    ach = byt / ((res["ms_fwd"] + res["ms_bwd"]) * 1e-3) / 1e9
+    res.update({"achieved": ach, "frac": ach / peak,
+                "note": "kernels alone (one CUDA graph per direction, L2 flushed, chip not power-capped by surrounding GEMMs)"})
+    return res
+
+
 def run_gpu(args, rank, world):
     import torch
     import cpmusic
@@ -553,6 +597,8 @@ def run_gpu(args, rank, world):
                 "launch_pairs_timed": n_pairs, "share_of_step": (tf + tb) / ms,
                 "tensor_frac_of_measured_bf16": (tok_call * 8 * 49152) / (ms_pair * 1e-3) / 1e12 / 1651.8 if ms_pair > 0 else 0.0}
     roofline_step = time_recurrent_step_kernel(dev, peak)
+    if rank == 0:
+        roofline["standalone"] = time_linattn_standalone(dev, peak)
     cpu = cpu_reference_sample() if world >= 1 and not args.no_cpu_baseline else None
     diag = {"rollout_us_per_token": round(it.phase_ms["rollout"] * 1e3 / ROLLOUT_LEN, 1), "rollout_mode": it.engine.mode,
             "rollout_layernorm_folded": bool(it.engine.fold), "under_torchrun": "TORCHELASTIC_RUN_ID" in os.environ,

@@ -326,14 +326,17 @@ cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
 // dependency through memory, so K/V tiles are prefetched ST_STAGES chunks ahead by TMA.
 // Used when there are enough (batch, head) pairs to fill the GPU; otherwise F1 + F2.
 // =============================================================================================
-constexpr int ST_STAGES = 3;
+#ifndef CPM_ST_STAGES
+#define CPM_ST_STAGES 2
+#endif
+constexpr int ST_STAGES = CPM_ST_STAGES;            // 2 stages: 66 KB of shared memory, three CTAs per SM
 constexpr uint32_t ST_STAGE_BYTES = 2 * TILE_BYTES;
 constexpr uint32_t ST_OFF_ONES = ST_STAGES * ST_STAGE_BYTES;                    // 2 KB of bf16 ones (layout-agnostic B operand)
 constexpr uint32_t ST_OFF_BAR = ST_OFF_ONES + 2048, ST_SMEM = ST_OFF_BAR + 64;
 constexpr uint32_t IDESC_Z8 = idesc_bf16(64, 8, true, true);                    // z[e] += sum_j Kf[j][e] * 1
 constexpr uint32_t TS_S = 0, TS_Z = 64;
 
-__global__ void __launch_bounds__(NTH)
+__global__ void __launch_bounds__(NTH, ST_STAGES == 2 ? 3 : 2)
 cp_prefix_stream_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV,
                             uint8_t *__restrict__ tiles, float *__restrict__ zs, int L, int H, int nchunks) {
     extern __shared__ __align__(1024) uint8_t sm[];

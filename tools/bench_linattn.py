@@ -17,10 +17,13 @@ def main():
     ap.add_argument("--iters", type=int, default=20)
     ap.add_argument("--shape", default=None, help="substring filter on the shape name")
     ap.add_argument("--dirs", nargs="+", default=["fwd", "bwd"])
+    ap.add_argument("--hot", type=int, default=0, help="run this many 8192^3 bf16 matmuls right before every timed call: the chip is then at "
+                    "its power cap with lowered SM clocks, as inside the update phase of bench.py")
     args = ap.parse_args()
     dev = torch.device("cuda:0")
     peak = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"] if os.path.exists(os.path.join(ROOT, "MEASURED_PEAKS.json")) else 6650.0
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    ha, hb = (torch.randn(8192, 8192, device=dev).bfloat16() for _ in range(2)) if args.hot else (None, None)
     for name, (N, L, H) in SHAPES.items():
         if args.shape and args.shape not in name:
             continue
@@ -54,6 +57,8 @@ def main():
                 tot = 0.0
                 a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
                 for _ in range(args.iters):
+                    for _ in range(args.hot):
+                        ha @ hb
                     flush.zero_()
                     a.record(); run(); b.record()
                     torch.cuda.synchronize()
