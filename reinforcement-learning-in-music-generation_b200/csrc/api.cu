@@ -208,8 +208,17 @@ int64_t cpm_linattn_workspace_bytes(int N, int L, int H) {
     if (N <= 0 || L <= 0 || H <= 0) return 0;
     int nseg, seg_len;
     plan_segments(N, H, L, &nseg, &seg_len);
-    const int64_t seg = 2ll * N * H * nseg * STATE_FLOATS * (int64_t)sizeof(float), cp = linattn_cp_workspace_bytes(N, L, H);
+    const int64_t seg = 2ll * N * H * nseg * STATE_FLOATS * (int64_t)sizeof(float), cp = linattn_cp_workspace_bytes(N, L, H, 64);
     return seg > cp ? seg : cp;
+}
+int64_t cpm_linattn_workspace_bytes_wide(int N, int L, int H, int E) {
+    if (E == 64) return cpm_linattn_workspace_bytes(N, L, H);
+    if (N <= 0 || L <= 0 || H <= 0 || E != 128) return 0;
+    return linattn_cp_workspace_bytes(N, L, H, 128);    // tensor-core path only: 0 unless L % 128 == 0
+}
+int64_t cpm_linattn_saved_bytes_wide(int N, int L, int H, int E) {
+    if (N <= 0 || L <= 0 || H <= 0 || (E != 64 && E != 128)) return 0;
+    return linattn_cp_saved_bytes(N, L, H, E);
 }
 int cpm_debug_linattn_timing(void *buf) {
     linattn_cp_set_timing_buffer(reinterpret_cast<long long *>(buf));
@@ -217,21 +226,23 @@ int cpm_debug_linattn_timing(void *buf) {
 }
 int64_t cpm_linattn_saved_bytes(int N, int L, int H) {
     if (N <= 0 || L <= 0 || H <= 0) return 0;
-    return linattn_cp_saved_bytes(N, L, H);
+    return linattn_cp_saved_bytes(N, L, H, 64);
 }
 
 static int linattn_check(const void *a, const void *b, const void *c, const void *d, int N, int L, int H, int E, int M,
                          int64_t ld_qkv, int64_t ld_o, int dtype, void *ws, int64_t ws_bytes) {
     CPM_REQUIRE(a && b && c && d, CPM_ERR_NULL, "linattn: q/k/v/out must be non-NULL");
     CPM_REQUIRE(N > 0 && L > 0 && H > 0, CPM_ERR_BAD_SHAPE, "linattn: N=%d L=%d H=%d must be positive", N, L, H);
-    CPM_REQUIRE(E == 64 && M == 64, CPM_ERR_BAD_SHAPE, "linattn: only E=M=64 is supported (got E=%d M=%d)", E, M);
+    CPM_REQUIRE((E == 64 || E == 128) && M == E, CPM_ERR_BAD_SHAPE, "linattn: head widths E = M = 64 or 128 are supported (got E=%d M=%d)", E, M);
     CPM_REQUIRE(dtype == CPM_F32 || dtype == CPM_BF16, CPM_ERR_BAD_DTYPE, "linattn: dtype %d", dtype);
+    CPM_REQUIRE(E == 64 || (dtype == CPM_BF16 && L % 128 == 0), CPM_ERR_UNSUPPORTED,
+                "linattn: 128-wide heads run on the tensor-core kernels only (bf16, L %% 128 == 0; got dtype %d, L=%d)", dtype, L);
     CPM_REQUIRE(ld_qkv >= (int64_t)H * E && ld_o >= (int64_t)H * M && ld_qkv % 8 == 0 && ld_o % 8 == 0, CPM_ERR_BAD_SHAPE,
-                "linattn: token strides (%lld,%lld) must be >= H*64 and multiples of 8", (long long)ld_qkv, (long long)ld_o);
+                "linattn: token strides (%lld,%lld) must be >= H*E and multiples of 8", (long long)ld_qkv, (long long)ld_o);
     CPM_REQUIRE(aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d), CPM_ERR_BAD_ALIGN,
                 "linattn: q/k/v/out must be 16-byte aligned");
-    CPM_REQUIRE(ws_bytes >= cpm_linattn_workspace_bytes(N, L, H) && (ws || ws_bytes == 0), CPM_ERR_WORKSPACE,
-                "linattn: workspace %lld < required %lld", (long long)ws_bytes, (long long)cpm_linattn_workspace_bytes(N, L, H));
+    CPM_REQUIRE(ws_bytes >= cpm_linattn_workspace_bytes_wide(N, L, H, E) && (ws || ws_bytes == 0), CPM_ERR_WORKSPACE,
+                "linattn: workspace %lld < required %lld", (long long)ws_bytes, (long long)cpm_linattn_workspace_bytes_wide(N, L, H, E));
     return CPM_OK;
 }
 
@@ -244,13 +255,17 @@ int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, floa
     bool tc_ok = dtype == CPM_BF16 && L % 128 == 0;
     CPM_REQUIRE(impl == 0 || impl == 1 || impl == 3, CPM_ERR_BAD_SHAPE, "linattn_fwd: impl %d (0 auto | 1 simt | 3 tcgen05 chunk-parallel)", impl);
     CPM_REQUIRE(impl != 3 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_fwd: tcgen05 path needs bf16 and L%%128==0");
-    CPM_REQUIRE(!saved || saved_bytes >= cpm_linattn_saved_bytes(N, L, H), CPM_ERR_WORKSPACE, "linattn_fwd: saved-state buffer %lld < %lld",
-                (long long)saved_bytes, (long long)cpm_linattn_saved_bytes(N, L, H));
+    CPM_REQUIRE(E == 64 || impl != 1, CPM_ERR_UNSUPPORTED, "linattn_fwd: the CUDA-core kernels are 64-wide");
+    CPM_REQUIRE(!saved || saved_bytes >= cpm_linattn_saved_bytes_wide(N, L, H, E), CPM_ERR_WORKSPACE, "linattn_fwd: saved-state buffer %lld < %lld",
+                (long long)saved_bytes, (long long)cpm_linattn_saved_bytes_wide(N, L, H, E));
     if (impl == 3 || (impl == 0 && tc_ok)) {
-        rc = linattn_fwd_cp_launch(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, workspace, saved, st);
-        // "-stream": one CTA per (batch, head) chain carries S / z in tensor memory across chunks (N*H >= 96); otherwise the
-        // per-chunk state kernels + scan
-        if (rc != CPM_ERR_UNSUPPORTED || impl == 3) { g_linattn_impl = (N * H >= 96 && L > 128) ? "tcgen05-cp-stream" : "tcgen05-cp"; return rc; }
+        rc = linattn_fwd_cp_launch(q, k, v, out, den, N, L, H, E, ld_qkv, ld_o, eps, workspace, saved, st);
+        // "-stream": one CTA per (batch, head) chain carries S / z in tensor memory across chunks (64-wide heads, N*H >= 96);
+        // otherwise the per-chunk state kernels + scan
+        if (rc != CPM_ERR_UNSUPPORTED || impl == 3 || E != 64) {
+            g_linattn_impl = (linattn_cp_streams(N, H, E) && L > 128) ? "tcgen05-cp-stream" : "tcgen05-cp";
+            return rc;
+        }
     }
     g_linattn_impl = "simt";
     return linattn_fwd_simt_launch(q, k, v, out, den, N, L, H, ld_qkv, ld_o, dtype, eps, workspace, st);
@@ -263,18 +278,19 @@ int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out
     int rc = linattn_check(q, k, v, out, N, L, H, E, M, ld_qkv, ld_o, dtype, workspace, workspace_bytes);
     if (rc) return rc;
     CPM_REQUIRE(den && gout && gq && gk && gv, CPM_ERR_NULL, "linattn_bwd: den/gout/gq/gk/gv must be non-NULL");
-    CPM_REQUIRE(ld_g >= (int64_t)H * 64 && ld_g % 8 == 0, CPM_ERR_BAD_SHAPE, "linattn_bwd: ld_g=%lld", (long long)ld_g);
+    CPM_REQUIRE(ld_g >= (int64_t)H * E && ld_g % 8 == 0, CPM_ERR_BAD_SHAPE, "linattn_bwd: ld_g=%lld", (long long)ld_g);
     CPM_REQUIRE(aligned16(gout) && aligned16(gq) && aligned16(gk) && aligned16(gv), CPM_ERR_BAD_ALIGN,
                 "linattn_bwd: gradient buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
     bool tc_ok = dtype == CPM_BF16 && L % 128 == 0;
     CPM_REQUIRE(impl == 0 || impl == 1 || impl == 3, CPM_ERR_BAD_SHAPE, "linattn_bwd: impl %d (0 auto | 1 simt | 3 tcgen05 chunk-parallel)", impl);
     CPM_REQUIRE(impl != 3 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_bwd: tcgen05 path needs bf16 and L%%128==0");
-    CPM_REQUIRE(!saved || saved_bytes >= cpm_linattn_saved_bytes(N, L, H), CPM_ERR_WORKSPACE, "linattn_bwd: saved-state buffer %lld < %lld",
-                (long long)saved_bytes, (long long)cpm_linattn_saved_bytes(N, L, H));
+    CPM_REQUIRE(E == 64 || impl != 1, CPM_ERR_UNSUPPORTED, "linattn_bwd: the CUDA-core kernels are 64-wide");
+    CPM_REQUIRE(!saved || saved_bytes >= cpm_linattn_saved_bytes_wide(N, L, H, E), CPM_ERR_WORKSPACE, "linattn_bwd: saved-state buffer %lld < %lld",
+                (long long)saved_bytes, (long long)cpm_linattn_saved_bytes_wide(N, L, H, E));
     if (impl == 3 || (impl == 0 && tc_ok)) {
-        rc = linattn_bwd_cp_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, workspace, saved, st);
-        if (rc != CPM_ERR_UNSUPPORTED || impl == 3) { g_linattn_impl = N * H >= 96 ? "tcgen05-cp-stream" : "tcgen05-cp"; return rc; }
+        rc = linattn_bwd_cp_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, E, ld_qkv, ld_o, ld_g, workspace, saved, st);
+        if (rc != CPM_ERR_UNSUPPORTED || impl == 3 || E != 64) { g_linattn_impl = linattn_cp_streams(N, H, E) ? "tcgen05-cp-stream" : "tcgen05-cp"; return rc; }
     }
     g_linattn_impl = "simt";
     return linattn_bwd_simt_launch(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, dtype, eps, workspace, st);

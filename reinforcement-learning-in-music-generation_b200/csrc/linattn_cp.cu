@@ -34,9 +34,6 @@ constexpr uint32_t IDESC_KM64 = idesc_bf16(128, 64, false, true);      // A K-ma
 constexpr uint32_t IDESC_KK64 = idesc_bf16(128, 64, false, false);     // A K-major, B K-major,  N=64
 constexpr uint32_t IDESC_MM64 = idesc_bf16(64, 64, true, true);        // A MN-major, B MN-major (M=64 state tile)
 
-// byte offsets inside the `saved` / workspace state regions: NHC tiles of 8 KB, then NHC x 64 floats
-__host__ __device__ inline int64_t state_tiles_bytes(int64_t nhc) { return nhc * (int64_t)S_TILE_BYTES; }
-__host__ __device__ inline int64_t state_region_bytes(int64_t nhc) { return nhc * (int64_t)(S_TILE_BYTES + 256); }
 
 // M=64 accumulator in TMEM columns [col, col+64) -> fp32 rows dst[e*64 + m] (128-thread kernels, warps 0..3:
 // warp w holds rows 16w..16w+15 in lanes 0..15 of its TMEM quarter).
@@ -181,94 +178,137 @@ __device__ __forceinline__ void store_row32(void *base, int64_t ld_elems, int64_
 }
 
 // =============================================================================================
-// F1: per-chunk state increments  dS = Kf^T V, dz = colsum Kf        (128 threads, 64 TMEM columns)
+// Head width.  D = number of 64-wide halves of a head (1: the reference's 64-wide heads; 2: 128-wide heads, SURVEY §8 a7 / cfg5
+// read as 8 x 128).  A 128-wide head is D tiles of q / k (feature halves a) and D tiles of v / out (value halves b) per chunk;
+// its state is D x D tiles S_ab = Kf_a^T V_b of 64 x 64 and D key-sum vectors z_a.  Tile (a, b) of chunk-slot s lives at
+// ((s * D + a) * D + b) * 8 KB of a state region, z_a at (s * D + a) * 64 floats behind the tiles; an fp32 increment is
+// [D*D tiles of 4096][D*64] floats.  The per-chunk kernels below are templates over D with every loop over a / b unrolled.
 // =============================================================================================
-constexpr uint32_t P_OFF_A = 0, P_OFF_B = 16384, P_OFF_C = 32768;      // up to three input tiles
-constexpr uint32_t PF_OFF_MISC = 32768, PB_OFF_MISC = 49152;
-constexpr uint32_t PF_SMEM = PF_OFF_MISC + 512 + 64, PB_SMEM = PB_OFF_MISC + 512 + 512 + 64;
+template <int D> struct Wide {
+    static constexpr int TILES = D * D;
+    static constexpr int STATE_F = TILES * 4096 + D * 64;                       // floats per fp32 increment
+    static constexpr uint32_t S_BYTES = TILES * S_TILE_BYTES;                   // bf16 state tiles per chunk-slot
+};
+template <int D> __host__ __device__ inline int64_t state_tiles_bytes_w(int64_t nhc) { return nhc * (int64_t)Wide<D>::S_BYTES; }
+template <int D> __host__ __device__ inline int64_t state_region_bytes_w(int64_t nhc) { return nhc * (int64_t)(Wide<D>::S_BYTES + D * 256); }
 
+// =============================================================================================
+// F1: per-chunk state increments  dS_ab = Kf_a^T V_b, dz_a = colsum Kf_a        (128 threads, D*D*64 TMEM columns)
+// =============================================================================================
+template <int D> struct PreCfg {
+    static constexpr uint32_t F_MISC = 2 * D * TILE_BYTES;                      // forward: K | V
+    static constexpr uint32_t F_SMEM = F_MISC + D * 512 + 64;
+    static constexpr uint32_t B_MISC = 3 * D * TILE_BYTES;                      // backward: Q | go | out
+    static constexpr uint32_t B_SMEM = B_MISC + D * 512 + 512 + 64;
+    static constexpr int TCOLS = D * D * 64;
+};
+
+template <int D>
 __global__ void __launch_bounds__(128)
 cp_state_fwd_kernel(const __grid_constant__ CUtensorMap tmK, const __grid_constant__ CUtensorMap tmV, float *__restrict__ part,
                     int L, int H, int nchunks) {
+    using C = PreCfg<D>;
     extern __shared__ __align__(1024) uint8_t sm[];
-    uint8_t *sK = sm + P_OFF_A, *sV = sm + P_OFF_B;
-    float *sdz = reinterpret_cast<float *>(sm + PF_OFF_MISC);                  // [2][64]
-    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + PF_OFF_MISC + 512), *bar_mma = bar_load + 1;
+    uint8_t *sK = sm, *sV = sm + D * TILE_BYTES;                               // D tiles each
+    float *sdz = reinterpret_cast<float *>(sm + C::F_MISC);                    // [D][2][64]
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + C::F_MISC + D * 512), *bar_mma = bar_load + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
     const int tid = threadIdx.x;
     const int per = nchunks - 1;
     const int nh = blockIdx.x / per, c = blockIdx.x % per, n = nh / H, h = nh % H;
-    const int grow = n * L + c * CHUNK, col0 = h * 64;
+    const int grow = n * L + c * CHUNK, col0 = h * 64 * D;
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
         fence_barrier_init();
-        mbar_expect_tx(bar_load, 2 * TILE_BYTES);
-        tma_load_2d(sK, &tmK, bar_load, col0, grow);
-        tma_load_2d(sV, &tmV, bar_load, col0, grow);
+        mbar_expect_tx(bar_load, 2 * D * TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            tma_load_2d(sK + a * TILE_BYTES, &tmK, bar_load, col0 + 64 * a, grow);
+            tma_load_2d(sV + a * TILE_BYTES, &tmV, bar_load, col0 + 64 * a, grow);
+        }
     }
-    if ((tid >> 5) == 0) tmem_alloc<64>(tmem_slot);
+    if ((tid >> 5) == 0) tmem_alloc<C::TCOLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
     const uint32_t tmem = *tmem_slot;
     mbar_wait(bar_load, 0);
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        const uint32_t off = sw128_off(tid, ch);
-        float f[8];
-        *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+    for (int a = 0; a < D; ++a) {
+#pragma unroll
+        for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t off = a * TILE_BYTES + sw128_off(tid, ch);
+            float f[8];
+            *reinterpret_cast<uint4 *>(sK + off) = phi8(*reinterpret_cast<const uint4 *>(sK + off), f);
+        }
     }
     fence_proxy_async();
     tc_fence_before();
     __syncthreads();
     if (tid == 0) {
         tc_fence_after();
-        const uint64_t dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
 #pragma unroll
-        for (int k = 0; k < 8; ++k) mma_ss(tmem, dK + 128 * k, dV + 128 * k, IDESC_MM64, k > 0);
+        for (int a = 0; a < D; ++a) {
+#pragma unroll
+            for (int b = 0; b < D; ++b) {
+                const uint64_t dK = smem_desc_sw128(smem_u32(sK + a * TILE_BYTES)), dV = smem_desc_sw128(smem_u32(sV + b * TILE_BYTES));
+#pragma unroll
+                for (int k = 0; k < 8; ++k) mma_ss(tmem + 64 * (a * D + b), dK + 128 * k, dV + 128 * k, IDESC_MM64, k > 0);
+            }
+        }
         mma_commit(bar_mma);
     }
-    sdz[tid] = colsum_half(sK, tid & 63, tid >> 6, nullptr);                   // overlaps the MMA
+#pragma unroll
+    for (int a = 0; a < D; ++a) sdz[a * 128 + tid] = colsum_half(sK + a * TILE_BYTES, tid & 63, tid >> 6, nullptr);   // overlaps the MMA
     mbar_wait(bar_mma, 0);
     tc_fence_after();
-    float *dst = part + ((int64_t)nh * nchunks + c) * STATE_FLOATS;
-    state64_to_global(tmem, 0, dst);
+    float *dst = part + ((int64_t)nh * nchunks + c) * Wide<D>::STATE_F;
+#pragma unroll
+    for (int t = 0; t < D * D; ++t) state64_to_global(tmem, 64 * t, dst + 4096 * t);
     tc_fence_before();
     __syncthreads();
-    if (tid < 64) dst[4096 + tid] = sdz[tid] + sdz[64 + tid];
-    if ((tid >> 5) == 0) tmem_dealloc<64>(tmem);
+    if (tid < 64) {
+#pragma unroll
+        for (int a = 0; a < D; ++a) dst[D * D * 4096 + 64 * a + tid] = sdz[a * 128 + tid] + sdz[a * 128 + 64 + tid];
+    }
+    if ((tid >> 5) == 0) tmem_dealloc<C::TCOLS>(tmem);
 }
 
 // =============================================================================================
-// B1: G' = go/den, gd = -(go.out)/den (stored per token), dR = Qf^T G', drz = Qf^T gd
+// B1: G' = go/den, gd = -(go.out)/den (stored per token), dR_ab = Qf_a^T G'_b, drz_a = Qf_a^T gd
 // =============================================================================================
+template <int D>
 __global__ void __launch_bounds__(128)
 cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmGo,
                     const __grid_constant__ CUtensorMap tmO, const float *__restrict__ den, float *__restrict__ gd_out,
                     float *__restrict__ part, int L, int H, int nchunks) {
+    using C = PreCfg<D>;
     extern __shared__ __align__(1024) uint8_t sm[];
-    uint8_t *sQ = sm + P_OFF_A, *sG = sm + P_OFF_B, *sO = sm + P_OFF_C;
-    float *sdr = reinterpret_cast<float *>(sm + PB_OFF_MISC);                  // [2][64]
-    float *sgd = sdr + 128;                                                    // [128]
-    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + PB_OFF_MISC + 1024), *bar_mma = bar_load + 1;
+    uint8_t *sQ = sm, *sG = sm + D * TILE_BYTES, *sO = sm + 2 * D * TILE_BYTES;
+    float *sdr = reinterpret_cast<float *>(sm + C::B_MISC);                    // [D][2][64]
+    float *sgd = sdr + D * 128;                                                // [128]
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + C::B_MISC + D * 512 + 512), *bar_mma = bar_load + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
     const int tid = threadIdx.x;
     const int nh = blockIdx.x / nchunks, c = blockIdx.x % nchunks, n = nh / H, h = nh % H;
-    const int grow = n * L + c * CHUNK, col0 = h * 64;
+    const int grow = n * L + c * CHUNK, col0 = h * 64 * D;
     const bool need_state = c > 0;                     // chunk 0's increment is never consumed (suffix scan)
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         mbar_init(bar_load, 1);
         mbar_init(bar_mma, 1);
         fence_barrier_init();
-        mbar_expect_tx(bar_load, (need_state ? 3 : 2) * TILE_BYTES);
-        tma_load_2d(sG, &tmGo, bar_load, col0, grow);
-        tma_load_2d(sO, &tmO, bar_load, col0, grow);
-        if (need_state) tma_load_2d(sQ, &tmQ, bar_load, col0, grow);
+        mbar_expect_tx(bar_load, (need_state ? 3 : 2) * D * TILE_BYTES);
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            tma_load_2d(sG + a * TILE_BYTES, &tmGo, bar_load, col0 + 64 * a, grow);
+            tma_load_2d(sO + a * TILE_BYTES, &tmO, bar_load, col0 + 64 * a, grow);
+            if (need_state) tma_load_2d(sQ + a * TILE_BYTES, &tmQ, bar_load, col0 + 64 * a, grow);
+        }
     }
-    if ((tid >> 5) == 0) tmem_alloc<64>(tmem_slot);
+    if ((tid >> 5) == 0) tmem_alloc<C::TCOLS>(tmem_slot);
     const float inv = 1.f / den[(int64_t)(grow + tid) * H + h];
     tc_fence_before();
     __syncthreads();
@@ -277,17 +317,20 @@ cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     mbar_wait(bar_load, 0);
     float dot = 0.f;
 #pragma unroll
-    for (int ch = 0; ch < 8; ++ch) {
-        const uint32_t off = sw128_off(tid, ch);
-        float gg[8], o[8];
-        unpack8(*reinterpret_cast<const uint4 *>(sG + off), gg);
-        unpack8(*reinterpret_cast<const uint4 *>(sO + off), o);
+    for (int a = 0; a < D; ++a) {
 #pragma unroll
-        for (int i = 0; i < 8; ++i) { dot = fmaf(gg[i], o[i], dot); gg[i] *= inv; }
-        if (need_state) {
-            *reinterpret_cast<uint4 *>(sG + off) = pack8(gg);
-            float f[8];
-            *reinterpret_cast<uint4 *>(sQ + off) = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
+        for (int ch = 0; ch < 8; ++ch) {
+            const uint32_t off = a * TILE_BYTES + sw128_off(tid, ch);
+            float gg[8], o[8];
+            unpack8(*reinterpret_cast<const uint4 *>(sG + off), gg);
+            unpack8(*reinterpret_cast<const uint4 *>(sO + off), o);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) { dot = fmaf(gg[i], o[i], dot); gg[i] *= inv; }
+            if (need_state) {
+                *reinterpret_cast<uint4 *>(sG + off) = pack8(gg);
+                float f[8];
+                *reinterpret_cast<uint4 *>(sQ + off) = phi8(*reinterpret_cast<const uint4 *>(sQ + off), f);
+            }
         }
     }
     const float gd = -inv * dot;
@@ -299,24 +342,35 @@ cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         __syncthreads();
         if (tid == 0) {
             tc_fence_after();
-            const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dG = smem_desc_sw128(smem_u32(sG));
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mma_ss(tmem, dQ + 128 * k, dG + 128 * k, IDESC_MM64, k > 0);
+            for (int a = 0; a < D; ++a) {
+#pragma unroll
+                for (int b = 0; b < D; ++b) {
+                    const uint64_t dQ = smem_desc_sw128(smem_u32(sQ + a * TILE_BYTES)), dG = smem_desc_sw128(smem_u32(sG + b * TILE_BYTES));
+#pragma unroll
+                    for (int k = 0; k < 8; ++k) mma_ss(tmem + 64 * (a * D + b), dQ + 128 * k, dG + 128 * k, IDESC_MM64, k > 0);
+                }
+            }
             mma_commit(bar_mma);
         }
-        sdr[tid] = colsum_half(sQ, tid & 63, tid >> 6, sgd);
+#pragma unroll
+        for (int a = 0; a < D; ++a) sdr[a * 128 + tid] = colsum_half(sQ + a * TILE_BYTES, tid & 63, tid >> 6, sgd);
         mbar_wait(bar_mma, 0);
         tc_fence_after();
-        float *dst = part + ((int64_t)nh * nchunks + c) * STATE_FLOATS;
-        state64_to_global(tmem, 0, dst);
+        float *dst = part + ((int64_t)nh * nchunks + c) * Wide<D>::STATE_F;
+#pragma unroll
+        for (int t = 0; t < D * D; ++t) state64_to_global(tmem, 64 * t, dst + 4096 * t);
         tc_fence_before();
         __syncthreads();
-        if (tid < 64) dst[4096 + tid] = sdr[tid] + sdr[64 + tid];
+        if (tid < 64) {
+#pragma unroll
+            for (int a = 0; a < D; ++a) dst[D * D * 4096 + 64 * a + tid] = sdr[a * 128 + tid] + sdr[a * 128 + 64 + tid];
+        }
     } else {
         tc_fence_before();
         __syncthreads();
     }
-    if ((tid >> 5) == 0) tmem_dealloc<64>(tmem);
+    if ((tid >> 5) == 0) tmem_dealloc<C::TCOLS>(tmem);
 }
 
 // =============================================================================================
@@ -559,40 +613,47 @@ cp_suffix_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
 // F2 / B2: exclusive prefix (reverse = 0) or exclusive suffix (reverse = 1) of the per-chunk increments over
 // the chunk axis; fp32 accumulation, bf16 state tile + fp32 z out.  One thread = 4 consecutive state floats.
 // =============================================================================================
+template <int D>
 __global__ void __launch_bounds__(256)
 cp_scan_kernel(const float *__restrict__ part, uint8_t *__restrict__ tiles, float *__restrict__ zs, int nchunks, int reverse) {
+    constexpr int STATE_F = Wide<D>::STATE_F, TILE4 = Wide<D>::TILES * 1024;     // float4 groups of the tiles part
     const int nh = blockIdx.x, i4 = blockIdx.y * 256 + threadIdx.x;
-    if (i4 >= STATE_FLOATS / 4) return;
-    const float4 *src = reinterpret_cast<const float4 *>(part + (int64_t)nh * nchunks * STATE_FLOATS) + i4;
+    if (i4 >= STATE_F / 4) return;
+    const float4 *src = reinterpret_cast<const float4 *>(part + (int64_t)nh * nchunks * STATE_F) + i4;
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
     for (int s = 0; s + 1 < nchunks; ++s) {
         const int c = reverse ? nchunks - 1 - s : s;        // increment consumed
         const int d = reverse ? c - 1 : c + 1;              // chunk that receives the running sum
-        const float4 p = src[(int64_t)c * (STATE_FLOATS / 4)];
+        const float4 p = src[(int64_t)c * (STATE_F / 4)];
         acc.x += p.x; acc.y += p.y; acc.z += p.z; acc.w += p.w;
         const int64_t slot = (int64_t)nh * nchunks + d;
-        if (i4 < 1024) {
+        if (i4 < TILE4) {
             uint2 o = make_uint2(pack_bf16(acc.x, acc.y), pack_bf16(acc.z, acc.w));
-            *reinterpret_cast<uint2 *>(tiles + slot * S_TILE_BYTES + (int64_t)i4 * 8) = o;
+            *reinterpret_cast<uint2 *>(tiles + slot * Wide<D>::S_BYTES + (int64_t)i4 * 8) = o;
         } else {
-            *reinterpret_cast<float4 *>(zs + slot * 64 + (i4 - 1024) * 4) = acc;
+            *reinterpret_cast<float4 *>(zs + slot * (D * 64) + (i4 - TILE4) * 4) = acc;
         }
     }
 }
 
 // =============================================================================================
-// F3: per-chunk outputs.  256 threads (two per token row), 128 TMEM columns, 3 CTAs / SM.
-//   shared memory: sQ | sV | sS | sK..sP  (the 32 KB bf16 score tile starts on the dead K tile)
+// F3: per-chunk outputs.  256 threads (two per token row), 128 TMEM columns; 3 CTAs / SM for 64-wide heads, 1 for 128-wide.
+//   shared memory: sQ (D tiles) | sV (D) | sS (D*D state tiles) | sK (D) .. sP  (the 32 KB bf16 score tile starts on the dead K tiles)
+//   P = sum_a Qf_a Kf_a^T (masked);  O_b = sum_a Qf_a Sp_ab + P V_b  in TMEM columns [64 b, 64 b + 64);  den = rowsum P + sum_a Qf_a . z_a
 // =============================================================================================
-constexpr uint32_t F_OFF_Q = 0, F_OFF_V = 16384, F_OFF_S = 32768, F_OFF_K = 40960, F_OFF_P = 40960;
-constexpr uint32_t F_OFF_Z = 73728 /* 64 floats */, F_OFF_DP = F_OFF_Z + 256 /* 2 x 128 floats */, F_OFF_BAR = F_OFF_DP + 1024,
-                   F_SMEM = F_OFF_BAR + 32;
+template <int D> struct FwdCfg {
+    static constexpr uint32_t OFF_Q = 0, OFF_V = D * TILE_BYTES, OFF_S = 2 * D * TILE_BYTES, OFF_K = OFF_S + D * D * S_TILE_BYTES, OFF_P = OFF_K;
+    static constexpr uint32_t OFF_Z = OFF_K + 2 * TILE_BYTES /* D*64 floats */, OFF_DP = OFF_Z + D * 256 /* 2 x 128 floats */,
+                              OFF_BAR = OFF_DP + 1024, SMEM = OFF_BAR + 32;
+};
+static_assert(FwdCfg<1>::OFF_Z == 73728 && FwdCfg<1>::SMEM == 75040, "64-wide layout: three CTAs per SM");
 
 #ifndef CPM_TMA_STORE
 #define CPM_TMA_STORE 1       // output rows leave through a swizzled shared-memory tile and ONE bulk tensor store (whole 128-byte lines)
 #endif
-__global__ void __launch_bounds__(NTH, 3)
+template <int D>
+__global__ void __launch_bounds__(NTH, D == 1 ? 3 : 1)
 cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                   const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmS,
                   const __grid_constant__ CUtensorMap tmO, const float *__restrict__ zp,
@@ -600,27 +661,37 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
                   long long *__restrict__ dbg) {
     // Persistent: CTA b handles tiles b, b + gridDim.x, ... in chunk-major order (tile t = chunk t / NH of pair t % NH),
     // so barrier / TMEM set-up is paid once and the next tile's TMA loads fly while this tile's epilogue runs.
+    using C = FwdCfg<D>;
+    // bulk-store staging: the score tile's second block - dead after the second UMMA round and, with 64-wide heads, not a target
+    // of the next tile's loads (K's one tile lies under the first block).  128-wide heads have two K tiles under it: plain stores.
+    constexpr bool TMA_OUT = CPM_TMA_STORE && D == 1;
     extern __shared__ __align__(1024) uint8_t sm[];
-    uint8_t *sQ = sm + F_OFF_Q, *sK = sm + F_OFF_K, *sV = sm + F_OFF_V, *sS = sm + F_OFF_S, *sP = sm + F_OFF_P;
-    uint8_t *sOut = sP + TILE_BYTES;                  // output staging: the score tile's second block - dead after the second UMMA round
-                                                      // and, unlike K's tile under its first block, not a target of the next tile's loads
-    float *sz = reinterpret_cast<float *>(sm + F_OFF_Z), *sdp = reinterpret_cast<float *>(sm + F_OFF_DP);
-    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + F_OFF_BAR), *bar_mma = bar_load + 1;
+    uint8_t *sQ = sm + C::OFF_Q, *sK = sm + C::OFF_K, *sV = sm + C::OFF_V, *sS = sm + C::OFF_S, *sP = sm + C::OFF_P;
+    uint8_t *sOut = sP + TILE_BYTES;
+    float *sz = reinterpret_cast<float *>(sm + C::OFF_Z), *sdp = reinterpret_cast<float *>(sm + C::OFF_DP);
+    uint64_t *bar_load = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR), *bar_mma = bar_load + 1;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_load + 2);
     const int tid = threadIdx.x;
     const int ntiles = NH * nchunks;
     auto issue_loads = [&](int t) {                   // tid 0 only
         const int c = t / NH, nh = t % NH, n = nh / H, h = nh % H;
-        const int grow = n * L + c * CHUNK, col0 = h * 64;
-        mbar_expect_tx(bar_load, 3 * TILE_BYTES + (c > 0 ? S_TILE_BYTES : 0));
-        tma_load_2d(sQ, &tmQ, bar_load, col0, grow);
-        tma_load_2d(sK, &tmK, bar_load, col0, grow);
-        tma_load_2d(sV, &tmV, bar_load, col0, grow);
-        if (c > 0) tma_load_2d(sS, &tmS, bar_load, 0, (int)(((int64_t)nh * nchunks + c) * 64));
+        const int grow = n * L + c * CHUNK, col0 = h * 64 * D;
+        mbar_expect_tx(bar_load, 3 * D * TILE_BYTES + (c > 0 ? D * D * S_TILE_BYTES : 0));
+#pragma unroll
+        for (int a = 0; a < D; ++a) {
+            tma_load_2d(sQ + a * TILE_BYTES, &tmQ, bar_load, col0 + 64 * a, grow);
+            tma_load_2d(sK + a * TILE_BYTES, &tmK, bar_load, col0 + 64 * a, grow);
+            tma_load_2d(sV + a * TILE_BYTES, &tmV, bar_load, col0 + 64 * a, grow);
+        }
+        if (c > 0) {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i)
+                tma_load_2d(sS + i * S_TILE_BYTES, &tmS, bar_load, 0, (int)((((int64_t)nh * nchunks + c) * (D * D) + i) * 64));
+        }
     };
-    auto fetch_z = [&](int t) -> float {              // tid < 64: the key-sum prefix of tile t (0 for a sequence's first chunk)
+    auto fetch_z = [&](int t) -> float {              // tid < 64 D: the key-sum prefix of tile t (0 for a sequence's first chunk)
         const int c = t / NH, nh = t % NH;
-        return c > 0 ? zp[((int64_t)nh * nchunks + c) * 64 + tid] : 0.f;
+        return c > 0 ? zp[((int64_t)nh * nchunks + c) * (64 * D) + tid] : 0.f;
     };
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
@@ -630,7 +701,7 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         if ((int)blockIdx.x < ntiles) issue_loads(blockIdx.x);
     }
     if ((tid >> 5) == 0) tmem_alloc<128>(tmem_slot);
-    if (tid < 64 && (int)blockIdx.x < ntiles) sz[tid] = fetch_z(blockIdx.x);
+    if (tid < 64 * D && (int)blockIdx.x < ntiles) sz[tid] = fetch_z(blockIdx.x);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -638,60 +709,71 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
     const Geo g(tmem);
     const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
     const uint64_t dP = smem_desc_sw128(smem_u32(sP)), dS = smem_desc_sw128(smem_u32(sS));
+    constexpr uint32_t TSTEP = TILE_BYTES >> 4, SSTEP = S_TILE_BYTES >> 4;          // descriptor steps to the next operand / state tile
     uint32_t ph_load = 0, ph_mma = 0;
     int dbg_i = 0;
 #define CPM_STAMP() do { if (dbg && tid == 0 && dbg_i < 64) dbg[(int64_t)blockIdx.x * 64 + dbg_i++] = clock64(); } while (0)
     CPM_STAMP();
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
         const int c = t / NH, nh = t % NH, n = nh / H, h = nh % H;
-        const int grow = n * L + c * CHUNK, col0 = h * 64;
+        const int grow = n * L + c * CHUNK, col0 = h * 64 * D;
         const bool have_state = c > 0;
         const int tn = t + gridDim.x;
         float z_next = 0.f;                               // prefetched now, parked in a register until the epilogue
-        if (tid < 64 && tn < ntiles) z_next = fetch_z(tn);
+        if (tid < 64 * D && tn < ntiles) z_next = fetch_z(tn);
         mbar_wait(bar_load, ph_load);
         ph_load ^= 1;
         CPM_STAMP();
         float den_part = 0.f;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const int ch = 4 * g.half + cc;
-            const uint32_t off = sw128_off(g.row, ch);
-            *reinterpret_cast<uint4 *>(sQ + off) = phi8_dot(*reinterpret_cast<const uint4 *>(sQ + off), sz + 8 * ch, den_part);
-            *reinterpret_cast<uint4 *>(sK + off) = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
+        for (int a = 0; a < D; ++a) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const int ch = 4 * g.half + cc;
+                const uint32_t off = a * TILE_BYTES + sw128_off(g.row, ch);
+                *reinterpret_cast<uint4 *>(sQ + off) = phi8_dot(*reinterpret_cast<const uint4 *>(sQ + off), sz + 64 * a + 8 * ch, den_part);
+                *reinterpret_cast<uint4 *>(sK + off) = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
+            }
         }
-#if CPM_TMA_STORE
-        if (tid == 0) tma_store_wait_read0();             // the previous tile's output store has read its staging block (long ago)
-#endif
+        if (TMA_OUT && tid == 0) tma_store_wait_read0();  // the previous tile's output store has read its staging block (long ago)
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         CPM_STAMP();
-        if (tid == 0) {                                   // P = Qf Kf^T
+        if (tid == 0) {                                   // P = sum_a Qf_a Kf_a^T
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ss(tmem, dQ + 2 * k, dK + 2 * k, IDESC_KK128, k > 0);
+            for (int a = 0; a < D; ++a) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem, dQ + a * TSTEP + 2 * k, dK + a * TSTEP + 2 * k, IDESC_KK128, (a | k) > 0);
+            }
             mma_commit(bar_mma);
         }
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
         CPM_STAMP();
-        den_part += convert_lean<true, false, false, true>(g, 0, sP, 0.f, nullptr);           // overwrites the dead K tile
+        den_part += convert_lean<true, false, false, true>(g, 0, sP, 0.f, nullptr);           // overwrites the dead K tiles
         sdp[g.half * 128 + g.row] = den_part;
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         CPM_STAMP();
-        if (tid == 0) {                                   // O = Qf Sp + P V   (into the score tile's first 64 columns)
+        if (tid == 0) {                                   // O_b = sum_a Qf_a Sp_ab + P V_b   (onto the score tile's columns [64 b, 64 b + 64))
             tc_fence_after();
-            uint32_t acc = 0;
-            if (have_state) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) { mma_ss(tmem, dQ + 2 * k, dS + 128 * k, IDESC_KM64, acc); acc = 1; }
+            for (int b = 0; b < D; ++b) {
+                uint32_t acc = 0;
+                if (have_state) {
+#pragma unroll
+                    for (int a = 0; a < D; ++a) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) { mma_ss(tmem + 64 * b, dQ + a * TSTEP + 2 * k, dS + (a * D + b) * SSTEP + 128 * k, IDESC_KM64, acc); acc = 1; }
+                    }
+                }
+#pragma unroll
+                for (int k = 0; k < 8; ++k) { mma_ss(tmem + 64 * b, dP + (k >> 2) * TSTEP + 2 * (k & 3), dV + b * TSTEP + 128 * k, IDESC_KM64, acc); acc = 1; }
             }
-#pragma unroll
-            for (int k = 0; k < 8; ++k) { mma_ss(tmem, dP + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dV + 128 * k, IDESC_KM64, acc); acc = 1; }
             mma_commit(bar_mma);
         }
         const float dn = sdp[g.row] + sdp[128 + g.row] + eps;
@@ -703,35 +785,32 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         CPM_STAMP();
         if (tn < ntiles) {                                // every operand tile is dead: fetch the next tile under the epilogue
             if (tid == 0) issue_loads(tn);
-            if (tid < 64) sz[tid] = z_next;
+            if (tid < 64 * D) sz[tid] = z_next;
         }
-        {
+#pragma unroll
+        for (int b = 0; b < D; ++b) {
             uint32_t r[32];
-            tmem_ld32(g.t_lane + 32 * g.half, r);
+            tmem_ld32(g.t_lane + 64 * b + 32 * g.half, r);
             tmem_ld_wait();
             uint4 o[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, inv);
-#if CPM_TMA_STORE
+            if (TMA_OUT) {
 #pragma unroll
-            for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sOut + sw128_off(g.row, 4 * g.half + cc)) = o[cc];
-            fence_proxy_async();
-#else
-            store_row32(out, ld_o, grow + g.row, col0 + 32 * g.half, o);
-#endif
+                for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sOut + sw128_off(g.row, 4 * g.half + cc)) = o[cc];
+                fence_proxy_async();
+            } else {
+                store_row32(out, ld_o, grow + g.row, col0 + 64 * b + 32 * g.half, o);
+            }
         }
         tc_fence_before();
         __syncthreads();                                  // TMEM columns, sz and sdp are reused by the next tile
         tc_fence_after();
-#if CPM_TMA_STORE
-        if (tid == 0) { tma_store_2d(&tmO, sOut, col0, grow); tma_store_commit(); }
-#endif
+        if (TMA_OUT && tid == 0) { tma_store_2d(&tmO, sOut, col0, grow); tma_store_commit(); }
         CPM_STAMP();
     }
 #undef CPM_STAMP
-#if CPM_TMA_STORE
-    if (tid == 0) tma_store_wait_all0();
-#endif
+    if (TMA_OUT && tid == 0) tma_store_wait_all0();
     if ((tid >> 5) == 0) tmem_dealloc<128>(tmem);
 }
 
@@ -744,10 +823,16 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
 // Loads are split over two barriers so the tiles that die first (Q, V, Sp after round 2) are refilled for the next
 // tile a whole round before the rest (K, G', Rs after round 3).
 // =============================================================================================
-constexpr uint32_t B_OFF_Q = 0, B_OFF_K = 16384, B_OFF_V = 32768, B_OFF_G = 49152, B_OFF_S = 65536, B_OFF_R = 73728, B_OFF_X = 81920;
-constexpr uint32_t B_OFF_GD = 114688 /* 128 floats: gd, later rz */, B_OFF_Z = B_OFF_GD + 512 /* 64 floats */, B_OFF_BAR = B_OFF_Z + 256,
-                   B_SMEM = B_OFF_BAR + 32;
-constexpr uint32_t TB_X = 0, TB_A1 = 128, TB_A2 = 192;
+template <int D> struct BwdCfg {
+    static constexpr uint32_t OFF_Q = 0, OFF_K = D * TILE_BYTES, OFF_V = 2 * D * TILE_BYTES, OFF_G = 3 * D * TILE_BYTES, OFF_S = 4 * D * TILE_BYTES,
+                              OFF_R = OFF_S + D * D * S_TILE_BYTES, OFF_X = OFF_R + D * D * S_TILE_BYTES;
+    static constexpr uint32_t OFF_GD = OFF_X + 2 * TILE_BYTES /* 128 floats: rz */, OFF_Z = OFF_GD + 512 /* D*64 floats */, OFF_BAR = OFF_Z + D * 256,
+                              SMEM = OFF_BAR + 32;
+    static constexpr uint32_t TB_X = 0, TB_A1 = 128, TB_A2 = 128 + 64 * D;        // score tile | dQf_a (D x 64 columns) | dKf_a
+    static constexpr int TCOLS = D == 1 ? 256 : 512;
+};
+static_assert(BwdCfg<1>::SMEM == 115488 && BwdCfg<1>::TB_A2 == 192, "64-wide layout: two CTAs per SM");
+static_assert(BwdCfg<2>::SMEM <= 232448, "128-wide layout: one CTA per SM, within the 227 KB a block may take");
 
 struct BwdMainArgs {
     const float *den, *gd, *zp, *rzs;
@@ -776,41 +861,62 @@ __device__ __forceinline__ void grad_row_epilogue(const uint32_t (&r)[32], const
     }
 }
 
-__global__ void __launch_bounds__(NTH, 2)
+template <int D>
+__global__ void __launch_bounds__(NTH, D == 1 ? 2 : 1)
 cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant__ CUtensorMap tmK,
                    const __grid_constant__ CUtensorMap tmV, const __grid_constant__ CUtensorMap tmGo,
                    const __grid_constant__ CUtensorMap tmS, const __grid_constant__ CUtensorMap tmR,
                    const __grid_constant__ CUtensorMap tmGq, const __grid_constant__ CUtensorMap tmGk, BwdMainArgs a) {
+    using C = BwdCfg<D>;
+    constexpr uint32_t TB_X = C::TB_X, TB_A1 = C::TB_A1, TB_A2 = C::TB_A2;
+    // dq / dk leave through the score buffer and two bulk tensor stores; 128-wide heads have four such tiles for the one 32 KB
+    // buffer and keep the 256-bit stores
+    constexpr bool TMA_OUT = CPM_TMA_STORE && D == 1;
     extern __shared__ __align__(1024) uint8_t sm[];
-    uint8_t *sQ = sm + B_OFF_Q, *sK = sm + B_OFF_K, *sV = sm + B_OFF_V, *sG = sm + B_OFF_G, *sS = sm + B_OFF_S, *sR = sm + B_OFF_R;
-    uint8_t *sX = sm + B_OFF_X;
-    float *sgd = reinterpret_cast<float *>(sm + B_OFF_GD), *sz = reinterpret_cast<float *>(sm + B_OFF_Z);
-    uint64_t *bar_a = reinterpret_cast<uint64_t *>(sm + B_OFF_BAR), *bar_b = bar_a + 1, *bar_mma = bar_a + 2;
+    uint8_t *sQ = sm + C::OFF_Q, *sK = sm + C::OFF_K, *sV = sm + C::OFF_V, *sG = sm + C::OFF_G, *sS = sm + C::OFF_S, *sR = sm + C::OFF_R;
+    uint8_t *sX = sm + C::OFF_X;
+    float *sgd = reinterpret_cast<float *>(sm + C::OFF_GD), *sz = reinterpret_cast<float *>(sm + C::OFF_Z);
+    uint64_t *bar_a = reinterpret_cast<uint64_t *>(sm + C::OFF_BAR), *bar_b = bar_a + 1, *bar_mma = bar_a + 2;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(bar_a + 3);
     const int tid = threadIdx.x;
     const int ntiles = a.NH * a.nchunks;
-    auto tile_coords = [&](int t, int &c, int &nh, int &grow, int &col0) {
+    auto tile_coords = [&](int t, int &c, int &nh, int &grow, int &col0, int &h) {
         c = t / a.NH; nh = t % a.NH;
-        const int n = nh / a.H, h = nh % a.H;
-        grow = n * a.L + c * CHUNK; col0 = h * 64;
+        const int n = nh / a.H;
+        h = nh % a.H;
+        grow = n * a.L + c * CHUNK; col0 = h * 64 * D;
     };
     auto issue_a = [&](int t) {                       // tid 0: the tiles that die last (after round 3): K, go, Rs
-        int c, nh, grow, col0;
-        tile_coords(t, c, nh, grow, col0);
+        int c, nh, grow, col0, h;
+        tile_coords(t, c, nh, grow, col0, h);
         const bool hr = c + 1 < a.nchunks;
-        mbar_expect_tx(bar_a, 2 * TILE_BYTES + (hr ? S_TILE_BYTES : 0));
-        tma_load_2d(sK, &tmK, bar_a, col0, grow);
-        tma_load_2d(sG, &tmGo, bar_a, col0, grow);
-        if (hr) tma_load_2d(sR, &tmR, bar_a, 0, (int)(((int64_t)nh * a.nchunks + c) * 64));
+        mbar_expect_tx(bar_a, 2 * D * TILE_BYTES + (hr ? D * D * S_TILE_BYTES : 0));
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            tma_load_2d(sK + i * TILE_BYTES, &tmK, bar_a, col0 + 64 * i, grow);
+            tma_load_2d(sG + i * TILE_BYTES, &tmGo, bar_a, col0 + 64 * i, grow);
+        }
+        if (hr) {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i)
+                tma_load_2d(sR + i * S_TILE_BYTES, &tmR, bar_a, 0, (int)((((int64_t)nh * a.nchunks + c) * (D * D) + i) * 64));
+        }
     };
     auto issue_b = [&](int t) {                       // tid 0: the tiles that die after round 2: Q, V, Sp
-        int c, nh, grow, col0;
-        tile_coords(t, c, nh, grow, col0);
+        int c, nh, grow, col0, h;
+        tile_coords(t, c, nh, grow, col0, h);
         const bool hs = c > 0;
-        mbar_expect_tx(bar_b, 2 * TILE_BYTES + (hs ? S_TILE_BYTES : 0));
-        tma_load_2d(sQ, &tmQ, bar_b, col0, grow);
-        tma_load_2d(sV, &tmV, bar_b, col0, grow);
-        if (hs) tma_load_2d(sS, &tmS, bar_b, 0, (int)(((int64_t)nh * a.nchunks + c) * 64));
+        mbar_expect_tx(bar_b, 2 * D * TILE_BYTES + (hs ? D * D * S_TILE_BYTES : 0));
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
+            tma_load_2d(sQ + i * TILE_BYTES, &tmQ, bar_b, col0 + 64 * i, grow);
+            tma_load_2d(sV + i * TILE_BYTES, &tmV, bar_b, col0 + 64 * i, grow);
+        }
+        if (hs) {
+#pragma unroll
+            for (int i = 0; i < D * D; ++i)
+                tma_load_2d(sS + i * S_TILE_BYTES, &tmS, bar_b, 0, (int)((((int64_t)nh * a.nchunks + c) * (D * D) + i) * 64));
+        }
     };
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
@@ -820,7 +926,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         fence_barrier_init();
         if ((int)blockIdx.x < ntiles) { issue_b(blockIdx.x); issue_a(blockIdx.x); }
     }
-    if ((tid >> 5) == 0) tmem_alloc<256>(tmem_slot);
+    if ((tid >> 5) == 0) tmem_alloc<C::TCOLS>(tmem_slot);
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -829,6 +935,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     const uint64_t dQ = smem_desc_sw128(smem_u32(sQ)), dK = smem_desc_sw128(smem_u32(sK)), dV = smem_desc_sw128(smem_u32(sV));
     const uint64_t dG = smem_desc_sw128(smem_u32(sG)), dS = smem_desc_sw128(smem_u32(sS)), dR = smem_desc_sw128(smem_u32(sR));
     const uint64_t dX = smem_desc_sw128(smem_u32(sX));
+    constexpr uint32_t TSTEP = TILE_BYTES >> 4, SSTEP = S_TILE_BYTES >> 4;          // descriptor steps to the next operand / state tile
     // The masked score tile X (rows i, 64 j contiguous per 128-byte row, two 16 KB blocks for j < 64 / j >= 64) read as an
     // MN-major A operand IS its transpose: M = j (two 64-wide atoms, LBO = one block apart), K = i.  WT = X^T (same values, same
     // mask) therefore needs no UMMA and no conversion pass of its own.
@@ -837,9 +944,9 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
     // per-row scalars of the first tile; later tiles' are prefetched one tile ahead
     float inv_n = 0.f, gd_n = 0.f;
     if ((int)blockIdx.x < ntiles) {
-        int c, nh, grow, col0;
-        tile_coords(blockIdx.x, c, nh, grow, col0);
-        const int64_t ri = (int64_t)(grow + g.row) * a.H + (col0 >> 6);
+        int c, nh, grow, col0, h;
+        tile_coords(blockIdx.x, c, nh, grow, col0, h);
+        const int64_t ri = (int64_t)(grow + g.row) * a.H + h;
         inv_n = 1.f / a.den[ri];
         gd_n = a.gd[ri];
     }
@@ -848,57 +955,64 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
 #define CPM_STAMP() do { if (a.dbg && tid == 0 && dbg_i < 128) a.dbg[(int64_t)blockIdx.x * 128 + dbg_i++] = clock64(); } while (0)
     CPM_STAMP();
     for (int t = blockIdx.x; t < ntiles; t += gridDim.x) {
-        int c, nh, grow, col0;
-        tile_coords(t, c, nh, grow, col0);
+        int c, nh, grow, col0, h;
+        tile_coords(t, c, nh, grow, col0, h);
         const bool have_s = c > 0, have_r = c + 1 < a.nchunks;
         const int64_t slot = (int64_t)nh * a.nchunks + c;
         const int tn = t + gridDim.x;
         const float inv = inv_n, gd = gd_n;
-        if (tid < 64) {                                    // z (dq epilogue) and rz (dk epilogue) of this tile
-            sz[tid] = have_s ? a.zp[slot * 64 + tid] : 0.f;
-            sgd[tid] = have_r ? a.rzs[slot * 64 + tid] : 0.f;
+        if (tid < 64 * D) {                                // z (dq epilogue) and rz (dk epilogue) of this tile
+            sz[tid] = have_s ? a.zp[slot * (64 * D) + tid] : 0.f;
+            sgd[tid] = have_r ? a.rzs[slot * (64 * D) + tid] : 0.f;
         }
         if (tn < ntiles) {                                // next tile's per-row scalars: in flight for the whole tile
-            int c2, nh2, grow2, col2;
-            tile_coords(tn, c2, nh2, grow2, col2);
-            const int64_t ri = (int64_t)(grow2 + g.row) * a.H + (col2 >> 6);
+            int c2, nh2, grow2, col2, h2;
+            tile_coords(tn, c2, nh2, grow2, col2, h2);
+            const int64_t ri = (int64_t)(grow2 + g.row) * a.H + h2;
             inv_n = a.den[ri];
             gd_n = a.gd[ri];
         }
-        uint32_t qfr[16], kfr[16];                         // this thread's Qf / Kf values (packed bf16) for phi'
+        uint32_t qfr[D][16], kfr[D][16];                   // this thread's Qf / Kf values (packed bf16) for phi'
         mbar_wait(bar_b, ph_b);
         ph_b ^= 1;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
-            const uint4 qv = phi8_lean(*reinterpret_cast<const uint4 *>(sQ + off));
-            *reinterpret_cast<uint4 *>(sQ + off) = qv;
-            qfr[4 * cc + 0] = qv.x; qfr[4 * cc + 1] = qv.y; qfr[4 * cc + 2] = qv.z; qfr[4 * cc + 3] = qv.w;
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const uint32_t off = i * TILE_BYTES + sw128_off(g.row, 4 * g.half + cc);
+                const uint4 qv = phi8_lean(*reinterpret_cast<const uint4 *>(sQ + off));
+                *reinterpret_cast<uint4 *>(sQ + off) = qv;
+                qfr[i][4 * cc + 0] = qv.x; qfr[i][4 * cc + 1] = qv.y; qfr[i][4 * cc + 2] = qv.z; qfr[i][4 * cc + 3] = qv.w;
+            }
         }
         CPM_STAMP();                                       // 1: Q, V, Sp landed; phi(Q) done
         mbar_wait(bar_a, ph_a);
         ph_a ^= 1;
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
-            const uint4 gv = *reinterpret_cast<const uint4 *>(sG + off);
-            *reinterpret_cast<uint4 *>(sG + off) = make_uint4(scale2(gv.x, inv), scale2(gv.y, inv), scale2(gv.z, inv), scale2(gv.w, inv));
-            const uint4 kv = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
-            *reinterpret_cast<uint4 *>(sK + off) = kv;
-            kfr[4 * cc + 0] = kv.x; kfr[4 * cc + 1] = kv.y; kfr[4 * cc + 2] = kv.z; kfr[4 * cc + 3] = kv.w;
+        for (int i = 0; i < D; ++i) {
+#pragma unroll
+            for (int cc = 0; cc < 4; ++cc) {
+                const uint32_t off = i * TILE_BYTES + sw128_off(g.row, 4 * g.half + cc);
+                const uint4 gv = *reinterpret_cast<const uint4 *>(sG + off);
+                *reinterpret_cast<uint4 *>(sG + off) = make_uint4(scale2(gv.x, inv), scale2(gv.y, inv), scale2(gv.z, inv), scale2(gv.w, inv));
+                const uint4 kv = phi8_lean(*reinterpret_cast<const uint4 *>(sK + off));
+                *reinterpret_cast<uint4 *>(sK + off) = kv;
+                kfr[i][4 * cc + 0] = kv.x; kfr[i][4 * cc + 1] = kv.y; kfr[i][4 * cc + 2] = kv.z; kfr[i][4 * cc + 3] = kv.w;
+            }
         }
-#if CPM_TMA_STORE
-        if (tid == 0) tma_store_wait_read0();              // the previous tile's dq / dk stores have read the score buffer (long ago)
-#endif
+        if (TMA_OUT && tid == 0) tma_store_wait_read0();   // the previous tile's dq / dk stores have read the score buffer (long ago)
         fence_proxy_async();
         tc_fence_before();
         __syncthreads();
         CPM_STAMP();                                       // 2: K, go, Rs landed; G', phi(K) done; CTA in step
-        // ---- round 1: X = G' V^T
+        // ---- round 1: X = sum_b G'_b V_b^T
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dG + 2 * k, dV + 2 * k, IDESC_KK128, k > 0);
+            for (int b = 0; b < D; ++b) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dG + b * TSTEP + 2 * k, dV + b * TSTEP + 2 * k, IDESC_KK128, (b | k) > 0);
+            }
             mma_commit(bar_mma);
         }
         mbar_wait(bar_mma, ph_mma);
@@ -910,24 +1024,39 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_before();
         __syncthreads();
         CPM_STAMP();                                       // 4: X converted; CTA in step
-        // ---- round 2: dQf = X Kf (+ G' Sp^T) ; dKf = X^T Qf (+ v Rs^T) ; PT = Kf Qf^T
+        // ---- round 2: dQf_a = X Kf_a (+ sum_b G'_b Sp_ab^T) ; dKf_a = X^T Qf_a (+ sum_b v_b Rs_ab^T) ; PT = sum_a Kf_a Qf_a^T
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                mma_ss(tmem + TB_A1, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dK + 128 * k, IDESC_KM64, k > 0);
-            if (have_s) {
+            for (int i = 0; i < D; ++i) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1, dG + 2 * k, dS + 2 * k, IDESC_KK64, 1);
+                for (int k = 0; k < 8; ++k)
+                    mma_ss(tmem + TB_A1 + 64 * i, dX + (k >> 2) * TSTEP + 2 * (k & 3), dK + i * TSTEP + 128 * k, IDESC_KM64, k > 0);
+                if (have_s) {
+#pragma unroll
+                    for (int b = 0; b < D; ++b) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A1 + 64 * i, dG + b * TSTEP + 2 * k, dS + (i * D + b) * SSTEP + 2 * k, IDESC_KK64, 1);
+                    }
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 8; ++k) mma_ss(tmem + TB_A2, dXT + 128 * k, dQ + 128 * k, IDESC_MM128, k > 0);
-            if (have_r) {
+            for (int i = 0; i < D; ++i) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A2, dV + 2 * k, dR + 2 * k, IDESC_KK64, 1);
+                for (int k = 0; k < 8; ++k) mma_ss(tmem + TB_A2 + 64 * i, dXT + 128 * k, dQ + i * TSTEP + 128 * k, IDESC_MM128, k > 0);
+                if (have_r) {
+#pragma unroll
+                    for (int b = 0; b < D; ++b) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_A2 + 64 * i, dV + b * TSTEP + 2 * k, dR + (i * D + b) * SSTEP + 2 * k, IDESC_KK64, 1);
+                    }
+                }
             }
 #pragma unroll
-            for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dQ + 2 * k, IDESC_KK128, k > 0);
+            for (int i = 0; i < D; ++i) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + i * TSTEP + 2 * k, dQ + i * TSTEP + 2 * k, IDESC_KK128, (i | k) > 0);
+            }
             mma_commit(bar_mma);
         }
         mbar_wait(bar_mma, ph_mma);
@@ -942,47 +1071,40 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_before();
         __syncthreads();
         CPM_STAMP();                                       // 6: PT converted; CTA in step
-        // ---- round 3: dv = PT G' (+ Kf Rs)
+        // ---- round 3: dv_b = PT G'_b (+ sum_a Kf_a Rs_ab)
         if (tid == 0) {
             tc_fence_after();
 #pragma unroll
-            for (int k = 0; k < 8; ++k)
-                mma_ss(tmem + TB_X, dX + (k >> 2) * (TILE_BYTES >> 4) + 2 * (k & 3), dG + 128 * k, IDESC_KM64, k > 0);
-            if (have_r) {
+            for (int b = 0; b < D; ++b) {
 #pragma unroll
-                for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X, dK + 2 * k, dR + 128 * k, IDESC_KM64, 1);
+                for (int k = 0; k < 8; ++k)
+                    mma_ss(tmem + TB_X + 64 * b, dX + (k >> 2) * TSTEP + 2 * (k & 3), dG + b * TSTEP + 128 * k, IDESC_KM64, k > 0);
+                if (have_r) {
+#pragma unroll
+                    for (int i = 0; i < D; ++i) {
+#pragma unroll
+                        for (int k = 0; k < 4; ++k) mma_ss(tmem + TB_X + 64 * b, dK + i * TSTEP + 2 * k, dR + (i * D + b) * SSTEP + 128 * k, IDESC_KM64, 1);
+                    }
+                }
             }
             mma_commit(bar_mma);
         }
-#if CPM_TMA_STORE
-        // dq / dk rows: finished in registers while round 3 runs; once it is done the score buffer is free and stages them
-        // (swizzled, block 0 = dq, block 1 = dk) for two bulk tensor stores - whole lines instead of 32-byte pieces per lane.
+        // dq / dk rows.  64-wide heads: finished in registers while round 3 runs; once it is done the score buffer is free and
+        // stages them (swizzled, block 0 = dq, block 1 = dk) for two bulk tensor stores - whole lines instead of 32-byte pieces per lane.
         uint4 oq[4], ok[4];
-        {
-            tc_fence_after();
+        tc_fence_after();
+#pragma unroll
+        for (int i = 0; i < D; ++i) {
             uint32_t r[32];
-            tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
+            tmem_ld32(g.t_lane + TB_A1 + 64 * i + 32 * g.half, r);
             tmem_ld_wait();
-            grad_row_epilogue<true>(r, qfr, sz + 32 * g.half, gd, oq);
-            tmem_ld32(g.t_lane + TB_A2 + 32 * g.half, r);
+            grad_row_epilogue<true>(r, qfr[i], sz + 64 * i + 32 * g.half, gd, oq);
+            if (!TMA_OUT) store_row32(a.gq, a.ld_g, grow + g.row, col0 + 64 * i + 32 * g.half, oq);
+            tmem_ld32(g.t_lane + TB_A2 + 64 * i + 32 * g.half, r);
             tmem_ld_wait();
-            grad_row_epilogue<true>(r, kfr, sgd + 32 * g.half, 1.f, ok);
+            grad_row_epilogue<true>(r, kfr[i], sgd + 64 * i + 32 * g.half, 1.f, ok);
+            if (!TMA_OUT) store_row32(a.gk, a.ld_g, grow + g.row, col0 + 64 * i + 32 * g.half, ok);
         }
-#else
-        {   // dq and dk rows
-            tc_fence_after();
-            uint32_t r[32];
-            tmem_ld32(g.t_lane + TB_A1 + 32 * g.half, r);
-            tmem_ld_wait();
-            uint4 o[4];
-            grad_row_epilogue<true>(r, qfr, sz + 32 * g.half, gd, o);
-            store_row32(a.gq, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
-            tmem_ld32(g.t_lane + TB_A2 + 32 * g.half, r);
-            tmem_ld_wait();
-            grad_row_epilogue<true>(r, kfr, sgd + 32 * g.half, 1.f, o);
-            store_row32(a.gk, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
-        }
-#endif
         if (tn < ntiles) inv_n = 1.f / inv_n;              // (prefetched den of the next tile)
         CPM_STAMP();                                       // 7: dq, dk rows computed (stored, without the bulk store)
         mbar_wait(bar_mma, ph_mma);
@@ -990,49 +1112,38 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         CPM_STAMP();                                       // 8: round 3 done
         if (tid == 0 && tn < ntiles) issue_a(tn);
-#if CPM_TMA_STORE
+        if (TMA_OUT) {
 #pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
-            *reinterpret_cast<uint4 *>(sX + off) = oq[cc];
-            *reinterpret_cast<uint4 *>(sX + TILE_BYTES + off) = ok[cc];
+            for (int cc = 0; cc < 4; ++cc) {
+                const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
+                *reinterpret_cast<uint4 *>(sX + off) = oq[cc];
+                *reinterpret_cast<uint4 *>(sX + TILE_BYTES + off) = ok[cc];
+            }
+            fence_proxy_async();
         }
-        fence_proxy_async();
-#endif
-        {   // dv rows
+#pragma unroll
+        for (int b = 0; b < D; ++b) {   // dv rows
             uint32_t r[32];
-            tmem_ld32(g.t_lane + TB_X + 32 * g.half, r);
+            tmem_ld32(g.t_lane + TB_X + 64 * b + 32 * g.half, r);
             tmem_ld_wait();
             uint4 o[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, 1.f);
-            store_row32(a.gv, a.ld_g, grow + g.row, col0 + 32 * g.half, o);
+            store_row32(a.gv, a.ld_g, grow + g.row, col0 + 64 * b + 32 * g.half, o);
         }
         tc_fence_before();
         __syncthreads();                                  // TMEM accumulators, sgd, sz are reused by the next tile
         tc_fence_after();
-#if CPM_TMA_STORE
-        if (tid == 0) {
+        if (TMA_OUT && tid == 0) {
             tma_store_2d(&tmGq, sX, col0, grow);
             tma_store_2d(&tmGk, sX + TILE_BYTES, col0, grow);
             tma_store_commit();
         }
-#endif
         CPM_STAMP();                                       // 9: dv rows stored; CTA in step
     }
 #undef CPM_STAMP
-#if CPM_TMA_STORE
-    if (tid == 0) tma_store_wait_all0();
-#endif
-    if ((tid >> 5) == 0) tmem_dealloc<256>(tmem);
-}
-
-int set_smem_once(const void *fn, uint32_t bytes, bool *done, const char *what) {
-    if (*done) return CPM_OK;
-    cudaError_t e = cudaFuncSetAttribute(fn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
-    if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "%s smem attribute: %s", what, cudaGetErrorString(e));
-    *done = true;
-    return CPM_OK;
+    if (TMA_OUT && tid == 0) tma_store_wait_all0();
+    if ((tid >> 5) == 0) tmem_dealloc<C::TCOLS>(tmem);
 }
 
 }  // namespace
@@ -1042,90 +1153,109 @@ int set_smem_once(const void *fn, uint32_t bytes, bool *done, const char *what) 
 static long long *g_cp_timing = nullptr;
 void linattn_cp_set_timing_buffer(long long *p) { g_cp_timing = p; }
 
-// workspace: [increments fp32 NHC x 4160][Sp region][Rs region][gd fp32 N*L*H]
-int64_t linattn_cp_workspace_bytes(int N, int L, int H) {
-    if (L % CHUNK != 0) return 0;
+// workspace: [increments fp32 NHC x Wide<D>::STATE_F][Sp region][Rs region][gd fp32 N*L*H];  width = 64 D
+int64_t linattn_cp_workspace_bytes(int N, int L, int H, int width) {
+    if (L % CHUNK != 0 || (width != 64 && width != 128)) return 0;
     const int64_t nhc = (int64_t)N * H * (L / CHUNK);
-    return nhc * STATE_FLOATS * 4 + 2 * state_region_bytes(nhc) + (int64_t)N * L * H * 4;
+    if (width == 128) return nhc * Wide<2>::STATE_F * 4 + 2 * state_region_bytes_w<2>(nhc) + (int64_t)N * L * H * 4;
+    return nhc * Wide<1>::STATE_F * 4 + 2 * state_region_bytes_w<1>(nhc) + (int64_t)N * L * H * 4;
 }
-int64_t linattn_cp_saved_bytes(int N, int L, int H) {
-    if (L % CHUNK != 0) return 0;
-    return state_region_bytes((int64_t)N * H * (L / CHUNK));
+int64_t linattn_cp_saved_bytes(int N, int L, int H, int width) {
+    if (L % CHUNK != 0 || (width != 64 && width != 128)) return 0;
+    const int64_t nhc = (int64_t)N * H * (L / CHUNK);
+    return width == 128 ? state_region_bytes_w<2>(nhc) : state_region_bytes_w<1>(nhc);
 }
 
 namespace {
-// F1 + F2 into a state region (tiles | z)
+template <typename K> int smem_attr(K kernel, uint32_t bytes, const char *what) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)bytes);
+    if (e != cudaSuccess) return fail(CPM_ERR_CUDA, "%s smem attribute: %s", what, cudaGetErrorString(e));
+    return CPM_OK;
+}
+template <int D> int set_attrs_once() {               // opt-in shared-memory sizes of every kernel of this head width
+    static bool done = false;
+    if (done) return CPM_OK;
+    int rc;
+    if ((rc = smem_attr(cp_state_fwd_kernel<D>, PreCfg<D>::F_SMEM, "cp_state_fwd"))) return rc;
+    if ((rc = smem_attr(cp_state_bwd_kernel<D>, PreCfg<D>::B_SMEM, "cp_state_bwd"))) return rc;
+    if ((rc = smem_attr(cp_out_fwd_kernel<D>, FwdCfg<D>::SMEM, "cp_out_fwd"))) return rc;
+    if ((rc = smem_attr(cp_bwd_main_kernel<D>, BwdCfg<D>::SMEM, "cp_bwd_main"))) return rc;
+    if (D == 1) {
+        if ((rc = smem_attr(cp_prefix_stream_fwd_kernel, ST_SMEM, "cp_prefix_stream_fwd"))) return rc;
+        if ((rc = smem_attr(cp_suffix_stream_bwd_kernel, SB_SMEM, "cp_suffix_stream_bwd"))) return rc;
+    }
+    done = true;
+    return CPM_OK;
+}
+// the streaming state kernels (one CTA per chain, state carried in TMEM) exist for 64-wide heads; they need enough chains to fill the GPU
+template <int D> bool use_stream(int N, int H) { return D == 1 && N * H >= 96; }
+
+// F1 + F2 (or F1s) into a state region (tiles | z)
+template <int D>
 int prefix_states(const void *k, const void *v, int N, int L, int H, int64_t ld_qkv, float *part, uint8_t *region, cudaStream_t st) {
     const int nchunks = L / CHUNK;
     if (nchunks <= 1) return CPM_OK;
     const int64_t nhc = (int64_t)N * H * nchunks;
     CUtensorMap tk, tv;
     int rc;
-    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
+    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64 * D;
     if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
-    float *zs = reinterpret_cast<float *>(region + state_tiles_bytes(nhc));
-    if (N * H >= 96) {                                  // enough independent (batch, head) chains: stream, no scan
-        static bool as = false;
-        if ((rc = set_smem_once((const void *)cp_prefix_stream_fwd_kernel, ST_SMEM, &as, "cp_prefix_stream_fwd"))) return rc;
+    float *zs = reinterpret_cast<float *>(region + state_tiles_bytes_w<D>(nhc));
+    if (use_stream<D>(N, H)) {
         cp_prefix_stream_fwd_kernel<<<N * H, NTH, ST_SMEM, st>>>(tk, tv, region, zs, L, H, nchunks);
         return check_launch("linattn_cp prefix stream");
     }
-    static bool a1 = false;
-    if ((rc = set_smem_once((const void *)cp_state_fwd_kernel, PF_SMEM, &a1, "cp_state_fwd"))) return rc;
-    cp_state_fwd_kernel<<<N * H * (nchunks - 1), 128, PF_SMEM, st>>>(tk, tv, part, L, H, nchunks);
-    cp_scan_kernel<<<dim3(N * H, (STATE_FLOATS / 4 + 255) / 256), 256, 0, st>>>(part, region, reinterpret_cast<float *>(region + state_tiles_bytes(nhc)),
-                                                                                nchunks, 0);
+    cp_state_fwd_kernel<D><<<N * H * (nchunks - 1), 128, PreCfg<D>::F_SMEM, st>>>(tk, tv, part, L, H, nchunks);
+    cp_scan_kernel<D><<<dim3(N * H, (Wide<D>::STATE_F / 4 + 255) / 256), 256, 0, st>>>(part, region, zs, nchunks, 0);
     return check_launch("linattn_cp prefix states");
 }
-}  // namespace
 
-int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int64_t ld_qkv,
-                          int64_t ld_o, float eps, void *ws, void *saved, cudaStream_t st) {
-    if (L % CHUNK != 0) return CPM_ERR_UNSUPPORTED;
+template <int D>
+int fwd_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int64_t ld_qkv, int64_t ld_o,
+               float eps, void *ws, void *saved, cudaStream_t st) {
     const int nchunks = L / CHUNK;
     const int64_t nhc = (int64_t)N * H * nchunks;
-    if (nhc * 64 > 0x7fffffffLL) return CPM_ERR_UNSUPPORTED;
+    if (nhc * 64 * D * D > 0x7fffffffLL) return CPM_ERR_UNSUPPORTED;
     float *part = reinterpret_cast<float *>(ws);
-    uint8_t *region = saved ? reinterpret_cast<uint8_t *>(saved) : reinterpret_cast<uint8_t *>(ws) + nhc * STATE_FLOATS * 4;
+    uint8_t *region = saved ? reinterpret_cast<uint8_t *>(saved) : reinterpret_cast<uint8_t *>(ws) + nhc * Wide<D>::STATE_F * 4;
     int rc;
-    if ((rc = prefix_states(k, v, N, L, H, ld_qkv, part, region, st))) return rc;
+    if ((rc = set_attrs_once<D>())) return rc;
+    if ((rc = prefix_states<D>(k, v, N, L, H, ld_qkv, part, region, st))) return rc;
     CUtensorMap tq, tk, tv, ts, to;
-    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
+    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64 * D;
     if ((rc = make_tmap_bf16_2d(&tq, q, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&to, out, inner, rows, ld_o, CHUNK))) return rc;
-    if ((rc = make_tmap_bf16_2d(&ts, region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
-    static bool a3 = false;
-    if ((rc = set_smem_once((const void *)cp_out_fwd_kernel, F_SMEM, &a3, "cp_out_fwd"))) return rc;
-    const int64_t slots = 3ll * num_sms();
-    cp_out_fwd_kernel<<<(unsigned)(nhc < slots ? nhc : slots), NTH, F_SMEM, st>>>(
-        tq, tk, tv, ts, to, reinterpret_cast<const float *>(region + state_tiles_bytes(nhc)), out, den, L, H, nchunks, N * H, ld_o, eps,
+    if ((rc = make_tmap_bf16_2d(&ts, region, 64, (uint64_t)nhc * 64 * D * D, 64, 64))) return rc;
+    const int64_t slots = (D == 1 ? 3ll : 1ll) * num_sms();
+    cp_out_fwd_kernel<D><<<(unsigned)(nhc < slots ? nhc : slots), NTH, FwdCfg<D>::SMEM, st>>>(
+        tq, tk, tv, ts, to, reinterpret_cast<const float *>(region + state_tiles_bytes_w<D>(nhc)), out, den, L, H, nchunks, N * H, ld_o, eps,
         g_cp_timing);
     return check_launch("linattn_fwd_cp");
 }
 
-int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout,
-                          void *gq, void *gk, void *gv, int N, int L, int H, int64_t ld_qkv, int64_t ld_o, int64_t ld_g,
-                          void *ws, const void *saved, cudaStream_t st) {
-    if (L % CHUNK != 0) return CPM_ERR_UNSUPPORTED;
+template <int D>
+int bwd_launch(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout, void *gq, void *gk,
+               void *gv, int N, int L, int H, int64_t ld_qkv, int64_t ld_o, int64_t ld_g, void *ws, const void *saved, cudaStream_t st) {
     const int nchunks = L / CHUNK;
     const int64_t nhc = (int64_t)N * H * nchunks;
-    if (nhc * 64 > 0x7fffffffLL) return CPM_ERR_UNSUPPORTED;
+    if (nhc * 64 * D * D > 0x7fffffffLL) return CPM_ERR_UNSUPPORTED;
     uint8_t *w8 = reinterpret_cast<uint8_t *>(ws);
     float *part = reinterpret_cast<float *>(w8);
-    uint8_t *sp_region = w8 + nhc * STATE_FLOATS * 4;
-    uint8_t *rs_region = sp_region + state_region_bytes(nhc);
-    float *gd = reinterpret_cast<float *>(rs_region + state_region_bytes(nhc));
+    uint8_t *sp_region = w8 + nhc * Wide<D>::STATE_F * 4;
+    uint8_t *rs_region = sp_region + state_region_bytes_w<D>(nhc);
+    float *gd = reinterpret_cast<float *>(rs_region + state_region_bytes_w<D>(nhc));
     int rc;
+    if ((rc = set_attrs_once<D>())) return rc;
     if (!saved) {                                       // forward did not keep its prefix states: rebuild them
-        if ((rc = prefix_states(k, v, N, L, H, ld_qkv, part, sp_region, st))) return rc;
+        if ((rc = prefix_states<D>(k, v, N, L, H, ld_qkv, part, sp_region, st))) return rc;
     } else {
         sp_region = const_cast<uint8_t *>(reinterpret_cast<const uint8_t *>(saved));
     }
     CUtensorMap tq, tk, tv, tgo, to, ts, tr, tgq, tgk;
-    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64;
+    const uint64_t rows = (uint64_t)N * L, inner = (uint64_t)H * 64 * D;
     if ((rc = make_tmap_bf16_2d(&tq, q, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tk, k, inner, rows, ld_qkv, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tv, v, inner, rows, ld_qkv, CHUNK))) return rc;
@@ -1133,30 +1263,43 @@ int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const voi
     if ((rc = make_tmap_bf16_2d(&to, out, inner, rows, ld_o, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tgq, gq, inner, rows, ld_g, CHUNK))) return rc;
     if ((rc = make_tmap_bf16_2d(&tgk, gk, inner, rows, ld_g, CHUNK))) return rc;
-    if ((rc = make_tmap_bf16_2d(&ts, sp_region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
-    if ((rc = make_tmap_bf16_2d(&tr, rs_region, 64, (uint64_t)nhc * 64, 64, 64))) return rc;
-    static bool a1 = false, a3 = false, a5 = false;
-    if ((rc = set_smem_once((const void *)cp_state_bwd_kernel, PB_SMEM, &a1, "cp_state_bwd"))) return rc;
-    if ((rc = set_smem_once((const void *)cp_bwd_main_kernel, B_SMEM, &a3, "cp_bwd_main"))) return rc;
-    if ((rc = set_smem_once((const void *)cp_suffix_stream_bwd_kernel, SB_SMEM, &a5, "cp_suffix_stream_bwd"))) return rc;
-    if (N * H >= 96) {                                  // enough independent (batch, head) chains: stream, no scan
-        cp_suffix_stream_bwd_kernel<<<N * H, NTH, SB_SMEM, st>>>(tq, tgo, to, den, gd, rs_region,
-                                                                 reinterpret_cast<float *>(rs_region + state_tiles_bytes(nhc)), L, H, nchunks);
+    if ((rc = make_tmap_bf16_2d(&ts, sp_region, 64, (uint64_t)nhc * 64 * D * D, 64, 64))) return rc;
+    if ((rc = make_tmap_bf16_2d(&tr, rs_region, 64, (uint64_t)nhc * 64 * D * D, 64, 64))) return rc;
+    float *rzs = reinterpret_cast<float *>(rs_region + state_tiles_bytes_w<D>(nhc));
+    if (use_stream<D>(N, H)) {
+        cp_suffix_stream_bwd_kernel<<<N * H, NTH, SB_SMEM, st>>>(tq, tgo, to, den, gd, rs_region, rzs, L, H, nchunks);
     } else {
-        cp_state_bwd_kernel<<<(unsigned)nhc, 128, PB_SMEM, st>>>(tq, tgo, to, den, gd, part, L, H, nchunks);
+        cp_state_bwd_kernel<D><<<(unsigned)nhc, 128, PreCfg<D>::B_SMEM, st>>>(tq, tgo, to, den, gd, part, L, H, nchunks);
         if (nchunks > 1)
-            cp_scan_kernel<<<dim3(N * H, (STATE_FLOATS / 4 + 255) / 256), 256, 0, st>>>(part, rs_region,
-                                                                                        reinterpret_cast<float *>(rs_region + state_tiles_bytes(nhc)), nchunks, 1);
+            cp_scan_kernel<D><<<dim3(N * H, (Wide<D>::STATE_F / 4 + 255) / 256), 256, 0, st>>>(part, rs_region, rzs, nchunks, 1);
     }
     BwdMainArgs a;
     a.den = den; a.gd = gd;
-    a.zp = reinterpret_cast<const float *>(sp_region + state_tiles_bytes(nhc));
-    a.rzs = reinterpret_cast<const float *>(rs_region + state_tiles_bytes(nhc));
+    a.zp = reinterpret_cast<const float *>(sp_region + state_tiles_bytes_w<D>(nhc));
+    a.rzs = rzs;
     a.gq = gq; a.gk = gk; a.gv = gv; a.ld_g = ld_g; a.L = L; a.H = H; a.nchunks = nchunks; a.NH = N * H;
     a.dbg = g_cp_timing;
-    const int64_t slots = 2ll * num_sms();
-    cp_bwd_main_kernel<<<(unsigned)(nhc < slots ? nhc : slots), NTH, B_SMEM, st>>>(tq, tk, tv, tgo, ts, tr, tgq, tgk, a);
+    const int64_t slots = (D == 1 ? 2ll : 1ll) * num_sms();
+    cp_bwd_main_kernel<D><<<(unsigned)(nhc < slots ? nhc : slots), NTH, BwdCfg<D>::SMEM, st>>>(tq, tk, tv, tgo, ts, tr, tgq, tgk, a);
     return check_launch("linattn_bwd_cp");
+}
+}  // namespace
+
+bool linattn_cp_streams(int N, int H, int width) { return width == 64 && N * H >= 96; }
+
+int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int width,
+                          int64_t ld_qkv, int64_t ld_o, float eps, void *ws, void *saved, cudaStream_t st) {
+    if (L % CHUNK != 0 || (width != 64 && width != 128)) return CPM_ERR_UNSUPPORTED;
+    return width == 128 ? fwd_launch<2>(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, ws, saved, st)
+                        : fwd_launch<1>(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, ws, saved, st);
+}
+
+int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout,
+                          void *gq, void *gk, void *gv, int N, int L, int H, int width, int64_t ld_qkv, int64_t ld_o, int64_t ld_g,
+                          void *ws, const void *saved, cudaStream_t st) {
+    if (L % CHUNK != 0 || (width != 64 && width != 128)) return CPM_ERR_UNSUPPORTED;
+    return width == 128 ? bwd_launch<2>(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, ws, saved, st)
+                        : bwd_launch<1>(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, ws, saved, st);
 }
 
 }  // namespace cpm

@@ -36,13 +36,15 @@ int linattn_segment_states_launch(const void *q, const void *k, const void *v, c
                                   const void *gout, int N, int L, int H, int64_t ld_qkv, int64_t ld_o, int dtype, void *ws,
                                   bool reverse_too, cudaStream_t st);
 // chunk-parallel tcgen05 path (linattn_cp.cu)
-int64_t linattn_cp_workspace_bytes(int N, int L, int H);
-int64_t linattn_cp_saved_bytes(int N, int L, int H);
+// width = head width: 64 (the reference's heads) or 128
+int64_t linattn_cp_workspace_bytes(int N, int L, int H, int width);
+int64_t linattn_cp_saved_bytes(int N, int L, int H, int width);
+bool linattn_cp_streams(int N, int H, int width);       // does a call of this shape take the streaming state kernels?
 void linattn_cp_set_timing_buffer(long long *p);
-int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H,
+int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int width,
                           int64_t ld_qkv, int64_t ld_o, float eps, void *ws, void *saved, cudaStream_t st);
 int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const void *out, const float *den,
-                          const void *gout, void *gq, void *gk, void *gv, int N, int L, int H, int64_t ld_qkv,
+                          const void *gout, void *gq, void *gk, void *gv, int N, int L, int H, int width, int64_t ld_qkv,
                           int64_t ld_o, int64_t ld_g, void *ws, const void *saved, cudaStream_t st);
 
 }  // namespace cpm

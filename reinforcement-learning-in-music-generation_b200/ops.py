@@ -157,8 +157,8 @@ def graph_capture(graph, **kw):
 
 
 # --------------------------------------------------------------------------- linear attention
-def linattn_workspace(N: int, L: int, H: int, device) -> torch.Tensor:
-    nbytes = _lib.load().cpm_linattn_workspace_bytes(N, L, H)
+def linattn_workspace(N: int, L: int, H: int, device, E: int = 64) -> torch.Tensor:
+    nbytes = _lib.load().cpm_linattn_workspace_bytes_wide(N, L, H, E)
     return torch.empty(max(nbytes, 16), dtype=torch.uint8, device=device)
 
 
@@ -172,13 +172,13 @@ def _check_qkv_layout(q, k, v):
     return N, L, H, E, q.stride(1)
 
 
-def linattn_saved(N: int, L: int, H: int, device) -> Optional[torch.Tensor]:
-    """Buffer for the chunk-parallel kernels' per-chunk prefix states (kept from fwd to bwd)."""
-    nbytes = _lib.load().cpm_linattn_saved_bytes(N, L, H)
+def linattn_saved(N: int, L: int, H: int, device, E: int = 64) -> Optional[torch.Tensor]:
+    """Buffer for the chunk-parallel kernels' per-chunk prefix states (kept from fwd to bwd); E = head width (64 | 128)."""
+    nbytes = _lib.load().cpm_linattn_saved_bytes_wide(N, L, H, E)
     return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
 
 
-def _linattn_extra_launches(N, L, H, bwd=False):
+def _linattn_extra_launches(N, L, H, bwd=False, E=64):
     """Kernels of one chunk-parallel call beyond the nominal two (launch accounting of bench.py).  Many (batch, head) chains:
     streaming state kernel + per-chunk kernel.  Few: per-chunk state kernel, scan, per-chunk kernel.  A single chunk has no
     prefix state to build (the backward still runs its pre-pass for the per-token normaliser gradients)."""
@@ -186,18 +186,18 @@ def _linattn_extra_launches(N, L, H, bwd=False):
         return 0                                  # CUDA-core path
     if L == 128:
         return 0 if bwd else -1
-    return 1 if N * H < 96 else 0
+    return 1 if (N * H < 96 or E != 64) else 0      # 128-wide heads: always per-chunk state kernel + scan
 
 
 def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True, saved=None):
-    """q,k,v: (N,L,H,64) views (may be column slices of one fused QKV buffer).  `saved`: optional
-    buffer from linattn_saved() that receives the prefix states for linattn_bwd_raw."""
+    """q,k,v: (N,L,H,E) views (may be column slices of one fused QKV buffer), E = 64, or 128 on the tensor-core path (bf16,
+    L % 128 == 0).  `saved`: optional buffer from linattn_saved() that receives the prefix states for linattn_bwd_raw."""
     _cuda(q, k, v)
     N, L, H, E, ld = _check_qkv_layout(q, k, v)
     out = torch.empty(N, L, H, E, dtype=q.dtype, device=q.device)
     den = torch.empty(N, L, H, dtype=torch.float32, device=q.device) if need_den else None
-    ws = linattn_workspace(N, L, H, q.device)
-    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H)
+    ws = linattn_workspace(N, L, H, q.device, E)
+    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H, E=E)
     with KernelTimer.span("linattn_fwd"):
         check(_lib.load().cpm_linattn_fwd(_p(q), _p(k), _p(v), _p(out), _p(den), N, L, H, E, E, ld, H * E,
                                           _dt(q), eps, impl, _p(ws), ws.numel(), _p(saved),
@@ -209,8 +209,8 @@ def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0, s
     N, L, H, E, ld = _check_qkv_layout(q, k, v)
     _, _, _, _, ldg = _check_qkv_layout(gq, gk, gv)
     gout = gout.contiguous()
-    ws = linattn_workspace(N, L, H, q.device)
-    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H, bwd=True)
+    ws = linattn_workspace(N, L, H, q.device, E)
+    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H, bwd=True, E=E)
     with KernelTimer.span("linattn_bwd"):
         check(_lib.load().cpm_linattn_bwd(_p(q), _p(k), _p(v), _p(out), _p(den), _p(gout), _p(gq), _p(gk), _p(gv),
                                           N, L, H, E, E, ld, H * E, ldg, _dt(q), eps, impl, _p(ws), ws.numel(),
@@ -218,7 +218,7 @@ def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0, s
 
 
 class _LinAttnFused(torch.autograd.Function):
-    """qkv (N,L,3*H*64) fused projection output -> (N,L,H*64).
+    """qkv (N,L,3*H*E) fused projection output -> (N,L,H*E); E = 64, or 128 for bf16 on the tensor-core kernels.
 
     bf16 sequences whose length is not a multiple of the 128-token chunk (e.g. the 50-token DQN windows,
     IRL_dqn_train.py:55-59) are zero-padded at the END to the next multiple and run through the tcgen05 kernels: the op is
@@ -230,7 +230,7 @@ class _LinAttnFused(torch.autograd.Function):
     def forward(ctx, qkv, H, eps, impl, want_den=False):
         N, L, W = qkv.shape
         E = W // (3 * H)
-        pad = (-L) % 128 if (impl == 0 and qkv.dtype == torch.bfloat16 and E == 64 and L > 0) else 0
+        pad = (-L) % 128 if (impl == 0 and qkv.dtype == torch.bfloat16 and E in (64, 128) and L > 0) else 0
         if pad:
             qkv_p = qkv.new_zeros(N, L + pad, W)
             qkv_p[:, :L] = qkv
@@ -240,7 +240,7 @@ class _LinAttnFused(torch.autograd.Function):
         Lp = L + pad
         q, k, v = (qkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
         need = ctx.needs_input_grad[0]
-        saved = linattn_saved(N, Lp, H, qkv.device) if (need and impl in (0, 3) and qkv.dtype == torch.bfloat16) else None
+        saved = linattn_saved(N, Lp, H, qkv.device, E) if (need and impl in (0, 3) and qkv.dtype == torch.bfloat16) else None
         out, den = linattn_fwd_raw(q, k, v, eps, impl, saved=saved)
         ctx.save_for_backward(qkv, out, den, saved)
         ctx.cfg = (H, E, eps, impl, L)
@@ -330,7 +330,8 @@ KEY_MASK_FILL = -30000.0        # elu(x) + 1 = exp(x) underflows to exactly 0 in
 
 
 def causal_linear_attention_fused(qkv, n_heads, eps=EPS_ATTN, impl=0, key_mask=None):
-    """qkv (N,L,3*H*E) -> (N,L,H*E); E = 64 (one kernel pass) or 128 (two passes over 64-wide virtual heads).
+    """qkv (N,L,3*H*E) -> (N,L,H*E); E = 64 or 128.  128-wide heads run natively on the tensor-core kernels in bf16 (templates of
+    the 64-wide kernels over the two halves of a head); fp32 takes two passes over 64-wide virtual heads (_linattn_fused_e128).
     ``key_mask`` (N,L) bool / 0-1: ft's key-padding mask, ``K = K * k_len.float_matrix``.  A padded key must
     feed neither the KV state nor the normaliser; the kernels apply the feature map themselves, so the padded keys are sent in as
     a large negative number, whose feature value (and derivative) is exactly zero - the same outputs and the same (zero) key
@@ -346,8 +347,8 @@ def causal_linear_attention_fused(qkv, n_heads, eps=EPS_ATTN, impl=0, key_mask=N
         is_key[HE:2 * HE] = True
         drop = (~key_mask.to(device=qkv.device).bool())[..., None] & is_key
         qkv = torch.where(drop, torch.full((), KEY_MASK_FILL, dtype=qkv.dtype, device=qkv.device), qkv)
-    if E == 128:
-        return _linattn_fused_e128(qkv, n_heads, eps, impl)
+    if E == 128 and not (qkv.dtype == torch.bfloat16 and qkv.is_cuda and impl in (0, 3) and (impl == 0 or qkv.shape[1] % 128 == 0)):
+        return _linattn_fused_e128(qkv, n_heads, eps, impl)      # fp32 parity mode: two passes over 64-wide virtual heads
     return _LinAttnFused.apply(qkv, n_heads, eps, impl)
 
 

@@ -174,11 +174,48 @@ def test_linattn_cfg5_long_sequence(cuda, cpm):
         assert not bool(g[:, t:].any()) and bool(g[:, :t].any())
 
 
+@pytest.mark.parametrize("shape", [(3, 128, 2), (2, 384, 3), (1, 2048, 8), (100, 256, 1), (2, 200, 2)])
+def test_linattn_native_128_wide_kernels_vs_oracle(cuda, cpm, shape):
+    """The NATIVE 128-wide path (cpm_linattn_fwd / bwd with E = M = 128: the per-chunk kernels instantiated over the two feature
+    halves of q / k and the two value halves of v / out - one K = 128 score tile, a 2 x 2 grid of state tiles per chunk): one
+    chunk (no prefix state), several chunks, a long sequence, many chains (still the per-chunk state kernels: the streaming ones
+    are 64-wide), a ragged length (zero-padded at the end).  Forward and all three gradients against the fp64 oracle at E = 128,
+    with the prefix states kept from the forward and rebuilt by the backward; and against the two-pass 64-wide decomposition."""
+    N, L, H = shape
+    gen = torch.Generator().manual_seed(3 * L + H)
+    qkv = torch.randn(N, L, 3 * H * 128, generator=gen).to(cuda).bfloat16().requires_grad_()
+    go = torch.randn(N, L, H * 128, generator=gen).to(cuda).bfloat16()
+    lib = cpm._lib.load()
+    before = cpm._lib.COUNTS["cpm_linattn_fwd"]
+    out = cpm.ops.causal_linear_attention_fused(qkv, H)
+    assert cpm._lib.COUNTS["cpm_linattn_fwd"] == before + 1, "one kernel pass, not the two-pass decomposition"
+    assert cpm.ops.linattn_last_impl() == "tcgen05-cp" and out.shape == (N, L, H * 128)
+    out.backward(go)
+    q, k, v = (qkv.detach()[..., i * H * 128:(i + 1) * H * 128].unflatten(-1, (H, 128)) for i in range(3))
+    ro, rq, rk, rv = _oracle_attn(q.float(), k.float(), v.float(), go.unflatten(-1, (H, 128)).float())
+    scale = 1.0 + math.sqrt(L / 1024.0)
+    _cmp(out.unflatten(-1, (H, 128)), ro, 3e-2, 2e-2, "out vs oracle")
+    g = qkv.grad
+    for i, (name, ref) in enumerate((("gq", rq), ("gk", rk), ("gv", rv))):
+        _cmp(g[..., i * H * 128:(i + 1) * H * 128].unflatten(-1, (H, 128)), ref, 4e-2 * scale, 3e-2, f"{name} vs oracle")
+    if L % 128 == 0:                                   # raw calls: backward without the kept prefix states rebuilds them
+        o2, den = cpm.ops.linattn_fwd_raw(q, k, v)
+        assert torch.equal(o2.reshape(N, L, H * 128), out.detach())
+        g2 = torch.empty_like(qkv.detach())
+        gq, gk, gv = (g2[..., i * H * 128:(i + 1) * H * 128].unflatten(-1, (H, 128)) for i in range(3))
+        cpm.ops.linattn_bwd_raw(q, k, v, o2, den, go.unflatten(-1, (H, 128)), gq, gk, gv, saved=None)
+        assert torch.equal(g2, g), "gradients with rebuilt prefix states differ from those with the kept ones"
+        assert lib.cpm_linattn_saved_bytes_wide(N, L, H, 128) == N * H * (L // 128) * (4 * 8192 + 512)
+    two = cpm.ops._linattn_fused_e128(qkv.detach(), H, cpm.ops.EPS_ATTN, 0)
+    _cmp(out, two, 3e-2, 2e-2, "native vs two 64-wide passes")
+
+
 @pytest.mark.parametrize("dtype,impl,shape", [(torch.float32, 1, (2, 150, 3)), (torch.float32, 1, (1, 64, 1)),
                                               (torch.bfloat16, 0, (2, 256, 4)), (torch.bfloat16, 0, (1, 1024, 8))])
 def test_linattn_head_width_128_vs_oracle(cuda, cpm, dtype, impl, shape):
-    """128-wide heads (cfg5 as 8 heads x 128): two passes of the 64-wide kernels over virtual heads,
-    recombined with the joint normaliser — forward and all three gradients against the fp64 oracle run at E = M = 128.
+    """128-wide heads (cfg5 as 8 heads x 128) through the ft-style (N,L,H,E) entry point: fp32 = two passes of the
+    64-wide kernels over virtual heads, recombined with the joint normaliser; bf16 = the native 128-wide tensor-core kernels —
+    forward and all three gradients against the fp64 oracle run at E = M = 128.
     Tolerances as for the 64-wide kernels (fp32 1e-4 class; bf16 storage 2e-2 class, on the same bf16-rounded inputs)."""
     N, L, H = shape
     gen = torch.Generator().manual_seed(L + H)

@@ -46,7 +46,18 @@ def test_argument_validation_without_gpu(cpm):
     p = ctypes.addressof(buf)
     p += (-p) % 16
     rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 64, 1, 32, 32, 64, 64, 0, 1e-6, 0, None, 0, None, 0, None)
-    assert rc == -1 and b"E=M=64" in lib.cpm_last_error_string()
+    assert rc == -1 and b"E = M = 64 or 128" in lib.cpm_last_error_string()
+    # 128-wide heads: tensor-core kernels only (bf16, whole 128-token chunks), never the CUDA-core path
+    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 128, 1, 128, 128, 128, 128, 0, 1e-6, 0, None, 0, None, 0, None)
+    assert rc == -7 and b"128-wide heads" in lib.cpm_last_error_string()            # fp32
+    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 100, 1, 128, 128, 128, 128, 1, 1e-6, 0, None, 0, None, 0, None)
+    assert rc == -7 and b"128-wide heads" in lib.cpm_last_error_string()            # bf16, ragged length
+    nhc = 2 * 8 * 4
+    assert lib.cpm_linattn_saved_bytes_wide(2, 512, 8, 128) == nhc * (4 * 8192 + 512)
+    assert lib.cpm_linattn_saved_bytes_wide(2, 512, 8, 64) == lib.cpm_linattn_saved_bytes(2, 512, 8)
+    assert lib.cpm_linattn_workspace_bytes_wide(2, 512, 8, 64) == lib.cpm_linattn_workspace_bytes(2, 512, 8)
+    assert lib.cpm_linattn_workspace_bytes_wide(2, 512, 8, 128) == nhc * (4 * 4096 + 128) * 4 + 2 * nhc * (4 * 8192 + 512) + 2 * 512 * 8 * 4
+    assert lib.cpm_linattn_workspace_bytes_wide(2, 500, 8, 128) == 0 and lib.cpm_linattn_workspace_bytes_wide(2, 512, 8, 96) == 0
     rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 128, 1, 64, 64, 64, 64, 0, 1e-6, 3, p, 1 << 20, None, 0, None)
     assert rc == -7                                                   # tcgen05 path refuses fp32
     rc = lib.cpm_linattn_fwd(p + 2, p, p, p, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 0, p, 1 << 20, None, 0, None)
