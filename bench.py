@@ -245,6 +245,7 @@ class PPOIteration:
         self.init_host = torch.stack([torch.randint(0, n, (self.songs,), generator=g) for n in VOCAB], -1).pin_memory()
         self.init_dev = self.init_host.to(dev)
         self.phase_ms = {"rollout": 0.0, "update": 0.0}
+        self.host_ms = {"generate": 0.0, "critic_enqueue": 0.0, "steps": 0}      # host time inside the enqueue calls
         self.cstream = torch.cuda.Stream(device=dev)
         if OVERLAP_CRITIC:
             cpmusic.ops.KernelTimer.exclude_streams.add(self.cstream.cuda_stream)
@@ -300,9 +301,15 @@ class PPOIteration:
             self.flush()
             ev[0].record()
         torch.cuda.nvtx.range_push("rollout")
+        h0 = time.perf_counter()
         roll = self.engine.generate(init_tokens)                       # tokens (B,T+1,A), logp (B,T,A)
+        h1 = time.perf_counter()
         torch.cuda.nvtx.range_pop()
         self._launch_pending()                                         # last iteration's critic update, under this rollout
+        h2 = time.perf_counter()
+        self.host_ms["generate"] += (h1 - h0) * 1e3
+        self.host_ms["critic_enqueue"] += (h2 - h1) * 1e3
+        self.host_ms["steps"] += 1
         if ev:
             ev[1].record()
         torch.cuda.nvtx.range_push("update")
@@ -604,7 +611,8 @@ def run_gpu(args, rank, world):
             "rollout_layernorm_folded": bool(it.engine.fold), "under_torchrun": "TORCHELASTIC_RUN_ID" in os.environ,
             "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "omp_num_threads": os.environ.get("OMP_NUM_THREADS"),
             "cpu_affinity": len(os.sched_getaffinity(0)), "state_base_mod_2MiB": int(it.engine.S.data_ptr() % (2 << 20)),
-            "allocator_reserved_GB": round(torch.cuda.memory_reserved(dev) / 2**30, 2), "gpu_name": torch.cuda.get_device_name(dev)}
+            "allocator_reserved_GB": round(torch.cuda.memory_reserved(dev) / 2**30, 2), "gpu_name": torch.cuda.get_device_name(dev),
+            "host_ms_per_step": {k: round(v / max(it.host_ms["steps"], 1), 1) for k, v in it.host_ms.items() if k != "steps"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",
             "data": "synthetic",

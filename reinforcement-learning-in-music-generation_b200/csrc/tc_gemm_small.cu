@@ -250,6 +250,7 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
         }
         if ((!SPLIT || cluster_ctarank() == 0) && lane < 16 && row < a.M) {
             __nv_bfloat16 *dst = a.D + (int64_t)row * a.ldd + n0;
+            uint4 ov[4];
 #pragma unroll
             for (int q = 0; q < 4; ++q) {
                 uint32_t w[4];
@@ -279,7 +280,23 @@ gemm_small_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant
                     }
                     w[j] = pack_bf16(x0, x1);
                 }
-                if (n0 + 8 * q + 8 <= a.N) *reinterpret_cast<uint4 *>(dst + 8 * q) = make_uint4(w[0], w[1], w[2], w[3]);
+                ov[q] = make_uint4(w[0], w[1], w[2], w[3]);
+            }
+#ifndef CPM_SMALL_STORE256
+#define CPM_SMALL_STORE256 1
+#endif
+            // the row's 64 bytes as two 256-bit stores (whole sectors) where the tile is complete and the row 32-byte aligned
+            if (CPM_SMALL_STORE256 && n0 + 32 <= a.N && (reinterpret_cast<uintptr_t>(dst) & 31u) == 0) {
+#pragma unroll
+                for (int i = 0; i < 2; ++i)
+                    asm volatile("st.global.v8.b32 [%0], {%1,%2,%3,%4,%5,%6,%7,%8};" ::"l"(dst + 16 * i), "r"(ov[2 * i].x), "r"(ov[2 * i].y),
+                                 "r"(ov[2 * i].z), "r"(ov[2 * i].w), "r"(ov[2 * i + 1].x), "r"(ov[2 * i + 1].y), "r"(ov[2 * i + 1].z),
+                                 "r"(ov[2 * i + 1].w)
+                                 : "memory");
+            } else {
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+                    if (n0 + 8 * q + 8 <= a.N) *reinterpret_cast<uint4 *>(dst + 8 * q) = ov[q];
             }
         }
     }
