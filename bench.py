@@ -42,6 +42,12 @@ MINIBATCH = int(os.environ.get("CPM_MINIBATCH", "128"))
 # The in-situ roofline timing of the attention kernels leaves the overlapped stream out (its launches share the GPU with the
 # rollout); CPM_OVERLAP_CRITIC=0 gives the strictly sequential iteration.
 OVERLAP_CRITIC = os.environ.get("CPM_OVERLAP_CRITIC", "1") == "1"
+# SMs the overlapped critic update may use (a CUDA green context, graphs.sm_partition_stream); 0 = the whole device (default).
+# Measured (profiles/r02_summary.md section O): the rollout takes 450 ms alone and 520-533 ms with the critic update alongside
+# whether that update may use all 148 SMs (and then lasts 190 ms instead of 111) or is confined to 48 (438 ms instead of 279) or 80 -
+# the loss follows the update's WORK, not the SMs it holds, so confining it buys nothing: 684.8 ms per iteration with 0,
+# 773.9 / 697.8 / 684.6 / 678.7 with 32 / 48 / 64 / 80 SMs.  Kept as a knob for A/B runs.
+CRITIC_SMS = int(os.environ.get("CPM_CRITIC_SMS", "0"))
 # DRAM bytes of one linear-attention fwd+bwd launch group measured with ncu (cold L2), keyed by the update minibatch shape
 # -> (bytes, the committed ncu log).  (128, 1024), final kernels of round 2: fwd 234.9+41.3 (streaming prefix) + 463.2+120.0 (per-chunk
 # output) MB, bwd 390.1+53.1 (streaming suffix) + 666.6+361.3 (main) MB.  (64, 1024): round-1 capture (same passes over the data).
@@ -246,7 +252,14 @@ class PPOIteration:
         self.init_dev = self.init_host.to(dev)
         self.phase_ms = {"rollout": 0.0, "update": 0.0}
         self.host_ms = {"generate": 0.0, "critic_enqueue": 0.0, "steps": 0}      # host time inside the enqueue calls
-        self.cstream = torch.cuda.Stream(device=dev)
+        self.cstream, self.critic_sms = None, 0
+        if OVERLAP_CRITIC and CRITIC_SMS > 0:
+            try:
+                self.cstream, self.critic_sms = cpmusic.graphs.sm_partition_stream(CRITIC_SMS, dev)
+            except Exception as e:                      # no green contexts on this driver: an ordinary side stream
+                print(f"bench: SM partition for the critic stream unavailable ({e}); using a plain stream", file=sys.stderr)
+        if self.cstream is None:
+            self.cstream = torch.cuda.Stream(device=dev)
         if OVERLAP_CRITIC:
             cpmusic.ops.KernelTimer.exclude_streams.add(self.cstream.cuda_stream)
         self.pending, self._inflight = None, None
@@ -612,6 +625,7 @@ def run_gpu(args, rank, world):
             "cuda_device_max_connections": os.environ.get("CUDA_DEVICE_MAX_CONNECTIONS"), "omp_num_threads": os.environ.get("OMP_NUM_THREADS"),
             "cpu_affinity": len(os.sched_getaffinity(0)), "state_base_mod_2MiB": int(it.engine.S.data_ptr() % (2 << 20)),
             "allocator_reserved_GB": round(torch.cuda.memory_reserved(dev) / 2**30, 2), "gpu_name": torch.cuda.get_device_name(dev),
+            "critic_sms": it.critic_sms if OVERLAP_CRITIC else None,
             "host_ms_per_step": {k: round(v / max(it.host_ms["steps"], 1), 1) for k, v in it.host_ms.items() if k != "steps"}}
     line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
             "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "bf16",

@@ -73,3 +73,34 @@ class GraphedTrainStep:
         self.graph.replay()
         self.model.invalidate_packs()                 # the masters moved under the host-side version stamps
         return self.losses
+
+
+# --------------------------------------------------------------------------- SM partitions for side streams
+_PARTITIONS = []        # (green context, stream handle) kept alive for the life of the process
+
+
+def sm_partition_stream(n_sms: int, device=None, priority: int = 0):
+    """A torch stream whose kernels run on ``n_sms`` SMs of the device only (a CUDA green context: driver API through
+    cuda-python, CUDA >= 12.4), sharing the primary context's memory.  For bulk work queued UNDERNEATH a latency-bound chain -
+    the critic update under the next rollout in bench.py: persistent GEMM kernels otherwise hold every SM for 150-300 us at a
+    time, and the token step's small dependent kernels, whatever their stream priority, cannot start until one of them ends
+    (measured, tools/probes/overlap_timeline.py: rollout 450 -> 533 ms with the update alongside, update 111 -> 190 ms - the two
+    streams time-slice).  Returns ``(stream, sms_granted)``; raises RuntimeError when green contexts are not available.
+    Kernels sized for the whole device still run correctly on the partition (their grids queue in waves)."""
+    from cuda.bindings import driver as drv
+
+    def ck(r):
+        if r[0] != drv.CUresult.CUDA_SUCCESS:
+            raise RuntimeError(f"green context: driver call failed with {r[0]}")
+        return r[1:] if len(r) > 2 else r[1]
+
+    dev = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
+    torch.zeros(1, device=dev)                                   # the primary context exists
+    cudev = ck(drv.cuDeviceGet(dev.index or 0))
+    res = ck(drv.cuDeviceGetDevResource(cudev, drv.CUdevResourceType.CU_DEV_RESOURCE_TYPE_SM))
+    groups, _, _ = ck(drv.cuDevSmResourceSplitByCount(1, res, 0, int(n_sms)))
+    desc = ck(drv.cuDevResourceGenerateDesc([groups[0]], 1))
+    gctx = ck(drv.cuGreenCtxCreate(desc, cudev, drv.CUgreenCtxCreate_flags.CU_GREEN_CTX_DEFAULT_STREAM))
+    handle = ck(drv.cuGreenCtxStreamCreate(gctx, drv.CUstream_flags.CU_STREAM_NON_BLOCKING, int(priority)))
+    _PARTITIONS.append((gctx, handle))
+    return torch.cuda.ExternalStream(int(handle), device=dev), int(groups[0].sm.smCount)
