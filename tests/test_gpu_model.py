@@ -535,3 +535,41 @@ def test_encoder_length_mask_vs_oracle(cuda, cpm, dtype, atol):
     assert (y_nomask[0] - yg[0]).abs().max() < atol                     # song 0 has no padding
     with pytest.raises(ValueError):
         enc(x.to(cuda), cpm.TriangularCausalMask(L, device=cuda), cpm.LengthMask(lengths.to(cuda), L + 1))
+
+
+def test_sm_partition_stream_runs_the_same_kernels_on_fewer_sms(cuda, cpm):
+    """graphs.sm_partition_stream: a torch stream confined to a subset of the SMs (CUDA green context).  The library's kernels -
+    a persistent 2-CTA GEMM sized for the whole device, the chunk-parallel attention pair, a row kernel - must give bit-identical
+    results there (their grids queue in waves) and the GEMM must take visibly longer on a third of the SMs."""
+    try:
+        side, got = cpm.graphs.sm_partition_stream(48, cuda)
+    except RuntimeError as e:
+        pytest.skip(f"green contexts unavailable: {e}")
+    assert 8 <= got <= 64
+    gen = torch.Generator().manual_seed(5)
+    x = torch.randn(16384, 512, generator=gen).to(cuda).bfloat16()
+    w = (torch.randn(1536, 512, generator=gen) / 16).to(cuda).bfloat16()
+    b = torch.randn(1536, generator=gen).to(cuda)
+
+    def work():
+        qkv = cpm.ops.gemm_nt(x, w, b).view(16, 1024, 1536)
+        att = cpm.ops.causal_linear_attention_fused(qkv, 8)
+        return qkv, att, cpm.ops.colsum(att.view(-1, 512))
+
+    def timed(stream):
+        with torch.cuda.stream(stream):
+            res = work()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(10):
+                cpm.ops.gemm_nt(x, w, b)
+            e1.record()
+        torch.cuda.synchronize()
+        return res, e0.elapsed_time(e1)
+
+    ref, t_full = timed(torch.cuda.current_stream())
+    side.wait_stream(torch.cuda.current_stream())
+    out, t_part = timed(side)
+    for name, a, r in zip(("gemm", "attention", "colsum"), out, ref):
+        assert torch.equal(a, r), f"{name} differs on the SM partition"
+    assert t_part > 1.5 * t_full, f"the partition stream is not confined: {t_part:.3f} ms vs {t_full:.3f} ms on the whole device"
