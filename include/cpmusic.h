@@ -64,7 +64,7 @@ const char *cpm_linattn_last_impl(void);
  * stride `ld_qkv` elements (so the three can be column slices of one fused QKV GEMM output);
  * out / gout are (N,L,H,M) with token stride `ld_o`; gq,gk,gv have token stride `ld_g`.
  * den is (N,L,H) fp32, written by fwd and read by bwd.  E = M = 64 (the reference), or 128 (see below).
- * impl: 0 = auto (chunk-parallel tcgen05 when dtype==BF16 and L%128==0, else simt), 1 = simt,
+ * impl: 0 = auto (chunk-parallel tcgen05 when dtype==BF16, else simt), 1 = simt,
  *       3 = tcgen05, chunk-parallel (one CTA per 128-token chunk; streaming state pre-pass, or per-chunk states + scan
  *           when there are fewer than 96 (batch, head) chains).
  * Workspace: cpm_linattn_workspace_bytes(N,L,H) bytes (segment / chunk states), scratch only.
@@ -75,7 +75,7 @@ const char *cpm_linattn_last_impl(void);
 int64_t cpm_linattn_workspace_bytes(int N, int L, int H);
 int64_t cpm_linattn_saved_bytes(int N, int L, int H);
 /* The same two sizes for head width E (= M) of 64 or 128.  128-wide heads (cfg5 read as 8 heads x 128) run on the
- * chunk-parallel tensor-core kernels only - bf16, L % 128 == 0, impl 0 or 3 - as templates of the 64-wide kernels over the
+ * chunk-parallel tensor-core kernels only - bf16, impl 0 or 3 - as templates of the 64-wide kernels over the
  * two feature halves of q / k and the two value halves of v / out: one score tile per chunk (K = 128), a 2 x 2 grid of 64 x 64
  * state tiles per chunk (saved: 4 bf16 tiles + 128 fp32 key sums per chunk and head).  Anything else returns 0 here and
  * CPM_ERR_UNSUPPORTED from cpm_linattn_fwd / bwd (the host side then runs two 64-wide passes, ops._linattn_fused_e128). */

@@ -214,7 +214,7 @@ int64_t cpm_linattn_workspace_bytes(int N, int L, int H) {
 int64_t cpm_linattn_workspace_bytes_wide(int N, int L, int H, int E) {
     if (E == 64) return cpm_linattn_workspace_bytes(N, L, H);
     if (N <= 0 || L <= 0 || H <= 0 || E != 128) return 0;
-    return linattn_cp_workspace_bytes(N, L, H, 128);    // tensor-core path only: 0 unless L % 128 == 0
+    return linattn_cp_workspace_bytes(N, L, H, 128);    // tensor-core path only
 }
 int64_t cpm_linattn_saved_bytes_wide(int N, int L, int H, int E) {
     if (N <= 0 || L <= 0 || H <= 0 || (E != 64 && E != 128)) return 0;
@@ -235,8 +235,8 @@ static int linattn_check(const void *a, const void *b, const void *c, const void
     CPM_REQUIRE(N > 0 && L > 0 && H > 0, CPM_ERR_BAD_SHAPE, "linattn: N=%d L=%d H=%d must be positive", N, L, H);
     CPM_REQUIRE((E == 64 || E == 128) && M == E, CPM_ERR_BAD_SHAPE, "linattn: head widths E = M = 64 or 128 are supported (got E=%d M=%d)", E, M);
     CPM_REQUIRE(dtype == CPM_F32 || dtype == CPM_BF16, CPM_ERR_BAD_DTYPE, "linattn: dtype %d", dtype);
-    CPM_REQUIRE(E == 64 || (dtype == CPM_BF16 && L % 128 == 0), CPM_ERR_UNSUPPORTED,
-                "linattn: 128-wide heads run on the tensor-core kernels only (bf16, L %% 128 == 0; got dtype %d, L=%d)", dtype, L);
+    CPM_REQUIRE(E == 64 || dtype == CPM_BF16, CPM_ERR_UNSUPPORTED,
+                "linattn: 128-wide heads run on the tensor-core kernels only (bf16; got dtype %d)", dtype);
     CPM_REQUIRE(ld_qkv >= (int64_t)H * E && ld_o >= (int64_t)H * M && ld_qkv % 8 == 0 && ld_o % 8 == 0, CPM_ERR_BAD_SHAPE,
                 "linattn: token strides (%lld,%lld) must be >= H*E and multiples of 8", (long long)ld_qkv, (long long)ld_o);
     CPM_REQUIRE(aligned16(a) && aligned16(b) && aligned16(c) && aligned16(d), CPM_ERR_BAD_ALIGN,
@@ -252,9 +252,9 @@ int cpm_linattn_fwd(const void *q, const void *k, const void *v, void *out, floa
     int rc = linattn_check(q, k, v, out, N, L, H, E, M, ld_qkv, ld_o, dtype, workspace, workspace_bytes);
     if (rc) return rc;
     cudaStream_t st = (cudaStream_t)stream;
-    bool tc_ok = dtype == CPM_BF16 && L % 128 == 0;
+    bool tc_ok = dtype == CPM_BF16;                     // any length: a short last chunk runs with its surplus rows masked out
     CPM_REQUIRE(impl == 0 || impl == 1 || impl == 3, CPM_ERR_BAD_SHAPE, "linattn_fwd: impl %d (0 auto | 1 simt | 3 tcgen05 chunk-parallel)", impl);
-    CPM_REQUIRE(impl != 3 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_fwd: tcgen05 path needs bf16 and L%%128==0");
+    CPM_REQUIRE(impl != 3 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_fwd: the tcgen05 path needs bf16");
     CPM_REQUIRE(E == 64 || impl != 1, CPM_ERR_UNSUPPORTED, "linattn_fwd: the CUDA-core kernels are 64-wide");
     CPM_REQUIRE(!saved || saved_bytes >= cpm_linattn_saved_bytes_wide(N, L, H, E), CPM_ERR_WORKSPACE, "linattn_fwd: saved-state buffer %lld < %lld",
                 (long long)saved_bytes, (long long)cpm_linattn_saved_bytes_wide(N, L, H, E));
@@ -282,9 +282,9 @@ int cpm_linattn_bwd(const void *q, const void *k, const void *v, const void *out
     CPM_REQUIRE(aligned16(gout) && aligned16(gq) && aligned16(gk) && aligned16(gv), CPM_ERR_BAD_ALIGN,
                 "linattn_bwd: gradient buffers must be 16-byte aligned");
     cudaStream_t st = (cudaStream_t)stream;
-    bool tc_ok = dtype == CPM_BF16 && L % 128 == 0;
+    bool tc_ok = dtype == CPM_BF16;
     CPM_REQUIRE(impl == 0 || impl == 1 || impl == 3, CPM_ERR_BAD_SHAPE, "linattn_bwd: impl %d (0 auto | 1 simt | 3 tcgen05 chunk-parallel)", impl);
-    CPM_REQUIRE(impl != 3 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_bwd: tcgen05 path needs bf16 and L%%128==0");
+    CPM_REQUIRE(impl != 3 || tc_ok, CPM_ERR_UNSUPPORTED, "linattn_bwd: the tcgen05 path needs bf16");
     CPM_REQUIRE(E == 64 || impl != 1, CPM_ERR_UNSUPPORTED, "linattn_bwd: the CUDA-core kernels are 64-wide");
     CPM_REQUIRE(!saved || saved_bytes >= cpm_linattn_saved_bytes_wide(N, L, H, E), CPM_ERR_WORKSPACE, "linattn_bwd: saved-state buffer %lld < %lld",
                 (long long)saved_bytes, (long long)cpm_linattn_saved_bytes_wide(N, L, H, E));

@@ -295,6 +295,7 @@ cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
     const int nh = blockIdx.x / nchunks, c = blockIdx.x % nchunks, n = nh / H, h = nh % H;
     const int grow = n * L + c * CHUNK, col0 = h * 64 * D;
     const bool need_state = c > 0;                     // chunk 0's increment is never consumed (suffix scan)
+    const bool live = tid < L - c * CHUNK;             // rows past the end of the sequence (a short last chunk): G' = 0, gd = 0, nothing stored
     if (tid == 0) {
         if (smem_u32(sm) & 1023u) { printf("cpmusic: dynamic shared memory is not 1024-byte aligned\n"); __trap(); }
         mbar_init(bar_load, 1);
@@ -309,7 +310,7 @@ cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
     }
     if ((tid >> 5) == 0) tmem_alloc<C::TCOLS>(tmem_slot);
-    const float inv = 1.f / den[(int64_t)(grow + tid) * H + h];
+    const float inv = live ? 1.f / den[(int64_t)(grow + tid) * H + h] : 0.f;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -334,7 +335,7 @@ cp_state_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_consta
         }
     }
     const float gd = -inv * dot;
-    gd_out[(int64_t)(grow + tid) * H + h] = gd;
+    if (live) gd_out[(int64_t)(grow + tid) * H + h] = gd;
     if (need_state) {                                   // uniform over the CTA
         sgd[tid] = gd;
         fence_proxy_async();
@@ -530,12 +531,14 @@ cp_suffix_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
     const int prow = tid >> 1, phalf = tid & 1;                                 // operand prep: two ADJACENT threads per token row
     const uint32_t t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     const int erow = 16 * (warp & 3) + (lane & 15), shalf = warp >> 2;          // snapshot: M=64 accumulator rows, column halves
-    float den_reg = den[(int64_t)(row0 + chunk_of(0) * CHUNK + prow) * H + h];
+    // rows past the end of the sequence (short last chunk): den reads as +inf, so G' = go / den = 0 and gd = 0; nothing is stored
+    auto den_of = [&](int c) { return c * CHUNK + prow < L ? den[(int64_t)(row0 + c * CHUNK + prow) * H + h] : __int_as_float(0x7f800000); };
+    float den_reg = den_of(chunk_of(0));
     auto prep = [&](int w) {
         const int s = w % SB_STAGES, c = chunk_of(w);
         uint8_t *sQ = sm + s * SB_STAGE_BYTES, *sG = sQ + TILE_BYTES, *sO = sQ + 2 * TILE_BYTES;
         const float inv = 1.f / den_reg;
-        if (w + 1 < nchunks) den_reg = den[(int64_t)(row0 + chunk_of(w + 1) * CHUNK + prow) * H + h];   // in flight during this prep
+        if (w + 1 < nchunks) den_reg = den_of(chunk_of(w + 1));                 // in flight during this prep
         mbar_wait(bar_full + s, (w / SB_STAGES) & 1);
         float dot = 0.f;
 #pragma unroll
@@ -555,7 +558,7 @@ cp_suffix_stream_bwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __gri
         dot += __shfl_xor_sync(0xffffffffu, dot, 1);
         const float gd = -inv * dot;
         if (phalf == 0) {
-            gd_out[(int64_t)(row0 + c * CHUNK + prow) * H + h] = gd;
+            if (c * CHUNK + prow < L) gd_out[(int64_t)(row0 + c * CHUNK + prow) * H + h] = gd;
             if (c > 0) {
                 const __nv_bfloat16 hi = __float2bfloat16_rn(gd), lo = __float2bfloat16_rn(gd - __bfloat162float(hi));
                 uint8_t *gt = sGd + (w & 1) * 2048 + (prow >> 6) * 1024;
@@ -718,6 +721,9 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         const int c = t / NH, nh = t % NH, n = nh / H, h = nh % H;
         const int grow = n * L + c * CHUNK, col0 = h * 64 * D;
         const bool have_state = c > 0;
+        // A sequence's last chunk may be short (L % 128 != 0): its tile then runs past the sequence into the rows of the next one
+        // (or past the tensor: zero fill).  Causality keeps those rows out of every real row's result; they are never WRITTEN.
+        const int valid = min(CHUNK, L - c * CHUNK);
         const int tn = t + gridDim.x;
         float z_next = 0.f;                               // prefetched now, parked in a register until the epilogue
         if (tid < 64 * D && tn < ntiles) z_next = fetch_z(tn);
@@ -778,7 +784,7 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
         }
         const float dn = sdp[g.row] + sdp[128 + g.row] + eps;
         const float inv = 1.f / dn;
-        if (den && g.half == 0) den[(int64_t)(grow + g.row) * H + h] = dn;
+        if (den && g.half == 0 && g.row < valid) den[(int64_t)(grow + g.row) * H + h] = dn;
         mbar_wait(bar_mma, ph_mma);
         ph_mma ^= 1;
         tc_fence_after();
@@ -795,18 +801,18 @@ cp_out_fwd_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constant
             uint4 o[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, inv);
-            if (TMA_OUT) {
+            if (TMA_OUT && valid == CHUNK) {
 #pragma unroll
                 for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sOut + sw128_off(g.row, 4 * g.half + cc)) = o[cc];
                 fence_proxy_async();
-            } else {
+            } else if (g.row < valid) {
                 store_row32(out, ld_o, grow + g.row, col0 + 64 * b + 32 * g.half, o);
             }
         }
         tc_fence_before();
         __syncthreads();                                  // TMEM columns, sz and sdp are reused by the next tile
         tc_fence_after();
-        if (TMA_OUT && tid == 0) { tma_store_2d(&tmO, sOut, col0, grow); tma_store_commit(); }
+        if (TMA_OUT && valid == CHUNK && tid == 0) { tma_store_2d(&tmO, sOut, col0, grow); tma_store_commit(); }
         CPM_STAMP();
     }
 #undef CPM_STAMP
@@ -947,8 +953,9 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         int c, nh, grow, col0, h;
         tile_coords(blockIdx.x, c, nh, grow, col0, h);
         const int64_t ri = (int64_t)(grow + g.row) * a.H + h;
-        inv_n = 1.f / a.den[ri];
-        gd_n = a.gd[ri];
+        const bool live = c * CHUNK + g.row < a.L;          // rows past the end of the sequence: G' = 0, gd = 0, nothing stored
+        inv_n = live ? 1.f / a.den[ri] : 0.f;
+        gd_n = live ? a.gd[ri] : 0.f;
     }
     uint32_t ph_a = 0, ph_b = 0, ph_mma = 0;
     int dbg_i = 0;
@@ -958,6 +965,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         int c, nh, grow, col0, h;
         tile_coords(t, c, nh, grow, col0, h);
         const bool have_s = c > 0, have_r = c + 1 < a.nchunks;
+        const int valid = min(CHUNK, a.L - c * CHUNK);      // < 128 in a short last chunk: those rows are computed with G' = 0 and not stored
         const int64_t slot = (int64_t)nh * a.nchunks + c;
         const int tn = t + gridDim.x;
         const float inv = inv_n, gd = gd_n;
@@ -969,8 +977,9 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             int c2, nh2, grow2, col2, h2;
             tile_coords(tn, c2, nh2, grow2, col2, h2);
             const int64_t ri = (int64_t)(grow2 + g.row) * a.H + h2;
-            inv_n = a.den[ri];
-            gd_n = a.gd[ri];
+            const bool live = c2 * CHUNK + g.row < a.L;
+            inv_n = live ? a.den[ri] : __int_as_float(0x7f800000);      // inverted below: 1 / inf = 0
+            gd_n = live ? a.gd[ri] : 0.f;
         }
         uint32_t qfr[D][16], kfr[D][16];                   // this thread's Qf / Kf values (packed bf16) for phi'
         mbar_wait(bar_b, ph_b);
@@ -1099,11 +1108,11 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             tmem_ld32(g.t_lane + TB_A1 + 64 * i + 32 * g.half, r);
             tmem_ld_wait();
             grad_row_epilogue<true>(r, qfr[i], sz + 64 * i + 32 * g.half, gd, oq);
-            if (!TMA_OUT) store_row32(a.gq, a.ld_g, grow + g.row, col0 + 64 * i + 32 * g.half, oq);
+            if (!(TMA_OUT && valid == CHUNK) && g.row < valid) store_row32(a.gq, a.ld_g, grow + g.row, col0 + 64 * i + 32 * g.half, oq);
             tmem_ld32(g.t_lane + TB_A2 + 64 * i + 32 * g.half, r);
             tmem_ld_wait();
             grad_row_epilogue<true>(r, kfr[i], sgd + 64 * i + 32 * g.half, 1.f, ok);
-            if (!TMA_OUT) store_row32(a.gk, a.ld_g, grow + g.row, col0 + 64 * i + 32 * g.half, ok);
+            if (!(TMA_OUT && valid == CHUNK) && g.row < valid) store_row32(a.gk, a.ld_g, grow + g.row, col0 + 64 * i + 32 * g.half, ok);
         }
         if (tn < ntiles) inv_n = 1.f / inv_n;              // (prefetched den of the next tile)
         CPM_STAMP();                                       // 7: dq, dk rows computed (stored, without the bulk store)
@@ -1112,7 +1121,7 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
         tc_fence_after();
         CPM_STAMP();                                       // 8: round 3 done
         if (tid == 0 && tn < ntiles) issue_a(tn);
-        if (TMA_OUT) {
+        if (TMA_OUT && valid == CHUNK) {
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) {
                 const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
@@ -1129,12 +1138,12 @@ cp_bwd_main_kernel(const __grid_constant__ CUtensorMap tmQ, const __grid_constan
             uint4 o[4];
 #pragma unroll
             for (int cc = 0; cc < 4; ++cc) o[cc] = pack8u(r + 8 * cc, 1.f);
-            store_row32(a.gv, a.ld_g, grow + g.row, col0 + 64 * b + 32 * g.half, o);
+            if (g.row < valid) store_row32(a.gv, a.ld_g, grow + g.row, col0 + 64 * b + 32 * g.half, o);
         }
         tc_fence_before();
         __syncthreads();                                  // TMEM accumulators, sgd, sz are reused by the next tile
         tc_fence_after();
-        if (TMA_OUT && tid == 0) {
+        if (TMA_OUT && valid == CHUNK && tid == 0) {
             tma_store_2d(&tmGq, sX, col0, grow);
             tma_store_2d(&tmGk, sX + TILE_BYTES, col0, grow);
             tma_store_commit();
@@ -1155,14 +1164,14 @@ void linattn_cp_set_timing_buffer(long long *p) { g_cp_timing = p; }
 
 // workspace: [increments fp32 NHC x Wide<D>::STATE_F][Sp region][Rs region][gd fp32 N*L*H];  width = 64 D
 int64_t linattn_cp_workspace_bytes(int N, int L, int H, int width) {
-    if (L % CHUNK != 0 || (width != 64 && width != 128)) return 0;
-    const int64_t nhc = (int64_t)N * H * (L / CHUNK);
+    if (L <= 0 || (width != 64 && width != 128)) return 0;
+    const int64_t nhc = (int64_t)N * H * ((L + CHUNK - 1) / CHUNK);
     if (width == 128) return nhc * Wide<2>::STATE_F * 4 + 2 * state_region_bytes_w<2>(nhc) + (int64_t)N * L * H * 4;
     return nhc * Wide<1>::STATE_F * 4 + 2 * state_region_bytes_w<1>(nhc) + (int64_t)N * L * H * 4;
 }
 int64_t linattn_cp_saved_bytes(int N, int L, int H, int width) {
-    if (L % CHUNK != 0 || (width != 64 && width != 128)) return 0;
-    const int64_t nhc = (int64_t)N * H * (L / CHUNK);
+    if (L <= 0 || (width != 64 && width != 128)) return 0;
+    const int64_t nhc = (int64_t)N * H * ((L + CHUNK - 1) / CHUNK);
     return width == 128 ? state_region_bytes_w<2>(nhc) : state_region_bytes_w<1>(nhc);
 }
 
@@ -1193,7 +1202,7 @@ template <int D> bool use_stream(int N, int H) { return D == 1 && N * H >= 96; }
 // F1 + F2 (or F1s) into a state region (tiles | z)
 template <int D>
 int prefix_states(const void *k, const void *v, int N, int L, int H, int64_t ld_qkv, float *part, uint8_t *region, cudaStream_t st) {
-    const int nchunks = L / CHUNK;
+    const int nchunks = (L + CHUNK - 1) / CHUNK;
     if (nchunks <= 1) return CPM_OK;
     const int64_t nhc = (int64_t)N * H * nchunks;
     CUtensorMap tk, tv;
@@ -1214,7 +1223,7 @@ int prefix_states(const void *k, const void *v, int N, int L, int H, int64_t ld_
 template <int D>
 int fwd_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int64_t ld_qkv, int64_t ld_o,
                float eps, void *ws, void *saved, cudaStream_t st) {
-    const int nchunks = L / CHUNK;
+    const int nchunks = (L + CHUNK - 1) / CHUNK;
     const int64_t nhc = (int64_t)N * H * nchunks;
     if (nhc * 64 * D * D > 0x7fffffffLL) return CPM_ERR_UNSUPPORTED;
     float *part = reinterpret_cast<float *>(ws);
@@ -1239,7 +1248,7 @@ int fwd_launch(const void *q, const void *k, const void *v, void *out, float *de
 template <int D>
 int bwd_launch(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout, void *gq, void *gk,
                void *gv, int N, int L, int H, int64_t ld_qkv, int64_t ld_o, int64_t ld_g, void *ws, const void *saved, cudaStream_t st) {
-    const int nchunks = L / CHUNK;
+    const int nchunks = (L + CHUNK - 1) / CHUNK;
     const int64_t nhc = (int64_t)N * H * nchunks;
     if (nhc * 64 * D * D > 0x7fffffffLL) return CPM_ERR_UNSUPPORTED;
     uint8_t *w8 = reinterpret_cast<uint8_t *>(ws);
@@ -1289,7 +1298,7 @@ bool linattn_cp_streams(int N, int H, int width) { return width == 64 && N * H >
 
 int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out, float *den, int N, int L, int H, int width,
                           int64_t ld_qkv, int64_t ld_o, float eps, void *ws, void *saved, cudaStream_t st) {
-    if (L % CHUNK != 0 || (width != 64 && width != 128)) return CPM_ERR_UNSUPPORTED;
+    if (L <= 0 || (width != 64 && width != 128)) return CPM_ERR_UNSUPPORTED;
     return width == 128 ? fwd_launch<2>(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, ws, saved, st)
                         : fwd_launch<1>(q, k, v, out, den, N, L, H, ld_qkv, ld_o, eps, ws, saved, st);
 }
@@ -1297,7 +1306,7 @@ int linattn_fwd_cp_launch(const void *q, const void *k, const void *v, void *out
 int linattn_bwd_cp_launch(const void *q, const void *k, const void *v, const void *out, const float *den, const void *gout,
                           void *gq, void *gk, void *gv, int N, int L, int H, int width, int64_t ld_qkv, int64_t ld_o, int64_t ld_g,
                           void *ws, const void *saved, cudaStream_t st) {
-    if (L % CHUNK != 0 || (width != 64 && width != 128)) return CPM_ERR_UNSUPPORTED;
+    if (L <= 0 || (width != 64 && width != 128)) return CPM_ERR_UNSUPPORTED;
     return width == 128 ? bwd_launch<2>(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, ws, saved, st)
                         : bwd_launch<1>(q, k, v, out, den, gout, gq, gk, gv, N, L, H, ld_qkv, ld_o, ld_g, ws, saved, st);
 }

@@ -178,26 +178,25 @@ def linattn_saved(N: int, L: int, H: int, device, E: int = 64) -> Optional[torch
     return torch.empty(nbytes, dtype=torch.uint8, device=device) if nbytes > 0 else None
 
 
-def _linattn_extra_launches(N, L, H, bwd=False, E=64):
-    """Kernels of one chunk-parallel call beyond the nominal two (launch accounting of bench.py).  Many (batch, head) chains:
-    streaming state kernel + per-chunk kernel.  Few: per-chunk state kernel, scan, per-chunk kernel.  A single chunk has no
-    prefix state to build (the backward still runs its pre-pass for the per-token normaliser gradients)."""
-    if L % 128 != 0:
-        return 0                                  # CUDA-core path
-    if L == 128:
+def _linattn_extra_launches(N, L, H, bwd=False, E=64, bf16=True):
+    """Kernels of one chunk-parallel call beyond the nominal two (launch accounting of bench.py).  Many (batch, head) chains of
+    64-wide heads: streaming state kernel + per-chunk kernel.  Otherwise: per-chunk state kernel, scan, per-chunk kernel.  A single
+    chunk has no prefix state to build (the backward still runs its pre-pass for the per-token normaliser gradients)."""
+    if not bf16:
+        return 0                                  # CUDA-core path (fp32 parity mode)
+    if L <= 128:
         return 0 if bwd else -1
     return 1 if (N * H < 96 or E != 64) else 0      # 128-wide heads: always per-chunk state kernel + scan
 
 
 def linattn_fwd_raw(q, k, v, eps=EPS_ATTN, impl=0, need_den=True, saved=None):
-    """q,k,v: (N,L,H,E) views (may be column slices of one fused QKV buffer), E = 64, or 128 on the tensor-core path (bf16,
-    L % 128 == 0).  `saved`: optional buffer from linattn_saved() that receives the prefix states for linattn_bwd_raw."""
+    """q,k,v: (N,L,H,E) views (may be column slices of one fused QKV buffer), E = 64, or 128 on the tensor-core path (bf16).  `saved`: optional buffer from linattn_saved() that receives the prefix states for linattn_bwd_raw."""
     _cuda(q, k, v)
     N, L, H, E, ld = _check_qkv_layout(q, k, v)
     out = torch.empty(N, L, H, E, dtype=q.dtype, device=q.device)
     den = torch.empty(N, L, H, dtype=torch.float32, device=q.device) if need_den else None
     ws = linattn_workspace(N, L, H, q.device, E)
-    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H, E=E)
+    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H, E=E, bf16=q.dtype == torch.bfloat16)
     with KernelTimer.span("linattn_fwd"):
         check(_lib.load().cpm_linattn_fwd(_p(q), _p(k), _p(v), _p(out), _p(den), N, L, H, E, E, ld, H * E,
                                           _dt(q), eps, impl, _p(ws), ws.numel(), _p(saved),
@@ -210,7 +209,7 @@ def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0, s
     _, _, _, _, ldg = _check_qkv_layout(gq, gk, gv)
     gout = gout.contiguous()
     ws = linattn_workspace(N, L, H, q.device, E)
-    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H, bwd=True, E=E)
+    _lib.EXTRA_LAUNCHES[0] += _linattn_extra_launches(N, L, H, bwd=True, E=E, bf16=q.dtype == torch.bfloat16)
     with KernelTimer.span("linattn_bwd"):
         check(_lib.load().cpm_linattn_bwd(_p(q), _p(k), _p(v), _p(out), _p(den), _p(gout), _p(gq), _p(gk), _p(gv),
                                           N, L, H, E, E, ld, H * E, ldg, _dt(q), eps, impl, _p(ws), ws.numel(),
@@ -220,35 +219,23 @@ def linattn_bwd_raw(q, k, v, out, den, gout, gq, gk, gv, eps=EPS_ATTN, impl=0, s
 class _LinAttnFused(torch.autograd.Function):
     """qkv (N,L,3*H*E) fused projection output -> (N,L,H*E); E = 64, or 128 for bf16 on the tensor-core kernels.
 
-    bf16 sequences whose length is not a multiple of the 128-token chunk (e.g. the 50-token DQN windows,
-    IRL_dqn_train.py:55-59) are zero-padded at the END to the next multiple and run through the tcgen05 kernels: the op is
-    causal, so padded positions cannot influence real ones (forward), and their upstream gradient is zero (backward).
-    Measured at 1024 x 50 x 8: 0.22 ms forward / 0.50 ms backward on 128 padded tokens against 0.62 / 2.10 ms on the CUDA-core
-    kernels at the true length."""
+    Any length: a sequence's last 128-token chunk may be short (e.g. the 50-token DQN windows, IRL_dqn_train.py:55-59) - the
+    tensor-core kernels mask its surplus rows themselves (no padded copies of the activations or gradients)."""
 
     @staticmethod
     def forward(ctx, qkv, H, eps, impl, want_den=False):
         N, L, W = qkv.shape
         E = W // (3 * H)
-        pad = (-L) % 128 if (impl == 0 and qkv.dtype == torch.bfloat16 and E in (64, 128) and L > 0) else 0
-        if pad:
-            qkv_p = qkv.new_zeros(N, L + pad, W)
-            qkv_p[:, :L] = qkv
-            qkv = qkv_p
-        else:
-            qkv = qkv.contiguous()
-        Lp = L + pad
+        qkv = qkv.contiguous()
         q, k, v = (qkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
         need = ctx.needs_input_grad[0]
-        saved = linattn_saved(N, Lp, H, qkv.device, E) if (need and impl in (0, 3) and qkv.dtype == torch.bfloat16) else None
+        saved = linattn_saved(N, L, H, qkv.device, E) if (need and impl in (0, 3) and qkv.dtype == torch.bfloat16) else None
         out, den = linattn_fwd_raw(q, k, v, eps, impl, saved=saved)
         ctx.save_for_backward(qkv, out, den, saved)
         ctx.cfg = (H, E, eps, impl, L)
-        res = out.view(N, Lp, H * E)
-        if pad:
-            res = res[:, :L].contiguous()
+        res = out.view(N, L, H * E)
         if want_den:                          # the kernel's normaliser as a second, non-differentiable output
-            den_out = den[:, :L].clone()
+            den_out = den.clone()
             ctx.mark_non_differentiable(den_out)
             return res, den_out
         return res
@@ -257,17 +244,12 @@ class _LinAttnFused(torch.autograd.Function):
     def backward(ctx, gout, *_unused):
         qkv, out, den, saved = ctx.saved_tensors
         H, E, eps, impl, L = ctx.cfg
-        N, Lp, W = qkv.shape
+        N = qkv.shape[0]
         q, k, v = (qkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
         gqkv = torch.empty_like(qkv)
         gq, gk, gv = (gqkv[..., i * H * E:(i + 1) * H * E].unflatten(-1, (H, E)) for i in range(3))
-        if Lp != L:
-            g = gout.new_zeros(N, Lp, H, E)
-            g[:, :L] = gout.reshape(N, L, H, E)
-        else:
-            g = gout.reshape(N, L, H, E)
-        linattn_bwd_raw(q, k, v, out, den, g, gq, gk, gv, eps, impl, saved=saved)
-        return (gqkv[:, :L] if Lp != L else gqkv), None, None, None, None
+        linattn_bwd_raw(q, k, v, out, den, gout.reshape(N, L, H, E), gq, gk, gv, eps, impl, saved=saved)
+        return gqkv, None, None, None, None
 
 
 class _LinAttn(torch.autograd.Function):
@@ -347,7 +329,7 @@ def causal_linear_attention_fused(qkv, n_heads, eps=EPS_ATTN, impl=0, key_mask=N
         is_key[HE:2 * HE] = True
         drop = (~key_mask.to(device=qkv.device).bool())[..., None] & is_key
         qkv = torch.where(drop, torch.full((), KEY_MASK_FILL, dtype=qkv.dtype, device=qkv.device), qkv)
-    if E == 128 and not (qkv.dtype == torch.bfloat16 and qkv.is_cuda and impl in (0, 3) and (impl == 0 or qkv.shape[1] % 128 == 0)):
+    if E == 128 and not (qkv.dtype == torch.bfloat16 and qkv.is_cuda and impl in (0, 3)):
         return _linattn_fused_e128(qkv, n_heads, eps, impl)      # fp32 parity mode: two passes over 64-wide virtual heads
     return _LinAttnFused.apply(qkv, n_heads, eps, impl)
 

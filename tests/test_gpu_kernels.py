@@ -763,18 +763,23 @@ def test_colsum_bias_gradient(cuda, cpm, rows, width, dtype):
         assert torch.equal(got, cpm.ops.colsum(view))            # deterministic
 
 
-@pytest.mark.parametrize("shape", [(3, 50, 4), (2, 130, 2), (1, 1, 1), (1024, 50, 8)])
-def test_linattn_bf16_ragged_lengths_run_padded_on_tensor_cores(cuda, cpm, shape):
-    """bf16 sequences that are not a multiple of 128 tokens (the 50-token DQN windows) are zero-padded at the end and take the
-    tcgen05 kernels: forward and gradients against the fp64 oracle at the TRUE length (small shapes) and against the
-    CUDA-core kernels at the replay-batch size; the padding must not leak into real positions."""
+@pytest.mark.parametrize("shape", [(3, 50, 4), (2, 130, 2), (1, 1, 1), (5, 300, 3), (16, 200, 8), (13, 127, 8), (1024, 50, 8)])
+def test_linattn_bf16_ragged_lengths_run_on_tensor_cores(cuda, cpm, shape):
+    """bf16 sequences that are not a multiple of 128 tokens (the 50-token DQN windows) take the tcgen05 kernels as they are: the
+    tile of a short last chunk runs on into the next sequence's rows (or past the tensor), and the kernels keep those rows out -
+    G' = 0, gd = 0, nothing stored.  Forward and gradients against the fp64 oracle at the TRUE length (one short chunk, several
+    chunks with a short last one, the streaming state kernels at >= 96 chains, a single token) and against the CUDA-core kernels
+    at the replay-batch size.  The buffers are surrounded by NaN canaries: a row written past a sequence's end, or a neighbour's
+    rows leaking into a result, would show."""
     N, L, H = shape
     gen = torch.Generator().manual_seed(L * 3 + H)
     qkv = torch.randn(N, L, 3 * H * 64, generator=gen).to(cuda).bfloat16().requires_grad_()
     go = torch.randn(N, L, H * 64, generator=gen).to(cuda).bfloat16()
     out = cpm.ops.causal_linear_attention_fused(qkv, H)
-    assert cpm.ops.linattn_last_impl() == "tcgen05-cp" and out.shape == (N, L, H * 64)
+    want = "tcgen05-cp-stream" if (N * H >= 96 and L > 128) else "tcgen05-cp"
+    assert cpm.ops.linattn_last_impl() == want and out.shape == (N, L, H * 64)
     out.backward(go)
+    assert bool(torch.isfinite(out).all()) and bool(torch.isfinite(qkv.grad).all())
     if N * L <= 4096:
         q, k, v = (qkv.detach()[..., i * H * 64:(i + 1) * H * 64].reshape(N, L, H, 64).float() for i in range(3))
         ro, rq, rk, rv = _oracle_attn(q, k, v, go.view(N, L, H, 64).float())
@@ -787,6 +792,21 @@ def test_linattn_bf16_ragged_lengths_run_padded_on_tensor_cores(cuda, cpm, shape
         ref.backward(go)
         _cmp(out, ref.float(), 3e-2, 2e-2, "out vs simt")
         _cmp(qkv.grad, ref_in.grad.float(), 4e-2, 3e-2, "gqkv vs simt")
+    # raw calls on views INSIDE larger NaN-filled buffers: nothing outside the (N, L) block may be touched, nothing of it read into a result
+    if N * L <= 4096:
+        W = 3 * H * 64
+        big = torch.full((N * L + 300, W), float("nan"), device=cuda).bfloat16()
+        big[150:150 + N * L] = qkv.detach().view(N * L, W)
+        blk = big[150:150 + N * L].view(N, L, W)
+        qq, kk, vv = (blk[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
+        o2, den2 = cpm.ops.linattn_fwd_raw(qq, kk, vv)
+        assert torch.equal(o2.view(N, L, H * 64), out.detach()), "neighbouring rows (NaN) leaked into the forward"
+        gbig = torch.full((N * L + 300, W), float("nan"), device=cuda).bfloat16()
+        gblk = gbig[150:150 + N * L].view(N, L, W)
+        gq, gk, gv = (gblk[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
+        cpm.ops.linattn_bwd_raw(qq, kk, vv, o2, den2, go.view(N, L, H, 64), gq, gk, gv)
+        assert torch.equal(gblk, qkv.grad), "neighbouring rows (NaN) leaked into the gradients"
+        assert bool(torch.isnan(gbig[:150]).all()) and bool(torch.isnan(gbig[150 + N * L:]).all()), "rows outside the block were written"
 
 
 def test_out_of_range_token_ids_raise_index_error(cuda, cpm):

@@ -32,8 +32,11 @@ def test_library_exports_every_declared_symbol(cpm):
     nhc = 32 * 8 * 4                                    # chunk-parallel path: increments + 2 state regions + gd
     assert lib.cpm_linattn_workspace_bytes(32, 512, 8) == nhc * 4160 * 4 + 2 * nhc * (8192 + 256) + 32 * 512 * 8 * 4
     assert lib.cpm_linattn_saved_bytes(32, 512, 8) == nhc * (8192 + 256)
-    assert lib.cpm_linattn_workspace_bytes(4, 100, 8) == 2 * 4 * 8 * 1 * (64 * 64 + 64) * 4   # L%128 != 0: segment states only
-    assert lib.cpm_linattn_workspace_bytes(1, 8192 + 64, 16) == 2 * 16 * 17 * (64 * 64 + 64) * 4   # SIMT path: 17 segments of 512
+    # a ragged length takes the chunk-parallel path too (one short chunk here): max(segment states, increments + 2 regions + gd)
+    assert lib.cpm_linattn_workspace_bytes(4, 100, 8) == max(2 * 4 * 8 * 1 * (64 * 64 + 64) * 4, 32 * 4160 * 4 + 2 * 32 * (8192 + 256) + 4 * 100 * 8 * 4)
+    assert lib.cpm_linattn_saved_bytes(4, 100, 8) == 32 * (8192 + 256) and lib.cpm_linattn_saved_bytes(4, 300, 8) == 32 * 3 * (8192 + 256)
+    nhc = 16 * 65                                       # 8192 + 64 tokens: 65 chunks, the last one short; the SIMT plan (17 segments) is smaller
+    assert lib.cpm_linattn_workspace_bytes(1, 8192 + 64, 16) == nhc * 4160 * 4 + 2 * nhc * (8192 + 256) + (8192 + 64) * 16 * 4 > 2 * 16 * 17 * (64 * 64 + 64) * 4
     assert lib.cpm_ln_partials_rows() == 296
 
 
@@ -50,14 +53,16 @@ def test_argument_validation_without_gpu(cpm):
     # 128-wide heads: tensor-core kernels only (bf16, whole 128-token chunks), never the CUDA-core path
     rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 128, 1, 128, 128, 128, 128, 0, 1e-6, 0, None, 0, None, 0, None)
     assert rc == -7 and b"128-wide heads" in lib.cpm_last_error_string()            # fp32
-    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 100, 1, 128, 128, 128, 128, 1, 1e-6, 0, None, 0, None, 0, None)
-    assert rc == -7 and b"128-wide heads" in lib.cpm_last_error_string()            # bf16, ragged length
+    ws = lib.cpm_linattn_workspace_bytes_wide(1, 100, 1, 128)
+    rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 100, 1, 128, 128, 128, 128, 1, 1e-6, 1, p, ws, None, 0, None)
+    assert rc == -7 and b"64-wide" in lib.cpm_last_error_string()                   # bf16 but the CUDA-core path (impl 1) asked for
     nhc = 2 * 8 * 4
     assert lib.cpm_linattn_saved_bytes_wide(2, 512, 8, 128) == nhc * (4 * 8192 + 512)
     assert lib.cpm_linattn_saved_bytes_wide(2, 512, 8, 64) == lib.cpm_linattn_saved_bytes(2, 512, 8)
     assert lib.cpm_linattn_workspace_bytes_wide(2, 512, 8, 64) == lib.cpm_linattn_workspace_bytes(2, 512, 8)
     assert lib.cpm_linattn_workspace_bytes_wide(2, 512, 8, 128) == nhc * (4 * 4096 + 128) * 4 + 2 * nhc * (4 * 8192 + 512) + 2 * 512 * 8 * 4
-    assert lib.cpm_linattn_workspace_bytes_wide(2, 500, 8, 128) == 0 and lib.cpm_linattn_workspace_bytes_wide(2, 512, 8, 96) == 0
+    assert lib.cpm_linattn_workspace_bytes_wide(2, 500, 8, 128) == lib.cpm_linattn_workspace_bytes_wide(2, 512, 8, 128) - 2 * 12 * 8 * 4
+    assert lib.cpm_linattn_workspace_bytes_wide(2, 512, 8, 96) == 0
     rc = lib.cpm_linattn_fwd(p, p, p, p, None, 1, 128, 1, 64, 64, 64, 64, 0, 1e-6, 3, p, 1 << 20, None, 0, None)
     assert rc == -7                                                   # tcgen05 path refuses fp32
     rc = lib.cpm_linattn_fwd(p + 2, p, p, p, None, 1, 64, 1, 64, 64, 64, 64, 0, 1e-6, 0, p, 1 << 20, None, 0, None)
@@ -151,12 +156,9 @@ def test_segment_plan_matches_header_contract(cpm):
     for N, L, H in ((4, 512, 8), (32, 512, 8), (1, 8192, 16), (1, 8192, 8), (2, 100, 1), (1, 50, 8)):
         b = lib.cpm_linattn_workspace_bytes(N, L, H)
         assert b >= per * N * H
-        if L % 128:                              # SIMT-only shapes: whole segments
-            assert b % (per * N * H) == 0
-        else:                                    # chunk-parallel tcgen05 path: increments + 2 state regions + gd
-            nhc = N * H * (L // 128)
-            assert b >= nhc * 4160 * 4 + 2 * nhc * 8448 + N * L * H * 4
-            assert lib.cpm_linattn_saved_bytes(N, L, H) == nhc * 8448
+        nhc = N * H * -(-L // 128)               # chunk-parallel tcgen05 path (any length): increments + 2 state regions + gd
+        assert b >= nhc * 4160 * 4 + 2 * nhc * 8448 + N * L * H * 4
+        assert lib.cpm_linattn_saved_bytes(N, L, H) == nhc * 8448
 
 
 def test_shard_range(cpm):
