@@ -167,6 +167,15 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
  * of a Linear layer from its output gradient (what autograd's `grad_output.sum(0)` computes for nn.Linear,
  * agent_pretrain.py:239 / every ft projection).  partials: caller-owned fp32 scratch of cpm_colsum_partials_rows(width) * width
  * floats.  width must be a multiple of 16 (bf16) / 8 (fp32), ld of 8.  out (width) fp32 is OVERWRITTEN.  Deterministic. */
+/* Refresh of the bf16 compute packings of a model's fp32 master parameters (encoder.PackCache: the row-concatenated weights every
+ * Linear of agent_pretrain.py:239-253 / dqn_policy/model.py:156-161 runs on) in ONE launch.  items_device: device array of n_items
+ * records of cpm_pack_item_bytes() bytes each, in this order (natural alignment, 8-byte pointers first):
+ *   const float *w (rows x cols master, contiguous), const float *b (rows, or NULL),
+ *   bf16 *wc (row-major destination, already offset to the master's first row), bf16 *wt (transposed destination offset to the
+ *   master's first COLUMN, row stride ld_t; or NULL), bf16 *bc (or NULL), float *b32 (or NULL), int rows, cols, ld_t, tile0
+ * with tile0 = number of 32 x 32 tiles of all earlier items; n_tiles = their total.  Round-to-nearest-even, as torch's copy_. */
+int cpm_pack_item_bytes(void);
+int cpm_pack_weights(const void *items_device, int n_items, int n_tiles, void *stream);
 int cpm_colsum_partials_rows(int width);
 int cpm_colsum(const void *x, int64_t rows, int width, int64_t ld, float *out, float *partials, int dtype, void *stream);
 

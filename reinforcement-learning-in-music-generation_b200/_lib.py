@@ -45,6 +45,8 @@ SIGNATURES = {
                                 c_int64, c_int64, c_int64, c_int, c_float, c_int, _P, c_int64, _P, c_int64, _P]),
     "cpm_linattn_step": (c_int, [_P, _P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int64, c_int64,
                                  c_int, c_float, _P]),
+    "cpm_pack_item_bytes": (c_int, []),
+    "cpm_pack_weights": (c_int, [_P, c_int, c_int, _P]),
     "cpm_colsum_partials_rows": (c_int, [c_int]),
     "cpm_colsum": (c_int, [_P, c_int64, c_int, c_int64, _P, _P, c_int, _P]),
     "cpm_reward_head": (c_int, [_P, _P, _P, _P, _P, c_int, c_int, c_int, c_int, c_int, _P]),
@@ -126,7 +128,7 @@ import collections
 COUNTS = collections.Counter()
 KERNELS_PER_CALL = collections.defaultdict(lambda: 1, {
     "cpm_version": 0, "cpm_last_error_string": 0, "cpm_error_name": 0, "cpm_linattn_last_impl": 0,
-    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_linattn_workspace_bytes_wide": 0, "cpm_linattn_saved_bytes_wide": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_rowdot_partials_rows": 0, "cpm_gemm_set_mode": 0, "cpm_set_chain_pdl": 0,
+    "cpm_linattn_workspace_bytes": 0, "cpm_linattn_saved_bytes": 0, "cpm_linattn_workspace_bytes_wide": 0, "cpm_linattn_saved_bytes_wide": 0, "cpm_set_rng_base": 0, "cpm_gelu_bwd_partials_rows": 0, "cpm_debug_linattn_timing": 0, "cpm_ln_partials_rows": 0, "cpm_colsum_partials_rows": 0, "cpm_pack_item_bytes": 0, "cpm_rowdot_partials_rows": 0, "cpm_gemm_set_mode": 0, "cpm_set_chain_pdl": 0,
     "cpm_rollout_plan_bytes": 0, "cpm_debug_rollout_timing": 0, "cpm_debug_small_timing": 0, "cpm_gemm_small_set_split": 0, "cpm_rollout_create": 0, "cpm_rollout_phases": 0, "cpm_rollout_destroy": 0,
 
     "cpm_linattn_fwd": 2, "cpm_linattn_bwd": 2, "cpm_ln_residual_bwd": 2, "cpm_colsum": 2, "cpm_rowdot_bwd": 2,      # chunk-parallel path: streaming state kernel + per-chunk

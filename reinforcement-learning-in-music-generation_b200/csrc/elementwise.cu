@@ -560,6 +560,55 @@ __global__ void __launch_bounds__(256) gelu_kernel(const T *__restrict__ x, cons
     }
 }
 
+// ---------------------------------------------------------------- packed compute copies of the fp32 masters, ONE launch
+// A model's Linear layers keep bf16 packings of their fp32 master weights (row-concatenated q / k / v, heads, ...): W (N x K) for
+// the forward GEMM, its transpose (K x N) for the data-gradient GEMM, the bias in bf16 and fp32.  After an optimizer step all of
+// them are stale at once; refreshing them Linear by Linear took five to eight tiny copy kernels each (~240 launches per model).
+// Here every 32 x 32 tile of every master is one thread block of a single launch: coalesced fp32 read, bf16 row-major write,
+// transposed write through shared memory; the blocks of a tile column 0 also copy the bias rows.
+struct PackItem {
+    const float *w, *b;          // master weight (rows x cols, contiguous) and bias (rows) or NULL
+    __nv_bfloat16 *wc, *wt, *bc; // destinations: wc + r0 * cols (row-major), wt + r0 (K x ld_t, transposed), bc + r0; wt / bc may be NULL
+    float *b32;                  // fp32 bias destination (+ r0) or NULL
+    int rows, cols, ld_t, tile0; // ld_t: row stride of wt (the packing's padded row count); tile0: first block of this item
+};
+__global__ void __launch_bounds__(256) pack_weights_kernel(const PackItem *__restrict__ items, int n_items) {
+    __shared__ float tile[32][33];
+    __shared__ int s_item;
+    if (threadIdx.x == 0 && threadIdx.y == 0) {
+        int lo = 0, hi = n_items - 1;                          // last item whose tile0 <= blockIdx.x
+        while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (items[mid].tile0 <= (int)blockIdx.x) lo = mid; else hi = mid - 1; }
+        s_item = lo;
+    }
+    __syncthreads();
+    const PackItem it = items[s_item];
+    const int tcols = (it.cols + 31) >> 5, t = blockIdx.x - it.tile0, tr = t / tcols, tc = t % tcols;
+    const int r0 = tr * 32, c0 = tc * 32, tx = threadIdx.x, ty = threadIdx.y;      // block (32, 8)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+        const int r = r0 + ty + 8 * j, c = c0 + tx;
+        float v = 0.f;
+        if (r < it.rows && c < it.cols) {
+            v = it.w[(int64_t)r * it.cols + c];
+            it.wc[(int64_t)r * it.cols + c] = __float2bfloat16_rn(v);
+        }
+        tile[ty + 8 * j][tx] = v;
+    }
+    __syncthreads();
+    if (it.wt) {
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int c = c0 + ty + 8 * j, r = r0 + tx;             // wt[c][r] = w[r][c]
+            if (r < it.rows && c < it.cols) it.wt[(int64_t)c * it.ld_t + r] = __float2bfloat16_rn(tile[tx][ty + 8 * j]);
+        }
+    }
+    if (tc == 0 && ty == 0 && it.b && r0 + tx < it.rows) {
+        const float bv = it.b[r0 + tx];
+        if (it.bc) it.bc[r0 + tx] = __float2bfloat16_rn(bv);
+        if (it.b32) it.b32[r0 + tx] = bv;
+    }
+}
+
 inline int grid_for(int64_t work_items, int threads) {
     int64_t b = (work_items + threads - 1) / threads;
     int64_t cap = (int64_t)num_sms() * 16;
@@ -736,6 +785,14 @@ int cpm_ln_residual_bwd(const void *gy, const void *s, const float *mean, const 
     const int width = (dres_bias ? 3 : 2) * d;
     reduce_partials_kernel<true><<<(width + 31) / 32, 256, 0, (cudaStream_t)stream>>>(partials, ln_bwd_blocks(d), 3 * d, d, dgamma, dbeta, dres_bias);
     return check_launch("ln_residual_bwd");
+}
+
+int cpm_pack_item_bytes(void) { return (int)sizeof(PackItem); }
+
+int cpm_pack_weights(const void *items_device, int n_items, int n_tiles, void *stream) {
+    CPM_REQUIRE(items_device && n_items > 0 && n_tiles > 0, CPM_ERR_NULL, "pack_weights: empty item table");
+    pack_weights_kernel<<<n_tiles, dim3(32, 8), 0, (cudaStream_t)stream>>>(reinterpret_cast<const PackItem *>(items_device), n_items);
+    return check_launch("pack_weights");
 }
 
 int cpm_colsum_partials_rows(int width) { return width > 0 ? 256 : 0; }      // upper bound of the row slabs for any dtype

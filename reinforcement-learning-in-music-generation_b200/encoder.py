@@ -104,6 +104,7 @@ class PackCache:
 
     def __init__(self):
         self._store = {}
+        self._table, self._table_key = None, None          # ops.PackTable over every bf16 packing of this cache (one-launch refresh)
 
     @staticmethod
     def _stamp(params, dtype):
@@ -121,6 +122,46 @@ class PackCache:
         if wt is not None:
             wt.copy_(wc.t())
 
+    # ---- one-launch refresh: after an optimizer step every packing of a model is stale at once
+    def _batched_entries(self):
+        out = []
+        for key, (stamp, packed) in self._store.items():
+            wc, bc, rows, masters, wt, b32 = packed
+            n = len(rows)
+            if wc.dtype != torch.bfloat16 or not wc.is_cuda or wt is None or b32 is None:
+                return None
+            r0 = 0
+            for w, b in zip(masters[:n], masters[n:]):
+                if w.dtype != torch.float32 or not w.is_contiguous() or b is None or b.dtype != torch.float32 or not b.is_contiguous():
+                    return None
+                out.append((w, b, wc, wt, bc, b32, r0))
+                r0 += w.shape[0]
+        return out
+
+    def _refresh_batched(self) -> bool:
+        """Refreshes EVERY packing of this cache from its masters with one kernel launch (cpm_pack_weights) and re-stamps them.
+        False when the cache holds something the kernel does not cover (fp32 parity packings, CPU tensors) or the item table
+        would have to be rebuilt during a CUDA-graph capture."""
+        if not self._store:
+            return False
+        key = tuple((k, p[1][0].data_ptr(), p[1][4].data_ptr() if p[1][4] is not None else 0, tuple(m.data_ptr() for m in p[1][3]))
+                    for k, p in self._store.items())
+        if key != self._table_key:
+            if torch.cuda.is_available() and torch.cuda.is_current_stream_capturing():
+                return False
+            entries = self._batched_entries()
+            if entries is None:
+                self._table, self._table_key = None, key
+                return False
+            self._table, self._table_key = ops.PackTable(entries, entries[0][2].device), key
+        if self._table is None:
+            return False
+        with torch.no_grad():
+            self._table.launch()
+        for k, (stamp, packed) in list(self._store.items()):
+            self._store[k] = (self._stamp(packed[3], stamp[-1]), packed)
+        return True
+
     def get(self, key, linears, dtype, pad_rows_to: int = 1):
         ws = [l.weight for l in linears]
         bs = [l.bias for l in linears]
@@ -128,6 +169,9 @@ class PackCache:
         hit = self._store.get(key)
         if hit is not None and hit[0] == stamp:
             return hit[1]
+        if (hit is not None and dtype == torch.bfloat16 and hit[1][0].dtype == dtype and len(hit[1][3]) == len(ws + bs)
+                and all(m is p for m, p in zip(hit[1][3], ws + bs)) and self._refresh_batched()):
+            return self._store[key][1]
         with torch.no_grad():
             rows = [int(w.shape[0]) for w in ws]
             padded = -(-sum(rows) // pad_rows_to) * pad_rows_to
@@ -153,6 +197,8 @@ class PackCache:
 
     def refresh_all(self):
         """Re-sync every existing packing with its masters (in place)."""
+        if any(self._stamp(packed[3], stamp[-1]) != stamp for stamp, packed in self._store.values()) and self._refresh_batched():
+            return
         with torch.no_grad():
             for key, (stamp, packed) in list(self._store.items()):
                 wc, bc, rows, masters, wt, b32 = packed
@@ -171,6 +217,7 @@ class PackCache:
 
     def clear(self):
         self._store.clear()
+        self._table, self._table_key = None, None
 
 
 def cached_linear(cache: PackCache, key, linears, x, dtype, pad_rows_to=1, use_bias=True):

@@ -615,6 +615,31 @@ class _PackedLinear(torch.autograd.Function):
         return (gx, None, None, None, *grads)
 
 
+class PackTable:
+    """Device-side item table of cpm_pack_weights for a fixed set of (master, packing) buffers; built once, launched per refresh."""
+
+    def __init__(self, entries, device):
+        """entries: (w, b, wc, wt, bc, b32, r0) per master - fp32 contiguous w (rows, cols) and b (rows) or None; bf16 wc (padded, cols),
+        wt (cols, padded) or None, bc (padded,) or None; fp32 b32 (padded,) or None; r0 = the master's first row in the packing."""
+        import struct
+        lib = _lib.load()
+        if lib.cpm_pack_item_bytes() != 64:
+            raise RuntimeError("cpm_pack_weights: unexpected item layout")
+        blob, tile0 = b"", 0
+        for (w, bias, wc, wt, bc, b32, r0) in entries:
+            rows, cols = w.shape
+            ptr = lambda t, off=0: 0 if t is None else t.data_ptr() + off * t.element_size()
+            blob += struct.pack("<6Q4i", ptr(w), ptr(bias), ptr(wc, r0 * cols), ptr(wt, r0), ptr(bc, r0), ptr(b32, r0), rows, cols,
+                                0 if wt is None else wt.shape[1], tile0)
+            tile0 += -(-rows // 32) * -(-cols // 32)
+        self.n_items, self.n_tiles = len(entries), tile0
+        self.table = torch.frombuffer(bytearray(blob), dtype=torch.uint8).to(device)
+        self.keep = entries                                   # the buffers the table points at
+
+    def launch(self):
+        check(_lib.load().cpm_pack_weights(_p(self.table), self.n_items, self.n_tiles, _st()))
+
+
 def colsum(x):
     """fp32 column sums of a 2-D bf16 / fp32 CUDA matrix (row stride free, unit column stride): cpm_colsum."""
     _cuda(x)

@@ -573,3 +573,42 @@ def test_sm_partition_stream_runs_the_same_kernels_on_fewer_sms(cuda, cpm):
     for name, a, r in zip(("gemm", "attention", "colsum"), out, ref):
         assert torch.equal(a, r), f"{name} differs on the SM partition"
     assert t_part > 1.5 * t_full, f"the partition stream is not confined: {t_part:.3f} ms vs {t_full:.3f} ms on the whole device"
+
+
+def test_pack_cache_one_launch_refresh_equals_per_layer_copies(cuda, cpm, golden):
+    """encoder.PackCache refreshes every bf16 packing of a model with ONE cpm_pack_weights launch after an optimizer step (row-major
+    copy, transposed copy, bf16 and fp32 bias per master; the zero rows that pad the 339 head rows to 344 stay zero).  Bit-identical
+    to the per-layer torch copies, for the encoder layers, the input projection and the concatenated heads; and a training step
+    after the refresh sees the new weights."""
+    torch.manual_seed(3)
+    VOCAB = [56, 135, 18, 87, 18, 25]
+    m = cpm.TransformerModel(VOCAB, d_model=256, n_layer=2, n_head=4, d_inner=512, dropout=0.0).to(cuda).train()
+    gen = torch.Generator().manual_seed(1)
+    x = torch.stack([torch.randint(0, n, (2, 128), generator=gen) for n in VOCAB], -1).to(cuda)
+    mask = torch.ones(2, 128, device=cuda)
+    opt = torch.optim.Adam(m.parameters(), lr=1e-2, fused=True)
+    caches = [c for c in (getattr(mod, "_cache", None) for mod in m.modules()) if isinstance(c, cpm.encoder.PackCache)]
+    assert caches
+    l0 = sum(m.train_step(x, x.roll(-1, 1), mask))
+    l0.backward()
+    opt.step()                                             # every packing is stale now
+    lib_calls = cpm._lib.COUNTS["cpm_pack_weights"]
+    l1 = sum(m.train_step(x, x.roll(-1, 1), mask))         # first get() of each cache refreshes all of its packings at once
+    assert cpm._lib.COUNTS["cpm_pack_weights"] - lib_calls == len([c for c in caches if c._table is not None]) >= 1
+    assert float(l1.detach()) < float(l0.detach())
+    n_checked = 0
+    for c in caches:
+        for key, (stamp, (wc, bc, rows, masters, wt, b32)) in c._store.items():
+            n = len(rows)
+            ref_w = torch.zeros_like(wc)
+            ref_b = torch.zeros_like(b32)
+            r0 = 0
+            for w, b in zip(masters[:n], masters[n:]):
+                ref_w[r0:r0 + w.shape[0]] = w.detach().to(torch.bfloat16)
+                ref_b[r0:r0 + w.shape[0]] = b.detach()
+                r0 += w.shape[0]
+            assert torch.equal(wc, ref_w), f"{key}: row-major packing"
+            assert torch.equal(wt, ref_w.t()), f"{key}: transposed packing"
+            assert torch.equal(b32, ref_b) and torch.equal(bc, ref_b.to(torch.bfloat16)), f"{key}: bias"
+            n_checked += 1
+    assert n_checked >= 2 * 4 + 2
