@@ -832,3 +832,34 @@ def test_out_of_range_token_ids_raise_index_error(cuda, cpm):
             cpm.ops.IndexGuard.poll(cuda)
             torch.cuda.synchronize()
     cpm.ops.IndexGuard.check(cuda)
+
+
+def test_row_stores_fall_back_when_rows_are_not_32_byte_aligned(cuda, cpm):
+    """The per-chunk attention kernels and the token-step GEMM write a lane's 64 bytes of a row as two 256-bit stores where the
+    address allows it and as four 128-bit stores otherwise (row strides that are multiples of 8 but not of 16 elements; tiles cut
+    off at N).  Both paths must give the same values: gradients into a buffer of odd row stride equal those into the dense one,
+    a ragged length (plain stores instead of the bulk tensor stores) included; same for the small GEMM into a strided output."""
+    gen = torch.Generator().manual_seed(9)
+    for (N, L, H) in ((3, 256, 2), (2, 200, 2)):
+        W = 3 * H * 64
+        qkv = torch.randn(N, L, W, generator=gen).to(cuda).bfloat16()
+        go = torch.randn(N, L, H, 64, generator=gen).to(cuda).bfloat16()
+        q, k, v = (qkv[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
+        out, den = cpm.ops.linattn_fwd_raw(q, k, v)
+        res = []
+        for width in (W, W + 8):                       # W + 8: rows of 3088 / 784 bytes - every other row starts 16 bytes off a 32-byte line
+            gbuf = torch.zeros(N, L, width, device=cuda, dtype=torch.bfloat16)
+            gq, gk, gv = (gbuf[..., i * H * 64:(i + 1) * H * 64].unflatten(-1, (H, 64)) for i in range(3))
+            cpm.ops.linattn_bwd_raw(q, k, v, out, den, go, gq, gk, gv)
+            assert not bool(gbuf[..., W:].any())
+            res.append(gbuf[..., :W].clone())
+        assert torch.equal(res[0], res[1])
+    a = torch.randn(200, 512, generator=gen).to(cuda).bfloat16()
+    w = (torch.randn(344, 512, generator=gen) / 16).to(cuda).bfloat16()
+    b = torch.randn(344, generator=gen).to(cuda)
+    dense = cpm.ops.gemm_nt_small(a, w, b)
+    wide = torch.zeros(200, 344 + 8, device=cuda, dtype=torch.bfloat16)
+    cpm.ops.gemm_nt_small(a, w, b, out=wide[:, :344])
+    assert torch.equal(wide[:, :344], dense) and not bool(wide[:, 344:].any())
+    ref = (a.float() @ w.float().t() + b)
+    assert (dense.float() - ref).abs().max() < 0.06
