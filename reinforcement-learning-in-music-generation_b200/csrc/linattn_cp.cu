@@ -1,9 +1,8 @@
 // Chunk-parallel causal linear attention on tcgen05 / TMA (sm_100a), bf16 I/O, fp32 accumulation.
 //
-// The sequential-chunk kernels (linattn_tc.cu) give one CTA a whole (batch, head) row of chunks, so a
-// 16 x 1024 x 8 call exposes only 128 independent chains to 148 SMs.  Here every 128-token chunk of
-// every (batch, head) is its own CTA; the inter-chunk dependency (the KV state) is broken out into a
-// tensor-core pre-pass plus a prefix scan:
+// One CTA per whole (batch, head) chain of chunks would expose only 128 independent chains of a 16 x 1024 x 8 call to
+// 148 SMs (the round-1 design, since removed).  Here every 128-token chunk of every (batch, head) is its own tile of a
+// persistent kernel; the inter-chunk dependency (the KV state) is broken out into a tensor-core pre-pass plus a prefix scan:
 //
 //   forward   F1  cp_state_fwd    per chunk c < C-1 : dS_c = Kf_c^T V_c (M64 N64 K128 UMMA), dz_c = colsum Kf_c   -> fp32 partials
 //             F2  cp_scan         per (n,h)         : exclusive prefix over c  -> Sp_c (bf16 tile), zp_c (fp32)   [saved for backward]
@@ -15,9 +14,14 @@
 //             B3  cp_bwd_main     per chunk         : dq, dk, dv of the chunk from (q,k,v,go) + Sp_c + Rs_c, all within the CTA
 //
 // HBM traffic per (chunk, head): forward reads q,k,v (48 KB) and writes out (16 KB) + den; k,v are read a
-// second time by F1 (L2 hits when the call fits the 126 MB L2) and the state costs 16.6 KB fp32 + 8.4 KB bf16
-// through L2.  Shared-memory tiles are SWIZZLE_128B as TMA writes them; the intra-chunk score tile goes
-// TMEM -> registers (mask, bf16) -> shared memory -> second UMMA, exactly as in linattn_tc.cu.
+// second time by the state kernel and the prefix tile costs 8.4 KB each way; backward reads q,k,v,go (64 KB), both state tiles,
+// writes dq,dk,dv (48 KB), and its state kernel reads q, go, out once more.  Measured at 128 x 1024 x 8: 2.33 GB of DRAM traffic
+// for 1.476 GB algorithmic, every kernel at 0.70-0.80 of the copy bandwidth on its own bytes (profiles/r02_summary.md, K).
+// Shared-memory tiles are SWIZZLE_128B as TMA writes them; the intra-chunk score tile goes TMEM -> registers (mask, bf16) ->
+// shared memory -> second UMMA.  Output rows leave as whole lines: out / dq / dk through a dead score-tile block and one bulk
+// tensor store per tile, dv and the state snapshots as 256-bit stores (128-bit stores at a 3 KB row stride were the longest
+// phase of a tile).  Any sequence length: a short last chunk's tile runs on into the next sequence's rows (or TMA zero fill) and
+// those rows are masked out (causality forward; G' = 0, gd = 0 backward) and never written.  Head width 64 or 128 (template D).
 #include "cpm_common.cuh"
 #include "linattn_plan.h"
 #include "tc_common.cuh"
@@ -100,8 +104,6 @@ __device__ __forceinline__ uint4 phi8_dot(uint4 r, const float *z, float &dot) {
 __device__ __forceinline__ uint32_t scale2(uint32_t u, float s) {
     return pack_bf16(__uint_as_float(u << 16) * s, __uint_as_float(u & 0xffff0000u) * s);
 }
-// phi'(x) from the bf16 feature value f = phi(x): f <= 1  <=>  x <= 0, where phi' = exp(x) = f; else 1
-__device__ __forceinline__ float dphi_from_f(float f) { return fminf(f, 1.f); }
 
 // TMEM [128 x 128] score tile -> (+row_add) (+col_add[c]) -> triangular mask -> bf16 -> sX block `half`.
 // LOWER keeps column c <= row, otherwise c >= row.  No row sums here (they come from a ones-column UMMA).

@@ -1,7 +1,6 @@
 // Chunked causal linear attention, CUDA-core implementation (fp32 math, fp32 or bf16 I/O).
 //
-// This is the fp32-exact parity path and the fallback for shapes the tcgen05 kernels
-// (linattn_tc.cu) do not take.  One CTA owns one (batch, head, segment) and walks its
+// This is the fp32-exact parity path (the tcgen05 kernels of linattn_cp.cu take every bf16 call).  One CTA owns one (batch, head, segment) and walks its
 // 64-token chunks sequentially, carrying the E×M KV state and the E-vector key sum in
 // shared memory; long sequences with few (batch, head) pairs are split into segments whose
 // initial states come from a segment-total pass + a prefix scan (workspace).

@@ -1,6 +1,5 @@
-// Device helpers shared by the tcgen05 linear-attention kernels (linattn_tc.cu: sequential-chunk
-// kernels; linattn_cp.cu: chunk-parallel kernels): feature map on packed bf16, per-thread tile geometry,
-// TMEM score tile -> masked bf16 shared-memory tile, swizzled-tile column sums.
+// Device helpers of the chunk-parallel tcgen05 linear-attention kernels (linattn_cp.cu): tile constants, feature map on
+// packed bf16, bf16 pack / unpack, per-thread tile geometry.
 #pragma once
 #include "cpm_common.cuh"
 #include "tc_common.cuh"
@@ -56,99 +55,6 @@ struct Geo {
         t_lane = tmem + ((uint32_t)((warp & 3) * 32) << 16);
     }
 };
-
-// 64x64 fp32 state in TMEM (M=64 layout) -> bf16 smem tile rows e, this thread's 32 columns
-__device__ __forceinline__ void state_half_to_smem(const Geo &g, uint32_t tm_col, uint8_t *sS) {
-    uint32_t r[32];
-    tmem_ld32(g.t_lane + tm_col + 32 * g.half, r);
-    tmem_ld_wait();
-    if (g.lane < 16) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sS + sw128_off(g.erow, g.half * 4 + cc)) = pack8u(r + 8 * cc, 1.f);
-    }
-}
-// initial state (fp32, row-major [e][m]) -> TMEM + bf16 smem tile
-__device__ __forceinline__ void seed_state_half(const Geo &g, const float *init, uint32_t tm_col, uint8_t *sS) {
-    uint32_t r[32];
-#pragma unroll
-    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(init[g.erow * 64 + g.half * 32 + i]);
-    tmem_st32(g.t_lane + tm_col + 32 * g.half, r);
-    if (g.lane < 16) {
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) *reinterpret_cast<uint4 *>(sS + sw128_off(g.erow, g.half * 4 + cc)) = pack8u(r + 8 * cc, 1.f);
-    }
-    tmem_st_wait();
-}
-
-// TMEM [128 x 128] score tile -> (+row_add, +col_add[c]) -> triangular mask -> bf16 -> sX block `half`.
-// LOWER keeps column c <= row (forward / dq);  otherwise keeps c >= row (dk/dv).  Returns the row sum of
-// the bf16-rounded kept entries over this thread's 64 columns.
-template <bool LOWER>
-__device__ __forceinline__ float convert_scores(const Geo &g, uint32_t tm_col, uint8_t *sX, float row_add, const float *col_add) {
-    float rowsum = 0.f;
-    const int wq = g.warp & 3;
-#pragma unroll
-    for (int pp = 0; pp < 2; ++pp) {
-        const int p = 2 * g.half + pp;                      // 32-column piece
-        uint32_t r[32];
-        const bool live = LOWER ? (p <= wq) : (p >= wq);
-        const bool diag = p == wq;
-        if (live) {
-            tmem_ld32(g.t_lane + tm_col + 32 * p, r);
-            tmem_ld_wait();
-        }
-#pragma unroll
-        for (int cc = 0; cc < 4; ++cc) {
-            uint32_t w[4];
-#pragma unroll
-            for (int i = 0; i < 4; ++i) {
-                const int c0 = 32 * p + 8 * cc + 2 * i;
-                float a = 0.f, b = 0.f;
-                if (live) {
-                    a = __uint_as_float(r[8 * cc + 2 * i]) + row_add + (col_add ? col_add[c0] : 0.f);
-                    b = __uint_as_float(r[8 * cc + 2 * i + 1]) + row_add + (col_add ? col_add[c0 + 1] : 0.f);
-                    if (diag) {
-                        if (LOWER) { a = c0 <= g.row ? a : 0.f; b = c0 + 1 <= g.row ? b : 0.f; }
-                        else { a = c0 >= g.row ? a : 0.f; b = c0 + 1 >= g.row ? b : 0.f; }
-                    }
-                }
-                const __nv_bfloat162 hb = __floats2bfloat162_rn(a, b);
-                const float2 fb = __bfloat1622float2(hb);
-                rowsum += fb.x + fb.y;
-                w[i] = *reinterpret_cast<const uint32_t *>(&hb);
-            }
-            *reinterpret_cast<uint4 *>(sX + g.half * TILE_BYTES + sw128_off(g.row, pp * 4 + cc)) = make_uint4(w[0], w[1], w[2], w[3]);
-        }
-    }
-    return rowsum;
-}
-
-// partial column sums over 32 rows (quarter) of a swizzled [128 x 64] bf16 tile, optionally row-weighted
-__device__ __forceinline__ float colsum_quarter(const uint8_t *tile, int e, int quarter, const float *w) {
-    float s = 0.f;
-#pragma unroll 8
-    for (int j = 32 * quarter; j < 32 * quarter + 32; ++j) {
-        const __nv_bfloat16 x = *reinterpret_cast<const __nv_bfloat16 *>(tile + sw128_off(j, e >> 3) + (e & 7) * 2);
-        s = fmaf(__bfloat162float(x), w ? w[j] : 1.f, s);
-    }
-    return s;
-}
-
-// G' = go/den in place over this thread's 4 chunks; returns the partial dot go.out
-__device__ __forceinline__ float prep_grad_half(const Geo &g, uint8_t *sG, const uint8_t *sOt, float inv) {
-    float dot = 0.f;
-#pragma unroll
-    for (int cc = 0; cc < 4; ++cc) {
-        const uint32_t off = sw128_off(g.row, 4 * g.half + cc);
-        float gg[8], o[8];
-        unpack8(*reinterpret_cast<const uint4 *>(sG + off), gg);
-        unpack8(*reinterpret_cast<const uint4 *>(sOt + off), o);
-#pragma unroll
-        for (int i = 0; i < 8; ++i) { dot = fmaf(gg[i], o[i], dot); gg[i] *= inv; }
-        *reinterpret_cast<uint4 *>(sG + off) = pack8(gg);
-    }
-    return dot;
-}
 
 }  // namespace tcdev
 }  // namespace cpm
