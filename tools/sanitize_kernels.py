@@ -16,6 +16,12 @@ if "attn" in which:
         out.backward(go.detach())
         torch.cuda.synchronize()
         print("attn", (N, L, H), ops.linattn_last_impl(), float(out.float().abs().mean()), flush=True)
+    for (N, L, H, E) in ((3, 50, 4, 64), (13, 200, 8, 64), (2, 256, 2, 128), (2, 200, 2, 128)):    # ragged lengths; 128-wide heads
+        q, k, v, go = (torch.randn(N, L, H, E, device=dev).bfloat16().requires_grad_() for _ in range(4))
+        out = ops.causal_linear_attention(q, k, v)
+        out.backward(go.detach())
+        torch.cuda.synchronize()
+        print("attn", (N, L, H, E), ops.linattn_last_impl(), float(out.float().abs().mean()), flush=True)
 if "step" in which:
     S, Z = torch.zeros(5, 4, 64, 64, device=dev), torch.zeros(5, 4, 64, device=dev)
     qkv = torch.randn(5, 3 * 256, device=dev).bfloat16()
