@@ -184,7 +184,10 @@ inline float dropout_scale8(float p) { uint32_t t = dropout_threshold8(p); retur
 // the programmatic-stream-serialization attribute: it may become resident while its predecessor still runs, executes its
 // set-up, and blocks in griddep_wait() until the predecessor has completed and flushed.  RULE for every chain kernel: call
 // griddep_wait() before the first access to anything another kernel of the chain produces OR still reads (buffers are recycled
-// by the allocator, so writes are ordered too); only constant data (weights, tables) may be touched before it.
+// by the allocator, so writes are ordered too); only constant data (weights, tables) may be touched before it.  Keep the call
+// UNCONDITIONAL and ahead of those accesses in program order: placed inside a branch (a grid-stride variant of the state kernel
+// tried `if (first tile) griddep_wait();`), nvcc hoisted the read-only `const __restrict__` loads of q / k / v over it and the
+// kernel consumed its predecessor's output too early (profiles/r02_summary.md, section S).
 __device__ __forceinline__ void griddep_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
 __device__ __forceinline__ void griddep_launch() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 extern int g_chain_pdl;
